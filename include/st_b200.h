@@ -1,0 +1,207 @@
+/* st_b200.h — C ABI of libst_b200.so, the sm_100a (B200) implementation of the Speech-Transformer
+ * hot path.  This is the drop-in boundary: plain pointers, sizes and a cudaStream_t; no torch or
+ * C++ types.  Every pointer is a DEVICE pointer unless stated otherwise; every tensor is fp32,
+ * row-major and contiguous unless a leading dimension / stride argument says otherwise.  Calls
+ * enqueue work on `stream` and return immediately.
+ *
+ * Return value: 0 on success, negative on error (ST_ERR_*); st_last_error() describes the failure.
+ *
+ * The reference is pure PyTorch (no FFI of its own); each entry point below replaces the eager
+ * ATen call sequence at the cited reference lines (paths relative to the reference repo root).
+ */
+#ifndef ST_B200_H_
+#define ST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define ST_OK 0
+#define ST_ERR_INVALID (-1)
+#define ST_ERR_CUDA (-2)
+#define ST_ERR_DEVICE (-3)
+#define ST_ERR_WORKSPACE (-4)
+
+/* ---- library ------------------------------------------------------------------------------- */
+int st_version(void);                       /* 10000*major + 100*minor + patch */
+const char* st_last_error(void);            /* host string, valid until the next failing call */
+int st_device_check(int device);            /* ST_OK iff `device` is compute capability 10.x */
+int st_set_option(const char* name, int v); /* debug/tuning switches, see st_host.cu */
+int st_selftest_count(void);
+int st_selftest(int which, double* rel_err_out /* host */); /* tcgen05 building-block self tests */
+
+/* ---- (C) residual + LayerNorm ---------------------------------------------------------------
+ * out = dropout(LayerNorm(a + b) * gamma + beta)           Attention.py:62,94  SubLayers.py:18,27
+ * b, z_out, mean_out, rstd_out may be NULL.  z_out receives a + b (needed by the backward).
+ * dropout_p == 0 disables dropout; round_tf32 != 0 rounds `out` to TF32 (it feeds a tensor-core op).
+ */
+int st_add_ln_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* out, float* z_out,
+                  float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_tf32, float dropout_p,
+                  uint64_t seed, cudaStream_t stream);
+/* dz = d(loss)/d(a+b); dgamma/dbeta/dzsum (each [d], may be NULL) are ACCUMULATED into (caller zeroes).
+ * dzsum = column sums of dz = bias gradient of the linear layer that produced the LN input. */
+int st_add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                  float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, int round_tf32,
+                  float dropout_p, uint64_t seed, cudaStream_t stream);
+
+/* ---- (D) label-smoothed / soft-target cross entropy -------------------------------------------
+ * LabelSmoothingLoss.forward (Loss.py:28-39): q_i = one_hot with q_i[target_i] = confidence, rows with
+ * target_i == padding_idx zeroed when padding_idx >= 0; then CrossEntropyLoss.forward (Loss.py:50-73):
+ * loss = sum_i sum_c weight_c q_ic (-log_softmax(logits_i)_c), divided by N when size_average.
+ * grad (may be NULL) receives d(loss)/d(logits).  row_loss is an N-float workspace.            */
+int st_lsce_fwd_bwd(const float* logits, int64_t ld_logits, const int64_t* target, const float* one_hot,
+                    const float* weight, float confidence, int64_t padding_idx, int size_average, int64_t N, int V,
+                    float* row_loss, float* loss, float* grad, int64_t ld_grad, cudaStream_t stream);
+/* CrossEntropyLoss.forward with a dense soft target q (N, V)                       Loss.py:50-73 */
+int st_softce_fwd_bwd(const float* logits, int64_t ld_logits, const float* q, const float* weight, int size_average,
+                      int64_t N, int V, float* row_loss, float* loss, float* grad, int64_t ld_grad,
+                      cudaStream_t stream);
+
+/* ---- TF32 tensor-core linear algebra ------------------------------------------------------------
+ * dst = round_to_tf32(src), 2-D strided copy (cols, lds, ldd multiples of 4).                   */
+int st_round_tf32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, cudaStream_t stream);
+/* out[c] += sum_r x[r, c]                                                                        */
+int st_colsum_add(const float* x, int64_t ld, int64_t rows, int cols, float* out, cudaStream_t stream);
+
+/* General TF32 GEMM on tcgen05 (operands must already be TF32-representable for exact TF32 semantics):
+ *   mode 0 (NT): C[M,N] = A[M,K] * B[N,K]^T     nn.Linear forward      Attention.py:74-76,92 SubLayers.py:25-26
+ *   mode 1 (NN): C[M,N] = A[M,K] * B[K,N]       its input gradient
+ *   mode 2 (TN): C[M,N] = A[K,M]^T * B[K,N]     its weight gradient (k_splits > 1: C must be zeroed, atomics)
+ * epilogue: (+bias[N]) -> (relu) -> (dropout) -> aux_mode 1: += aux[M,ldaux] | 2: zero where aux <= 0
+ *           -> (round to TF32).                                                                   */
+typedef struct {
+  const float* bias;
+  const float* aux;
+  int64_t ldaux;
+  int aux_mode;
+  int relu;
+  int round_tf32;
+  int k_splits;
+  float dropout_p;
+  uint64_t seed;
+} st_gemm_epilogue;
+int st_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+            int K, const st_gemm_epilogue* ep /* host, may be NULL */, cudaStream_t stream);
+
+/* ---- (A) attention core: softmax(mask(Q K^T / sqrt(d_k))) V for all heads ------------------------
+ * Attention.py:78-90 (split heads, scores, masked_fill_(-inf), softmax, dropout, P·V, merge heads)
+ * and Attention.py:27-35 (ScaledDotProductAttention = the H == 1 case).
+ * q: (B*Lq, >= H*dk) with leading dimension ldq; head h occupies columns [h*dk, (h+1)*dk).  Same for
+ * k, v (B*Lk rows), ctx (B*Lq rows, merged heads).  Operands must be TF32-representable.
+ * mask: NULL or bytes, nonzero = masked, element (b,i,j) at mask[b*ms_b + i*ms_q + j*ms_k] (stride 0
+ * broadcasts, as in the expanded view built by Utils.py:53-54).  A fully masked row yields NaN, like
+ * the reference.  lse: (B,H,Lq) log-sum-exp of the scaled masked scores (saved for backward).
+ * attn: NULL, or (B,H,Lq,Lk) to receive the post-dropout probabilities the module returns.        */
+typedef struct {
+  int B, H, Lq, Lk, dk;
+  const float* q; int64_t ldq;
+  const float* k; int64_t ldk;
+  const float* v; int64_t ldv;
+  const uint8_t* mask; int64_t ms_b, ms_q, ms_k;
+  float dropout_p; uint64_t seed;
+  float* ctx; int64_t ldctx;
+  float* lse;
+  float* attn;
+} st_attn_args;
+int st_attn_fwd(const st_attn_args* a /* host */, cudaStream_t stream);
+
+typedef struct {
+  st_attn_args f;       /* the forward problem: q,k,v,mask,dropout,ctx,lse exactly as given to / produced by st_attn_fwd */
+  const float* dctx; int64_t lddctx;   /* gradient w.r.t. ctx (TF32-representable) */
+  float* delta;                        /* (B,H,Lq) workspace */
+  float* dq; int64_t lddq;             /* gradients, same indexing as q/k/v; rounded to TF32 */
+  float* dk; int64_t lddk;
+  float* dv; int64_t lddv;
+} st_attn_bwd_args;
+int st_attn_bwd(const st_attn_bwd_args* a /* host */, cudaStream_t stream);
+
+/* ---- composite: MultiHeadAttention.forward / backward -------------------------------------------
+ * Attention.py:64-96:  LN(Linear_o(attention(Linear_q(q), Linear_k(k), Linear_v(v), mask)) + residual)
+ * `residual` is v in the reference (Attention.py:94); the caller passes the tensor to add.
+ * q_in/k_in/v_in: (B*Lq, d), (B*Lk, d), (B*Lk, d).  Weights are [out, in] like nn.Linear.
+ * `saved` is a caller-allocated float buffer of st_mha_saved_floats() elements that forward fills and
+ * backward reads; `ws` is scratch of st_mha_ws_floats() elements (contents undefined afterwards).  */
+typedef struct {
+  int B, Lq, Lk, H, d_model, dk;
+  const float* q_in; const float* k_in; const float* v_in;
+  const float* residual;
+  const float* wq; const float* bq; const float* wk; const float* bk;
+  const float* wv; const float* bv; const float* wo; const float* bo;
+  const float* ln_g; const float* ln_b;
+  const uint8_t* mask; int64_t ms_b, ms_q, ms_k;
+  float eps; float dropout_p; uint64_t seed;
+  int inputs_tf32;      /* q_in/k_in/v_in are already TF32-representable: skip the rounding copies */
+  int round_out;        /* round the module output to TF32 (it feeds the next layer's GEMM) */
+  float* out;           /* (B*Lq, d) */
+  float* attn;          /* NULL or (B,H,Lq,Lk) */
+  float* saved; int64_t saved_floats;
+  float* ws; int64_t ws_floats;
+} st_mha_args;
+int64_t st_mha_saved_floats(int B, int Lq, int Lk, int H, int d_model, int same_qkv, int same_kv, int inputs_tf32);
+int64_t st_mha_ws_floats(int B, int Lq, int Lk, int H, int d_model);
+int st_mha_fwd(const st_mha_args* a /* host */, cudaStream_t stream);
+
+typedef struct {
+  st_mha_args f;        /* same problem description as forward (out/attn unused) */
+  const float* dout;    /* (B*Lq, d) */
+  float* dq_in; float* dk_in; float* dv_in;   /* (rows, d); when inputs alias (self-attention) pass the same
+                                                 pointer and the sum is written once */
+  float* dresidual;     /* (B*Lq, d) gradient of the residual input; may alias one of the above only if
+                           that tensor is the residual (then the sum is formed) */
+  float* dwq; float* dbq; float* dwk; float* dbk; float* dwv; float* dbv; float* dwo; float* dbo;
+  float* dln_g; float* dln_b;                 /* all parameter gradients are OVERWRITTEN */
+} st_mha_bwd_args;
+int st_mha_bwd(const st_mha_bwd_args* a /* host */, cudaStream_t stream);
+
+/* ---- composite: PositionwiseFeedForward.forward / backward ---------------------------------------
+ * SubLayers.py:24-28:  dropout2(LN(x + fc2(dropout1(relu(fc1(x))))))                               */
+typedef struct {
+  int64_t rows; int d_model, d_ff;
+  const float* x;
+  const float* w1; const float* b1; const float* w2; const float* b2;
+  const float* ln_g; const float* ln_b;
+  float eps; float dropout_p; uint64_t seed;
+  int x_is_tf32;        /* x is already TF32-representable (produced by this library with round_out) */
+  int round_out;
+  float* out;
+  float* saved; int64_t saved_floats;
+  float* ws; int64_t ws_floats;
+} st_ffn_args;
+int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32);
+int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff);
+int st_ffn_fwd(const st_ffn_args* a /* host */, cudaStream_t stream);
+
+typedef struct {
+  st_ffn_args f;
+  const float* dout;
+  float* dx;
+  float* dw1; float* db1; float* dw2; float* db2; float* dln_g; float* dln_b;   /* OVERWRITTEN */
+} st_ffn_bwd_args;
+int st_ffn_bwd(const st_ffn_bwd_args* a /* host */, cudaStream_t stream);
+
+/* ---- flat-buffer optimizer step (train.py:45-46, Optim.py:9-14,36-45) --------------------------------
+ * st_sumsq: *out += sum(x[i]^2) (caller zeroes `out`, a device float).
+ * st_adam_step: g' = grad * grad_scale * min(1, max_grad_norm / (sqrt(*norm_ws) * grad_scale + 1e-6))
+ * (clip_grad_norm_ semantics; skipped when norm_ws is NULL or max_grad_norm <= 0), then torch.optim.Adam's
+ * update with bias correction for `step` (1-based).  n must be a multiple of 4.                       */
+int st_sumsq(const float* x, int64_t n, float* out, cudaStream_t stream);
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  int64_t n;
+  float lr, beta1, beta2, eps;
+  int step;
+  float max_grad_norm, grad_scale;
+  const float* norm_ws;
+} st_adam_args;
+int st_adam_step(const st_adam_args* a /* host */, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ST_B200_H_ */

@@ -1,0 +1,140 @@
+"""ctypes binding of libst_b200.so (include/st_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or the current device is not sm_100,
+every operator raises.  The structures below mirror the C structs field for field.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libst_b200.so")
+
+c_float_p = C.c_void_p  # raw device pointers travel as integers
+i64 = C.c_int64
+u64 = C.c_uint64
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("aux", C.c_void_p), ("ldaux", i64), ("aux_mode", C.c_int),
+                ("relu", C.c_int), ("round_tf32", C.c_int), ("k_splits", C.c_int),
+                ("dropout_p", C.c_float), ("seed", u64)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("dk", C.c_int),
+                ("q", C.c_void_p), ("ldq", i64), ("k", C.c_void_p), ("ldk", i64), ("v", C.c_void_p), ("ldv", i64),
+                ("mask", C.c_void_p), ("ms_b", i64), ("ms_q", i64), ("ms_k", i64),
+                ("dropout_p", C.c_float), ("seed", u64),
+                ("ctx", C.c_void_p), ("ldctx", i64), ("lse", C.c_void_p), ("attn", C.c_void_p)]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [("f", AttnArgs), ("dctx", C.c_void_p), ("lddctx", i64), ("delta", C.c_void_p),
+                ("dq", C.c_void_p), ("lddq", i64), ("dk", C.c_void_p), ("lddk", i64), ("dv", C.c_void_p), ("lddv", i64)]
+
+
+class MhaArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("H", C.c_int), ("d_model", C.c_int), ("dk", C.c_int),
+                ("q_in", C.c_void_p), ("k_in", C.c_void_p), ("v_in", C.c_void_p), ("residual", C.c_void_p),
+                ("wq", C.c_void_p), ("bq", C.c_void_p), ("wk", C.c_void_p), ("bk", C.c_void_p),
+                ("wv", C.c_void_p), ("bv", C.c_void_p), ("wo", C.c_void_p), ("bo", C.c_void_p),
+                ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
+                ("mask", C.c_void_p), ("ms_b", i64), ("ms_q", i64), ("ms_k", i64),
+                ("eps", C.c_float), ("dropout_p", C.c_float), ("seed", u64),
+                ("inputs_tf32", C.c_int), ("round_out", C.c_int),
+                ("out", C.c_void_p), ("attn", C.c_void_p),
+                ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64)]
+
+
+class MhaBwdArgs(C.Structure):
+    _fields_ = [("f", MhaArgs), ("dout", C.c_void_p),
+                ("dq_in", C.c_void_p), ("dk_in", C.c_void_p), ("dv_in", C.c_void_p), ("dresidual", C.c_void_p),
+                ("dwq", C.c_void_p), ("dbq", C.c_void_p), ("dwk", C.c_void_p), ("dbk", C.c_void_p),
+                ("dwv", C.c_void_p), ("dbv", C.c_void_p), ("dwo", C.c_void_p), ("dbo", C.c_void_p),
+                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p)]
+
+
+class FfnArgs(C.Structure):
+    _fields_ = [("rows", i64), ("d_model", C.c_int), ("d_ff", C.c_int),
+                ("x", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
+                ("eps", C.c_float), ("dropout_p", C.c_float), ("seed", u64),
+                ("x_is_tf32", C.c_int), ("round_out", C.c_int),
+                ("out", C.c_void_p), ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64)]
+
+
+class FfnBwdArgs(C.Structure):
+    _fields_ = [("f", FfnArgs), ("dout", C.c_void_p), ("dx", C.c_void_p),
+                ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
+                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", i64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("step", C.c_int), ("max_grad_norm", C.c_float), ("grad_scale", C.c_float),
+                ("norm_ws", C.c_void_p)]
+
+
+# every symbol include/st_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_S = C.c_void_p  # cudaStream_t
+SIGNATURES = {
+    "st_version": (C.c_int, []),
+    "st_last_error": (C.c_char_p, []),
+    "st_device_check": (C.c_int, [C.c_int]),
+    "st_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "st_selftest_count": (C.c_int, []),
+    "st_selftest": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "st_add_ln_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, i64, C.c_int, C.c_float, C.c_int, C.c_float, u64, _S]),
+    "st_add_ln_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, i64, C.c_int, C.c_int, C.c_float, u64, _S]),
+    "st_lsce_fwd_bwd": (C.c_int, [_P, i64, _P, _P, _P, C.c_float, i64, C.c_int, i64, C.c_int, _P, _P, _P, i64, _S]),
+    "st_softce_fwd_bwd": (C.c_int, [_P, i64, _P, _P, C.c_int, i64, C.c_int, _P, _P, _P, i64, _S]),
+    "st_round_tf32": (C.c_int, [_P, i64, _P, i64, i64, C.c_int, _S]),
+    "st_colsum_add": (C.c_int, [_P, i64, i64, C.c_int, _P, _S]),
+    "st_gemm": (C.c_int, [C.c_int, _P, i64, _P, i64, _P, i64, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), _S]),
+    "st_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _S]),
+    "st_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), _S]),
+    "st_mha_saved_floats": (i64, [C.c_int] * 8),
+    "st_mha_ws_floats": (i64, [C.c_int] * 5),
+    "st_mha_fwd": (C.c_int, [C.POINTER(MhaArgs), _S]),
+    "st_mha_bwd": (C.c_int, [C.POINTER(MhaBwdArgs), _S]),
+    "st_ffn_saved_floats": (i64, [i64, C.c_int, C.c_int, C.c_int]),
+    "st_ffn_ws_floats": (i64, [i64, C.c_int, C.c_int]),
+    "st_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), _S]),
+    "st_ffn_bwd": (C.c_int, [C.POINTER(FfnBwdArgs), _S]),
+    "st_sumsq": (C.c_int, [_P, i64, _P, _S]),
+    "st_adam_step": (C.c_int, [C.POINTER(AdamArgs), _S]),
+}
+
+_lib = None
+
+
+class StError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libst_b200.so and bind every declared symbol. Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StError(
+            f"{LIB_PATH} not found: build it with `python speech-tranformer-pytorch_b200/build.py` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().st_last_error()
+        raise StError(f"libst_b200 error {status}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,503 @@
+// st_api.cu — the extern "C" boundary (include/st_b200.h) and the host-side orchestration of the
+// composite operators: MultiHeadAttention (transformer/Attention.py:64-96) and
+// PositionwiseFeedForward (transformer/SubLayers.py:24-28), forward and backward.
+//
+// Precision contract: every tensor-core operand is rounded to TF32 with round-to-nearest where it
+// is PRODUCED (GEMM / LayerNorm / attention epilogues) or, for tensors that arrive from outside the
+// library, by one explicit rounding pass; accumulation is fp32.
+#include <math.h>
+#include <string.h>
+
+#include "../../include/st_b200.h"
+#include "st_gemm.cuh"
+#include "st_host.h"
+#include "st_kernels.h"
+
+namespace st {
+
+DropoutCfg make_dropout(float p, uint64_t seed) {
+  DropoutCfg c;
+  if (p > 0.f) {
+    double t = static_cast<double>(p) * 4294967296.0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    c.thresh = static_cast<uint32_t>(t);
+    if (c.thresh == 0) c.thresh = 1;
+    c.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+    c.seed = seed;
+  }
+  return c;
+}
+
+int selftest(int which, double* err);
+int selftest_count();
+
+namespace {
+
+// split-K factor for a weight-gradient GEMM: enough CTAs to fill the machine ~2x, at least 4 k-blocks each
+int wgrad_splits(int m_out, int n_out, int64_t k_len) {
+  const int bn = n_out > 128 ? 256 : (n_out > 64 ? 128 : 64);
+  const int tiles = ((m_out + 127) / 128) * ((n_out + bn - 1) / bn);
+  const int64_t kblocks = (k_len + 31) / 32;
+  int s = (2 * num_sms() + tiles - 1) / tiles;
+  const int64_t max_s = kblocks / 4 > 0 ? kblocks / 4 : 1;
+  if (s > max_s) s = static_cast<int>(max_s);
+  return s < 1 ? 1 : s;
+}
+
+// dW[out,in] = dY[rows,out]^T * X[rows,in]   (overwrites dW)
+int wgrad(cudaStream_t s, const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, int rows, int n_out,
+          int n_in) {
+  ST_CHECK_CUDA(cudaMemsetAsync(dw, 0, static_cast<size_t>(n_out) * n_in * sizeof(float), s));
+  GemmEpilogue ep;
+  ep.atomic = 1;
+  return gemm_tf32(s, GEMM_TN, dy, lddy, x, ldx, dw, n_in, n_out, n_in, rows, ep, wgrad_splits(n_out, n_in, rows));
+}
+
+struct Carver {
+  float* base;
+  int64_t used = 0;
+  int64_t cap;
+  Carver(float* b, int64_t c) : base(b), cap(c) {}
+  float* take(int64_t n) {
+    n = (n + 63) & ~int64_t(63);  // keep every sub-buffer 256-byte aligned
+    float* p = base + used;
+    used += n;
+    return p;
+  }
+  bool ok() const { return base != nullptr && used <= cap; }
+};
+int64_t pad64(int64_t n) { return (n + 63) & ~int64_t(63); }
+
+// ------------------------------------------------------------------ MHA buffer plans
+struct MhaPlan {
+  bool same_qkv, same_kv;
+  int64_t M, Mk;
+  int d;
+  // saved
+  float *xq_r, *xk_r, *xv_r;  // rounded inputs (alias the inputs when inputs_tf32)
+  float *projq, *projk, *projv;
+  int64_t ldpq, ldpk, ldpv;
+  float *ctx, *lse, *z, *mean, *rstd, *w_r /*[3d,d] q,k,v*/, *b_pack /*[3d]*/, *wo_r;
+};
+
+int64_t mha_saved_floats(int B, int Lq, int Lk, int H, int d, bool same_qkv, bool same_kv, bool inputs_tf32) {
+  const int64_t M = static_cast<int64_t>(B) * Lq, Mk = static_cast<int64_t>(B) * Lk;
+  int64_t n = 0;
+  if (!inputs_tf32) {
+    n += pad64(M * d);
+    if (!same_qkv) { n += pad64(Mk * d); if (!same_kv) n += pad64(Mk * d); }
+  }
+  n += same_qkv ? pad64(M * 3 * d) : pad64(M * d) + (same_kv ? pad64(Mk * 2 * d) : 2 * pad64(Mk * d));
+  n += pad64(M * d);                               // ctx
+  n += pad64(static_cast<int64_t>(B) * H * Lq);    // lse
+  n += pad64(M * d) + 2 * pad64(M);                // z, mean, rstd
+  n += pad64(3ll * d * d) + pad64(3 * d) + pad64(static_cast<int64_t>(d) * d);
+  return n;
+}
+
+int plan_mha(const st_mha_args& a, MhaPlan& p) {
+  p.same_qkv = (a.q_in == a.k_in && a.k_in == a.v_in && a.Lq == a.Lk);
+  p.same_kv = (a.k_in == a.v_in);
+  p.M = static_cast<int64_t>(a.B) * a.Lq;
+  p.Mk = static_cast<int64_t>(a.B) * a.Lk;
+  p.d = a.d_model;
+  const int d = a.d_model;
+  Carver c(a.saved, a.saved_floats);
+  if (a.inputs_tf32) {
+    p.xq_r = const_cast<float*>(a.q_in); p.xk_r = const_cast<float*>(a.k_in); p.xv_r = const_cast<float*>(a.v_in);
+  } else {
+    p.xq_r = c.take(p.M * d);
+    if (p.same_qkv) { p.xk_r = p.xv_r = p.xq_r; }
+    else {
+      p.xk_r = c.take(p.Mk * d);
+      p.xv_r = p.same_kv ? p.xk_r : c.take(p.Mk * d);
+    }
+  }
+  if (p.same_qkv) {
+    float* b = c.take(p.M * 3 * d);
+    p.projq = b; p.projk = b + d; p.projv = b + 2 * d;
+    p.ldpq = p.ldpk = p.ldpv = 3 * d;
+  } else {
+    p.projq = c.take(p.M * d); p.ldpq = d;
+    if (p.same_kv) {
+      float* b = c.take(p.Mk * 2 * d);
+      p.projk = b; p.projv = b + d; p.ldpk = p.ldpv = 2 * d;
+    } else {
+      p.projk = c.take(p.Mk * d); p.projv = c.take(p.Mk * d); p.ldpk = p.ldpv = d;
+    }
+  }
+  p.ctx = c.take(p.M * d);
+  p.lse = c.take(static_cast<int64_t>(a.B) * a.H * a.Lq);
+  p.z = c.take(p.M * d);
+  p.mean = c.take(p.M);
+  p.rstd = c.take(p.M);
+  p.w_r = c.take(3ll * d * d);
+  p.b_pack = c.take(3 * d);
+  p.wo_r = c.take(static_cast<int64_t>(d) * d);
+  if (!c.ok()) {
+    set_error("st_mha: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
+    return ST_ERR_WORKSPACE;
+  }
+  return ST_OK;
+}
+
+int check_mha(const st_mha_args& a) {
+  ST_REQUIRE(a.B > 0 && a.Lq > 0 && a.Lk > 0 && a.H > 0, "st_mha: empty problem");
+  ST_REQUIRE(a.d_model == a.H * a.dk, "st_mha: d_model (%d) != n_head (%d) * d_k (%d)", a.d_model, a.H, a.dk);
+  ST_REQUIRE(a.dk == 32 || a.dk == 64 || a.dk == 128, "st_mha: d_k must be 32, 64 or 128 (got %d)", a.dk);
+  return ST_OK;
+}
+
+int64_t mha_ws_floats(int B, int Lq, int Lk, int H, int d) {
+  const int64_t M = static_cast<int64_t>(B) * Lq, Mk = static_cast<int64_t>(B) * Lk;
+  // backward: dz, dctx, dprojq, dprojk, dprojv, delta
+  return 2 * pad64(M * d) + pad64(M * 3 * d) + 2 * pad64(Mk * 2 * d) + pad64(static_cast<int64_t>(B) * H * Lq) + 64;
+}
+
+}  // namespace
+}  // namespace st
+
+using namespace st;
+
+extern "C" {
+
+int st_version(void) { return 100; }
+const char* st_last_error(void) { return last_error(); }
+
+int st_device_check(int device) {
+  cudaDeviceProp prop;
+  ST_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d (%s); this library only runs on sm_100 (B200)", device, prop.major, prop.minor, prop.name);
+    return ST_ERR_DEVICE;
+  }
+  return ST_OK;
+}
+
+int st_set_option(const char* name, int v) { return set_option(name, v); }
+int st_selftest_count(void) { return selftest_count(); }
+int st_selftest(int which, double* rel_err_out) { return selftest(which, rel_err_out); }
+
+int st_add_ln_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* out, float* z_out,
+                  float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_tf32, float dropout_p,
+                  uint64_t seed, cudaStream_t stream) {
+  return add_ln_fwd(stream, a, b, gamma, beta, out, z_out, mean_out, rstd_out, rows, d, eps, round_tf32,
+                    make_dropout(dropout_p, seed));
+}
+
+int st_add_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                  float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, int round_tf32,
+                  float dropout_p, uint64_t seed, cudaStream_t stream) {
+  return add_ln_bwd(stream, dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum, rows, d, round_tf32,
+                    make_dropout(dropout_p, seed));
+}
+
+int st_lsce_fwd_bwd(const float* logits, int64_t ld_logits, const int64_t* target, const float* one_hot,
+                    const float* weight, float confidence, int64_t padding_idx, int size_average, int64_t N, int V,
+                    float* row_loss, float* loss, float* grad, int64_t ld_grad, cudaStream_t stream) {
+  LsceArgs a{};
+  a.logits = logits; a.ldl = ld_logits; a.target = target; a.q_dense = nullptr; a.one_hot = one_hot; a.weight = weight;
+  a.confidence = confidence; a.padding_idx = padding_idx;
+  a.inv_z = (size_average && N > 0) ? 1.f / static_cast<float>(N) : 1.f;
+  a.N = N; a.V = V; a.row_loss = row_loss; a.loss = loss; a.grad = grad; a.ldg = ld_grad;
+  ST_REQUIRE(target != nullptr && one_hot != nullptr, "st_lsce_fwd_bwd: target and one_hot are required");
+  return lsce_fwd_bwd(stream, a);
+}
+
+int st_softce_fwd_bwd(const float* logits, int64_t ld_logits, const float* q, const float* weight, int size_average,
+                      int64_t N, int V, float* row_loss, float* loss, float* grad, int64_t ld_grad,
+                      cudaStream_t stream) {
+  LsceArgs a{};
+  a.logits = logits; a.ldl = ld_logits; a.target = nullptr; a.q_dense = q; a.one_hot = nullptr; a.weight = weight;
+  a.confidence = 0.f; a.padding_idx = -1;
+  a.inv_z = (size_average && N > 0) ? 1.f / static_cast<float>(N) : 1.f;
+  a.N = N; a.V = V; a.row_loss = row_loss; a.loss = loss; a.grad = grad; a.ldg = ld_grad;
+  ST_REQUIRE(q != nullptr, "st_softce_fwd_bwd: q is required");
+  return lsce_fwd_bwd(stream, a);
+}
+
+int st_round_tf32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, cudaStream_t stream) {
+  return round_tf32_2d(stream, src, lds, dst, ldd, rows, cols);
+}
+int st_colsum_add(const float* x, int64_t ld, int64_t rows, int cols, float* out, cudaStream_t stream) {
+  return colsum_add(stream, x, ld, rows, cols, out);
+}
+
+int st_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+            int K, const st_gemm_epilogue* e, cudaStream_t stream) {
+  ST_REQUIRE(mode >= 0 && mode <= 2, "st_gemm: bad mode %d", mode);
+  GemmEpilogue ep;
+  int splits = 1;
+  if (e) {
+    ep.bias = e->bias; ep.aux = e->aux; ep.ldaux = e->ldaux; ep.aux_mode = e->aux_mode; ep.relu = e->relu;
+    ep.round_tf32 = e->round_tf32;
+    const DropoutCfg dc = make_dropout(e->dropout_p, e->seed);
+    ep.drop_thresh = dc.thresh; ep.drop_scale = dc.scale; ep.drop_seed = dc.seed;
+    splits = e->k_splits > 1 ? e->k_splits : 1;
+    ep.atomic = splits > 1;
+    ST_REQUIRE(!ep.aux_mode || ep.aux, "st_gemm: aux_mode set without aux");
+  }
+  return gemm_tf32(stream, static_cast<GemmMode>(mode), A, lda, B, ldb, C, ldc, M, N, K, ep, splits);
+}
+
+int st_sumsq(const float* x, int64_t n, float* out, cudaStream_t stream) { return sumsq_add(stream, x, n, out); }
+int st_adam_step(const st_adam_args* a, cudaStream_t stream) {
+  ST_REQUIRE(a != nullptr, "st_adam_step: null args");
+  return adam_step(stream, a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->n, a->lr, a->beta1, a->beta2, a->eps,
+                   a->step, a->max_grad_norm, a->grad_scale, a->norm_ws);
+}
+
+// ------------------------------------------------------------------ attention core
+static AttnArgs to_attn(const st_attn_args& a) {
+  AttnArgs r{};
+  r.B = a.B; r.H = a.H; r.Lq = a.Lq; r.Lk = a.Lk; r.dk = a.dk;
+  r.q = a.q; r.ldq = a.ldq; r.k = a.k; r.ldk = a.ldk; r.v = a.v; r.ldv = a.ldv;
+  r.mask = a.mask; r.ms_b = a.ms_b; r.ms_q = a.ms_q; r.ms_k = a.ms_k;
+  r.scale = 1.f / sqrtf(static_cast<float>(a.dk));
+  r.drop = make_dropout(a.dropout_p, a.seed);
+  r.ctx = a.ctx; r.ldctx = a.ldctx; r.lse = a.lse; r.attn = a.attn;
+  return r;
+}
+
+int st_attn_fwd(const st_attn_args* a, cudaStream_t stream) {
+  ST_REQUIRE(a != nullptr, "st_attn_fwd: null args");
+  return attn_fwd(stream, to_attn(*a));
+}
+
+int st_attn_bwd(const st_attn_bwd_args* a, cudaStream_t stream) {
+  ST_REQUIRE(a != nullptr, "st_attn_bwd: null args");
+  AttnBwdArgs b{};
+  b.f = to_attn(a->f);
+  b.dctx = a->dctx; b.lddctx = a->lddctx; b.delta = a->delta;
+  b.dq = a->dq; b.lddq = a->lddq; b.dk_ = a->dk; b.lddk = a->lddk; b.dv = a->dv; b.lddv = a->lddv;
+  return attn_bwd(stream, b);
+}
+
+// ------------------------------------------------------------------ MultiHeadAttention
+int64_t st_mha_saved_floats(int B, int Lq, int Lk, int H, int d_model, int same_qkv, int same_kv, int inputs_tf32) {
+  return mha_saved_floats(B, Lq, Lk, H, d_model, same_qkv != 0, same_kv != 0 || same_qkv != 0, inputs_tf32 != 0);
+}
+int64_t st_mha_ws_floats(int B, int Lq, int Lk, int H, int d_model) { return mha_ws_floats(B, Lq, Lk, H, d_model); }
+
+int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
+  ST_REQUIRE(ap != nullptr, "st_mha_fwd: null args");
+  const st_mha_args& a = *ap;
+  ST_TRY(check_mha(a));
+  MhaPlan p;
+  ST_TRY(plan_mha(a, p));
+  const int d = a.d_model;
+  const int M = static_cast<int>(p.M), Mk = static_cast<int>(p.Mk);
+
+  // 1. TF32 copies of the weights, packed [wq; wk; wv] so that shared inputs need one GEMM
+  ST_TRY(round_tf32_2d(s, a.wq, d, p.w_r, d, d, d));
+  ST_TRY(round_tf32_2d(s, a.wk, d, p.w_r + static_cast<int64_t>(d) * d, d, d, d));
+  ST_TRY(round_tf32_2d(s, a.wv, d, p.w_r + 2ll * d * d, d, d, d));
+  ST_TRY(round_tf32_2d(s, a.wo, d, p.wo_r, d, d, d));
+  ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack, a.bq, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + d, a.bk, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + 2 * d, a.bv, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  // 2. TF32 copies of the inputs
+  if (!a.inputs_tf32) {
+    ST_TRY(round_tf32_2d(s, a.q_in, d, p.xq_r, d, M, d));
+    if (!p.same_qkv) {
+      ST_TRY(round_tf32_2d(s, a.k_in, d, p.xk_r, d, Mk, d));
+      if (!p.same_kv) ST_TRY(round_tf32_2d(s, a.v_in, d, p.xv_r, d, Mk, d));
+    }
+  }
+  // 3. projections (Attention.py:74-76), outputs rounded for the attention MMAs
+  GemmEpilogue ep;
+  ep.round_tf32 = 1;
+  if (p.same_qkv) {
+    ep.bias = p.b_pack;
+    ST_TRY(gemm_tf32(s, GEMM_NT, p.xq_r, d, p.w_r, d, p.projq, p.ldpq, M, 3 * d, d, ep));
+  } else {
+    ep.bias = p.b_pack;
+    ST_TRY(gemm_tf32(s, GEMM_NT, p.xq_r, d, p.w_r, d, p.projq, p.ldpq, M, d, d, ep));
+    if (p.same_kv) {
+      ep.bias = p.b_pack + d;
+      ST_TRY(gemm_tf32(s, GEMM_NT, p.xk_r, d, p.w_r + static_cast<int64_t>(d) * d, d, p.projk, p.ldpk, Mk, 2 * d, d, ep));
+    } else {
+      ep.bias = p.b_pack + d;
+      ST_TRY(gemm_tf32(s, GEMM_NT, p.xk_r, d, p.w_r + static_cast<int64_t>(d) * d, d, p.projk, p.ldpk, Mk, d, d, ep));
+      ep.bias = p.b_pack + 2 * d;
+      ST_TRY(gemm_tf32(s, GEMM_NT, p.xv_r, d, p.w_r + 2ll * d * d, d, p.projv, p.ldpv, Mk, d, d, ep));
+    }
+  }
+  // 4. attention core (Attention.py:78-90)
+  AttnArgs at{};
+  at.B = a.B; at.H = a.H; at.Lq = a.Lq; at.Lk = a.Lk; at.dk = a.dk;
+  at.q = p.projq; at.ldq = p.ldpq; at.k = p.projk; at.ldk = p.ldpk; at.v = p.projv; at.ldv = p.ldpv;
+  at.mask = a.mask; at.ms_b = a.ms_b; at.ms_q = a.ms_q; at.ms_k = a.ms_k;
+  at.scale = 1.f / sqrtf(static_cast<float>(a.dk));
+  at.drop = make_dropout(a.dropout_p, a.seed);
+  at.ctx = p.ctx; at.ldctx = d; at.lse = p.lse; at.attn = a.attn;
+  ST_TRY(attn_fwd(s, at));
+  // 5. output projection + bias + residual (Attention.py:92,94)
+  GemmEpilogue eo;
+  eo.bias = a.bo; eo.aux = a.residual; eo.ldaux = d; eo.aux_mode = 1;
+  ST_TRY(gemm_tf32(s, GEMM_NT, p.ctx, d, p.wo_r, d, p.z, d, M, d, d, eo));
+  // 6. LayerNorm (Attention.py:94)
+  return add_ln_fwd(s, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out, DropoutCfg{});
+}
+
+int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
+  ST_REQUIRE(bp != nullptr, "st_mha_bwd: null args");
+  const st_mha_bwd_args& b = *bp;
+  const st_mha_args& a = b.f;
+  ST_TRY(check_mha(a));
+  MhaPlan p;
+  ST_TRY(plan_mha(a, p));
+  const int d = a.d_model;
+  const int M = static_cast<int>(p.M), Mk = static_cast<int>(p.Mk);
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= mha_ws_floats(a.B, a.Lq, a.Lk, a.H, d), "st_mha_bwd: workspace too small");
+  Carver w(a.ws, a.ws_floats);
+  float* dz = w.take(p.M * d);
+  float* dctx = w.take(p.M * d);
+  float *dpq, *dpk, *dpv;
+  if (p.same_qkv) { float* t = w.take(p.M * 3 * d); dpq = t; dpk = t + d; dpv = t + 2 * d; }
+  else {
+    dpq = w.take(p.M * d);
+    if (p.same_kv) { float* t = w.take(p.Mk * 2 * d); dpk = t; dpv = t + d; }
+    else { dpk = w.take(p.Mk * d); dpv = w.take(p.Mk * d); }
+  }
+  float* delta = w.take(static_cast<int64_t>(a.B) * a.H * a.Lq);
+
+  // LayerNorm backward; dbo = column sums of dz
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_g, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_b, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dbo, 0, d * sizeof(float), s));
+  ST_TRY(add_ln_bwd(s, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d, 1, DropoutCfg{}));
+  // output projection backward
+  {
+    GemmEpilogue e; e.round_tf32 = 1;
+    ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.wo_r, d, dctx, d, M, d, d, e));
+    ST_TRY(wgrad(s, dz, d, p.ctx, d, b.dwo, M, d, d));
+  }
+  // attention core backward
+  {
+    AttnBwdArgs ab{};
+    AttnArgs& at = ab.f;
+    at.B = a.B; at.H = a.H; at.Lq = a.Lq; at.Lk = a.Lk; at.dk = a.dk;
+    at.q = p.projq; at.ldq = p.ldpq; at.k = p.projk; at.ldk = p.ldpk; at.v = p.projv; at.ldv = p.ldpv;
+    at.mask = a.mask; at.ms_b = a.ms_b; at.ms_q = a.ms_q; at.ms_k = a.ms_k;
+    at.scale = 1.f / sqrtf(static_cast<float>(a.dk));
+    at.drop = make_dropout(a.dropout_p, a.seed);
+    at.ctx = p.ctx; at.ldctx = d; at.lse = p.lse; at.attn = nullptr;
+    ab.dctx = dctx; ab.lddctx = d; ab.delta = delta;
+    ab.dq = dpq; ab.lddq = p.ldpq; ab.dk_ = dpk; ab.lddk = p.ldpk; ab.dv = dpv; ab.lddv = p.ldpv;
+    ST_TRY(attn_bwd(s, ab));
+  }
+  // projection bias / weight gradients
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dbv, 0, d * sizeof(float), s));
+  ST_TRY(colsum_add(s, dpq, p.ldpq, M, d, b.dbq));
+  ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, d, b.dbk));
+  ST_TRY(colsum_add(s, dpv, p.ldpv, Mk, d, b.dbv));
+  ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d));
+  ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d));
+  ST_TRY(wgrad(s, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d));
+  // input gradients; the residual branch contributes dz to whichever input it aliased
+  const bool res_q = (a.residual == a.q_in), res_k = (a.residual == a.k_in), res_v = (a.residual == a.v_in);
+  auto with_res = [&](bool on) { GemmEpilogue e; if (on) { e.aux = dz; e.ldaux = d; e.aux_mode = 1; } return e; };
+  if (p.same_qkv) {
+    ST_TRY(gemm_tf32(s, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, M, d, 3 * d, with_res(res_q)));
+  } else {
+    ST_TRY(gemm_tf32(s, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, M, d, d, with_res(res_q)));
+    if (p.same_kv) {
+      ST_TRY(gemm_tf32(s, GEMM_NN, dpk, p.ldpk, p.w_r + static_cast<int64_t>(d) * d, d, b.dk_in, d, Mk, d, 2 * d, with_res(res_k || res_v)));
+    } else {
+      ST_TRY(gemm_tf32(s, GEMM_NN, dpk, p.ldpk, p.w_r + static_cast<int64_t>(d) * d, d, b.dk_in, d, Mk, d, d, with_res(res_k)));
+      ST_TRY(gemm_tf32(s, GEMM_NN, dpv, p.ldpv, p.w_r + 2ll * d * d, d, b.dv_in, d, Mk, d, d, with_res(res_v && !res_k)));
+    }
+  }
+  if (!(res_q || res_k || res_v)) {
+    ST_REQUIRE(b.dresidual != nullptr, "st_mha_bwd: dresidual is required when residual is a separate tensor");
+    ST_CHECK_CUDA(cudaMemcpyAsync(b.dresidual, dz, p.M * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return ST_OK;
+}
+
+// ------------------------------------------------------------------ PositionwiseFeedForward
+namespace {
+struct FfnPlan { float *x_r, *h, *z, *mean, *rstd, *w1_r, *w2_r; };
+int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
+  Carver c(a.saved, a.saved_floats);
+  p.x_r = a.x_is_tf32 ? const_cast<float*>(a.x) : c.take(a.rows * a.d_model);
+  p.h = c.take(a.rows * a.d_ff);
+  p.z = c.take(a.rows * a.d_model);
+  p.mean = c.take(a.rows);
+  p.rstd = c.take(a.rows);
+  p.w1_r = c.take(static_cast<int64_t>(a.d_ff) * a.d_model);
+  p.w2_r = c.take(static_cast<int64_t>(a.d_ff) * a.d_model);
+  if (!c.ok()) {
+    set_error("st_ffn: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
+    return ST_ERR_WORKSPACE;
+  }
+  return ST_OK;
+}
+constexpr uint64_t kSeedMix1 = 0x5DEECE66Dull, kSeedMix2 = 0xB5297A4D3F84D5B5ull;
+}  // namespace
+
+int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32) {
+  return (x_is_tf32 ? 0 : pad64(rows * d_model)) + pad64(rows * d_ff) + pad64(rows * d_model) + 2 * pad64(rows) +
+         2 * pad64(static_cast<int64_t>(d_ff) * d_model);
+}
+int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff) { return pad64(rows * d_model) + pad64(rows * d_ff) + 64; }
+
+int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
+  ST_REQUIRE(ap != nullptr, "st_ffn_fwd: null args");
+  const st_ffn_args& a = *ap;
+  ST_REQUIRE(a.rows > 0 && a.rows < (1ll << 31) && a.d_model > 0 && a.d_ff > 0, "st_ffn: bad shape");
+  FfnPlan p;
+  ST_TRY(plan_ffn(a, p));
+  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff;
+  ST_TRY(round_tf32_2d(s, a.w1, d, p.w1_r, d, f, d));
+  ST_TRY(round_tf32_2d(s, a.w2, f, p.w2_r, f, d, f));
+  if (!a.x_is_tf32) ST_TRY(round_tf32_2d(s, a.x, d, p.x_r, d, M, d));
+  // h = dropout1(relu(fc1(x)))                                           SubLayers.py:25
+  GemmEpilogue e1;
+  e1.bias = a.b1; e1.relu = 1; e1.round_tf32 = 1;
+  const DropoutCfg d1 = make_dropout(a.dropout_p, a.seed ^ kSeedMix1);
+  e1.drop_thresh = d1.thresh; e1.drop_scale = d1.scale; e1.drop_seed = d1.seed;
+  ST_TRY(gemm_tf32(s, GEMM_NT, p.x_r, d, p.w1_r, d, p.h, f, M, f, d, e1));
+  // z = x + fc2(h)                                                       SubLayers.py:26-27
+  GemmEpilogue e2;
+  e2.bias = a.b2; e2.aux = a.x; e2.ldaux = d; e2.aux_mode = 1;
+  ST_TRY(gemm_tf32(s, GEMM_NT, p.h, f, p.w2_r, f, p.z, d, M, d, f, e2));
+  // out = dropout2(LN(z))                                                SubLayers.py:27
+  return add_ln_fwd(s, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out,
+                    make_dropout(a.dropout_p, a.seed ^ kSeedMix2));
+}
+
+int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
+  ST_REQUIRE(bp != nullptr, "st_ffn_bwd: null args");
+  const st_ffn_bwd_args& b = *bp;
+  const st_ffn_args& a = b.f;
+  FfnPlan p;
+  ST_TRY(plan_ffn(a, p));
+  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff;
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= st_ffn_ws_floats(a.rows, d, f), "st_ffn_bwd: workspace too small");
+  Carver w(a.ws, a.ws_floats);
+  float* dz = w.take(a.rows * d);
+  float* dh = w.take(a.rows * f);
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_g, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_b, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.db2, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.db1, 0, f * sizeof(float), s));
+  ST_TRY(add_ln_bwd(s, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d, 1,
+                    make_dropout(a.dropout_p, a.seed ^ kSeedMix2)));
+  // dh = (dz W2) * [h > 0] * dropout1 scale
+  GemmEpilogue e;
+  e.aux = p.h; e.ldaux = f; e.aux_mode = 2; e.round_tf32 = 1;
+  e.aux_scale = make_dropout(a.dropout_p, 0).scale;
+  ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.w2_r, f, dh, f, M, f, d, e));
+  ST_TRY(wgrad(s, dz, d, p.h, f, b.dw2, M, d, f));
+  ST_TRY(colsum_add(s, dh, f, M, f, b.db1));
+  ST_TRY(wgrad(s, dh, f, p.x_r, d, b.dw1, M, f, d));
+  GemmEpilogue ex;
+  ex.aux = dz; ex.ldaux = d; ex.aux_mode = 1;
+  return gemm_tf32(s, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, M, d, f, ex);
+}
+
+}  // extern "C"

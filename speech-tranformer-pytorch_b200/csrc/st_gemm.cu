@@ -1,0 +1,341 @@
+// st_gemm.cu — persistent, warp-specialised TF32 GEMM on tcgen05 tensor cores.
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  : epilogue (tcgen05.ld -> bias / ReLU / residual / TF32 rounding -> global)
+//
+// Output tile 128 x BN (BN in {64,128,256}); K is consumed in blocks of 32 fp32 (= one 128-byte
+// swizzle atom); accumulators are double-buffered in TMEM (2*BN columns) so the epilogue of
+// tile i overlaps the main loop of tile i+1.  Operands may be K-major or MN-major (see
+// st_common.cuh), which covers forward (NT), data-gradient (NN) and weight-gradient (TN) GEMMs
+// without any transposed copies in HBM.
+#include "st_common.cuh"
+#include "st_gemm.cuh"
+#include "st_host.h"
+
+namespace st {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                       // fp32 elements per k-block = 128 bytes
+constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  float* C;
+  int64_t ldc;
+  int M, N, K;
+  int m_tiles, n_tiles, k_splits;
+  int kblocks_total, kblocks_per_split;
+  GemmEpilogue ep;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_mn * p.k_splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 32; ++i)
+              tma_load_2d(sa + i * 4096, &tmap_a, &full_bar[stage], m_blk * BM + i * 32, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i)
+              tma_load_2d(sb + i * 4096, &tmap_b, &full_bar[stage], n_blk * BN + i * 32, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            // K-major: +32 B per MMA inside the 128 B swizzle row.  MN-major: next 8-row K atom (+1024 B);
+            // 32-wide MN groups are 4096 B apart (one TMA box each).
+            const uint64_t adesc = A_MN ? umma_desc_sw128(sa + k * 1024, 4096, 1024) : umma_desc_kmajor(sa + k * 32);
+            const uint64_t bdesc = B_MN ? umma_desc_sw128(sb + k * 1024, 4096, 1024) : umma_desc_kmajor(sb + k * 32);
+            umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const GemmEpilogue& ep = p.ep;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool aux_vec_ok = ep.aux && ((ep.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* crow = p.C + static_cast<int64_t>(row) * p.ldc;
+      const float* auxrow = ep.aux ? ep.aux + static_cast<int64_t>(row) * ep.ldaux : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < p.N) {
+          const bool full = (col0 + 32 <= p.N);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) v[t] = __uint_as_float(r[j + t]);
+            const int col = col0 + j;
+            if (full || col + 3 < p.N) {
+              if (ep.bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(ep.bias + col);  // N%4==0 checked on host
+                v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+              }
+              if (ep.relu) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
+              }
+              if (ep.drop_thresh) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const uint64_t idx = static_cast<uint64_t>(row) * p.N + (col + t);
+                  v[t] = dropout_keep(ep.drop_seed, idx, ep.drop_thresh) ? v[t] * ep.drop_scale : 0.f;
+                }
+              }
+              if (ep.aux_mode) {
+                float a[4];
+                if (aux_vec_ok) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(auxrow + col);
+                  a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+                } else {
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) a[t] = auxrow[col + t];
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[t] = (ep.aux_mode == 1) ? v[t] + a[t] : (a[t] > 0.f ? v[t] * ep.aux_scale : 0.f);
+              }
+              if (ep.round_tf32) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[t] = tf32_rna(v[t]);
+              }
+              if (ep.atomic) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) atomicAdd(crow + col + t, v[t]);
+              } else if (vec_ok) {
+                *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
+              } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) crow[col + t] = v[t];
+              }
+            } else {
+              // ragged N tail: scalar path
+              for (int t = 0; t < 4; ++t) {
+                const int cc = col + t;
+                if (cc >= p.N) break;
+                float x = v[t];
+                if (ep.bias) x += ep.bias[cc];
+                if (ep.relu) x = fmaxf(x, 0.f);
+                if (ep.drop_thresh) {
+                  const uint64_t idx = static_cast<uint64_t>(row) * p.N + cc;
+                  x = dropout_keep(ep.drop_seed, idx, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
+                }
+                if (ep.aux_mode == 1) x += auxrow[cc];
+                if (ep.aux_mode == 2) x = auxrow[cc] > 0.f ? x * ep.aux_scale : 0.f;
+                if (ep.round_tf32) x = tf32_rna(x);
+                if (ep.atomic) atomicAdd(crow + cc, x); else crow[cc] = x;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation; benign race (idempotent)
+  if (!attr_set) {
+    ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  int cap = get_option("gemm_max_ctas");
+  if (cap <= 0) cap = num_sms();
+  const int grid = tiles < cap ? tiles : cap;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  ST_CHECK_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+template <int BN>
+int dispatch_mode(cudaStream_t stream, GemmMode mode, const CUtensorMap& ta, const CUtensorMap& tb,
+                  const GemmParams& p) {
+  switch (mode) {
+    case GEMM_NT: return launch_gemm<BN, false, false>(stream, ta, tb, p);
+    case GEMM_NN: return launch_gemm<BN, false, true>(stream, ta, tb, p);
+    case GEMM_TN: return launch_gemm<BN, true, true>(stream, ta, tb, p);
+  }
+  set_error("gemm_tf32: bad mode %d", static_cast<int>(mode));
+  return ST_ERR_INVALID;
+}
+
+}  // namespace
+
+int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+              int64_t ldc, int M, int N, int K, const GemmEpilogue& ep, int k_splits) {
+  ST_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tf32: empty problem M=%d N=%d K=%d", M, N, K);
+  ST_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             "gemm_tf32: operands must be 16-byte aligned");
+  ST_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "gemm_tf32: lda=%lld ldb=%lld must be multiples of 4 floats",
+             (long long)lda, (long long)ldb);
+  ST_REQUIRE(!ep.bias || ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0),
+             "gemm_tf32: bias needs N%%4==0 and 16-byte alignment");
+  ST_REQUIRE(k_splits >= 1 && (k_splits == 1 || ep.atomic), "gemm_tf32: split-K needs the atomic epilogue");
+
+  const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
+  GemmParams p;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  p.kblocks_total = (K + BK - 1) / BK;
+  if (k_splits > p.kblocks_total) k_splits = p.kblocks_total;
+  p.kblocks_per_split = (p.kblocks_total + k_splits - 1) / k_splits;
+  p.k_splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.ep = ep;
+
+  CUtensorMap ta, tb;
+  {
+    // A: K-major -> dims {K, M}; MN-major (TN) -> stored [K, M], dims {M, K}
+    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(lda) * 4};
+    uint32_t box[2];
+    if (mode == GEMM_TN) { dims[0] = M; dims[1] = K; box[0] = 32; box[1] = 32; }
+    else                 { dims[0] = K; dims[1] = M; box[0] = 32; box[1] = BM; }
+    ST_TRY(make_tmap_f32(&ta, A, 2, dims, strides, box));
+  }
+  {
+    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(ldb) * 4};
+    uint32_t box[2];
+    if (mode == GEMM_NT) { dims[0] = K; dims[1] = N; box[0] = 32; box[1] = static_cast<uint32_t>(BN); }
+    else                 { dims[0] = N; dims[1] = K; box[0] = 32; box[1] = 32; }
+    ST_TRY(make_tmap_f32(&tb, B, 2, dims, strides, box));
+  }
+  switch (BN) {
+    case 256: return dispatch_mode<256>(stream, mode, ta, tb, p);
+    case 128: return dispatch_mode<128>(stream, mode, ta, tb, p);
+    default:  return dispatch_mode<64>(stream, mode, ta, tb, p);
+  }
+}
+
+}  // namespace st

@@ -1,0 +1,34 @@
+// st_gemm.cuh — interface of the TF32 tcgen05 GEMM core used by every projection on the path
+// (reference: the nn.Linear calls at transformer/Attention.py:74-76,92 and SubLayers.py:25-26).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace st {
+
+// Operand layouts (all row-major fp32 in HBM):
+//   GEMM_NT  C[M,N] = A[M,K] * B[N,K]^T      forward linear      (A K-major,  B K-major)
+//   GEMM_NN  C[M,N] = A[M,K] * B[K,N]        data gradient       (A K-major,  B MN-major)
+//   GEMM_TN  C[M,N] = A[K,M]^T * B[K,N]      weight gradient     (A MN-major, B MN-major)
+enum GemmMode : int { GEMM_NT = 0, GEMM_NN = 1, GEMM_TN = 2 };
+
+struct GemmEpilogue {
+  const float* bias = nullptr;  // [N], added to every row
+  const float* aux = nullptr;   // [M, ldaux]
+  int64_t ldaux = 0;
+  int aux_mode = 0;    // 0: none   1: out += aux (residual)   2: out = aux > 0 ? out * aux_scale : 0 (ReLU backward)
+  float aux_scale = 1.f;
+  int relu = 0;        // out = max(out, 0) (after bias)
+  int round_tf32 = 0;  // round the stored value to TF32 (round-to-nearest) — the value feeds another MMA
+  int atomic = 0;      // accumulate into C with red.global.add (split-K partial sums)
+  // inverted dropout applied after ReLU (SubLayers.py:25); keep iff hash(seed, row*N+col) >= thresh
+  uint32_t drop_thresh = 0;
+  float drop_scale = 1.f;
+  uint64_t drop_seed = 0;
+};
+
+// k_splits > 1 requires ep.atomic and a zero-initialised C.
+int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+              int64_t ldc, int M, int N, int K, const GemmEpilogue& ep, int k_splits = 1);
+
+}  // namespace st

@@ -1,0 +1,94 @@
+// st_host.cu — error string, device query and TMA tensor-map construction.
+#include "st_host.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+
+namespace st {
+
+namespace {
+std::mutex g_err_mutex;
+char g_err[1024] = "";
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  std::lock_guard<std::mutex> lock(g_err_mutex);
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const char* last_error() { return g_err; }
+
+namespace {
+struct Option { const char* name; int value; };
+Option g_options[] = {
+    {"gemm_max_ctas", 0},   // 0 = one CTA per SM; >0 caps the persistent grid (tests multi-tile paths)
+    {"attn_p_smem", 0},     // 1 = stage softmax probabilities through smem instead of TMEM
+};
+}  // namespace
+
+int set_option(const char* name, int value) {
+  for (auto& o : g_options)
+    if (strcmp(o.name, name) == 0) { o.value = value; return ST_OK; }
+  set_error("unknown option '%s'", name);
+  return ST_ERR_INVALID;
+}
+int get_option(const char* name) {
+  for (auto& o : g_options)
+    if (strcmp(o.name, name) == 0) return o.value;
+  return 0;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+      return ST_ERR_CUDA;
+    }
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstrides[i] = strides_bytes[i];
+  }
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                      gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu] stride0 %llu box [%u,%u,%u] base %p",
+              static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, base);
+    return ST_ERR_CUDA;
+  }
+  return ST_OK;
+}
+
+}  // namespace st

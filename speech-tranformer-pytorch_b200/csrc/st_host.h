@@ -1,0 +1,53 @@
+// st_host.h — host-side plumbing shared by the launchers: error reporting across the C ABI and
+// TMA tensor-map construction (driver entry point resolved at run time; no libcuda link).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/st_b200.h"
+
+namespace st {
+
+// status codes (ST_OK, ST_ERR_*) come from the public header
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define ST_CHECK_CUDA(expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      st::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
+      return ST_ERR_CUDA;                                                                        \
+    }                                                                                                \
+  } while (0)
+
+#define ST_REQUIRE(cond, ...)              \
+  do {                                     \
+    if (!(cond)) {                         \
+      st::set_error(__VA_ARGS__);          \
+      return ST_ERR_INVALID;           \
+    }                                      \
+  } while (0)
+
+#define ST_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != ST_OK) return _s; \
+  } while (0)
+
+// Build a tiled tensor map over fp32 data with 128-byte swizzle.  dims/strides are innermost
+// first; strides_bytes[i] is the byte stride of dim i+1 (dim 0 is contiguous).  Out-of-bounds
+// elements are zero-filled.
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+int num_sms();
+
+// debug / tuning options (st_set_option over the C ABI); unknown names are rejected.
+int set_option(const char* name, int value);
+int get_option(const char* name);
+
+}  // namespace st

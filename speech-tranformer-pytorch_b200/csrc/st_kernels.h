@@ -1,0 +1,78 @@
+// st_kernels.h — internal C++ interface of the kernel launchers (everything below the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace st {
+
+// Inverted dropout with a stateless counter RNG: element idx is kept iff hash(seed, idx) >= thresh
+// and then scaled by `scale` = 1/(1-p).  thresh == 0 disables dropout.
+struct DropoutCfg {
+  uint32_t thresh = 0;
+  float scale = 1.f;
+  uint64_t seed = 0;
+};
+DropoutCfg make_dropout(float p, uint64_t seed);
+
+// ---- st_ln.cu
+int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float* gamma, const float* beta, float* out,
+               float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
+               const DropoutCfg& drop);
+int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd,
+               const float* gamma, float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
+               int round_out, const DropoutCfg& drop);
+int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols);
+int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, int cols, float* out);
+
+// ---- st_optim.cu
+int sumsq_add(cudaStream_t s, const float* x, int64_t n, float* out);
+int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+              float eps, int step, float max_norm, float gscale, const float* sumsq);
+
+// ---- st_lsce.cu
+struct LsceArgs {
+  const float* logits;   // (N, ldl)
+  int64_t ldl;
+  const int64_t* target; // (N,)  sparse mode, or nullptr
+  const float* q_dense;  // (N, V) dense soft target (CrossEntropyLoss mode), or nullptr
+  const float* one_hot;  // (V,)  base smoothed row (sparse mode)
+  const float* weight;   // (V,)
+  float confidence;
+  int64_t padding_idx;   // rows with target == padding_idx are zeroed when padding_idx >= 0
+  float inv_z;           // 1/N if size_average else 1
+  int64_t N;
+  int V;
+  float* row_loss;       // (N,) workspace
+  float* loss;           // scalar out
+  float* grad;           // (N, ldg) out, may be nullptr
+  int64_t ldg;
+};
+int lsce_fwd_bwd(cudaStream_t stream, const LsceArgs& a);
+
+// ---- st_attn.cu
+struct AttnArgs {
+  int B, H, Lq, Lk, dk;
+  const float* q; int64_t ldq;   // row (b*Lq + i) at q + row*ldq, head h at column h*dk
+  const float* k; int64_t ldk;
+  const float* v; int64_t ldv;
+  const uint8_t* mask;           // nullable; element (b,i,j) at mask[b*ms_b + i*ms_q + j*ms_k]; nonzero = masked
+  int64_t ms_b, ms_q, ms_k;
+  float scale;                   // 1/sqrt(dk)
+  DropoutCfg drop;               // dropout on the attention probabilities (Attention.py:89)
+  float* ctx; int64_t ldctx;     // (B*Lq, H*dk) merged heads
+  float* lse;                    // (B, H, Lq) natural-log sum-exp of the scaled, masked scores
+  float* attn;                   // nullable (B, H, Lq, Lk): post-dropout probabilities (return value of the module)
+};
+int attn_fwd(cudaStream_t stream, const AttnArgs& a);
+
+struct AttnBwdArgs {
+  AttnArgs f;                    // forward problem (q,k,v,mask,lse,ctx as produced by attn_fwd)
+  const float* dctx; int64_t lddctx;
+  float* delta;                  // (B, H, Lq) workspace: rowsum(dctx * ctx)
+  float* dq; int64_t lddq;       // same indexing as q/k/v
+  float* dk_; int64_t lddk;
+  float* dv; int64_t lddv;
+};
+int attn_bwd(cudaStream_t stream, const AttnBwdArgs& a);
+
+}  // namespace st

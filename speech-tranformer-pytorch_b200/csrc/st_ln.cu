@@ -1,0 +1,298 @@
+// st_ln.cu — HBM-bound row kernels: residual + LayerNorm forward/backward
+// (reference: `self.layernorm(output + v)` transformer/Attention.py:94 and
+// `self.dropout2(self.layernorm(inputs + ffn_output))` transformer/SubLayers.py:27),
+// TF32 rounding copies and column sums (bias gradients).
+//
+// One warp owns one row; every lane keeps its slice of the row in registers (float4 x VPL), so each
+// element is read once and written once.  Grids are persistent (a multiple of the SM count) and
+// stride over rows; per-column reductions stay in registers until the end of the kernel.
+#include "st_common.cuh"
+#include "st_host.h"
+#include "st_kernels.h"
+
+namespace st {
+
+namespace {
+
+constexpr int LN_THREADS = 256;
+constexpr int LN_WARPS = LN_THREADS / 32;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---------------------------------------------------------------- forward
+template <int VPL>
+__global__ void __launch_bounds__(LN_THREADS)
+add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float* __restrict__ out, float* __restrict__ z_out,
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int d, float eps,
+                  int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const float inv_d = 1.f / static_cast<float>(d);
+
+  float4 g[VPL], bt[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) { g[i] = ld4(gamma + c); bt[i] = ld4(beta + c); }
+  }
+
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp; row < rows;
+       row += static_cast<int64_t>(gridDim.x) * LN_WARPS) {
+    const float* ar = a + row * d;
+    const float* br = b ? b + row * d : nullptr;
+    float4 x[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        x[i] = ld4(ar + c);
+        if (br) {
+          const float4 y = ld4(br + c);
+          x[i].x += y.x; x[i].y += y.y; x[i].z += y.z; x[i].w += y.w;
+        }
+        s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+      }
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        const float d0 = x[i].x - mean, d1 = x[i].y - mean, d2 = x[i].z - mean, d3 = x[i].w - mean;
+        v += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(v) * inv_d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        if (z_out) st4(z_out + row * d + c, x[i]);
+        float o[4] = {(x[i].x - mean) * rstd * g[i].x + bt[i].x, (x[i].y - mean) * rstd * g[i].y + bt[i].y,
+                      (x[i].z - mean) * rstd * g[i].z + bt[i].z, (x[i].w - mean) * rstd * g[i].w + bt[i].w};
+        if (drop_thresh) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            o[t] = dropout_keep(drop_seed, static_cast<uint64_t>(row) * d + c + t, drop_thresh) ? o[t] * drop_scale : 0.f;
+        }
+        if (round_out) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o[t] = tf32_rna(o[t]);
+        }
+        st4(out + row * d + c, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat;  dbeta += dy;
+// dzsum += dz (the bias gradient of the linear layer that produced z).
+template <int VPL>
+__global__ void __launch_bounds__(LN_THREADS)
+add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
+                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dzsum, int64_t rows,
+                  int d, int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed) {
+  __shared__ float red[LN_WARPS][32 * 4 + 4];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const float inv_d = 1.f / static_cast<float>(d);
+
+  float4 g[VPL];
+  float4 acc_g[VPL], acc_b[VPL], acc_z[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    g[i] = (c < d) ? ld4(gamma + c) : make_float4(0, 0, 0, 0);
+    acc_g[i] = acc_b[i] = acc_z[i] = make_float4(0, 0, 0, 0);
+  }
+
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp; row < rows;
+       row += static_cast<int64_t>(gridDim.x) * LN_WARPS) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float4 xh[VPL], gy[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float4 dyv = ld4(dy + row * d + c);
+        if (drop_thresh) {
+          float* e = reinterpret_cast<float*>(&dyv);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            e[t] = dropout_keep(drop_seed, static_cast<uint64_t>(row) * d + c + t, drop_thresh) ? e[t] * drop_scale : 0.f;
+        }
+        const float4 zv = ld4(z + row * d + c);
+        xh[i] = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
+        gy[i] = make_float4(dyv.x * g[i].x, dyv.y * g[i].y, dyv.z * g[i].z, dyv.w * g[i].w);
+        s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+        s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+        acc_g[i].x += dyv.x * xh[i].x; acc_g[i].y += dyv.y * xh[i].y;
+        acc_g[i].z += dyv.z * xh[i].z; acc_g[i].w += dyv.w * xh[i].w;
+        acc_b[i].x += dyv.x; acc_b[i].y += dyv.y; acc_b[i].z += dyv.z; acc_b[i].w += dyv.w;
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d;
+    const float c2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float o[4] = {rstd * (gy[i].x - c1 - xh[i].x * c2), rstd * (gy[i].y - c1 - xh[i].y * c2),
+                      rstd * (gy[i].z - c1 - xh[i].z * c2), rstd * (gy[i].w - c1 - xh[i].w * c2)};
+        acc_z[i].x += o[0]; acc_z[i].y += o[1]; acc_z[i].z += o[2]; acc_z[i].w += o[3];
+        if (round_out) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o[t] = tf32_rna(o[t]);
+        }
+        st4(dz + row * d + c, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+  }
+
+  // block-level column reduction, then one atomic per column per block
+  auto reduce_store = [&](float4 (&acc)[VPL], float* dst) {
+    if (!dst) return;  // uniform across the block
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      __syncthreads();
+      red[warp][lane * 4 + 0] = acc[i].x; red[warp][lane * 4 + 1] = acc[i].y;
+      red[warp][lane * 4 + 2] = acc[i].z; red[warp][lane * 4 + 3] = acc[i].w;
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) s += red[w][threadIdx.x];
+        const int c = i * 128 + threadIdx.x;
+        if (c < d) atomicAdd(dst + c, s);
+      }
+    }
+  };
+  reduce_store(acc_g, dgamma);
+  reduce_store(acc_b, dbeta);
+  reduce_store(acc_z, dzsum);
+}
+
+// ---------------------------------------------------------------- TF32 rounding copy (2-D, strided)
+__global__ void __launch_bounds__(256)
+round_tf32_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
+                  int cols4) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols4;
+    const int c = static_cast<int>(i - r * cols4) * 4;
+    float4 v = ld4(src + r * lds + c);
+    v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+    st4(dst + r * ldd + c, v);
+  }
+}
+
+// ---------------------------------------------------------------- column sums: out[c] += sum_r X[r,c]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][132];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  float4 acc = make_float4(0, 0, 0, 0);
+  if (c < cols) {
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + warp; r < rows; r += static_cast<int64_t>(gridDim.y) * 8) {
+      const float4 v = ld4(x + r * ld + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  red[warp][lane * 4 + 0] = acc.x; red[warp][lane * 4 + 1] = acc.y;
+  red[warp][lane * 4 + 2] = acc.z; red[warp][lane * 4 + 3] = acc.w;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < cols) atomicAdd(out + cc, s);
+  }
+}
+
+int persistent_grid(int64_t work_blocks, int per_sm) {
+  const int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
+  return static_cast<int>(work_blocks < cap ? (work_blocks > 0 ? work_blocks : 1) : cap);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float* gamma, const float* beta, float* out,
+               float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
+               const DropoutCfg& drop) {
+  if (rows == 0) return ST_OK;
+  ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_fwd: d=%d must be a multiple of 4 and <= 1024", d);
+  ST_REQUIRE(aligned16(a) && (!b || aligned16(b)) && aligned16(gamma) && aligned16(beta) && aligned16(out) &&
+                 (!z_out || aligned16(z_out)),
+             "add_ln_fwd: pointers must be 16-byte aligned");
+  const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 8);
+#define ST_LAUNCH(VPL)                                                                                              \
+  add_ln_fwd_kernel<VPL><<<grid, LN_THREADS, 0, stream>>>(a, b, gamma, beta, out, z_out, mean_out, rstd_out, rows, \
+                                                          d, eps, round_out, drop.thresh, drop.scale, drop.seed)
+  if (d <= 128) ST_LAUNCH(1);
+  else if (d <= 256) ST_LAUNCH(2);
+  else if (d <= 512) ST_LAUNCH(4);
+  else ST_LAUNCH(8);
+#undef ST_LAUNCH
+  ST_CHECK_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd,
+               const float* gamma, float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
+               int round_out, const DropoutCfg& drop) {
+  if (rows == 0) return ST_OK;
+  ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_bwd: d=%d must be a multiple of 4 and <= 1024", d);
+  ST_REQUIRE(aligned16(dy) && aligned16(z) && aligned16(gamma) && aligned16(dz), "add_ln_bwd: pointers must be 16-byte aligned");
+  const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 4);
+#define ST_LAUNCH(VPL)                                                                                          \
+  add_ln_bwd_kernel<VPL><<<grid, LN_THREADS, 0, stream>>>(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum,  \
+                                                          rows, d, round_out, drop.thresh, drop.scale, drop.seed)
+  if (d <= 128) ST_LAUNCH(1);
+  else if (d <= 256) ST_LAUNCH(2);
+  else if (d <= 512) ST_LAUNCH(4);
+  else ST_LAUNCH(8);
+#undef ST_LAUNCH
+  ST_CHECK_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols) {
+  if (rows == 0 || cols == 0) return ST_OK;
+  ST_REQUIRE((cols & 3) == 0 && (lds & 3) == 0 && (ldd & 3) == 0 && aligned16(src) && aligned16(dst),
+             "round_tf32: cols/ld must be multiples of 4 and pointers 16-byte aligned (cols=%d)", cols);
+  const int64_t total = rows * (cols / 4);
+  const int grid = persistent_grid((total + 255) / 256, 16);
+  round_tf32_kernel<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, rows, cols / 4);
+  ST_CHECK_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, int cols, float* out) {
+  if (rows == 0 || cols == 0) return ST_OK;
+  ST_REQUIRE((cols & 3) == 0 && (ld & 3) == 0 && aligned16(x), "colsum: cols/ld must be multiples of 4 (cols=%d)", cols);
+  dim3 grid((cols + 127) / 128, 1);
+  int64_t ychunks = (rows + 63) / 64;
+  const int64_t cap = (static_cast<int64_t>(num_sms()) * 8 + grid.x - 1) / grid.x;
+  grid.y = static_cast<unsigned>(ychunks < cap ? ychunks : cap);
+  colsum_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, cols, out);
+  ST_CHECK_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+}  // namespace st

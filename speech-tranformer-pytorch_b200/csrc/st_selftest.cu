@@ -1,0 +1,239 @@
+// st_selftest.cu — device self-tests for the tcgen05 building blocks, callable over the C ABI
+// (st_selftest).  Each test builds inputs that are exactly representable in TF32, runs the device
+// path and compares with a double-precision host computation, so a wrong descriptor / swizzle /
+// TMEM lane mapping shows up as an O(1) error rather than hiding inside TF32 noise.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "st_common.cuh"
+#include "st_gemm.cuh"
+#include "st_host.h"
+#include "st_kernels.h"
+
+namespace st {
+
+namespace {
+
+float host_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & ~0x1FFFu;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+struct Lcg {
+  uint64_t s;
+  explicit Lcg(uint64_t seed) : s(seed * 2862933555777941757ull + 3037000493ull) {}
+  float next() {  // uniform in [-1, 1)
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    return static_cast<float>(static_cast<int32_t>(s >> 32)) * (1.0f / 2147483648.0f);
+  }
+};
+
+struct DevBuf {
+  float* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) { return cudaMalloc(&p, n * sizeof(float)) == cudaSuccess ? 0 : -1; }
+};
+
+// One GEMM case.  Returns max |dev - ref| / max|ref| through *err.
+int gemm_case(GemmMode mode, int M, int N, int K, int splits, bool bias, bool relu, int aux_mode, bool round_out,
+              double* err, int ldc_extra = 0, int max_ctas = 0) {
+  // logical A[M,K], B^T... build in the storage layout each mode expects
+  const int lda = (mode == GEMM_TN) ? ((M + 3) & ~3) + 4 : ((K + 3) & ~3) + 4;
+  const int ldb = (mode == GEMM_NT) ? ((K + 3) & ~3) + 4 : ((N + 3) & ~3) + 8;
+  const int ldc = N + ldc_extra;  // ldc_extra = 3 exercises the unaligned scalar store path
+  const int a_rows = (mode == GEMM_TN) ? K : M;
+  const int b_rows = (mode == GEMM_NT) ? N : K;
+  std::vector<float> hA(static_cast<size_t>(a_rows) * lda), hB(static_cast<size_t>(b_rows) * ldb);
+  std::vector<float> hbias(N), haux(static_cast<size_t>(M) * N), hC(static_cast<size_t>(M) * ldc, 0.f);
+  Lcg rng(1234 + M * 7 + N * 13 + K * 17 + static_cast<int>(mode));
+  for (auto& x : hA) x = host_tf32(rng.next());
+  for (auto& x : hB) x = host_tf32(rng.next());
+  for (auto& x : hbias) x = rng.next();
+  for (auto& x : haux) x = rng.next();
+  auto Aat = [&](int m, int k) { return mode == GEMM_TN ? hA[static_cast<size_t>(k) * lda + m] : hA[static_cast<size_t>(m) * lda + k]; };
+  auto Bat = [&](int n, int k) { return mode == GEMM_NT ? hB[static_cast<size_t>(n) * ldb + k] : hB[static_cast<size_t>(k) * ldb + n]; };
+
+  DevBuf dA, dB, dC, dbias, daux;
+  if (dA.alloc(hA.size()) || dB.alloc(hB.size()) || dC.alloc(hC.size()) || dbias.alloc(N) || daux.alloc(haux.size())) {
+    set_error("selftest: cudaMalloc failed");
+    return ST_ERR_CUDA;
+  }
+  ST_CHECK_CUDA(cudaMemcpy(dA.p, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
+  ST_CHECK_CUDA(cudaMemcpy(dB.p, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice));
+  ST_CHECK_CUDA(cudaMemcpy(dbias.p, hbias.data(), hbias.size() * 4, cudaMemcpyHostToDevice));
+  ST_CHECK_CUDA(cudaMemcpy(daux.p, haux.data(), haux.size() * 4, cudaMemcpyHostToDevice));
+  ST_CHECK_CUDA(cudaMemset(dC.p, 0, hC.size() * 4));
+
+  GemmEpilogue ep;
+  ep.bias = bias ? dbias.p : nullptr;
+  ep.relu = relu ? 1 : 0;
+  ep.aux = aux_mode ? daux.p : nullptr;
+  ep.ldaux = N;
+  ep.aux_mode = aux_mode;
+  ep.round_tf32 = round_out ? 1 : 0;
+  ep.atomic = splits > 1 ? 1 : 0;
+  set_option("gemm_max_ctas", max_ctas);
+  const int st = gemm_tf32(0, mode, dA.p, lda, dB.p, ldb, dC.p, ldc, M, N, K, ep, splits);
+  set_option("gemm_max_ctas", 0);
+  ST_TRY(st);
+  ST_CHECK_CUDA(cudaDeviceSynchronize());
+  ST_CHECK_CUDA(cudaMemcpy(hC.data(), dC.p, hC.size() * 4, cudaMemcpyDeviceToHost));
+
+  double max_ref = 0, max_err = 0;
+  for (int m = 0; m < M; ++m) {
+    for (int n = 0; n < N; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += static_cast<double>(Aat(m, k)) * static_cast<double>(Bat(n, k));
+      if (bias) acc += hbias[n];
+      if (relu) acc = acc > 0 ? acc : 0;
+      if (aux_mode == 1) acc += haux[static_cast<size_t>(m) * N + n];
+      if (aux_mode == 2) acc = haux[static_cast<size_t>(m) * N + n] > 0 ? acc : 0;
+      if (round_out) acc = host_tf32(static_cast<float>(acc));
+      const double got = hC[static_cast<size_t>(m) * ldc + n];
+      max_ref = fmax(max_ref, fabs(acc));
+      const double e = fabs(got - acc);
+      max_err = fmax(max_err, isnan(got) ? 1e30 : e);
+    }
+  }
+  *err = max_err / (max_ref > 0 ? max_ref : 1);
+  return ST_OK;
+}
+
+// ---- tcgen05.mma with the A operand in TMEM (.ts form) --------------------------------------
+// One CTA, 128 threads.  A[128, K] is written to TMEM by its owning lanes (tcgen05.st), B comes
+// from a TMA-loaded smem tile that is either K-major ([N, K] row-major in HBM) or MN-major
+// ([K, N] row-major in HBM).  D[128, N] is read back with tcgen05.ld.
+template <int N, int K, bool B_MN>
+__global__ void __launch_bounds__(128)
+ts_mma_test_kernel(const __grid_constant__ CUtensorMap tmap_b, const float* __restrict__ A, float* __restrict__ D) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  constexpr int TCOLS = 256;  // A at [0, K), D at [128, 128+N)
+  static_assert(K <= 128 && N <= 128, "test tile");
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_b, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar_b, N * K * 4);
+    if (!B_MN) {
+      for (int g = 0; g < K / 32; ++g) tma_load_2d(smem + g * (N * 128), &tmap_b, &bar_b, g * 32, 0);  // box {32 k, N}
+    } else {
+      for (int g = 0; g < N / 32; ++g) tma_load_2d(smem + g * (K * 128), &tmap_b, &bar_b, g * 32, 0);  // box {32 n, K}
+    }
+  }
+  // A row -> TMEM lane
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c = 0; c < K / 32; ++c) {
+    uint32_t r[32];
+    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(A[threadIdx.x * K + c * 32 + i]);
+    tmem_st32(lane_addr + c * 32, r);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    mbar_wait(&bar_b, 0);
+    constexpr uint32_t idesc = umma_idesc_tf32(128, N, false, B_MN);
+    const uint32_t sb = smem_u32(smem);
+    for (int k = 0; k < K / 8; ++k) {
+      const uint64_t bdesc = B_MN ? umma_desc_sw128(sb + k * 1024, K * 128, 1024)
+                                  : umma_desc_kmajor(sb + (k / 4) * (N * 128) + (k % 4) * 32);
+      umma_tf32_ts(tmem + 128, tmem + k * 8, bdesc, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c = 0; c < N / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(lane_addr + 128 + c * 32, r);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) D[threadIdx.x * N + c * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
+}
+
+template <int N, int K, bool B_MN>
+int ts_case(double* err) {
+  std::vector<float> hA(128 * K), hB(static_cast<size_t>(N) * K), hD(128 * N);
+  Lcg rng(99 + N + K + (B_MN ? 1000 : 0));
+  for (auto& x : hA) x = host_tf32(rng.next());
+  for (auto& x : hB) x = host_tf32(rng.next());  // K-major: [N][K];  MN-major: [K][N]
+  DevBuf dA, dB, dD;
+  if (dA.alloc(hA.size()) || dB.alloc(hB.size()) || dD.alloc(hD.size())) { set_error("selftest: cudaMalloc failed"); return ST_ERR_CUDA; }
+  ST_CHECK_CUDA(cudaMemcpy(dA.p, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice));
+  ST_CHECK_CUDA(cudaMemcpy(dB.p, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice));
+  CUtensorMap tb;
+  uint64_t dims[2], strides[1];
+  uint32_t box[2];
+  if (!B_MN) { dims[0] = K; dims[1] = N; strides[0] = K * 4; box[0] = 32; box[1] = N; }
+  else       { dims[0] = N; dims[1] = K; strides[0] = N * 4; box[0] = 32; box[1] = K; }
+  ST_TRY(make_tmap_f32(&tb, dB.p, 2, dims, strides, box));
+  auto kern = ts_mma_test_kernel<N, K, B_MN>;
+  const int smem = N * K * 4 + 1024;
+  ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<1, 128, smem>>>(tb, dA.p, dD.p);
+  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_CUDA(cudaDeviceSynchronize());
+  ST_CHECK_CUDA(cudaMemcpy(hD.data(), dD.p, hD.size() * 4, cudaMemcpyDeviceToHost));
+  double max_ref = 0, max_err = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k)
+        acc += static_cast<double>(hA[m * K + k]) * static_cast<double>(B_MN ? hB[static_cast<size_t>(k) * N + n] : hB[static_cast<size_t>(n) * K + k]);
+      const double got = hD[m * N + n];
+      max_ref = fmax(max_ref, fabs(acc));
+      max_err = fmax(max_err, isnan(got) ? 1e30 : fabs(got - acc));
+    }
+  *err = max_err / (max_ref > 0 ? max_ref : 1);
+  return ST_OK;
+}
+
+}  // namespace
+
+// which: 0..N-1 selects a case; returns status, writes the relative error.
+int selftest(int which, double* err) {
+  *err = -1.0;
+  switch (which) {
+    case 0:  return gemm_case(GEMM_NT, 128, 64, 32, 1, false, false, 0, false, err);    // single MMA k-block
+    case 1:  return gemm_case(GEMM_NT, 128, 256, 128, 1, false, false, 0, false, err);  // BN=256, 4 k-blocks
+    case 2:  return gemm_case(GEMM_NT, 384, 512, 512, 1, true, true, 0, true, err, 0, 2);  // 3 tiles per CTA + bias/relu/round
+    case 3:  return gemm_case(GEMM_NT, 200, 136, 72, 1, true, false, 1, false, err, 3); // ragged M/N/K + residual, unaligned ldc
+    case 4:  return gemm_case(GEMM_NN, 128, 64, 32, 1, false, false, 0, false, err);    // MN-major B, single block
+    case 5:  return gemm_case(GEMM_NN, 384, 512, 1536, 1, false, false, 2, true, err);  // dgrad shape + relu mask
+    case 6:  return gemm_case(GEMM_TN, 128, 64, 32, 1, false, false, 0, false, err);    // MN-major A and B
+    case 7:  return gemm_case(GEMM_TN, 512, 512, 4096, 4, false, false, 0, false, err, 0, 3); // wgrad, split-K atomics, 3 CTAs
+    case 8:  return gemm_case(GEMM_TN, 136, 200, 1000, 3, false, false, 0, false, err); // ragged wgrad
+    case 9:  return gemm_case(GEMM_NT, 20000, 512, 64, 1, true, false, 0, false, err);  // >1 tile per CTA at full grid
+    case 10: return ts_case<64, 32, false>(err);    // A in TMEM, B K-major
+    case 11: return ts_case<128, 64, false>(err);
+    case 12: return ts_case<64, 32, true>(err);     // A in TMEM, B MN-major
+    case 13: return ts_case<64, 128, true>(err);
+    case 14: return gemm_case(GEMM_NN, 300, 4340, 512, 1, false, false, 0, false, err); // wide N (vocab-like)
+    default: set_error("selftest: no case %d", which); return ST_ERR_INVALID;
+  }
+}
+
+int selftest_count() { return 15; }
+
+}  // namespace st
