@@ -130,6 +130,22 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 //            `lbo` bytes apart.  Both are exactly what a 128B-swizzled TMA box of 32 fp32 x R rows
 //            produces.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);        // [0,14)  start address >> 4
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;   // [16,30) leading byte offset >> 4
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;   // [32,46) stride byte offset >> 4
+  d |= static_cast<uint64_t>(1) << 46;                           // [46,48) descriptor version = 1 (sm_100)
+  d |= static_cast<uint64_t>(layout_type & 7) << 61;             // [61,64) 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+// MN-major TF32 operand: 32(MN) x 4(K) fp32 atoms (4 rows of 128 B, 32-byte chunks XOR row%4), K atoms 512 B apart,
+// 32-wide MN groups `lbo` bytes apart; one MMA (K = 8) spans two K atoms.  Matches TMA SWIZZLE_128B_ATOM_32B boxes
+// of 32 fp32 x R rows.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return umma_desc(smem_addr, lbo_bytes, 512, 1);
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);        // [0,14)  start address >> 4

@@ -7,7 +7,7 @@
 // Output tile 128 x BN (BN in {64,128,256}); K is consumed in blocks of 32 fp32 (= one 128-byte
 // swizzle atom); accumulators are double-buffered in TMEM (2*BN columns) so the epilogue of
 // tile i overlaps the main loop of tile i+1.  Operands may be K-major or MN-major (see
-// st_common.cuh), which covers forward (NT), data-gradient (NN) and weight-gradient (TN) GEMMs
+// st_common.cuh; MN-major TF32 tiles use the 32-byte-atom swizzle), which covers forward (NT), data-gradient (NN) and weight-gradient (TN) GEMMs
 // without any transposed copies in HBM.
 #include "st_common.cuh"
 #include "st_gemm.cuh"
@@ -142,8 +142,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < BK / 8; ++k) {
             // K-major: +32 B per MMA inside the 128 B swizzle row.  MN-major: next 8-row K atom (+1024 B);
             // 32-wide MN groups are 4096 B apart (one TMA box each).
-            const uint64_t adesc = A_MN ? umma_desc_sw128(sa + k * 1024, 4096, 1024) : umma_desc_kmajor(sa + k * 32);
-            const uint64_t bdesc = B_MN ? umma_desc_sw128(sb + k * 1024, 4096, 1024) : umma_desc_kmajor(sb + k * 32);
+            const uint64_t adesc = A_MN ? umma_desc_mnmajor(sa + k * 1024, 4096) : umma_desc_kmajor(sa + k * 32);
+            const uint64_t bdesc = B_MN ? umma_desc_mnmajor(sb + k * 1024, 4096) : umma_desc_kmajor(sb + k * 32);
             umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
@@ -322,14 +322,14 @@ int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, c
     uint32_t box[2];
     if (mode == GEMM_TN) { dims[0] = M; dims[1] = K; box[0] = 32; box[1] = 32; }
     else                 { dims[0] = K; dims[1] = M; box[0] = 32; box[1] = BM; }
-    ST_TRY(make_tmap_f32(&ta, A, 2, dims, strides, box));
+    ST_TRY(make_tmap_f32(&ta, A, 2, dims, strides, box, (mode == GEMM_TN) ? 1 : 0));
   }
   {
     uint64_t dims[2], strides[1] = {static_cast<uint64_t>(ldb) * 4};
     uint32_t box[2];
     if (mode == GEMM_NT) { dims[0] = K; dims[1] = N; box[0] = 32; box[1] = static_cast<uint32_t>(BN); }
     else                 { dims[0] = N; dims[1] = K; box[0] = 32; box[1] = 32; }
-    ST_TRY(make_tmap_f32(&tb, B, 2, dims, strides, box));
+    ST_TRY(make_tmap_f32(&tb, B, 2, dims, strides, box, (mode != GEMM_NT) ? 1 : 0));
   }
   switch (BN) {
     case 256: return dispatch_mode<256>(stream, mode, ta, tb, p);

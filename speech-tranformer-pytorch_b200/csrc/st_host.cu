@@ -56,7 +56,7 @@ int num_sms() {
 }
 
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+                  const uint32_t* box, int atom32) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -79,7 +79,8 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     if (i + 1 < rank) gstrides[i] = strides_bytes[i];
   }
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                      gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu] stride0 %llu box [%u,%u,%u] base %p",

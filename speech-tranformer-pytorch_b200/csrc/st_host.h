@@ -41,8 +41,10 @@ const char* last_error();
 // Build a tiled tensor map over fp32 data with 128-byte swizzle.  dims/strides are innermost
 // first; strides_bytes[i] is the byte stride of dim i+1 (dim 0 is contiguous).  Out-of-bounds
 // elements are zero-filled.
+// atom32: 0 = SWIZZLE_128B (16-byte chunks; K-major operands), 1 = SWIZZLE_128B_ATOM_32B (32-byte chunks; the only
+// layout tcgen05 accepts for MN-major TF32 operands, UMMA layout type SWIZZLE_128B_BASE32B).
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box);
+                  const uint32_t* box, int atom32 = 0);
 
 int num_sms();
 
