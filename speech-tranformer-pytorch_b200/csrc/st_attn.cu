@@ -1,14 +1,746 @@
-// st_attn.cu — placeholder until the tcgen05 attention kernels land (next commit).
+// st_attn.cu — fused multi-head attention core on tcgen05 (TF32 operands, fp32 accumulate).
+//
+// Reference: transformer/Attention.py:78-90 — split heads, scores = Q K^T / sqrt(d_k),
+// masked_fill_(mask, -inf), softmax, dropout, P V, merge heads — and its autograd backward.
+// The (B, h, Lq, Lk) score tensor the reference materialises (1 GB per layer at B=32, T=1000) never
+// leaves the SM here: S lives in TMEM, the softmax runs thread-per-row out of TMEM, P goes back to
+// TMEM as the A operand of the P·V MMA.
+//
+// Forward  : one CTA per (128-query tile, head, batch), flash-style online softmax over key tiles.
+// Backward : two kernels, no atomics —
+//   dKV : one CTA per (128-key tile, head, batch), loops over query tiles; S^T = K Q^T and
+//         dP^T = V dO^T are recomputed, dV += P^T dO and dK += dS^T Q accumulate in TMEM;
+//   dQ  : one CTA per (128-query tile, head, batch), loops over key tiles; dQ += dS K in TMEM.
+// A tile that is consumed both along d (K-major operand, 16-byte swizzle) and along the sequence
+// (MN-major operand, which for TF32 must use the 32-byte-atom swizzle) is fetched by two TMA loads.
+//
+// Thread t of the 128-thread CTA owns TMEM lane t = one row of the tile, so row max / row sum need
+// no shuffles.  Masks are arbitrary byte tensors with strides (stride 0 over queries for the
+// key-padding masks of Utils.py:41-57); masked => probability exactly 0; a fully masked row gives
+// NaN, as the reference does.
+#include <math.h>
+
+#include "st_common.cuh"
 #include "st_host.h"
 #include "st_kernels.h"
 
 namespace st {
-int attn_fwd(cudaStream_t, const AttnArgs&) {
-  set_error("attn_fwd: not built yet");
-  return ST_ERR_INVALID;
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnDev {
+  int B, H, Lq, Lk;
+  const uint8_t* mask;
+  int64_t ms_b, ms_q, ms_k;
+  float scale;        // 1/sqrt(dk)
+  float scale_log2;   // scale * log2(e)
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint64_t drop_seed;
+  float* ctx; int64_t ldctx;
+  float* lse2;        // (B,H,Lq) log2-domain log-sum-exp of the scaled masked scores
+  float* attn;
+  // backward
+  const float* delta;
+  float* dq; int64_t lddq;
+  float* dk; int64_t lddk;
+  float* dv; int64_t lddv;
+};
+
+// bit i set <=> (query row, key k0+i) is masked.  Keys beyond Lk are always masked.
+__device__ __forceinline__ uint32_t mask_bits_row(const AttnDev& p, int b, int row, bool row_ok, int k0) {
+  uint32_t bits = 0;
+  const int valid = p.Lk - k0;  // number of in-range keys in this 32-chunk (may be <= 0 or > 32)
+  if (valid < 32) bits = valid <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << valid);
+  if (p.mask != nullptr && row_ok && valid > 0) {
+    const uint8_t* m = p.mask + b * p.ms_b + static_cast<int64_t>(row) * p.ms_q + static_cast<int64_t>(k0) * p.ms_k;
+    if (p.ms_k == 1 && valid >= 32 && ((reinterpret_cast<uintptr_t>(m) & 3) == 0)) {
+      const uint32_t* m4 = reinterpret_cast<const uint32_t*>(m);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t v = m4[w];
+        bits |= ((v & 0x000000FFu) ? 1u : 0u) << (w * 4 + 0);
+        bits |= ((v & 0x0000FF00u) ? 1u : 0u) << (w * 4 + 1);
+        bits |= ((v & 0x00FF0000u) ? 1u : 0u) << (w * 4 + 2);
+        bits |= ((v & 0xFF000000u) ? 1u : 0u) << (w * 4 + 3);
+      }
+    } else {
+      const int n = valid < 32 ? valid : 32;
+      for (int i = 0; i < n; ++i) bits |= (m[static_cast<int64_t>(i) * p.ms_k] ? 1u : 0u) << i;
+    }
+  }
+  return bits;
 }
-int attn_bwd(cudaStream_t, const AttnBwdArgs&) {
-  set_error("attn_bwd: not built yet");
-  return ST_ERR_INVALID;
+
+// ================================================================================ forward
+template <int DK, int BKV>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnDev p) {
+  constexpr int BQ = 128;
+  constexpr int G = DK / 32;                // 32-column groups (one TMA box each)
+  constexpr int Q_BYTES = BQ * DK * 4;
+  constexpr int KV_BYTES = BKV * DK * 4;
+  constexpr uint32_t TCOLS = 256;           // S/P at [0,BKV), O at [BKV, BKV+DK)
+  static_assert(BKV + DK <= 256, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + KV_BYTES;
+  __shared__ uint64_t bar_q, bar_k, bar_v, bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int row = q0 + tid;
+  const bool row_ok = row < p.Lq;
+  const int n_kv = (p.Lk + BKV - 1) / BKV;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+    mbar_init(&bar_q, 1); mbar_init(&bar_k, 1); mbar_init(&bar_v, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t T_S = 0, T_O = BKV;
+
+  uint32_t k_loads = 0, s_count = 0;  // phase counters for bar_k / bar_s (thread 0 issues, all wait)
+
+  auto load_k = [&](int j) {
+    mbar_arrive_expect_tx(&bar_k, KV_BYTES);
+#pragma unroll
+    for (int g = 0; g < G; ++g) tma_load_3d(sK + g * (BKV * 128), &tmap_k, &bar_k, h * DK + g * 32, j * BKV, b);
+  };
+  auto load_v = [&](int j) {
+    mbar_arrive_expect_tx(&bar_v, KV_BYTES);
+#pragma unroll
+    for (int g = 0; g < G; ++g) tma_load_3d(sV + g * (BKV * 128), &tmap_v, &bar_v, h * DK + g * 32, j * BKV, b);
+  };
+  auto issue_s = [&]() {  // S = Q K^T  (both K-major)
+    constexpr uint32_t idesc = umma_idesc_tf32(128, BKV, false, false);
+    const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK);
+#pragma unroll
+    for (int ks = 0; ks < DK / 8; ++ks)
+      umma_tf32_ss(tmem + T_S, umma_desc_kmajor(aq + (ks / 4) * (BQ * 128) + (ks % 4) * 32),
+                   umma_desc_kmajor(bk + (ks / 4) * (BKV * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+    umma_commit(&bar_s);
+  };
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_q, Q_BYTES);
+#pragma unroll
+    for (int g = 0; g < G; ++g) tma_load_3d(sQ + g * (BQ * 128), &tmap_q, &bar_q, h * DK + g * 32, q0, b);
+    load_k(0);
+    load_v(0);
+    mbar_wait(&bar_q, 0);
+    mbar_wait(&bar_k, 0);
+    tc_fence_after();
+    issue_s();
+  }
+  k_loads = 1;
+
+  float o[DK];
+#pragma unroll
+  for (int i = 0; i < DK; ++i) o[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  const uint64_t rng_row = (static_cast<uint64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
+
+  for (int j = 0; j < n_kv; ++j) {
+    mbar_wait(&bar_s, s_count & 1);
+    ++s_count;
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_kv) load_k(j + 1);  // S_j has consumed K_j
+
+    // ---- pass 1: row max over this tile
+    uint32_t mbits[BKV / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < BKV / 32; ++c) {
+      mbits[c] = mask_bits_row(p, b, row, row_ok, j * BKV + c * 32);
+      uint32_t r[32];
+      tmem_ld32(t_lane + T_S + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (!((mbits[c] >> i) & 1u)) mx = fmaxf(mx, __uint_as_float(r[i]) * p.scale_log2);
+    }
+    const float m_new = fmaxf(m_run, mx);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = exp2f(m_run - m_use);  // m_run == -inf -> 0
+    // ---- pass 2: probabilities -> TMEM (A operand of P·V), row sum
+    float l_tile = 0.f;
+#pragma unroll
+    for (int c = 0; c < BKV / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(t_lane + T_S + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float pv = ((mbits[c] >> i) & 1u) ? 0.f : exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_use);
+        l_tile += pv;
+        if (p.drop_thresh) {
+          const uint64_t idx = rng_row * p.Lk + (j * BKV + c * 32 + i);
+          pv = dropout_keep(p.drop_seed, idx, p.drop_thresh) ? pv * p.drop_scale : 0.f;
+        }
+        r[i] = __float_as_uint(tf32_rna(pv));
+      }
+      tmem_st32(t_lane + T_S + c * 32, r);
+    }
+    l_run = l_run * alpha + l_tile;
+    m_run = m_new;
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+
+    if (tid == 0) {  // O_tile = P V   (A = P in TMEM, B = V MN-major)
+      tc_fence_after();
+      mbar_wait(&bar_v, j & 1);
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+      const uint32_t bv = smem_u32(sV);
+#pragma unroll
+      for (int ks = 0; ks < BKV / 8; ++ks)
+        umma_tf32_ts(tmem + T_O, tmem + T_S + ks * 8, umma_desc_mnmajor(bv + ks * 1024, BKV * 128), idesc,
+                     ks > 0 ? 1u : 0u);
+      umma_commit(&bar_o);
+    }
+    mbar_wait(&bar_o, j & 1);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_kv) {
+      load_v(j + 1);                       // P·V has consumed V_j
+      mbar_wait(&bar_k, k_loads & 1);      // K_{j+1}
+      tc_fence_after();
+      issue_s();                           // overlaps the O accumulation below
+    }
+    if (j + 1 < n_kv) ++k_loads;
+    // ---- O += alpha-corrected accumulate in registers
+#pragma unroll
+    for (int c = 0; c < DK / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(t_lane + T_O + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+    }
+  }
+
+  // ---- finalize: ctx = O / l (NaN for a fully masked row: 0 * inf), lse
+  const float inv_l = 1.f / l_run;
+  const float lse2 = m_run + log2f(l_run);
+  if (row_ok) {
+    float* dst = p.ctx + (static_cast<int64_t>(b) * p.Lq + row) * p.ldctx + h * DK;
+#pragma unroll
+    for (int i = 0; i < DK; i += 4)
+      *reinterpret_cast<float4*>(dst + i) = make_float4(tf32_rna(o[i] * inv_l), tf32_rna(o[i + 1] * inv_l),
+                                                        tf32_rna(o[i + 2] * inv_l), tf32_rna(o[i + 3] * inv_l));
+    p.lse2[(static_cast<int64_t>(b) * p.H + h) * p.Lq + row] = lse2;
+  }
+
+  // ---- optional second sweep: materialise the (post-dropout) probabilities the module returns
+  if (p.attn != nullptr) {
+    for (int j = 0; j < n_kv; ++j) {
+      tc_fence_before();
+      __syncthreads();  // every thread is done with the S region / previous sweep step
+      if (tid == 0) {
+        tc_fence_after();
+        load_k(j);
+        mbar_wait(&bar_k, k_loads & 1);
+        tc_fence_after();
+        issue_s();
+      }
+      ++k_loads;
+      mbar_wait(&bar_s, s_count & 1);
+      ++s_count;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        const int k0 = j * BKV + c * 32;
+        const uint32_t mb = mask_bits_row(p, b, row, row_ok, k0);
+        uint32_t r[32];
+        tmem_ld32(t_lane + T_S + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* dst = p.attn + ((static_cast<int64_t>(b) * p.H + h) * p.Lq + row) * p.Lk + k0;
+          for (int i = 0; i < 32; ++i) {
+            if (k0 + i >= p.Lk) break;
+            float pv = ((mb >> i) & 1u) ? 0.f : exp2f(__uint_as_float(r[i]) * p.scale_log2 - lse2);
+            if (l_run == 0.f) pv = __int_as_float(0x7fc00000);  // fully masked row: NaN like softmax(-inf row)
+            if (p.drop_thresh) {
+              const uint64_t idx = rng_row * p.Lk + (k0 + i);
+              pv = dropout_keep(p.drop_seed, idx, p.drop_thresh) ? pv * p.drop_scale : 0.f;
+            }
+            dst[i] = pv;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
 }
+
+// ================================================================================ delta = rowsum(dO * O) per head
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const float* __restrict__ dctx, int64_t lddctx, const float* __restrict__ ctx, int64_t ldctx,
+                  float* __restrict__ delta, int B, int H, int Lq, int dk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = static_cast<int64_t>(B) * Lq;
+  const int d = H * dk;
+  const int grp = dk / 4;  // lanes per head within a 128-column chunk (8, 16 or 32)
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < rows;
+       row += static_cast<int64_t>(gridDim.x) * 8) {
+    const int b = static_cast<int>(row / Lq), q = static_cast<int>(row - static_cast<int64_t>(b) * Lq);
+    for (int c0 = 0; c0 < d; c0 += 128) {
+      const int c = c0 + lane * 4;
+      float s = 0.f;
+      if (c < d) {
+        const float4 a = *reinterpret_cast<const float4*>(dctx + row * lddctx + c);
+        const float4 o = *reinterpret_cast<const float4*>(ctx + row * ldctx + c);
+        s = (a.x * o.x + a.y * o.y) + (a.z * o.z + a.w * o.w);
+      }
+      for (int off = 1; off < grp; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (c < d && (lane % grp) == 0) delta[(static_cast<int64_t>(b) * H + c / dk) * Lq + q] = s;
+    }
+  }
+}
+
+// ================================================================================ backward: dK, dV
+template <int DK, int BQ>
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                    const __grid_constant__ CUtensorMap tmap_q_k, const __grid_constant__ CUtensorMap tmap_q_mn,
+                    const __grid_constant__ CUtensorMap tmap_do_k, const __grid_constant__ CUtensorMap tmap_do_mn,
+                    const AttnDev p) {
+  constexpr int BKV = 128;
+  constexpr int G = DK / 32;
+  constexpr int KV_BYTES = BKV * DK * 4;
+  constexpr int QT_BYTES = BQ * DK * 4;
+  constexpr uint32_t TCOLS = 512;
+  constexpr uint32_t T_ST = 0, T_DPT = BQ, T_DV = 2 * BQ, T_DK = 2 * BQ + DK;
+  static_assert(2 * BQ + 2 * DK <= 512, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sQk = sV + KV_BYTES;
+  uint8_t* sQm = sQk + QT_BYTES;
+  uint8_t* sDOk = sQm + QT_BYTES;
+  uint8_t* sDOm = sDOk + QT_BYTES;
+  __shared__ uint64_t bar_kv, bar_ld, bar_s, bar_acc;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_lse[BQ], s_delta[BQ];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+  const int key = kv0 + tid;
+  const bool key_ok = key < p.Lk;
+  const int n_q = (p.Lq + BQ - 1) / BQ;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_q_k);
+    tma_prefetch_desc(&tmap_q_mn); tma_prefetch_desc(&tmap_do_k); tma_prefetch_desc(&tmap_do_mn);
+    mbar_init(&bar_kv, 1); mbar_init(&bar_ld, 1); mbar_init(&bar_s, 1); mbar_init(&bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_kv, 2 * KV_BYTES);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      tma_load_3d(sK + g * (BKV * 128), &tmap_k, &bar_kv, h * DK + g * 32, kv0, b);
+      tma_load_3d(sV + g * (BKV * 128), &tmap_v, &bar_kv, h * DK + g * 32, kv0, b);
+    }
+  }
+  // key-padding masks (stride 0 over queries) are a per-thread constant
+  const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
+  bool key_masked = !key_ok;
+  if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
+  const bool mask_dense = (p.mask != nullptr) && !mask_per_key;
+
+  for (int it = 0; it < n_q; ++it) {
+    const int q0 = it * BQ;
+    if (tid == 0) {
+      if (it > 0) { mbar_wait(&bar_acc, (it - 1) & 1); tc_fence_after(); }  // previous MMAs done with Q/dO tiles
+      mbar_arrive_expect_tx(&bar_ld, 4 * QT_BYTES);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        tma_load_3d(sQk + g * (BQ * 128), &tmap_q_k, &bar_ld, h * DK + g * 32, q0, b);
+        tma_load_3d(sQm + g * (BQ * 128), &tmap_q_mn, &bar_ld, h * DK + g * 32, q0, b);
+        tma_load_3d(sDOk + g * (BQ * 128), &tmap_do_k, &bar_ld, h * DK + g * 32, q0, b);
+        tma_load_3d(sDOm + g * (BQ * 128), &tmap_do_mn, &bar_ld, h * DK + g * 32, q0, b);
+      }
+    }
+    if (tid < BQ) {
+      const int q = q0 + tid;
+      const int64_t o = (static_cast<int64_t>(b) * p.H + h) * p.Lq + q;
+      s_lse[tid] = q < p.Lq ? p.lse2[o] : INFINITY;  // +inf => probability 0 for padded query rows
+      s_delta[tid] = q < p.Lq ? p.delta[o] : 0.f;
+    }
+    if (tid == 0) {
+      if (it == 0) mbar_wait(&bar_kv, 0);
+      mbar_wait(&bar_ld, it & 1);
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_tf32(128, BQ, false, false);
+      const uint32_t ak = smem_u32(sK), av = smem_u32(sV), bq = smem_u32(sQk), bdo = smem_u32(sDOk);
+#pragma unroll
+      for (int ks = 0; ks < DK / 8; ++ks)  // S^T = K Q^T
+        umma_tf32_ss(tmem + T_ST, umma_desc_kmajor(ak + (ks / 4) * (BKV * 128) + (ks % 4) * 32),
+                     umma_desc_kmajor(bq + (ks / 4) * (BQ * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < DK / 8; ++ks)  // dP^T = V dO^T
+        umma_tf32_ss(tmem + T_DPT, umma_desc_kmajor(av + (ks / 4) * (BKV * 128) + (ks % 4) * 32),
+                     umma_desc_kmajor(bdo + (ks / 4) * (BQ * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+      umma_commit(&bar_s);
+    }
+    __syncthreads();  // s_lse / s_delta visible
+    mbar_wait(&bar_s, it & 1);
+    tc_fence_after();
+
+#pragma unroll 1
+    for (int c = 0; c < BQ / 32; ++c) {
+      uint32_t rs[32], rd[32];
+      tmem_ld32(t_lane + T_ST + c * 32, rs);
+      tmem_ld32(t_lane + T_DPT + c * 32, rd);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int qi = c * 32 + i;
+        const int q = q0 + qi;
+        bool masked = key_masked;
+        if (mask_dense && key_ok && q < p.Lq)
+          masked = p.mask[b * p.ms_b + static_cast<int64_t>(q) * p.ms_q + static_cast<int64_t>(key) * p.ms_k] != 0;
+        float pr = masked ? 0.f : exp2f(__uint_as_float(rs[i]) * p.scale_log2 - s_lse[qi]);
+        float dp = __uint_as_float(rd[i]);
+        float pd = pr;
+        if (p.drop_thresh) {
+          const uint64_t idx = ((static_cast<uint64_t>(b) * p.H + h) * p.Lq + (q < p.Lq ? q : 0)) * p.Lk + (key_ok ? key : 0);
+          const bool keep = dropout_keep(p.drop_seed, idx, p.drop_thresh);
+          pd = keep ? pr * p.drop_scale : 0.f;
+          dp = keep ? dp * p.drop_scale : 0.f;
+        }
+        const float ds = pr * (dp - s_delta[qi]) * p.scale;
+        rs[i] = __float_as_uint(tf32_rna(pd));
+        rd[i] = __float_as_uint(tf32_rna(ds));
+      }
+      tmem_st32(t_lane + T_ST + c * 32, rs);
+      tmem_st32(t_lane + T_DPT + c * 32, rd);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+      const uint32_t bdo = smem_u32(sDOm), bq = smem_u32(sQm);
+#pragma unroll
+      for (int ks = 0; ks < BQ / 8; ++ks)  // dV += P^T dO
+        umma_tf32_ts(tmem + T_DV, tmem + T_ST + ks * 8, umma_desc_mnmajor(bdo + ks * 1024, BQ * 128), idesc,
+                     (it > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < BQ / 8; ++ks)  // dK += dS^T Q
+        umma_tf32_ts(tmem + T_DK, tmem + T_DPT + ks * 8, umma_desc_mnmajor(bq + ks * 1024, BQ * 128), idesc,
+                     (it > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&bar_acc);
+    }
+  }
+  mbar_wait(&bar_acc, (n_q - 1) & 1);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < DK / 32; ++c) {
+    uint32_t rv[32], rk[32];
+    tmem_ld32(t_lane + T_DV + c * 32, rv);
+    tmem_ld32(t_lane + T_DK + c * 32, rk);
+    tmem_ld_wait();
+    if (key_ok) {
+      float* dvp = p.dv + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + c * 32;
+      float* dkp = p.dk + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + c * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        *reinterpret_cast<float4*>(dvp + i) =
+            make_float4(tf32_rna(__uint_as_float(rv[i])), tf32_rna(__uint_as_float(rv[i + 1])),
+                        tf32_rna(__uint_as_float(rv[i + 2])), tf32_rna(__uint_as_float(rv[i + 3])));
+        *reinterpret_cast<float4*>(dkp + i) =
+            make_float4(tf32_rna(__uint_as_float(rk[i])), tf32_rna(__uint_as_float(rk[i + 1])),
+                        tf32_rna(__uint_as_float(rk[i + 2])), tf32_rna(__uint_as_float(rk[i + 3])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
+}
+
+// ================================================================================ backward: dQ
+template <int DK, int BKV>
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                   const __grid_constant__ CUtensorMap tmap_k_k, const __grid_constant__ CUtensorMap tmap_k_mn,
+                   const __grid_constant__ CUtensorMap tmap_v_k, const AttnDev p) {
+  constexpr int BQ = 128;
+  constexpr int G = DK / 32;
+  constexpr int Q_BYTES = BQ * DK * 4;
+  constexpr int KT_BYTES = BKV * DK * 4;
+  constexpr uint32_t TCOLS = 512;
+  constexpr uint32_t T_S = 0, T_DP = BKV, T_DQ = 2 * BKV;
+  static_assert(2 * BKV + DK <= 512, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sDO = sQ + Q_BYTES;
+  uint8_t* sKk = sDO + Q_BYTES;
+  uint8_t* sKm = sKk + KT_BYTES;
+  uint8_t* sVk = sKm + KT_BYTES;
+  __shared__ uint64_t bar_q, bar_ld, bar_s, bar_acc;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int row = q0 + tid;
+  const bool row_ok = row < p.Lq;
+  const int n_kv = (p.Lk + BKV - 1) / BKV;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k_k);
+    tma_prefetch_desc(&tmap_k_mn); tma_prefetch_desc(&tmap_v_k);
+    mbar_init(&bar_q, 1); mbar_init(&bar_ld, 1); mbar_init(&bar_s, 1); mbar_init(&bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_q, 2 * Q_BYTES);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      tma_load_3d(sQ + g * (BQ * 128), &tmap_q, &bar_q, h * DK + g * 32, q0, b);
+      tma_load_3d(sDO + g * (BQ * 128), &tmap_do, &bar_q, h * DK + g * 32, q0, b);
+    }
+  }
+  const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
+  const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
+  const float delta = row_ok ? p.delta[stat] : 0.f;
+
+  for (int j = 0; j < n_kv; ++j) {
+    if (tid == 0) {
+      if (j > 0) { mbar_wait(&bar_acc, (j - 1) & 1); tc_fence_after(); }
+      mbar_arrive_expect_tx(&bar_ld, 3 * KT_BYTES);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        tma_load_3d(sKk + g * (BKV * 128), &tmap_k_k, &bar_ld, h * DK + g * 32, j * BKV, b);
+        tma_load_3d(sKm + g * (BKV * 128), &tmap_k_mn, &bar_ld, h * DK + g * 32, j * BKV, b);
+        tma_load_3d(sVk + g * (BKV * 128), &tmap_v_k, &bar_ld, h * DK + g * 32, j * BKV, b);
+      }
+      if (j == 0) mbar_wait(&bar_q, 0);
+      mbar_wait(&bar_ld, j & 1);
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_tf32(128, BKV, false, false);
+      const uint32_t aq = smem_u32(sQ), ado = smem_u32(sDO), bk = smem_u32(sKk), bv = smem_u32(sVk);
+#pragma unroll
+      for (int ks = 0; ks < DK / 8; ++ks)  // S = Q K^T
+        umma_tf32_ss(tmem + T_S, umma_desc_kmajor(aq + (ks / 4) * (BQ * 128) + (ks % 4) * 32),
+                     umma_desc_kmajor(bk + (ks / 4) * (BKV * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < DK / 8; ++ks)  // dP = dO V^T
+        umma_tf32_ss(tmem + T_DP, umma_desc_kmajor(ado + (ks / 4) * (BQ * 128) + (ks % 4) * 32),
+                     umma_desc_kmajor(bv + (ks / 4) * (BKV * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+      umma_commit(&bar_s);
+    }
+    mbar_wait(&bar_s, j & 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BKV / 32; ++c) {
+      const int k0 = j * BKV + c * 32;
+      const uint32_t mb = mask_bits_row(p, b, row, row_ok, k0);
+      uint32_t rs[32], rd[32];
+      tmem_ld32(t_lane + T_S + c * 32, rs);
+      tmem_ld32(t_lane + T_DP + c * 32, rd);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float pr = ((mb >> i) & 1u) ? 0.f : exp2f(__uint_as_float(rs[i]) * p.scale_log2 - lse2);
+        float dp = __uint_as_float(rd[i]);
+        if (p.drop_thresh) {
+          const uint64_t idx = static_cast<uint64_t>(stat) * p.Lk + (k0 + i < p.Lk ? k0 + i : 0);
+          dp = dropout_keep(p.drop_seed, idx, p.drop_thresh) ? dp * p.drop_scale : 0.f;
+        }
+        rd[i] = __float_as_uint(tf32_rna(pr * (dp - delta) * p.scale));
+      }
+      tmem_st32(t_lane + T_DP + c * 32, rd);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {  // dQ += dS K   (A = dS in TMEM, B = K MN-major)
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+      const uint32_t bk = smem_u32(sKm);
+#pragma unroll
+      for (int ks = 0; ks < BKV / 8; ++ks)
+        umma_tf32_ts(tmem + T_DQ, tmem + T_DP + ks * 8, umma_desc_mnmajor(bk + ks * 1024, BKV * 128), idesc,
+                     (j > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&bar_acc);
+    }
+  }
+  mbar_wait(&bar_acc, (n_kv - 1) & 1);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < DK / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_lane + T_DQ + c * 32, r);
+    tmem_ld_wait();
+    if (row_ok) {
+      float* dst = p.dq + (static_cast<int64_t>(b) * p.Lq + row) * p.lddq + h * DK + c * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(dst + i) =
+            make_float4(tf32_rna(__uint_as_float(r[i])), tf32_rna(__uint_as_float(r[i + 1])),
+                        tf32_rna(__uint_as_float(r[i + 2])), tf32_rna(__uint_as_float(r[i + 3])));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
+}
+
+// ================================================================================ host side
+// 3-D tensor map over a (B, L, H*dk) activation addressed as rows of `ld` floats: dims {H*dk, L, B}.
+int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 4, static_cast<uint64_t>(L) * static_cast<uint64_t>(ld) * 4};
+  const uint32_t box[3] = {32, static_cast<uint32_t>(box_rows), 1};
+  return make_tmap_f32(m, base, 3, dims, strides, box, atom32);
+}
+
+int check_attn(const AttnArgs& a, const char* who) {
+  ST_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "%s: empty problem", who);
+  ST_REQUIRE(a.dk == 32 || a.dk == 64 || a.dk == 128, "%s: d_k must be 32, 64 or 128 (got %d)", who, a.dk);
+  ST_REQUIRE((a.ldq & 3) == 0 && (a.ldk & 3) == 0 && (a.ldv & 3) == 0 && (a.ldctx & 3) == 0,
+             "%s: leading dimensions must be multiples of 4", who);
+  ST_REQUIRE(((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
+               reinterpret_cast<uintptr_t>(a.ctx)) & 15) == 0, "%s: pointers must be 16-byte aligned", who);
+  return ST_OK;
+}
+
+AttnDev to_dev(const AttnArgs& a) {
+  AttnDev p{};
+  p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk;
+  p.mask = a.mask; p.ms_b = a.ms_b; p.ms_q = a.ms_q; p.ms_k = a.ms_k;
+  p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
+  p.drop_thresh = a.drop.thresh; p.drop_scale = a.drop.scale; p.drop_seed = a.drop.seed;
+  p.ctx = a.ctx; p.ldctx = a.ldctx; p.lse2 = a.lse; p.attn = a.attn;
+  return p;
+}
+
+template <int DK, int BKV>
+int launch_fwd(cudaStream_t s, const AttnArgs& a) {
+  CUtensorMap tq, tk, tv;
+  const int cols = a.H * DK;
+  ST_TRY(make_act_tmap(&tq, a.q, a.ldq, cols, a.Lq, a.B, 128, 0));
+  ST_TRY(make_act_tmap(&tk, a.k, a.ldk, cols, a.Lk, a.B, BKV, 0));
+  ST_TRY(make_act_tmap(&tv, a.v, a.ldv, cols, a.Lk, a.B, BKV, 1));
+  constexpr int SMEM = 128 * DK * 4 + 2 * BKV * DK * 4 + 1024;
+  auto kern = attn_fwd_kernel<DK, BKV>;
+  static bool attr = false;
+  if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+  dim3 grid((a.Lq + 127) / 128, a.H, a.B);
+  kern<<<grid, 128, SMEM, s>>>(tq, tk, tv, to_dev(a));
+  ST_CHECK_CUDA(cudaGetLastError());
+  return ST_OK;
+}
+
+template <int DK, int BQ, int BKV>
+int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
+  const AttnArgs& f = a.f;
+  const int cols = f.H * DK;
+  AttnDev p = to_dev(f);
+  p.delta = a.delta; p.dq = a.dq; p.lddq = a.lddq; p.dk = a.dk_; p.lddk = a.lddk; p.dv = a.dv; p.lddv = a.lddv;
+  {
+    const int64_t rows = static_cast<int64_t>(f.B) * f.Lq;
+    const int64_t blocks = (rows + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+    attn_delta_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(a.dctx, a.lddctx, f.ctx, f.ldctx,
+                                                                                    a.delta, f.B, f.H, f.Lq, DK);
+    ST_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    CUtensorMap tk, tv, tqk, tqm, tdk, tdm;
+    ST_TRY(make_act_tmap(&tk, f.k, f.ldk, cols, f.Lk, f.B, 128, 0));
+    ST_TRY(make_act_tmap(&tv, f.v, f.ldv, cols, f.Lk, f.B, 128, 0));
+    ST_TRY(make_act_tmap(&tqk, f.q, f.ldq, cols, f.Lq, f.B, BQ, 0));
+    ST_TRY(make_act_tmap(&tqm, f.q, f.ldq, cols, f.Lq, f.B, BQ, 1));
+    ST_TRY(make_act_tmap(&tdk, a.dctx, a.lddctx, cols, f.Lq, f.B, BQ, 0));
+    ST_TRY(make_act_tmap(&tdm, a.dctx, a.lddctx, cols, f.Lq, f.B, BQ, 1));
+    constexpr int SMEM = 2 * 128 * DK * 4 + 4 * BQ * DK * 4 + 1024;
+    auto kern = attn_bwd_dkv_kernel<DK, BQ>;
+    static bool attr = false;
+    if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+    dim3 grid((f.Lk + 127) / 128, f.H, f.B);
+    kern<<<grid, 128, SMEM, s>>>(tk, tv, tqk, tqm, tdk, tdm, p);
+    ST_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    CUtensorMap tq, tdo, tkk, tkm, tvk;
+    ST_TRY(make_act_tmap(&tq, f.q, f.ldq, cols, f.Lq, f.B, 128, 0));
+    ST_TRY(make_act_tmap(&tdo, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0));
+    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BKV, 0));
+    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BKV, 1));
+    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BKV, 0));
+    constexpr int SMEM = 2 * 128 * DK * 4 + 3 * BKV * DK * 4 + 1024;
+    auto kern = attn_bwd_dq_kernel<DK, BKV>;
+    static bool attr = false;
+    if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+    dim3 grid((f.Lq + 127) / 128, f.H, f.B);
+    kern<<<grid, 128, SMEM, s>>>(tq, tdo, tkk, tkm, tvk, p);
+    ST_CHECK_CUDA(cudaGetLastError());
+  }
+  return ST_OK;
+}
+
+}  // namespace
+
+int attn_fwd(cudaStream_t s, const AttnArgs& a) {
+  ST_TRY(check_attn(a, "attn_fwd"));
+  ST_REQUIRE(a.lse != nullptr, "attn_fwd: lse buffer is required");
+  switch (a.dk) {
+    case 32: return launch_fwd<32, 128>(s, a);
+    case 64: return launch_fwd<64, 128>(s, a);
+    default: return launch_fwd<128, 64>(s, a);
+  }
+}
+
+int attn_bwd(cudaStream_t s, const AttnBwdArgs& a) {
+  ST_TRY(check_attn(a.f, "attn_bwd"));
+  ST_REQUIRE(a.dctx && a.delta && a.dq && a.dk_ && a.dv && a.f.lse, "attn_bwd: null buffer");
+  ST_REQUIRE((a.lddctx & 3) == 0 && (a.lddq & 3) == 0 && (a.lddk & 3) == 0 && (a.lddv & 3) == 0,
+             "attn_bwd: leading dimensions must be multiples of 4");
+  switch (a.f.dk) {
+    case 32: return launch_bwd<32, 128, 128>(s, a);
+    case 64: return launch_bwd<64, 128, 128>(s, a);
+    default: return launch_bwd<128, 32, 32>(s, a);
+  }
+}
+
 }  // namespace st

@@ -1,0 +1,436 @@
+"""torch-facing wrappers over the C ABI (include/st_b200.h): raw-pointer plumbing and autograd.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every kernel that runs is
+from libst_b200.so.  Nothing here falls back to a PyTorch implementation: CPU tensors, non-fp32
+tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import StError, check
+
+__all__ = ["add_layer_norm", "multi_head_attention", "positionwise_ffn", "label_smoothing_ce", "soft_target_ce",
+           "attention_core", "linear_tf32", "round_tf32", "is_tf32_clean", "mark_tf32_clean", "next_seed"]
+
+
+# ------------------------------------------------------------------------------------------------
+# plumbing
+# ------------------------------------------------------------------------------------------------
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor — the B200 hot path has no CPU fallback")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_device_ok = set()
+
+
+def _lib_for(t: torch.Tensor):
+    lib = _lib.load()
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if dev not in _device_ok:
+        check(lib.st_device_check(dev))
+        _device_ok.add(dev)
+    return lib
+
+
+_TF32_TAG = "_st_tf32_clean"
+
+
+def is_tf32_clean(t: torch.Tensor) -> bool:
+    """True if `t` was produced by this library already rounded to TF32 (so no rounding copy is needed)."""
+    return bool(getattr(t, _TF32_TAG, False))
+
+
+def mark_tf32_clean(t: torch.Tensor) -> torch.Tensor:
+    setattr(t, _TF32_TAG, True)
+    return t
+
+
+_seed_state = [0]
+
+
+def next_seed() -> int:
+    """A fresh 63-bit dropout seed derived from torch's CPU generator (reproducible under manual_seed)."""
+    _seed_state[0] += 1
+    base = int(torch.empty((), dtype=torch.int64).random_().item())
+    return (base ^ (_seed_state[0] * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
+
+
+def _same(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride())
+
+
+def _mask_args(mask: Optional[torch.Tensor], B: int, Lq: int, Lk: int, device) -> Tuple[Optional[torch.Tensor], int, int, int]:
+    """Accept bool or uint8, any strides (stride-0 broadcast views are NOT materialised)."""
+    if mask is None:
+        return None, 0, 0, 0
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    elif mask.dtype != torch.uint8:
+        raise RuntimeError(f"mask: expected bool or uint8, got {mask.dtype}")
+    if tuple(mask.shape) != (B, Lq, Lk):
+        raise RuntimeError(f"mask: expected shape {(B, Lq, Lk)}, got {tuple(mask.shape)}")
+    if mask.device != device:
+        mask = mask.to(device)
+    sb, sq, sk = mask.stride()
+    return mask, sb, sq, sk
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise helpers
+# ------------------------------------------------------------------------------------------------
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    x = _contig(_need(x, "x"))
+    lib = _lib_for(x)
+    out = torch.empty_like(x)
+    cols = x.shape[-1]
+    rows = x.numel() // max(cols, 1)
+    check(lib.st_round_tf32(_p(x), cols, _p(out), cols, rows, cols, _stream()))
+    return mark_tf32_clean(out)
+
+
+def linear_tf32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False
+                ) -> torch.Tensor:
+    """y = x @ weight.T + bias on the tcgen05 TF32 GEMM (no autograd). Operands are rounded to TF32 first."""
+    x = _contig(_need(x, "x"))
+    weight = _contig(_need(weight, "weight"))
+    lib = _lib_for(x)
+    K = x.shape[-1]
+    M = x.numel() // K
+    N = weight.shape[0]
+    xr = x if is_tf32_clean(x) else round_tf32(x)
+    wr = round_tf32(weight)
+    out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
+    ep = _lib.GemmEpilogue(bias=_p(bias), aux=None, ldaux=0, aux_mode=0, relu=int(relu), round_tf32=0, k_splits=1,
+                           dropout_p=0.0, seed=0)
+    check(lib.st_gemm(0, _p(xr), K, _p(wr), K, _p(out), N, M, N, K, C.byref(ep), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# (C) residual + LayerNorm
+# ------------------------------------------------------------------------------------------------
+class _AddLayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps, dropout_p, seed, round_out):
+        a = _contig(_need(a, "a"))
+        lib = _lib_for(a)
+        d = a.shape[-1]
+        rows = a.numel() // d
+        if b is not None:
+            b = _contig(_need(b, "b"))
+            if b.shape != a.shape:
+                raise RuntimeError(f"add_layer_norm: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+        gamma = _contig(_need(gamma, "gamma"))
+        beta = _contig(_need(beta, "beta"))
+        out = torch.empty_like(a)
+        z = torch.empty_like(a) if b is not None else None
+        mean = torch.empty(rows, device=a.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=a.device, dtype=torch.float32)
+        check(lib.st_add_ln_fwd(_p(a), _p(b), _p(gamma), _p(beta), _p(out), _p(z), _p(mean), _p(rstd), rows, d,
+                                float(eps), int(round_out), float(dropout_p), int(seed), _stream()))
+        ctx.save_for_backward(z if z is not None else a, mean, rstd, gamma)
+        ctx.cfg = (rows, d, float(dropout_p), int(seed), b is not None)
+        if round_out:
+            mark_tf32_clean(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, mean, rstd, gamma = ctx.saved_tensors
+        rows, d, p, seed, has_b = ctx.cfg
+        dy = _contig(dy)
+        lib = _lib_for(dy)
+        dz = torch.empty_like(z)
+        dgamma = torch.zeros(d, device=z.device, dtype=torch.float32)
+        dbeta = torch.zeros(d, device=z.device, dtype=torch.float32)
+        check(lib.st_add_ln_bwd(_p(dy), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(dgamma), _p(dbeta), None,
+                                rows, d, 0, p, seed, _stream()))
+        return dz, (dz if has_b else None), dgamma, dbeta, None, None, None, None
+
+
+def add_layer_norm(a, b, gamma, beta, eps: float = 1e-6, dropout_p: float = 0.0, seed: int = 0,
+                   round_out: bool = False):
+    """dropout(LayerNorm(a + b) * gamma + beta) — Attention.py:94, SubLayers.py:27."""
+    return _AddLayerNorm.apply(a, b, gamma, beta, eps, dropout_p, seed, round_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# (A) attention core (no projections) — also ScaledDotProductAttention
+# ------------------------------------------------------------------------------------------------
+class _AttentionCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, mask, n_head, dropout_p, seed, need_attn):
+        q, k, v = (_contig(_need(t, n)) for t, n in ((q, "q"), (k, "k"), (v, "v")))
+        lib = _lib_for(q)
+        B, Lq, d = q.shape
+        Lk = k.shape[1]
+        dk = d // n_head
+        mask_t, sb, sq, sk = _mask_args(mask, B, Lq, Lk, q.device)
+        qr = q if is_tf32_clean(q) else round_tf32(q)
+        kr = qr if _same(k, q) else (k if is_tf32_clean(k) else round_tf32(k))
+        vr = kr if _same(v, k) else (v if is_tf32_clean(v) else round_tf32(v))
+        out = torch.empty(B, Lq, d, device=q.device, dtype=torch.float32)
+        lse = torch.empty(B, n_head, Lq, device=q.device, dtype=torch.float32)
+        attn = torch.empty(B, n_head, Lq, Lk, device=q.device, dtype=torch.float32) if need_attn else None
+        a = _lib.AttnArgs(B=B, H=n_head, Lq=Lq, Lk=Lk, dk=dk, q=_p(qr), ldq=d, k=_p(kr), ldk=d, v=_p(vr), ldv=d,
+                          mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, dropout_p=float(dropout_p), seed=int(seed),
+                          ctx=_p(out), ldctx=d, lse=_p(lse), attn=_p(attn))
+        check(lib.st_attn_fwd(C.byref(a), _stream()))
+        ctx.save_for_backward(qr, kr, vr, out, lse, mask_t)
+        ctx.cfg = (B, n_head, Lq, Lk, dk, float(dropout_p), int(seed))
+        ctx.mark_non_differentiable(*([attn] if attn is not None else []))
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, dout, _dattn):
+        qr, kr, vr, out, lse, mask_t = ctx.saved_tensors
+        B, H, Lq, Lk, dk, p, seed = ctx.cfg
+        d = H * dk
+        lib = _lib_for(qr)
+        dor = round_tf32(_contig(dout))
+        _, sb, sq, sk = _mask_args(mask_t, B, Lq, Lk, qr.device)
+        dq = torch.empty_like(qr)
+        dkk = torch.empty_like(kr)
+        dv = torch.empty_like(vr)
+        delta = torch.empty(B, H, Lq, device=qr.device, dtype=torch.float32)
+        f = _lib.AttnArgs(B=B, H=H, Lq=Lq, Lk=Lk, dk=dk, q=_p(qr), ldq=d, k=_p(kr), ldk=d, v=_p(vr), ldv=d,
+                          mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, dropout_p=p, seed=seed,
+                          ctx=_p(out), ldctx=d, lse=_p(lse), attn=None)
+        a = _lib.AttnBwdArgs(f=f, dctx=_p(dor), lddctx=d, delta=_p(delta), dq=_p(dq), lddq=d, dk=_p(dkk), lddk=d,
+                             dv=_p(dv), lddv=d)
+        check(lib.st_attn_bwd(C.byref(a), _stream()))
+        return dq, dkk, dv, None, None, None, None, None
+
+
+def attention_core(q, k, v, mask=None, n_head: int = 1, dropout_p: float = 0.0, seed: int = 0,
+                   need_attn: bool = False):
+    """softmax(mask(q k^T / sqrt(d_k))) v over `n_head` heads; q,k,v are (B, L, n_head*d_k)."""
+    return _AttentionCore.apply(q, k, v, mask, n_head, dropout_p, seed, need_attn)
+
+
+# ------------------------------------------------------------------------------------------------
+# composite MultiHeadAttention
+# ------------------------------------------------------------------------------------------------
+class _MultiHeadAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, mask, wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b, n_head, residual, eps, dropout_p,
+                seed, need_attn, round_out):
+        q, k, v = (_need(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v")))
+        same_qk, same_kv = _same(q, k), _same(k, v)
+        qc = _contig(q)
+        kc = qc if same_qk else _contig(k)
+        vc = kc if same_kv else _contig(v)
+        lib = _lib_for(qc)
+        if qc.dim() != 3 or kc.dim() != 3 or vc.dim() != 3:
+            raise RuntimeError("multi_head_attention: q, k, v must be (batch, length, d_model)")
+        B, Lq, d = qc.shape
+        Lk = kc.shape[1]
+        if vc.shape != kc.shape or kc.shape[0] != B or kc.shape[2] != d:
+            raise RuntimeError(f"multi_head_attention: incompatible shapes q{tuple(qc.shape)} k{tuple(kc.shape)} v{tuple(vc.shape)}")
+        dk = d // n_head
+        res = vc if residual == "v" else qc
+        if res.shape != qc.shape:
+            # the reference's `output + v` (Attention.py:94) fails the same way when len_q != len_k
+            raise RuntimeError(f"The size of tensor a ({Lq}) must match the size of tensor b ({res.shape[1]}) at "
+                               "non-singleton dimension 1 (residual='v' with len_q != len_k; use residual='q')")
+        mask_t, sb, sq, sk = _mask_args(mask, B, Lq, Lk, qc.device)
+        params = [_contig(_need(t, "parameter")) for t in (wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b)]
+        inputs_tf32 = int(is_tf32_clean(q) and is_tf32_clean(k) and is_tf32_clean(v))
+        same_qkv = int(same_qk and same_kv and Lq == Lk)
+        n_saved = lib.st_mha_saved_floats(B, Lq, Lk, n_head, d, same_qkv, int(same_kv), inputs_tf32)
+        saved = torch.empty(n_saved, device=qc.device, dtype=torch.float32)
+        out = torch.empty(B, Lq, d, device=qc.device, dtype=torch.float32)
+        attn = torch.empty(B, n_head, Lq, Lk, device=qc.device, dtype=torch.float32) if need_attn else None
+        a = _lib.MhaArgs(B=B, Lq=Lq, Lk=Lk, H=n_head, d_model=d, dk=dk, q_in=_p(qc), k_in=_p(kc), v_in=_p(vc),
+                         residual=_p(res), wq=_p(params[0]), bq=_p(params[1]), wk=_p(params[2]), bk=_p(params[3]),
+                         wv=_p(params[4]), bv=_p(params[5]), wo=_p(params[6]), bo=_p(params[7]), ln_g=_p(params[8]),
+                         ln_b=_p(params[9]), mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, eps=float(eps),
+                         dropout_p=float(dropout_p), seed=int(seed), inputs_tf32=inputs_tf32, round_out=int(round_out),
+                         out=_p(out), attn=_p(attn), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
+        check(lib.st_mha_fwd(C.byref(a), _stream()))
+        ctx.save_for_backward(qc, kc, vc, mask_t, saved, *params)
+        ctx.cfg = (B, Lq, Lk, n_head, d, dk, residual, float(eps), float(dropout_p), int(seed), inputs_tf32,
+                   same_qk, same_kv)
+        if attn is not None:
+            ctx.mark_non_differentiable(attn)
+        if round_out:
+            mark_tf32_clean(out)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, dout, _dattn):
+        qc, kc, vc, mask_t, saved, *params = ctx.saved_tensors
+        B, Lq, Lk, H, d, dk, residual, eps, p, seed, inputs_tf32, same_qk, same_kv = ctx.cfg
+        lib = _lib_for(qc)
+        dout = _contig(dout)
+        dev = qc.device
+        _, sb, sq, sk = _mask_args(mask_t, B, Lq, Lk, dev)
+        res = vc if residual == "v" else qc
+        n_ws = lib.st_mha_ws_floats(B, Lq, Lk, H, d)
+        ws = torch.empty(n_ws, device=dev, dtype=torch.float32)
+        same_qkv = same_qk and same_kv
+        dq_in = torch.empty_like(qc)
+        dk_in = dq_in if same_qkv else torch.empty_like(kc)
+        dv_in = dk_in if same_kv else torch.empty_like(vc)
+        grads = [torch.empty_like(t) for t in params]
+        f = _lib.MhaArgs(B=B, Lq=Lq, Lk=Lk, H=H, d_model=d, dk=dk, q_in=_p(qc), k_in=_p(kc), v_in=_p(vc),
+                         residual=_p(res), wq=_p(params[0]), bq=_p(params[1]), wk=_p(params[2]), bk=_p(params[3]),
+                         wv=_p(params[4]), bv=_p(params[5]), wo=_p(params[6]), bo=_p(params[7]), ln_g=_p(params[8]),
+                         ln_b=_p(params[9]), mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, eps=eps, dropout_p=p,
+                         seed=seed, inputs_tf32=inputs_tf32, round_out=0, out=None, attn=None, saved=_p(saved),
+                         saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws)
+        a = _lib.MhaBwdArgs(f=f, dout=_p(dout), dq_in=_p(dq_in), dk_in=_p(dk_in), dv_in=_p(dv_in), dresidual=None,
+                            dwq=_p(grads[0]), dbq=_p(grads[1]), dwk=_p(grads[2]), dbk=_p(grads[3]), dwv=_p(grads[4]),
+                            dbv=_p(grads[5]), dwo=_p(grads[6]), dbo=_p(grads[7]), dln_g=_p(grads[8]),
+                            dln_b=_p(grads[9]))
+        check(lib.st_mha_bwd(C.byref(a), _stream()))
+        # aliased inputs received ONE combined gradient; hand it to the first alias only
+        gq, gk, gv = dq_in, (None if same_qkv else dk_in), (None if same_kv else dv_in)
+        if same_qk and not same_kv:   # q is k but v differs: separate buffers were filled, combine them
+            gq, gk = dq_in + dk_in, None
+        return (gq, gk, gv, None, *grads, None, None, None, None, None, None, None)
+
+
+def multi_head_attention(q, k, v, mask, wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b, n_head: int, residual: str = "v",
+                         eps: float = 1e-6, dropout_p: float = 0.0, seed: int = 0, need_attn: bool = False,
+                         round_out: bool = True):
+    """MultiHeadAttention.forward (Attention.py:64-96) as one fused operator. Returns (out, attn or None)."""
+    if residual not in ("v", "q"):
+        raise ValueError("residual must be 'v' (reference behaviour) or 'q'")
+    return _MultiHeadAttention.apply(q, k, v, mask, wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b, n_head, residual, eps,
+                                     dropout_p, seed, need_attn, round_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# composite PositionwiseFeedForward
+# ------------------------------------------------------------------------------------------------
+class _PositionwiseFFN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, ln_g, ln_b, eps, dropout_p, seed, round_out):
+        x_clean = int(is_tf32_clean(x))
+        xc = _contig(_need(x, "inputs"))
+        lib = _lib_for(xc)
+        d = xc.shape[-1]
+        rows = xc.numel() // d
+        params = [_contig(_need(t, "parameter")) for t in (w1, b1, w2, b2, ln_g, ln_b)]
+        d_ff = params[0].shape[0]
+        n_saved = lib.st_ffn_saved_floats(rows, d, d_ff, x_clean)
+        saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
+        out = torch.empty_like(xc)
+        a = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(xc), w1=_p(params[0]), b1=_p(params[1]),
+                         w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=float(eps),
+                         dropout_p=float(dropout_p), seed=int(seed), x_is_tf32=x_clean, round_out=int(round_out),
+                         out=_p(out), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
+        check(lib.st_ffn_fwd(C.byref(a), _stream()))
+        ctx.save_for_backward(xc, saved, *params)
+        ctx.cfg = (rows, d, d_ff, float(eps), float(dropout_p), int(seed), x_clean)
+        if round_out:
+            mark_tf32_clean(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, saved, *params = ctx.saved_tensors
+        rows, d, d_ff, eps, p, seed, x_clean = ctx.cfg
+        lib = _lib_for(xc)
+        dout = _contig(dout)
+        n_ws = lib.st_ffn_ws_floats(rows, d, d_ff)
+        ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
+        dx = torch.empty_like(xc)
+        grads = [torch.empty_like(t) for t in params]
+        f = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(xc), w1=_p(params[0]), b1=_p(params[1]),
+                         w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=eps,
+                         dropout_p=p, seed=seed, x_is_tf32=x_clean, round_out=0, out=None, saved=_p(saved),
+                         saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws)
+        a = _lib.FfnBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw1=_p(grads[0]), db1=_p(grads[1]), dw2=_p(grads[2]),
+                            db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]))
+        check(lib.st_ffn_bwd(C.byref(a), _stream()))
+        return (dx, *grads, None, None, None, None)
+
+
+def positionwise_ffn(x, w1, b1, w2, b2, ln_g, ln_b, eps: float = 1e-6, dropout_p: float = 0.0, seed: int = 0,
+                     round_out: bool = True):
+    """PositionwiseFeedForward.forward (SubLayers.py:24-28) as one fused operator."""
+    return _PositionwiseFFN.apply(x, w1, b1, w2, b2, ln_g, ln_b, eps, dropout_p, seed, round_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# (D) label-smoothed / soft-target cross entropy
+# ------------------------------------------------------------------------------------------------
+class _LabelSmoothingCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, one_hot, weight, confidence, padding_idx, size_average):
+        logits = _contig(_need(logits, "output"))
+        lib = _lib_for(logits)
+        if logits.dim() != 2:
+            raise AssertionError("inputs.dim() == 2")            # Loss.py:51
+        N, V = logits.shape
+        target = _contig(_need(target, "target", torch.int64))
+        one_hot = _contig(_need(one_hot, "one_hot")).view(-1)
+        weight = _contig(_need(weight, "weight")).view(-1)
+        row_loss = torch.empty(max(N, 1), device=logits.device, dtype=torch.float32)
+        loss = torch.empty((), device=logits.device, dtype=torch.float32)
+        grad = torch.empty_like(logits)
+        check(lib.st_lsce_fwd_bwd(_p(logits), V, _p(target), _p(one_hot), _p(weight), float(confidence),
+                                  int(padding_idx), int(bool(size_average)), N, V, _p(row_loss), _p(loss), _p(grad), V,
+                                  _stream()))
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss, None, None, None, None, None, None
+
+
+def label_smoothing_ce(logits, target, one_hot, weight, confidence: float, padding_idx: int, size_average: bool = True):
+    return _LabelSmoothingCE.apply(logits, target, one_hot, weight, confidence, padding_idx, size_average)
+
+
+class _SoftTargetCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, q, weight, size_average):
+        logits = _contig(_need(logits, "inputs"))
+        q = _contig(_need(q, "target"))
+        lib = _lib_for(logits)
+        N, V = logits.shape
+        weight = _contig(_need(weight, "weight")).view(-1)
+        row_loss = torch.empty(max(N, 1), device=logits.device, dtype=torch.float32)
+        loss = torch.empty((), device=logits.device, dtype=torch.float32)
+        grad = torch.empty_like(logits)
+        check(lib.st_softce_fwd_bwd(_p(logits), V, _p(q), _p(weight), int(bool(size_average)), N, V, _p(row_loss),
+                                    _p(loss), _p(grad), V, _stream()))
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss, None, None, None
+
+
+def soft_target_ce(logits, q, weight, size_average: bool = True):
+    return _SoftTargetCE.apply(logits, q, weight, size_average)

@@ -1,0 +1,30 @@
+"""B200 drop-in for the reference's transformer/SubLayers.py (PositionwiseFeedForward, :9-28)."""
+import torch.nn as nn
+import torch.nn.init as init
+
+from .. import functional as F
+
+__all__ = ["PositionwiseFeedForward"]
+
+
+class PositionwiseFeedForward(nn.Module):
+    """dropout2(LayerNorm(x + fc2(dropout1(relu(fc1(x)))))) — SubLayers.py:24-28, one fused operator."""
+
+    def __init__(self, d_model, d_ff, dropout=0.1):
+        super(PositionwiseFeedForward, self).__init__()
+        self.fc1 = nn.Linear(d_model, d_ff, bias=True)
+        self.fc2 = nn.Linear(d_ff, d_model, bias=True)
+        self.relu = nn.ReLU()
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.layernorm = nn.LayerNorm(d_model, eps=1e-6)
+
+        # initialization (SubLayers.py:21-22)
+        init.xavier_normal_(self.fc1.weight.data)
+        init.xavier_normal_(self.fc2.weight.data)
+
+    def forward(self, inputs):
+        p = self.dropout1.p if self.training else 0.0
+        return F.positionwise_ffn(inputs, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                  self.layernorm.weight, self.layernorm.bias, eps=self.layernorm.eps, dropout_p=p,
+                                  seed=F.next_seed() if p > 0 else 0, round_out=True)

@@ -1,0 +1,349 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures.  Tolerance for floating point: max|a-b| / max|b| <= 1e-3 (BASELINE.json north_star);
+masks / indices / exact zeros are checked bit-exactly."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import TOL, golden, relerr, t, torch_params
+from oracle import st_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def stb():
+    import speech_tranformer_pytorch_b200 as m
+    m.build()
+    m._lib.check(m._lib.load().st_device_check(0))
+    return m
+
+
+def _grad_check(cuda_params, oracle_params, tol=TOL):
+    scale = max(p.grad.abs().max().item() for p in oracle_params.values())
+    for k, p in oracle_params.items():
+        got = cuda_params[k].grad
+        assert got is not None, k
+        err = (got.detach().cpu().double() - p.grad.double()).abs().max().item() / scale
+        assert err < tol, (k, err)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_selftests(stb):
+    import ctypes
+    lib = stb._lib.load()
+    for i in range(lib.st_selftest_count()):
+        err = ctypes.c_double(-1)
+        st = lib.st_selftest(i, ctypes.byref(err))
+        assert st == 0 and 0 <= err.value < 1e-4, (i, st, err.value, lib.st_last_error())
+
+
+# ------------------------------------------------------------------------------------------------ (C) add + LayerNorm
+@pytest.mark.parametrize("rows,d,has_b", [(37, 64, True), (1000, 512, True), (5, 128, False), (300, 1024, True), (64, 256, False)])
+def test_add_layer_norm(stb, rows, d, has_b):
+    F = stb.functional
+    gen = torch.Generator().manual_seed(rows + d)
+    a = torch.randn(rows, d, generator=gen)
+    b = torch.randn(rows, d, generator=gen) if has_b else None
+    gamma = 1 + 0.3 * torch.randn(d, generator=gen)
+    beta = 0.2 * torch.randn(d, generator=gen)
+    g = torch.randn(rows, d, generator=gen)
+    ref_in = [x.clone().double().requires_grad_() if x is not None else None for x in (a, b, gamma, beta)]
+    ref = O.add_layer_norm(*ref_in)
+    ref.backward(g.double())
+    cu_in = [x.to(DEV).requires_grad_() if x is not None else None for x in (a, b, gamma, beta)]
+    out = F.add_layer_norm(*cu_in, eps=1e-6)
+    out.backward(g.to(DEV))
+    assert relerr(out, ref) < 1e-5
+    for c, r in zip(cu_in, ref_in):
+        if c is not None:
+            assert relerr(c.grad, r.grad) < 2e-5
+
+
+def test_add_layer_norm_dropout_statistics(stb):
+    F = stb.functional
+    a = torch.randn(2000, 512, device=DEV)
+    gamma, beta = torch.ones(512, device=DEV), torch.zeros(512, device=DEV)
+    base = F.add_layer_norm(a, None, gamma, beta)
+    out = F.add_layer_norm(a, None, gamma, beta, dropout_p=0.25, seed=123)
+    kept = out != 0
+    frac = kept.float().mean().item()
+    assert abs(frac - 0.75) < 0.01
+    assert torch.allclose(out[kept], base[kept] / 0.75, rtol=1e-5, atol=1e-6)
+    out2 = F.add_layer_norm(a, None, gamma, beta, dropout_p=0.25, seed=123)
+    assert torch.equal(out, out2), "same seed must reproduce the mask"
+
+
+# ------------------------------------------------------------------------------------------------ (D) CE
+@pytest.mark.parametrize("ii", [-1, 0, 3])
+@pytest.mark.parametrize("sa", [True, False])
+@pytest.mark.parametrize("wname", ["w", "u"])
+def test_label_smoothing_golden(stb, ii, sa, wname):
+    g = golden("lsce")
+    key = f"ii{ii}_sa{int(sa)}_{wname}"
+    V = g["logits"].shape[1]
+    w = t(g["weight"]) if wname == "w" else torch.ones(V)
+    crit = stb.LabelSmoothingLoss(0.1, V, weight=w.to(DEV), size_average=sa, ignore_index=ii).to(DEV)
+    assert np.array_equal(crit.one_hot.cpu().numpy(), g["onehot_" + key])
+    x = t(g["logits"], DEV).requires_grad_()
+    loss = crit(x, t(g["target"], DEV))
+    loss.backward()
+    assert relerr(loss, g["loss_" + key]) < 1e-5
+    assert relerr(x.grad, g["grad_" + key]) < 1e-5
+    zero_rows = (t(g["target"]) == ii) if ii >= 0 else torch.zeros(len(g["target"]), dtype=torch.bool)
+    assert torch.all(x.grad.cpu()[zero_rows] == 0), "ignored rows must get exactly zero gradient"
+
+
+def test_soft_target_ce_golden(stb):
+    g = golden("lsce")
+    x = t(g["logits"], DEV).requires_grad_()
+    loss = stb.CrossEntropyLoss(t(g["weight"], DEV), True)(x, t(g["dense_q"], DEV))
+    loss.backward()
+    assert relerr(loss, g["dense_loss"]) < 1e-5 and relerr(x.grad, g["dense_grad"]) < 1e-5
+
+
+def test_label_smoothing_headline_shape(stb):
+    """N=1600, V=4337 (config 2) against the oracle; empty batch; weight=None error behaviour."""
+    N, V = 1600, 4337
+    gen = torch.Generator().manual_seed(0)
+    logits = 3 * torch.randn(N, V, generator=gen)
+    target = torch.randint(0, V, (N,), generator=gen)
+    target[::7] = 0
+    w = 0.5 + torch.rand(V, generator=gen)
+    x = logits.clone().requires_grad_()
+    ref = O.label_smoothing_loss(x, target, O.smoothing_one_hot(0.1, V, 0), w, 0.1, 0, True)
+    ref.backward()
+    crit = stb.LabelSmoothingLoss(0.1, V, weight=w.to(DEV), ignore_index=0).to(DEV)
+    xc = logits.to(DEV).requires_grad_()
+    loss = crit(xc, target.to(DEV))
+    (2 * loss).backward()
+    assert relerr(loss, ref) < 1e-5
+    assert relerr(xc.grad, 2 * x.grad) < 1e-4
+    with pytest.raises(AttributeError):
+        stb.LabelSmoothingLoss(0.1, V).to(DEV)(xc, target.to(DEV))
+
+
+# ------------------------------------------------------------------------------------------------ (A) attention core / SDPA
+def test_sdpa_golden(stb):
+    g = golden("sdpa")
+    q, k, v = (t(g[n], DEV).requires_grad_() for n in "qkv")
+    m = stb.ScaledDotProductAttention(32).eval()
+    out, w = m(q, k, v, t(g["mask"], DEV).bool())
+    out.backward(t(g["g"], DEV))
+    assert relerr(out, g["out"]) < TOL and relerr(w, g["attn"]) < TOL
+    for a, b in ((q.grad, "dq"), (k.grad, "dk"), (v.grad, "dv")):
+        assert relerr(a, g[b]) < TOL, b
+    assert torch.all(w.cpu()[t(g["mask"]).bool()] == 0), "masked weights must be exactly zero"
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,dk,kind", [
+    (2, 2, 9, 9, 32, "pad"), (2, 8, 200, 200, 64, "pad"), (1, 4, 130, 257, 128, "pad"), (2, 4, 50, 50, 64, "causal"),
+    (2, 8, 50, 333, 64, "pad"), (1, 1, 1, 1, 64, "none"), (3, 2, 129, 128, 32, "none")])
+def test_attention_core(stb, B, H, Lq, Lk, dk, kind):
+    F = stb.functional
+    d = H * dk
+    gen = torch.Generator().manual_seed(B * 1000 + Lq + Lk)
+    q = torch.randn(B, Lq, d, generator=gen)
+    k = torch.randn(B, Lk, d, generator=gen)
+    v = torch.randn(B, Lk, d, generator=gen)
+    g = torch.randn(B, Lq, d, generator=gen)
+    mask = None
+    if kind == "pad":
+        kl = torch.randint(max(1, Lk // 2), Lk + 1, (B,), generator=gen)
+        kl[0] = Lk
+        mask = O.padding_info_mask(torch.full((B,), Lq), kl).bool()
+    elif kind == "causal":
+        lens = torch.tensor([Lq, max(1, Lq - 7)][:B])
+        mask = O.decoder_self_mask(lens)
+
+    def ref_fn(q, k, v):
+        sh = lambda x: x.view(B, -1, H, dk).transpose(1, 2).reshape(B * H, -1, dk)
+        m = None if mask is None else mask.unsqueeze(1).expand(B, H, Lq, Lk).reshape(B * H, Lq, Lk)
+        o, w = O.scaled_dot_product_attention(sh(q), sh(k), sh(v), m, dk)
+        return o.view(B, H, Lq, dk).transpose(1, 2).reshape(B, Lq, d), w.view(B, H, Lq, Lk)
+
+    rq, rk, rv = (x.clone().double().requires_grad_() for x in (q, k, v))
+    ro, rw = ref_fn(rq, rk, rv)
+    ro.backward(g.double())
+    cq, ck, cv = (x.to(DEV).requires_grad_() for x in (q, k, v))
+    co, cw = F.attention_core(cq, ck, cv, None if mask is None else mask.to(DEV), n_head=H, need_attn=True)
+    co.backward(g.to(DEV))
+    assert relerr(co, ro) < TOL
+    assert relerr(cw, rw) < TOL
+    if mask is not None:
+        mm = mask.unsqueeze(1).expand(B, H, Lq, Lk)
+        assert torch.all(cw.cpu()[mm] == 0)
+    for a, b, n in ((cq.grad, rq.grad, "dq"), (ck.grad, rk.grad, "dk"), (cv.grad, rv.grad, "dv")):
+        assert relerr(a, b) < TOL, n
+
+
+def test_fully_masked_row_is_nan(stb):
+    """softmax over an all -inf row is NaN in the reference; same here, other rows unaffected."""
+    F = stb.functional
+    B, H, L, dk = 1, 2, 20, 32
+    q = torch.randn(B, L, H * dk, device=DEV)
+    mask = torch.zeros(B, L, L, dtype=torch.bool, device=DEV)
+    mask[0, 3, :] = True
+    out, w = F.attention_core(q, q, q, mask, n_head=H, need_attn=True)
+    assert torch.isnan(out[0, 3]).all() and torch.isnan(w[0, :, 3]).all()
+    keep = torch.ones(L, dtype=torch.bool)
+    keep[3] = False
+    assert not torch.isnan(out[0, keep]).any()
+
+
+def test_mask_dtypes_and_views(stb):
+    """uint8 (what Utils.py builds) and bool masks, expanded stride-0 views and dense copies agree bit-exactly."""
+    F = stb.functional
+    B, H, L, dk = 2, 2, 70, 32
+    q = torch.randn(B, L, H * dk, device=DEV)
+    m_view = O.padding_info_mask(torch.tensor([70, 41]), torch.tensor([70, 41])).to(DEV)  # uint8, stride (L,0,1)
+    assert m_view.dtype == torch.uint8 and m_view.stride(1) == 0
+    o1, w1 = F.attention_core(q, q, q, m_view, n_head=H, need_attn=True)
+    o2, w2 = F.attention_core(q, q, q, m_view.bool().contiguous(), n_head=H, need_attn=True)
+    assert torch.equal(o1, o2) and torch.equal(w1, w2)
+
+
+# ------------------------------------------------------------------------------------------------ modules vs golden
+@pytest.mark.parametrize("name", ["mha_self_padmask", "mha_self_causal", "mha_self_nomask_h4", "mha_cross_eqlen"])
+def test_mha_module_golden(stb, name):
+    g = golden(name)
+    H = int(g["n_head"])
+    d = g["q"].shape[-1]
+    m = stb.MultiHeadAttention(H, d, d // H, d // H, dropout=0.1, return_attention=True).to(DEV).eval()
+    m.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith("p.")})
+    q = t(g["q"], DEV).requires_grad_()
+    cross = bool(g["cross"])
+    kv = t(g["kv"], DEV).requires_grad_() if cross else q
+    mask = t(g["mask"], DEV).bool() if "mask" in g else None
+    out, attn = m(q, kv, kv, mask)
+    out.backward(t(g["g"], DEV))
+    assert relerr(out, g["out"]) < TOL
+    assert relerr(attn, g["attn"]) < TOL
+    assert relerr(q.grad, g["dq"]) < TOL
+    if cross:
+        assert relerr(kv.grad, g["dkv"]) < TOL
+    scale = max(np.abs(g["g." + k]).max() for k, _ in m.named_parameters())
+    for k, p in m.named_parameters():
+        err = (p.grad.cpu().double() - t(g["g." + k]).double()).abs().max().item() / scale
+        assert err < TOL, (k, err)
+
+
+def test_ffn_module_golden(stb):
+    g = golden("ffn")
+    m = stb.PositionwiseFeedForward(64, 128).to(DEV).eval()
+    m.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith("p.")})
+    x = t(g["x"], DEV).requires_grad_()
+    y = m(x)
+    y.backward(t(g["g"], DEV))
+    assert relerr(y, g["out"]) < TOL and relerr(x.grad, g["dx"]) < TOL
+    for k, p in m.named_parameters():
+        assert relerr(p.grad, g["g." + k]) < TOL, k
+
+
+class _EncoderLayer(torch.nn.Module):
+    """Layers.py:8-22 re-typed against the drop-in modules (the reference file itself is not on the GPU box)."""
+
+    def __init__(self, stb, d_model, d_inner, n_head, residual="v"):
+        super().__init__()
+        self.slf_attn = stb.MultiHeadAttention(n_head, d_model, d_model // n_head, d_model // n_head, residual=residual)
+        self.pos_ffn = stb.PositionwiseFeedForward(d_model, d_inner)
+
+    def forward(self, x, mask=None):
+        a, w = self.slf_attn(x, x, x, mask=mask)
+        return self.pos_ffn(a), w
+
+
+def test_encoder_layer_golden(stb):
+    g = golden("encoder_layer")
+    m = _EncoderLayer(stb, 64, 128, 2).to(DEV).eval()
+    m.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith("p.")})
+    x = t(g["x"], DEV).requires_grad_()
+    y, _ = m(x, t(g["mask"], DEV).bool())
+    y.backward(t(g["g"], DEV))
+    assert relerr(y, g["out"]) < TOL and relerr(x.grad, g["dx"]) < TOL
+    scale = max(np.abs(g["g." + k]).max() for k, _ in m.named_parameters())
+    for k, p in m.named_parameters():
+        err = (p.grad.cpu().double() - t(g["g." + k]).double()).abs().max().item() / scale
+        assert err < TOL, (k, err)
+
+
+# ------------------------------------------------------------------------------------------------ modules vs oracle, larger
+@pytest.mark.parametrize("B,L,d,H,dff", [(2, 300, 512, 8, 2048), (3, 77, 64, 2, 128), (2, 150, 512, 4, 1024)])
+def test_encoder_layer_vs_oracle(stb, B, L, d, H, dff):
+    gen = torch.Generator().manual_seed(L)
+    m = _EncoderLayer(stb, d, dff, H).eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() >= 2:
+                torch.nn.init.xavier_normal_(p, generator=gen)
+            elif n.endswith("layernorm.weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=gen))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=gen))
+    P = {k: v.detach().clone().double().requires_grad_() for k, v in m.state_dict().items()}
+    x = torch.randn(B, L, d, generator=gen)
+    lens = torch.randint(L // 2, L + 1, (B,), generator=gen)
+    lens[0] = L
+    mask = O.padding_info_mask(lens, lens).bool()
+    g = torch.randn(B, L, d, generator=gen)
+    rx = x.clone().double().requires_grad_()
+    ry = O.encoder_layer(rx, mask, P, H)
+    ry.backward(g.double())
+    m = m.to(DEV)
+    cx = x.to(DEV).requires_grad_()
+    cy, _ = m(cx, mask.to(DEV))
+    cy.backward(g.to(DEV))
+    assert relerr(cy, ry) < TOL
+    assert relerr(cx.grad, rx.grad) < TOL
+    _grad_check(dict(m.named_parameters()), P)
+
+
+def test_cross_attention_residual_q(stb):
+    """Lq != Lk: the reference's `+ v` cannot run; residual='q' is the documented switch."""
+    B, Lq, Lk, d, H = 2, 50, 333, 512, 8
+    gen = torch.Generator().manual_seed(11)
+    m = stb.MultiHeadAttention(H, d, d // H, d // H, residual="q", return_attention=True).eval()
+    P = {k: v.detach().clone().double().requires_grad_() for k, v in m.state_dict().items()}
+    q, kv, g = torch.randn(B, Lq, d, generator=gen), torch.randn(B, Lk, d, generator=gen), torch.randn(B, Lq, d, generator=gen)
+    mask = O.padding_info_mask(torch.tensor([Lq, Lq]), torch.tensor([Lk, 200])).bool()
+    rq, rkv = q.clone().double().requires_grad_(), kv.clone().double().requires_grad_()
+    ro, rw = O.multi_head_attention(rq, rkv, rkv, mask, P, H, residual="q")
+    ro.backward(g.double())
+    m = m.to(DEV)
+    cq, ckv = q.to(DEV).requires_grad_(), kv.to(DEV).requires_grad_()
+    co, cw = m(cq, ckv, ckv, mask.to(DEV))
+    co.backward(g.to(DEV))
+    assert relerr(co, ro) < TOL and relerr(cw, rw) < TOL
+    assert relerr(cq.grad, rq.grad) < TOL and relerr(ckv.grad, rkv.grad) < TOL
+    _grad_check(dict(m.named_parameters()), P)
+    with pytest.raises(RuntimeError):
+        stb.MultiHeadAttention(H, d, d // H, d // H, residual="v").to(DEV)(cq, ckv, ckv)
+
+
+def test_state_dict_interchange_and_errors(stb):
+    m = stb.MultiHeadAttention(2, 64, 32, 32)
+    assert set(m.state_dict()) == {f"{a}.{b}" for a in ("linear_q", "linear_k", "linear_v", "output_linear", "layernorm")
+                                   for b in ("weight", "bias")}
+    with pytest.raises(AssertionError):
+        stb.MultiHeadAttention(3, 64, 32, 32)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 4, 64), torch.randn(1, 4, 64), torch.randn(1, 4, 64))  # CPU tensors: no fallback
+
+
+def test_dropout_train_mode_runs_and_is_unbiased(stb):
+    """Train mode (dropout 0.1 at the three reference positions): finite, seed-reproducible, mean-preserving."""
+    torch.manual_seed(0)
+    m = _EncoderLayer(stb, 512, 2048, 8).to(DEV).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.1
+    x = torch.randn(2, 256, 512, device=DEV, requires_grad=True)
+    y, _ = m(x)
+    y.sum().backward()
+    assert torch.isfinite(y).all() and torch.isfinite(x.grad).all()
+    frac_zero = (y == 0).float().mean().item()
+    assert abs(frac_zero - 0.1) < 0.01, frac_zero   # dropout2 after the FFN LayerNorm (SubLayers.py:27)
