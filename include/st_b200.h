@@ -175,6 +175,8 @@ typedef struct {
 } st_ffn_args;
 int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32);
 int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff);
+/* float offset inside `saved` of the hidden activation h = dropout1(relu(fc1(x))), shape (rows, d_ff) — test hook */
+int64_t st_ffn_hidden_offset(int64_t rows, int d_model, int d_ff, int x_is_tf32);
 int st_ffn_fwd(const st_ffn_args* a /* host */, cudaStream_t stream);
 
 typedef struct {

@@ -109,8 +109,16 @@ def multi_head_attention(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor]
 # (a-3) PositionwiseFeedForward.forward — SubLayers.py:24-28
 # params: fc1|fc2 .weight/.bias, layernorm.weight/.bias
 # ---------------------------------------------------------------------------------------------
-def positionwise_ffn(x: Tensor, params: Dict[str, Tensor], eps: float = 1e-6) -> Tensor:
-    h = torch.relu(x @ params["fc1.weight"].t() + params["fc1.bias"])      # :25
+def ffn_preactivation(x: Tensor, params: Dict[str, Tensor]) -> Tensor:
+    return x @ params["fc1.weight"].t() + params["fc1.bias"]
+
+
+def positionwise_ffn(x: Tensor, params: Dict[str, Tensor], eps: float = 1e-6, gate: Optional[Tensor] = None) -> Tensor:
+    """`gate` (0/1, shape of the hidden activation) overrides the ReLU's own active set.  A test compares
+    gradients for a FIXED gate pattern, because a reduced-precision forward may legitimately put a
+    pre-activation that is within rounding error of 0 on the other side of the kink."""
+    pre = ffn_preactivation(x, params)
+    h = torch.relu(pre) if gate is None else pre * gate.to(pre.dtype)     # :25
     y = h @ params["fc2.weight"].t() + params["fc2.bias"]                  # :26
     return add_layer_norm(x, y, params["layernorm.weight"], params["layernorm.bias"], eps)  # :27
 
@@ -123,16 +131,17 @@ def _sub(params: Dict[str, Tensor], prefix: str) -> Dict[str, Tensor]:
     return {k[n:]: v for k, v in params.items() if k.startswith(prefix)}
 
 
-def encoder_layer(x: Tensor, mask: Optional[Tensor], params: Dict[str, Tensor], n_head: int) -> Tensor:
+def encoder_layer(x: Tensor, mask: Optional[Tensor], params: Dict[str, Tensor], n_head: int,
+                  ffn_gate: Optional[Tensor] = None) -> Tensor:
     a, _ = multi_head_attention(x, x, x, mask, _sub(params, "slf_attn."), n_head)
-    return positionwise_ffn(a, _sub(params, "pos_ffn."))
+    return positionwise_ffn(a, _sub(params, "pos_ffn."), gate=ffn_gate)
 
 
 def decoder_layer(x: Tensor, enc: Tensor, slf_mask: Optional[Tensor], enc_mask: Optional[Tensor],
-                  params: Dict[str, Tensor], n_head: int) -> Tensor:
+                  params: Dict[str, Tensor], n_head: int, residual: str = "q", ffn_gate: Optional[Tensor] = None) -> Tensor:
     a, _ = multi_head_attention(x, x, x, slf_mask, _sub(params, "slf_attn."), n_head)
-    c, _ = multi_head_attention(a, enc, enc, enc_mask, _sub(params, "enc_attn."), n_head, residual="q")
-    return positionwise_ffn(c, _sub(params, "pos_ffn."))
+    c, _ = multi_head_attention(a, enc, enc, enc_mask, _sub(params, "enc_attn."), n_head, residual=residual)
+    return positionwise_ffn(c, _sub(params, "pos_ffn."), gate=ffn_gate)
 
 
 # ---------------------------------------------------------------------------------------------

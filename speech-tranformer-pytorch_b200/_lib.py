@@ -103,6 +103,7 @@ SIGNATURES = {
     "st_mha_bwd": (C.c_int, [C.POINTER(MhaBwdArgs), _S]),
     "st_ffn_saved_floats": (i64, [i64, C.c_int, C.c_int, C.c_int]),
     "st_ffn_ws_floats": (i64, [i64, C.c_int, C.c_int]),
+    "st_ffn_hidden_offset": (i64, [i64, C.c_int, C.c_int, C.c_int]),
     "st_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), _S]),
     "st_ffn_bwd": (C.c_int, [C.POINTER(FfnBwdArgs), _S]),
     "st_sumsq": (C.c_int, [_P, i64, _P, _S]),

@@ -443,6 +443,10 @@ int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32) 
   return (x_is_tf32 ? 0 : pad64(rows * d_model)) + pad64(rows * d_ff) + pad64(rows * d_model) + 2 * pad64(rows) +
          2 * pad64(static_cast<int64_t>(d_ff) * d_model);
 }
+int64_t st_ffn_hidden_offset(int64_t rows, int d_model, int d_ff, int x_is_tf32) {
+  (void)d_ff;
+  return x_is_tf32 ? 0 : pad64(rows * d_model);
+}
 int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff) { return pad64(rows * d_model) + pad64(rows * d_ff) + 64; }
 
 int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {

@@ -349,10 +349,13 @@ class _PositionwiseFFN(torch.autograd.Function):
         ctx.cfg = (rows, d, d_ff, float(eps), float(dropout_p), int(seed), x_clean)
         if round_out:
             mark_tf32_clean(out)
-        return out
+        off = lib.st_ffn_hidden_offset(rows, d, d_ff, x_clean)
+        hidden = saved[off:off + rows * d_ff].view(*xc.shape[:-1], d_ff)
+        ctx.mark_non_differentiable(hidden)
+        return out, hidden
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _dhidden):
         xc, saved, *params = ctx.saved_tensors
         rows, d, d_ff, eps, p, seed, x_clean = ctx.cfg
         lib = _lib_for(xc)
@@ -372,9 +375,14 @@ class _PositionwiseFFN(torch.autograd.Function):
 
 
 def positionwise_ffn(x, w1, b1, w2, b2, ln_g, ln_b, eps: float = 1e-6, dropout_p: float = 0.0, seed: int = 0,
-                     round_out: bool = True):
-    """PositionwiseFeedForward.forward (SubLayers.py:24-28) as one fused operator."""
-    return _PositionwiseFFN.apply(x, w1, b1, w2, b2, ln_g, ln_b, eps, dropout_p, seed, round_out)
+                     round_out: bool = True, return_hidden: bool = False):
+    """PositionwiseFeedForward.forward (SubLayers.py:24-28) as one fused operator.
+
+    return_hidden=True additionally returns the (non-differentiable) hidden activation
+    dropout1(relu(fc1(x))) that backward will use — a test hook: parity of the gradient of a
+    piecewise-linear function is only defined for a given ReLU gate pattern."""
+    out, hidden = _PositionwiseFFN.apply(x, w1, b1, w2, b2, ln_g, ln_b, eps, dropout_p, seed, round_out)
+    return (out, hidden) if return_hidden else out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -19,12 +19,18 @@ class PositionwiseFeedForward(nn.Module):
         self.dropout2 = nn.Dropout(dropout)
         self.layernorm = nn.LayerNorm(d_model, eps=1e-6)
 
+        self.keep_hidden = False     # test hook: keep the hidden activation of the last forward in .last_hidden
+        self.last_hidden = None
+
         # initialization (SubLayers.py:21-22)
         init.xavier_normal_(self.fc1.weight.data)
         init.xavier_normal_(self.fc2.weight.data)
 
     def forward(self, inputs):
         p = self.dropout1.p if self.training else 0.0
-        return F.positionwise_ffn(inputs, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
-                                  self.layernorm.weight, self.layernorm.bias, eps=self.layernorm.eps, dropout_p=p,
-                                  seed=F.next_seed() if p > 0 else 0, round_out=True)
+        out, hidden = F.positionwise_ffn(inputs, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                         self.layernorm.weight, self.layernorm.bias, eps=self.layernorm.eps,
+                                         dropout_p=p, seed=F.next_seed() if p > 0 else 0, round_out=True,
+                                         return_hidden=True)
+        self.last_hidden = hidden if self.keep_hidden else None
+        return out

@@ -37,6 +37,26 @@ def relerr(a, b):
     return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
 
 
+def relu_gate_from_cuda(hidden_cuda, pre_oracle):
+    """Gate pattern (0/1) the CUDA forward used, checked against the oracle's pre-activations.
+
+    The gradient of a piecewise-linear function is only comparable for a fixed set of active ReLU units:
+    any reduced-precision forward (TF32 here) may put a pre-activation that lies within its rounding
+    error of 0 on the other side of the kink, which flips a whole gradient term.  So: (1) assert that
+    the CUDA gate differs from the oracle's only where |pre| is tiny (<= 1% of the pre-activation std)
+    and only for a small fraction of units, (2) return the CUDA gate for the oracle to differentiate with.
+    """
+    gate = hidden_cuda.detach().cpu() > 0
+    pre = pre_oracle.detach().cpu()
+    assert gate.shape == pre.shape, (gate.shape, pre.shape)
+    flips = gate != (pre > 0)
+    if flips.any():
+        tau = 1e-2 * pre.double().std().item()
+        assert pre[flips].abs().max().item() <= tau, ("ReLU gate differs away from the kink", pre[flips].abs().max().item(), tau)
+        assert flips.double().mean().item() < 1e-2
+    return gate.to(torch.float64)
+
+
 def params(g, prefix="p."):
     return {k[len(prefix):]: v for k, v in g.items() if k.startswith(prefix)}
 
