@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200: frames/sec of one training step
+(forward + label-smoothed CE + backward + gradient all-reduce + clip + Noam-Adam, i.e. the body of
+train.py:37-46) of the 6+6-layer Speech-Transformer of BASELINE.json configs[1]
+(d_model 512, 8 heads, d_ff 2048, fp32 storage / TF32 tensor cores, synthetic 80-dim fbank, B=32 per GPU, T=1000).
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU PyTorch path on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = all ranks' frames / max-over-ranks device time with inputs resident
+in HBM; `e2e` = same through the public module API with pinned-host inputs copied H2D and the loss read back
+D2H every step; `roofline` = the dominant kernel (the tcgen05 TF32 GEMM) timed live with CUDA events;
+`cpu_baseline` = the reference's CPU path on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec fwd+bwd at (B=32,T=1000,d=512)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=1000, help="T_max")
+    ap.add_argument("--targets", type=int, default=50, help="L_max")
+    ap.add_argument("--layers", type=int, default=6)
+    ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--cpu-sample-batch", type=int, default=2, help="utterances per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_step_fn(args, batch):
+    """The reference's own training step on CPU: oracle/_ref (patched scratch copy of the reference package,
+    kind 'reference') when present, else the oracle port (kind 'port').  Returns (step_fn, kind, frames/step)."""
+    import torch
+    import types
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    from oracle import st_oracle as O
+    inputs, targets, in_len, tgt_len, truth = O.synthetic_batch(batch, args.frames, args.targets, 80, 4337, seed=2018)
+    V, d = 4337, 512
+    cfgd = dict(feature_dim=80, vocab_size=V, max_inputs_length=2048, max_target_length=64, d_model=d, n_heads=8, d_k=64,
+                d_v=64, d_inner_hid=2048, num_enc_layer=args.layers, num_dec_layer=args.layers, dropout=args.dropout,
+                emb_scale=1, return_attns=False)
+    if os.path.isdir(os.path.join(ref_dir, "transformer")) and not os.environ.get("ST_BENCH_FORCE_PORT"):
+        kind = "reference"
+        for name in ("editdistance", "matplotlib", "matplotlib.pyplot", "tensorboardX"):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        for k in [k for k in sys.modules if k == "transformer" or k.startswith("transformer.")]:
+            del sys.modules[k]
+        sys.path.insert(0, ref_dir)
+        from transformer.Models import Transformer
+        from transformer.Loss import LabelSmoothingLoss
+        from transformer.Optim import ScheduledOptim
+        from transformer.Utils import AttrDict, init_parameters
+        sys.path.pop(0)
+        torch.manual_seed(2018)
+        model = Transformer(AttrDict(cfgd))
+        init_parameters(model)
+        model.train()
+        crit = LabelSmoothingLoss(0.1, V, weight=torch.ones(V), size_average=True, ignore_index=0)
+        optim = ScheduledOptim(model, d, AttrDict({"n_warmup_steps": 12000}))
+        state = {"step": 0}
+
+        def step():
+            state["step"] += 1
+            optim.zero_grad()
+            logits, _ = model(inputs, in_len, targets, tgt_len)                                  # train.py:39
+            loss = crit(logits.contiguous().view(-1, V), truth.contiguous().view(-1))            # train.py:40
+            loss.backward()                                                                      # train.py:44
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)                              # train.py:45
+            optim.step(state["step"])                                                            # train.py:46
+            return float(loss)
+    else:
+        kind = "port"
+        from oracle import model_port
+        step = model_port.make_train_step(cfgd, inputs, targets, in_len, tgt_len, truth)
+    return step, kind, batch * args.frames
+
+
+def run_cpu(args, steps, warmup, batch):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, kind, frames = cpu_reference_step_fn(args, batch)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": frames * steps / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{batch} utterances x T={args.frames} (of B={args.batch}) per step, full {args.layers}+{args.layers} model, "
+                      f"train mode dropout {args.dropout}, fwd+loss+bwd+clip+Adam, {steps} timed steps after {warmup} warm-up",
+            "ms_per_step": 1e3 * total / steps}
+
+
+def workload_config(args, n):
+    return {"workload": f"BASELINE.json configs[1]: {args.layers}+{args.layers}-layer enc/dec d_model=512 h=8 d_ff=2048, fp32 storage / "
+                        f"TF32 tensor cores, synthetic 80-dim fbank B={args.batch}/GPU T={args.frames} L<={args.targets} V=4337",
+            "step": "fwd + label-smoothed CE + bwd + grad all-reduce + clip + Noam-Adam (train.py:37-46)",
+            "dropout": args.dropout, "per_gpu_batch": args.batch, "global_batch": args.batch * n, "parallelism": f"dp{n}",
+            "l2": "per-step working set (several GB of activations) >> 126 MB L2, no explicit flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.gpus
+    res = run_cpu(args, max(1, args.steps), max(0, args.warmup), args.cpu_sample_batch)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": n, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = world
+
+    import speech_tranformer_pytorch_b200 as stb
+    from speech_tranformer_pytorch_b200 import data as sdata, model as smodel, parallel as spar
+    stb.build()
+    lib = stb._lib.load()
+    stb._lib.check(lib.st_device_check(local))
+
+    V, d = 4337, 512
+    cfg = smodel.headline_config(num_enc_layer=args.layers, num_dec_layer=args.layers, dropout=args.dropout)
+    torch.manual_seed(2018)
+    net = smodel.Transformer(cfg)
+    smodel.init_parameters(net)
+    net = net.to(dev).train()
+    crit = stb.LabelSmoothingLoss(0.1, V, weight=torch.ones(V, device=dev), size_average=True, ignore_index=0).to(dev)
+    trainer = spar.DataParallelTrainer(net, d_model=d, n_warmup_steps=12000, max_grad_norm=5.0)
+    trainer.broadcast_parameters(0)
+
+    host = sdata.synthetic_batch(args.batch, args.frames, args.targets, 80, V, seed=2018 + rank, pin=True)
+    resident = [t.to(dev) for t in host]
+
+    def step_on(inputs, targets, in_len, tgt_len, truth):
+        def loss_fn():
+            logits, _ = net(inputs, in_len, targets, tgt_len)
+            return crit(logits.view(-1, V), truth.view(-1))
+        return trainer.train_step(loss_fn)
+
+    def step_resident():
+        return step_on(*resident)
+
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def step_e2e():
+        batch = [t.to(dev, non_blocking=True) for t in host]      # pinned host -> device, every step
+        loss = step_on(*batch)
+        return loss.item()                                        # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = lib.st_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = lib.st_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    frames = args.batch * args.frames * n * args.steps
+    value = frames / (ms * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "ms_per_step": ms_e2e / args.steps}
+
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream
+    roofline, breakdown = None, None
+    if not args.no_roofline:
+        import ctypes as C
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
+            "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md)"
+        # TF32 dense peak is not in MEASURED_PEAKS.json: measure it the same way (8192^3 torch.matmul, allow_tf32)
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b
+        lib.st_profile_reset()
+        lib.st_profile_enable(1)
+        psteps = min(args.steps, 3)
+        ms_prof = timed(step_resident, psteps)
+        lib.st_profile_enable(0)
+        breakdown = {}
+        for c in range(lib.st_profile_classes()):
+            t, w, k = C.c_double(), C.c_double(), C.c_int64()
+            stb._lib.check(lib.st_profile_read(c, C.byref(t), C.byref(w), C.byref(k)))
+            if k.value:
+                breakdown[lib.st_profile_class_name(c).decode()] = {
+                    "launches_per_step": k.value / psteps, "ms_per_step": t.value / psteps,
+                    "share_of_step": t.value / ms_prof, "work_per_step": w.value / psteps,
+                    "rate": w.value / (t.value * 1e-3) / 1e12 if t.value > 0 else None}
+        lib.st_profile_reset()
+        g = breakdown.get("gemm_tf32")
+        if g:
+            roofline = {"kernel": "gemm_tf32_kernel (tcgen05 kind::tf32, all projection / FFN / gradient GEMMs)",
+                        "bound": "tensor", "achieved": g["rate"], "peak": peak, "unit": "TFLOP/s",
+                        "frac": g["rate"] / peak, "traffic": None, "peak_source": peak_src,
+                        "peak_tf32_measured": tf32_peak, "frac_of_tf32_peak": g["rate"] / tf32_peak,
+                        "flops_per_launch": g["work_per_step"] / g["launches_per_step"],
+                        "avg_launch_ms": g["ms_per_step"] / g["launches_per_step"],
+                        "share_of_step": g["share_of_step"],
+                        "note": "achieved = algorithmic 2MNK FLOPs / CUDA-event time over every GEMM launch of the profiled "
+                                "steps; TF32 runs at half the bf16 MMA rate, so frac against the bf16 peak is capped at 0.5"}
+
+    cpu = None
+    if rank == 0 and n == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = run_cpu(args, steps=2, warmup=1, batch=args.cpu_sample_batch)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)[:200]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic", "config": workload_config(args, n),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "kernel_breakdown": breakdown, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))

@@ -33,6 +33,14 @@ int st_version(void);                       /* 10000*major + 100*minor + patch *
 const char* st_last_error(void);            /* host string, valid until the next failing call */
 int st_device_check(int device);            /* ST_OK iff `device` is compute capability 10.x */
 int st_set_option(const char* name, int v); /* debug/tuning switches, see st_host.cu */
+int64_t st_launch_count(void);              /* kernels this library has launched in this process so far */
+/* Optional per-kernel-class timing with CUDA events on the launching stream (used by bench.py's roofline).
+ * `work` is the algorithmic FLOP count (tensor-core classes) or byte count (HBM classes) of the launches.  */
+int st_profile_enable(int on);
+int st_profile_reset(void);
+int st_profile_classes(void);
+const char* st_profile_class_name(int cls);
+int st_profile_read(int cls, double* ms /* host */, double* work /* host */, int64_t* launches /* host */);
 int st_selftest_count(void);
 int st_selftest(int which, double* rel_err_out /* host */); /* tcgen05 building-block self tests */
 

@@ -86,6 +86,12 @@ SIGNATURES = {
     "st_last_error": (C.c_char_p, []),
     "st_device_check": (C.c_int, [C.c_int]),
     "st_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "st_launch_count": (i64, []),
+    "st_profile_enable": (C.c_int, [C.c_int]),
+    "st_profile_reset": (C.c_int, []),
+    "st_profile_classes": (C.c_int, []),
+    "st_profile_class_name": (C.c_char_p, [C.c_int]),
+    "st_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
     "st_selftest_count": (C.c_int, []),
     "st_selftest": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "st_add_ln_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, i64, C.c_int, C.c_float, C.c_int, C.c_float, u64, _S]),

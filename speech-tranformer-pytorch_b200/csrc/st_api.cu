@@ -175,6 +175,21 @@ int st_device_check(int device) {
 }
 
 int st_set_option(const char* name, int v) { return set_option(name, v); }
+int64_t st_launch_count(void) { return static_cast<int64_t>(launch_count()); }
+int st_profile_enable(int on) { profile_enable(on); return ST_OK; }
+int st_profile_reset(void) { profile_reset(); return ST_OK; }
+int st_profile_classes(void) { return PROF_NUM; }
+const char* st_profile_class_name(int cls) {
+  static const char* names[PROF_NUM] = {"gemm_tf32", "attn_fwd", "attn_bwd_dkv", "attn_bwd_dq", "attn_bwd_delta", "add_ln_fwd",
+                                        "add_ln_bwd", "round_tf32", "colsum", "lsce", "sumsq", "adam"};
+  return (cls >= 0 && cls < PROF_NUM) ? names[cls] : "?";
+}
+int st_profile_read(int cls, double* ms, double* work, int64_t* launches) {
+  long long n = 0;
+  const int st = profile_read(cls, ms, work, &n);
+  *launches = n;
+  return st;
+}
 int st_selftest_count(void) { return selftest_count(); }
 int st_selftest(int which, double* rel_err_out) { return selftest(which, rel_err_out); }
 

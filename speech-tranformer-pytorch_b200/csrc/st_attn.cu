@@ -666,8 +666,9 @@ int launch_fwd(cudaStream_t s, const AttnArgs& a) {
   static bool attr = false;
   if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
   dim3 grid((a.Lq + 127) / 128, a.H, a.B);
+  ProfScope prof(s, PROF_ATTN_FWD, 4.0 * a.B * a.H * static_cast<double>(a.Lq) * a.Lk * DK);
   kern<<<grid, 128, SMEM, s>>>(tq, tk, tv, to_dev(a));
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
@@ -681,9 +682,10 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
     const int64_t rows = static_cast<int64_t>(f.B) * f.Lq;
     const int64_t blocks = (rows + 7) / 8;
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+    ProfScope prof(s, PROF_ATTN_DELTA, 2.0 * rows * cols * 4);
     attn_delta_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(a.dctx, a.lddctx, f.ctx, f.ldctx,
                                                                                     a.delta, f.B, f.H, f.Lq, DK);
-    ST_CHECK_CUDA(cudaGetLastError());
+    ST_CHECK_LAUNCH();
   }
   {
     CUtensorMap tk, tv, tqk, tqm, tdk, tdm;
@@ -698,8 +700,10 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
     static bool attr = false;
     if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
     dim3 grid((f.Lk + 127) / 128, f.H, f.B);
+    // algorithmic share of the attention backward carried by this kernel: dV and dK (S, dP recompute not counted)
+    ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
     kern<<<grid, 128, SMEM, s>>>(tk, tv, tqk, tqm, tdk, tdm, p);
-    ST_CHECK_CUDA(cudaGetLastError());
+    ST_CHECK_LAUNCH();
   }
   {
     CUtensorMap tq, tdo, tkk, tkm, tvk;
@@ -713,8 +717,10 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
     static bool attr = false;
     if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
     dim3 grid((f.Lq + 127) / 128, f.H, f.B);
+    // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
+    ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
     kern<<<grid, 128, SMEM, s>>>(tq, tdo, tkk, tkm, tvk, p);
-    ST_CHECK_CUDA(cudaGetLastError());
+    ST_CHECK_LAUNCH();
   }
   return ST_OK;
 }

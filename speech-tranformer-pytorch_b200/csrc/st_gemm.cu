@@ -274,8 +274,9 @@ int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& t
   int cap = get_option("gemm_max_ctas");
   if (cap <= 0) cap = num_sms();
   const int grid = tiles < cap ? tiles : cap;
+  ProfScope prof(stream, PROF_GEMM, 2.0 * p.M * static_cast<double>(p.N) * p.K);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 

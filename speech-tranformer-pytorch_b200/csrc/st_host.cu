@@ -2,9 +2,11 @@
 #include "st_host.h"
 
 #include <cudaTypedefs.h>
+#include <atomic>
 #include <mutex>
 #include <stdarg.h>
 #include <string.h>
+#include <vector>
 
 namespace st {
 
@@ -24,6 +26,12 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 namespace {
+std::atomic<long long> g_launches{0};
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
 struct Option { const char* name; int value; };
 Option g_options[] = {
     {"gemm_max_ctas", 0},   // 0 = one CTA per SM; >0 caps the persistent grid (tests multi-tile paths)
@@ -41,6 +49,56 @@ int get_option(const char* name) {
   for (auto& o : g_options)
     if (strcmp(o.name, name) == 0) return o.value;
   return 0;
+}
+
+// ---- per-kernel-class event timing
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+void profile_enable(int on) { g_prof_on.store(on ? 1 : 0, std::memory_order_relaxed); }
+
+ProfScope::ProfScope(cudaStream_t s, ProfClass cls, double work) : stream(s), slot(-1) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r{};
+  r.cls = cls;
+  r.work = work;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, s);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back(r);
+  slot = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (slot < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot].b, stream);
+}
+
+int profile_read(int cls, double* ms, double* work, long long* launches) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  double t = 0, w = 0;
+  long long n = 0;
+  for (auto& r : g_prof) {
+    if (r.cls != cls) continue;
+    float e = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) {
+      set_error("profile_read: event query failed");
+      return ST_ERR_CUDA;
+    }
+    t += e; w += r.work; ++n;
+  }
+  *ms = t; *work = w; *launches = n;
+  return ST_OK;
+}
+
+void profile_reset() {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
 }
 
 int num_sms() {

@@ -12,6 +12,8 @@ namespace st {
 
 // status codes (ST_OK, ST_ERR_*) come from the public header
 
+void count_launch();
+long long launch_count();
 void set_error(const char* fmt, ...);
 const char* last_error();
 
@@ -24,7 +26,14 @@ const char* last_error();
     }                                                                                                \
   } while (0)
 
-#define ST_REQUIRE(cond, ...)              \
+// after every kernel launch: count it (st_launch_count over the C ABI) and surface launch errors
+#define ST_CHECK_LAUNCH()                  \
+  do {                                     \
+    st::count_launch();                    \
+    ST_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
+
+#define ST_REQUIRE(cond, ...)            \
   do {                                     \
     if (!(cond)) {                         \
       st::set_error(__VA_ARGS__);          \
@@ -47,6 +56,22 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint32_t* box, int atom32 = 0);
 
 int num_sms();
+
+// ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py for the
+// roofline numbers.  Disabled by default; when disabled a ProfScope costs one relaxed atomic load.
+enum ProfClass : int {
+  PROF_GEMM = 0, PROF_ATTN_FWD, PROF_ATTN_DKV, PROF_ATTN_DQ, PROF_ATTN_DELTA, PROF_LN_FWD, PROF_LN_BWD, PROF_ROUND,
+  PROF_COLSUM, PROF_LSCE, PROF_SUMSQ, PROF_ADAM, PROF_NUM
+};
+struct ProfScope {
+  ProfScope(cudaStream_t s, ProfClass cls, double work);  // work: algorithmic FLOPs (tensor kernels) or bytes (HBM kernels)
+  ~ProfScope();
+  cudaStream_t stream;
+  int slot;
+};
+void profile_enable(int on);
+int profile_read(int cls, double* ms, double* work, long long* launches);  // synchronises; sums since the last reset
+void profile_reset();
 
 // debug / tuning options (st_set_option over the C ABI); unknown names are rejected.
 int set_option(const char* name, int value);

@@ -241,7 +241,8 @@ int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float*
                  (!z_out || aligned16(z_out)),
              "add_ln_fwd: pointers must be 16-byte aligned");
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 8);
-#define ST_LAUNCH(VPL)                                                                                              \
+  ProfScope prof(stream, PROF_LN_FWD, (b ? 3.0 : 2.0) * rows * d * 4 + (z_out ? 1.0 * rows * d * 4 : 0.0));
+#define ST_LAUNCH(VPL)                                                                                            \
   add_ln_fwd_kernel<VPL><<<grid, LN_THREADS, 0, stream>>>(a, b, gamma, beta, out, z_out, mean_out, rstd_out, rows, \
                                                           d, eps, round_out, drop.thresh, drop.scale, drop.seed)
   if (d <= 128) ST_LAUNCH(1);
@@ -249,7 +250,7 @@ int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float*
   else if (d <= 512) ST_LAUNCH(4);
   else ST_LAUNCH(8);
 #undef ST_LAUNCH
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
@@ -260,7 +261,8 @@ int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float
   ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_bwd: d=%d must be a multiple of 4 and <= 1024", d);
   ST_REQUIRE(aligned16(dy) && aligned16(z) && aligned16(gamma) && aligned16(dz), "add_ln_bwd: pointers must be 16-byte aligned");
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 4);
-#define ST_LAUNCH(VPL)                                                                                          \
+  ProfScope prof(stream, PROF_LN_BWD, 3.0 * rows * d * 4);
+#define ST_LAUNCH(VPL)                                                                                         \
   add_ln_bwd_kernel<VPL><<<grid, LN_THREADS, 0, stream>>>(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum,  \
                                                           rows, d, round_out, drop.thresh, drop.scale, drop.seed)
   if (d <= 128) ST_LAUNCH(1);
@@ -268,7 +270,7 @@ int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float
   else if (d <= 512) ST_LAUNCH(4);
   else ST_LAUNCH(8);
 #undef ST_LAUNCH
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
@@ -278,8 +280,9 @@ int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst
              "round_tf32: cols/ld must be multiples of 4 and pointers 16-byte aligned (cols=%d)", cols);
   const int64_t total = rows * (cols / 4);
   const int grid = persistent_grid((total + 255) / 256, 16);
+  ProfScope prof(stream, PROF_ROUND, 2.0 * rows * cols * 4);
   round_tf32_kernel<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, rows, cols / 4);
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
@@ -290,8 +293,9 @@ int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, in
   int64_t ychunks = (rows + 63) / 64;
   const int64_t cap = (static_cast<int64_t>(num_sms()) * 8 + grid.x - 1) / grid.x;
   grid.y = static_cast<unsigned>(ychunks < cap ? ychunks : cap);
+  ProfScope prof(stream, PROF_COLSUM, 1.0 * rows * cols * 4);
   colsum_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, cols, out);
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 

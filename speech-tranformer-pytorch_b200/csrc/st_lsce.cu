@@ -106,15 +106,17 @@ int lsce_fwd_bwd(cudaStream_t stream, const LsceArgs& a) {
   ST_REQUIRE(a.N >= 0 && a.V > 0, "lsce: bad shape N=%lld V=%d", (long long)a.N, a.V);
   ST_REQUIRE(a.weight != nullptr, "lsce: class weight vector is required (Loss.py:59)");
   ST_REQUIRE((a.target != nullptr) != (a.q_dense != nullptr), "lsce: exactly one of target / q_dense must be given");
+  // algorithmic bytes: read logits once + write the gradient once
+  ProfScope prof(stream, PROF_LSCE, (a.grad ? 2.0 : 1.0) * a.N * a.V * 4 + (a.q_dense ? 1.0 * a.N * a.V * 4 : 8.0 * a.N));
   if (a.N > 0) {
     if (a.q_dense)
       lsce_kernel<true><<<static_cast<unsigned>(a.N), CE_THREADS, 0, stream>>>(a);
     else
       lsce_kernel<false><<<static_cast<unsigned>(a.N), CE_THREADS, 0, stream>>>(a);
-    ST_CHECK_CUDA(cudaGetLastError());
+    ST_CHECK_LAUNCH();
   }
   lsce_reduce_kernel<<<1, CE_THREADS, 0, stream>>>(a.row_loss, a.N, a.inv_z, a.loss);
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 

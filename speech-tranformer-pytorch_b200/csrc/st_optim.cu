@@ -85,8 +85,9 @@ int sumsq_add(cudaStream_t s, const float* x, int64_t n, float* out) {
   ST_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sumsq: pointer must be 16-byte aligned");
   const int64_t blocks = (n / 4 + 255) / 256;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  ProfScope prof(s, PROF_SUMSQ, 4.0 * n);
   sumsq_kernel<<<static_cast<unsigned>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap), 256, 0, s>>>(x, n, out);
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
@@ -103,8 +104,9 @@ int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, int6
   a.max_norm = max_norm; a.gscale = gscale; a.sumsq = sumsq;
   const int64_t blocks = (n / 4 + 255) / 256;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  ProfScope prof(s, PROF_ADAM, 7.0 * 4.0 * n);  // read p,g,m,v + write p,m,v
   adam_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(a);
-  ST_CHECK_CUDA(cudaGetLastError());
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 

@@ -1,0 +1,34 @@
+"""Synthetic filterbank batches in the layout of the reference's Dataset.__getitem__ (Dataset.py:34-51,
+56-68): inputs (B, T_max, F) fp32 ~ N(0,1) (post-CMVN statistics, Dataset.py:89-92) with zero-filled tails,
+targets = [BOS] + labels, ground_truth = labels + [BOS] (sic, Dataset.py:36-37), PAD = 0 padding, int64
+length vectors.  There is no network for datasets, so this is what bench.py and the smoke test feed."""
+import torch
+
+PAD, UNK, BOS, EOS = 0, 1, 2, 3
+
+
+def synthetic_batch(batch: int, t_max: int, l_max: int, feat: int, vocab: int, seed: int = 2018, fixed_len: bool = True,
+                    t_min: int = 1, l_min: int = 10, pin: bool = False):
+    g = torch.Generator().manual_seed(seed)
+    if fixed_len:
+        in_len = torch.full((batch,), t_max, dtype=torch.int64)
+    else:
+        in_len = torch.randint(max(t_min, 1), t_max + 1, (batch,), generator=g)
+        in_len[0] = t_max
+    tgt_len = torch.randint(min(l_min, l_max), l_max + 1, (batch,), generator=g)
+    tgt_len[0] = l_max
+    inputs = torch.randn(batch, t_max, feat, generator=g)
+    targets = torch.zeros(batch, l_max, dtype=torch.int64)
+    truth = torch.zeros(batch, l_max, dtype=torch.int64)
+    for b in range(batch):
+        inputs[b, int(in_len[b]):] = 0
+        n = int(tgt_len[b]) - 1
+        labels = torch.randint(4, vocab, (n,), generator=g)
+        targets[b, 0] = BOS
+        targets[b, 1:n + 1] = labels
+        truth[b, :n] = labels
+        truth[b, n] = BOS
+    out = (inputs, targets, in_len, tgt_len, truth)
+    if pin and torch.cuda.is_available():
+        out = tuple(t.pin_memory() for t in out)
+    return out

@@ -1,0 +1,114 @@
+"""Data-parallel training step around one flat parameter / gradient buffer.
+
+Mirrors the reference's only parallelism strategy, train_multi.py: one process per GPU (:128), parameters
+broadcast from rank 0 once (:176-177), every step the gradients are all-reduced (average) across ranks
+(Horovod DistributedOptimizer, :161-163), then clip + Noam-Adam (train.py:45-46, Optim.py:9-45).  Here all
+parameters live in ONE contiguous fp32 buffer and all gradients in another, so a step issues exactly one
+NCCL all-reduce over NVLink/NVSwitch and two HBM-bound kernels (squared norm, fused clip+Adam) from
+libst_b200.so.  The clip uses the REDUCED gradient (the reference clips local gradients before Horovod has
+synchronised them, train_multi.py:66 — a bug not reproduced here).
+
+The flattening / bucketing logic is device-agnostic and is exercised on CPU with gloo (tests/test_dp_gloo.py);
+`step()` needs the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def noam_lr(d_model: int, n_warmup_steps: int, step: int) -> float:
+    """Optim.update_learning_rate (Optim.py:36-45): d^-0.5 * min(step^-0.5, step * warmup^-1.5)."""
+    return d_model ** -0.5 * min(step ** -0.5, step * n_warmup_steps ** -1.5)
+
+
+class FlatParams:
+    """Re-homes a module's parameters into one flat buffer (and their .grad into another)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        if any(p.device != dev or p.dtype != dt for p in self.params):
+            raise ValueError("all parameters must share one device and dtype")
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 3) // 4 * 4          # keep every parameter 16-byte aligned
+        self.numel = n
+        self.flat = torch.zeros(n, device=dev, dtype=dt)
+        self.grad = torch.zeros(n, device=dev, dtype=dt)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                self.flat[o:o + p.numel()].copy_(p.reshape(-1))
+                p.data = self.flat[o:o + p.numel()].view_as(p)
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):      # autograd accumulates in place into these views
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+
+class DataParallelTrainer:
+    """zero_grad -> (caller: forward + backward) -> allreduce -> clip + Adam, on flat buffers."""
+
+    def __init__(self, module: torch.nn.Module, d_model: int, n_warmup_steps: int = 12000, max_grad_norm: float = 5.0,
+                 betas=(0.9, 0.98), eps: float = 1e-9, process_group=None):
+        self.module = module
+        self.fp = FlatParams(module.parameters())
+        self.exp_avg = torch.zeros_like(self.fp.flat)
+        self.exp_avg_sq = torch.zeros_like(self.fp.flat)
+        self.norm_ws = torch.zeros(1, device=self.fp.flat.device, dtype=torch.float32)
+        self.d_model, self.n_warmup_steps, self.max_grad_norm = d_model, n_warmup_steps, max_grad_norm
+        self.betas, self.eps = betas, eps
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.global_step = 0
+        self.lr = 0.0
+
+    # --- train_multi.py:176-177
+    def broadcast_parameters(self, src: int = 0) -> None:
+        if self.world > 1:
+            dist.broadcast(self.fp.flat, src=src, group=self.group)
+
+    def zero_grad(self) -> None:
+        self.fp.zero_grad()
+
+    # --- train_multi.py:161-163 (one collective for the whole model)
+    def allreduce_gradients(self):
+        if self.world > 1:
+            return dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=False)
+        return None
+
+    # --- train.py:45-46
+    def step(self) -> None:
+        from . import _lib
+        from .functional import _stream
+        lib = _lib.load()
+        self.global_step += 1
+        self.lr = noam_lr(self.d_model, self.n_warmup_steps, self.global_step)
+        g = self.fp.grad
+        self.norm_ws.zero_()
+        s = _stream()
+        _lib.check(lib.st_sumsq(g.data_ptr(), g.numel(), self.norm_ws.data_ptr(), s))
+        a = _lib.AdamArgs(param=self.fp.flat.data_ptr(), grad=g.data_ptr(), exp_avg=self.exp_avg.data_ptr(),
+                          exp_avg_sq=self.exp_avg_sq.data_ptr(), n=g.numel(), lr=self.lr, beta1=self.betas[0],
+                          beta2=self.betas[1], eps=self.eps, step=self.global_step, max_grad_norm=self.max_grad_norm,
+                          grad_scale=1.0 / self.world, norm_ws=self.norm_ws.data_ptr())
+        _lib.check(lib.st_adam_step(C.byref(a), s))
+
+    def train_step(self, loss_fn) -> torch.Tensor:
+        """One full step: loss_fn() must run forward and return the scalar loss."""
+        self.zero_grad()
+        loss = loss_fn()
+        loss.backward()
+        self.allreduce_gradients()
+        self.step()
+        return loss
