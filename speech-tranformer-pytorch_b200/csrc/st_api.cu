@@ -17,12 +17,12 @@ namespace st {
 
 DropoutCfg make_dropout(float p, uint64_t seed) {
   DropoutCfg c;
-  if (p > 0.f) {
-    double t = static_cast<double>(p) * 4294967296.0;
-    if (t > 4294967295.0) t = 4294967295.0;
+  if (p > 0.f) {  // drop probability quantised to thresh/65536; the scale uses the quantised value (unbiased)
+    long t = lround(static_cast<double>(p) * 65536.0);
+    if (t < 1) t = 1;
+    if (t > 65535) t = 65535;
     c.thresh = static_cast<uint32_t>(t);
-    if (c.thresh == 0) c.thresh = 1;
-    c.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+    c.scale = 65536.f / static_cast<float>(65536 - t);
     c.seed = seed;
   }
   return c;

@@ -3,19 +3,25 @@
 // Reference: transformer/Attention.py:78-90 — split heads, scores = Q K^T / sqrt(d_k),
 // masked_fill_(mask, -inf), softmax, dropout, P V, merge heads — and its autograd backward.
 // The (B, h, Lq, Lk) score tensor the reference materialises (1 GB per layer at B=32, T=1000) never
-// leaves the SM here: S lives in TMEM, the softmax runs thread-per-row out of TMEM, P goes back to
-// TMEM as the A operand of the P·V MMA.
+// leaves the SM here: S lives in TMEM, the softmax runs out of TMEM, P goes back to TMEM as the
+// A operand of the P·V MMA.
 //
-// Forward  : one CTA per (128-query tile, head, batch), flash-style online softmax over key tiles.
+// Forward  : one CTA per (128-query tile, head, batch), flash-style online softmax over key tiles;
+//            256 threads = 2 threads per query row (each owns half of the tile's columns), 2 CTAs per SM
+//            so one CTA's MMAs overlap the other's softmax.
 // Backward : two kernels, no atomics —
 //   dKV : one CTA per (128-key tile, head, batch), loops over query tiles; S^T = K Q^T and
 //         dP^T = V dO^T are recomputed, dV += P^T dO and dK += dS^T Q accumulate in TMEM;
 //   dQ  : one CTA per (128-query tile, head, batch), loops over key tiles; dQ += dS K in TMEM.
+//   Both use 4 threads per tile row (one 32-column slice each, 512 threads).
+// These kernels are bound by the softmax ALU work (exp2, dropout hash, TF32 rounding: ~16-20
+// instructions per score against 2 MMAs of 512 cycles per 128x128 tile), so the layout maximises
+// resident warps rather than tile size.
 // A tile that is consumed both along d (K-major operand, 16-byte swizzle) and along the sequence
 // (MN-major operand, which for TF32 must use the 32-byte-atom swizzle) is fetched by two TMA loads.
 //
-// Thread t of the 128-thread CTA owns TMEM lane t = one row of the tile, so row max / row sum need
-// no shuffles.  Masks are arbitrary byte tensors with strides (stride 0 over queries for the
+// TMEM lane = tile row; warp w may touch lanes 32*(w%4)..+31, so warps w, w+4, w+8, ... share rows and
+// split columns.  Masks are arbitrary byte tensors with strides (stride 0 over queries for the
 // key-padding masks of Utils.py:41-57); masked => probability exactly 0; a fully masked row gives
 // NaN, as the reference does.
 #include <math.h>
@@ -74,9 +80,47 @@ __device__ __forceinline__ uint32_t mask_bits_row(const AttnDev& p, int b, int r
   return bits;
 }
 
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], uint32_t mb) {
+  float mx = -INFINITY;
+  if (mb == 0u) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (!((mb >> i) & 1u)) mx = fmaxf(mx, __uint_as_float(r[i]));
+  }
+  return mx;
+}
+
+// r <- tf32(dropout(exp2(r*scale_log2 - m))) with masked entries 0; returns the (pre-dropout) row-sum part.
+// col0 is the global key index of r[0] (even), key the per-row dropout key.
+__device__ __forceinline__ float chunk_probs(uint32_t (&r)[32], uint32_t mb, float scale_log2, float m_use,
+                                             uint32_t thresh, float dscale, uint32_t key, uint32_t col0) {
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_use));
+    float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_use));
+    if (mb != 0u) {
+      if ((mb >> i) & 1u) p0 = 0.f;
+      if ((mb >> (i + 1)) & 1u) p1 = 0.f;
+    }
+    l += p0 + p1;
+    if (thresh) {
+      const uint32_t bits = dropout_pair(key, col0 + i);
+      p0 = ((bits & 0xFFFFu) >= thresh) ? p0 * dscale : 0.f;
+      p1 = ((bits >> 16) >= thresh) ? p1 * dscale : 0.f;
+    }
+    r[i] = __float_as_uint(tf32_rna(p0));
+    r[i + 1] = __float_as_uint(tf32_rna(p1));
+  }
+  return l;
+}
+
 // ================================================================================ forward
 template <int DK, int BKV>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnDev p) {
   constexpr int BQ = 128;
@@ -84,7 +128,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   constexpr int Q_BYTES = BQ * DK * 4;
   constexpr int KV_BYTES = BKV * DK * 4;
   constexpr uint32_t TCOLS = 256;           // S/P at [0,BKV), O at [BKV, BKV+DK)
-  static_assert(BKV + DK <= 256, "TMEM budget");
+  constexpr int SH = BKV / 2;               // score columns per thread
+  constexpr int NCH = SH / 32;              // 32-column chunks per thread
+  constexpr int OH = DK / 2;                // output columns per thread
+  static_assert(BKV + DK <= 256 && NCH >= 1, "tile configuration");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -93,10 +140,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sV = sK + KV_BYTES;
   __shared__ uint64_t bar_q, bar_k, bar_v, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_part[2][BQ];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int rit = quarter * 32 + lane;      // row in tile
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
-  const int row = q0 + tid;
+  const int row = q0 + rit;
   const bool row_ok = row < p.Lq;
   const int n_kv = (p.Lk + BKV - 1) / BKV;
 
@@ -110,8 +160,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const uint32_t T_S = 0, T_O = BKV;
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+  constexpr uint32_t T_S = 0, T_O = BKV;
 
   uint32_t k_loads = 0, s_count = 0;  // phase counters for bar_k / bar_s (thread 0 issues, all wait)
 
@@ -148,11 +198,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   k_loads = 1;
 
-  float o[DK];
+  float o[OH];
 #pragma unroll
-  for (int i = 0; i < DK; ++i) o[i] = 0.f;
+  for (int i = 0; i < OH; ++i) o[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
   const uint64_t rng_row = (static_cast<uint64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
+  const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, rng_row) : 0u;
 
   for (int j = 0; j < n_kv; ++j) {
     mbar_wait(&bar_s, s_count & 1);
@@ -160,40 +211,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tc_fence_after();
     if (tid == 0 && j + 1 < n_kv) load_k(j + 1);  // S_j has consumed K_j
 
-    // ---- pass 1: row max over this tile
-    uint32_t mbits[BKV / 32];
+    // ---- pass 1: row max over this thread's half of the tile, combined through smem
+    uint32_t mbits[NCH];
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < BKV / 32; ++c) {
-      mbits[c] = mask_bits_row(p, b, row, row_ok, j * BKV + c * 32);
+    for (int c = 0; c < NCH; ++c) {
+      const int col0 = half * SH + c * 32;
+      mbits[c] = mask_bits_row(p, b, row, row_ok, j * BKV + col0);
       uint32_t r[32];
-      tmem_ld32(t_lane + T_S + c * 32, r);
+      tmem_ld32(t_lane + T_S + col0, r);
       tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (!((mbits[c] >> i) & 1u)) mx = fmaxf(mx, __uint_as_float(r[i]) * p.scale_log2);
+      mx = fmaxf(mx, chunk_max(r, mbits[c]));
     }
+    s_part[half][rit] = mx;
+    __syncthreads();
+    mx = fmaxf(s_part[0][rit], s_part[1][rit]) * p.scale_log2;
     const float m_new = fmaxf(m_run, mx);
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-    const float alpha = exp2f(m_run - m_use);  // m_run == -inf -> 0
+    const float alpha = fast_exp2(m_run - m_use);  // m_run == -inf -> 0
     // ---- pass 2: probabilities -> TMEM (A operand of P·V), row sum
     float l_tile = 0.f;
 #pragma unroll
-    for (int c = 0; c < BKV / 32; ++c) {
+    for (int c = 0; c < NCH; ++c) {
+      const int col0 = half * SH + c * 32;
       uint32_t r[32];
-      tmem_ld32(t_lane + T_S + c * 32, r);
+      tmem_ld32(t_lane + T_S + col0, r);
       tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float pv = ((mbits[c] >> i) & 1u) ? 0.f : exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_use);
-        l_tile += pv;
-        if (p.drop_thresh) {
-          const uint64_t idx = rng_row * p.Lk + (j * BKV + c * 32 + i);
-          pv = dropout_keep(p.drop_seed, idx, p.drop_thresh) ? pv * p.drop_scale : 0.f;
-        }
-        r[i] = __float_as_uint(tf32_rna(pv));
-      }
-      tmem_st32(t_lane + T_S + c * 32, r);
+      l_tile += chunk_probs(r, mbits[c], p.scale_log2, m_use, p.drop_thresh, p.drop_scale, drop_key,
+                            static_cast<uint32_t>(j * BKV + col0));
+      tmem_st32(t_lane + T_S + col0, r);
     }
     l_run = l_run * alpha + l_tile;
     m_run = m_new;
@@ -222,27 +268,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       issue_s();                           // overlaps the O accumulation below
     }
     if (j + 1 < n_kv) ++k_loads;
-    // ---- O += alpha-corrected accumulate in registers
+    // ---- O += alpha-corrected accumulate in registers (this thread's half of the head dim)
+    if constexpr (OH >= 32) {
 #pragma unroll
-    for (int c = 0; c < DK / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(t_lane + T_O + c * 32, r);
+      for (int c = 0; c < OH / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + T_O + half * OH + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
+      }
+    } else {
+      uint32_t r[16];
+      tmem_ld16(t_lane + T_O + half * OH, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+      for (int i = 0; i < 16; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(r[i]));
     }
   }
 
   // ---- finalize: ctx = O / l (NaN for a fully masked row: 0 * inf), lse
-  const float inv_l = 1.f / l_run;
-  const float lse2 = m_run + log2f(l_run);
+  __syncthreads();
+  s_part[half][rit] = l_run;
+  __syncthreads();
+  const float l_tot = s_part[0][rit] + s_part[1][rit];
+  const float inv_l = 1.f / l_tot;
+  const float lse2 = m_run + log2f(l_tot);
   if (row_ok) {
-    float* dst = p.ctx + (static_cast<int64_t>(b) * p.Lq + row) * p.ldctx + h * DK;
+    float* dst = p.ctx + (static_cast<int64_t>(b) * p.Lq + row) * p.ldctx + h * DK + half * OH;
 #pragma unroll
-    for (int i = 0; i < DK; i += 4)
+    for (int i = 0; i < OH; i += 4)
       *reinterpret_cast<float4*>(dst + i) = make_float4(tf32_rna(o[i] * inv_l), tf32_rna(o[i + 1] * inv_l),
                                                         tf32_rna(o[i + 2] * inv_l), tf32_rna(o[i + 3] * inv_l));
-    p.lse2[(static_cast<int64_t>(b) * p.H + h) * p.Lq + row] = lse2;
+    if (half == 0) p.lse2[(static_cast<int64_t>(b) * p.H + h) * p.Lq + row] = lse2;
   }
 
   // ---- optional second sweep: materialise the (post-dropout) probabilities the module returns
@@ -262,22 +320,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       ++s_count;
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        const int k0 = j * BKV + c * 32;
+      for (int c = 0; c < NCH; ++c) {
+        const int k0 = j * BKV + half * SH + c * 32;
         const uint32_t mb = mask_bits_row(p, b, row, row_ok, k0);
         uint32_t r[32];
-        tmem_ld32(t_lane + T_S + c * 32, r);
+        tmem_ld32(t_lane + T_S + half * SH + c * 32, r);
         tmem_ld_wait();
         if (row_ok) {
           float* dst = p.attn + ((static_cast<int64_t>(b) * p.H + h) * p.Lq + row) * p.Lk + k0;
           for (int i = 0; i < 32; ++i) {
             if (k0 + i >= p.Lk) break;
-            float pv = ((mb >> i) & 1u) ? 0.f : exp2f(__uint_as_float(r[i]) * p.scale_log2 - lse2);
-            if (l_run == 0.f) pv = __int_as_float(0x7fc00000);  // fully masked row: NaN like softmax(-inf row)
-            if (p.drop_thresh) {
-              const uint64_t idx = rng_row * p.Lk + (k0 + i);
-              pv = dropout_keep(p.drop_seed, idx, p.drop_thresh) ? pv * p.drop_scale : 0.f;
-            }
+            float pv = ((mb >> i) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, -lse2));
+            if (l_tot == 0.f) pv = __int_as_float(0x7fc00000);  // fully masked row: NaN like softmax(-inf row)
+            if (p.drop_thresh)
+              pv = dropout_keep(dropout_pair(drop_key, k0 + i), k0 + i, p.drop_thresh) ? pv * p.drop_scale : 0.f;
             dst[i] = pv;
           }
         }
@@ -317,12 +373,13 @@ attn_delta_kernel(const float* __restrict__ dctx, int64_t lddctx, const float* _
 
 // ================================================================================ backward: dK, dV
 template <int DK, int BQ>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(4 * BQ, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                     const __grid_constant__ CUtensorMap tmap_q_k, const __grid_constant__ CUtensorMap tmap_q_mn,
                     const __grid_constant__ CUtensorMap tmap_do_k, const __grid_constant__ CUtensorMap tmap_do_mn,
                     const AttnDev p) {
   constexpr int BKV = 128;
+  constexpr int NS = BQ / 32;               // column slices = threads per key row
   constexpr int G = DK / 32;
   constexpr int KV_BYTES = BKV * DK * 4;
   constexpr int QT_BYTES = BQ * DK * 4;
@@ -341,10 +398,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
   __shared__ uint64_t bar_kv, bar_ld, bar_s, bar_acc;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_lse[BQ], s_delta[BQ];
+  __shared__ uint32_t s_key[BQ];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, slice = warp >> 2;
   const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
-  const int key = kv0 + tid;
+  const int key = kv0 + quarter * 32 + lane;
   const bool key_ok = key < p.Lk;
   const int n_q = (p.Lq + BQ - 1) / BQ;
 
@@ -359,7 +418,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bar_kv, 2 * KV_BYTES);
@@ -374,6 +433,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
   bool key_masked = !key_ok;
   if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
   const bool mask_dense = (p.mask != nullptr) && !mask_per_key;
+  const uint32_t ukey = static_cast<uint32_t>(key_ok ? key : 0);
 
   for (int it = 0; it < n_q; ++it) {
     const int q0 = it * BQ;
@@ -388,11 +448,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         tma_load_3d(sDOm + g * (BQ * 128), &tmap_do_mn, &bar_ld, h * DK + g * 32, q0, b);
       }
     }
-    if (tid < BQ) {
-      const int q = q0 + tid;
-      const int64_t o = (static_cast<int64_t>(b) * p.H + h) * p.Lq + q;
-      s_lse[tid] = q < p.Lq ? p.lse2[o] : INFINITY;  // +inf => probability 0 for padded query rows
-      s_delta[tid] = q < p.Lq ? p.delta[o] : 0.f;
+    if (tid >= 3 * BQ) {  // the last BQ threads (never the issuing thread 0)
+      const int t = tid - 3 * BQ;
+      const int q = q0 + t;
+      const int64_t o = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (q < p.Lq ? q : 0);
+      s_lse[t] = q < p.Lq ? p.lse2[o] : INFINITY;  // +inf => probability 0 for padded query rows
+      s_delta[t] = q < p.Lq ? p.delta[o] : 0.f;
+      s_key[t] = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(o)) : 0u;
     }
     if (tid == 0) {
       if (it == 0) mbar_wait(&bar_kv, 0);
@@ -410,12 +472,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                      umma_desc_kmajor(bdo + (ks / 4) * (BQ * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
       umma_commit(&bar_s);
     }
-    __syncthreads();  // s_lse / s_delta visible
+    __syncthreads();  // s_lse / s_delta / s_key visible
     mbar_wait(&bar_s, it & 1);
     tc_fence_after();
 
-#pragma unroll 1
-    for (int c = 0; c < BQ / 32; ++c) {
+    {
+      const int c = slice;  // this thread's 32 query columns
       uint32_t rs[32], rd[32];
       tmem_ld32(t_lane + T_ST + c * 32, rs);
       tmem_ld32(t_lane + T_DPT + c * 32, rd);
@@ -423,16 +485,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int qi = c * 32 + i;
-        const int q = q0 + qi;
         bool masked = key_masked;
-        if (mask_dense && key_ok && q < p.Lq)
-          masked = p.mask[b * p.ms_b + static_cast<int64_t>(q) * p.ms_q + static_cast<int64_t>(key) * p.ms_k] != 0;
-        float pr = masked ? 0.f : exp2f(__uint_as_float(rs[i]) * p.scale_log2 - s_lse[qi]);
+        if (mask_dense) {
+          const int q = q0 + qi;
+          if (key_ok && q < p.Lq)
+            masked = p.mask[b * p.ms_b + static_cast<int64_t>(q) * p.ms_q + static_cast<int64_t>(key) * p.ms_k] != 0;
+        }
+        const float pr = masked ? 0.f : fast_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -s_lse[qi]));
         float dp = __uint_as_float(rd[i]);
         float pd = pr;
         if (p.drop_thresh) {
-          const uint64_t idx = ((static_cast<uint64_t>(b) * p.H + h) * p.Lq + (q < p.Lq ? q : 0)) * p.Lk + (key_ok ? key : 0);
-          const bool keep = dropout_keep(p.drop_seed, idx, p.drop_thresh);
+          const bool keep = dropout_keep(dropout_pair(s_key[qi], ukey), ukey, p.drop_thresh);
           pd = keep ? pr * p.drop_scale : 0.f;
           dp = keep ? dp * p.drop_scale : 0.f;
         }
@@ -464,7 +527,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
   mbar_wait(&bar_acc, (n_q - 1) & 1);
   tc_fence_after();
 #pragma unroll 1
-  for (int c = 0; c < DK / 32; ++c) {
+  for (int c = slice; c < DK / 32; c += NS) {
     uint32_t rv[32], rk[32];
     tmem_ld32(t_lane + T_DV + c * 32, rv);
     tmem_ld32(t_lane + T_DK + c * 32, rk);
@@ -490,11 +553,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
 
 // ================================================================================ backward: dQ
 template <int DK, int BKV>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(4 * BKV, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                    const __grid_constant__ CUtensorMap tmap_k_k, const __grid_constant__ CUtensorMap tmap_k_mn,
                    const __grid_constant__ CUtensorMap tmap_v_k, const AttnDev p) {
   constexpr int BQ = 128;
+  constexpr int NS = BKV / 32;
   constexpr int G = DK / 32;
   constexpr int Q_BYTES = BQ * DK * 4;
   constexpr int KT_BYTES = BKV * DK * 4;
@@ -512,9 +576,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __shared__ uint64_t bar_q, bar_ld, bar_s, bar_acc;
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, slice = warp >> 2;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
-  const int row = q0 + tid;
+  const int row = q0 + quarter * 32 + lane;
   const bool row_ok = row < p.Lq;
   const int n_kv = (p.Lk + BKV - 1) / BKV;
 
@@ -529,7 +594,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bar_q, 2 * Q_BYTES);
@@ -542,6 +607,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
   const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
   const float delta = row_ok ? p.delta[stat] : 0.f;
+  const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(stat)) : 0u;
 
   for (int j = 0; j < n_kv; ++j) {
     if (tid == 0) {
@@ -570,8 +636,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
     mbar_wait(&bar_s, j & 1);
     tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BKV / 32; ++c) {
+    {
+      const int c = slice;
       const int k0 = j * BKV + c * 32;
       const uint32_t mb = mask_bits_row(p, b, row, row_ok, k0);
       uint32_t rs[32], rd[32];
@@ -579,14 +645,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tmem_ld32(t_lane + T_DP + c * 32, rd);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float pr = ((mb >> i) & 1u) ? 0.f : exp2f(__uint_as_float(rs[i]) * p.scale_log2 - lse2);
-        float dp = __uint_as_float(rd[i]);
-        if (p.drop_thresh) {
-          const uint64_t idx = static_cast<uint64_t>(stat) * p.Lk + (k0 + i < p.Lk ? k0 + i : 0);
-          dp = dropout_keep(p.drop_seed, idx, p.drop_thresh) ? dp * p.drop_scale : 0.f;
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = fast_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
+        float p1 = fast_exp2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -lse2));
+        if (mb != 0u) {
+          if ((mb >> i) & 1u) p0 = 0.f;
+          if ((mb >> (i + 1)) & 1u) p1 = 0.f;
         }
-        rd[i] = __float_as_uint(tf32_rna(pr * (dp - delta) * p.scale));
+        float d0 = __uint_as_float(rd[i]), d1 = __uint_as_float(rd[i + 1]);
+        if (p.drop_thresh) {
+          const uint32_t bits = dropout_pair(drop_key, static_cast<uint32_t>(k0 + i));
+          d0 = ((bits & 0xFFFFu) >= p.drop_thresh) ? d0 * p.drop_scale : 0.f;
+          d1 = ((bits >> 16) >= p.drop_thresh) ? d1 * p.drop_scale : 0.f;
+        }
+        rd[i] = __float_as_uint(tf32_rna(p0 * (d0 - delta) * p.scale));
+        rd[i + 1] = __float_as_uint(tf32_rna(p1 * (d1 - delta) * p.scale));
       }
       tmem_st32(t_lane + T_DP + c * 32, rd);
     }
@@ -607,7 +680,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   mbar_wait(&bar_acc, (n_kv - 1) & 1);
   tc_fence_after();
 #pragma unroll 1
-  for (int c = 0; c < DK / 32; ++c) {
+  for (int c = slice; c < DK / 32; c += NS) {
     uint32_t r[32];
     tmem_ld32(t_lane + T_DQ + c * 32, r);
     tmem_ld_wait();
@@ -667,7 +740,7 @@ int launch_fwd(cudaStream_t s, const AttnArgs& a) {
   if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
   dim3 grid((a.Lq + 127) / 128, a.H, a.B);
   ProfScope prof(s, PROF_ATTN_FWD, 4.0 * a.B * a.H * static_cast<double>(a.Lq) * a.Lk * DK);
-  kern<<<grid, 128, SMEM, s>>>(tq, tk, tv, to_dev(a));
+  kern<<<grid, 256, SMEM, s>>>(tq, tk, tv, to_dev(a));
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -702,7 +775,7 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
     dim3 grid((f.Lk + 127) / 128, f.H, f.B);
     // algorithmic share of the attention backward carried by this kernel: dV and dK (S, dP recompute not counted)
     ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    kern<<<grid, 128, SMEM, s>>>(tk, tv, tqk, tqm, tdk, tdm, p);
+    kern<<<grid, 4 * BQ, SMEM, s>>>(tk, tv, tqk, tqm, tdk, tdm, p);
     ST_CHECK_LAUNCH();
   }
   {
@@ -719,7 +792,7 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
     dim3 grid((f.Lq + 127) / 128, f.H, f.B);
     // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
     ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    kern<<<grid, 128, SMEM, s>>>(tq, tdo, tkk, tkm, tvk, p);
+    kern<<<grid, 4 * BKV, SMEM, s>>>(tq, tdo, tkk, tkm, tvk, p);
     ST_CHECK_LAUNCH();
   }
   return ST_OK;

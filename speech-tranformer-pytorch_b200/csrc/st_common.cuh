@@ -258,18 +258,33 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// counter-based RNG for dropout: one 32-bit draw per (seed, offset, element index).
-// Stateless so that backward regenerates the forward mask exactly.
-__device__ __forceinline__ uint32_t hash_rng(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return static_cast<uint32_t>(z >> 32);
+// ------------------------------------------------------------------------------------------
+// Counter-based RNG for dropout.  Stateless — element (row, col) of a tensor always gets the same
+// draw for a given seed — so the backward kernels regenerate the forward mask exactly, in any
+// traversal order.  One 32-bit integer hash yields two 16-bit uniform draws (columns 2j and 2j+1);
+// the drop probability is quantised to thresh16 / 65536.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU;
+  x ^= x >> 15; x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
 }
-// keep-decision for dropout probability p (drop if u < p)
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t p_threshold) {
-  return hash_rng(seed, idx) >= p_threshold;
+__device__ __forceinline__ uint32_t dropout_row_key(uint64_t seed, uint64_t row) {
+  const uint32_t r = static_cast<uint32_t>(row) * 0x9E3779B9u + static_cast<uint32_t>(row >> 32) * 0x85EBCA6Bu;
+  return mix32(static_cast<uint32_t>(seed) ^ mix32(r + static_cast<uint32_t>(seed >> 32)));
+}
+__device__ __forceinline__ uint32_t dropout_pair(uint32_t row_key, uint32_t col) {
+  return mix32(row_key + (col >> 1) * 0x9E3779B9u);
+}
+__device__ __forceinline__ bool dropout_keep(uint32_t pair_bits, uint32_t col, uint32_t thresh16) {
+  return ((col & 1u) ? (pair_bits >> 16) : (pair_bits & 0xFFFFu)) >= thresh16;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 }  // namespace st

@@ -171,6 +171,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool row_ok = row < p.M;
       float* crow = p.C + static_cast<int64_t>(row) * p.ldc;
       const float* auxrow = ep.aux ? ep.aux + static_cast<int64_t>(row) * ep.ldaux : nullptr;
+      const uint32_t drop_key = ep.drop_thresh ? dropout_row_key(ep.drop_seed, static_cast<uint64_t>(row)) : 0u;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -196,9 +197,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
               if (ep.drop_thresh) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const uint64_t idx = static_cast<uint64_t>(row) * p.N + (col + t);
-                  v[t] = dropout_keep(ep.drop_seed, idx, ep.drop_thresh) ? v[t] * ep.drop_scale : 0.f;
+                for (int t = 0; t < 4; t += 2) {  // col is a multiple of 4: one hash per column pair
+                  const uint32_t bits = dropout_pair(drop_key, col + t);
+                  v[t] = dropout_keep(bits, 0, ep.drop_thresh) ? v[t] * ep.drop_scale : 0.f;
+                  v[t + 1] = dropout_keep(bits, 1, ep.drop_thresh) ? v[t + 1] * ep.drop_scale : 0.f;
                 }
               }
               if (ep.aux_mode) {
@@ -234,10 +236,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 float x = v[t];
                 if (ep.bias) x += ep.bias[cc];
                 if (ep.relu) x = fmaxf(x, 0.f);
-                if (ep.drop_thresh) {
-                  const uint64_t idx = static_cast<uint64_t>(row) * p.N + cc;
-                  x = dropout_keep(ep.drop_seed, idx, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
-                }
+                if (ep.drop_thresh)
+                  x = dropout_keep(dropout_pair(drop_key, cc), cc, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
                 if (ep.aux_mode == 1) x += auxrow[cc];
                 if (ep.aux_mode == 2) x = auxrow[cc] > 0.f ? x * ep.aux_scale : 0.f;
                 if (ep.round_tf32) x = tf32_rna(x);

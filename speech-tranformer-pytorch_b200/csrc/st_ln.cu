@@ -79,9 +79,13 @@ add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
         float o[4] = {(x[i].x - mean) * rstd * g[i].x + bt[i].x, (x[i].y - mean) * rstd * g[i].y + bt[i].y,
                       (x[i].z - mean) * rstd * g[i].z + bt[i].z, (x[i].w - mean) * rstd * g[i].w + bt[i].w};
         if (drop_thresh) {
+          const uint32_t key = dropout_row_key(drop_seed, static_cast<uint64_t>(row));
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            o[t] = dropout_keep(drop_seed, static_cast<uint64_t>(row) * d + c + t, drop_thresh) ? o[t] * drop_scale : 0.f;
+          for (int t = 0; t < 4; t += 2) {
+            const uint32_t bits = dropout_pair(key, c + t);
+            o[t] = dropout_keep(bits, 0, drop_thresh) ? o[t] * drop_scale : 0.f;
+            o[t + 1] = dropout_keep(bits, 1, drop_thresh) ? o[t + 1] * drop_scale : 0.f;
+          }
         }
         if (round_out) {
 #pragma unroll
@@ -128,9 +132,13 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
         float4 dyv = ld4(dy + row * d + c);
         if (drop_thresh) {
           float* e = reinterpret_cast<float*>(&dyv);
+          const uint32_t key = dropout_row_key(drop_seed, static_cast<uint64_t>(row));
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            e[t] = dropout_keep(drop_seed, static_cast<uint64_t>(row) * d + c + t, drop_thresh) ? e[t] * drop_scale : 0.f;
+          for (int t = 0; t < 4; t += 2) {
+            const uint32_t bits = dropout_pair(key, c + t);
+            e[t] = dropout_keep(bits, 0, drop_thresh) ? e[t] * drop_scale : 0.f;
+            e[t + 1] = dropout_keep(bits, 1, drop_thresh) ? e[t + 1] * drop_scale : 0.f;
+          }
         }
         const float4 zv = ld4(z + row * d + c);
         xh[i] = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
