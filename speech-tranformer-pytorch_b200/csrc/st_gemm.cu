@@ -2,13 +2,19 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..5  : epilogue (tcgen05.ld -> bias / ReLU / residual / TF32 rounding -> global)
+//   warps 2..5  : epilogue (tcgen05.ld -> smem transpose -> bias / ReLU / dropout / residual / TF32
+//                 rounding -> coalesced global stores)
 //
 // Output tile 128 x BN (BN in {64,128,256}); K is consumed in blocks of 32 fp32 (= one 128-byte
 // swizzle atom); accumulators are double-buffered in TMEM (2*BN columns) so the epilogue of
 // tile i overlaps the main loop of tile i+1.  Operands may be K-major or MN-major (see
-// st_common.cuh; MN-major TF32 tiles use the 32-byte-atom swizzle), which covers forward (NT), data-gradient (NN) and weight-gradient (TN) GEMMs
-// without any transposed copies in HBM.
+// st_common.cuh; MN-major TF32 tiles use the 32-byte-atom swizzle), which covers forward (NT),
+// data-gradient (NN) and weight-gradient (TN) GEMMs without any transposed copies in HBM.
+//
+// Epilogue: a TMEM lane is an output row, so tcgen05.ld hands each thread 32 consecutive columns
+// of ITS row; storing that directly would touch 32 different 128-byte lines per instruction.  Each
+// epilogue warp therefore transposes 32x32 blocks through a padded smem tile and stores 4 full
+// 128-byte row segments per instruction (bias and residual loads are coalesced the same way).
 #include "st_common.cuh"
 #include "st_gemm.cuh"
 #include "st_host.h"
@@ -21,6 +27,8 @@ constexpr int BM = 128;
 constexpr int BK = 32;                       // fp32 elements per k-block = 128 bytes
 constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
 constexpr int GEMM_THREADS = 192;
+constexpr int EPI_LD = 36;                   // padded row length (floats) of the per-warp transpose tile
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
 
 template <int BN>
 struct GemmCfg {
@@ -28,7 +36,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -49,7 +57,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + EPI_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -140,7 +149,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            // K-major: +32 B per MMA inside the 128 B swizzle row.  MN-major: next 8-row K atom (+1024 B);
+            // K-major: +32 B per MMA inside the 128 B swizzle row.  MN-major: next 8-row K atom pair (+1024 B);
             // 32-wide MN groups are 4096 B apart (one TMA box each).
             const uint64_t adesc = A_MN ? umma_desc_mnmajor(sa + k * 1024, 4096) : umma_desc_kmajor(sa + k * 32);
             const uint64_t bdesc = B_MN ? umma_desc_mnmajor(sb + k * 1024, 4096) : umma_desc_kmajor(sb + k * 32);
@@ -158,94 +167,92 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const GemmEpilogue& ep = p.ep;
+    float* stg = epi_smem + (warp - 2) * (32 * EPI_LD);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    const bool aux_vec_ok = ep.aux && ((ep.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0);
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0) &&
+                        (!ep.aux || (((ep.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0)));
+    const int lcol = (lane & 7) * 4;   // this lane's 4 columns inside a 32-column chunk
+    const int lrow = lane >> 3;        // and its row inside each group of 4 rows
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles;
       const int m_blk = (tile / p.n_tiles) % p.m_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      float* crow = p.C + static_cast<int64_t>(row) * p.ldc;
-      const float* auxrow = ep.aux ? ep.aux + static_cast<int64_t>(row) * ep.ldaux : nullptr;
-      const uint32_t drop_key = ep.drop_thresh ? dropout_row_key(ep.drop_seed, static_cast<uint64_t>(row)) : 0u;
+      const int row_base = m_blk * BM + quarter * 32;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.N) {
-          const bool full = (col0 + 32 <= p.N);
+        const int col = n_blk * BN + c * 32 + lcol;
+        if (n_blk * BN + c * 32 >= p.N) break;  // warp-uniform: nothing left in this tile row-block
+        {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float v[4];
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * EPI_LD + j * 4) =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                            __uint_as_float(r[4 * j + 3]));
+        }
+        __syncwarp();
+        float b4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ep.bias) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) v[t] = __uint_as_float(r[j + t]);
-            const int col = col0 + j;
-            if (full || col + 3 < p.N) {
-              if (ep.bias) {
-                const float4 b4 = *reinterpret_cast<const float4*>(ep.bias + col);  // N%4==0 checked on host
-                v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
-              }
-              if (ep.relu) {
+          for (int t = 0; t < 4; ++t)
+            if (col + t < p.N) b4[t] = ep.bias[col + t];
+        }
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + lrow;
+          const int row = row_base + rr;
+          if (row >= p.M || col >= p.N) continue;
+          const float4 s4 = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + lcol);
+          float v[4] = {s4.x + b4[0], s4.y + b4[1], s4.z + b4[2], s4.w + b4[3]};
+          if (ep.relu) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
-              }
-              if (ep.drop_thresh) {
+            for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
+          }
+          if (ep.drop_thresh) {
+            const uint32_t key = dropout_row_key(ep.drop_seed, static_cast<uint64_t>(row));
 #pragma unroll
-                for (int t = 0; t < 4; t += 2) {  // col is a multiple of 4: one hash per column pair
-                  const uint32_t bits = dropout_pair(drop_key, col + t);
-                  v[t] = dropout_keep(bits, 0, ep.drop_thresh) ? v[t] * ep.drop_scale : 0.f;
-                  v[t + 1] = dropout_keep(bits, 1, ep.drop_thresh) ? v[t + 1] * ep.drop_scale : 0.f;
-                }
-              }
-              if (ep.aux_mode) {
-                float a[4];
-                if (aux_vec_ok) {
-                  const float4 a4 = *reinterpret_cast<const float4*>(auxrow + col);
-                  a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
-                } else {
+            for (int t = 0; t < 4; t += 2) {  // col is a multiple of 4: one hash per column pair
+              const uint32_t bits = dropout_pair(key, col + t);
+              v[t] = ((bits & 0xFFFFu) >= ep.drop_thresh) ? v[t] * ep.drop_scale : 0.f;
+              v[t + 1] = ((bits >> 16) >= ep.drop_thresh) ? v[t + 1] * ep.drop_scale : 0.f;
+            }
+          }
+          float* cp = p.C + static_cast<int64_t>(row) * p.ldc + col;
+          const float* ap = ep.aux ? ep.aux + static_cast<int64_t>(row) * ep.ldaux + col : nullptr;
+          if (vec_ok) {  // all 4 columns in range (N % 4 == 0)
+            if (ep.aux_mode) {
+              const float4 a4 = *reinterpret_cast<const float4*>(ap);
+              const float a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-                  for (int t = 0; t < 4; ++t) a[t] = auxrow[col + t];
-                }
+              for (int t = 0; t < 4; ++t) v[t] = (ep.aux_mode == 1) ? v[t] + a[t] : (a[t] > 0.f ? v[t] * ep.aux_scale : 0.f);
+            }
+            if (ep.round_tf32) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) v[t] = (ep.aux_mode == 1) ? v[t] + a[t] : (a[t] > 0.f ? v[t] * ep.aux_scale : 0.f);
-              }
-              if (ep.round_tf32) {
+              for (int t = 0; t < 4; ++t) v[t] = tf32_rna(v[t]);
+            }
+            if (ep.atomic) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) v[t] = tf32_rna(v[t]);
-              }
-              if (ep.atomic) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) atomicAdd(crow + col + t, v[t]);
-              } else if (vec_ok) {
-                *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
-              } else {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) crow[col + t] = v[t];
-              }
+              for (int t = 0; t < 4; ++t) atomicAdd(cp + t, v[t]);
             } else {
-              // ragged N tail: scalar path
-              for (int t = 0; t < 4; ++t) {
-                const int cc = col + t;
-                if (cc >= p.N) break;
-                float x = v[t];
-                if (ep.bias) x += ep.bias[cc];
-                if (ep.relu) x = fmaxf(x, 0.f);
-                if (ep.drop_thresh)
-                  x = dropout_keep(dropout_pair(drop_key, cc), cc, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
-                if (ep.aux_mode == 1) x += auxrow[cc];
-                if (ep.aux_mode == 2) x = auxrow[cc] > 0.f ? x * ep.aux_scale : 0.f;
-                if (ep.round_tf32) x = tf32_rna(x);
-                if (ep.atomic) atomicAdd(crow + cc, x); else crow[cc] = x;
-              }
+              *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (col + t >= p.N) break;
+              float x = v[t];
+              if (ep.aux_mode == 1) x += ap[t];
+              if (ep.aux_mode == 2) x = ap[t] > 0.f ? x * ep.aux_scale : 0.f;
+              if (ep.round_tf32) x = tf32_rna(x);
+              if (ep.atomic) atomicAdd(cp + t, x); else cp[t] = x;
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -292,6 +299,19 @@ int dispatch_mode(cudaStream_t stream, GemmMode mode, const CUtensorMap& ta, con
   return ST_ERR_INVALID;
 }
 
+// Tile width: 256 when that still gives every SM a tile; otherwise narrower tiles spread a small problem
+// (decoder-side GEMMs with M = B*L ~ 1600 rows) over more SMs.
+int pick_bn(int M, int N, int k_splits) {
+  if (N <= 64) return 64;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int sms = num_sms();
+  const int forced = get_option("gemm_bn");
+  if (forced == 64 || forced == 128 || forced == 256) return (forced > 64 && N <= 64) ? 64 : forced;
+  if (N > 128 && m_tiles * ((N + 255) / 256) * k_splits >= sms) return 256;
+  if (N > 64 && m_tiles * ((N + 127) / 128) * k_splits >= sms) return 128;
+  return 64;
+}
+
 }  // namespace
 
 int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
@@ -301,19 +321,17 @@ int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, c
              "gemm_tf32: operands must be 16-byte aligned");
   ST_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "gemm_tf32: lda=%lld ldb=%lld must be multiples of 4 floats",
              (long long)lda, (long long)ldb);
-  ST_REQUIRE(!ep.bias || ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0),
-             "gemm_tf32: bias needs N%%4==0 and 16-byte alignment");
   ST_REQUIRE(k_splits >= 1 && (k_splits == 1 || ep.atomic), "gemm_tf32: split-K needs the atomic epilogue");
 
-  const int BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
   GemmParams p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
-  p.m_tiles = (M + BM - 1) / BM;
-  p.n_tiles = (N + BN - 1) / BN;
   p.kblocks_total = (K + BK - 1) / BK;
   if (k_splits > p.kblocks_total) k_splits = p.kblocks_total;
   p.kblocks_per_split = (p.kblocks_total + k_splits - 1) / k_splits;
   p.k_splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  const int BN = pick_bn(M, N, p.k_splits);
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + BN - 1) / BN;
   p.ep = ep;
 
   CUtensorMap ta, tb;

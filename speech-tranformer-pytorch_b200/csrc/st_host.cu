@@ -35,7 +35,7 @@ namespace {
 struct Option { const char* name; int value; };
 Option g_options[] = {
     {"gemm_max_ctas", 0},   // 0 = one CTA per SM; >0 caps the persistent grid (tests multi-tile paths)
-    {"attn_p_smem", 0},     // 1 = stage softmax probabilities through smem instead of TMEM
+    {"gemm_bn", 0},         // 0 = heuristic; 64/128/256 forces the GEMM tile width (tuning / tests)
 };
 }  // namespace
 
