@@ -38,6 +38,7 @@ int64_t st_launch_count(void);              /* kernels this library has launched
  * `work` is the algorithmic FLOP count (tensor-core classes) or byte count (HBM classes) of the launches.  */
 int st_profile_enable(int on);
 int st_profile_reset(void);
+int st_profile_dump(const char* path /* host */);   /* CSV of every recorded launch: index,class,work,ms */
 int st_profile_classes(void);
 const char* st_profile_class_name(int cls);
 int st_profile_read(int cls, double* ms /* host */, double* work /* host */, int64_t* launches /* host */);

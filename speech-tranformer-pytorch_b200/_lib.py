@@ -89,6 +89,7 @@ SIGNATURES = {
     "st_launch_count": (i64, []),
     "st_profile_enable": (C.c_int, [C.c_int]),
     "st_profile_reset": (C.c_int, []),
+    "st_profile_dump": (C.c_int, [C.c_char_p]),
     "st_profile_classes": (C.c_int, []),
     "st_profile_class_name": (C.c_char_p, [C.c_int]),
     "st_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),

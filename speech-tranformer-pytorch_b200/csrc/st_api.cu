@@ -178,6 +178,7 @@ int st_set_option(const char* name, int v) { return set_option(name, v); }
 int64_t st_launch_count(void) { return static_cast<int64_t>(launch_count()); }
 int st_profile_enable(int on) { profile_enable(on); return ST_OK; }
 int st_profile_reset(void) { profile_reset(); return ST_OK; }
+int st_profile_dump(const char* path) { return profile_dump(path); }
 int st_profile_classes(void) { return PROF_NUM; }
 const char* st_profile_class_name(int cls) {
   static const char* names[PROF_NUM] = {"gemm_tf32", "attn_fwd", "attn_bwd_dkv", "attn_bwd_dq", "attn_bwd_delta", "add_ln_fwd",

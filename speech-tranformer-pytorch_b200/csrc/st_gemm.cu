@@ -184,6 +184,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int c = 0; c < BN / 32; ++c) {
         const int col = n_blk * BN + c * 32 + lcol;
         if (n_blk * BN + c * 32 >= p.N) break;  // warp-uniform: nothing left in this tile row-block
+        // residual / ReLU-mask operand: issue all 8 row loads of this chunk now so their HBM latency overlaps the
+        // TMEM read and the smem transpose instead of serialising inside the store loop
+        float4 aux4[8];
+        if (ep.aux_mode && vec_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = row_base + i * 4 + lrow;
+            aux4[i] = (row < p.M && col < p.N)
+                          ? __ldg(reinterpret_cast<const float4*>(ep.aux + static_cast<int64_t>(row) * ep.ldaux + col))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         {
           uint32_t r[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, r);
@@ -201,7 +213,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int t = 0; t < 4; ++t)
             if (col + t < p.N) b4[t] = ep.bias[col + t];
         }
-#pragma unroll 2
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + lrow;
           const int row = row_base + rr;
@@ -225,8 +237,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const float* ap = ep.aux ? ep.aux + static_cast<int64_t>(row) * ep.ldaux + col : nullptr;
           if (vec_ok) {  // all 4 columns in range (N % 4 == 0)
             if (ep.aux_mode) {
-              const float4 a4 = *reinterpret_cast<const float4*>(ap);
-              const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+              const float a[4] = {aux4[i].x, aux4[i].y, aux4[i].z, aux4[i].w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) v[t] = (ep.aux_mode == 1) ? v[t] + a[t] : (a[t] > 0.f ? v[t] * ep.aux_scale : 0.f);
             }

@@ -95,6 +95,21 @@ int profile_read(int cls, double* ms, double* work, long long* launches) {
   return ST_OK;
 }
 
+int profile_dump(const char* path) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  FILE* f = fopen(path, "w");
+  if (!f) { set_error("profile_dump: cannot open %s", path); return ST_ERR_INVALID; }
+  fprintf(f, "index,class,work,ms\n");
+  int i = 0;
+  for (auto& r : g_prof) {
+    float e = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&e, r.a, r.b);
+    fprintf(f, "%d,%d,%.0f,%.6f\n", i++, r.cls, r.work, e);
+  }
+  fclose(f);
+  return ST_OK;
+}
+
 void profile_reset() {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -72,6 +72,7 @@ struct ProfScope {
 void profile_enable(int on);
 int profile_read(int cls, double* ms, double* work, long long* launches);  // synchronises; sums since the last reset
 void profile_reset();
+int profile_dump(const char* path);  // CSV: one line per recorded launch
 
 // debug / tuning options (st_set_option over the C ABI); unknown names are rejected.
 int set_option(const char* name, int value);

@@ -1,0 +1,37 @@
+"""One profiled training step of the headline model: per-(kernel class, work size) launch statistics.
+python tools/profile_step.py [--layers 6] [--batch 32] [--frames 1000] [--dropout 0.1] [--csv out.csv]"""
+import argparse, collections, ctypes as C, os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import speech_tranformer_pytorch_b200 as stb
+from speech_tranformer_pytorch_b200 import data as sdata, model as smodel, parallel as spar
+ap = argparse.ArgumentParser()
+ap.add_argument("--layers", type=int, default=6); ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--frames", type=int, default=1000); ap.add_argument("--dropout", type=float, default=0.1)
+ap.add_argument("--csv", default="gpurun_out/profile_step.csv")
+a = ap.parse_args()
+lib = stb._lib.load(); dev = torch.device("cuda", 0); V = 4337
+torch.manual_seed(2018)
+net = smodel.Transformer(smodel.headline_config(num_enc_layer=a.layers, num_dec_layer=a.layers, dropout=a.dropout))
+smodel.init_parameters(net); net = net.to(dev).train()
+crit = stb.LabelSmoothingLoss(0.1, V, weight=torch.ones(V, device=dev), ignore_index=0).to(dev)
+tr = spar.DataParallelTrainer(net, d_model=512)
+batch = [t.to(dev) for t in sdata.synthetic_batch(a.batch, a.frames, 50, 80, V)]
+def step():
+    inputs, targets, il, tl, truth = batch
+    return tr.train_step(lambda: crit(net(inputs, il, targets, tl)[0].view(-1, V), truth.view(-1)))
+for _ in range(3): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); step(); e1.record(); torch.cuda.synchronize()
+print(f"unprofiled step: {e0.elapsed_time(e1):.2f} ms")
+lib.st_profile_reset(); lib.st_profile_enable(1); step(); torch.cuda.synchronize(); lib.st_profile_enable(0)
+os.makedirs(os.path.dirname(a.csv) or ".", exist_ok=True)
+lib.st_profile_dump(a.csv.encode())
+names = [lib.st_profile_class_name(i).decode() for i in range(lib.st_profile_classes())]
+groups = collections.OrderedDict()
+for line in open(a.csv).read().splitlines()[1:]:
+    _, cls, work, ms = line.split(","); k = (int(cls), float(work)); g = groups.setdefault(k, [0, 0.0]); g[0] += 1; g[1] += float(ms)
+tot = sum(g[1] for g in groups.values())
+print(f"profiled kernels total {tot:.2f} ms")
+for (cls, work), (n, ms) in sorted(groups.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f"{names[cls]:15s} work {work:14.4g} x{n:3d}  total {ms:7.3f} ms  avg {ms / n * 1e3:8.1f} us  rate {work * n / ms / 1e9:8.1f} G/s*1e3")
