@@ -24,6 +24,11 @@ DropoutCfg make_dropout(float p, uint64_t seed) {
     c.thresh = static_cast<uint32_t>(t);
     c.scale = 65536.f / static_cast<float>(65536 - t);
     c.seed = seed;
+    double t32 = floor(static_cast<double>(p) * 4294967296.0);
+    if (t32 < 1.0) t32 = 1.0;
+    if (t32 > 4294967295.0) t32 = 4294967295.0;
+    c.thresh32 = static_cast<uint32_t>(t32);
+    c.scale32 = static_cast<float>(4294967296.0 / (4294967296.0 - t32));
   }
   return c;
 }

@@ -93,27 +93,25 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], uint32_t mb)
   return mx;
 }
 
-// r <- tf32(dropout(exp2(r*scale_log2 - m))) with masked entries 0; returns the (pre-dropout) row-sum part.
-// col0 is the global key index of r[0] (even), key the per-row dropout key.
+// r <- tf32(keep ? exp2(r*scale_log2 - m) : 0) with masked entries 0; returns the (pre-dropout) row-sum part.
+// The inverted-dropout scale is NOT applied here (it is folded into the final normalisation of O).
+// ckey: this chunk's 32 per-column dropout keys in shared memory (16-byte aligned); rowkey: the row's key.
 __device__ __forceinline__ float chunk_probs(uint32_t (&r)[32], uint32_t mb, float scale_log2, float m_use,
-                                             uint32_t thresh, float dscale, uint32_t key, uint32_t col0) {
+                                             uint32_t thresh, uint32_t rowkey, const uint32_t* ckey) {
   float l = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_use));
-    float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_use));
-    if (mb != 0u) {
-      if ((mb >> i) & 1u) p0 = 0.f;
-      if ((mb >> (i + 1)) & 1u) p1 = 0.f;
+  for (int i = 0; i < 32; i += 4) {
+    uint4 ck = make_uint4(0u, 0u, 0u, 0u);
+    if (thresh) ck = *reinterpret_cast<const uint4*>(ckey + i);
+    const uint32_t cks[4] = {ck.x, ck.y, ck.z, ck.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float pv = fast_exp2(fmaf(__uint_as_float(r[i + t]), scale_log2, -m_use));
+      if (mb != 0u && ((mb >> (i + t)) & 1u)) pv = 0.f;
+      l += pv;
+      if (thresh && !dropout_keep_xor(rowkey, cks[t], thresh)) pv = 0.f;
+      r[i + t] = __float_as_uint(tf32_rna(pv));
     }
-    l += p0 + p1;
-    if (thresh) {
-      const uint32_t bits = dropout_pair(key, col0 + i);
-      p0 = ((bits & 0xFFFFu) >= thresh) ? p0 * dscale : 0.f;
-      p1 = ((bits >> 16) >= thresh) ? p1 * dscale : 0.f;
-    }
-    r[i] = __float_as_uint(tf32_rna(p0));
-    r[i + 1] = __float_as_uint(tf32_rna(p1));
   }
   return l;
 }
@@ -141,6 +139,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __shared__ uint64_t bar_q, bar_k, bar_v, bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_part[2][BQ];
+  __shared__ __align__(16) uint32_t s_ckey[BKV];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
@@ -210,6 +209,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     ++s_count;
     tc_fence_after();
     if (tid == 0 && j + 1 < n_kv) load_k(j + 1);  // S_j has consumed K_j
+    if (p.drop_thresh && tid < BKV) s_ckey[tid] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(j * BKV + tid));
 
     // ---- pass 1: row max over this thread's half of the tile, combined through smem
     uint32_t mbits[NCH];
@@ -237,8 +237,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint32_t r[32];
       tmem_ld32(t_lane + T_S + col0, r);
       tmem_ld_wait();
-      l_tile += chunk_probs(r, mbits[c], p.scale_log2, m_use, p.drop_thresh, p.drop_scale, drop_key,
-                            static_cast<uint32_t>(j * BKV + col0));
+      l_tile += chunk_probs(r, mbits[c], p.scale_log2, m_use, p.drop_thresh, drop_key, s_ckey + col0);
       tmem_st32(t_lane + T_S + col0, r);
     }
     l_run = l_run * alpha + l_tile;
@@ -292,7 +291,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   s_part[half][rit] = l_run;
   __syncthreads();
   const float l_tot = s_part[0][rit] + s_part[1][rit];
-  const float inv_l = 1.f / l_tot;
+  const float inv_l = (p.drop_thresh ? p.drop_scale : 1.f) / l_tot;   // inverted-dropout scale folded in here
   const float lse2 = m_run + log2f(l_tot);
   if (row_ok) {
     float* dst = p.ctx + (static_cast<int64_t>(b) * p.Lq + row) * p.ldctx + h * DK + half * OH;
@@ -333,7 +332,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             float pv = ((mb >> i) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, -lse2));
             if (l_tot == 0.f) pv = __int_as_float(0x7fc00000);  // fully masked row: NaN like softmax(-inf row)
             if (p.drop_thresh)
-              pv = dropout_keep(dropout_pair(drop_key, k0 + i), k0 + i, p.drop_thresh) ? pv * p.drop_scale : 0.f;
+              pv = dropout_keep_xor(drop_key, dropout_col_key(p.drop_seed, static_cast<uint32_t>(k0 + i)), p.drop_thresh)
+                       ? pv * p.drop_scale : 0.f;
             dst[i] = pv;
           }
         }
@@ -397,8 +397,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
   uint8_t* sDOm = sDOk + QT_BYTES;
   __shared__ uint64_t bar_kv, bar_ld, bar_s, bar_acc;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_lse[BQ], s_delta[BQ];
-  __shared__ uint32_t s_key[BQ];
+  __shared__ __align__(16) float s_lse[BQ];
+  __shared__ __align__(16) float s_delta[BQ];
+  __shared__ __align__(16) uint32_t s_key[BQ];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, slice = warp >> 2;
@@ -433,7 +434,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
   bool key_masked = !key_ok;
   if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
   const bool mask_dense = (p.mask != nullptr) && !mask_per_key;
-  const uint32_t ukey = static_cast<uint32_t>(key_ok ? key : 0);
+  const uint32_t my_ckey = p.drop_thresh ? dropout_col_key(p.drop_seed, static_cast<uint32_t>(key_ok ? key : 0)) : 0u;
+  const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
 
   for (int it = 0; it < n_q; ++it) {
     const int q0 = it * BQ;
@@ -482,26 +484,33 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
       tmem_ld32(t_lane + T_ST + c * 32, rs);
       tmem_ld32(t_lane + T_DPT + c * 32, rd);
       tmem_ld_wait();
+      // The inverted-dropout scale of P (-> dV) and the softmax scale of dS (-> dK) are applied once in the epilogue.
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int qi = c * 32 + i;
-        bool masked = key_masked;
-        if (mask_dense) {
-          const int q = q0 + qi;
-          if (key_ok && q < p.Lq)
-            masked = p.mask[b * p.ms_b + static_cast<int64_t>(q) * p.ms_q + static_cast<int64_t>(key) * p.ms_k] != 0;
+      for (int i = 0; i < 32; i += 4) {
+        const int qb = c * 32 + i;
+        const float4 lse4 = *reinterpret_cast<const float4*>(s_lse + qb);
+        const float4 del4 = *reinterpret_cast<const float4*>(s_delta + qb);
+        uint4 key4 = make_uint4(0u, 0u, 0u, 0u);
+        if (p.drop_thresh) key4 = *reinterpret_cast<const uint4*>(s_key + qb);
+        const float lses[4] = {lse4.x, lse4.y, lse4.z, lse4.w};
+        const float dels[4] = {del4.x, del4.y, del4.z, del4.w};
+        const uint32_t rks[4] = {key4.x, key4.y, key4.z, key4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          bool masked = key_masked;
+          if (mask_dense) {
+            const int q = q0 + qb + t;
+            if (key_ok && q < p.Lq)
+              masked = p.mask[b * p.ms_b + static_cast<int64_t>(q) * p.ms_q + static_cast<int64_t>(key) * p.ms_k] != 0;
+          }
+          const float pr = masked ? 0.f : fast_exp2(fmaf(__uint_as_float(rs[i + t]), p.scale_log2, -lses[t]));
+          float dp = __uint_as_float(rd[i + t]);
+          float pd = pr;
+          if (p.drop_thresh && !dropout_keep_xor(rks[t], my_ckey, p.drop_thresh)) { pd = 0.f; dp = 0.f; }
+          const float ds = pr * fmaf(dp, dscale, -dels[t]);
+          rs[i + t] = __float_as_uint(tf32_rna(pd));
+          rd[i + t] = __float_as_uint(tf32_rna(ds));
         }
-        const float pr = masked ? 0.f : fast_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -s_lse[qi]));
-        float dp = __uint_as_float(rd[i]);
-        float pd = pr;
-        if (p.drop_thresh) {
-          const bool keep = dropout_keep(dropout_pair(s_key[qi], ukey), ukey, p.drop_thresh);
-          pd = keep ? pr * p.drop_scale : 0.f;
-          dp = keep ? dp * p.drop_scale : 0.f;
-        }
-        const float ds = pr * (dp - s_delta[qi]) * p.scale;
-        rs[i] = __float_as_uint(tf32_rna(pd));
-        rd[i] = __float_as_uint(tf32_rna(ds));
       }
       tmem_st32(t_lane + T_ST + c * 32, rs);
       tmem_st32(t_lane + T_DPT + c * 32, rd);
@@ -538,11 +547,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         *reinterpret_cast<float4*>(dvp + i) =
-            make_float4(tf32_rna(__uint_as_float(rv[i])), tf32_rna(__uint_as_float(rv[i + 1])),
-                        tf32_rna(__uint_as_float(rv[i + 2])), tf32_rna(__uint_as_float(rv[i + 3])));
+            make_float4(tf32_rna(__uint_as_float(rv[i]) * dscale), tf32_rna(__uint_as_float(rv[i + 1]) * dscale),
+                        tf32_rna(__uint_as_float(rv[i + 2]) * dscale), tf32_rna(__uint_as_float(rv[i + 3]) * dscale));
         *reinterpret_cast<float4*>(dkp + i) =
-            make_float4(tf32_rna(__uint_as_float(rk[i])), tf32_rna(__uint_as_float(rk[i + 1])),
-                        tf32_rna(__uint_as_float(rk[i + 2])), tf32_rna(__uint_as_float(rk[i + 3])));
+            make_float4(tf32_rna(__uint_as_float(rk[i]) * p.scale), tf32_rna(__uint_as_float(rk[i + 1]) * p.scale),
+                        tf32_rna(__uint_as_float(rk[i + 2]) * p.scale), tf32_rna(__uint_as_float(rk[i + 3]) * p.scale));
       }
     }
   }
@@ -575,6 +584,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint8_t* sVk = sKm + KT_BYTES;
   __shared__ uint64_t bar_q, bar_ld, bar_s, bar_acc;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) uint32_t s_ckey[BKV];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, slice = warp >> 2;
@@ -608,6 +618,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
   const float delta = row_ok ? p.delta[stat] : 0.f;
   const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(stat)) : 0u;
+  const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
 
   for (int j = 0; j < n_kv; ++j) {
     if (tid == 0) {
@@ -634,6 +645,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                      umma_desc_kmajor(bv + (ks / 4) * (BKV * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
       umma_commit(&bar_s);
     }
+    if (p.drop_thresh) {  // per-column dropout keys of this key tile (previous readers passed the barrier below)
+      if (tid < BKV) s_ckey[tid] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(j * BKV + tid));
+      __syncthreads();
+    }
     mbar_wait(&bar_s, j & 1);
     tc_fence_after();
     {
@@ -644,22 +659,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tmem_ld32(t_lane + T_S + c * 32, rs);
       tmem_ld32(t_lane + T_DP + c * 32, rd);
       tmem_ld_wait();
+      // dS without the softmax scale (applied once to dQ in the epilogue)
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float p0 = fast_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2));
-        float p1 = fast_exp2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -lse2));
-        if (mb != 0u) {
-          if ((mb >> i) & 1u) p0 = 0.f;
-          if ((mb >> (i + 1)) & 1u) p1 = 0.f;
+      for (int i = 0; i < 32; i += 4) {
+        uint4 ck = make_uint4(0u, 0u, 0u, 0u);
+        if (p.drop_thresh) ck = *reinterpret_cast<const uint4*>(s_ckey + c * 32 + i);
+        const uint32_t cks[4] = {ck.x, ck.y, ck.z, ck.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float pr = fast_exp2(fmaf(__uint_as_float(rs[i + t]), p.scale_log2, -lse2));
+          if (mb != 0u && ((mb >> (i + t)) & 1u)) pr = 0.f;
+          float dp = __uint_as_float(rd[i + t]);
+          if (p.drop_thresh && !dropout_keep_xor(drop_key, cks[t], p.drop_thresh)) dp = 0.f;
+          rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -delta)));
         }
-        float d0 = __uint_as_float(rd[i]), d1 = __uint_as_float(rd[i + 1]);
-        if (p.drop_thresh) {
-          const uint32_t bits = dropout_pair(drop_key, static_cast<uint32_t>(k0 + i));
-          d0 = ((bits & 0xFFFFu) >= p.drop_thresh) ? d0 * p.drop_scale : 0.f;
-          d1 = ((bits >> 16) >= p.drop_thresh) ? d1 * p.drop_scale : 0.f;
-        }
-        rd[i] = __float_as_uint(tf32_rna(p0 * (d0 - delta) * p.scale));
-        rd[i + 1] = __float_as_uint(tf32_rna(p1 * (d1 - delta) * p.scale));
       }
       tmem_st32(t_lane + T_DP + c * 32, rd);
     }
@@ -689,8 +702,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
       for (int i = 0; i < 32; i += 4)
         *reinterpret_cast<float4*>(dst + i) =
-            make_float4(tf32_rna(__uint_as_float(r[i])), tf32_rna(__uint_as_float(r[i + 1])),
-                        tf32_rna(__uint_as_float(r[i + 2])), tf32_rna(__uint_as_float(r[i + 3])));
+            make_float4(tf32_rna(__uint_as_float(r[i]) * p.scale), tf32_rna(__uint_as_float(r[i + 1]) * p.scale),
+                        tf32_rna(__uint_as_float(r[i + 2]) * p.scale), tf32_rna(__uint_as_float(r[i + 3]) * p.scale));
     }
   }
   tc_fence_before();
@@ -722,7 +735,7 @@ AttnDev to_dev(const AttnArgs& a) {
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk;
   p.mask = a.mask; p.ms_b = a.ms_b; p.ms_q = a.ms_q; p.ms_k = a.ms_k;
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
-  p.drop_thresh = a.drop.thresh; p.drop_scale = a.drop.scale; p.drop_seed = a.drop.seed;
+  p.drop_thresh = a.drop.thresh32; p.drop_scale = a.drop.scale32; p.drop_seed = a.drop.seed;
   p.ctx = a.ctx; p.ldctx = a.ldctx; p.lse2 = a.lse; p.attn = a.attn;
   return p;
 }

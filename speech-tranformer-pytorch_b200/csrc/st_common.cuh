@@ -281,6 +281,17 @@ __device__ __forceinline__ bool dropout_keep(uint32_t pair_bits, uint32_t col, u
   return ((col & 1u) ? (pair_bits >> 16) : (pair_bits & 0xFFFFu)) >= thresh16;
 }
 
+// Attention-probability dropout: element (row, col) is kept iff ((row_key ^ col_key) * odd) >= thresh32.
+// Row and column keys are full 32-bit hashes computed once per row / per column, so the per-element cost is
+// three integer ops, and forward (row-major traversal) and backward (column-major traversal in the dK/dV
+// kernel) regenerate identical masks.
+__device__ __forceinline__ uint32_t dropout_col_key(uint64_t seed, uint32_t col) {
+  return mix32((col * 0x9E3779B9u + 0x7F4A7C15u) ^ static_cast<uint32_t>(seed >> 32) ^ 0x5bd1e995u);
+}
+__device__ __forceinline__ bool dropout_keep_xor(uint32_t row_key, uint32_t col_key, uint32_t thresh32) {
+  return ((row_key ^ col_key) * 0x9E3779B1u) >= thresh32;
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; -inf -> 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

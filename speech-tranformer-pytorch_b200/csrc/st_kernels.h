@@ -8,9 +8,11 @@ namespace st {
 // Inverted dropout with a stateless counter RNG: element idx is kept iff hash(seed, idx) >= thresh
 // and then scaled by `scale` = 1/(1-p).  thresh == 0 disables dropout.
 struct DropoutCfg {
-  uint32_t thresh = 0;
+  uint32_t thresh = 0;     // 16-bit threshold (drop probability thresh/65536) for the pair-hash scheme
   float scale = 1.f;
   uint64_t seed = 0;
+  uint32_t thresh32 = 0;   // 32-bit threshold (drop probability thresh32/2^32) for the attention xor-key scheme
+  float scale32 = 1.f;
 };
 DropoutCfg make_dropout(float p, uint64_t seed);
 

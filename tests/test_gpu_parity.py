@@ -189,6 +189,40 @@ def test_attention_core(stb, B, H, Lq, Lk, dk, kind):
         assert relerr(a, b) < TOL_ATTN, n
 
 
+@pytest.mark.parametrize("B,H,L,dk", [(2, 4, 200, 64), (1, 2, 130, 32), (1, 2, 70, 128)])
+def test_attention_dropout_forward_backward_consistent(stb, B, H, L, dk):
+    """Dropout on the attention probabilities (Attention.py:89): the reference RNG stream cannot be matched, so
+    the kept set is read back from the returned (post-dropout) weights and the oracle is evaluated with exactly
+    that mask.  Forward and BOTH backward kernels must have used the same mask, or the gradients disagree."""
+    F = stb.functional
+    p_drop, d = 0.3, H * dk
+    gen = torch.Generator().manual_seed(L)
+    q, k, v, g = (torch.randn(B, L, d, generator=gen) for _ in range(4))
+    lens = torch.tensor([L, L - 9][:B])
+    mask = O.padding_info_mask(lens, lens).bool()
+    cq, ck, cv = (x.to(DEV).requires_grad_() for x in (q, k, v))
+    co, cw = F.attention_core(cq, ck, cv, mask.to(DEV), n_head=H, dropout_p=p_drop, seed=1234, need_attn=True)
+    co.backward(g.to(DEV))
+    co2, cw2 = F.attention_core(cq, ck, cv, mask.to(DEV), n_head=H, dropout_p=p_drop, seed=1234, need_attn=True)
+    assert torch.equal(cw, cw2) and torch.equal(co, co2), "same seed must reproduce the mask"
+
+    rq, rk, rv = (x.clone().double().requires_grad_() for x in (q, k, v))
+    sh = lambda x: x.view(B, L, H, dk).transpose(1, 2)
+    s = torch.matmul(sh(rq), sh(rk).transpose(2, 3)) / math.sqrt(dk)
+    pr = torch.softmax(s.masked_fill(mask.unsqueeze(1), -float("inf")), -1)
+    keep = (cw.cpu() != 0)
+    visible = pr > 1e-6                      # probabilities large enough that "dropped" is distinguishable from "~0"
+    frac = 1.0 - keep[visible].double().mean().item()
+    assert abs(frac - p_drop) < 0.01, frac
+    pd = pr * keep / (1.0 - p_drop)
+    assert relerr(cw, pd) < TOL_ATTN
+    ro = torch.matmul(pd, sh(rv)).transpose(1, 2).reshape(B, L, d)
+    ro.backward(g.double())
+    assert relerr(co, ro) < TOL_ATTN
+    for a, b_, n in ((cq.grad, rq.grad, "dq"), (ck.grad, rk.grad, "dk"), (cv.grad, rv.grad, "dv")):
+        assert relerr(a, b_) < TOL_ATTN, n
+
+
 def test_fully_masked_row_is_nan(stb):
     """softmax over an all -inf row is NaN in the reference; same here, other rows unaffected."""
     F = stb.functional
