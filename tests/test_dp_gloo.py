@@ -1,0 +1,92 @@
+"""World-size-2 data-parallel logic on CPU with the gloo backend (the N>1 path of bench.py minus the kernels):
+flat parameter/gradient buffers, one all-reduce per step, parameter broadcast, Noam schedule.
+Mirrors train_multi.py:136-139,161-163,176-177."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from speech_tranformer_pytorch_b200 import parallel as P
+        torch.manual_seed(100 + rank)                      # different initial parameters on each rank
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        tr = P.DataParallelTrainer(net, d_model=512, n_warmup_steps=100, max_grad_norm=5.0)
+        # parameters are views of ONE flat buffer, 16-byte aligned each
+        assert tr.fp.numel == sum((p.numel() + 3) // 4 * 4 for p in net.parameters())
+        for p, o in zip(tr.fp.params, tr.fp.offsets):
+            assert p.data_ptr() == tr.fp.flat.data_ptr() + 4 * o and o % 4 == 0
+        tr.broadcast_parameters(0)                         # train_multi.py:176
+        flat0 = tr.fp.flat.clone()
+        gathered = [torch.empty_like(flat0) for _ in range(world)]
+        dist.all_gather(gathered, flat0)
+        assert all(torch.equal(g, gathered[0]) for g in gathered), "broadcast must equalise parameters"
+        # one step on a rank-dependent shard (DistributedSampler analogue: disjoint utterances per rank)
+        torch.manual_seed(7)
+        x_all, y_all = torch.randn(8, 6), torch.randn(8, 3)
+        xs, ys = x_all[rank::world], y_all[rank::world]
+        tr.zero_grad()
+        loss = ((net(xs) - ys) ** 2).mean()
+        loss.backward()
+        for p, o in zip(tr.fp.params, tr.fp.offsets):      # autograd accumulated INTO the flat gradient buffer
+            assert p.grad.data_ptr() == tr.fp.grad.data_ptr() + 4 * o
+        local = tr.fp.grad.clone()
+        tr.allreduce_gradients()                           # train_multi.py:161-163 — ONE collective
+        summed = tr.fp.grad.clone()
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        assert torch.allclose(summed, sum(parts)), "all-reduce(SUM) of the flat buffer"
+        # the averaged gradient equals the gradient of the mean loss over the union of the shards
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        with torch.no_grad():
+            for pr, p in zip(ref.parameters(), net.parameters()):
+                pr.copy_(p)
+        (((ref(x_all) - y_all) ** 2).mean()).backward()
+        for pr, p in zip(ref.parameters(), net.parameters()):
+            assert torch.allclose(p.grad / world, pr.grad, atol=1e-6)
+        q.put((rank, "ok", float(loss)))
+    except Exception as e:  # surface the failure in the parent
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_buffer_data_parallel_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in results:
+        assert status == "ok", f"rank {rank}: {info}"
+
+
+def test_noam_schedule_matches_reference_formula():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import numpy as np
+    from speech_tranformer_pytorch_b200 import parallel as P
+    for step in (1, 10, 11999, 12000, 12001, 50000):       # Optim.py:39-41
+        ref = np.power(512, -0.5) * np.min([np.power(step, -0.5), np.power(12000, -1.5) * step])
+        assert abs(P.noam_lr(512, 12000, step) - ref) < 1e-12
