@@ -96,24 +96,100 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], uint32_t mb)
 // r <- tf32(keep ? exp2(r*scale_log2 - m) : 0) with masked entries 0; returns the (pre-dropout) row-sum part.
 // The inverted-dropout scale is NOT applied here (it is folded into the final normalisation of O).
 // ckey: this chunk's 32 per-column dropout keys in shared memory (16-byte aligned); rowkey: the row's key.
-__device__ __forceinline__ float chunk_probs(uint32_t (&r)[32], uint32_t mb, float scale_log2, float m_use,
-                                             uint32_t thresh, uint32_t rowkey, const uint32_t* ckey) {
+template <bool MASK, bool DROP>
+__device__ __forceinline__ float chunk_probs_t(uint32_t (&r)[32], uint32_t mb, float scale_log2, float m_use,
+                                               uint32_t thresh, uint32_t rowkey, const uint32_t* ckey) {
   float l = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     uint4 ck = make_uint4(0u, 0u, 0u, 0u);
-    if (thresh) ck = *reinterpret_cast<const uint4*>(ckey + i);
+    if (DROP) ck = *reinterpret_cast<const uint4*>(ckey + i);
     const uint32_t cks[4] = {ck.x, ck.y, ck.z, ck.w};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       float pv = fast_exp2(fmaf(__uint_as_float(r[i + t]), scale_log2, -m_use));
-      if (mb != 0u && ((mb >> (i + t)) & 1u)) pv = 0.f;
+      if (MASK && ((mb >> (i + t)) & 1u)) pv = 0.f;
       l += pv;
-      if (thresh && !dropout_keep_xor(rowkey, cks[t], thresh)) pv = 0.f;
+      if (DROP && !dropout_keep_xor(rowkey, cks[t], thresh)) pv = 0.f;
       r[i + t] = __float_as_uint(tf32_rna(pv));
     }
   }
   return l;
+}
+// dispatch on (any masked entry in this chunk?, dropout on?) so the common unmasked path carries no per-element tests
+__device__ __forceinline__ float chunk_probs(uint32_t (&r)[32], uint32_t mb, float scale_log2, float m_use,
+                                             uint32_t thresh, uint32_t rowkey, const uint32_t* ckey) {
+  if (mb == 0u) {
+    return thresh ? chunk_probs_t<false, true>(r, mb, scale_log2, m_use, thresh, rowkey, ckey)
+                  : chunk_probs_t<false, false>(r, mb, scale_log2, m_use, thresh, rowkey, ckey);
+  }
+  return thresh ? chunk_probs_t<true, true>(r, mb, scale_log2, m_use, thresh, rowkey, ckey)
+                : chunk_probs_t<true, false>(r, mb, scale_log2, m_use, thresh, rowkey, ckey);
+}
+
+// dS chunk of the dQ kernel: rd <- tf32(P * (keep ? dP*dscale : 0) - P*delta), P = exp2(S*scale_log2 - lse2)
+template <bool MASK, bool DROP>
+__device__ __forceinline__ void chunk_ds_t(const uint32_t (&rs)[32], uint32_t (&rd)[32], uint32_t mb, float scale_log2,
+                                           float lse2, float delta, float dscale, uint32_t thresh, uint32_t rowkey,
+                                           const uint32_t* ckey) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    uint4 ck = make_uint4(0u, 0u, 0u, 0u);
+    if (DROP) ck = *reinterpret_cast<const uint4*>(ckey + i);
+    const uint32_t cks[4] = {ck.x, ck.y, ck.z, ck.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float pr = fast_exp2(fmaf(__uint_as_float(rs[i + t]), scale_log2, -lse2));
+      if (MASK && ((mb >> (i + t)) & 1u)) pr = 0.f;
+      float dp = __uint_as_float(rd[i + t]);
+      if (DROP && !dropout_keep_xor(rowkey, cks[t], thresh)) dp = 0.f;
+      rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -delta)));
+    }
+  }
+}
+__device__ __forceinline__ void chunk_ds(const uint32_t (&rs)[32], uint32_t (&rd)[32], uint32_t mb, float scale_log2,
+                                         float lse2, float delta, float dscale, uint32_t thresh, uint32_t rowkey,
+                                         const uint32_t* ckey) {
+  if (mb == 0u) {
+    if (thresh) chunk_ds_t<false, true>(rs, rd, mb, scale_log2, lse2, delta, dscale, thresh, rowkey, ckey);
+    else chunk_ds_t<false, false>(rs, rd, mb, scale_log2, lse2, delta, dscale, thresh, rowkey, ckey);
+  } else {
+    if (thresh) chunk_ds_t<true, true>(rs, rd, mb, scale_log2, lse2, delta, dscale, thresh, rowkey, ckey);
+    else chunk_ds_t<true, false>(rs, rd, mb, scale_log2, lse2, delta, dscale, thresh, rowkey, ckey);
+  }
+}
+
+// P^T / dS^T chunk of the dK/dV kernel (thread = key row, 32 query columns):
+//   rs <- tf32(keep ? P : 0),  rd <- tf32(P * ((keep ? dP : 0) * dscale - delta_q)),  P = exp2(S*scale_log2 - lse2_q)
+// lse / delta / rkey: this chunk's per-query statistics and dropout row keys in shared memory (16-byte aligned).
+template <bool DENSE, bool DROP>
+__device__ __forceinline__ void chunk_dkv_t(uint32_t (&rs)[32], uint32_t (&rd)[32], const float* lse, const float* delta,
+                                            const uint32_t* rkey, float scale_log2, float dscale, uint32_t thresh,
+                                            uint32_t my_ckey, const uint8_t* mrow, int64_t ms_q, int q_first, int Lq,
+                                            bool key_ok) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 lse4 = *reinterpret_cast<const float4*>(lse + i);
+    const float4 del4 = *reinterpret_cast<const float4*>(delta + i);
+    uint4 key4 = make_uint4(0u, 0u, 0u, 0u);
+    if (DROP) key4 = *reinterpret_cast<const uint4*>(rkey + i);
+    const float lses[4] = {lse4.x, lse4.y, lse4.z, lse4.w};
+    const float dels[4] = {del4.x, del4.y, del4.z, del4.w};
+    const uint32_t rks[4] = {key4.x, key4.y, key4.z, key4.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float pr = fast_exp2(fmaf(__uint_as_float(rs[i + t]), scale_log2, -lses[t]));
+      if (DENSE) {
+        const int q = q_first + i + t;
+        if (!key_ok || (q < Lq && mrow[static_cast<int64_t>(q) * ms_q] != 0)) pr = 0.f;
+      }
+      float dp = __uint_as_float(rd[i + t]);
+      float pd = pr;
+      if (DROP && !dropout_keep_xor(rks[t], my_ckey, thresh)) { pd = 0.f; dp = 0.f; }
+      rs[i + t] = __float_as_uint(tf32_rna(pd));
+      rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -dels[t])));
+    }
+  }
 }
 
 // ================================================================================ forward
@@ -140,6 +216,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __shared__ uint32_t tmem_slot;
   __shared__ float s_part[2][BQ];
   __shared__ __align__(16) uint32_t s_ckey[BKV];
+  __shared__ uint32_t s_mb[2][BKV / 32];    // mask bits of the current / next key tile when every row shares them
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
@@ -148,6 +225,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int row = q0 + rit;
   const bool row_ok = row < p.Lq;
   const int n_kv = (p.Lk + BKV - 1) / BKV;
+  // key-padding masks (stride 0 over queries, Utils.py:53-54) and "no mask" give every row of the tile the same
+  // bits: compute them once per tile (one thread per 32-key chunk), one tile ahead
+  const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
+  if (shared_mask && tid < BKV / 32) s_mb[0][tid] = mask_bits_row(p, b, 0, true, tid * 32);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
@@ -210,6 +291,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tc_fence_after();
     if (tid == 0 && j + 1 < n_kv) load_k(j + 1);  // S_j has consumed K_j
     if (p.drop_thresh && tid < BKV) s_ckey[tid] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(j * BKV + tid));
+    if (shared_mask && tid < BKV / 32 && j + 1 < n_kv)
+      s_mb[(j + 1) & 1][tid] = mask_bits_row(p, b, 0, true, (j + 1) * BKV + tid * 32);
 
     // ---- pass 1: row max over this thread's half of the tile, combined through smem
     uint32_t mbits[NCH];
@@ -217,7 +300,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col0 = half * SH + c * 32;
-      mbits[c] = mask_bits_row(p, b, row, row_ok, j * BKV + col0);
+      mbits[c] = shared_mask ? s_mb[j & 1][col0 / 32] : mask_bits_row(p, b, row, row_ok, j * BKV + col0);
       uint32_t r[32];
       tmem_ld32(t_lane + T_S + col0, r);
       tmem_ld_wait();
@@ -485,31 +568,21 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
       tmem_ld32(t_lane + T_DPT + c * 32, rd);
       tmem_ld_wait();
       // The inverted-dropout scale of P (-> dV) and the softmax scale of dS (-> dK) are applied once in the epilogue.
+      if (!mask_dense && key_masked) {  // this key is padding for every query: P = dS = 0
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const int qb = c * 32 + i;
-        const float4 lse4 = *reinterpret_cast<const float4*>(s_lse + qb);
-        const float4 del4 = *reinterpret_cast<const float4*>(s_delta + qb);
-        uint4 key4 = make_uint4(0u, 0u, 0u, 0u);
-        if (p.drop_thresh) key4 = *reinterpret_cast<const uint4*>(s_key + qb);
-        const float lses[4] = {lse4.x, lse4.y, lse4.z, lse4.w};
-        const float dels[4] = {del4.x, del4.y, del4.z, del4.w};
-        const uint32_t rks[4] = {key4.x, key4.y, key4.z, key4.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          bool masked = key_masked;
-          if (mask_dense) {
-            const int q = q0 + qb + t;
-            if (key_ok && q < p.Lq)
-              masked = p.mask[b * p.ms_b + static_cast<int64_t>(q) * p.ms_q + static_cast<int64_t>(key) * p.ms_k] != 0;
-          }
-          const float pr = masked ? 0.f : fast_exp2(fmaf(__uint_as_float(rs[i + t]), p.scale_log2, -lses[t]));
-          float dp = __uint_as_float(rd[i + t]);
-          float pd = pr;
-          if (p.drop_thresh && !dropout_keep_xor(rks[t], my_ckey, p.drop_thresh)) { pd = 0.f; dp = 0.f; }
-          const float ds = pr * fmaf(dp, dscale, -dels[t]);
-          rs[i + t] = __float_as_uint(tf32_rna(pd));
-          rd[i + t] = __float_as_uint(tf32_rna(ds));
+        for (int i = 0; i < 32; ++i) { rs[i] = 0u; rd[i] = 0u; }
+      } else {
+        const uint8_t* mrow = mask_dense ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
+        if (mask_dense) {
+          if (p.drop_thresh) chunk_dkv_t<true, true>(rs, rd, s_lse + c * 32, s_delta + c * 32, s_key + c * 32, p.scale_log2, dscale,
+                                                    p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, key_ok);
+          else chunk_dkv_t<true, false>(rs, rd, s_lse + c * 32, s_delta + c * 32, s_key + c * 32, p.scale_log2, dscale,
+                                        p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, key_ok);
+        } else {
+          if (p.drop_thresh) chunk_dkv_t<false, true>(rs, rd, s_lse + c * 32, s_delta + c * 32, s_key + c * 32, p.scale_log2, dscale,
+                                                     p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, key_ok);
+          else chunk_dkv_t<false, false>(rs, rd, s_lse + c * 32, s_delta + c * 32, s_key + c * 32, p.scale_log2, dscale,
+                                         p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, key_ok);
         }
       }
       tmem_st32(t_lane + T_ST + c * 32, rs);
@@ -585,6 +658,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __shared__ uint64_t bar_q, bar_ld, bar_s, bar_acc;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) uint32_t s_ckey[BKV];
+  __shared__ uint32_t s_mb[2][BKV / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, slice = warp >> 2;
@@ -592,6 +666,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int row = q0 + quarter * 32 + lane;
   const bool row_ok = row < p.Lq;
   const int n_kv = (p.Lk + BKV - 1) / BKV;
+  const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
+  if (shared_mask && tid < BKV / 32) s_mb[0][tid] = mask_bits_row(p, b, 0, true, tid * 32);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k_k);
@@ -645,6 +721,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                      umma_desc_kmajor(bv + (ks / 4) * (BKV * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
       umma_commit(&bar_s);
     }
+    if (shared_mask && tid < BKV / 32 && j + 1 < n_kv)   // next tile's shared mask bits (read after the barrier below)
+      s_mb[(j + 1) & 1][tid] = mask_bits_row(p, b, 0, true, (j + 1) * BKV + tid * 32);
     if (p.drop_thresh) {  // per-column dropout keys of this key tile (previous readers passed the barrier below)
       if (tid < BKV) s_ckey[tid] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(j * BKV + tid));
       __syncthreads();
@@ -654,26 +732,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     {
       const int c = slice;
       const int k0 = j * BKV + c * 32;
-      const uint32_t mb = mask_bits_row(p, b, row, row_ok, k0);
+      const uint32_t mb = shared_mask ? s_mb[j & 1][c] : mask_bits_row(p, b, row, row_ok, k0);
       uint32_t rs[32], rd[32];
       tmem_ld32(t_lane + T_S + c * 32, rs);
       tmem_ld32(t_lane + T_DP + c * 32, rd);
       tmem_ld_wait();
       // dS without the softmax scale (applied once to dQ in the epilogue)
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        uint4 ck = make_uint4(0u, 0u, 0u, 0u);
-        if (p.drop_thresh) ck = *reinterpret_cast<const uint4*>(s_ckey + c * 32 + i);
-        const uint32_t cks[4] = {ck.x, ck.y, ck.z, ck.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float pr = fast_exp2(fmaf(__uint_as_float(rs[i + t]), p.scale_log2, -lse2));
-          if (mb != 0u && ((mb >> (i + t)) & 1u)) pr = 0.f;
-          float dp = __uint_as_float(rd[i + t]);
-          if (p.drop_thresh && !dropout_keep_xor(drop_key, cks[t], p.drop_thresh)) dp = 0.f;
-          rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -delta)));
-        }
-      }
+      chunk_ds(rs, rd, mb, p.scale_log2, lse2, delta, dscale, p.drop_thresh, drop_key, s_ckey + c * 32);
       tmem_st32(t_lane + T_DP + c * 32, rd);
     }
     tmem_st_wait();
