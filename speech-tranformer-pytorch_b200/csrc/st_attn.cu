@@ -26,59 +26,11 @@
 // NaN, as the reference does.
 #include <math.h>
 
-#include "st_common.cuh"
-#include "st_host.h"
-#include "st_kernels.h"
+#include "st_attn.cuh"
 
 namespace st {
 
 namespace {
-
-constexpr float kLog2e = 1.4426950408889634f;
-
-struct AttnDev {
-  int B, H, Lq, Lk;
-  const uint8_t* mask;
-  int64_t ms_b, ms_q, ms_k;
-  float scale;        // 1/sqrt(dk)
-  float scale_log2;   // scale * log2(e)
-  uint32_t drop_thresh;
-  float drop_scale;
-  uint64_t drop_seed;
-  float* ctx; int64_t ldctx;
-  float* lse2;        // (B,H,Lq) log2-domain log-sum-exp of the scaled masked scores
-  float* attn;
-  // backward
-  const float* delta;
-  float* dq; int64_t lddq;
-  float* dk; int64_t lddk;
-  float* dv; int64_t lddv;
-};
-
-// bit i set <=> (query row, key k0+i) is masked.  Keys beyond Lk are always masked.
-__device__ __forceinline__ uint32_t mask_bits_row(const AttnDev& p, int b, int row, bool row_ok, int k0) {
-  uint32_t bits = 0;
-  const int valid = p.Lk - k0;  // number of in-range keys in this 32-chunk (may be <= 0 or > 32)
-  if (valid < 32) bits = valid <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << valid);
-  if (p.mask != nullptr && row_ok && valid > 0) {
-    const uint8_t* m = p.mask + b * p.ms_b + static_cast<int64_t>(row) * p.ms_q + static_cast<int64_t>(k0) * p.ms_k;
-    if (p.ms_k == 1 && valid >= 32 && ((reinterpret_cast<uintptr_t>(m) & 3) == 0)) {
-      const uint32_t* m4 = reinterpret_cast<const uint32_t*>(m);
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const uint32_t v = m4[w];
-        bits |= ((v & 0x000000FFu) ? 1u : 0u) << (w * 4 + 0);
-        bits |= ((v & 0x0000FF00u) ? 1u : 0u) << (w * 4 + 1);
-        bits |= ((v & 0x00FF0000u) ? 1u : 0u) << (w * 4 + 2);
-        bits |= ((v & 0xFF000000u) ? 1u : 0u) << (w * 4 + 3);
-      }
-    } else {
-      const int n = valid < 32 ? valid : 32;
-      for (int i = 0; i < n; ++i) bits |= (m[static_cast<int64_t>(i) * p.ms_k] ? 1u : 0u) << i;
-    }
-  }
-  return bits;
-}
 
 __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], uint32_t mb) {
   float mx = -INFINITY;
@@ -776,6 +728,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
 }
 
+}  // namespace
+
 // ================================================================================ host side
 // 3-D tensor map over a (B, L, H*dk) activation addressed as rows of `ld` floats: dims {H*dk, L, B}.
 int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32) {
@@ -795,7 +749,7 @@ int check_attn(const AttnArgs& a, const char* who) {
   return ST_OK;
 }
 
-AttnDev to_dev(const AttnArgs& a) {
+AttnDev attn_to_dev(const AttnArgs& a) {
   AttnDev p{};
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk;
   p.mask = a.mask; p.ms_b = a.ms_b; p.ms_q = a.ms_q; p.ms_k = a.ms_k;
@@ -804,6 +758,8 @@ AttnDev to_dev(const AttnArgs& a) {
   p.ctx = a.ctx; p.ldctx = a.ldctx; p.lse2 = a.lse; p.attn = a.attn;
   return p;
 }
+
+namespace {
 
 template <int DK, int BKV>
 int launch_fwd(cudaStream_t s, const AttnArgs& a) {
@@ -818,7 +774,7 @@ int launch_fwd(cudaStream_t s, const AttnArgs& a) {
   if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
   dim3 grid((a.Lq + 127) / 128, a.H, a.B);
   ProfScope prof(s, PROF_ATTN_FWD, 4.0 * a.B * a.H * static_cast<double>(a.Lq) * a.Lk * DK);
-  kern<<<grid, 256, SMEM, s>>>(tq, tk, tv, to_dev(a));
+  kern<<<grid, 256, SMEM, s>>>(tq, tk, tv, attn_to_dev(a));
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -827,7 +783,7 @@ template <int DK, int BQ, int BKV>
 int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
   const AttnArgs& f = a.f;
   const int cols = f.H * DK;
-  AttnDev p = to_dev(f);
+  AttnDev p = attn_to_dev(f);
   p.delta = a.delta; p.dq = a.dq; p.lddq = a.lddq; p.dk = a.dk_; p.lddk = a.lddk; p.dv = a.dv; p.lddv = a.lddv;
   {
     const int64_t rows = static_cast<int64_t>(f.B) * f.Lq;
@@ -838,6 +794,7 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
                                                                                     a.delta, f.B, f.H, f.Lq, DK);
     ST_CHECK_LAUNCH();
   }
+  if (DK <= 64 && !get_option("attn_bwd_simple")) return attn_bwd_pipelined(s, a, p);  // st_attn_bwd.cu
   {
     CUtensorMap tk, tv, tqk, tqm, tdk, tdm;
     ST_TRY(make_act_tmap(&tk, f.k, f.ldk, cols, f.Lk, f.B, 128, 0));

@@ -1,0 +1,63 @@
+// st_attn.cuh — declarations shared by the attention kernels (st_attn.cu: forward + simple backward,
+// st_attn_bwd.cu: warp-specialised pipelined backward).
+#pragma once
+#include "st_common.cuh"
+#include "st_host.h"
+#include "st_kernels.h"
+
+namespace st {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnDev {
+  int B, H, Lq, Lk;
+  const uint8_t* mask;
+  int64_t ms_b, ms_q, ms_k;
+  float scale;        // 1/sqrt(dk)
+  float scale_log2;   // scale * log2(e)
+  uint32_t drop_thresh;   // 32-bit threshold of the xor-key dropout scheme (0 = off)
+  float drop_scale;
+  uint64_t drop_seed;
+  float* ctx; int64_t ldctx;
+  float* lse2;        // (B,H,Lq) log2-domain log-sum-exp of the scaled masked scores
+  float* attn;
+  // backward
+  const float* delta;
+  float* dq; int64_t lddq;
+  float* dk; int64_t lddk;
+  float* dv; int64_t lddv;
+};
+
+// bit i set <=> (query row, key k0+i) is masked.  Keys beyond Lk are always masked.
+__device__ __forceinline__ uint32_t mask_bits_row(const AttnDev& p, int b, int row, bool row_ok, int k0) {
+  uint32_t bits = 0;
+  const int valid = p.Lk - k0;  // number of in-range keys in this 32-chunk (may be <= 0 or > 32)
+  if (valid < 32) bits = valid <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << valid);
+  if (p.mask != nullptr && row_ok && valid > 0) {
+    const uint8_t* m = p.mask + b * p.ms_b + static_cast<int64_t>(row) * p.ms_q + static_cast<int64_t>(k0) * p.ms_k;
+    if (p.ms_k == 1 && valid >= 32 && ((reinterpret_cast<uintptr_t>(m) & 3) == 0)) {
+      const uint32_t* m4 = reinterpret_cast<const uint32_t*>(m);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t v = m4[w];
+        bits |= ((v & 0x000000FFu) ? 1u : 0u) << (w * 4 + 0);
+        bits |= ((v & 0x0000FF00u) ? 1u : 0u) << (w * 4 + 1);
+        bits |= ((v & 0x00FF0000u) ? 1u : 0u) << (w * 4 + 2);
+        bits |= ((v & 0xFF000000u) ? 1u : 0u) << (w * 4 + 3);
+      }
+    } else {
+      const int n = valid < 32 ? valid : 32;
+      for (int i = 0; i < n; ++i) bits |= (m[static_cast<int64_t>(i) * p.ms_k] ? 1u : 0u) << i;
+    }
+  }
+  return bits;
+}
+
+// host helpers (st_attn.cu)
+int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32);
+AttnDev attn_to_dev(const AttnArgs& a);
+
+// st_attn_bwd.cu: pipelined dQ and dK/dV kernels for d_k in {32, 64}; p already carries the backward pointers
+int attn_bwd_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p);
+
+}  // namespace st

@@ -1,0 +1,499 @@
+// st_attn_bwd.cu — warp-specialised, software-pipelined attention backward for d_k in {32, 64}.
+//
+// Same mathematics as the simple kernels in st_attn.cu (autograd of transformer/Attention.py:82-90), but
+// organised like the GEMM: the CTA has a TMA-producer warp, a single-thread tcgen05.mma issuer warp and
+// 16 compute warps that only ever wait on mbarriers (no __syncthreads in the loop):
+//
+//   producer : 2-stage smem ring of the streamed 64-row tiles (+ per-tile metadata: dropout keys, mask bits,
+//              log-sum-exp / delta), released by tcgen05.commit of the MMAs that consumed them
+//   MMA warp : A(t) = the two "recompute" MMAs of tile t into TMEM buffer t&1  (S, dP  or  S^T, dP^T),
+//              B(t) = the gradient MMAs consuming what the compute warps wrote back (A operand in TMEM);
+//              issue order A(0) A(1) B(0) A(2) B(1) ... so A(t+1) runs under the compute phase of tile t
+//   compute  : 4 threads per tile row (16 columns each): tcgen05.ld -> exp2 / dropout / dS -> tcgen05.st,
+//              then arrive on the "written back" barrier
+//
+//   dQ  kernel: one CTA per 128-query tile, streams 64-key tiles:   dQ += dS K
+//   dKV kernel: one CTA per 128-key tile,   streams 64-query tiles: dV += P^T dO,  dK += dS^T Q
+// TMEM: 2 x (64 + 64) columns for the double-buffered S/dP pair + the fp32 gradient accumulators.
+#include "st_attn.cuh"
+
+namespace st {
+
+namespace {
+
+constexpr int BT = 64;                 // streamed tile height
+constexpr int NCOMP = 512;             // compute threads
+constexpr int NTHREADS = NCOMP + 64;   // + producer warp + MMA warp
+constexpr int W_PROD = NCOMP / 32;     // warp 16
+constexpr int W_MMA = W_PROD + 1;      // warp 17
+
+// dS chunk (dQ kernel; thread = query row, 16 key columns)
+template <bool MASK, bool DROP>
+__device__ __forceinline__ void ds16_t(const uint32_t (&rs)[16], uint32_t (&rd)[16], uint32_t mb, float scale_log2, float lse2,
+                                       float delta, float dscale, uint32_t thresh, uint32_t rowkey, const uint32_t* ckey) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    uint4 ck = make_uint4(0u, 0u, 0u, 0u);
+    if (DROP) ck = *reinterpret_cast<const uint4*>(ckey + i);
+    const uint32_t cks[4] = {ck.x, ck.y, ck.z, ck.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float pr = fast_exp2(fmaf(__uint_as_float(rs[i + t]), scale_log2, -lse2));
+      if (MASK && ((mb >> (i + t)) & 1u)) pr = 0.f;
+      float dp = __uint_as_float(rd[i + t]);
+      if (DROP && !dropout_keep_xor(rowkey, cks[t], thresh)) dp = 0.f;
+      rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -delta)));
+    }
+  }
+}
+
+// P^T / dS^T chunk (dKV kernel; thread = key row, 16 query columns)
+template <bool DENSE, bool DROP>
+__device__ __forceinline__ void dkv16_t(uint32_t (&rs)[16], uint32_t (&rd)[16], const float* lse, const float* delta,
+                                        const uint32_t* rkey, float scale_log2, float dscale, uint32_t thresh,
+                                        uint32_t my_ckey, const uint8_t* mrow, int64_t ms_q, int q_first, int Lq, bool key_ok) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 lse4 = *reinterpret_cast<const float4*>(lse + i);
+    const float4 del4 = *reinterpret_cast<const float4*>(delta + i);
+    uint4 key4 = make_uint4(0u, 0u, 0u, 0u);
+    if (DROP) key4 = *reinterpret_cast<const uint4*>(rkey + i);
+    const float lses[4] = {lse4.x, lse4.y, lse4.z, lse4.w};
+    const float dels[4] = {del4.x, del4.y, del4.z, del4.w};
+    const uint32_t rks[4] = {key4.x, key4.y, key4.z, key4.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float pr = fast_exp2(fmaf(__uint_as_float(rs[i + t]), scale_log2, -lses[t]));
+      if (DENSE) {
+        const int q = q_first + i + t;
+        if (!key_ok || (q < Lq && mrow[static_cast<int64_t>(q) * ms_q] != 0)) pr = 0.f;
+      }
+      float dp = __uint_as_float(rd[i + t]);
+      float pd = pr;
+      if (DROP && !dropout_keep_xor(rks[t], my_ckey, thresh)) { pd = 0.f; dp = 0.f; }
+      rs[i + t] = __float_as_uint(tf32_rna(pd));
+      rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -dels[t])));
+    }
+  }
+}
+
+// ================================================================================ dQ
+template <int DK>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dq_pipe(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                 const __grid_constant__ CUtensorMap tmap_k_k, const __grid_constant__ CUtensorMap tmap_k_mn,
+                 const __grid_constant__ CUtensorMap tmap_v_k, const AttnDev p) {
+  constexpr int BQ = 128;
+  constexpr int G = DK / 32;
+  constexpr int Q_BYTES = BQ * DK * 4;
+  constexpr int T_BYTES = BT * DK * 4;
+  constexpr int STAGE_BYTES = 3 * T_BYTES;
+  constexpr uint32_t TCOLS = 512;
+  constexpr uint32_t T_S = 0, T_DP = 2 * BT, T_DQ = 4 * BT;
+  static_assert(4 * BT + DK <= 512, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sDO = sQ + Q_BYTES;
+  uint8_t* sStage = sDO + Q_BYTES;   // per stage: Kk | Km | Vk
+  __shared__ uint64_t bar_q, ld_full[2], ld_empty[2], s_full[2], ds_full[2], acc_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) uint32_t s_ckey[2][BT];
+  __shared__ uint32_t s_mb[2][BT / 32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + BT - 1) / BT;
+  const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
+
+  if (tid == 0) {
+    mbar_init(&bar_q, 1); mbar_init(&acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ld_full[s], 1); mbar_init(&ld_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], NCOMP);
+    }
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == W_PROD) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k_k);
+      tma_prefetch_desc(&tmap_k_mn); tma_prefetch_desc(&tmap_v_k);
+      mbar_arrive_expect_tx(&bar_q, 2 * Q_BYTES);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        tma_load_3d(sQ + g * (BQ * 128), &tmap_q, &bar_q, h * DK + g * 32, q0, b);
+        tma_load_3d(sDO + g * (BQ * 128), &tmap_do, &bar_q, h * DK + g * 32, q0, b);
+      }
+    }
+    for (int t = 0; t < n_kv; ++t) {
+      const int s = t & 1;
+      mbar_wait(&ld_empty[s], ((t >> 1) & 1) ^ 1);
+      if (p.drop_thresh) {
+        s_ckey[s][lane] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(t * BT + lane));
+        s_ckey[s][lane + 32] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(t * BT + lane + 32));
+      }
+      if (lane < BT / 32) s_mb[s][lane] = shared_mask ? mask_bits_row(p, b, 0, true, t * BT + lane * 32) : 0u;
+      __syncwarp();
+      if (lane == 0) {
+        uint8_t* st = sStage + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&ld_full[s], STAGE_BYTES);   // release: the metadata stores above become visible with it
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          tma_load_3d(st + g * (BT * 128), &tmap_k_k, &ld_full[s], h * DK + g * 32, t * BT, b);
+          tma_load_3d(st + T_BYTES + g * (BT * 128), &tmap_k_mn, &ld_full[s], h * DK + g * 32, t * BT, b);
+          tma_load_3d(st + 2 * T_BYTES + g * (BT * 128), &tmap_v_k, &ld_full[s], h * DK + g * 32, t * BT, b);
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t aq = smem_u32(sQ), ado = smem_u32(sDO), st0 = smem_u32(sStage);
+      auto issue_a = [&](int t) {   // S(t) = Q K^T, dP(t) = dO V^T   (all operands K-major)
+        const int s = t & 1;
+        mbar_wait(&ld_full[s], (t >> 1) & 1);
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
+        const uint32_t bk = st0 + s * STAGE_BYTES, bv = bk + 2 * T_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < DK / 8; ++ks)
+          umma_tf32_ss(tmem + T_S + s * BT, umma_desc_kmajor(aq + (ks / 4) * (BQ * 128) + (ks % 4) * 32),
+                       umma_desc_kmajor(bk + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < DK / 8; ++ks)
+          umma_tf32_ss(tmem + T_DP + s * BT, umma_desc_kmajor(ado + (ks / 4) * (BQ * 128) + (ks % 4) * 32),
+                       umma_desc_kmajor(bv + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(&s_full[s]);
+      };
+      auto issue_b = [&](int t) {   // dQ += dS(t) K(t)   (A = dS in TMEM, B = K MN-major)
+        const int s = t & 1;
+        mbar_wait(&ds_full[s], (t >> 1) & 1);
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+        const uint32_t bkm = st0 + s * STAGE_BYTES + T_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BT / 8; ++ks)
+          umma_tf32_ts(tmem + T_DQ, tmem + T_DP + s * BT + ks * 8, umma_desc_mnmajor(bkm + ks * 1024, BT * 128), idesc,
+                       (t > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&ld_empty[s]);   // stage s (and TMEM pair s) free once everything issued so far has retired
+      };
+      mbar_wait(&bar_q, 0);
+      issue_a(0);
+      for (int t = 0; t < n_kv; ++t) {
+        if (t + 1 < n_kv) issue_a(t + 1);
+        issue_b(t);
+      }
+      umma_commit(&acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== compute warps =====================
+    const int quarter = warp & 3, slice = warp >> 2;
+    const int row = q0 + quarter * 32 + lane;
+    const bool row_ok = row < p.Lq;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int col0 = slice * 16;
+    const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
+    const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
+    const float delta = row_ok ? p.delta[stat] : 0.f;
+    const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(stat)) : 0u;
+    const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
+    for (int t = 0; t < n_kv; ++t) {
+      const int s = t & 1;
+      mbar_wait(&s_full[s], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t word = shared_mask ? s_mb[s][col0 >> 5] : mask_bits_row(p, b, row, row_ok, t * BT + (col0 & ~31));
+      const uint32_t mb = (word >> (col0 & 31)) & 0xFFFFu;
+      uint32_t rs[16], rd[16];
+      tmem_ld16(t_lane + T_S + s * BT + col0, rs);
+      tmem_ld16(t_lane + T_DP + s * BT + col0, rd);
+      tmem_ld_wait();
+      const uint32_t* ck = s_ckey[s] + col0;
+      if (mb == 0u) {
+        if (p.drop_thresh) ds16_t<false, true>(rs, rd, mb, p.scale_log2, lse2, delta, dscale, p.drop_thresh, drop_key, ck);
+        else ds16_t<false, false>(rs, rd, mb, p.scale_log2, lse2, delta, dscale, p.drop_thresh, drop_key, ck);
+      } else {
+        if (p.drop_thresh) ds16_t<true, true>(rs, rd, mb, p.scale_log2, lse2, delta, dscale, p.drop_thresh, drop_key, ck);
+        else ds16_t<true, false>(rs, rd, mb, p.scale_log2, lse2, delta, dscale, p.drop_thresh, drop_key, ck);
+      }
+      tmem_st16(t_lane + T_DP + s * BT + col0, rd);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&ds_full[s]);
+    }
+    // ---- epilogue: dQ = scale * accumulator
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    if (col0 < DK) {
+      uint32_t r[16];
+      tmem_ld16(t_lane + T_DQ + col0, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        float* dst = p.dq + (static_cast<int64_t>(b) * p.Lq + row) * p.lddq + h * DK + col0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(dst + i) =
+              make_float4(tf32_rna(__uint_as_float(r[i]) * p.scale), tf32_rna(__uint_as_float(r[i + 1]) * p.scale),
+                          tf32_rna(__uint_as_float(r[i + 2]) * p.scale), tf32_rna(__uint_as_float(r[i + 3]) * p.scale));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
+}
+
+// ================================================================================ dK, dV
+template <int DK>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dkv_pipe(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                  const __grid_constant__ CUtensorMap tmap_q_k, const __grid_constant__ CUtensorMap tmap_q_mn,
+                  const __grid_constant__ CUtensorMap tmap_do_k, const __grid_constant__ CUtensorMap tmap_do_mn,
+                  const AttnDev p) {
+  constexpr int BKV = 128;
+  constexpr int G = DK / 32;
+  constexpr int KV_BYTES = BKV * DK * 4;
+  constexpr int T_BYTES = BT * DK * 4;
+  constexpr int STAGE_BYTES = 4 * T_BYTES;   // Qk | Qm | dOk | dOm
+  constexpr uint32_t TCOLS = 512;
+  constexpr uint32_t T_ST = 0, T_DPT = 2 * BT, T_DV = 4 * BT, T_DK = 4 * BT + DK;
+  static_assert(4 * BT + 2 * DK <= 512, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sStage = sV + KV_BYTES;
+  __shared__ uint64_t bar_kv, ld_full[2], ld_empty[2], s_full[2], ds_full[2], acc_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_lse[2][BT];
+  __shared__ __align__(16) float s_delta[2][BT];
+  __shared__ __align__(16) uint32_t s_rkey[2][BT];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+  const int n_q = (p.Lq + BT - 1) / BT;
+
+  if (tid == 0) {
+    mbar_init(&bar_kv, 1); mbar_init(&acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ld_full[s], 1); mbar_init(&ld_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], NCOMP);
+    }
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == W_PROD) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_q_k);
+      tma_prefetch_desc(&tmap_q_mn); tma_prefetch_desc(&tmap_do_k); tma_prefetch_desc(&tmap_do_mn);
+      mbar_arrive_expect_tx(&bar_kv, 2 * KV_BYTES);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        tma_load_3d(sK + g * (BKV * 128), &tmap_k, &bar_kv, h * DK + g * 32, kv0, b);
+        tma_load_3d(sV + g * (BKV * 128), &tmap_v, &bar_kv, h * DK + g * 32, kv0, b);
+      }
+    }
+    for (int t = 0; t < n_q; ++t) {
+      const int s = t & 1;
+      mbar_wait(&ld_empty[s], ((t >> 1) & 1) ^ 1);
+#pragma unroll
+      for (int e = lane; e < BT; e += 32) {   // per-query statistics of this tile
+        const int q = t * BT + e;
+        const int64_t o = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (q < p.Lq ? q : 0);
+        s_lse[s][e] = q < p.Lq ? p.lse2[o] : INFINITY;   // +inf => probability 0 for padded query rows
+        s_delta[s][e] = q < p.Lq ? p.delta[o] : 0.f;
+        s_rkey[s][e] = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(o)) : 0u;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        uint8_t* st = sStage + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&ld_full[s], STAGE_BYTES);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          tma_load_3d(st + g * (BT * 128), &tmap_q_k, &ld_full[s], h * DK + g * 32, t * BT, b);
+          tma_load_3d(st + T_BYTES + g * (BT * 128), &tmap_q_mn, &ld_full[s], h * DK + g * 32, t * BT, b);
+          tma_load_3d(st + 2 * T_BYTES + g * (BT * 128), &tmap_do_k, &ld_full[s], h * DK + g * 32, t * BT, b);
+          tma_load_3d(st + 3 * T_BYTES + g * (BT * 128), &tmap_do_mn, &ld_full[s], h * DK + g * 32, t * BT, b);
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t ak = smem_u32(sK), av = smem_u32(sV), st0 = smem_u32(sStage);
+      auto issue_a = [&](int t) {   // S^T(t) = K Q^T, dP^T(t) = V dO^T
+        const int s = t & 1;
+        mbar_wait(&ld_full[s], (t >> 1) & 1);
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
+        const uint32_t bq = st0 + s * STAGE_BYTES, bdo = bq + 2 * T_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < DK / 8; ++ks)
+          umma_tf32_ss(tmem + T_ST + s * BT, umma_desc_kmajor(ak + (ks / 4) * (BKV * 128) + (ks % 4) * 32),
+                       umma_desc_kmajor(bq + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < DK / 8; ++ks)
+          umma_tf32_ss(tmem + T_DPT + s * BT, umma_desc_kmajor(av + (ks / 4) * (BKV * 128) + (ks % 4) * 32),
+                       umma_desc_kmajor(bdo + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(&s_full[s]);
+      };
+      auto issue_b = [&](int t) {   // dV += P^T dO, dK += dS^T Q   (A in TMEM, B MN-major)
+        const int s = t & 1;
+        mbar_wait(&ds_full[s], (t >> 1) & 1);
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+        const uint32_t bqm = st0 + s * STAGE_BYTES + T_BYTES, bdom = st0 + s * STAGE_BYTES + 3 * T_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BT / 8; ++ks)
+          umma_tf32_ts(tmem + T_DV, tmem + T_ST + s * BT + ks * 8, umma_desc_mnmajor(bdom + ks * 1024, BT * 128), idesc,
+                       (t > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < BT / 8; ++ks)
+          umma_tf32_ts(tmem + T_DK, tmem + T_DPT + s * BT + ks * 8, umma_desc_mnmajor(bqm + ks * 1024, BT * 128), idesc,
+                       (t > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&ld_empty[s]);
+      };
+      mbar_wait(&bar_kv, 0);
+      issue_a(0);
+      for (int t = 0; t < n_q; ++t) {
+        if (t + 1 < n_q) issue_a(t + 1);
+        issue_b(t);
+      }
+      umma_commit(&acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== compute warps =====================
+    const int quarter = warp & 3, slice = warp >> 2;
+    const int key = kv0 + quarter * 32 + lane;
+    const bool key_ok = key < p.Lk;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int col0 = slice * 16;
+    const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
+    bool key_masked = !key_ok;
+    if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
+    const bool mask_dense = (p.mask != nullptr) && !mask_per_key;
+    const uint8_t* mrow = mask_dense ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
+    const uint32_t my_ckey = p.drop_thresh ? dropout_col_key(p.drop_seed, static_cast<uint32_t>(key_ok ? key : 0)) : 0u;
+    const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
+    for (int t = 0; t < n_q; ++t) {
+      const int s = t & 1;
+      mbar_wait(&s_full[s], (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t rs[16], rd[16];
+      // tcgen05.ld/st are warp-collective (.sync.aligned): every lane executes them, whatever its key's mask state
+      tmem_ld16(t_lane + T_ST + s * BT + col0, rs);
+      tmem_ld16(t_lane + T_DPT + s * BT + col0, rd);
+      tmem_ld_wait();
+      if (!mask_dense && key_masked) {   // this key is padding for every query: P = dS = 0
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { rs[i] = 0u; rd[i] = 0u; }
+      } else {
+        const float* ls = s_lse[s] + col0;
+        const float* de = s_delta[s] + col0;
+        const uint32_t* rk = s_rkey[s] + col0;
+        const int qf = t * BT + col0;
+        if (mask_dense) {
+          if (p.drop_thresh) dkv16_t<true, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
+          else dkv16_t<true, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
+        } else {
+          if (p.drop_thresh) dkv16_t<false, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
+          else dkv16_t<false, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
+        }
+      }
+      tmem_st16(t_lane + T_ST + s * BT + col0, rs);
+      tmem_st16(t_lane + T_DPT + s * BT + col0, rd);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&ds_full[s]);
+    }
+    // ---- epilogue: dV = dropout-scale * acc, dK = softmax-scale * acc
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    if (col0 < DK) {
+      uint32_t rv[16], rk[16];
+      tmem_ld16(t_lane + T_DV + col0, rv);
+      tmem_ld16(t_lane + T_DK + col0, rk);
+      tmem_ld_wait();
+      if (key_ok) {
+        float* dvp = p.dv + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + col0;
+        float* dkp = p.dk + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + col0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          *reinterpret_cast<float4*>(dvp + i) =
+              make_float4(tf32_rna(__uint_as_float(rv[i]) * dscale), tf32_rna(__uint_as_float(rv[i + 1]) * dscale),
+                          tf32_rna(__uint_as_float(rv[i + 2]) * dscale), tf32_rna(__uint_as_float(rv[i + 3]) * dscale));
+          *reinterpret_cast<float4*>(dkp + i) =
+              make_float4(tf32_rna(__uint_as_float(rk[i]) * p.scale), tf32_rna(__uint_as_float(rk[i + 1]) * p.scale),
+                          tf32_rna(__uint_as_float(rk[i + 2]) * p.scale), tf32_rna(__uint_as_float(rk[i + 3]) * p.scale));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
+}
+
+template <int DK>
+int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
+  const AttnArgs& f = a.f;
+  const int cols = f.H * DK;
+  {
+    CUtensorMap tk, tv, tqk, tqm, tdk, tdm;
+    ST_TRY(make_act_tmap(&tk, f.k, f.ldk, cols, f.Lk, f.B, 128, 0));
+    ST_TRY(make_act_tmap(&tv, f.v, f.ldv, cols, f.Lk, f.B, 128, 0));
+    ST_TRY(make_act_tmap(&tqk, f.q, f.ldq, cols, f.Lq, f.B, BT, 0));
+    ST_TRY(make_act_tmap(&tqm, f.q, f.ldq, cols, f.Lq, f.B, BT, 1));
+    ST_TRY(make_act_tmap(&tdk, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, 0));
+    ST_TRY(make_act_tmap(&tdm, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, 1));
+    constexpr int SMEM = 2 * 128 * DK * 4 + 2 * 4 * BT * DK * 4 + 1024;
+    auto kern = attn_bwd_dkv_pipe<DK>;
+    static bool attr = false;
+    if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+    dim3 grid((f.Lk + 127) / 128, f.H, f.B);
+    // algorithmic share of the attention backward carried by this kernel: dV and dK (S, dP recompute not counted)
+    ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
+    kern<<<grid, NTHREADS, SMEM, s>>>(tk, tv, tqk, tqm, tdk, tdm, p);
+    ST_CHECK_LAUNCH();
+  }
+  {
+    CUtensorMap tq, tdo, tkk, tkm, tvk;
+    ST_TRY(make_act_tmap(&tq, f.q, f.ldq, cols, f.Lq, f.B, 128, 0));
+    ST_TRY(make_act_tmap(&tdo, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0));
+    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BT, 0));
+    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BT, 1));
+    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BT, 0));
+    constexpr int SMEM = 2 * 128 * DK * 4 + 2 * 3 * BT * DK * 4 + 1024;
+    auto kern = attn_bwd_dq_pipe<DK>;
+    static bool attr = false;
+    if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+    dim3 grid((f.Lq + 127) / 128, f.H, f.B);
+    // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
+    ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
+    kern<<<grid, NTHREADS, SMEM, s>>>(tq, tdo, tkk, tkm, tvk, p);
+    ST_CHECK_LAUNCH();
+  }
+  return ST_OK;
+}
+
+}  // namespace
+
+int attn_bwd_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
+  return a.f.dk == 32 ? launch_pipelined<32>(s, a, p) : launch_pipelined<64>(s, a, p);
+}
+
+}  // namespace st
