@@ -199,13 +199,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   auto load_k = [&](int j) {
     mbar_arrive_expect_tx(&bar_k, KV_BYTES);
-#pragma unroll
-    for (int g = 0; g < G; ++g) tma_load_3d(sK + g * (BKV * 128), &tmap_k, &bar_k, h * DK + g * 32, j * BKV, b);
+    tma_load_4d(sK, &tmap_k, &bar_k, 0, j * BKV, h * G, b);
   };
   auto load_v = [&](int j) {
     mbar_arrive_expect_tx(&bar_v, KV_BYTES);
-#pragma unroll
-    for (int g = 0; g < G; ++g) tma_load_3d(sV + g * (BKV * 128), &tmap_v, &bar_v, h * DK + g * 32, j * BKV, b);
+    tma_load_4d(sV, &tmap_v, &bar_v, 0, j * BKV, h * G, b);
   };
   auto issue_s = [&]() {  // S = Q K^T  (both K-major)
     constexpr uint32_t idesc = umma_idesc_tf32(128, BKV, false, false);
@@ -219,8 +217,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bar_q, Q_BYTES);
-#pragma unroll
-    for (int g = 0; g < G; ++g) tma_load_3d(sQ + g * (BQ * 128), &tmap_q, &bar_q, h * DK + g * 32, q0, b);
+    tma_load_4d(sQ, &tmap_q, &bar_q, 0, q0, h * G, b);
     load_k(0);
     load_v(0);
     mbar_wait(&bar_q, 0);
@@ -458,11 +455,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bar_kv, 2 * KV_BYTES);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      tma_load_3d(sK + g * (BKV * 128), &tmap_k, &bar_kv, h * DK + g * 32, kv0, b);
-      tma_load_3d(sV + g * (BKV * 128), &tmap_v, &bar_kv, h * DK + g * 32, kv0, b);
-    }
+      tma_load_4d(sK, &tmap_k, &bar_kv, 0, kv0, h * G, b);
+      tma_load_4d(sV, &tmap_v, &bar_kv, 0, kv0, h * G, b);
+
   }
   // key-padding masks (stride 0 over queries) are a per-thread constant
   const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
@@ -477,13 +472,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     if (tid == 0) {
       if (it > 0) { mbar_wait(&bar_acc, (it - 1) & 1); tc_fence_after(); }  // previous MMAs done with Q/dO tiles
       mbar_arrive_expect_tx(&bar_ld, 4 * QT_BYTES);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        tma_load_3d(sQk + g * (BQ * 128), &tmap_q_k, &bar_ld, h * DK + g * 32, q0, b);
-        tma_load_3d(sQm + g * (BQ * 128), &tmap_q_mn, &bar_ld, h * DK + g * 32, q0, b);
-        tma_load_3d(sDOk + g * (BQ * 128), &tmap_do_k, &bar_ld, h * DK + g * 32, q0, b);
-        tma_load_3d(sDOm + g * (BQ * 128), &tmap_do_mn, &bar_ld, h * DK + g * 32, q0, b);
-      }
+        tma_load_4d(sQk, &tmap_q_k, &bar_ld, 0, q0, h * G, b);
+        tma_load_4d(sQm, &tmap_q_mn, &bar_ld, 0, q0, h * G, b);
+        tma_load_4d(sDOk, &tmap_do_k, &bar_ld, 0, q0, h * G, b);
+        tma_load_4d(sDOm, &tmap_do_mn, &bar_ld, 0, q0, h * G, b);
+
     }
     if (tid >= 3 * BQ) {  // the last BQ threads (never the issuing thread 0)
       const int t = tid - 3 * BQ;
@@ -636,11 +629,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   if (tid == 0) {
     mbar_arrive_expect_tx(&bar_q, 2 * Q_BYTES);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      tma_load_3d(sQ + g * (BQ * 128), &tmap_q, &bar_q, h * DK + g * 32, q0, b);
-      tma_load_3d(sDO + g * (BQ * 128), &tmap_do, &bar_q, h * DK + g * 32, q0, b);
-    }
+      tma_load_4d(sQ, &tmap_q, &bar_q, 0, q0, h * G, b);
+      tma_load_4d(sDO, &tmap_do, &bar_q, 0, q0, h * G, b);
+
   }
   const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
   const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
@@ -652,12 +643,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (tid == 0) {
       if (j > 0) { mbar_wait(&bar_acc, (j - 1) & 1); tc_fence_after(); }
       mbar_arrive_expect_tx(&bar_ld, 3 * KT_BYTES);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        tma_load_3d(sKk + g * (BKV * 128), &tmap_k_k, &bar_ld, h * DK + g * 32, j * BKV, b);
-        tma_load_3d(sKm + g * (BKV * 128), &tmap_k_mn, &bar_ld, h * DK + g * 32, j * BKV, b);
-        tma_load_3d(sVk + g * (BKV * 128), &tmap_v_k, &bar_ld, h * DK + g * 32, j * BKV, b);
-      }
+        tma_load_4d(sKk, &tmap_k_k, &bar_ld, 0, j * BKV, h * G, b);
+        tma_load_4d(sKm, &tmap_k_mn, &bar_ld, 0, j * BKV, h * G, b);
+        tma_load_4d(sVk, &tmap_v_k, &bar_ld, 0, j * BKV, h * G, b);
+
       if (j == 0) mbar_wait(&bar_q, 0);
       mbar_wait(&bar_ld, j & 1);
       tc_fence_after();
@@ -731,12 +720,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 }  // namespace
 
 // ================================================================================ host side
-// 3-D tensor map over a (B, L, H*dk) activation addressed as rows of `ld` floats: dims {H*dk, L, B}.
-int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32) {
-  const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
-  const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 4, static_cast<uint64_t>(L) * static_cast<uint64_t>(ld) * 4};
-  const uint32_t box[3] = {32, static_cast<uint32_t>(box_rows), 1};
-  return make_tmap_f32(m, base, 3, dims, strides, box, atom32);
+// 4-D tensor map over a (B, L, H*dk) activation addressed as rows of `ld` floats, viewed as
+// {32 columns, L rows, H*dk/32 column groups, B}: one box {32, box_rows, dk/32, 1} fetches a whole head tile and lands it
+// as [column group][row][32 floats] — the canonical 128-byte-swizzled UMMA operand layout — with ONE TMA instruction.
+int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32, int dk) {
+  const uint64_t dims[4] = {32, static_cast<uint64_t>(L), static_cast<uint64_t>(cols / 32), static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(ld) * 4, 128, static_cast<uint64_t>(L) * static_cast<uint64_t>(ld) * 4};
+  const uint32_t box[4] = {32, static_cast<uint32_t>(box_rows), static_cast<uint32_t>(dk / 32), 1};
+  return make_tmap_f32(m, base, 4, dims, strides, box, atom32);
 }
 
 int check_attn(const AttnArgs& a, const char* who) {
@@ -765,9 +756,9 @@ template <int DK, int BKV>
 int launch_fwd(cudaStream_t s, const AttnArgs& a) {
   CUtensorMap tq, tk, tv;
   const int cols = a.H * DK;
-  ST_TRY(make_act_tmap(&tq, a.q, a.ldq, cols, a.Lq, a.B, 128, 0));
-  ST_TRY(make_act_tmap(&tk, a.k, a.ldk, cols, a.Lk, a.B, BKV, 0));
-  ST_TRY(make_act_tmap(&tv, a.v, a.ldv, cols, a.Lk, a.B, BKV, 1));
+  ST_TRY(make_act_tmap(&tq, a.q, a.ldq, cols, a.Lq, a.B, 128, 0, DK));
+  ST_TRY(make_act_tmap(&tk, a.k, a.ldk, cols, a.Lk, a.B, BKV, 0, DK));
+  ST_TRY(make_act_tmap(&tv, a.v, a.ldv, cols, a.Lk, a.B, BKV, 1, DK));
   constexpr int SMEM = 128 * DK * 4 + 2 * BKV * DK * 4 + 1024;
   auto kern = attn_fwd_kernel<DK, BKV>;
   static bool attr = false;
@@ -797,12 +788,12 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
   if (DK <= 64 && !get_option("attn_bwd_simple")) return attn_bwd_pipelined(s, a, p);  // st_attn_bwd.cu
   {
     CUtensorMap tk, tv, tqk, tqm, tdk, tdm;
-    ST_TRY(make_act_tmap(&tk, f.k, f.ldk, cols, f.Lk, f.B, 128, 0));
-    ST_TRY(make_act_tmap(&tv, f.v, f.ldv, cols, f.Lk, f.B, 128, 0));
-    ST_TRY(make_act_tmap(&tqk, f.q, f.ldq, cols, f.Lq, f.B, BQ, 0));
-    ST_TRY(make_act_tmap(&tqm, f.q, f.ldq, cols, f.Lq, f.B, BQ, 1));
-    ST_TRY(make_act_tmap(&tdk, a.dctx, a.lddctx, cols, f.Lq, f.B, BQ, 0));
-    ST_TRY(make_act_tmap(&tdm, a.dctx, a.lddctx, cols, f.Lq, f.B, BQ, 1));
+    ST_TRY(make_act_tmap(&tk, f.k, f.ldk, cols, f.Lk, f.B, 128, 0, DK));
+    ST_TRY(make_act_tmap(&tv, f.v, f.ldv, cols, f.Lk, f.B, 128, 0, DK));
+    ST_TRY(make_act_tmap(&tqk, f.q, f.ldq, cols, f.Lq, f.B, BQ, 0, DK));
+    ST_TRY(make_act_tmap(&tqm, f.q, f.ldq, cols, f.Lq, f.B, BQ, 1, DK));
+    ST_TRY(make_act_tmap(&tdk, a.dctx, a.lddctx, cols, f.Lq, f.B, BQ, 0, DK));
+    ST_TRY(make_act_tmap(&tdm, a.dctx, a.lddctx, cols, f.Lq, f.B, BQ, 1, DK));
     constexpr int SMEM = 2 * 128 * DK * 4 + 4 * BQ * DK * 4 + 1024;
     auto kern = attn_bwd_dkv_kernel<DK, BQ>;
     static bool attr = false;
@@ -815,11 +806,11 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
   }
   {
     CUtensorMap tq, tdo, tkk, tkm, tvk;
-    ST_TRY(make_act_tmap(&tq, f.q, f.ldq, cols, f.Lq, f.B, 128, 0));
-    ST_TRY(make_act_tmap(&tdo, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0));
-    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BKV, 0));
-    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BKV, 1));
-    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BKV, 0));
+    ST_TRY(make_act_tmap(&tq, f.q, f.ldq, cols, f.Lq, f.B, 128, 0, DK));
+    ST_TRY(make_act_tmap(&tdo, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0, DK));
+    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BKV, 0, DK));
+    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BKV, 1, DK));
+    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BKV, 0, DK));
     constexpr int SMEM = 2 * 128 * DK * 4 + 3 * BKV * DK * 4 + 1024;
     auto kern = attn_bwd_dq_kernel<DK, BKV>;
     static bool attr = false;

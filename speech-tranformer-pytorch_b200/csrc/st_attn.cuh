@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t mask_bits_row(const AttnDev& p, int b, int r
 }
 
 // host helpers (st_attn.cu)
-int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32);
+int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32, int dk);
 AttnDev attn_to_dev(const AttnArgs& a);
 
 // st_attn_bwd.cu: pipelined dQ and dK/dV kernels for d_k in {32, 64}; p already carries the backward pointers

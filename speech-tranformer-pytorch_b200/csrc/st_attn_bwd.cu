@@ -4,9 +4,13 @@
 // organised like the GEMM: the CTA has a TMA-producer warp, a single-thread tcgen05.mma issuer warp and
 // 16 compute warps that only ever wait on mbarriers (no __syncthreads in the loop):
 //
-//   producer : 2-stage smem ring of the streamed 64-row tiles (+ per-tile metadata: dropout keys, mask bits,
-//              log-sum-exp / delta), released by tcgen05.commit of the MMAs that consumed them
-//   MMA warp : A(t) = the two "recompute" MMAs of tile t into TMEM buffer t&1  (S, dP  or  S^T, dP^T),
+//   resident : the CTA's own 128-row tiles (Q, dO in the dQ kernel; K, V in the dK/dV kernel) are the A operands
+//              of the "recompute" MMAs.  They are written ONCE into TMEM by the compute threads (lane = row,
+//              column = feature) and consumed with the .ts MMA form, so they occupy no shared memory and are not
+//              re-read from smem by every MMA
+//   producer : multi-stage smem ring (4 / 3 stages) of the streamed 64-row tiles, one 4-D TMA box per operand copy,
+//              + per-tile metadata (dropout keys, mask bits, log-sum-exp / delta), released by tcgen05.commit
+//   MMA warp : A(t) = the two recompute MMAs of tile t into TMEM buffer t&1  (S, dP  or  S^T, dP^T),
 //              B(t) = the gradient MMAs consuming what the compute warps wrote back (A operand in TMEM);
 //              issue order A(0) A(1) B(0) A(2) B(1) ... so A(t+1) runs under the compute phase of tile t
 //   compute  : 4 threads per tile row (16 columns each): tcgen05.ld -> exp2 / dropout / dS -> tcgen05.st,
@@ -14,7 +18,9 @@
 //
 //   dQ  kernel: one CTA per 128-query tile, streams 64-key tiles:   dQ += dS K
 //   dKV kernel: one CTA per 128-key tile,   streams 64-query tiles: dV += P^T dO,  dK += dS^T Q
-// TMEM: 2 x (64 + 64) columns for the double-buffered S/dP pair + the fp32 gradient accumulators.
+// The kernels are bound by the bytes streamed into each SM (K-major + MN-major copies of every streamed tile);
+// the deep ring keeps those loads in flight behind the MMAs and the softmax arithmetic.
+// TMEM (512 columns): 2 x (64 + 64) double-buffered S/dP pair, the fp32 gradient accumulators, the resident tiles.
 #include "st_attn.cuh"
 
 namespace st {
@@ -77,30 +83,48 @@ __device__ __forceinline__ void dkv16_t(uint32_t (&rs)[16], uint32_t (&rd)[16], 
   }
 }
 
+// Resident tiles -> TMEM: compute slice `slice` (0..3) owns one 32-column chunk of one of the two resident tensors
+// (x0 at columns [t_x0, t_x0+DK), x1 at [t_x1, ...)); the thread writes its row's 32 floats (zeros for rows >= L).
+template <int DK>
+__device__ __forceinline__ void resident_to_tmem(const float* x0, int64_t ld0, const float* x1, int64_t ld1, int64_t row,
+                                                 bool row_ok, int h, int slice, uint32_t t_lane, uint32_t t_x0, uint32_t t_x1) {
+  constexpr int CH = DK / 32;            // 32-column chunks per tensor
+  if (slice < 2 * CH) {                  // warp-uniform
+    const int which = slice / CH, c = slice % CH;
+    const float* src = (which == 0 ? x0 + row * ld0 : x1 + row * ld1) + h * DK + c * 32;
+    uint32_t r[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok) v = __ldg(reinterpret_cast<const float4*>(src + i));
+      r[i] = __float_as_uint(v.x); r[i + 1] = __float_as_uint(v.y); r[i + 2] = __float_as_uint(v.z); r[i + 3] = __float_as_uint(v.w);
+    }
+    tmem_st32(t_lane + (which == 0 ? t_x0 : t_x1) + c * 32, r);
+    tmem_st_wait();
+  }
+}
+
 // ================================================================================ dQ
 template <int DK>
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_bwd_dq_pipe(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restrict__ dctx, int64_t lddctx,
                  const __grid_constant__ CUtensorMap tmap_k_k, const __grid_constant__ CUtensorMap tmap_k_mn,
                  const __grid_constant__ CUtensorMap tmap_v_k, const AttnDev p) {
   constexpr int BQ = 128;
   constexpr int G = DK / 32;
-  constexpr int Q_BYTES = BQ * DK * 4;
+  constexpr int STAGES = 4;
   constexpr int T_BYTES = BT * DK * 4;
-  constexpr int STAGE_BYTES = 3 * T_BYTES;
+  constexpr int STAGE_BYTES = 3 * T_BYTES;   // Kk | Km | Vk
   constexpr uint32_t TCOLS = 512;
-  constexpr uint32_t T_S = 0, T_DP = 2 * BT, T_DQ = 4 * BT;
-  static_assert(4 * BT + DK <= 512, "TMEM budget");
+  constexpr uint32_t T_S = 0, T_DP = 2 * BT, T_DQ = 4 * BT, T_Q = 4 * BT + DK, T_DO = 4 * BT + 2 * DK;
+  static_assert(4 * BT + 3 * DK <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sDO = sQ + Q_BYTES;
-  uint8_t* sStage = sDO + Q_BYTES;   // per stage: Kk | Km | Vk
-  __shared__ uint64_t bar_q, ld_full[2], ld_empty[2], s_full[2], ds_full[2], acc_full;
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t res_ready, ld_full[STAGES], ld_empty[STAGES], s_full[2], ds_full[2], acc_full;
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) uint32_t s_ckey[2][BT];
-  __shared__ uint32_t s_mb[2][BT / 32];
+  __shared__ __align__(16) uint32_t s_ckey[STAGES][BT];
+  __shared__ uint32_t s_mb[STAGES][BT / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -108,10 +132,9 @@ attn_bwd_dq_pipe(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
 
   if (tid == 0) {
-    mbar_init(&bar_q, 1); mbar_init(&acc_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&ld_full[s], 1); mbar_init(&ld_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], NCOMP);
-    }
+    mbar_init(&res_ready, NCOMP); mbar_init(&acc_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ld_full[s], 1); mbar_init(&ld_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], NCOMP); }
     fence_mbar_init();
   }
   if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
@@ -122,19 +145,10 @@ attn_bwd_dq_pipe(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   if (warp == W_PROD) {
     // ===================== producer =====================
-    if (lane == 0) {
-      tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k_k);
-      tma_prefetch_desc(&tmap_k_mn); tma_prefetch_desc(&tmap_v_k);
-      mbar_arrive_expect_tx(&bar_q, 2 * Q_BYTES);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        tma_load_3d(sQ + g * (BQ * 128), &tmap_q, &bar_q, h * DK + g * 32, q0, b);
-        tma_load_3d(sDO + g * (BQ * 128), &tmap_do, &bar_q, h * DK + g * 32, q0, b);
-      }
-    }
+    if (lane == 0) { tma_prefetch_desc(&tmap_k_k); tma_prefetch_desc(&tmap_k_mn); tma_prefetch_desc(&tmap_v_k); }
     for (int t = 0; t < n_kv; ++t) {
-      const int s = t & 1;
-      mbar_wait(&ld_empty[s], ((t >> 1) & 1) ^ 1);
+      const int s = t % STAGES;
+      mbar_wait(&ld_empty[s], ((t / STAGES) & 1) ^ 1);
       if (p.drop_thresh) {
         s_ckey[s][lane] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(t * BT + lane));
         s_ckey[s][lane + 32] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(t * BT + lane + 32));
@@ -144,47 +158,45 @@ attn_bwd_dq_pipe(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (lane == 0) {
         uint8_t* st = sStage + s * STAGE_BYTES;
         mbar_arrive_expect_tx(&ld_full[s], STAGE_BYTES);   // release: the metadata stores above become visible with it
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          tma_load_3d(st + g * (BT * 128), &tmap_k_k, &ld_full[s], h * DK + g * 32, t * BT, b);
-          tma_load_3d(st + T_BYTES + g * (BT * 128), &tmap_k_mn, &ld_full[s], h * DK + g * 32, t * BT, b);
-          tma_load_3d(st + 2 * T_BYTES + g * (BT * 128), &tmap_v_k, &ld_full[s], h * DK + g * 32, t * BT, b);
-        }
+        tma_load_4d(st, &tmap_k_k, &ld_full[s], 0, t * BT, h * G, b);
+        tma_load_4d(st + T_BYTES, &tmap_k_mn, &ld_full[s], 0, t * BT, h * G, b);
+        tma_load_4d(st + 2 * T_BYTES, &tmap_v_k, &ld_full[s], 0, t * BT, h * G, b);
       }
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t aq = smem_u32(sQ), ado = smem_u32(sDO), st0 = smem_u32(sStage);
-      auto issue_a = [&](int t) {   // S(t) = Q K^T, dP(t) = dO V^T   (all operands K-major)
-        const int s = t & 1;
-        mbar_wait(&ld_full[s], (t >> 1) & 1);
+      const uint32_t st0 = smem_u32(sStage);
+      auto issue_a = [&](int t) {   // S(t) = Q K^T, dP(t) = dO V^T   (A = resident tile in TMEM, B K-major)
+        const int s = t % STAGES, tb = t & 1;
+        mbar_wait(&ld_full[s], (t / STAGES) & 1);
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
         const uint32_t bk = st0 + s * STAGE_BYTES, bv = bk + 2 * T_BYTES;
 #pragma unroll
         for (int ks = 0; ks < DK / 8; ++ks)
-          umma_tf32_ss(tmem + T_S + s * BT, umma_desc_kmajor(aq + (ks / 4) * (BQ * 128) + (ks % 4) * 32),
+          umma_tf32_ts(tmem + T_S + tb * BT, tmem + T_Q + ks * 8,
                        umma_desc_kmajor(bk + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < DK / 8; ++ks)
-          umma_tf32_ss(tmem + T_DP + s * BT, umma_desc_kmajor(ado + (ks / 4) * (BQ * 128) + (ks % 4) * 32),
+          umma_tf32_ts(tmem + T_DP + tb * BT, tmem + T_DO + ks * 8,
                        umma_desc_kmajor(bv + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
-        umma_commit(&s_full[s]);
+        umma_commit(&s_full[tb]);
       };
       auto issue_b = [&](int t) {   // dQ += dS(t) K(t)   (A = dS in TMEM, B = K MN-major)
-        const int s = t & 1;
-        mbar_wait(&ds_full[s], (t >> 1) & 1);
+        const int s = t % STAGES, tb = t & 1;
+        mbar_wait(&ds_full[tb], (t >> 1) & 1);
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
         const uint32_t bkm = st0 + s * STAGE_BYTES + T_BYTES;
 #pragma unroll
         for (int ks = 0; ks < BT / 8; ++ks)
-          umma_tf32_ts(tmem + T_DQ, tmem + T_DP + s * BT + ks * 8, umma_desc_mnmajor(bkm + ks * 1024, BT * 128), idesc,
+          umma_tf32_ts(tmem + T_DQ, tmem + T_DP + tb * BT + ks * 8, umma_desc_mnmajor(bkm + ks * 1024, BT * 128), idesc,
                        (t > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&ld_empty[s]);   // stage s (and TMEM pair s) free once everything issued so far has retired
+        umma_commit(&ld_empty[s]);   // stage s free once everything issued so far has retired
       };
-      mbar_wait(&bar_q, 0);
+      mbar_wait(&res_ready, 0);
+      tc_fence_after();
       issue_a(0);
       for (int t = 0; t < n_kv; ++t) {
         if (t + 1 < n_kv) issue_a(t + 1);
@@ -200,20 +212,24 @@ attn_bwd_dq_pipe(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const bool row_ok = row < p.Lq;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int col0 = slice * 16;
+    const int64_t grow = static_cast<int64_t>(b) * p.Lq + (row_ok ? row : 0);
+    resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO);
+    tc_fence_before();
+    mbar_arrive(&res_ready);
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
     const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
     const float delta = row_ok ? p.delta[stat] : 0.f;
     const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(stat)) : 0u;
     const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
     for (int t = 0; t < n_kv; ++t) {
-      const int s = t & 1;
-      mbar_wait(&s_full[s], (t >> 1) & 1);
+      const int s = t % STAGES, tb = t & 1;
+      mbar_wait(&s_full[tb], (t >> 1) & 1);
       tc_fence_after();
       const uint32_t word = shared_mask ? s_mb[s][col0 >> 5] : mask_bits_row(p, b, row, row_ok, t * BT + (col0 & ~31));
       const uint32_t mb = (word >> (col0 & 31)) & 0xFFFFu;
       uint32_t rs[16], rd[16];
-      tmem_ld16(t_lane + T_S + s * BT + col0, rs);
-      tmem_ld16(t_lane + T_DP + s * BT + col0, rd);
+      tmem_ld16(t_lane + T_S + tb * BT + col0, rs);
+      tmem_ld16(t_lane + T_DP + tb * BT + col0, rd);
       tmem_ld_wait();
       const uint32_t* ck = s_ckey[s] + col0;
       if (mb == 0u) {
@@ -223,10 +239,10 @@ attn_bwd_dq_pipe(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (p.drop_thresh) ds16_t<true, true>(rs, rd, mb, p.scale_log2, lse2, delta, dscale, p.drop_thresh, drop_key, ck);
         else ds16_t<true, false>(rs, rd, mb, p.scale_log2, lse2, delta, dscale, p.drop_thresh, drop_key, ck);
       }
-      tmem_st16(t_lane + T_DP + s * BT + col0, rd);
+      tmem_st16(t_lane + T_DP + tb * BT + col0, rd);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&ds_full[s]);
+      mbar_arrive(&ds_full[tb]);
     }
     // ---- epilogue: dQ = scale * accumulator
     mbar_wait(&acc_full, 0);
@@ -253,39 +269,35 @@ attn_bwd_dq_pipe(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // ================================================================================ dK, dV
 template <int DK>
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_bwd_dkv_pipe(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restrict__ v, int64_t ldv,
                   const __grid_constant__ CUtensorMap tmap_q_k, const __grid_constant__ CUtensorMap tmap_q_mn,
                   const __grid_constant__ CUtensorMap tmap_do_k, const __grid_constant__ CUtensorMap tmap_do_mn,
                   const AttnDev p) {
   constexpr int BKV = 128;
   constexpr int G = DK / 32;
-  constexpr int KV_BYTES = BKV * DK * 4;
+  constexpr int STAGES = 3;
   constexpr int T_BYTES = BT * DK * 4;
   constexpr int STAGE_BYTES = 4 * T_BYTES;   // Qk | Qm | dOk | dOm
   constexpr uint32_t TCOLS = 512;
-  constexpr uint32_t T_ST = 0, T_DPT = 2 * BT, T_DV = 4 * BT, T_DK = 4 * BT + DK;
-  static_assert(4 * BT + 2 * DK <= 512, "TMEM budget");
+  constexpr uint32_t T_ST = 0, T_DPT = 2 * BT, T_DV = 4 * BT, T_DK = 4 * BT + DK, T_K = 4 * BT + 2 * DK, T_V = 4 * BT + 3 * DK;
+  static_assert(4 * BT + 4 * DK <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + KV_BYTES;
-  uint8_t* sStage = sV + KV_BYTES;
-  __shared__ uint64_t bar_kv, ld_full[2], ld_empty[2], s_full[2], ds_full[2], acc_full;
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t res_ready, ld_full[STAGES], ld_empty[STAGES], s_full[2], ds_full[2], acc_full;
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float s_lse[2][BT];
-  __shared__ __align__(16) float s_delta[2][BT];
-  __shared__ __align__(16) uint32_t s_rkey[2][BT];
+  __shared__ __align__(16) float s_lse[STAGES][BT];
+  __shared__ __align__(16) float s_delta[STAGES][BT];
+  __shared__ __align__(16) uint32_t s_rkey[STAGES][BT];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
   const int n_q = (p.Lq + BT - 1) / BT;
 
   if (tid == 0) {
-    mbar_init(&bar_kv, 1); mbar_init(&acc_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&ld_full[s], 1); mbar_init(&ld_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], NCOMP);
-    }
+    mbar_init(&res_ready, NCOMP); mbar_init(&acc_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ld_full[s], 1); mbar_init(&ld_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], NCOMP); }
     fence_mbar_init();
   }
   if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
@@ -297,18 +309,11 @@ attn_bwd_dkv_pipe(const __grid_constant__ CUtensorMap tmap_k, const __grid_const
   if (warp == W_PROD) {
     // ===================== producer =====================
     if (lane == 0) {
-      tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_q_k);
-      tma_prefetch_desc(&tmap_q_mn); tma_prefetch_desc(&tmap_do_k); tma_prefetch_desc(&tmap_do_mn);
-      mbar_arrive_expect_tx(&bar_kv, 2 * KV_BYTES);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        tma_load_3d(sK + g * (BKV * 128), &tmap_k, &bar_kv, h * DK + g * 32, kv0, b);
-        tma_load_3d(sV + g * (BKV * 128), &tmap_v, &bar_kv, h * DK + g * 32, kv0, b);
-      }
+      tma_prefetch_desc(&tmap_q_k); tma_prefetch_desc(&tmap_q_mn); tma_prefetch_desc(&tmap_do_k); tma_prefetch_desc(&tmap_do_mn);
     }
     for (int t = 0; t < n_q; ++t) {
-      const int s = t & 1;
-      mbar_wait(&ld_empty[s], ((t >> 1) & 1) ^ 1);
+      const int s = t % STAGES;
+      mbar_wait(&ld_empty[s], ((t / STAGES) & 1) ^ 1);
 #pragma unroll
       for (int e = lane; e < BT; e += 32) {   // per-query statistics of this tile
         const int q = t * BT + e;
@@ -321,52 +326,50 @@ attn_bwd_dkv_pipe(const __grid_constant__ CUtensorMap tmap_k, const __grid_const
       if (lane == 0) {
         uint8_t* st = sStage + s * STAGE_BYTES;
         mbar_arrive_expect_tx(&ld_full[s], STAGE_BYTES);
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          tma_load_3d(st + g * (BT * 128), &tmap_q_k, &ld_full[s], h * DK + g * 32, t * BT, b);
-          tma_load_3d(st + T_BYTES + g * (BT * 128), &tmap_q_mn, &ld_full[s], h * DK + g * 32, t * BT, b);
-          tma_load_3d(st + 2 * T_BYTES + g * (BT * 128), &tmap_do_k, &ld_full[s], h * DK + g * 32, t * BT, b);
-          tma_load_3d(st + 3 * T_BYTES + g * (BT * 128), &tmap_do_mn, &ld_full[s], h * DK + g * 32, t * BT, b);
-        }
+        tma_load_4d(st, &tmap_q_k, &ld_full[s], 0, t * BT, h * G, b);
+        tma_load_4d(st + T_BYTES, &tmap_q_mn, &ld_full[s], 0, t * BT, h * G, b);
+        tma_load_4d(st + 2 * T_BYTES, &tmap_do_k, &ld_full[s], 0, t * BT, h * G, b);
+        tma_load_4d(st + 3 * T_BYTES, &tmap_do_mn, &ld_full[s], 0, t * BT, h * G, b);
       }
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t ak = smem_u32(sK), av = smem_u32(sV), st0 = smem_u32(sStage);
-      auto issue_a = [&](int t) {   // S^T(t) = K Q^T, dP^T(t) = V dO^T
-        const int s = t & 1;
-        mbar_wait(&ld_full[s], (t >> 1) & 1);
+      const uint32_t st0 = smem_u32(sStage);
+      auto issue_a = [&](int t) {   // S^T(t) = K Q^T, dP^T(t) = V dO^T   (A = resident tile in TMEM, B K-major)
+        const int s = t % STAGES, tb = t & 1;
+        mbar_wait(&ld_full[s], (t / STAGES) & 1);
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
         const uint32_t bq = st0 + s * STAGE_BYTES, bdo = bq + 2 * T_BYTES;
 #pragma unroll
         for (int ks = 0; ks < DK / 8; ++ks)
-          umma_tf32_ss(tmem + T_ST + s * BT, umma_desc_kmajor(ak + (ks / 4) * (BKV * 128) + (ks % 4) * 32),
+          umma_tf32_ts(tmem + T_ST + tb * BT, tmem + T_K + ks * 8,
                        umma_desc_kmajor(bq + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < DK / 8; ++ks)
-          umma_tf32_ss(tmem + T_DPT + s * BT, umma_desc_kmajor(av + (ks / 4) * (BKV * 128) + (ks % 4) * 32),
+          umma_tf32_ts(tmem + T_DPT + tb * BT, tmem + T_V + ks * 8,
                        umma_desc_kmajor(bdo + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
-        umma_commit(&s_full[s]);
+        umma_commit(&s_full[tb]);
       };
       auto issue_b = [&](int t) {   // dV += P^T dO, dK += dS^T Q   (A in TMEM, B MN-major)
-        const int s = t & 1;
-        mbar_wait(&ds_full[s], (t >> 1) & 1);
+        const int s = t % STAGES, tb = t & 1;
+        mbar_wait(&ds_full[tb], (t >> 1) & 1);
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
         const uint32_t bqm = st0 + s * STAGE_BYTES + T_BYTES, bdom = st0 + s * STAGE_BYTES + 3 * T_BYTES;
 #pragma unroll
         for (int ks = 0; ks < BT / 8; ++ks)
-          umma_tf32_ts(tmem + T_DV, tmem + T_ST + s * BT + ks * 8, umma_desc_mnmajor(bdom + ks * 1024, BT * 128), idesc,
+          umma_tf32_ts(tmem + T_DV, tmem + T_ST + tb * BT + ks * 8, umma_desc_mnmajor(bdom + ks * 1024, BT * 128), idesc,
                        (t > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < BT / 8; ++ks)
-          umma_tf32_ts(tmem + T_DK, tmem + T_DPT + s * BT + ks * 8, umma_desc_mnmajor(bqm + ks * 1024, BT * 128), idesc,
+          umma_tf32_ts(tmem + T_DK, tmem + T_DPT + tb * BT + ks * 8, umma_desc_mnmajor(bqm + ks * 1024, BT * 128), idesc,
                        (t > 0 || ks > 0) ? 1u : 0u);
         umma_commit(&ld_empty[s]);
       };
-      mbar_wait(&bar_kv, 0);
+      mbar_wait(&res_ready, 0);
+      tc_fence_after();
       issue_a(0);
       for (int t = 0; t < n_q; ++t) {
         if (t + 1 < n_q) issue_a(t + 1);
@@ -382,6 +385,10 @@ attn_bwd_dkv_pipe(const __grid_constant__ CUtensorMap tmap_k, const __grid_const
     const bool key_ok = key < p.Lk;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int col0 = slice * 16;
+    const int64_t grow = static_cast<int64_t>(b) * p.Lk + (key_ok ? key : 0);
+    resident_to_tmem<DK>(k, ldk, v, ldv, grow, key_ok, h, slice, t_lane, T_K, T_V);
+    tc_fence_before();
+    mbar_arrive(&res_ready);
     const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
     bool key_masked = !key_ok;
     if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
@@ -390,13 +397,13 @@ attn_bwd_dkv_pipe(const __grid_constant__ CUtensorMap tmap_k, const __grid_const
     const uint32_t my_ckey = p.drop_thresh ? dropout_col_key(p.drop_seed, static_cast<uint32_t>(key_ok ? key : 0)) : 0u;
     const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
     for (int t = 0; t < n_q; ++t) {
-      const int s = t & 1;
-      mbar_wait(&s_full[s], (t >> 1) & 1);
+      const int s = t % STAGES, tb = t & 1;
+      mbar_wait(&s_full[tb], (t >> 1) & 1);
       tc_fence_after();
       uint32_t rs[16], rd[16];
       // tcgen05.ld/st are warp-collective (.sync.aligned): every lane executes them, whatever its key's mask state
-      tmem_ld16(t_lane + T_ST + s * BT + col0, rs);
-      tmem_ld16(t_lane + T_DPT + s * BT + col0, rd);
+      tmem_ld16(t_lane + T_ST + tb * BT + col0, rs);
+      tmem_ld16(t_lane + T_DPT + tb * BT + col0, rd);
       tmem_ld_wait();
       if (!mask_dense && key_masked) {   // this key is padding for every query: P = dS = 0
 #pragma unroll
@@ -414,11 +421,11 @@ attn_bwd_dkv_pipe(const __grid_constant__ CUtensorMap tmap_k, const __grid_const
           else dkv16_t<false, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
         }
       }
-      tmem_st16(t_lane + T_ST + s * BT + col0, rs);
-      tmem_st16(t_lane + T_DPT + s * BT + col0, rd);
+      tmem_st16(t_lane + T_ST + tb * BT + col0, rs);
+      tmem_st16(t_lane + T_DPT + tb * BT + col0, rd);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&ds_full[s]);
+      mbar_arrive(&ds_full[tb]);
     }
     // ---- epilogue: dV = dropout-scale * acc, dK = softmax-scale * acc
     mbar_wait(&acc_full, 0);
@@ -453,38 +460,34 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
   const AttnArgs& f = a.f;
   const int cols = f.H * DK;
   {
-    CUtensorMap tk, tv, tqk, tqm, tdk, tdm;
-    ST_TRY(make_act_tmap(&tk, f.k, f.ldk, cols, f.Lk, f.B, 128, 0));
-    ST_TRY(make_act_tmap(&tv, f.v, f.ldv, cols, f.Lk, f.B, 128, 0));
-    ST_TRY(make_act_tmap(&tqk, f.q, f.ldq, cols, f.Lq, f.B, BT, 0));
-    ST_TRY(make_act_tmap(&tqm, f.q, f.ldq, cols, f.Lq, f.B, BT, 1));
-    ST_TRY(make_act_tmap(&tdk, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, 0));
-    ST_TRY(make_act_tmap(&tdm, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, 1));
-    constexpr int SMEM = 2 * 128 * DK * 4 + 2 * 4 * BT * DK * 4 + 1024;
+    CUtensorMap tqk, tqm, tdk, tdm;
+    ST_TRY(make_act_tmap(&tqk, f.q, f.ldq, cols, f.Lq, f.B, BT, 0, DK));
+    ST_TRY(make_act_tmap(&tqm, f.q, f.ldq, cols, f.Lq, f.B, BT, 1, DK));
+    ST_TRY(make_act_tmap(&tdk, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, 0, DK));
+    ST_TRY(make_act_tmap(&tdm, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, 1, DK));
+    constexpr int SMEM = 3 * 4 * BT * DK * 4 + 1024;
     auto kern = attn_bwd_dkv_pipe<DK>;
     static bool attr = false;
     if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
     dim3 grid((f.Lk + 127) / 128, f.H, f.B);
     // algorithmic share of the attention backward carried by this kernel: dV and dK (S, dP recompute not counted)
     ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    kern<<<grid, NTHREADS, SMEM, s>>>(tk, tv, tqk, tqm, tdk, tdm, p);
+    kern<<<grid, NTHREADS, SMEM, s>>>(f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, p);
     ST_CHECK_LAUNCH();
   }
   {
-    CUtensorMap tq, tdo, tkk, tkm, tvk;
-    ST_TRY(make_act_tmap(&tq, f.q, f.ldq, cols, f.Lq, f.B, 128, 0));
-    ST_TRY(make_act_tmap(&tdo, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0));
-    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BT, 0));
-    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BT, 1));
-    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BT, 0));
-    constexpr int SMEM = 2 * 128 * DK * 4 + 2 * 3 * BT * DK * 4 + 1024;
+    CUtensorMap tkk, tkm, tvk;
+    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BT, 0, DK));
+    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BT, 1, DK));
+    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BT, 0, DK));
+    constexpr int SMEM = 4 * 3 * BT * DK * 4 + 1024;
     auto kern = attn_bwd_dq_pipe<DK>;
     static bool attr = false;
     if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
     dim3 grid((f.Lq + 127) / 128, f.H, f.B);
     // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
     ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    kern<<<grid, NTHREADS, SMEM, s>>>(tq, tdo, tkk, tkm, tvk, p);
+    kern<<<grid, NTHREADS, SMEM, s>>>(f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, p);
     ST_CHECK_LAUNCH();
   }
   return ST_OK;

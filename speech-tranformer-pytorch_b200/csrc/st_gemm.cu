@@ -48,7 +48,10 @@ struct GemmParams {
   GemmEpilogue ep;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster own vertically adjacent output tiles
+// (same n_blk), each TMA-loads half of the shared B tile and multicasts it to both, which cuts the L2->SM operand
+// traffic per CTA from A+B to A+B/2; a smem stage is then released by BOTH consumers (multicast tcgen05.commit).
+template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -73,7 +76,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -86,21 +89,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_mn = p.m_tiles * p.n_tiles;
+  // work units: CL vertically adjacent tiles; CTA `crank` of the cluster takes tile m = unit_m * CL + crank
+  const int crank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m_units = (p.m_tiles + CL - 1) / CL;
+  const int tiles_mn = m_units * p.n_tiles;
   const int num_tiles = tiles_mn * p.k_splits;
+  const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         const int n_blk = tile % p.n_tiles;
-        const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+        const int m_blk = ((tile / p.n_tiles) % m_units) * CL + crank;
         const int split = tile / tiles_mn;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
@@ -116,12 +123,26 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int i = 0; i < BM / 32; ++i)
               tma_load_2d(sa + i * 4096, &tmap_a, &full_bar[stage], m_blk * BM + i * 32, kb * BK);
           }
-          if (!B_MN) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
+          if (CL == 1) {
+            if (!B_MN) {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 32; ++i)
-              tma_load_2d(sb + i * 4096, &tmap_b, &full_bar[stage], n_blk * BN + i * 32, kb * BK);
+              for (int i = 0; i < BN / 32; ++i)
+                tma_load_2d(sb + i * 4096, &tmap_b, &full_bar[stage], n_blk * BN + i * 32, kb * BK);
+            }
+          } else {  // this CTA fetches its half of the B tile for the whole cluster
+            constexpr uint16_t kAll = (1u << CL) - 1;
+            if (!B_MN) {
+              tma_load_2d_mc(sb + crank * (BN / CL) * 128, &tmap_b, &full_bar[stage], kb * BK,
+                             n_blk * BN + crank * (BN / CL), kAll);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 32 / CL; ++i) {
+                const int g = crank * (BN / 32 / CL) + i;
+                tma_load_2d_mc(sb + g * 4096, &tmap_b, &full_bar[stage], n_blk * BN + g * 32, kb * BK, kAll);
+              }
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -135,7 +156,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         const int split = tile / tiles_mn;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
@@ -155,7 +176,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint64_t bdesc = B_MN ? umma_desc_mnmajor(sb + k * 1024, 4096) : umma_desc_kmajor(sb + k * 32);
             umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          // frees the smem stage once these MMAs retire (in every CTA whose TMA writes into it)
+          if (CL > 1) umma_commit_mc(&empty_bar[stage], (1u << CL) - 1); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
@@ -174,9 +196,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         (!ep.aux || (((ep.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0)));
     const int lcol = (lane & 7) * 4;   // this lane's 4 columns inside a 32-column chunk
     const int lrow = lane >> 3;        // and its row inside each group of 4 rows
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       const int n_blk = tile % p.n_tiles;
-      const int m_blk = (tile / p.n_tiles) % p.m_tiles;
+      const int m_blk = ((tile / p.n_tiles) % m_units) * CL + crank;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row_base = m_blk * BM + quarter * 32;
@@ -272,39 +294,54 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA may exit while a peer can still write into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_set = false;  // per instantiation; benign race (idempotent)
   if (!attr_set) {
     ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int units = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.k_splits;
   int cap = get_option("gemm_max_ctas");
   if (cap <= 0) cap = num_sms();
-  const int grid = tiles < cap ? tiles : cap;
+  cap = cap / CL > 0 ? cap / CL : 1;
+  const int grid = (units < cap ? units : cap) * CL;
   ProfScope prof(stream, PROF_GEMM, 2.0 * p.M * static_cast<double>(p.N) * p.K);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  if (CL == 1) {
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  }
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
-template <int BN>
+template <int BN, int CL>
 int dispatch_mode(cudaStream_t stream, GemmMode mode, const CUtensorMap& ta, const CUtensorMap& tb,
                   const GemmParams& p) {
   switch (mode) {
-    case GEMM_NT: return launch_gemm<BN, false, false>(stream, ta, tb, p);
-    case GEMM_NN: return launch_gemm<BN, false, true>(stream, ta, tb, p);
-    case GEMM_TN: return launch_gemm<BN, true, true>(stream, ta, tb, p);
+    case GEMM_NT: return launch_gemm<BN, false, false, CL>(stream, ta, tb, p);
+    case GEMM_NN: return launch_gemm<BN, false, true, CL>(stream, ta, tb, p);
+    case GEMM_TN: return launch_gemm<BN, true, true, CL>(stream, ta, tb, p);
   }
   set_error("gemm_tf32: bad mode %d", static_cast<int>(mode));
   return ST_ERR_INVALID;
@@ -344,6 +381,12 @@ int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, c
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = (N + BN - 1) / BN;
   p.ep = ep;
+  // 2-CTA clusters with a multicast B tile
+  // (measured on B200: correct but 10-20 % SLOWER than independent CTAs at these shapes — the two CTAs run in
+  // lock-step and the bytes delivered to each SM do not change — so it is opt-in: st_set_option("gemm_cluster", 2))
+  int CL = 1;
+  const int forced_cl = get_option("gemm_cluster");
+  if (forced_cl == 1 || (forced_cl == 2 && BN == 256 && p.m_tiles >= 2)) CL = forced_cl;
 
   CUtensorMap ta, tb;
   {
@@ -357,14 +400,14 @@ int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, c
   {
     uint64_t dims[2], strides[1] = {static_cast<uint64_t>(ldb) * 4};
     uint32_t box[2];
-    if (mode == GEMM_NT) { dims[0] = K; dims[1] = N; box[0] = 32; box[1] = static_cast<uint32_t>(BN); }
+    if (mode == GEMM_NT) { dims[0] = K; dims[1] = N; box[0] = 32; box[1] = static_cast<uint32_t>(BN / CL); }
     else                 { dims[0] = N; dims[1] = K; box[0] = 32; box[1] = 32; }
     ST_TRY(make_tmap_f32(&tb, B, 2, dims, strides, box, (mode != GEMM_NT) ? 1 : 0));
   }
   switch (BN) {
-    case 256: return dispatch_mode<256>(stream, mode, ta, tb, p);
-    case 128: return dispatch_mode<128>(stream, mode, ta, tb, p);
-    default:  return dispatch_mode<64>(stream, mode, ta, tb, p);
+    case 256: return CL == 2 ? dispatch_mode<256, 2>(stream, mode, ta, tb, p) : dispatch_mode<256, 1>(stream, mode, ta, tb, p);
+    case 128: return dispatch_mode<128, 1>(stream, mode, ta, tb, p);
+    default:  return dispatch_mode<64, 1>(stream, mode, ta, tb, p);
   }
 }
 

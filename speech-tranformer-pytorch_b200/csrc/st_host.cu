@@ -36,6 +36,7 @@ struct Option { const char* name; int value; };
 Option g_options[] = {
     {"gemm_max_ctas", 0},   // 0 = one CTA per SM; >0 caps the persistent grid (tests multi-tile paths)
     {"attn_bwd_simple", 0}, // 1 = use the non-pipelined attention backward kernels for every d_k (A/B testing)
+    {"gemm_cluster", 0},    // 0 = heuristic; 1 / 2 forces the GEMM cluster size (2 = multicast B tile)
     {"gemm_bn", 0},       // 0 = heuristic; 64/128/256 forces the GEMM tile width (tuning / tests)
 };
 }  // namespace

@@ -231,10 +231,21 @@ int selftest(int which, double* err) {
     case 12: return ts_case<64, 32, true>(err);     // A in TMEM, B MN-major
     case 13: return ts_case<64, 128, true>(err);
     case 14: return gemm_case(GEMM_NN, 300, 4340, 512, 1, false, false, 0, false, err); // wide N (vocab-like)
+    case 15: case 16: case 17: case 18: case 19: {   // 2-CTA clusters with the multicast B tile, all three operand modes
+      set_option("gemm_cluster", 2);
+      int st = ST_ERR_INVALID;
+      if (which == 15) st = gemm_case(GEMM_NT, 384, 512, 512, 1, true, true, 0, true, err, 0, 4);     // odd m_tiles, 2 clusters
+      if (which == 16) st = gemm_case(GEMM_NN, 300, 768, 256, 1, false, false, 1, false, err);        // ragged M, residual
+      if (which == 17) st = gemm_case(GEMM_TN, 512, 512, 4096, 4, false, false, 0, false, err, 0, 6); // split-K atomics
+      if (which == 18) st = gemm_case(GEMM_NT, 20000, 512, 64, 1, true, false, 0, false, err);        // full grid, many units
+      if (which == 19) st = gemm_case(GEMM_NT, 256, 300, 72, 1, false, false, 0, false, err, 3);      // ragged N/K tails
+      set_option("gemm_cluster", 0);
+      return st;
+    }
     default: set_error("selftest: no case %d", which); return ST_ERR_INVALID;
   }
 }
 
-int selftest_count() { return 15; }
+int selftest_count() { return 20; }
 
 }  // namespace st
