@@ -36,7 +36,8 @@ struct Option { const char* name; int value; };
 Option g_options[] = {
     {"gemm_max_ctas", 0},   // 0 = one CTA per SM; >0 caps the persistent grid (tests multi-tile paths)
     {"attn_bwd_simple", 0}, // 1 = use the non-pipelined attention backward kernels for every d_k (A/B testing)
-    {"gemm_cluster", 0},    // 0 = heuristic; 1 / 2 forces the GEMM cluster size (2 = multicast B tile)
+    {"gemm_cluster", 0},    // 0 = heuristic; 1 = independent CTAs, 2 = multicast B tile, 3 = CTA-pair MMA (cta_group::2)
+    {"gemm_generic_epilogue", 0},   // 1 = force the generic (runtime-flag) GEMM epilogue (tests)
     {"gemm_bn", 0},       // 0 = heuristic; 64/128/256 forces the GEMM tile width (tuning / tests)
 };
 }  // namespace
@@ -55,7 +56,7 @@ int get_option(const char* name) {
 
 // ---- per-kernel-class event timing
 namespace {
-struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+struct ProfRec { cudaEvent_t a, b; int cls; double work; long long tag; };
 std::atomic<int> g_prof_on{0};
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
@@ -63,11 +64,12 @@ std::vector<ProfRec> g_prof;
 
 void profile_enable(int on) { g_prof_on.store(on ? 1 : 0, std::memory_order_relaxed); }
 
-ProfScope::ProfScope(cudaStream_t s, ProfClass cls, double work) : stream(s), slot(-1) {
+ProfScope::ProfScope(cudaStream_t s, ProfClass cls, double work, long long tag) : stream(s), slot(-1) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
   ProfRec r{};
   r.cls = cls;
   r.work = work;
+  r.tag = tag;
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
   cudaEventRecord(r.a, s);
   std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -101,12 +103,12 @@ int profile_dump(const char* path) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   FILE* f = fopen(path, "w");
   if (!f) { set_error("profile_dump: cannot open %s", path); return ST_ERR_INVALID; }
-  fprintf(f, "index,class,work,ms\n");
+  fprintf(f, "index,class,work,ms,tag\n");
   int i = 0;
   for (auto& r : g_prof) {
     float e = 0.f;
     if (cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&e, r.a, r.b);
-    fprintf(f, "%d,%d,%.0f,%.6f\n", i++, r.cls, r.work, e);
+    fprintf(f, "%d,%d,%.0f,%.6f,%lld\n", i++, r.cls, r.work, e, r.tag);
   }
   fclose(f);
   return ST_OK;

@@ -64,7 +64,7 @@ enum ProfClass : int {
   PROF_COLSUM, PROF_LSCE, PROF_SUMSQ, PROF_ADAM, PROF_NUM
 };
 struct ProfScope {
-  ProfScope(cudaStream_t s, ProfClass cls, double work);  // work: algorithmic FLOPs (tensor kernels) or bytes (HBM kernels)
+  ProfScope(cudaStream_t s, ProfClass cls, double work, long long tag = 0);   // tag: free-form id kept in the dump  // work: algorithmic FLOPs (tensor kernels) or bytes (HBM kernels)
   ~ProfScope();
   cudaStream_t stream;
   int slot;

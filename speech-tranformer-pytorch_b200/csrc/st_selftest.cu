@@ -242,10 +242,24 @@ int selftest(int which, double* err) {
       set_option("gemm_cluster", 0);
       return st;
     }
+    case 20: case 21: case 22: case 23: case 24: case 25: {   // CTA-pair MMA (cta_group::2), all three operand modes
+      set_option("gemm_cluster", 3);
+      set_option("gemm_bn", 256);
+      int st = ST_ERR_INVALID;
+      if (which == 20) st = gemm_case(GEMM_NT, 256, 256, 32, 1, false, false, 0, false, err);         // one pair, one k-block
+      if (which == 21) st = gemm_case(GEMM_NT, 384, 512, 512, 1, true, true, 0, true, err, 0, 4);     // odd m_tiles, 2 pairs
+      if (which == 22) st = gemm_case(GEMM_NN, 300, 768, 256, 1, false, false, 1, false, err);        // ragged M, residual
+      if (which == 23) st = gemm_case(GEMM_TN, 512, 512, 4096, 4, false, false, 0, false, err, 0, 6); // split-K atomics
+      if (which == 24) st = gemm_case(GEMM_NT, 20000, 512, 64, 1, true, false, 0, false, err);        // full grid, many units
+      if (which == 25) st = gemm_case(GEMM_NT, 256, 300, 72, 1, false, false, 0, false, err, 3);      // ragged N/K tails
+      set_option("gemm_cluster", 0);
+      set_option("gemm_bn", 0);
+      return st;
+    }
     default: set_error("selftest: no case %d", which); return ST_ERR_INVALID;
   }
 }
 
-int selftest_count() { return 20; }
+int selftest_count() { return 26; }
 
 }  // namespace st

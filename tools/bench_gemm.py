@@ -5,12 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import speech_tranformer_pytorch_b200 as stb
 L = stb._lib; lib = L.load(); DEV = "cuda:0"
 def p(t): return None if t is None else t.data_ptr()
+if os.environ.get("ST_GEMM_CLUSTER"): lib.st_set_option(b"gemm_cluster", int(os.environ["ST_GEMM_CLUSTER"]))
 flush = torch.empty(256 * 1024 * 1024 // 4, device=DEV)
 def run(mode, M, N, K, splits=1, iters=5, bias=True, aux_mode=0, drop=0.0):
     A = torch.randn((K, M) if mode == 2 else (M, K), device=DEV); B = torch.randn((N, K) if mode == 0 else (K, N), device=DEV)
     Cm = torch.zeros(M, N, device=DEV); bvec = torch.randn(N, device=DEV) if bias and mode == 0 else None
     aux = torch.randn(M, N, device=DEV) if aux_mode else None
-    ep = L.GemmEpilogue(bias=p(bvec), aux=p(aux), ldaux=N, aux_mode=aux_mode, relu=1 if drop else 0, round_tf32=1 if mode != 2 else 0, k_splits=splits, dropout_p=drop, seed=7)
+    ep = L.GemmEpilogue(bias=p(bvec), aux=p(aux), ldaux=N, aux_mode=aux_mode, relu=1 if drop else 0, round_tf32=1 if (mode != 2 and aux_mode != 1) else 0, k_splits=splits, dropout_p=drop, seed=7)
     ts = []
     for i in range(iters + 2):
         flush.zero_()

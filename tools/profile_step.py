@@ -30,8 +30,13 @@ lib.st_profile_dump(a.csv.encode())
 names = [lib.st_profile_class_name(i).decode() for i in range(lib.st_profile_classes())]
 groups = collections.OrderedDict()
 for line in open(a.csv).read().splitlines()[1:]:
-    _, cls, work, ms = line.split(","); k = (int(cls), float(work)); g = groups.setdefault(k, [0, 0.0]); g[0] += 1; g[1] += float(ms)
+    _, cls, work, ms, tag = line.split(","); k = (int(cls), float(work), int(tag)); g = groups.setdefault(k, [0, 0.0]); g[0] += 1; g[1] += float(ms)
 tot = sum(g[1] for g in groups.values())
 print(f"profiled kernels total {tot:.2f} ms")
-for (cls, work), (n, ms) in sorted(groups.items(), key=lambda kv: -kv[1][1])[:40]:
-    print(f"{names[cls]:15s} work {work:14.4g} x{n:3d}  total {ms:7.3f} ms  avg {ms / n * 1e3:8.1f} us  rate {work * n / ms / 1e9:8.1f} G/s*1e3")
+def tagstr(t):
+    if not t: return ""
+    bn, var, fl, mode = t & 15, (t >> 4) & 15, (t >> 8) & 15, (t >> 12) & 15
+    K, N, M = ((t >> 16) & 0x3FFFF) * 8, (t >> 34) & 0x3FFF, (t >> 48) * 8
+    return f" M{M} N{N} K{K} {'NT NN TN'.split()[mode]} fl{fl} var{var} bn{bn * 64}"
+for (cls, work, tag), (n, ms) in sorted(groups.items(), key=lambda kv: -kv[1][1])[:60]:
+    print(f"{names[cls]:15s}{tagstr(tag):44s} work {work:14.4g} x{n:3d}  total {ms:7.3f} ms  avg {ms / n * 1e3:8.1f} us  rate {work * n / ms / 1e9:8.1f} G/s*1e3")
