@@ -408,16 +408,32 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
     ab.dq = dpq; ab.lddq = p.ldpq; ab.dk_ = dpk; ab.lddk = p.ldpk; ab.dv = dpv; ab.lddv = p.ldpv;
     ST_TRY(attn_bwd(s, ab));
   }
-  // projection bias / weight gradients
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dbv, 0, d * sizeof(float), s));
-  ST_TRY(colsum_add(s, dpq, p.ldpq, M, d, b.dbq));
-  ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, d, b.dbk));
-  ST_TRY(colsum_add(s, dpv, p.ldpv, Mk, d, b.dbv));
-  ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d));
-  ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d));
-  ST_TRY(wgrad(s, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d));
+  // projection bias / weight gradients.  When the caller hands out dW / db as slices of one packed [wq; wk; wv]
+  // buffer (functional.py does) and the projections share their input, one GEMM / column sum covers all of them.
+  const int64_t dd = static_cast<int64_t>(d) * d;
+  const bool pack_kv = p.same_kv && b.dwv == b.dwk + dd && b.dbv == b.dbk + d;
+  const bool pack_qkv = p.same_qkv && pack_kv && b.dwk == b.dwq + dd && b.dbk == b.dbq + d;
+  if (pack_qkv) {
+    ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, 3 * d * sizeof(float), s));
+    ST_TRY(colsum_add(s, dpq, p.ldpq, M, 3 * d, b.dbq));
+    ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d));
+  } else {
+    ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, d * sizeof(float), s));
+    ST_TRY(colsum_add(s, dpq, p.ldpq, M, d, b.dbq));
+    ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d));
+    if (pack_kv) {
+      ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, 2 * d * sizeof(float), s));
+      ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, 2 * d, b.dbk));
+      ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d));
+    } else {
+      ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, d * sizeof(float), s));
+      ST_CHECK_CUDA(cudaMemsetAsync(b.dbv, 0, d * sizeof(float), s));
+      ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, d, b.dbk));
+      ST_TRY(colsum_add(s, dpv, p.ldpv, Mk, d, b.dbv));
+      ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d));
+      ST_TRY(wgrad(s, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d));
+    }
+  }
   // input gradients; the residual branch contributes dz to whichever input it aliased
   const bool res_q = (a.residual == a.q_in), res_k = (a.residual == a.k_in), res_v = (a.residual == a.v_in);
   auto with_res = [&](bool on) { GemmEpilogue e; if (on) { e.aux = dz; e.ldaux = d; e.aux_mode = 1; } return e; };

@@ -2,8 +2,8 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..5  : epilogue (tcgen05.ld -> smem transpose -> bias / ReLU / dropout / residual / TF32
-//                 rounding -> coalesced global stores)
+//   warps 2..9  : epilogue (tcgen05.ld -> smem transpose -> bias / ReLU / dropout / residual / TF32
+//                 rounding -> coalesced global stores); two warps per TMEM lane quarter
 //
 // Output tile 128 x BN (BN in {64,128,256}); K is consumed in blocks of 32 fp32 (= one 128-byte
 // swizzle atom); accumulators are double-buffered in TMEM (2*BN columns) so the epilogue of
@@ -21,7 +21,7 @@
 //
 // Epilogue: a TMEM lane is an output row, so tcgen05.ld hands each thread 32 consecutive columns
 // of ITS row; storing that directly would touch 32 different 128-byte lines per instruction.  Each
-// epilogue warp therefore transposes 32x32 blocks through a padded smem tile and stores 4 full
+// epilogue warp therefore transposes 32x32 blocks through a swizzled smem tile and stores 4 full
 // 128-byte row segments per instruction (bias and residual loads are coalesced the same way).
 #include "st_common.cuh"
 #include "st_gemm.cuh"
@@ -34,9 +34,13 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;                       // fp32 elements per k-block = 128 bytes
 constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_LD = 36;                   // padded row length (floats) of the per-warp transpose tile
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, interleaved over the 32-column chunks
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;   // one XOR-swizzled 32 x 32 fp32 transpose tile per epilogue warp
+
+// float offset of (row, 4-float group g) in a warp's transpose tile: 128-byte rows, 16-byte groups XOR-swizzled by
+// the row so that both the row-per-lane writes and the 8-lanes-per-row reads are bank-conflict free without padding
+__device__ __forceinline__ int epi_swz(int row, int g) { return row * 32 + ((g ^ (row & 7)) << 2); }
 
 template <int BN>
 struct GemmCfg {
@@ -89,22 +93,22 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 // Pull this warp's 32 x BN slice of the aux operand towards L2 while the tile's main loop is still running
 // (lane l fetches the 128-byte lines of row l).
 template <int BN>
-__device__ __forceinline__ void prefetch_aux_tile(const GemmParams& p, int m_blk, int n_blk, int quarter, int lane) {
+__device__ __forceinline__ void prefetch_aux_tile(const GemmParams& p, int m_blk, int n_blk, int quarter, int half, int lane) {
   const int row = m_blk * BM + quarter * 32 + lane;
   if (row >= p.M) return;
   const float* a = p.ep.aux + static_cast<int64_t>(row) * p.ep.ldaux + n_blk * BN;
   const int cols = min(BN, p.N - n_blk * BN);
 #pragma unroll
-  for (int c = 0; c < BN; c += 32)
-    if (c < cols) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + c));
+  for (int c = 0; c < BN; c += 32 * (EPI_WARPS / 4))
+    if (c + half * 32 < cols) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + c + half * 32));
 }
 
 // Drain this warp's 32 rows of one 128 x BN accumulator.  tmem_acc: TMEM address of (warp's first lane, first
-// accumulator column); stg_s: shared-space address of the warp's 32 x EPI_LD transpose tile.
+// accumulator column); stg_s: shared-space address of the warp's swizzled 32 x 32 transpose tile.
 // Requires the host-checked "vector" conditions: C / aux / bias 16-byte aligned, ldc, ldaux, N multiples of 4.
 template <int BN, int F>
 __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_s, uint32_t tmem_acc, int m_blk, int n_blk,
-                                              int quarter, int lane) {
+                                              int quarter, int half, int lane) {
   constexpr bool RELU = (F == EPI_RELU_DROP_ROUND);
   constexpr bool DROP = (F == EPI_RELU_DROP_ROUND);
   constexpr int AUX = (F == EPI_AUX_ADD) ? 1 : (F == EPI_AUX_MASK_ROUND ? 2 : 0);
@@ -126,11 +130,9 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
 #pragma unroll
     for (int i = 0; i < 8; ++i) keys[i] = dropout_row_key(ep.drop_seed, static_cast<uint64_t>(row0 + 4 * i));
   }
-  const uint32_t st_w = stg_s + lane * (EPI_LD * 4);
-  const uint32_t st_r = stg_s + (lrow * EPI_LD + lcol) * 4;
   const int n_chunks = min(BN / 32, (p.N - n_blk * BN + 31) >> 5);
 #pragma unroll 1
-  for (int c = 0; c < n_chunks; ++c) {
+  for (int c = half; c < n_chunks; c += EPI_WARPS / 4) {
     const int col = col0 + c * 32;
     const bool col_ok = col < p.N;
     // residual / ReLU-mask operand and bias: issue the loads first, their latency hides behind the TMEM read and
@@ -150,14 +152,14 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        sts128(st_w + j * 16, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+        sts128(stg_s + epi_swz(lane, j) * 4, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                __uint_as_float(r[4 * j + 3]));
     }
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (col_ok && i * 4 < rows_left) {
-        const float4 s4 = lds128(st_r + i * (4 * EPI_LD * 4));
+        const float4 s4 = lds128(stg_s + epi_swz(i * 4 + lrow, lane & 7) * 4);
         float v[4] = {s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w};
         if (RELU) {
 #pragma unroll
@@ -197,7 +199,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
 // Any flag combination, any alignment (scalar loads / stores where needed).
 template <int BN>
 __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, uint32_t tmem_acc, int m_blk, int n_blk,
-                                              int quarter, int lane) {
+                                              int quarter, int half, int lane) {
   const GemmEpilogue& ep = p.ep;
   const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0) &&
                       (!ep.aux || (((ep.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0)));
@@ -205,7 +207,7 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
   const int lrow = lane >> 3;
   const int row_base = m_blk * BM + quarter * 32;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = half; c < BN / 32; c += EPI_WARPS / 4) {
     const int col = n_blk * BN + c * 32 + lcol;
     if (n_blk * BN + c * 32 >= p.N) break;  // warp-uniform: nothing left in this tile row-block
     {
@@ -214,7 +216,7 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stg + lane * EPI_LD + j * 4) =
+        *reinterpret_cast<float4*>(stg + epi_swz(lane, j)) =
             make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                         __uint_as_float(r[4 * j + 3]));
     }
@@ -230,7 +232,7 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
       const int rr = i * 4 + lrow;
       const int row = row_base + rr;
       if (row >= p.M || col >= p.N) continue;
-      const float4 s4 = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + lcol);
+      const float4 s4 = *reinterpret_cast<const float4*>(stg + epi_swz(rr, lane & 7));
       float v[4] = {s4.x + b4[0], s4.y + b4[1], s4.z + b4[2], s4.w + b4[3]};
       if (ep.relu) {
 #pragma unroll
@@ -272,16 +274,16 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
 
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* stg, uint32_t tmem_acc, int m_blk, int n_blk,
-                                              int quarter, int lane) {
+                                              int quarter, int half, int lane) {
   const uint32_t stg_s = smem_u32(stg);
   switch (p.flavour) {   // warp-uniform
-    case EPI_PLAIN:           epilogue_fast<BN, EPI_PLAIN>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, lane); break;
-    case EPI_ROUND:           epilogue_fast<BN, EPI_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, lane); break;
-    case EPI_AUX_ADD:         epilogue_fast<BN, EPI_AUX_ADD>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, lane); break;
-    case EPI_RELU_DROP_ROUND: epilogue_fast<BN, EPI_RELU_DROP_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, lane); break;
-    case EPI_AUX_MASK_ROUND:  epilogue_fast<BN, EPI_AUX_MASK_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, lane); break;
-    case EPI_ATOMIC:          epilogue_fast<BN, EPI_ATOMIC>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, lane); break;
-    default:                  epilogue_generic<BN>(p, stg, tmem_acc, m_blk, n_blk, quarter, lane); break;
+    case EPI_PLAIN:           epilogue_fast<BN, EPI_PLAIN>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
+    case EPI_ROUND:           epilogue_fast<BN, EPI_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
+    case EPI_AUX_ADD:         epilogue_fast<BN, EPI_AUX_ADD>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
+    case EPI_RELU_DROP_ROUND: epilogue_fast<BN, EPI_RELU_DROP_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
+    case EPI_AUX_MASK_ROUND:  epilogue_fast<BN, EPI_AUX_MASK_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
+    case EPI_ATOMIC:          epilogue_fast<BN, EPI_ATOMIC>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
+    default:                  epilogue_generic<BN>(p, stg, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
   }
 }
 
@@ -318,7 +320,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], EPI_WARPS * 32);
     }
     fence_mbar_init();
   }
@@ -424,19 +426,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = epi_smem + (warp - 2) * (32 * EPI_LD);
+    const int half = (warp - 2) >> 2;
+    float* stg = epi_smem + (warp - 2) * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       const int n_blk = tile % p.n_tiles;
       const int m_blk = ((tile / p.n_tiles) % m_units) * CL + crank;
-      if (p.flavour == EPI_AUX_ADD || p.flavour == EPI_AUX_MASK_ROUND) prefetch_aux_tile<BN>(p, m_blk, n_blk, quarter, lane);
+      if (p.flavour == EPI_AUX_ADD || p.flavour == EPI_AUX_MASK_ROUND) prefetch_aux_tile<BN>(p, m_blk, n_blk, quarter, half, lane);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN>(p, stg, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN, m_blk, n_blk, quarter,
-                        lane);
+                        half, lane);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -491,7 +494,7 @@ gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 256);   // 128 epilogue threads of each CTA
+      mbar_init(&tempty_bar[s], 2 * EPI_WARPS * 32);   // the epilogue threads of both CTAs
     }
     fence_mbar_init();
   }
@@ -578,19 +581,20 @@ gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5, both CTAs) =====================
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
     const int quarter = warp & 3;
-    float* stg = epi_smem + (warp - 2) * (32 * EPI_LD);
+    const int half = (warp - 2) >> 2;
+    float* stg = epi_smem + (warp - 2) * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       const int n_blk = tile % p.n_tiles;
       const int m_blk = ((tile / p.n_tiles) % m_units) * 2 + crank;
-      if (p.flavour == EPI_AUX_ADD || p.flavour == EPI_AUX_MASK_ROUND) prefetch_aux_tile<BN>(p, m_blk, n_blk, quarter, lane);
+      if (p.flavour == EPI_AUX_ADD || p.flavour == EPI_AUX_MASK_ROUND) prefetch_aux_tile<BN>(p, m_blk, n_blk, quarter, half, lane);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN>(p, stg, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN, m_blk, n_blk, quarter,
-                        lane);
+                        half, lane);
       tc_fence_before();
       mbar_arrive_cluster(&tempty_bar[acc], 0);   // the leader's MMA warp owns the accumulator hand-back barrier
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -296,6 +296,13 @@ class _MultiHeadAttention(torch.autograd.Function):
         dk_in = dq_in if same_qkv else torch.empty_like(kc)
         dv_in = dk_in if same_kv else torch.empty_like(vc)
         grads = [torch.empty_like(t) for t in params]
+        if params[0].shape == params[2].shape == params[4].shape == (d, d):
+            # dW / db of the three projections as slices of one packed buffer: st_mha_bwd then computes projections that
+            # share an input (self-attention: all three; cross-attention: k and v) with ONE wgrad GEMM / column sum
+            gw = torch.empty(3 * d, d, device=dev, dtype=torch.float32)
+            gb = torch.empty(3 * d, device=dev, dtype=torch.float32)
+            for i in range(3):
+                grads[2 * i], grads[2 * i + 1] = gw[i * d:(i + 1) * d], gb[i * d:(i + 1) * d]
         f = _lib.MhaArgs(B=B, Lq=Lq, Lk=Lk, H=H, d_model=d, dk=dk, q_in=_p(qc), k_in=_p(kc), v_in=_p(vc),
                          residual=_p(res), wq=_p(params[0]), bq=_p(params[1]), wk=_p(params[2]), bk=_p(params[3]),
                          wv=_p(params[4]), bv=_p(params[5]), wo=_p(params[6]), bo=_p(params[7]), ln_g=_p(params[8]),
