@@ -73,7 +73,7 @@ int st_softce_fwd_bwd(const float* logits, int64_t ld_logits, const float* q, co
                       cudaStream_t stream);
 
 /* ---- TF32 tensor-core linear algebra ------------------------------------------------------------
- * dst = round_to_tf32(src), 2-D strided copy (cols, lds, ldd multiples of 4).                   */
+ * dst = round_to_tf32(src), 2-D strided copy (vectorised when cols, lds, ldd are multiples of 4). */
 int st_round_tf32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, cudaStream_t stream);
 /* out[c] += sum_r x[r, c]                                                                        */
 int st_colsum_add(const float* x, int64_t ld, int64_t rows, int cols, float* out, cudaStream_t stream);
@@ -195,6 +195,66 @@ typedef struct {
   float* dw1; float* db1; float* dw2; float* db2; float* dln_g; float* dln_b;   /* OVERWRITTEN */
 } st_ffn_bwd_args;
 int st_ffn_bwd(const st_ffn_bwd_args* a /* host */, cudaStream_t stream);
+
+/* ---- callers either side of the path ------------------------------------------------
+ * Decoder input (Models.py:84-87, Embedding.py:21-29): out[i] = table[idx[i]] + pe[i mod pe_rows]
+ * (pe may be NULL).  idx are int64 token ids in [0, vocab).  round_tf32 rounds the result (it feeds a GEMM). */
+int st_embed_fwd(const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, float* out, int64_t n, int d,
+                 int vocab, int round_tf32, cudaStream_t stream);
+/* dtable[idx[i]] += dout[i] for idx[i] != padding_idx (nn.Embedding(padding_idx=PAD) semantics, Models.py:73);
+ * zero_first clears the (vocab, d) gradient table before accumulating.                                     */
+int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab, int64_t padding_idx,
+                 int zero_first, cudaStream_t stream);
+
+/* Encoder input front-end (Models.py:28-33,42-44):
+ *   out = LayerNorm(Dropout(ReLU(x W^T + b))) * gamma + beta + pe[frame index]
+ * x: (rows, in_dim) with rows = B*T and frame index = row mod T; in_dim a multiple of 4 (80 for fbank).
+ * pe: (>= T, d_model) sinusoid table or NULL.  saved / ws as for the other composites.                     */
+typedef struct {
+  int64_t rows; int T; int in_dim, d_model;
+  const float* x;
+  const float* w; const float* b;
+  const float* ln_g; const float* ln_b;
+  const float* pe;
+  float eps; float dropout_p; uint64_t seed;
+  int round_out;
+  float* out;
+  float* saved; int64_t saved_floats;
+  float* ws; int64_t ws_floats;
+} st_frontend_args;
+int64_t st_frontend_saved_floats(int64_t rows, int in_dim, int d_model);
+int64_t st_frontend_ws_floats(int64_t rows, int in_dim, int d_model);
+/* float offset inside `saved` of h = Dropout(ReLU(Linear(x))), shape (rows, d_model) — test hook (ReLU gate pattern) */
+int64_t st_frontend_hidden_offset(int64_t rows, int in_dim, int d_model);
+int st_frontend_fwd(const st_frontend_args* a /* host */, cudaStream_t stream);
+typedef struct {
+  st_frontend_args f;
+  const float* dout;
+  float* dx;                       /* may be NULL: acoustic features need no gradient */
+  float* dw; float* db; float* dln_g; float* dln_b;   /* OVERWRITTEN */
+} st_frontend_bwd_args;
+int st_frontend_bwd(const st_frontend_bwd_args* a /* host */, cudaStream_t stream);
+
+/* Plain linear layer y = x W^T (+ b) on the TF32 tensor cores — the vocabulary projection tgt_word_proj
+ * (Models.py:145,151).  out_dim may be any size (V = 4337); y has leading dimension ldy >= out_dim.
+ * Backward accepts dy with any leading dimension lddy >= out_dim; dx / dw / db may each be NULL.           */
+typedef struct {
+  int64_t rows; int in_dim, out_dim;
+  const float* x; int x_is_tf32;
+  const float* w; const float* b;
+  float* y; int64_t ldy;
+  float* saved; int64_t saved_floats;
+  float* ws; int64_t ws_floats;
+} st_linear_args;
+int64_t st_linear_saved_floats(int64_t rows, int in_dim, int out_dim, int x_is_tf32);
+int64_t st_linear_ws_floats(int64_t rows, int in_dim, int out_dim);
+int st_linear_fwd(const st_linear_args* a /* host */, cudaStream_t stream);
+typedef struct {
+  st_linear_args f;
+  const float* dy; int64_t lddy;
+  float* dx; float* dw; float* db;                    /* OVERWRITTEN */
+} st_linear_bwd_args;
+int st_linear_bwd(const st_linear_bwd_args* a /* host */, cudaStream_t stream);
 
 /* ---- flat-buffer optimizer step (train.py:45-46, Optim.py:9-14,36-45) --------------------------------
  * st_sumsq: *out += sum(x[i]^2) (caller zeroes `out`, a device float).

@@ -59,21 +59,41 @@ def init_params(cfg: dict, seed: int = 2018) -> dict:
     return {k: v.requires_grad_() for k, v in P.items()}
 
 
-def forward(P: dict, cfg: dict, inputs, in_len, targets, tgt_len):
+def forward(P: dict, cfg: dict, inputs, in_len, targets, tgt_len, gate_fn=None):
+    """`gate_fn(name, pre_activation) -> 0/1 gate or None` lets a test pin the active set of every ReLU (the
+    front-end's, "frontend", and each layer's FFN, "encoder.layer_stack.i" / "decoder.layer_stack.i") to the one a
+    reduced-precision forward used — gradients of a piecewise-linear function are only comparable for a fixed
+    active set (tests/helpers.relu_gate_from_cuda)."""
     d, H = cfg["d_model"], cfg["n_heads"]
     T, L = inputs.size(1), targets.size(1)
-    pe = sinusoid(max(T, L), d)
-    x = torch.relu(inputs @ P["encoder.input_proj.0.weight"].t() + P["encoder.input_proj.0.bias"])      # Models.py:28-33
+    dt = P["tgt_word_proj.weight"].dtype
+    pe = sinusoid(max(T, L), d).to(dt)
+    inputs = inputs.to(dt)
+
+    def relu(name, pre):
+        gate = gate_fn(name, pre) if gate_fn is not None else None
+        return torch.relu(pre) if gate is None else pre * gate.to(pre.dtype)
+
+    def ffn(name, x, prm):
+        gate = gate_fn(name, O.ffn_preactivation(x, prm)) if gate_fn is not None else None
+        return O.positionwise_ffn(x, prm, gate=gate)
+
+    x = relu("frontend", inputs @ P["encoder.input_proj.0.weight"].t() + P["encoder.input_proj.0.bias"])  # Models.py:28-33
     x = O.add_layer_norm(x, None, P["encoder.input_proj.3.weight"], P["encoder.input_proj.3.bias"]) + pe[:T]
     enc_mask = O.padding_info_mask(in_len, in_len).bool()                                                # Models.py:46
     sub = lambda pre: {k[len(pre):]: v for k, v in P.items() if k.startswith(pre)}
     for i in range(cfg["num_enc_layer"]):
-        x = O.encoder_layer(x, enc_mask, sub(f"encoder.layer_stack.{i}."), H)
+        name = f"encoder.layer_stack.{i}"
+        a, _ = O.multi_head_attention(x, x, x, enc_mask, sub(name + ".slf_attn."), H)                    # Layers.py:18-22
+        x = ffn(name, a, sub(name + ".pos_ffn."))
     y = P["decoder.tgt_word_emb.weight"][targets] + pe[:L]                                               # Models.py:84-87
     slf_mask = O.decoder_self_mask(tgt_len)                                                              # Models.py:89-94
     cross_mask = O.padding_info_mask(tgt_len, in_len).bool()                                             # Models.py:96-97
     for i in range(cfg["num_dec_layer"]):
-        y = O.decoder_layer(y, x, slf_mask, cross_mask, sub(f"decoder.layer_stack.{i}."), H)
+        name = f"decoder.layer_stack.{i}"
+        a, _ = O.multi_head_attention(y, y, y, slf_mask, sub(name + ".slf_attn."), H)                    # Layers.py:37-44
+        c, _ = O.multi_head_attention(a, x, x, cross_mask, sub(name + ".enc_attn."), H, residual="q")
+        y = ffn(name, c, sub(name + ".pos_ffn."))
     return y @ P["tgt_word_proj.weight"].t()                                                             # Models.py:151
 
 

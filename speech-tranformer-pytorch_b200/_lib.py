@@ -71,6 +71,29 @@ class FfnBwdArgs(C.Structure):
                 ("dln_g", C.c_void_p), ("dln_b", C.c_void_p)]
 
 
+class FrontendArgs(C.Structure):
+    _fields_ = [("rows", i64), ("T", C.c_int), ("in_dim", C.c_int), ("d_model", C.c_int),
+                ("x", C.c_void_p), ("w", C.c_void_p), ("b", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
+                ("pe", C.c_void_p), ("eps", C.c_float), ("dropout_p", C.c_float), ("seed", u64), ("round_out", C.c_int),
+                ("out", C.c_void_p), ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64)]
+
+
+class FrontendBwdArgs(C.Structure):
+    _fields_ = [("f", FrontendArgs), ("dout", C.c_void_p), ("dx", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p),
+                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p)]
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [("rows", i64), ("in_dim", C.c_int), ("out_dim", C.c_int), ("x", C.c_void_p), ("x_is_tf32", C.c_int),
+                ("w", C.c_void_p), ("b", C.c_void_p), ("y", C.c_void_p), ("ldy", i64),
+                ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64)]
+
+
+class LinearBwdArgs(C.Structure):
+    _fields_ = [("f", LinearArgs), ("dy", C.c_void_p), ("lddy", i64), ("dx", C.c_void_p), ("dw", C.c_void_p),
+                ("db", C.c_void_p)]
+
+
 class AdamArgs(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("n", i64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
@@ -113,6 +136,17 @@ SIGNATURES = {
     "st_ffn_hidden_offset": (i64, [i64, C.c_int, C.c_int, C.c_int]),
     "st_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), _S]),
     "st_ffn_bwd": (C.c_int, [C.POINTER(FfnBwdArgs), _S]),
+    "st_embed_fwd": (C.c_int, [_P, _P, _P, i64, _P, i64, C.c_int, C.c_int, C.c_int, _S]),
+    "st_embed_bwd": (C.c_int, [_P, _P, _P, i64, C.c_int, C.c_int, i64, C.c_int, _S]),
+    "st_frontend_saved_floats": (i64, [i64, C.c_int, C.c_int]),
+    "st_frontend_ws_floats": (i64, [i64, C.c_int, C.c_int]),
+    "st_frontend_hidden_offset": (i64, [i64, C.c_int, C.c_int]),
+    "st_frontend_fwd": (C.c_int, [C.POINTER(FrontendArgs), _S]),
+    "st_frontend_bwd": (C.c_int, [C.POINTER(FrontendBwdArgs), _S]),
+    "st_linear_saved_floats": (i64, [i64, C.c_int, C.c_int, C.c_int]),
+    "st_linear_ws_floats": (i64, [i64, C.c_int, C.c_int]),
+    "st_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _S]),
+    "st_linear_bwd": (C.c_int, [C.POINTER(LinearBwdArgs), _S]),
     "st_sumsq": (C.c_int, [_P, i64, _P, _S]),
     "st_adam_step": (C.c_int, [C.POINTER(AdamArgs), _S]),
 }

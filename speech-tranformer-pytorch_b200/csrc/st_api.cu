@@ -187,7 +187,7 @@ int st_profile_dump(const char* path) { return profile_dump(path); }
 int st_profile_classes(void) { return PROF_NUM; }
 const char* st_profile_class_name(int cls) {
   static const char* names[PROF_NUM] = {"gemm_tf32", "attn_fwd", "attn_bwd_dkv", "attn_bwd_dq", "attn_bwd_delta", "add_ln_fwd",
-                                        "add_ln_bwd", "round_tf32", "colsum", "lsce", "sumsq", "adam"};
+                                        "add_ln_bwd", "round_tf32", "colsum", "lsce", "sumsq", "adam", "embed"};
   return (cls >= 0 && cls < PROF_NUM) ? names[cls] : "?";
 }
 int st_profile_read(int cls, double* ms, double* work, int64_t* launches) {
@@ -539,6 +539,154 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   GemmEpilogue ex;
   ex.aux = dz; ex.ldaux = d; ex.aux_mode = 1;
   return gemm_tf32(s, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, M, d, f, ex);
+}
+
+
+// ------------------------------------------------------------------ decoder input: embedding + positional encoding
+int st_embed_fwd(const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, float* out, int64_t n, int d,
+                 int vocab, int round_tf32, cudaStream_t stream) {
+  return embed_fwd(stream, idx, table, pe, pe_rows, out, n, d, vocab, round_tf32);
+}
+int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab, int64_t padding_idx,
+                 int zero_first, cudaStream_t stream) {
+  return embed_bwd(stream, idx, dout, dtable, n, d, vocab, padding_idx, zero_first);
+}
+
+// ------------------------------------------------------------------ encoder input front-end (Models.py:28-33,42-44)
+namespace {
+struct FrontPlan { float *x_r, *w_r, *h, *mean, *rstd; };
+int plan_front(const st_frontend_args& a, FrontPlan& p) {
+  ST_REQUIRE(a.rows > 0 && a.rows < (1ll << 31) && a.in_dim > 0 && (a.in_dim & 3) == 0 && a.d_model > 0 && a.T > 0,
+             "st_frontend: bad shape (rows=%lld T=%d in_dim=%d must be a multiple of 4, d_model=%d)", (long long)a.rows, a.T,
+             a.in_dim, a.d_model);
+  Carver c(a.saved, a.saved_floats);
+  p.x_r = c.take(a.rows * a.in_dim);
+  p.w_r = c.take(static_cast<int64_t>(a.d_model) * a.in_dim);
+  p.h = c.take(a.rows * a.d_model);
+  p.mean = c.take(a.rows);
+  p.rstd = c.take(a.rows);
+  if (!c.ok()) {
+    set_error("st_frontend: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
+    return ST_ERR_WORKSPACE;
+  }
+  return ST_OK;
+}
+constexpr uint64_t kSeedMixFront = 0x2545F4914F6CDD1Dull;
+}  // namespace
+
+int64_t st_frontend_saved_floats(int64_t rows, int in_dim, int d_model) {
+  return pad64(rows * in_dim) + pad64(static_cast<int64_t>(d_model) * in_dim) + pad64(rows * d_model) + 2 * pad64(rows);
+}
+int64_t st_frontend_hidden_offset(int64_t rows, int in_dim, int d_model) {
+  return pad64(rows * in_dim) + pad64(static_cast<int64_t>(d_model) * in_dim);
+}
+int64_t st_frontend_ws_floats(int64_t rows, int in_dim, int d_model) { (void)in_dim; return pad64(rows * d_model) + 64; }
+
+int st_frontend_fwd(const st_frontend_args* ap, cudaStream_t s) {
+  ST_REQUIRE(ap != nullptr, "st_frontend_fwd: null args");
+  const st_frontend_args& a = *ap;
+  FrontPlan p;
+  ST_TRY(plan_front(a, p));
+  const int M = static_cast<int>(a.rows), d = a.d_model, k = a.in_dim;
+  ST_TRY(round_tf32_2d(s, a.x, k, p.x_r, k, M, k));
+  ST_TRY(round_tf32_2d(s, a.w, k, p.w_r, k, d, k));
+  // h = Dropout(ReLU(Linear(x)))                                          Models.py:28-31
+  GemmEpilogue e;
+  e.bias = a.b; e.relu = 1;
+  const DropoutCfg dc = make_dropout(a.dropout_p, a.seed ^ kSeedMixFront);
+  e.drop_thresh = dc.thresh; e.drop_scale = dc.scale; e.drop_seed = dc.seed;
+  ST_TRY(gemm_tf32(s, GEMM_NT, p.x_r, k, p.w_r, k, p.h, d, M, d, k, e));
+  // out = LayerNorm(h) + positional encoding of the frame index          Models.py:32,42-44
+  return add_ln_fwd(s, p.h, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out, DropoutCfg{},
+                    a.pe, a.T);
+}
+
+int st_frontend_bwd(const st_frontend_bwd_args* bp, cudaStream_t s) {
+  ST_REQUIRE(bp != nullptr, "st_frontend_bwd: null args");
+  const st_frontend_bwd_args& b = *bp;
+  const st_frontend_args& a = b.f;
+  FrontPlan p;
+  ST_TRY(plan_front(a, p));
+  const int M = static_cast<int>(a.rows), d = a.d_model, k = a.in_dim;
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= st_frontend_ws_floats(a.rows, k, d), "st_frontend_bwd: workspace too small");
+  Carver w(a.ws, a.ws_floats);
+  float* dz = w.take(a.rows * d);
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_g, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_b, 0, d * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(b.db, 0, d * sizeof(float), s));
+  // LayerNorm backward, then the gate of dropout(relu(.)) (h > 0 <=> kept and positive); db = column sums of the result
+  ST_TRY(add_ln_bwd(s, b.dout, p.h, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db, M, d, 1, DropoutCfg{}, p.h,
+                    make_dropout(a.dropout_p, 0).scale));
+  ST_TRY(wgrad(s, dz, d, p.x_r, k, b.dw, M, d, k));
+  if (b.dx) {
+    GemmEpilogue e;
+    ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.w_r, k, b.dx, k, M, k, d, e));
+  }
+  return ST_OK;
+}
+
+// ------------------------------------------------------------------ plain linear layer (vocabulary projection, Models.py:145,151)
+namespace {
+struct LinPlan { float *x_r, *w_r; };
+int plan_linear(const st_linear_args& a, LinPlan& p) {
+  ST_REQUIRE(a.rows > 0 && a.rows < (1ll << 31) && a.in_dim > 0 && (a.in_dim & 3) == 0 && a.out_dim > 0,
+             "st_linear: bad shape (rows=%lld in_dim=%d must be a multiple of 4, out_dim=%d)", (long long)a.rows, a.in_dim, a.out_dim);
+  Carver c(a.saved, a.saved_floats);
+  p.x_r = a.x_is_tf32 ? const_cast<float*>(a.x) : c.take(a.rows * a.in_dim);
+  p.w_r = c.take(static_cast<int64_t>(a.out_dim) * a.in_dim);
+  if (!c.ok()) {
+    set_error("st_linear: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
+    return ST_ERR_WORKSPACE;
+  }
+  return ST_OK;
+}
+int64_t pad4(int64_t n) { return (n + 3) & ~int64_t(3); }
+}  // namespace
+
+int64_t st_linear_saved_floats(int64_t rows, int in_dim, int out_dim, int x_is_tf32) {
+  return (x_is_tf32 ? 0 : pad64(rows * in_dim)) + pad64(static_cast<int64_t>(out_dim) * in_dim);
+}
+int64_t st_linear_ws_floats(int64_t rows, int in_dim, int out_dim) { (void)in_dim; return pad64(rows * pad4(out_dim)) + 64; }
+
+int st_linear_fwd(const st_linear_args* ap, cudaStream_t s) {
+  ST_REQUIRE(ap != nullptr, "st_linear_fwd: null args");
+  const st_linear_args& a = *ap;
+  LinPlan p;
+  ST_TRY(plan_linear(a, p));
+  ST_REQUIRE(a.ldy >= a.out_dim, "st_linear_fwd: ldy (%lld) < out_dim (%d)", (long long)a.ldy, a.out_dim);
+  const int M = static_cast<int>(a.rows), k = a.in_dim, n = a.out_dim;
+  if (!a.x_is_tf32) ST_TRY(round_tf32_2d(s, a.x, k, p.x_r, k, M, k));
+  ST_TRY(round_tf32_2d(s, a.w, k, p.w_r, k, n, k));
+  GemmEpilogue e;
+  e.bias = a.b;
+  return gemm_tf32(s, GEMM_NT, p.x_r, k, p.w_r, k, a.y, a.ldy, M, n, k, e);
+}
+
+int st_linear_bwd(const st_linear_bwd_args* bp, cudaStream_t s) {
+  ST_REQUIRE(bp != nullptr, "st_linear_bwd: null args");
+  const st_linear_bwd_args& b = *bp;
+  const st_linear_args& a = b.f;
+  LinPlan p;
+  ST_TRY(plan_linear(a, p));
+  const int M = static_cast<int>(a.rows), k = a.in_dim, n = a.out_dim;
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= st_linear_ws_floats(a.rows, k, n), "st_linear_bwd: workspace too small");
+  ST_REQUIRE(b.lddy >= n, "st_linear_bwd: lddy (%lld) < out_dim (%d)", (long long)b.lddy, n);
+  Carver w(a.ws, a.ws_floats);
+  const int64_t ldr = pad4(n);
+  float* dy_r = w.take(a.rows * ldr);
+  if (ldr != n)   // the ragged tail columns are read by float4 column sums: keep them finite
+    ST_CHECK_CUDA(cudaMemsetAsync(dy_r, 0, static_cast<size_t>(a.rows) * ldr * sizeof(float), s));
+  ST_TRY(round_tf32_2d(s, b.dy, b.lddy, dy_r, ldr, M, n));
+  if (b.dx) {
+    GemmEpilogue e;
+    ST_TRY(gemm_tf32(s, GEMM_NN, dy_r, ldr, p.w_r, k, b.dx, k, M, k, n, e));
+  }
+  if (b.dw) ST_TRY(wgrad(s, dy_r, ldr, p.x_r, k, b.dw, M, n, k));
+  if (b.db && a.b) {
+    ST_CHECK_CUDA(cudaMemsetAsync(b.db, 0, n * sizeof(float), s));
+    ST_TRY(colsum_add(s, dy_r, ldr, M, n, b.db));
+  }
+  return ST_OK;
 }
 
 }  // extern "C"

@@ -19,12 +19,18 @@ DropoutCfg make_dropout(float p, uint64_t seed);
 // ---- st_ln.cu
 int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float* gamma, const float* beta, float* out,
                float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
-               const DropoutCfg& drop);
+               const DropoutCfg& drop, const float* post = nullptr, int64_t post_rows = 0);
 int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd,
                const float* gamma, float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
-               int round_out, const DropoutCfg& drop);
+               int round_out, const DropoutCfg& drop, const float* gate = nullptr, float gate_scale = 1.f);
 int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols);
 int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, int cols, float* out);
+
+// ---- st_embed.cu
+int embed_fwd(cudaStream_t stream, const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, float* out,
+              int64_t n, int d, int vocab, int round_out);
+int embed_bwd(cudaStream_t stream, const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab,
+              int64_t padding_idx, int zero_first);
 
 // ---- st_optim.cu
 int sumsq_add(cudaStream_t s, const float* x, int64_t n, float* out);

@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(LN_THREADS)
 add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* __restrict__ out, float* __restrict__ z_out,
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int d, float eps,
-                  int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed) {
+                  int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
+                  const float* __restrict__ post, int64_t post_rows) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const float inv_d = 1.f / static_cast<float>(d);
@@ -87,6 +88,10 @@ add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
             o[t + 1] = dropout_keep(bits, 1, drop_thresh) ? o[t + 1] * drop_scale : 0.f;
           }
         }
+        if (post) {   // + positional encoding row (row mod post_rows), Models.py:42-44
+          const float4 pv = ld4(post + (row % post_rows) * d + c);
+          o[0] += pv.x; o[1] += pv.y; o[2] += pv.z; o[3] += pv.w;
+        }
         if (round_out) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) o[t] = tf32_rna(o[t]);
@@ -105,7 +110,8 @@ __global__ void __launch_bounds__(LN_THREADS)
 add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
                   const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dzsum, int64_t rows,
-                  int d, int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed) {
+                  int d, int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
+                  const float* __restrict__ gate, float gate_scale) {
   __shared__ float red[LN_WARPS][32 * 4 + 4];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -158,6 +164,11 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
       if (c < d) {
         float o[4] = {rstd * (gy[i].x - c1 - xh[i].x * c2), rstd * (gy[i].y - c1 - xh[i].y * c2),
                       rstd * (gy[i].z - c1 - xh[i].z * c2), rstd * (gy[i].w - c1 - xh[i].w * c2)};
+        if (gate) {   // gradient through dropout(relu(.)) whose output is `gate`: pass (scaled) where it was kept and positive
+          const float4 gv = ld4(gate + row * d + c);
+          o[0] = gv.x > 0.f ? o[0] * gate_scale : 0.f; o[1] = gv.y > 0.f ? o[1] * gate_scale : 0.f;
+          o[2] = gv.z > 0.f ? o[2] * gate_scale : 0.f; o[3] = gv.w > 0.f ? o[3] * gate_scale : 0.f;
+        }
         acc_z[i].x += o[0]; acc_z[i].y += o[1]; acc_z[i].z += o[2]; acc_z[i].w += o[3];
         if (round_out) {
 #pragma unroll
@@ -206,6 +217,19 @@ round_tf32_kernel(const float* __restrict__ src, int64_t lds, float* __restrict_
   }
 }
 
+// scalar variant for ragged widths / unaligned leading dimensions (vocabulary-sized logits gradients, V = 4337)
+__global__ void __launch_bounds__(256)
+round_tf32_scalar_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
+                         int cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    dst[r * ldd + c] = tf32_rna(src[r * lds + c]);
+  }
+}
+
 // ---------------------------------------------------------------- column sums: out[c] += sum_r X[r,c]
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
@@ -242,8 +266,9 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float* gamma, const float* beta, float* out,
                float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
-               const DropoutCfg& drop) {
+               const DropoutCfg& drop, const float* post, int64_t post_rows) {
   if (rows == 0) return ST_OK;
+  ST_REQUIRE(!post || (post_rows > 0 && aligned16(post)), "add_ln_fwd: post operand needs post_rows > 0 and 16-byte alignment");
   ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_fwd: d=%d must be a multiple of 4 and <= 1024", d);
   ST_REQUIRE(aligned16(a) && (!b || aligned16(b)) && aligned16(gamma) && aligned16(beta) && aligned16(out) &&
                  (!z_out || aligned16(z_out)),
@@ -252,7 +277,8 @@ int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float*
   ProfScope prof(stream, PROF_LN_FWD, (b ? 3.0 : 2.0) * rows * d * 4 + (z_out ? 1.0 * rows * d * 4 : 0.0));
 #define ST_LAUNCH(VPL)                                                                                            \
   add_ln_fwd_kernel<VPL><<<grid, LN_THREADS, 0, stream>>>(a, b, gamma, beta, out, z_out, mean_out, rstd_out, rows, \
-                                                          d, eps, round_out, drop.thresh, drop.scale, drop.seed)
+                                                          d, eps, round_out, drop.thresh, drop.scale, drop.seed, post, \
+                                                          post_rows)
   if (d <= 128) ST_LAUNCH(1);
   else if (d <= 256) ST_LAUNCH(2);
   else if (d <= 512) ST_LAUNCH(4);
@@ -264,15 +290,17 @@ int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float*
 
 int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd,
                const float* gamma, float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
-               int round_out, const DropoutCfg& drop) {
+               int round_out, const DropoutCfg& drop, const float* gate, float gate_scale) {
   if (rows == 0) return ST_OK;
+  ST_REQUIRE(!gate || aligned16(gate), "add_ln_bwd: gate must be 16-byte aligned");
   ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_bwd: d=%d must be a multiple of 4 and <= 1024", d);
   ST_REQUIRE(aligned16(dy) && aligned16(z) && aligned16(gamma) && aligned16(dz), "add_ln_bwd: pointers must be 16-byte aligned");
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 4);
   ProfScope prof(stream, PROF_LN_BWD, 3.0 * rows * d * 4);
 #define ST_LAUNCH(VPL)                                                                                         \
   add_ln_bwd_kernel<VPL><<<grid, LN_THREADS, 0, stream>>>(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum,  \
-                                                          rows, d, round_out, drop.thresh, drop.scale, drop.seed)
+                                                          rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, \
+                                                          gate_scale)
   if (d <= 128) ST_LAUNCH(1);
   else if (d <= 256) ST_LAUNCH(2);
   else if (d <= 512) ST_LAUNCH(4);
@@ -284,8 +312,15 @@ int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float
 
 int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols) {
   if (rows == 0 || cols == 0) return ST_OK;
-  ST_REQUIRE((cols & 3) == 0 && (lds & 3) == 0 && (ldd & 3) == 0 && aligned16(src) && aligned16(dst),
-             "round_tf32: cols/ld must be multiples of 4 and pointers 16-byte aligned (cols=%d)", cols);
+  ST_REQUIRE(lds >= cols && ldd >= cols, "round_tf32: leading dimensions (%lld, %lld) smaller than cols=%d",
+             (long long)lds, (long long)ldd, cols);
+  if (!((cols & 3) == 0 && (lds & 3) == 0 && (ldd & 3) == 0 && aligned16(src) && aligned16(dst))) {
+    const int64_t n = rows * cols;
+    ProfScope prof(stream, PROF_ROUND, 2.0 * rows * cols * 4);
+    round_tf32_scalar_kernel<<<persistent_grid((n + 255) / 256, 16), 256, 0, stream>>>(src, lds, dst, ldd, rows, cols);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+  }
   const int64_t total = rows * (cols / 4);
   const int grid = persistent_grid((total + 255) / 256, 16);
   ProfScope prof(stream, PROF_ROUND, 2.0 * rows * cols * 4);
@@ -296,7 +331,9 @@ int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst
 
 int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, int cols, float* out) {
   if (rows == 0 || cols == 0) return ST_OK;
-  ST_REQUIRE((cols & 3) == 0 && (ld & 3) == 0 && aligned16(x), "colsum: cols/ld must be multiples of 4 (cols=%d)", cols);
+  // float4 loads: a ragged width is fine as long as the (padded) row is long enough to read the last group
+  ST_REQUIRE((ld & 3) == 0 && ld >= ((cols + 3) & ~3) && aligned16(x),
+             "colsum: ld must be a multiple of 4 and >= cols rounded up to 4 (cols=%d ld=%lld)", cols, (long long)ld);
   dim3 grid((cols + 127) / 128, 1);
   int64_t ychunks = (rows + 63) / 64;
   const int64_t cap = (static_cast<int64_t>(num_sms()) * 8 + grid.x - 1) / grid.x;

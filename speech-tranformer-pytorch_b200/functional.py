@@ -7,6 +7,7 @@ tensors or a missing library raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -15,7 +16,8 @@ from . import _lib
 from ._lib import StError, check
 
 __all__ = ["add_layer_norm", "multi_head_attention", "positionwise_ffn", "label_smoothing_ce", "soft_target_ce",
-           "attention_core", "linear_tf32", "round_tf32", "is_tf32_clean", "mark_tf32_clean", "next_seed"]
+           "attention_core", "linear_tf32", "round_tf32", "is_tf32_clean", "mark_tf32_clean", "next_seed",
+           "frontend", "linear", "embedding", "GradSink", "attach_grad_sink"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -55,6 +57,11 @@ def _lib_for(t: torch.Tensor):
     return lib
 
 
+# Module outputs feed the next module's GEMMs.  True: the producing kernel rounds them to TF32 in its epilogue (no
+# extra pass; the residual stream then carries one 2^-11 rounding per module).  False: outputs stay exact fp32 and
+# every consumer makes its own rounded operand copy (one extra read+write of the activation per module).
+ROUND_OUT = os.environ.get("ST_ROUND_OUT", "1") != "0"
+
 _TF32_TAG = "_st_tf32_clean"
 
 
@@ -66,6 +73,52 @@ def is_tf32_clean(t: torch.Tensor) -> bool:
 def mark_tf32_clean(t: torch.Tensor) -> torch.Tensor:
     setattr(t, _TF32_TAG, True)
     return t
+
+
+class GradSink:
+    """Where a parameter's gradient lives in a trainer-owned flat buffer (parallel.FlatParams).
+
+    The composite backward kernels OVERWRITE their parameter gradients, so when every parameter of an operator
+    carries a sink they write straight into the flat gradient buffer and return None to autograd — no temporary, no
+    AccumulateGrad `+=` kernel (263 of them per step in the 6+6 model).  `written` guards weight sharing: a second
+    use of the same parameter within one step falls back to the ordinary accumulate path."""
+    __slots__ = ("view", "written")
+
+    def __init__(self, view: torch.Tensor):
+        self.view, self.written = view, False
+
+
+_SINK_ATTR = "_st_grad_sink"
+
+
+def attach_grad_sink(param: torch.Tensor, view: torch.Tensor) -> GradSink:
+    sink = GradSink(view)
+    setattr(param, _SINK_ATTR, sink)
+    return sink
+
+
+def _sinks_of(params):
+    """The params' sinks if ALL of them have an unwritten sink of the right shape, else None."""
+    out = []
+    for p in params:
+        if p is None:
+            out.append(None)
+            continue
+        s = getattr(p, _SINK_ATTR, None)
+        if s is None or s.written or s.view.shape != p.shape or not s.view.is_contiguous():
+            return None
+        out.append(s)
+    return out
+
+
+def _claim(sinks):
+    """Inside backward: take the sinks (None if any was written meanwhile) and mark them written."""
+    if sinks is None or any(s is not None and s.written for s in sinks):
+        return None
+    for s in sinks:
+        if s is not None:
+            s.written = True
+    return [None if s is None else s.view for s in sinks]
 
 
 _seed_state = [0]
@@ -272,6 +325,7 @@ class _MultiHeadAttention(torch.autograd.Function):
                          out=_p(out), attn=_p(attn), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
         check(lib.st_mha_fwd(C.byref(a), _stream()))
         ctx.save_for_backward(qc, kc, vc, mask_t, saved, *params)
+        ctx.sinks = _sinks_of((wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b))
         ctx.cfg = (B, Lq, Lk, n_head, d, dk, residual, float(eps), float(dropout_p), int(seed), inputs_tf32,
                    same_qk, same_kv)
         if attn is not None:
@@ -295,8 +349,9 @@ class _MultiHeadAttention(torch.autograd.Function):
         dq_in = torch.empty_like(qc)
         dk_in = dq_in if same_qkv else torch.empty_like(kc)
         dv_in = dk_in if same_kv else torch.empty_like(vc)
-        grads = [torch.empty_like(t) for t in params]
-        if params[0].shape == params[2].shape == params[4].shape == (d, d):
+        direct = _claim(ctx.sinks)
+        grads = direct if direct is not None else [torch.empty_like(t) for t in params]
+        if direct is None and params[0].shape == params[2].shape == params[4].shape == (d, d):
             # dW / db of the three projections as slices of one packed buffer: st_mha_bwd then computes projections that
             # share an input (self-attention: all three; cross-attention: k and v) with ONE wgrad GEMM / column sum
             gw = torch.empty(3 * d, d, device=dev, dtype=torch.float32)
@@ -318,6 +373,8 @@ class _MultiHeadAttention(torch.autograd.Function):
         gq, gk, gv = dq_in, (None if same_qkv else dk_in), (None if same_kv else dv_in)
         if same_qk and not same_kv:   # q is k but v differs: separate buffers were filled, combine them
             gq, gk = dq_in + dk_in, None
+        if direct is not None:        # parameter gradients already sit in the trainer's flat buffer
+            grads = [None] * len(params)
         return (gq, gk, gv, None, *grads, None, None, None, None, None, None, None)
 
 
@@ -353,6 +410,7 @@ class _PositionwiseFFN(torch.autograd.Function):
                          out=_p(out), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
         check(lib.st_ffn_fwd(C.byref(a), _stream()))
         ctx.save_for_backward(xc, saved, *params)
+        ctx.sinks = _sinks_of((w1, b1, w2, b2, ln_g, ln_b))
         ctx.cfg = (rows, d, d_ff, float(eps), float(dropout_p), int(seed), x_clean)
         if round_out:
             mark_tf32_clean(out)
@@ -370,7 +428,8 @@ class _PositionwiseFFN(torch.autograd.Function):
         n_ws = lib.st_ffn_ws_floats(rows, d, d_ff)
         ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
         dx = torch.empty_like(xc)
-        grads = [torch.empty_like(t) for t in params]
+        direct = _claim(ctx.sinks)
+        grads = direct if direct is not None else [torch.empty_like(t) for t in params]
         f = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(xc), w1=_p(params[0]), b1=_p(params[1]),
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=eps,
                          dropout_p=p, seed=seed, x_is_tf32=x_clean, round_out=0, out=None, saved=_p(saved),
@@ -378,6 +437,8 @@ class _PositionwiseFFN(torch.autograd.Function):
         a = _lib.FfnBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw1=_p(grads[0]), db1=_p(grads[1]), dw2=_p(grads[2]),
                             db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]))
         check(lib.st_ffn_bwd(C.byref(a), _stream()))
+        if direct is not None:
+            grads = [None] * len(params)
         return (dx, *grads, None, None, None, None)
 
 
@@ -398,27 +459,34 @@ def positionwise_ffn(x, w1, b1, w2, b2, ln_g, ln_b, eps: float = 1e-6, dropout_p
 class _LabelSmoothingCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target, one_hot, weight, confidence, padding_idx, size_average):
-        logits = _contig(_need(logits, "output"))
-        lib = _lib_for(logits)
+        logits = _need(logits, "output")
         if logits.dim() != 2:
             raise AssertionError("inputs.dim() == 2")            # Loss.py:51
         N, V = logits.shape
+        if not (logits.stride(1) == 1 and (N <= 1 or logits.stride(0) >= V)):   # row-padded views are read in place
+            logits = logits.contiguous()
+        lib = _lib_for(logits)
+        ldl = logits.stride(0) if N > 1 else max(V, 1)
+        ldg = (V + 3) // 4 * 4
         target = _contig(_need(target, "target", torch.int64))
         one_hot = _contig(_need(one_hot, "one_hot")).view(-1)
         weight = _contig(_need(weight, "weight")).view(-1)
         row_loss = torch.empty(max(N, 1), device=logits.device, dtype=torch.float32)
         loss = torch.empty((), device=logits.device, dtype=torch.float32)
-        grad = torch.empty_like(logits)
-        check(lib.st_lsce_fwd_bwd(_p(logits), V, _p(target), _p(one_hot), _p(weight), float(confidence),
-                                  int(padding_idx), int(bool(size_average)), N, V, _p(row_loss), _p(loss), _p(grad), V,
+        # gradient rows padded to a multiple of 4 floats: a consumer GEMM (st_linear_bwd) can read it in place
+        grad = torch.zeros(N, ldg, device=logits.device, dtype=torch.float32) if ldg != V else \
+            torch.empty(N, V, device=logits.device, dtype=torch.float32)
+        check(lib.st_lsce_fwd_bwd(_p(logits), ldl, _p(target), _p(one_hot), _p(weight), float(confidence),
+                                  int(padding_idx), int(bool(size_average)), N, V, _p(row_loss), _p(loss), _p(grad), ldg,
                                   _stream()))
         ctx.save_for_backward(grad)
+        ctx.V = V
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
         (grad,) = ctx.saved_tensors
-        return grad * dloss, None, None, None, None, None, None
+        return (grad * dloss)[:, :ctx.V], None, None, None, None, None, None
 
 
 def label_smoothing_ce(logits, target, one_hot, weight, confidence: float, padding_idx: int, size_average: bool = True):
@@ -449,3 +517,169 @@ class _SoftTargetCE(torch.autograd.Function):
 
 def soft_target_ce(logits, q, weight, size_average: bool = True):
     return _SoftTargetCE.apply(logits, q, weight, size_average)
+
+
+# ------------------------------------------------------------------------------------------------
+# callers either side of the path: encoder front-end, vocabulary projection, embedding
+# ------------------------------------------------------------------------------------------------
+class _Frontend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, ln_g, ln_b, pe, eps, dropout_p, seed, round_out):
+        xc = _contig(_need(x, "inputs"))
+        if xc.dim() != 3:
+            raise RuntimeError("frontend: inputs must be (batch, frames, feature_dim)")
+        lib = _lib_for(xc)
+        B, T, k = xc.shape
+        params = [_contig(_need(t, "parameter")) for t in (w, b, ln_g, ln_b)]
+        d = params[0].shape[0]
+        if params[0].shape != (d, k):
+            raise RuntimeError(f"frontend: weight {tuple(params[0].shape)} does not match feature_dim {k}")
+        if pe is not None:
+            pe = _contig(_need(pe, "pe"))
+            if pe.shape[-1] != d or pe.numel() // d < T:
+                raise RuntimeError(f"frontend: positional table {tuple(pe.shape)} too small for T={T}, d={d}")
+        rows = B * T
+        n_saved = lib.st_frontend_saved_floats(rows, k, d)
+        saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
+        out = torch.empty(B, T, d, device=xc.device, dtype=torch.float32)
+        a = _lib.FrontendArgs(rows=rows, T=T, in_dim=k, d_model=d, x=_p(xc), w=_p(params[0]), b=_p(params[1]),
+                              ln_g=_p(params[2]), ln_b=_p(params[3]), pe=_p(pe), eps=float(eps),
+                              dropout_p=float(dropout_p), seed=int(seed), round_out=int(round_out), out=_p(out),
+                              saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
+        check(lib.st_frontend_fwd(C.byref(a), _stream()))
+        ctx.save_for_backward(xc, saved, pe, *params)
+        ctx.sinks = _sinks_of((w, b, ln_g, ln_b))
+        ctx.cfg = (rows, T, k, d, float(eps), float(dropout_p), int(seed))
+        if round_out:
+            mark_tf32_clean(out)
+        off = lib.st_frontend_hidden_offset(rows, k, d)
+        hidden = saved[off:off + rows * d].view(B, T, d)
+        ctx.mark_non_differentiable(hidden)
+        return out, hidden
+
+    @staticmethod
+    def backward(ctx, dout, _dhidden):
+        xc, saved, pe, *params = ctx.saved_tensors
+        rows, T, k, d, eps, p, seed = ctx.cfg
+        lib = _lib_for(xc)
+        dout = _contig(dout)
+        n_ws = lib.st_frontend_ws_floats(rows, k, d)
+        ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        direct = _claim(ctx.sinks)
+        grads = direct if direct is not None else [torch.empty_like(t) for t in params]
+        f = _lib.FrontendArgs(rows=rows, T=T, in_dim=k, d_model=d, x=_p(xc), w=_p(params[0]), b=_p(params[1]),
+                              ln_g=_p(params[2]), ln_b=_p(params[3]), pe=_p(pe), eps=eps, dropout_p=p, seed=seed,
+                              round_out=0, out=None, saved=_p(saved), saved_floats=saved.numel(), ws=_p(ws),
+                              ws_floats=n_ws)
+        a = _lib.FrontendBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw=_p(grads[0]), db=_p(grads[1]), dln_g=_p(grads[2]),
+                                 dln_b=_p(grads[3]))
+        check(lib.st_frontend_bwd(C.byref(a), _stream()))
+        if direct is not None:
+            grads = [None] * 4
+        return (dx, *grads, None, None, None, None, None)
+
+
+def frontend(x, w, b, ln_g, ln_b, pe=None, eps: float = 1e-6, dropout_p: float = 0.0, seed: int = 0,
+             round_out: bool = None, return_hidden: bool = False):
+    """Encoder input front-end, Models.py:28-33,42-44: LayerNorm(Dropout(ReLU(Linear(x)))) + pe[:T] as one operator.
+    return_hidden additionally returns Dropout(ReLU(Linear(x))) (non-differentiable test hook, cf. positionwise_ffn)."""
+    out, hidden = _Frontend.apply(x, w, b, ln_g, ln_b, pe, eps, dropout_p, seed, ROUND_OUT if round_out is None else round_out)
+    return (out, hidden) if return_hidden else out
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x_clean = int(is_tf32_clean(x))
+        xc = _contig(_need(x, "input"))
+        lib = _lib_for(xc)
+        k = xc.shape[-1]
+        rows = xc.numel() // k
+        wc = _contig(_need(w, "weight"))
+        bc = None if b is None else _contig(_need(b, "bias"))
+        n = wc.shape[0]
+        if wc.shape != (n, k):
+            raise RuntimeError(f"linear: weight {tuple(wc.shape)} does not match input features {k}")
+        ldy = (n + 3) // 4 * 4
+        n_saved = lib.st_linear_saved_floats(rows, k, n, x_clean)
+        saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
+        y = torch.empty(rows, ldy, device=xc.device, dtype=torch.float32)
+        a = _lib.LinearArgs(rows=rows, in_dim=k, out_dim=n, x=_p(xc), x_is_tf32=x_clean, w=_p(wc), b=_p(bc), y=_p(y),
+                            ldy=ldy, saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
+        check(lib.st_linear_fwd(C.byref(a), _stream()))
+        ctx.save_for_backward(xc, saved, wc, bc)
+        ctx.sinks = _sinks_of((w, b)) if b is not None else _sinks_of((w,))
+        ctx.cfg = (rows, k, n, x_clean)
+        return y[:, :n].view(*xc.shape[:-1], n)        # a row-padded view when n % 4 != 0 (V = 4337)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, saved, wc, bc = ctx.saved_tensors
+        rows, k, n, x_clean = ctx.cfg
+        lib = _lib_for(xc)
+        dy2 = dy.reshape(rows, n)
+        if dy2.stride(1) != 1 or (rows > 1 and dy2.stride(0) < n):
+            dy2 = dy2.contiguous()
+        lddy = dy2.stride(0) if rows > 1 else n
+        n_ws = lib.st_linear_ws_floats(rows, k, n)
+        ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        direct = _claim(ctx.sinks)
+        if direct is not None:
+            dw, db = direct[0], (direct[1] if bc is not None else None)
+        else:
+            dw = torch.empty_like(wc) if ctx.needs_input_grad[1] else None
+            db = torch.empty_like(bc) if (bc is not None and ctx.needs_input_grad[2]) else None
+        f = _lib.LinearArgs(rows=rows, in_dim=k, out_dim=n, x=_p(xc), x_is_tf32=x_clean, w=_p(wc), b=_p(bc), y=None, ldy=n,
+                            saved=_p(saved), saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws)
+        a = _lib.LinearBwdArgs(f=f, dy=_p(dy2), lddy=lddy, dx=_p(dx), dw=_p(dw), db=_p(db))
+        check(lib.st_linear_bwd(C.byref(a), _stream()))
+        if direct is not None:
+            dw = db = None
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """y = x @ weight.T + bias (nn.Linear, e.g. tgt_word_proj Models.py:145,151) on the tcgen05 TF32 GEMM, with autograd."""
+    return _Linear.apply(x, weight, bias)
+
+
+class _Embedding(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, table, pe, padding_idx, round_out):
+        idx = _contig(_need(idx, "indices", torch.int64))
+        table = _contig(_need(table, "embedding weight"))
+        lib = _lib_for(table)
+        vocab, d = table.shape
+        if idx.dim() != 2:
+            raise RuntimeError("embedding: indices must be (batch, length)")
+        B, L = idx.shape
+        if pe is not None:
+            pe = _contig(_need(pe, "pe"))
+            if pe.shape[-1] != d or pe.numel() // d < L:
+                raise RuntimeError(f"embedding: positional table {tuple(pe.shape)} too small for L={L}, d={d}")
+        out = torch.empty(B, L, d, device=table.device, dtype=torch.float32)
+        check(lib.st_embed_fwd(_p(idx), _p(table), _p(pe), L, _p(out), B * L, d, vocab, int(round_out), _stream()))
+        ctx.save_for_backward(idx)
+        ctx.sinks = _sinks_of((table,))
+        ctx.cfg = (vocab, d, int(padding_idx))
+        if round_out:
+            mark_tf32_clean(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        vocab, d, padding_idx = ctx.cfg
+        dout = _contig(dout)
+        lib = _lib_for(dout)
+        direct = _claim(ctx.sinks)
+        dtable = direct[0] if direct is not None else torch.empty(vocab, d, device=dout.device, dtype=torch.float32)
+        check(lib.st_embed_bwd(_p(idx), _p(dout), _p(dtable), idx.numel(), d, vocab, padding_idx, 1, _stream()))
+        return None, (None if direct is not None else dtable), None, None, None
+
+
+def embedding(idx, table, pe=None, padding_idx: int = -1, round_out: bool = None):
+    """table[idx] + pe[:L] (Models.py:84-87); the padding row receives no gradient (nn.Embedding padding_idx)."""
+    return _Embedding.apply(idx, table, pe, padding_idx, ROUND_OUT if round_out is None else round_out)

@@ -8,14 +8,17 @@ the query) because the file as written raises on every call.
 
 Masks are built on the device from the length vectors (no numpy loop, no per-step H2D copy, no `.item()`
 sync — cf. Utils.py:41-70, Embedding.py:22); the key-padding mask stays a stride-0 broadcast view.
-The input front-end, the embedding and the vocabulary projection are plain PyTorch for now (SURVEY.md §8f
-ranks them "next"); every attention / FFN / LayerNorm-residual / loss op is from libst_b200.so.
+The input front-end (Linear -> ReLU -> Dropout -> LayerNorm + positional encoding), the target embedding and the
+vocabulary projection run on libst_b200.so as well (st_frontend_*, st_embed_*, st_linear_*), so a
+training step launches no PyTorch compute kernel between the batch and the loss; the sub-modules stay ordinary
+nn.Linear / nn.LayerNorm / nn.Embedding parameter holders with the reference's names.
 """
 import math
 
 import torch
 import torch.nn as nn
 
+from . import functional as F
 from .transformer.Attention import MultiHeadAttention
 from .transformer.SubLayers import PositionwiseFeedForward
 
@@ -95,7 +98,12 @@ class Encoder(nn.Module):
 
     def forward(self, inputs, inputs_length, return_attns=False):
         T = inputs.size(1)
-        enc_output = self.input_proj(inputs) + self.position_enc(T)                 # Models.py:42-44
+        lin, drop, ln = self.input_proj[0], self.input_proj[2], self.input_proj[3]
+        p = drop.p if self.training else 0.0
+        enc_output, hidden = F.frontend(inputs, lin.weight, lin.bias, ln.weight, ln.bias, self.position_enc(T)[0],
+                                        eps=ln.eps, dropout_p=p, seed=F.next_seed() if p > 0 else 0,
+                                        return_hidden=True)                           # Models.py:28-33,42-44
+        self.last_hidden = hidden if getattr(self, "keep_hidden", False) else None    # test hook (ReLU gate pattern)
         mask = key_padding_mask(inputs_length, T, T)                                # Models.py:46
         attns = []
         for layer in self.layer_stack:
@@ -122,7 +130,8 @@ class Decoder(nn.Module):
     def forward(self, outputs_data, outputs_pos, input_pos, enc_output, return_attns=False):
         B, L = outputs_data.shape
         T = enc_output.size(1)
-        dec_output = self.tgt_word_emb(outputs_data) + self.position_enc(L)          # Models.py:84-87 (as intended)
+        dec_output = F.embedding(outputs_data, self.tgt_word_emb.weight, self.position_enc(L)[0],
+                                 padding_idx=PAD)                                     # Models.py:84-87 (as intended)
         slf_mask = key_padding_mask(outputs_pos, L, L) | subsequent_mask(B, L, outputs_data.device)   # :89-94
         enc_mask = key_padding_mask(input_pos, L, T)                                 # :96-97
         slf_attns, enc_attns = [], []
@@ -153,7 +162,8 @@ class Transformer(nn.Module):
         enc_output, enc_slf_attn = self.encoder(inputs, inputs_pos, self.return_attns)
         dec_output, dec_slf_attn, dec_enc_attn = self.decoder(targets, targets_pos, inputs_pos, enc_output,
                                                               self.return_attns)
-        return self.tgt_word_proj(dec_output), (enc_slf_attn, dec_slf_attn, dec_enc_attn)
+        logits = F.linear(dec_output, self.tgt_word_proj.weight, self.tgt_word_proj.bias)     # Models.py:151
+        return logits, (enc_slf_attn, dec_slf_attn, dec_enc_attn)
 
 
 class ModelConfig(dict):

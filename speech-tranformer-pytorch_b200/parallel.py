@@ -26,8 +26,31 @@ def noam_lr(d_model: int, n_warmup_steps: int, step: int) -> float:
     return d_model ** -0.5 * min(step ** -0.5, step * n_warmup_steps ** -1.5)
 
 
+def ordered_parameters(module: torch.nn.Module) -> List[torch.nn.Parameter]:
+    """The module's parameters in the order the flat buffer stores them: registration order, except that each
+    MultiHeadAttention keeps [Wq; Wk; Wv] and [bq; bk; bv] adjacent so that st_mha_bwd can produce the packed
+    projection gradients with ONE weight-gradient GEMM / column sum directly inside the flat gradient buffer."""
+    seen, out = set(), []
+
+    def add(p):
+        if p is not None and id(p) not in seen:
+            seen.add(id(p))
+            out.append(p)
+
+    for m in module.modules():
+        if all(hasattr(m, n) for n in ("linear_q", "linear_k", "linear_v", "output_linear", "layernorm")):
+            for p in (m.linear_q.weight, m.linear_k.weight, m.linear_v.weight, m.linear_q.bias, m.linear_k.bias,
+                      m.linear_v.bias):
+                add(p)
+        for p in m.parameters(recurse=False):
+            add(p)
+    return out
+
+
 class FlatParams:
-    """Re-homes a module's parameters into one flat buffer (and their .grad into another)."""
+    """Re-homes a module's parameters into one flat buffer (and their .grad into another).  Every parameter gets a
+    GradSink (functional.attach_grad_sink) pointing at its slice of the gradient buffer: the composite backward
+    operators write parameter gradients there directly instead of going through autograd's accumulation."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -48,12 +71,16 @@ class FlatParams:
                 self.flat[o:o + p.numel()].copy_(p.reshape(-1))
                 p.data = self.flat[o:o + p.numel()].view_as(p)
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
+        from .functional import attach_grad_sink
+        self.sinks = [attach_grad_sink(p, p.grad) for p in self.params]
 
     def zero_grad(self) -> None:
-        self.grad.zero_()
-        for p, o in zip(self.params, self.offsets):      # autograd accumulates in place into these views
+        self.grad.zero_()                                # one memset; direct writers overwrite, autograd accumulates
+        for p, o, s in zip(self.params, self.offsets, self.sinks):
+            s.written = False
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
+                s.view = p.grad
 
 
 class DataParallelTrainer:
@@ -62,7 +89,7 @@ class DataParallelTrainer:
     def __init__(self, module: torch.nn.Module, d_model: int, n_warmup_steps: int = 12000, max_grad_norm: float = 5.0,
                  betas=(0.9, 0.98), eps: float = 1e-9, process_group=None):
         self.module = module
-        self.fp = FlatParams(module.parameters())
+        self.fp = FlatParams(ordered_parameters(module))
         self.exp_avg = torch.zeros_like(self.fp.flat)
         self.exp_avg_sq = torch.zeros_like(self.fp.flat)
         self.norm_ws = torch.zeros(1, device=self.fp.flat.device, dtype=torch.float32)

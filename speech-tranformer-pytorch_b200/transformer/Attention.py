@@ -77,5 +77,5 @@ class MultiHeadAttention(nn.Module):
             self.linear_v.weight, self.linear_v.bias, self.output_linear.weight, self.output_linear.bias,
             self.layernorm.weight, self.layernorm.bias,
             n_head=self.n_head, residual=self.residual, eps=self.layernorm.eps, dropout_p=p,
-            seed=F.next_seed() if p > 0 else 0, need_attn=self.return_attention, round_out=True)
+            seed=F.next_seed() if p > 0 else 0, need_attn=self.return_attention, round_out=F.ROUND_OUT)
         return out, attns

@@ -30,7 +30,7 @@ class PositionwiseFeedForward(nn.Module):
         p = self.dropout1.p if self.training else 0.0
         out, hidden = F.positionwise_ffn(inputs, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
                                          self.layernorm.weight, self.layernorm.bias, eps=self.layernorm.eps,
-                                         dropout_p=p, seed=F.next_seed() if p > 0 else 0, round_out=True,
+                                         dropout_p=p, seed=F.next_seed() if p > 0 else 0, round_out=F.ROUND_OUT,
                                          return_hidden=True)
         self.last_hidden = hidden if self.keep_hidden else None
         return out

@@ -138,3 +138,29 @@ def test_synthetic_batch_layout():
         n = int(tl[b])
         assert tgt[b, 0] == O.BOS and torch.all(tgt[b, n:] == O.PAD) and gt[b, n - 1] == O.BOS
         assert torch.equal(tgt[b, 1:n], gt[b, :n - 1])
+
+
+# ------------------------------------------------------------------------------------------------ whole model
+def test_model_port_matches_reference_model():
+    """oracle/model_port.py (front-end, embedding, layer stacks, vocabulary projection, loss) against the
+    reference's own Transformer run by oracle/make_golden_model.py (eval mode, ragged batch): logits, loss and
+    every parameter gradient."""
+    from oracle import model_port
+    g = golden("transformer_small")
+    cfg = dict(d_model=64, n_heads=2, num_enc_layer=2, num_dec_layer=2, vocab_size=31)
+    P = {k[2:]: t(v).clone().requires_grad_() for k, v in g.items() if k.startswith("p.") and not k.endswith(".pe")}
+    inputs, targets = t(g["inputs"]), t(g["targets"])
+    in_len, tgt_len, truth = t(g["in_len"]), t(g["tgt_len"]), t(g["truth"])
+    logits = model_port.forward(P, cfg, inputs, in_len, targets, tgt_len)
+    V = 31
+    loss = O.label_smoothing_loss(logits.reshape(-1, V), truth.reshape(-1), O.smoothing_one_hot(0.1, V, 0), torch.ones(V),
+                                  0.1, 0, True)
+    loss.backward()
+    assert relerr(logits, g["logits"]) < 2e-5
+    assert abs(float(loss) - float(g["loss"])) < 2e-5 * abs(float(g["loss"]))
+    scale = max(np.abs(v).max() for k, v in g.items() if k.startswith("g."))
+    for k, v in g.items():
+        if k.startswith("g."):
+            got = P[k[2:]].grad
+            assert got is not None, k
+            assert (got.numpy() - v).__abs__().max() / scale < 2e-5, k
