@@ -320,6 +320,47 @@ def main_b200(args):
                         "note": "achieved = algorithmic 2MNK FLOPs / CUDA-event time over every GEMM launch of the profiled "
                                 "steps; TF32 runs at half the bf16 MMA rate, so frac against the bf16 peak is capped at 0.5"}
 
+    # ---- the fused EncoderLayer alone (north_star: tensor-pipe utilisation of EncoderLayer fwd+bwd at B=32,T=1000,d=512,h=8)
+    enc_layer = None
+    if rank == 0 and not args.no_roofline:
+        layer = net.encoder.layer_stack[0]
+        lx = torch.randn(args.batch, args.frames, d, device=dev)
+        lg = torch.randn(args.batch, args.frames, d, device=dev)
+        lmask = smodel.key_padding_mask(resident[2], args.frames, args.frames)
+        lparams = [q for q in layer.parameters()]
+
+        def layer_step():
+            for q in lparams:
+                q.grad = None
+            xin = lx.detach().requires_grad_()
+            y, _ = layer(xin, slf_attn_mask=lmask)
+            y.backward(lg)
+
+        for _ in range(3):
+            layer_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            layer_step()
+        e1.record()
+        torch.cuda.synchronize()
+        lms = e0.elapsed_time(e1) / reps
+        N_tok, T_, h_, dk_, dff_ = args.batch * args.frames, args.frames, 8, 64, 2048
+        flops = 3.0 * (8.0 * N_tok * d * d + 4.0 * args.batch * h_ * T_ * T_ * dk_ + 4.0 * N_tok * d * dff_)
+        tf = flops / (lms * 1e-3) / 1e12
+        enc_layer = {"ms_fwd_bwd": lms, "algorithmic_gflop": flops / 1e9, "tflops": tf,
+                     "frames_per_s": N_tok / (lms * 1e-3),
+                     "frac_of_tf32_peak_measured": tf / tf32_peak if tf32_peak else None,
+                     "frac_of_bf16_peak": tf / peak,
+                     "note": "one EncoderLayer (MHA + FFN, train mode, dropout 0.1) forward + backward, B x T x 512 resident in HBM; "
+                             "FLOPs = 3 x (8Nd^2 + 4BhT^2dk + 4Nd*dff), no recompute counted; the path computes in TF32, "
+                             "whose tensor-pipe rate is half the bf16 rate"}
+        for q in lparams:
+            q.grad = None
+        trainer.zero_grad()
+
     cpu = None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
         try:
@@ -333,7 +374,7 @@ def main_b200(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic", "config": workload_config(args, n),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "kernel_breakdown": breakdown, "cpu_baseline": cpu}
+                "kernel_breakdown": breakdown, "encoder_layer": enc_layer, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -42,6 +42,11 @@ int st_profile_dump(const char* path /* host */);   /* CSV of every recorded lau
 int st_profile_classes(void);
 const char* st_profile_class_name(int cls);
 int st_profile_read(int cls, double* ms /* host */, double* work /* host */, int64_t* launches /* host */);
+/* debug: clock64() timeline of one CTA of the attention dK/dV kernel (option "attn_trace"); returns the slot count */
+int st_debug_read_trace(uint64_t* host_out /* host */, int n);
+/* debug: cycles per tcgen05.mma (M=128, N=n, K=8, kind::tf32) issued back to back by one CTA.
+ * variant bit 0: A operand from TMEM (.ts) instead of shared memory; bit 1: B operand MN-major instead of K-major. */
+int st_debug_mma_bench(int variant, int n, int iters, double* clk_per_mma /* host */);
 int st_selftest_count(void);
 int st_selftest(int which, double* rel_err_out /* host */); /* tcgen05 building-block self tests */
 

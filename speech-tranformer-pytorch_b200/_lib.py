@@ -116,6 +116,8 @@ SIGNATURES = {
     "st_profile_classes": (C.c_int, []),
     "st_profile_class_name": (C.c_char_p, [C.c_int]),
     "st_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
+    "st_debug_read_trace": (C.c_int, [C.POINTER(u64), C.c_int]),
+    "st_debug_mma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "st_selftest_count": (C.c_int, []),
     "st_selftest": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "st_add_ln_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, i64, C.c_int, C.c_float, C.c_int, C.c_float, u64, _S]),

@@ -12,6 +12,7 @@
 #include "st_gemm.cuh"
 #include "st_host.h"
 #include "st_kernels.h"
+#include "st_attn.cuh"
 
 namespace st {
 
@@ -34,6 +35,7 @@ DropoutCfg make_dropout(float p, uint64_t seed) {
 }
 
 int selftest(int which, double* err);
+int mma_bench(int variant, int n, int iters, double* clk_per_mma);
 int selftest_count();
 
 namespace {
@@ -196,6 +198,8 @@ int st_profile_read(int cls, double* ms, double* work, int64_t* launches) {
   *launches = n;
   return st;
 }
+int st_debug_read_trace(uint64_t* host_out, int n) { return attn_read_trace(reinterpret_cast<unsigned long long*>(host_out), n); }
+int st_debug_mma_bench(int variant, int n, int iters, double* clk_per_mma) { return mma_bench(variant, n, iters, clk_per_mma); }
 int st_selftest_count(void) { return selftest_count(); }
 int st_selftest(int which, double* rel_err_out) { return selftest(which, rel_err_out); }
 

@@ -63,7 +63,7 @@ __device__ __forceinline__ float chunk_probs_t(uint32_t (&r)[32], uint32_t mb, f
       if (MASK && ((mb >> (i + t)) & 1u)) pv = 0.f;
       l += pv;
       if (DROP && !dropout_keep_xor(rowkey, cks[t], thresh)) pv = 0.f;
-      r[i + t] = __float_as_uint(tf32_rna(pv));
+      r[i + t] = tf32_rna_mma_bits(pv);
     }
   }
   return l;
@@ -95,7 +95,7 @@ __device__ __forceinline__ void chunk_ds_t(const uint32_t (&rs)[32], uint32_t (&
       if (MASK && ((mb >> (i + t)) & 1u)) pr = 0.f;
       float dp = __uint_as_float(rd[i + t]);
       if (DROP && !dropout_keep_xor(rowkey, cks[t], thresh)) dp = 0.f;
-      rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -delta)));
+      rd[i + t] = tf32_rna_mma_bits(pr * fmaf(dp, dscale, -delta));
     }
   }
 }
@@ -138,8 +138,8 @@ __device__ __forceinline__ void chunk_dkv_t(uint32_t (&rs)[32], uint32_t (&rd)[3
       float dp = __uint_as_float(rd[i + t]);
       float pd = pr;
       if (DROP && !dropout_keep_xor(rks[t], my_ckey, thresh)) { pd = 0.f; dp = 0.f; }
-      rs[i + t] = __float_as_uint(tf32_rna(pd));
-      rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -dels[t])));
+      rs[i + t] = tf32_rna_mma_bits(pd);
+      rd[i + t] = tf32_rna_mma_bits(pr * fmaf(dp, dscale, -dels[t]));
     }
   }
 }
@@ -207,23 +207,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   };
   auto issue_s = [&]() {  // S = Q K^T  (both K-major)
     constexpr uint32_t idesc = umma_idesc_tf32(128, BKV, false, false);
-    const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK);
+    const uint64_t aq0 = umma_desc_kmajor(smem_u32(sQ)), bk0 = umma_desc_kmajor(smem_u32(sK));
 #pragma unroll
     for (int ks = 0; ks < DK / 8; ++ks)
-      umma_tf32_ss(tmem + T_S, umma_desc_kmajor(aq + (ks / 4) * (BQ * 128) + (ks % 4) * 32),
-                   umma_desc_kmajor(bk + (ks / 4) * (BKV * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+      umma_tf32_ss(tmem + T_S, aq0 + static_cast<uint64_t>(((ks / 4) * (BQ * 128) + (ks % 4) * 32) >> 4),
+                   bk0 + static_cast<uint64_t>(((ks / 4) * (BKV * 128) + (ks % 4) * 32) >> 4), idesc, ks > 0 ? 1u : 0u);
     umma_commit(&bar_s);
   };
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bar_q, Q_BYTES);
-    tma_load_4d(sQ, &tmap_q, &bar_q, 0, q0, h * G, b);
-    load_k(0);
-    load_v(0);
+  // tcgen05.mma / TMA are issued by ONE lane of a CONVERGED warp 0, chosen with elect.sync: under a plain `tid == 0`
+  // branch the compiler wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop (60-120 cycles each, tools/mma_bench.py).
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_q, Q_BYTES);
+      tma_load_4d(sQ, &tmap_q, &bar_q, 0, q0, h * G, b);
+      load_k(0);
+      load_v(0);
+    }
+    __syncwarp();
     mbar_wait(&bar_q, 0);
     mbar_wait(&bar_k, 0);
     tc_fence_after();
-    issue_s();
+    if (elect_one()) issue_s();
+    __syncwarp();
   }
   k_loads = 1;
 
@@ -278,25 +284,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tc_fence_before();
     __syncthreads();
 
-    if (tid == 0) {  // O_tile = P V   (A = P in TMEM, B = V MN-major)
+    if (warp == 0) {  // O_tile = P V   (A = P in TMEM, B = V MN-major)
       tc_fence_after();
       mbar_wait(&bar_v, j & 1);
       tc_fence_after();
-      constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
-      const uint32_t bv = smem_u32(sV);
+      if (elect_one()) {
+        constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+        const uint64_t bv0 = umma_desc_mnmajor(smem_u32(sV), BKV * 128);
 #pragma unroll
-      for (int ks = 0; ks < BKV / 8; ++ks)
-        umma_tf32_ts(tmem + T_O, tmem + T_S + ks * 8, umma_desc_mnmajor(bv + ks * 1024, BKV * 128), idesc,
-                     ks > 0 ? 1u : 0u);
-      umma_commit(&bar_o);
+        for (int ks = 0; ks < BKV / 8; ++ks)
+          umma_tf32_ts(tmem + T_O, tmem + T_S + ks * 8, bv0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(&bar_o);
+      }
+      __syncwarp();
     }
     mbar_wait(&bar_o, j & 1);
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {
-      load_v(j + 1);                       // P·V has consumed V_j
+    if (warp == 0 && j + 1 < n_kv) {
+      if (elect_one()) load_v(j + 1);      // P·V has consumed V_j
+      __syncwarp();
       mbar_wait(&bar_k, k_loads & 1);      // K_{j+1}
       tc_fence_after();
-      issue_s();                           // overlaps the O accumulation below
+      if (elect_one()) issue_s();          // overlaps the O accumulation below
+      __syncwarp();
     }
     if (j + 1 < n_kv) ++k_loads;
     // ---- O += alpha-corrected accumulate in registers (this thread's half of the head dim)
@@ -339,12 +349,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int j = 0; j < n_kv; ++j) {
       tc_fence_before();
       __syncthreads();  // every thread is done with the S region / previous sweep step
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
-        load_k(j);
+        if (elect_one()) load_k(j);
+        __syncwarp();
         mbar_wait(&bar_k, k_loads & 1);
         tc_fence_after();
-        issue_s();
+        if (elect_one()) issue_s();
+        __syncwarp();
       }
       ++k_loads;
       mbar_wait(&bar_s, s_count & 1);
@@ -775,6 +787,7 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
   const AttnArgs& f = a.f;
   const int cols = f.H * DK;
   AttnDev p = attn_to_dev(f);
+  p.trace = get_option("attn_trace");
   p.delta = a.delta; p.dq = a.dq; p.lddq = a.lddq; p.dk = a.dk_; p.lddk = a.lddk; p.dv = a.dv; p.lddv = a.lddv;
   {
     const int64_t rows = static_cast<int64_t>(f.B) * f.Lq;

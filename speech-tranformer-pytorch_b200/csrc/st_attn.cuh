@@ -26,6 +26,7 @@ struct AttnDev {
   float* dq; int64_t lddq;
   float* dk; int64_t lddk;
   float* dv; int64_t lddv;
+  int trace;          // debug: record the pipeline timeline of CTA (0,0,0) (option "attn_trace")
 };
 
 // bit i set <=> (query row, key k0+i) is masked.  Keys beyond Lk are always masked.
@@ -59,5 +60,6 @@ AttnDev attn_to_dev(const AttnArgs& a);
 
 // st_attn_bwd.cu: pipelined dQ and dK/dV kernels for d_k in {32, 64}; p already carries the backward pointers
 int attn_bwd_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p);
+int attn_read_trace(unsigned long long* host_out, int n);   // returns the number of slots
 
 }  // namespace st

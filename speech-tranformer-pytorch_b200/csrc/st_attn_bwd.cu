@@ -27,6 +27,15 @@ namespace st {
 
 namespace {
 
+// Optional in-kernel timeline (option "attn_trace"): CTA (0,0,0) of the dK/dV kernel records clock64() at its pipeline
+// hand-offs — slot layout [role][tile][event]; read back with st_debug_read_trace (tools/trace_attn.py).
+constexpr int TRACE_TILES = 24, TRACE_EVENTS = 6;
+__device__ unsigned long long g_trace[2 * TRACE_TILES * TRACE_EVENTS];
+#define ST_TRACE(role, tile, ev)                                                                      \
+  do {                                                                                                \
+    if (trace_on && (tile) < TRACE_TILES) g_trace[((role) * TRACE_TILES + (tile)) * TRACE_EVENTS + (ev)] = clock64(); \
+  } while (0)
+
 constexpr int BT = 64;                 // streamed tile height
 constexpr int NCOMP = 512;             // compute threads
 constexpr int NTHREADS = NCOMP + 64;   // + producer warp + MMA warp
@@ -48,7 +57,7 @@ __device__ __forceinline__ void ds16_t(const uint32_t (&rs)[16], uint32_t (&rd)[
       if (MASK && ((mb >> (i + t)) & 1u)) pr = 0.f;
       float dp = __uint_as_float(rd[i + t]);
       if (DROP && !dropout_keep_xor(rowkey, cks[t], thresh)) dp = 0.f;
-      rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -delta)));
+      rd[i + t] = tf32_rna_mma_bits(pr * fmaf(dp, dscale, -delta));
     }
   }
 }
@@ -77,8 +86,8 @@ __device__ __forceinline__ void dkv16_t(uint32_t (&rs)[16], uint32_t (&rd)[16], 
       float dp = __uint_as_float(rd[i + t]);
       float pd = pr;
       if (DROP && !dropout_keep_xor(rks[t], my_ckey, thresh)) { pd = 0.f; dp = 0.f; }
-      rs[i + t] = __float_as_uint(tf32_rna(pd));
-      rd[i + t] = __float_as_uint(tf32_rna(pr * fmaf(dp, dscale, -dels[t])));
+      rs[i + t] = tf32_rna_mma_bits(pd);
+      rd[i + t] = tf32_rna_mma_bits(pr * fmaf(dp, dscale, -dels[t]));
     }
   }
 }
@@ -105,22 +114,29 @@ __device__ __forceinline__ void resident_to_tmem(const float* x0, int64_t ld0, c
 }
 
 // ================================================================================ dQ
-template <int DK>
+// RS = true: the resident Q / dO tiles live in SHARED memory (one TMA box each) and the recompute MMAs use the .ss form.
+// The tensor-memory read port (tcgen05.ld of S / dP by the compute warps + the A operands of .ts MMAs) is the busiest
+// resource of these kernels; with N = 64 a .ts MMA re-reads a 4 KB A slice from TMEM for only 64 output columns.
+template <int DK, bool RS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restrict__ dctx, int64_t lddctx,
                  const __grid_constant__ CUtensorMap tmap_k_k, const __grid_constant__ CUtensorMap tmap_k_mn,
-                 const __grid_constant__ CUtensorMap tmap_v_k, const AttnDev p) {
+                 const __grid_constant__ CUtensorMap tmap_v_k, const __grid_constant__ CUtensorMap tmap_q_res,
+                 const __grid_constant__ CUtensorMap tmap_do_res, const AttnDev p) {
   constexpr int BQ = 128;
   constexpr int G = DK / 32;
-  constexpr int STAGES = 4;
+  constexpr int STAGES = RS ? 3 : 4;
   constexpr int T_BYTES = BT * DK * 4;
   constexpr int STAGE_BYTES = 3 * T_BYTES;   // Kk | Km | Vk
+  constexpr int RES_BYTES = BQ * DK * 4;     // one resident tile (RS only)
   constexpr uint32_t TCOLS = 512;
   constexpr uint32_t T_S = 0, T_DP = 2 * BT, T_DQ = 4 * BT, T_Q = 4 * BT + DK, T_DO = 4 * BT + 2 * DK;
   static_assert(4 * BT + 3 * DK <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sBase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sRes = sBase;                                   // RS: Q | dO resident tiles (K-major, 128B swizzle)
+  uint8_t* sStage = sBase + (RS ? 2 * RES_BYTES : 0);
   __shared__ uint64_t res_ready, ld_full[STAGES], ld_empty[STAGES], s_full[2], ds_full[2], acc_full;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) uint32_t s_ckey[STAGES][BT];
@@ -132,7 +148,7 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
   const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
 
   if (tid == 0) {
-    mbar_init(&res_ready, NCOMP); mbar_init(&acc_full, 1);
+    mbar_init(&res_ready, RS ? 1 : NCOMP); mbar_init(&acc_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&ld_full[s], 1); mbar_init(&ld_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], NCOMP); }
     fence_mbar_init();
@@ -146,6 +162,11 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
   if (warp == W_PROD) {
     // ===================== producer =====================
     if (lane == 0) { tma_prefetch_desc(&tmap_k_k); tma_prefetch_desc(&tmap_k_mn); tma_prefetch_desc(&tmap_v_k); }
+    if (RS && lane == 0) {
+      mbar_arrive_expect_tx(&res_ready, 2 * RES_BYTES);
+      tma_load_4d(sRes, &tmap_q_res, &res_ready, 0, q0, h * G, b);              // rows >= Lq are zero-filled by TMA
+      tma_load_4d(sRes + RES_BYTES, &tmap_do_res, &res_ready, 0, q0, h * G, b);
+    }
     for (int t = 0; t < n_kv; ++t) {
       const int s = t % STAGES;
       mbar_wait(&ld_empty[s], ((t / STAGES) & 1) ^ 1);
@@ -165,35 +186,49 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The WARP stays converged (every lane waits on the barriers); one lane, chosen by elect.sync, issues.  Issuing
+    // under `lane == 0` instead makes the compiler wrap every tcgen05.mma in an ELECT / BRA.U.ANY loop (~60-120 cycles
+    // per MMA, measured: tools/mma_bench.py), which starves the tensor pipe for these N = 64 MMAs (floor 32 cycles).
+    {
       const uint32_t st0 = smem_u32(sStage);
-      auto issue_a = [&](int t) {   // S(t) = Q K^T, dP(t) = dO V^T   (A = resident tile in TMEM, B K-major)
+      const uint32_t rq = smem_u32(sRes), rdo = rq + RES_BYTES;
+      auto koff = [](int ks, int rows) { return static_cast<uint64_t>(((ks / 4) * (rows * 128) + (ks % 4) * 32) >> 4); };
+      auto issue_a = [&](int t) {   // S(t) = Q K^T, dP(t) = dO V^T   (A = resident tile, B K-major)
         const int s = t % STAGES, tb = t & 1;
         mbar_wait(&ld_full[s], (t / STAGES) & 1);
         tc_fence_after();
-        constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
-        const uint32_t bk = st0 + s * STAGE_BYTES, bv = bk + 2 * T_BYTES;
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
+          const uint64_t bk0 = umma_desc_kmajor(st0 + s * STAGE_BYTES), bv0 = umma_desc_kmajor(st0 + s * STAGE_BYTES + 2 * T_BYTES);
+          const uint64_t aq0 = umma_desc_kmajor(rq), ado0 = umma_desc_kmajor(rdo);
 #pragma unroll
-        for (int ks = 0; ks < DK / 8; ++ks)
-          umma_tf32_ts(tmem + T_S + tb * BT, tmem + T_Q + ks * 8,
-                       umma_desc_kmajor(bk + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < DK / 8; ++ks) {
+            if (RS) umma_tf32_ss(tmem + T_S + tb * BT, aq0 + koff(ks, BQ), bk0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            else umma_tf32_ts(tmem + T_S + tb * BT, tmem + T_Q + ks * 8, bk0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int ks = 0; ks < DK / 8; ++ks)
-          umma_tf32_ts(tmem + T_DP + tb * BT, tmem + T_DO + ks * 8,
-                       umma_desc_kmajor(bv + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
-        umma_commit(&s_full[tb]);
+          for (int ks = 0; ks < DK / 8; ++ks) {
+            if (RS) umma_tf32_ss(tmem + T_DP + tb * BT, ado0 + koff(ks, BQ), bv0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            else umma_tf32_ts(tmem + T_DP + tb * BT, tmem + T_DO + ks * 8, bv0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[tb]);
+        }
+        __syncwarp();
       };
       auto issue_b = [&](int t) {   // dQ += dS(t) K(t)   (A = dS in TMEM, B = K MN-major)
         const int s = t % STAGES, tb = t & 1;
         mbar_wait(&ds_full[tb], (t >> 1) & 1);
         tc_fence_after();
-        constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
-        const uint32_t bkm = st0 + s * STAGE_BYTES + T_BYTES;
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+          const uint64_t bkm0 = umma_desc_mnmajor(st0 + s * STAGE_BYTES + T_BYTES, BT * 128);
 #pragma unroll
-        for (int ks = 0; ks < BT / 8; ++ks)
-          umma_tf32_ts(tmem + T_DQ, tmem + T_DP + tb * BT + ks * 8, umma_desc_mnmajor(bkm + ks * 1024, BT * 128), idesc,
-                       (t > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&ld_empty[s]);   // stage s free once everything issued so far has retired
+          for (int ks = 0; ks < BT / 8; ++ks)
+            umma_tf32_ts(tmem + T_DQ, tmem + T_DP + tb * BT + ks * 8, bkm0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+                         (t > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&ld_empty[s]);   // stage s free once everything issued so far has retired
+        }
+        __syncwarp();
       };
       mbar_wait(&res_ready, 0);
       tc_fence_after();
@@ -202,7 +237,7 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
         if (t + 1 < n_kv) issue_a(t + 1);
         issue_b(t);
       }
-      umma_commit(&acc_full);
+      if (elect_one()) umma_commit(&acc_full);
     }
     __syncwarp();
   } else {
@@ -213,9 +248,11 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int col0 = slice * 16;
     const int64_t grow = static_cast<int64_t>(b) * p.Lq + (row_ok ? row : 0);
-    resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO);
-    tc_fence_before();
-    mbar_arrive(&res_ready);
+    if (!RS) {
+      resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO);
+      tc_fence_before();
+      mbar_arrive(&res_ready);
+    }
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
     const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
     const float delta = row_ok ? p.delta[stat] : 0.f;
@@ -267,23 +304,27 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
 }
 
 // ================================================================================ dK, dV
-template <int DK>
+template <int DK, bool RS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restrict__ v, int64_t ldv,
                   const __grid_constant__ CUtensorMap tmap_q_k, const __grid_constant__ CUtensorMap tmap_q_mn,
                   const __grid_constant__ CUtensorMap tmap_do_k, const __grid_constant__ CUtensorMap tmap_do_mn,
+                  const __grid_constant__ CUtensorMap tmap_k_res, const __grid_constant__ CUtensorMap tmap_v_res,
                   const AttnDev p) {
   constexpr int BKV = 128;
   constexpr int G = DK / 32;
-  constexpr int STAGES = 3;
+  constexpr int STAGES = (RS && DK == 64) ? 2 : 3;
   constexpr int T_BYTES = BT * DK * 4;
   constexpr int STAGE_BYTES = 4 * T_BYTES;   // Qk | Qm | dOk | dOm
+  constexpr int RES_BYTES = BKV * DK * 4;
   constexpr uint32_t TCOLS = 512;
   constexpr uint32_t T_ST = 0, T_DPT = 2 * BT, T_DV = 4 * BT, T_DK = 4 * BT + DK, T_K = 4 * BT + 2 * DK, T_V = 4 * BT + 3 * DK;
   static_assert(4 * BT + 4 * DK <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sBase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sRes = sBase;                                   // RS: K | V resident tiles (K-major, 128B swizzle)
+  uint8_t* sStage = sBase + (RS ? 2 * RES_BYTES : 0);
   __shared__ uint64_t res_ready, ld_full[STAGES], ld_empty[STAGES], s_full[2], ds_full[2], acc_full;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_lse[STAGES][BT];
@@ -293,9 +334,10 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
   const int n_q = (p.Lq + BT - 1) / BT;
+  const bool trace_on = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
   if (tid == 0) {
-    mbar_init(&res_ready, NCOMP); mbar_init(&acc_full, 1);
+    mbar_init(&res_ready, RS ? 1 : NCOMP); mbar_init(&acc_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&ld_full[s], 1); mbar_init(&ld_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], NCOMP); }
     fence_mbar_init();
@@ -310,6 +352,11 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
     // ===================== producer =====================
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q_k); tma_prefetch_desc(&tmap_q_mn); tma_prefetch_desc(&tmap_do_k); tma_prefetch_desc(&tmap_do_mn);
+      if (RS) {
+        mbar_arrive_expect_tx(&res_ready, 2 * RES_BYTES);
+        tma_load_4d(sRes, &tmap_k_res, &res_ready, 0, kv0, h * G, b);             // rows >= Lk are zero-filled by TMA
+        tma_load_4d(sRes + RES_BYTES, &tmap_v_res, &res_ready, 0, kv0, h * G, b);
+      }
     }
     for (int t = 0; t < n_q; ++t) {
       const int s = t % STAGES;
@@ -333,40 +380,58 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
       }
     }
   } else if (warp == W_MMA) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp + elect.sync, see the dQ kernel) =====================
+    {
       const uint32_t st0 = smem_u32(sStage);
-      auto issue_a = [&](int t) {   // S^T(t) = K Q^T, dP^T(t) = V dO^T   (A = resident tile in TMEM, B K-major)
+      const uint32_t rk = smem_u32(sRes), rv = rk + RES_BYTES;
+      auto koff = [](int ks, int rows) { return static_cast<uint64_t>(((ks / 4) * (rows * 128) + (ks % 4) * 32) >> 4); };
+      auto issue_a = [&](int t) {   // S^T(t) = K Q^T, dP^T(t) = V dO^T   (A = resident tile, B K-major)
         const int s = t % STAGES, tb = t & 1;
+        ST_TRACE(0, t, 0);
         mbar_wait(&ld_full[s], (t / STAGES) & 1);
+        ST_TRACE(0, t, 1);
         tc_fence_after();
-        constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
-        const uint32_t bq = st0 + s * STAGE_BYTES, bdo = bq + 2 * T_BYTES;
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
+          const uint64_t bq0 = umma_desc_kmajor(st0 + s * STAGE_BYTES), bdo0 = umma_desc_kmajor(st0 + s * STAGE_BYTES + 2 * T_BYTES);
+          const uint64_t ak0 = umma_desc_kmajor(rk), av0 = umma_desc_kmajor(rv);
 #pragma unroll
-        for (int ks = 0; ks < DK / 8; ++ks)
-          umma_tf32_ts(tmem + T_ST + tb * BT, tmem + T_K + ks * 8,
-                       umma_desc_kmajor(bq + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < DK / 8; ++ks) {
+            if (RS) umma_tf32_ss(tmem + T_ST + tb * BT, ak0 + koff(ks, BKV), bq0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            else umma_tf32_ts(tmem + T_ST + tb * BT, tmem + T_K + ks * 8, bq0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int ks = 0; ks < DK / 8; ++ks)
-          umma_tf32_ts(tmem + T_DPT + tb * BT, tmem + T_V + ks * 8,
-                       umma_desc_kmajor(bdo + (ks / 4) * (BT * 128) + (ks % 4) * 32), idesc, ks > 0 ? 1u : 0u);
-        umma_commit(&s_full[tb]);
+          for (int ks = 0; ks < DK / 8; ++ks) {
+            if (RS) umma_tf32_ss(tmem + T_DPT + tb * BT, av0 + koff(ks, BKV), bdo0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            else umma_tf32_ts(tmem + T_DPT + tb * BT, tmem + T_V + ks * 8, bdo0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[tb]);
+        }
+        __syncwarp();
+        ST_TRACE(0, t, 2);
       };
       auto issue_b = [&](int t) {   // dV += P^T dO, dK += dS^T Q   (A in TMEM, B MN-major)
         const int s = t % STAGES, tb = t & 1;
+        ST_TRACE(0, t, 3);
         mbar_wait(&ds_full[tb], (t >> 1) & 1);
+        ST_TRACE(0, t, 4);
         tc_fence_after();
-        constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
-        const uint32_t bqm = st0 + s * STAGE_BYTES + T_BYTES, bdom = st0 + s * STAGE_BYTES + 3 * T_BYTES;
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+          const uint64_t bqm0 = umma_desc_mnmajor(st0 + s * STAGE_BYTES + T_BYTES, BT * 128);
+          const uint64_t bdom0 = umma_desc_mnmajor(st0 + s * STAGE_BYTES + 3 * T_BYTES, BT * 128);
 #pragma unroll
-        for (int ks = 0; ks < BT / 8; ++ks)
-          umma_tf32_ts(tmem + T_DV, tmem + T_ST + tb * BT + ks * 8, umma_desc_mnmajor(bdom + ks * 1024, BT * 128), idesc,
-                       (t > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < BT / 8; ++ks)
+            umma_tf32_ts(tmem + T_DV, tmem + T_ST + tb * BT + ks * 8, bdom0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+                         (t > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < BT / 8; ++ks)
-          umma_tf32_ts(tmem + T_DK, tmem + T_DPT + tb * BT + ks * 8, umma_desc_mnmajor(bqm + ks * 1024, BT * 128), idesc,
-                       (t > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&ld_empty[s]);
+          for (int ks = 0; ks < BT / 8; ++ks)
+            umma_tf32_ts(tmem + T_DK, tmem + T_DPT + tb * BT + ks * 8, bqm0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+                         (t > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&ld_empty[s]);
+        }
+        __syncwarp();
+        ST_TRACE(0, t, 5);
       };
       mbar_wait(&res_ready, 0);
       tc_fence_after();
@@ -375,7 +440,7 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
         if (t + 1 < n_q) issue_a(t + 1);
         issue_b(t);
       }
-      umma_commit(&acc_full);
+      if (elect_one()) umma_commit(&acc_full);
     }
     __syncwarp();
   } else {
@@ -386,9 +451,11 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int col0 = slice * 16;
     const int64_t grow = static_cast<int64_t>(b) * p.Lk + (key_ok ? key : 0);
-    resident_to_tmem<DK>(k, ldk, v, ldv, grow, key_ok, h, slice, t_lane, T_K, T_V);
-    tc_fence_before();
-    mbar_arrive(&res_ready);
+    if (!RS) {
+      resident_to_tmem<DK>(k, ldk, v, ldv, grow, key_ok, h, slice, t_lane, T_K, T_V);
+      tc_fence_before();
+      mbar_arrive(&res_ready);
+    }
     const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
     bool key_masked = !key_ok;
     if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
@@ -398,13 +465,16 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
     const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
     for (int t = 0; t < n_q; ++t) {
       const int s = t % STAGES, tb = t & 1;
+      if (tid == 0) ST_TRACE(1, t, 0);
       mbar_wait(&s_full[tb], (t >> 1) & 1);
+      if (tid == 0) ST_TRACE(1, t, 1);
       tc_fence_after();
       uint32_t rs[16], rd[16];
       // tcgen05.ld/st are warp-collective (.sync.aligned): every lane executes them, whatever its key's mask state
       tmem_ld16(t_lane + T_ST + tb * BT + col0, rs);
       tmem_ld16(t_lane + T_DPT + tb * BT + col0, rd);
       tmem_ld_wait();
+      if (tid == 0) ST_TRACE(1, t, 2);
       if (!mask_dense && key_masked) {   // this key is padding for every query: P = dS = 0
 #pragma unroll
         for (int i = 0; i < 16; ++i) { rs[i] = 0u; rd[i] = 0u; }
@@ -421,11 +491,14 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
           else dkv16_t<false, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
         }
       }
+      if (tid == 0) ST_TRACE(1, t, 3);
       tmem_st16(t_lane + T_ST + tb * BT + col0, rs);
       tmem_st16(t_lane + T_DPT + tb * BT + col0, rd);
       tmem_st_wait();
+      if (tid == 0) ST_TRACE(1, t, 4);
       tc_fence_before();
       mbar_arrive(&ds_full[tb]);
+      if (tid == 0) ST_TRACE(1, t, 5);
     }
     // ---- epilogue: dV = dropout-scale * acc, dK = softmax-scale * acc
     mbar_wait(&acc_full, 0);
@@ -465,14 +538,20 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     ST_TRY(make_act_tmap(&tqm, f.q, f.ldq, cols, f.Lq, f.B, BT, 1, DK));
     ST_TRY(make_act_tmap(&tdk, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, 0, DK));
     ST_TRY(make_act_tmap(&tdm, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, 1, DK));
-    constexpr int SMEM = 3 * 4 * BT * DK * 4 + 1024;
-    auto kern = attn_bwd_dkv_pipe<DK>;
-    static bool attr = false;
-    if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+    CUtensorMap tkr, tvr;
+    ST_TRY(make_act_tmap(&tkr, f.k, f.ldk, cols, f.Lk, f.B, 128, 0, DK));
+    ST_TRY(make_act_tmap(&tvr, f.v, f.ldv, cols, f.Lk, f.B, 128, 0, DK));
+    const bool rs = get_option("attn_dkv_res_smem") != 0;
+    constexpr int SMEM_TS = 3 * 4 * BT * DK * 4 + 1024;
+    constexpr int SMEM_RS = (DK == 64 ? 2 : 3) * 4 * BT * DK * 4 + 2 * 128 * DK * 4 + 1024;
+    const int SMEM = rs ? SMEM_RS : SMEM_TS;
+    auto kern = rs ? attn_bwd_dkv_pipe<DK, true> : attn_bwd_dkv_pipe<DK, false>;
+    static bool attr[2] = {false, false};
+    if (!attr[rs]) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr[rs] = true; }
     dim3 grid((f.Lk + 127) / 128, f.H, f.B);
     // algorithmic share of the attention backward carried by this kernel: dV and dK (S, dP recompute not counted)
     ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    kern<<<grid, NTHREADS, SMEM, s>>>(f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, p);
+    kern<<<grid, NTHREADS, SMEM, s>>>(f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, tkr, tvr, p);
     ST_CHECK_LAUNCH();
   }
   {
@@ -480,20 +559,33 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BT, 0, DK));
     ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BT, 1, DK));
     ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BT, 0, DK));
-    constexpr int SMEM = 4 * 3 * BT * DK * 4 + 1024;
-    auto kern = attn_bwd_dq_pipe<DK>;
-    static bool attr = false;
-    if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+    CUtensorMap tqr, tdr;
+    ST_TRY(make_act_tmap(&tqr, f.q, f.ldq, cols, f.Lq, f.B, 128, 0, DK));
+    ST_TRY(make_act_tmap(&tdr, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0, DK));
+    const bool rs = get_option("attn_dq_res_smem") != 0;
+    constexpr int SMEM_TS = 4 * 3 * BT * DK * 4 + 1024;
+    constexpr int SMEM_RS = 3 * 3 * BT * DK * 4 + 2 * 128 * DK * 4 + 1024;
+    const int SMEM = rs ? SMEM_RS : SMEM_TS;
+    auto kern = rs ? attn_bwd_dq_pipe<DK, true> : attn_bwd_dq_pipe<DK, false>;
+    static bool attr[2] = {false, false};
+    if (!attr[rs]) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr[rs] = true; }
     dim3 grid((f.Lq + 127) / 128, f.H, f.B);
     // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
     ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    kern<<<grid, NTHREADS, SMEM, s>>>(f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, p);
+    kern<<<grid, NTHREADS, SMEM, s>>>(f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, tqr, tdr, p);
     ST_CHECK_LAUNCH();
   }
   return ST_OK;
 }
 
 }  // namespace
+
+int attn_read_trace(unsigned long long* host_out, int n) {
+  const int total = 2 * TRACE_TILES * TRACE_EVENTS;
+  ST_CHECK_CUDA(cudaDeviceSynchronize());
+  ST_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * (n < total ? n : total)));
+  return total;
+}
 
 int attn_bwd_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
   return a.f.dk == 32 ? launch_pipelined<32>(s, a, p) : launch_pipelined<64>(s, a, p);

@@ -39,6 +39,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// Same rounding for a value that is ONLY ever read by the tensor core (TMEM / smem MMA operands): the MMA ignores the
+// low 13 mantissa bits, so adding half an ulp of the TF32 grid is enough — one integer add instead of the three
+// instructions cvt.rna.tf32 compiles to (range check + add + mask).  Inf becomes NaN (irrelevant for probabilities and
+// score gradients); the unmasked low bits never reach memory that anything else reads.
+__device__ __forceinline__ uint32_t tf32_rna_mma_bits(float x) { return __float_as_uint(x) + 0x1000u; }
+
 // ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------

@@ -342,7 +342,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // Converged warp; one lane chosen by elect.sync issues (under a `lane == 0` branch the compiler wraps every
+    // uniform-datapath instruction — UTMALDG, UTCHMMA — in an ELECT / BRA.U.ANY loop, 60-120 cycles each).
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
@@ -355,6 +357,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
+          if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (!A_MN) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
@@ -384,13 +387,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp + elect.sync) =====================
+    {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -408,19 +413,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
+          if (elect_one()) {
             // K-major: +32 B per MMA inside the 128 B swizzle row.  MN-major: next 8-row K atom pair (+1024 B);
-            // 32-wide MN groups are 4096 B apart (one TMA box each).
-            const uint64_t adesc = A_MN ? umma_desc_mnmajor(sa + k * 1024, 4096) : umma_desc_kmajor(sa + k * 32);
-            const uint64_t bdesc = B_MN ? umma_desc_mnmajor(sb + k * 1024, 4096) : umma_desc_kmajor(sb + k * 32);
-            umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            // 32-wide MN groups are 4096 B apart (one TMA box each).  Descriptors = base + constant (no re-encoding).
+            const uint64_t a0 = A_MN ? umma_desc_mnmajor(sa, 4096) : umma_desc_kmajor(sa);
+            const uint64_t b0 = B_MN ? umma_desc_mnmajor(sb, 4096) : umma_desc_kmajor(sb);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_ss(d_tmem, a0 + static_cast<uint64_t>((A_MN ? k * 1024 : k * 32) >> 4),
+                           b0 + static_cast<uint64_t>((B_MN ? k * 1024 : k * 32) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            // frees the smem stage once these MMAs retire (in every CTA whose TMA writes into it)
+            if (CL > 1) umma_commit_mc(&empty_bar[stage], (1u << CL) - 1); else umma_commit(&empty_bar[stage]);
+            if (kb + 1 == kb1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
           }
-          // frees the smem stage once these MMAs retire (in every CTA whose TMA writes into it)
-          if (CL > 1) umma_commit_mc(&empty_bar[stage], (1u << CL) - 1); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -513,8 +521,8 @@ gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; converged warp + elect.sync) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
@@ -527,6 +535,7 @@ gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S2_STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
+          if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S2_STAGE_BYTES);   // bytes of BOTH CTAs
           if (!A_MN) {
             tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
@@ -542,13 +551,15 @@ gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             for (int i = 0; i < 4; ++i)
               tma_load_2d_2sm(sb + i * 4096, &tmap_b, &full_bar[stage], n_blk * BN + crank * 128 + i * 32, kb * BK);
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_tf32(256, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -566,16 +577,19 @@ gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S2_STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
+          if (elect_one()) {
+            const uint64_t a0 = A_MN ? umma_desc_mnmajor(sa, 4096) : umma_desc_kmajor(sa);
+            const uint64_t b0 = B_MN ? umma_desc_mnmajor(sb, 4096) : umma_desc_kmajor(sb);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t adesc = A_MN ? umma_desc_mnmajor(sa + k * 1024, 4096) : umma_desc_kmajor(sa + k * 32);
-            const uint64_t bdesc = B_MN ? umma_desc_mnmajor(sb + k * 1024, 4096) : umma_desc_kmajor(sb + k * 32);
-            umma_tf32_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_ss_2sm(d_tmem, a0 + static_cast<uint64_t>((A_MN ? k * 1024 : k * 32) >> 4),
+                               b0 + static_cast<uint64_t>((B_MN ? k * 1024 : k * 32) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm_mc(&empty_bar[stage], 3);   // release the stage in both CTAs
+            if (kb + 1 == kb1) umma_commit_2sm_mc(&tfull_bar[acc], 3);   // accumulators complete -> both epilogues
           }
-          umma_commit_2sm_mc(&empty_bar[stage], 3);   // release the stage in both CTAs
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm_mc(&tfull_bar[acc], 3);       // accumulators complete -> both epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

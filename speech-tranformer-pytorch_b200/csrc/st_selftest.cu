@@ -262,4 +262,107 @@ int selftest(int which, double* err) {
 
 int selftest_count() { return 26; }
 
+// ---- tcgen05.mma issue-rate microbenchmark (design input for the attention kernels; tools/mma_bench.py) --------
+// One CTA issues `iters` groups of 16 TF32 MMAs (M = 128, N = n, K = 8 each, the k-offset pattern of the attention
+// kernels) back to back and waits for the last commit; reports cycles per MMA.  Operand contents are zeros.
+//   variant bit 0: A from TMEM (.ts) instead of shared memory;  bit 1: B MN-major (32-byte-atom swizzle) instead of K-major
+namespace {
+__global__ void __launch_bounds__(128, 1) mma_bench_kernel(int variant, int n, int iters, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (32 + 64) * 1024 / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  {   // zero the TMEM A region (columns 256..319)
+    uint32_t z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = 0u;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    tmem_st32(t_lane + 256, z);
+    tmem_st32(t_lane + 288, z);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t sA = smem_u32(sm), sB = sA + 32 * 1024;
+  const bool a_tmem = variant & 1, b_mn = variant & 2;
+  const uint32_t idesc = umma_idesc_tf32(128, n, false, b_mn);
+  const int nacc = ((variant >> 2) & 3) + 1;                       // accumulators cycled through (1, 2 or 4)
+  if (!(variant & 16)) {
+    // (a) the issuing THREAD: everything under `tid == 0`
+    if (tid == 0) {
+      uint32_t phase = 0;
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ks = j & 7;
+          const uint64_t bdesc = b_mn ? umma_desc_mnmajor(sB + ks * 1024, 64 * 128)
+                                      : umma_desc_kmajor(sB + (ks / 4) * (n * 128) + (ks % 4) * 32);
+          const uint32_t dcol = static_cast<uint32_t>((j % nacc) * n) & 255u;
+          if (a_tmem) umma_tf32_ts(tmem + dcol, tmem + 256 + ks * 8, bdesc, idesc, 1u);
+          else umma_tf32_ss(tmem + dcol, umma_desc_kmajor(sA + (ks / 4) * (128 * 128) + (ks % 4) * 32), bdesc, idesc, 1u);
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+      }
+      out[0] = static_cast<unsigned long long>(clock64() - t0);
+    }
+  } else if (warp == 0) {
+    // (b) the issuing WARP stays converged; one elected lane issues (elect.sync), descriptors are base + constant
+    uint32_t phase = 0;
+    const uint64_t a0 = umma_desc_kmajor(sA);
+    const uint64_t b0 = b_mn ? umma_desc_mnmajor(sB, 64 * 128) : umma_desc_kmajor(sB);
+    const uint32_t bgrp = b_mn ? 0u : static_cast<uint32_t>(n * 128) >> 4;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ks = j & 7;
+          const uint64_t bdesc = b_mn ? b0 + static_cast<uint64_t>((ks * 1024) >> 4)
+                                      : b0 + static_cast<uint64_t>((ks / 4) * bgrp + (((ks % 4) * 32) >> 4));
+          const uint32_t dcol = static_cast<uint32_t>((j % nacc) * n) & 255u;
+          if (a_tmem) umma_tf32_ts(tmem + dcol, tmem + 256 + ks * 8, bdesc, idesc, 1u);
+          else umma_tf32_ss(tmem + dcol, a0 + static_cast<uint64_t>(((ks / 4) * (128 * 128) + (ks % 4) * 32) >> 4), bdesc, idesc, 1u);
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    if (tid == 0) out[0] = static_cast<unsigned long long>(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+}  // namespace
+
+int mma_bench(int variant, int n, int iters, double* clk_per_mma) {
+  ST_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && iters > 0 && variant >= 0 && variant < 32, "mma_bench: bad arguments");
+  unsigned long long* d = nullptr;
+  ST_CHECK_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+  const int smem = (32 + 64) * 1024 + 1024;
+  ST_CHECK_CUDA(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_bench_kernel<<<1, 128, smem>>>(variant, n, iters, d);
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  ST_CHECK_CUDA(e);
+  *clk_per_mma = static_cast<double>(h) / (16.0 * iters);
+  return ST_OK;
+}
+
 }  // namespace st

@@ -7,3 +7,4 @@ if d.get("roofline"):
 for k, v in (d.get("kernel_breakdown") or {}).items():
     print(f"  {k:16s} {v['ms_per_step']:8.3f} ms  share {v['share_of_step']:.3f}  launches {v['launches_per_step']:.0f}  rate {v['rate']:.2f} T(FLOP|B)/s")
 if d.get("cpu_baseline"): print("cpu_baseline:", d["cpu_baseline"])
+if d.get("encoder_layer"): e = d["encoder_layer"]; print(f"encoder layer fwd+bwd: {e['ms_fwd_bwd']:.3f} ms  {e['tflops']:.1f} TFLOP/s = {e['frac_of_tf32_peak_measured']:.3f} of TF32 peak, {e['frac_of_bf16_peak']:.3f} of bf16 peak")
