@@ -541,7 +541,11 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     CUtensorMap tkr, tvr;
     ST_TRY(make_act_tmap(&tkr, f.k, f.ldk, cols, f.Lk, f.B, 128, 0, DK));
     ST_TRY(make_act_tmap(&tvr, f.v, f.ldv, cols, f.Lk, f.B, 128, 0, DK));
-    const bool rs = get_option("attn_dkv_res_smem") != 0;
+    // Few query tiles (decoder cross-/self-attention, Lq <= 128): the CTA is prologue-bound, and fetching the resident K/V
+    // tiles with one TMA box each beats the LDG -> tcgen05.st path (183 -> 134 us at B=32, h=8, Lq=50, Lk=1000); with many
+    // query tiles the third ring stage matters more.  Option: 0 = this heuristic, 1 = always shared memory, 2 = always TMEM.
+    const int rs_opt = get_option("attn_dkv_res_smem");
+    const bool rs = rs_opt == 1 || (rs_opt == 0 && f.Lq <= 2 * BT);
     constexpr int SMEM_TS = 3 * 4 * BT * DK * 4 + 1024;
     constexpr int SMEM_RS = (DK == 64 ? 2 : 3) * 4 * BT * DK * 4 + 2 * 128 * DK * 4 + 1024;
     const int SMEM = rs ? SMEM_RS : SMEM_TS;

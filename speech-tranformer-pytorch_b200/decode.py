@@ -1,0 +1,235 @@
+"""Incremental decoding with K/V reuse and on-device beam search (BASELINE.json configs[4]).
+
+The reference has only the O(L^2) full-prefix re-decode of transformer/Decode.py:48-179 driven by
+transformer/Beam.py:43-74 (both stale: undefined symbols, old constructor, float `prev_k`).  This module is the
+decode path those files describe, built for the B200 library:
+
+  * the encoder runs once; every decoder layer's cross-attention K/V projection of the encoder output is computed
+    ONCE per utterance and shared by all beams (the beam hypotheses of an utterance are the query rows of one
+    attention problem: B x beam x T, key-padding mask broadcast with stride 0);
+  * self-attention K/V of already decoded positions live in a time-major cache (L_max, B*beam, d); appending a step
+    writes one contiguous row, and a step attends with Lq = 1 over Lk = t + 1 by presenting the (hypothesis, head)
+    pairs as B*beam*h heads of a single batch — no re-packing, no mask;
+  * one decoder step = the new token only: 5 projection GEMMs + 2 attention calls + 2 residual-LayerNorms + the fused
+    FFN per layer, all from libst_b200.so (st_gemm / st_attn_fwd / st_add_ln_fwd / st_ffn_fwd / st_embed_fwd);
+  * beam bookkeeping (Beam.advance: add scores, top-k over beam x vocab, integer-floor back-pointer, Beam.py:43-74)
+    stays on the device; the host only polls an "all finished" flag.
+
+There is no CPU fallback.  Parity: tests/test_gpu_decode.py checks step logits against the full-prefix decoder and
+the beam result against oracle/decode_port.py (the reference's algorithm on the CPU oracle model).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from . import functional as F
+from ._lib import check
+from .model import PAD, key_padding_mask
+
+BOS, EOS = 1, 2   # transformer/Constants.py:2-3
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class _Linear:
+    """A weight rounded to TF32 once (inference weights do not change) + its bias."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+        self.w = F.round_tf32(weight.detach())
+        self.b = None if bias is None else bias.detach().contiguous()
+        self.n, self.k = self.w.shape
+
+    def __call__(self, lib, x: torch.Tensor, out: torch.Tensor, ldc: Optional[int] = None, residual: Optional[torch.Tensor] = None,
+                 round_out: bool = True):
+        """out[:, :n] = x @ w.T + b (+ residual); x is (rows, k) TF32-clean, out has leading dimension ldc."""
+        rows = x.shape[0]
+        ep = _lib.GemmEpilogue(bias=_p(self.b), aux=_p(residual), ldaux=self.n if residual is not None else 0,
+                               aux_mode=1 if residual is not None else 0, relu=0, round_tf32=int(round_out), k_splits=1,
+                               dropout_p=0.0, seed=0)
+        check(lib.st_gemm(0, _p(x), self.k, _p(self.w), self.k, _p(out), ldc or self.n, rows, self.n, self.k, C.byref(ep),
+                          F._stream()))
+        return out
+
+
+class _LayerWeights:
+    def __init__(self, layer):
+        sa, ca, ff = layer.slf_attn, layer.enc_attn, layer.pos_ffn
+        self.q, self.k, self.v = (_Linear(m.weight, m.bias) for m in (sa.linear_q, sa.linear_k, sa.linear_v))
+        self.so = _Linear(sa.output_linear.weight, sa.output_linear.bias)
+        self.s_ln = (sa.layernorm.weight.detach(), sa.layernorm.bias.detach(), sa.layernorm.eps)
+        self.cq = _Linear(ca.linear_q.weight, ca.linear_q.bias)
+        self.ckv = _Linear(torch.cat([ca.linear_k.weight, ca.linear_v.weight], 0), torch.cat([ca.linear_k.bias, ca.linear_v.bias], 0))
+        self.co = _Linear(ca.output_linear.weight, ca.output_linear.bias)
+        self.c_ln = (ca.layernorm.weight.detach(), ca.layernorm.bias.detach(), ca.layernorm.eps)
+        self.ffn = ff
+        self.n_head = sa.n_head
+
+
+class IncrementalDecoder:
+    """Decoder of a `model.Transformer` that advances one target position per call, reusing cached K/V."""
+
+    def __init__(self, net, max_len: Optional[int] = None):
+        self.net = net
+        self.lib = _lib.load()
+        dec = net.decoder
+        self.d = dec.d_model
+        self.max_len = int(max_len or dec.n_max_seq)
+        self.layers = [_LayerWeights(l) for l in dec.layer_stack]
+        self.proj = _Linear(net.tgt_word_proj.weight, net.tgt_word_proj.bias)
+        self.emb = dec.tgt_word_emb.weight.detach()
+        self.pe = dec.position_enc.pe[0].detach()
+        self.vocab = self.emb.shape[0]
+        self.state = None
+
+    # ---- once per batch ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def start(self, inputs: torch.Tensor, input_lengths: torch.Tensor, beam: int = 1) -> None:
+        """Encode the utterances and project every layer's cross-attention K/V once (shared by all beams)."""
+        net = self.net
+        if net.training:
+            raise RuntimeError("IncrementalDecoder: call net.eval() first (decoding does not apply dropout)")
+        enc, _ = net.encoder(inputs, input_lengths)
+        B, T, d = enc.shape
+        enc2 = enc.reshape(B * T, d)
+        if not F.is_tf32_clean(enc):
+            enc2 = F.round_tf32(enc2)
+        dev = enc.device
+        n = B * beam
+        kv = []
+        for lw in self.layers:
+            buf = torch.empty(B * T, 2 * d, device=dev, dtype=torch.float32)
+            lw.ckv(self.lib, enc2, buf)                       # [K | V] of the encoder output, Attention.py:75-76
+            kv.append(buf)
+        self.state = {
+            "B": B, "beam": beam, "T": T, "t": 0, "cross_kv": kv,
+            "cross_mask": key_padding_mask(input_lengths, beam, T),          # (B, beam, T), stride 0 over beams
+            "k": [torch.zeros(self.max_len, n, d, device=dev) for _ in self.layers],
+            "v": [torch.zeros(self.max_len, n, d, device=dev) for _ in self.layers],
+        }
+
+    # ---- attention helpers -----------------------------------------------------------------------------------
+    def _attn(self, B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, mask, out):
+        dk = self.d // self.layers[0].n_head
+        lse = torch.empty(B * H * Lq, device=q.device, dtype=torch.float32)
+        if mask is not None:
+            m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+            sb, sq, sk = m.stride()
+        else:
+            m, sb, sq, sk = None, 0, 0, 0
+        a = _lib.AttnArgs(B=B, H=H, Lq=Lq, Lk=Lk, dk=dk, q=_p(q), ldq=ldq, k=_p(k), ldk=ldk, v=_p(v), ldv=ldv, mask=_p(m),
+                          ms_b=sb, ms_q=sq, ms_k=sk, dropout_p=0.0, seed=0, ctx=_p(out), ldctx=ldq, lse=_p(lse), attn=None)
+        check(self.lib.st_attn_fwd(C.byref(a), F._stream()))
+        return out
+
+    def _ln(self, z, ln, out):
+        g, b, eps = ln
+        rows, d = z.shape
+        check(self.lib.st_add_ln_fwd(_p(z), None, _p(g), _p(b), _p(out), None, None, None, rows, d, float(eps), 1, 0.0, 0,
+                                     F._stream()))
+        return F.mark_tf32_clean(out)
+
+    # ---- one target position -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens: (B*beam,) int64, the symbols at position t.  Returns the logits (B*beam, V) for position t + 1."""
+        st, lib, d = self.state, self.lib, self.d
+        B, beam, T, t = st["B"], st["beam"], st["T"], st["t"]
+        n = B * beam
+        if t >= self.max_len:
+            raise RuntimeError(f"IncrementalDecoder: position {t} exceeds max_len {self.max_len}")
+        dev = tokens.device
+        x = torch.empty(n, d, device=dev, dtype=torch.float32)
+        # embedding row + positional encoding of position t (Models.py:84-87)
+        check(lib.st_embed_fwd(_p(tokens.contiguous()), _p(self.emb), _p(self.pe[t:t + 1]), 1, _p(x), n, d, self.vocab, 1,
+                               F._stream()))
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        for i, lw in enumerate(self.layers):
+            H = lw.n_head
+            # masked self-attention over the cached positions 0..t (Layers.py:37-38): q of the new token only
+            q = lw.q(lib, x, new(n, d))
+            lw.k(lib, x, st["k"][i][t])                      # append: one contiguous (n, d) row of the time-major cache
+            lw.v(lib, x, st["v"][i][t])
+            ctx = self._attn(1, n * H, 1, t + 1, q, n * d, st["k"][i], n * d, st["v"][i], n * d, None, new(n, d))
+            a = self._ln(lw.so(lib, ctx, new(n, d), residual=x, round_out=False), lw.s_ln, new(n, d))
+            # cross-attention: the beams of an utterance are the query rows; K/V of the encoder output are shared
+            q2 = lw.cq(lib, a, new(n, d))
+            kv = st["cross_kv"][i]
+            ctx2 = self._attn(B, H, beam, T, q2, d, kv, 2 * d, kv[:, d:], 2 * d, st["cross_mask"], new(n, d))
+            c = self._ln(lw.co(lib, ctx2, new(n, d), residual=a, round_out=False), lw.c_ln, new(n, d))
+            # position-wise FFN (fused operator, SubLayers.py:24-28)
+            f = lw.ffn
+            x = F.positionwise_ffn(c, f.fc1.weight, f.fc1.bias, f.fc2.weight, f.fc2.bias, f.layernorm.weight, f.layernorm.bias,
+                                   eps=f.layernorm.eps, dropout_p=0.0, seed=0, round_out=True)
+        st["t"] = t + 1
+        ldy = (self.vocab + 3) // 4 * 4
+        logits = torch.empty(n, ldy, device=dev, dtype=torch.float32)
+        self.proj(lib, x, logits, ldc=ldy, round_out=False)                  # Models.py:151
+        return logits[:, :self.vocab]
+
+    @torch.no_grad()
+    def reorder(self, parent: torch.Tensor) -> None:
+        """Beam search re-parenting: hypothesis j continues hypothesis parent[j] (global indices into B*beam)."""
+        st = self.state
+        t = st["t"]
+        for i in range(len(self.layers)):
+            st["k"][i][:t] = st["k"][i][:t].index_select(1, parent)
+            st["v"][i][:t] = st["v"][i][:t].index_select(1, parent)
+
+
+@torch.no_grad()
+def beam_search(net, inputs: torch.Tensor, input_lengths: torch.Tensor, beam: int = 10, max_len: int = 50,
+                n_best: int = 1, eos: int = EOS) -> Tuple[List[List[List[int]]], torch.Tensor]:
+    """Beam decode a batch (Decode.decode_batch, Decode.py:48-179, with Beam.advance semantics, Beam.py:43-74):
+    every step adds log-probabilities to the running beam scores, keeps the `beam` best of beam x vocab, records
+    the integer back-pointer and symbol; an utterance is finished when its best hypothesis ends in EOS.
+    Returns (hypotheses[b][k] = token list without BOS, scores (B, n_best))."""
+    dec = IncrementalDecoder(net, max_len=max_len)
+    dec.start(inputs, input_lengths, beam)
+    B, V, dev = inputs.size(0), dec.vocab, inputs.device
+    scores = torch.zeros(B, beam, device=dev)
+    tokens = torch.full((B * beam,), BOS, dtype=torch.int64, device=dev)
+    done = torch.zeros(B, dtype=torch.bool, device=dev)
+    base = (torch.arange(B, device=dev) * beam).unsqueeze(1)
+    prev_ks, next_ys = [], []
+    for t in range(max_len):
+        logp = torch.log_softmax(dec.step(tokens), dim=-1).view(B, beam, V)
+        cand = logp + scores.unsqueeze(2) if t > 0 else logp[:, :1]      # first step: all beams are identical (Beam.py:49-52)
+        best, idx = cand.reshape(B, -1).topk(beam, dim=1)
+        prev_k = torch.div(idx, V, rounding_mode="floor")                # integer back-pointer (Beam.py:66)
+        y = idx - prev_k * V
+        # finished utterances are frozen: their beams keep their scores and repeat themselves
+        keep = done.unsqueeze(1)
+        prev_k = torch.where(keep, torch.arange(beam, device=dev).expand(B, -1), prev_k)
+        y = torch.where(keep, torch.full_like(y, PAD), y)
+        scores = torch.where(keep, scores, best)
+        prev_ks.append(prev_k)
+        next_ys.append(y)
+        done = done | (y[:, 0] == eos)                                   # Beam.py:70-72
+        if bool(done.all()):
+            break
+        dec.reorder((base + prev_k).reshape(-1))
+        tokens = y.reshape(-1)
+    # back-track (Beam.get_hypothesis, Beam.py:100-118) for the n_best final beams, best score first
+    order = scores.sort(dim=1, descending=True)
+    prev = torch.stack(prev_ks).cpu()      # (steps, B, beam)
+    ys = torch.stack(next_ys).cpu()
+    top = order.indices[:, :n_best].cpu()
+    hyps = []
+    for b in range(B):
+        per = []
+        for k in top[b].tolist():
+            seq = []
+            for j in range(len(prev_ks) - 1, -1, -1):
+                tok = int(ys[j, b, k])
+                if tok != PAD:
+                    seq.append(tok)
+                k = int(prev[j, b, k])
+            per.append(seq[::-1])
+        hyps.append(per)
+    return hyps, order.values[:, :n_best]

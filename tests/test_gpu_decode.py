@@ -1,0 +1,80 @@
+"""GPU parity of incremental decoding with K/V reuse and on-device beam search against the
+full-prefix decoder and oracle/decode_port.py (the reference's Decode.py / Beam.py algorithm on the CPU oracle)."""
+import pytest
+import torch
+
+from helpers import golden, relerr, t
+from oracle import decode_port, model_port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_MODEL = 3e-3          # composed-model tolerance, see tests/test_gpu_model.py
+CFG = dict(d_model=64, n_heads=2, num_enc_layer=2, num_dec_layer=2, vocab_size=31)
+
+
+@pytest.fixture(scope="module")
+def stb():
+    import speech_tranformer_pytorch_b200 as m
+    m.build()
+    m._lib.check(m._lib.load().st_device_check(0))
+    return m
+
+
+def _model(stb, g, sharpen=1.0):
+    from test_gpu_model import _small_model
+    net = _small_model(stb, g)
+    P = {k[2:]: t(v).double() for k, v in g.items() if k.startswith("p.") and not k.endswith(".pe")}
+    if sharpen != 1.0:   # peaky output distributions: top-k decisions far from ties, robust to TF32 vs fp64
+        with torch.no_grad():
+            net.tgt_word_proj.weight.mul_(sharpen)
+        P["tgt_word_proj.weight"] = P["tgt_word_proj.weight"] * sharpen
+    return net, P
+
+
+def test_incremental_steps_match_full_prefix_decoder(stb):
+    """Teacher-forced: the logits of every incremental step (cached K/V, one new position) equal the last position of
+    the full-prefix decoder — this library's own full forward and the CPU oracle."""
+    from speech_tranformer_pytorch_b200.decode import IncrementalDecoder
+    g = golden("transformer_small")
+    net, P = _model(stb, g)
+    inputs, in_len, targets = t(g["inputs"]), t(g["in_len"]), t(g["targets"])
+    B, L = targets.shape
+    beam = 2                                                     # two identical beams per utterance: exercises the beam-as-query-rows layout
+    dec = IncrementalDecoder(net, max_len=16)
+    dec.start(inputs.to(DEV), in_len.to(DEV), beam=beam)
+    rep = targets.repeat_interleave(beam, 0)
+    full_len = torch.full((B,), L, dtype=torch.int64)
+    with torch.no_grad():
+        full, _ = net(inputs.to(DEV), in_len.to(DEV), targets.to(DEV), full_len.to(DEV))      # causal: position t sees 0..t
+    ref = model_port.forward(P, CFG, inputs, in_len, targets, full_len)
+    for step in range(L):
+        logits = dec.step(rep[:, step].to(DEV))
+        assert logits.shape == (B * beam, 31)
+        assert torch.equal(logits[0::beam], logits[1::beam])     # identical beams -> identical rows, bit for bit
+        assert relerr(logits[0::beam], ref[:, step]) < TOL_MODEL, step
+        assert relerr(logits[0::beam], full[:, step]) < TOL_MODEL, step
+
+
+@pytest.mark.parametrize("beam,eos", [(1, 2), (4, 2), (4, 3)])   # eos = 3: some utterances finish early (frozen beams)
+def test_beam_search_matches_oracle(stb, beam, eos):
+    from speech_tranformer_pytorch_b200.decode import beam_search
+    g = golden("transformer_small")
+    net, P = _model(stb, g, sharpen=12.0)
+    inputs, in_len = t(g["inputs"]), t(g["in_len"])
+    hyps, scores = beam_search(net, inputs.to(DEV), in_len.to(DEV), beam=beam, max_len=10, n_best=min(beam, 2), eos=eos)
+    rhyps, rscores = decode_port.beam_search(P, CFG, inputs.double(), in_len, beam=beam, max_len=10, n_best=min(beam, 2), eos=eos)
+    assert relerr(scores, rscores) < 2e-2                         # sums of up to 10 log-probabilities of sharpened logits
+    for b in range(inputs.size(0)):
+        for k in range(len(rhyps[b])):
+            if hyps[b][k] != rhyps[b][k]:                        # only acceptable at a near-tie between hypotheses
+                assert abs(float(scores[b, k]) - float(rscores[b, k])) < 1e-2 * max(1.0, abs(float(rscores[b, k]))), (b, k, hyps[b][k], rhyps[b][k])
+    assert sum(hyps[b][0] == rhyps[b][0] for b in range(inputs.size(0))) >= inputs.size(0) - 1
+
+
+def test_decode_requires_eval_mode(stb):
+    from speech_tranformer_pytorch_b200.decode import IncrementalDecoder
+    g = golden("transformer_small")
+    net, _ = _model(stb, g)
+    net.train()
+    with pytest.raises(RuntimeError):
+        IncrementalDecoder(net).start(t(g["inputs"]).to(DEV), t(g["in_len"]).to(DEV))
