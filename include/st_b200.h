@@ -156,6 +156,10 @@ typedef struct {
   float* attn;          /* NULL or (B,H,Lq,Lk) */
   float* saved; int64_t saved_floats;
   float* ws; int64_t ws_floats;
+  /* Optional TF32-rounded copies of the weights, maintained by the caller (st_adam_step writes them): when all four
+   * are given, [wq; wk; wv] are adjacent in memory (wk_tf32 == wq_tf32 + d*d, ...) and so are the biases
+   * (bk == bq + d, bv == bk + d), the per-call rounding / packing passes are skipped.  NULL = round internally. */
+  const float* wq_tf32; const float* wk_tf32; const float* wv_tf32; const float* wo_tf32;
 } st_mha_args;
 int64_t st_mha_saved_floats(int B, int Lq, int Lk, int H, int d_model, int same_qkv, int same_kv, int inputs_tf32);
 int64_t st_mha_ws_floats(int B, int Lq, int Lk, int H, int d_model);
@@ -186,6 +190,7 @@ typedef struct {
   float* out;
   float* saved; int64_t saved_floats;
   float* ws; int64_t ws_floats;
+  const float* w1_tf32; const float* w2_tf32;   /* optional TF32-rounded weights (see st_mha_args); NULL = round internally */
 } st_ffn_args;
 int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32);
 int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff);
@@ -274,6 +279,7 @@ typedef struct {
   int step;
   float max_grad_norm, grad_scale;
   const float* norm_ws;
+  float* param_tf32;    /* optional (n floats): receives round_to_tf32(updated param) for the next step's GEMMs */
 } st_adam_args;
 int st_adam_step(const st_adam_args* a /* host */, cudaStream_t stream);
 

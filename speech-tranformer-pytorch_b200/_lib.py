@@ -45,7 +45,8 @@ class MhaArgs(C.Structure):
                 ("eps", C.c_float), ("dropout_p", C.c_float), ("seed", u64),
                 ("inputs_tf32", C.c_int), ("round_out", C.c_int),
                 ("out", C.c_void_p), ("attn", C.c_void_p),
-                ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64)]
+                ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64),
+                ("wq_tf32", C.c_void_p), ("wk_tf32", C.c_void_p), ("wv_tf32", C.c_void_p), ("wo_tf32", C.c_void_p)]
 
 
 class MhaBwdArgs(C.Structure):
@@ -62,7 +63,8 @@ class FfnArgs(C.Structure):
                 ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
                 ("eps", C.c_float), ("dropout_p", C.c_float), ("seed", u64),
                 ("x_is_tf32", C.c_int), ("round_out", C.c_int),
-                ("out", C.c_void_p), ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64)]
+                ("out", C.c_void_p), ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64),
+                ("w1_tf32", C.c_void_p), ("w2_tf32", C.c_void_p)]
 
 
 class FfnBwdArgs(C.Structure):
@@ -98,7 +100,7 @@ class AdamArgs(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("n", i64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("step", C.c_int), ("max_grad_norm", C.c_float), ("grad_scale", C.c_float),
-                ("norm_ws", C.c_void_p)]
+                ("norm_ws", C.c_void_p), ("param_tf32", C.c_void_p)]
 
 
 # every symbol include/st_b200.h declares: name -> (restype, argtypes)

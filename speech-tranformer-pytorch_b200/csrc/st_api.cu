@@ -85,7 +85,14 @@ struct MhaPlan {
   float *projq, *projk, *projv;
   int64_t ldpq, ldpk, ldpv;
   float *ctx, *lse, *z, *mean, *rstd, *w_r /*[3d,d] q,k,v*/, *b_pack /*[3d]*/, *wo_r;
+  bool pre_rounded;
 };
+
+bool mha_pre_rounded(const st_mha_args& a) {
+  const int64_t dd = static_cast<int64_t>(a.d_model) * a.d_model;
+  return a.wq_tf32 && a.wk_tf32 && a.wv_tf32 && a.wo_tf32 && a.wk_tf32 == a.wq_tf32 + dd && a.wv_tf32 == a.wk_tf32 + dd &&
+         a.bk == a.bq + a.d_model && a.bv == a.bk + a.d_model;
+}
 
 int64_t mha_saved_floats(int B, int Lq, int Lk, int H, int d, bool same_qkv, bool same_kv, bool inputs_tf32) {
   const int64_t M = static_cast<int64_t>(B) * Lq, Mk = static_cast<int64_t>(B) * Lk;
@@ -141,6 +148,12 @@ int plan_mha(const st_mha_args& a, MhaPlan& p) {
   p.w_r = c.take(3ll * d * d);
   p.b_pack = c.take(3 * d);
   p.wo_r = c.take(static_cast<int64_t>(d) * d);
+  p.pre_rounded = mha_pre_rounded(a);
+  if (p.pre_rounded) {   // caller-maintained TF32 weights, already packed: nothing to round, copy or save
+    p.w_r = const_cast<float*>(a.wq_tf32);
+    p.b_pack = const_cast<float*>(a.bq);
+    p.wo_r = const_cast<float*>(a.wo_tf32);
+  }
   if (!c.ok()) {
     set_error("st_mha: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
     return ST_ERR_WORKSPACE;
@@ -269,7 +282,7 @@ int st_sumsq(const float* x, int64_t n, float* out, cudaStream_t stream) { retur
 int st_adam_step(const st_adam_args* a, cudaStream_t stream) {
   ST_REQUIRE(a != nullptr, "st_adam_step: null args");
   return adam_step(stream, a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->n, a->lr, a->beta1, a->beta2, a->eps,
-                   a->step, a->max_grad_norm, a->grad_scale, a->norm_ws);
+                   a->step, a->max_grad_norm, a->grad_scale, a->norm_ws, a->param_tf32);
 }
 
 // ------------------------------------------------------------------ attention core
@@ -314,13 +327,15 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
   const int M = static_cast<int>(p.M), Mk = static_cast<int>(p.Mk);
 
   // 1. TF32 copies of the weights, packed [wq; wk; wv] so that shared inputs need one GEMM
-  ST_TRY(round_tf32_2d(s, a.wq, d, p.w_r, d, d, d));
-  ST_TRY(round_tf32_2d(s, a.wk, d, p.w_r + static_cast<int64_t>(d) * d, d, d, d));
-  ST_TRY(round_tf32_2d(s, a.wv, d, p.w_r + 2ll * d * d, d, d, d));
-  ST_TRY(round_tf32_2d(s, a.wo, d, p.wo_r, d, d, d));
-  ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack, a.bq, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + d, a.bk, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + 2 * d, a.bv, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (!p.pre_rounded) {
+    ST_TRY(round_tf32_2d(s, a.wq, d, p.w_r, d, d, d));
+    ST_TRY(round_tf32_2d(s, a.wk, d, p.w_r + static_cast<int64_t>(d) * d, d, d, d));
+    ST_TRY(round_tf32_2d(s, a.wv, d, p.w_r + 2ll * d * d, d, d, d));
+    ST_TRY(round_tf32_2d(s, a.wo, d, p.wo_r, d, d, d));
+    ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack, a.bq, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + d, a.bk, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + 2 * d, a.bv, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
   // 2. TF32 copies of the inputs
   if (!a.inputs_tf32) {
     ST_TRY(round_tf32_2d(s, a.q_in, d, p.xq_r, d, M, d));
@@ -471,6 +486,7 @@ int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
   p.rstd = c.take(a.rows);
   p.w1_r = c.take(static_cast<int64_t>(a.d_ff) * a.d_model);
   p.w2_r = c.take(static_cast<int64_t>(a.d_ff) * a.d_model);
+  if (a.w1_tf32 && a.w2_tf32) { p.w1_r = const_cast<float*>(a.w1_tf32); p.w2_r = const_cast<float*>(a.w2_tf32); }
   if (!c.ok()) {
     set_error("st_ffn: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
     return ST_ERR_WORKSPACE;
@@ -497,8 +513,10 @@ int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
   FfnPlan p;
   ST_TRY(plan_ffn(a, p));
   const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff;
-  ST_TRY(round_tf32_2d(s, a.w1, d, p.w1_r, d, f, d));
-  ST_TRY(round_tf32_2d(s, a.w2, f, p.w2_r, f, d, f));
+  if (!(a.w1_tf32 && a.w2_tf32)) {
+    ST_TRY(round_tf32_2d(s, a.w1, d, p.w1_r, d, f, d));
+    ST_TRY(round_tf32_2d(s, a.w2, f, p.w2_r, f, d, f));
+  }
   if (!a.x_is_tf32) ST_TRY(round_tf32_2d(s, a.x, d, p.x_r, d, M, d));
   // h = dropout1(relu(fc1(x)))                                           SubLayers.py:25
   GemmEpilogue e1;

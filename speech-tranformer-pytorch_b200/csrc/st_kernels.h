@@ -35,7 +35,7 @@ int embed_bwd(cudaStream_t stream, const int64_t* idx, const float* dout, float*
 // ---- st_optim.cu
 int sumsq_add(cudaStream_t s, const float* x, int64_t n, float* out);
 int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
-              float eps, int step, float max_norm, float gscale, const float* sumsq);
+              float eps, int step, float max_norm, float gscale, const float* sumsq, float* p_tf32 = nullptr);
 
 // ---- st_lsce.cu
 struct LsceArgs {

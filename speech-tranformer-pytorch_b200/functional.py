@@ -17,7 +17,7 @@ from ._lib import StError, check
 
 __all__ = ["add_layer_norm", "multi_head_attention", "positionwise_ffn", "label_smoothing_ce", "soft_target_ce",
            "attention_core", "linear_tf32", "round_tf32", "is_tf32_clean", "mark_tf32_clean", "next_seed",
-           "frontend", "linear", "embedding", "GradSink", "attach_grad_sink"]
+           "frontend", "linear", "embedding", "GradSink", "attach_grad_sink", "attach_tf32_twin"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -89,6 +89,25 @@ class GradSink:
 
 
 _SINK_ATTR = "_st_grad_sink"
+_TWIN_ATTR = "_st_tf32_twin"
+
+
+def attach_tf32_twin(param: torch.Tensor, view: torch.Tensor) -> None:
+    """Register a caller-maintained TF32-rounded copy of `param` (parallel.FlatParams keeps it current from inside the
+    Adam kernel).  The copy is used only while the parameter's version counter is unchanged, so any PyTorch-side
+    in-place modification (load_state_dict, init, ...) silently falls back to rounding the weight per call."""
+    setattr(param, _TWIN_ATTR, (view, param._version))
+
+
+def _twins_of(params):
+    """The params' TF32 twins if ALL of them have a current one, else None."""
+    out = []
+    for p in params:
+        tw = getattr(p, _TWIN_ATTR, None)
+        if tw is None or tw[1] != p._version or tw[0].shape != p.shape:
+            return None
+        out.append(tw[0])
+    return out
 
 
 def attach_grad_sink(param: torch.Tensor, view: torch.Tensor) -> GradSink:
@@ -317,13 +336,16 @@ class _MultiHeadAttention(torch.autograd.Function):
         saved = torch.empty(n_saved, device=qc.device, dtype=torch.float32)
         out = torch.empty(B, Lq, d, device=qc.device, dtype=torch.float32)
         attn = torch.empty(B, n_head, Lq, Lk, device=qc.device, dtype=torch.float32) if need_attn else None
+        twins = _twins_of((wq, wk, wv, wo)) or [None] * 4
         a = _lib.MhaArgs(B=B, Lq=Lq, Lk=Lk, H=n_head, d_model=d, dk=dk, q_in=_p(qc), k_in=_p(kc), v_in=_p(vc),
                          residual=_p(res), wq=_p(params[0]), bq=_p(params[1]), wk=_p(params[2]), bk=_p(params[3]),
                          wv=_p(params[4]), bv=_p(params[5]), wo=_p(params[6]), bo=_p(params[7]), ln_g=_p(params[8]),
                          ln_b=_p(params[9]), mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, eps=float(eps),
                          dropout_p=float(dropout_p), seed=int(seed), inputs_tf32=inputs_tf32, round_out=int(round_out),
-                         out=_p(out), attn=_p(attn), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
+                         out=_p(out), attn=_p(attn), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0,
+                         wq_tf32=_p(twins[0]), wk_tf32=_p(twins[1]), wv_tf32=_p(twins[2]), wo_tf32=_p(twins[3]))
         check(lib.st_mha_fwd(C.byref(a), _stream()))
+        ctx.twins = twins          # backward must present the same weight copies the forward used
         ctx.save_for_backward(qc, kc, vc, mask_t, saved, *params)
         ctx.sinks = _sinks_of((wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b))
         ctx.cfg = (B, Lq, Lk, n_head, d, dk, residual, float(eps), float(dropout_p), int(seed), inputs_tf32,
@@ -363,7 +385,8 @@ class _MultiHeadAttention(torch.autograd.Function):
                          wv=_p(params[4]), bv=_p(params[5]), wo=_p(params[6]), bo=_p(params[7]), ln_g=_p(params[8]),
                          ln_b=_p(params[9]), mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, eps=eps, dropout_p=p,
                          seed=seed, inputs_tf32=inputs_tf32, round_out=0, out=None, attn=None, saved=_p(saved),
-                         saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws)
+                         saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws, wq_tf32=_p(ctx.twins[0]),
+                         wk_tf32=_p(ctx.twins[1]), wv_tf32=_p(ctx.twins[2]), wo_tf32=_p(ctx.twins[3]))
         a = _lib.MhaBwdArgs(f=f, dout=_p(dout), dq_in=_p(dq_in), dk_in=_p(dk_in), dv_in=_p(dv_in), dresidual=None,
                             dwq=_p(grads[0]), dbq=_p(grads[1]), dwk=_p(grads[2]), dbk=_p(grads[3]), dwv=_p(grads[4]),
                             dbv=_p(grads[5]), dwo=_p(grads[6]), dbo=_p(grads[7]), dln_g=_p(grads[8]),
@@ -404,11 +427,14 @@ class _PositionwiseFFN(torch.autograd.Function):
         n_saved = lib.st_ffn_saved_floats(rows, d, d_ff, x_clean)
         saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
         out = torch.empty_like(xc)
+        twins = _twins_of((w1, w2)) or [None] * 2
         a = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(xc), w1=_p(params[0]), b1=_p(params[1]),
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=float(eps),
                          dropout_p=float(dropout_p), seed=int(seed), x_is_tf32=x_clean, round_out=int(round_out),
-                         out=_p(out), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
+                         out=_p(out), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0,
+                         w1_tf32=_p(twins[0]), w2_tf32=_p(twins[1]))
         check(lib.st_ffn_fwd(C.byref(a), _stream()))
+        ctx.twins = twins
         ctx.save_for_backward(xc, saved, *params)
         ctx.sinks = _sinks_of((w1, b1, w2, b2, ln_g, ln_b))
         ctx.cfg = (rows, d, d_ff, float(eps), float(dropout_p), int(seed), x_clean)
@@ -433,7 +459,8 @@ class _PositionwiseFFN(torch.autograd.Function):
         f = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(xc), w1=_p(params[0]), b1=_p(params[1]),
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=eps,
                          dropout_p=p, seed=seed, x_is_tf32=x_clean, round_out=0, out=None, saved=_p(saved),
-                         saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws)
+                         saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws, w1_tf32=_p(ctx.twins[0]),
+                         w2_tf32=_p(ctx.twins[1]))
         a = _lib.FfnBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw1=_p(grads[0]), db1=_p(grads[1]), dw2=_p(grads[2]),
                             db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]))
         check(lib.st_ffn_bwd(C.byref(a), _stream()))

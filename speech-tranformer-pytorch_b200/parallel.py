@@ -73,6 +73,23 @@ class FlatParams:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
         from .functional import attach_grad_sink
         self.sinks = [attach_grad_sink(p, p.grad) for p in self.params]
+        # TF32-rounded twin of the whole parameter buffer: the fused Adam kernel rewrites it every step, so the
+        # attention / FFN operators never round (or re-pack) a weight matrix themselves
+        self.flat_tf32 = torch.empty_like(self.flat) if self.flat.is_cuda else None
+        self.refresh_rounded()
+
+    def refresh_rounded(self) -> None:
+        """Recompute the TF32 twins from the fp32 parameters (after a broadcast, load_state_dict, manual edits)."""
+        if self.flat_tf32 is None:
+            return
+        from . import _lib
+        from .functional import _stream, attach_tf32_twin
+        lib = _lib.load()
+        _lib.check(lib.st_round_tf32(self.flat.data_ptr(), self.numel, self.flat_tf32.data_ptr(), self.numel, 1, self.numel,
+                                     _stream()))
+        for p, o in zip(self.params, self.offsets):
+            if p.dim() >= 2:
+                attach_tf32_twin(p, self.flat_tf32[o:o + p.numel()].view_as(p))
 
     def zero_grad(self) -> None:
         self.grad.zero_()                                # one memset; direct writers overwrite, autograd accumulates
@@ -104,6 +121,7 @@ class DataParallelTrainer:
     def broadcast_parameters(self, src: int = 0) -> None:
         if self.world > 1:
             dist.broadcast(self.fp.flat, src=src, group=self.group)
+            self.fp.refresh_rounded()
 
     def zero_grad(self) -> None:
         self.fp.zero_grad()
@@ -128,7 +146,8 @@ class DataParallelTrainer:
         a = _lib.AdamArgs(param=self.fp.flat.data_ptr(), grad=g.data_ptr(), exp_avg=self.exp_avg.data_ptr(),
                           exp_avg_sq=self.exp_avg_sq.data_ptr(), n=g.numel(), lr=self.lr, beta1=self.betas[0],
                           beta2=self.betas[1], eps=self.eps, step=self.global_step, max_grad_norm=self.max_grad_norm,
-                          grad_scale=1.0 / self.world, norm_ws=self.norm_ws.data_ptr())
+                          grad_scale=1.0 / self.world, norm_ws=self.norm_ws.data_ptr(),
+                          param_tf32=None if self.fp.flat_tf32 is None else self.fp.flat_tf32.data_ptr())
         _lib.check(lib.st_adam_step(C.byref(a), s))
 
     def train_step(self, loss_fn) -> torch.Tensor:
