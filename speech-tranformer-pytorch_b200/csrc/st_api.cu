@@ -401,6 +401,7 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
     else { dpk = w.take(p.Mk * d); dpv = w.take(p.Mk * d); }
   }
   float* delta = w.take(static_cast<int64_t>(a.B) * a.H * a.Lq);
+  const bool fused_bias = attn_bwd_fuses_bias(a.dk);
 
   // LayerNorm backward; dbo = column sums of dz
   ST_CHECK_CUDA(cudaMemsetAsync(b.dln_g, 0, d * sizeof(float), s));
@@ -425,6 +426,12 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
     at.ctx = p.ctx; at.ldctx = d; at.lse = p.lse; at.attn = nullptr;
     ab.dctx = dctx; ab.lddctx = d; ab.delta = delta;
     ab.dq = dpq; ab.lddq = p.ldpq; ab.dk_ = dpk; ab.lddk = p.ldpk; ab.dv = dpv; ab.lddv = p.ldpv;
+    if (fused_bias) {   // dbq / dbk / dbv = column sums of dq / dk / dv, accumulated by the kernels' epilogues
+      ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, d * sizeof(float), s));
+      ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, d * sizeof(float), s));
+      ST_CHECK_CUDA(cudaMemsetAsync(b.dbv, 0, d * sizeof(float), s));
+      ab.dbq = b.dbq; ab.dbk = b.dbk; ab.dbv = b.dbv;
+    }
     ST_TRY(attn_bwd(s, ab));
   }
   // projection bias / weight gradients.  When the caller hands out dW / db as slices of one packed [wq; wk; wv]
@@ -433,22 +440,30 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   const bool pack_kv = p.same_kv && b.dwv == b.dwk + dd && b.dbv == b.dbk + d;
   const bool pack_qkv = p.same_qkv && pack_kv && b.dwk == b.dwq + dd && b.dbk == b.dbq + d;
   if (pack_qkv) {
-    ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, 3 * d * sizeof(float), s));
-    ST_TRY(colsum_add(s, dpq, p.ldpq, M, 3 * d, b.dbq));
+    if (!fused_bias) {
+      ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, 3 * d * sizeof(float), s));
+      ST_TRY(colsum_add(s, dpq, p.ldpq, M, 3 * d, b.dbq));
+    }
     ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d));
   } else {
-    ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, d * sizeof(float), s));
-    ST_TRY(colsum_add(s, dpq, p.ldpq, M, d, b.dbq));
+    if (!fused_bias) {
+      ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, d * sizeof(float), s));
+      ST_TRY(colsum_add(s, dpq, p.ldpq, M, d, b.dbq));
+    }
     ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d));
     if (pack_kv) {
-      ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, 2 * d * sizeof(float), s));
-      ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, 2 * d, b.dbk));
+      if (!fused_bias) {
+        ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, 2 * d * sizeof(float), s));
+        ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, 2 * d, b.dbk));
+      }
       ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d));
     } else {
-      ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, d * sizeof(float), s));
-      ST_CHECK_CUDA(cudaMemsetAsync(b.dbv, 0, d * sizeof(float), s));
-      ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, d, b.dbk));
-      ST_TRY(colsum_add(s, dpv, p.ldpv, Mk, d, b.dbv));
+      if (!fused_bias) {
+        ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, d * sizeof(float), s));
+        ST_CHECK_CUDA(cudaMemsetAsync(b.dbv, 0, d * sizeof(float), s));
+        ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, d, b.dbk));
+        ST_TRY(colsum_add(s, dpv, p.ldpv, Mk, d, b.dbv));
+      }
       ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d));
       ST_TRY(wgrad(s, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d));
     }
@@ -554,9 +569,9 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   GemmEpilogue e;
   e.aux = p.h; e.ldaux = f; e.aux_mode = 2; e.round_tf32 = 1;
   e.aux_scale = make_dropout(a.dropout_p, 0).scale;
+  e.colsum = b.db1;   // db1 = column sums of dh, accumulated by the epilogue that produces dh
   ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.w2_r, f, dh, f, M, f, d, e));
   ST_TRY(wgrad(s, dz, d, p.h, f, b.dw2, M, d, f));
-  ST_TRY(colsum_add(s, dh, f, M, f, b.db1));
   ST_TRY(wgrad(s, dh, f, p.x_r, d, b.dw1, M, f, d));
   GemmEpilogue ex;
   ex.aux = dz; ex.ldaux = d; ex.aux_mode = 1;

@@ -752,6 +752,11 @@ int check_attn(const AttnArgs& a, const char* who) {
   return ST_OK;
 }
 
+// Measured on B200 (6+6 x 512, B=32, T=1000): accumulating the bias column sums from the dK/dV and dQ epilogues costs more
+// (same-address L2 reductions from 2048 CTAs: dkv +14 %, dq +5 %) than the separate 35 us column-sum pass it replaces,
+// so it is opt-in (option "attn_fuse_bias"); the GEMM-epilogue fusion of the FFN bias gradient is always on.
+bool attn_bwd_fuses_bias(int dk) { return get_option("attn_fuse_bias") && dk <= 64 && !get_option("attn_bwd_simple"); }
+
 AttnDev attn_to_dev(const AttnArgs& a) {
   AttnDev p{};
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk;
@@ -788,6 +793,7 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
   const int cols = f.H * DK;
   AttnDev p = attn_to_dev(f);
   p.trace = get_option("attn_trace");
+  p.dbq = a.dbq; p.dbk = a.dbk; p.dbv = a.dbv;
   p.delta = a.delta; p.dq = a.dq; p.lddq = a.lddq; p.dk = a.dk_; p.lddk = a.lddk; p.dv = a.dv; p.lddv = a.lddv;
   {
     const int64_t rows = static_cast<int64_t>(f.B) * f.Lq;

@@ -26,6 +26,7 @@ struct AttnDev {
   float* dq; int64_t lddq;
   float* dk; int64_t lddk;
   float* dv; int64_t lddv;
+  float* dbq; float* dbk; float* dbv;   // optional [H*dk]: column sums of dq / dk / dv ACCUMULATED here (projection bias gradients)
   int trace;          // debug: record the pipeline timeline of CTA (0,0,0) (option "attn_trace")
 };
 

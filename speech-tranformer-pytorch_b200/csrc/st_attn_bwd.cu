@@ -92,6 +92,16 @@ __device__ __forceinline__ void dkv16_t(uint32_t (&rs)[16], uint32_t (&rd)[16], 
   }
 }
 
+// Column sums of a 128-row output tile (this thread: one row, 16 consecutive columns) added to out[0..16): the bias
+// gradient of the projection that produced the attention input.  Epilogue only (once per CTA).
+__device__ __forceinline__ void bias_colsum16(const float (&v)[16], float* out, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float s = warp_sum(v[i]);
+    if (lane == i) atomicAdd(out + i, s);
+  }
+}
+
 // Resident tiles -> TMEM: compute slice `slice` (0..3) owns one 32-column chunk of one of the two resident tensors
 // (x0 at columns [t_x0, t_x0+DK), x1 at [t_x1, ...)); the thread writes its row's 32 floats (zeros for rows >= L).
 template <int DK>
@@ -288,14 +298,16 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
       uint32_t r[16];
       tmem_ld16(t_lane + T_DQ + col0, r);
       tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = row_ok ? __uint_as_float(r[i]) * p.scale : 0.f;
       if (row_ok) {
         float* dst = p.dq + (static_cast<int64_t>(b) * p.Lq + row) * p.lddq + h * DK + col0;
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(dst + i) =
-              make_float4(tf32_rna(__uint_as_float(r[i]) * p.scale), tf32_rna(__uint_as_float(r[i + 1]) * p.scale),
-                          tf32_rna(__uint_as_float(r[i + 2]) * p.scale), tf32_rna(__uint_as_float(r[i + 3]) * p.scale));
+          *reinterpret_cast<float4*>(dst + i) = make_float4(tf32_rna(v[i]), tf32_rna(v[i + 1]), tf32_rna(v[i + 2]), tf32_rna(v[i + 3]));
       }
+      if (p.dbq) bias_colsum16(v, p.dbq + h * DK + col0, lane);
     }
   }
   tc_fence_before();
@@ -508,19 +520,23 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
       tmem_ld16(t_lane + T_DV + col0, rv);
       tmem_ld16(t_lane + T_DK + col0, rk);
       tmem_ld_wait();
+      float vv[16], vk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        vv[i] = key_ok ? __uint_as_float(rv[i]) * dscale : 0.f;
+        vk[i] = key_ok ? __uint_as_float(rk[i]) * p.scale : 0.f;
+      }
       if (key_ok) {
         float* dvp = p.dv + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + col0;
         float* dkp = p.dk + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + col0;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          *reinterpret_cast<float4*>(dvp + i) =
-              make_float4(tf32_rna(__uint_as_float(rv[i]) * dscale), tf32_rna(__uint_as_float(rv[i + 1]) * dscale),
-                          tf32_rna(__uint_as_float(rv[i + 2]) * dscale), tf32_rna(__uint_as_float(rv[i + 3]) * dscale));
-          *reinterpret_cast<float4*>(dkp + i) =
-              make_float4(tf32_rna(__uint_as_float(rk[i]) * p.scale), tf32_rna(__uint_as_float(rk[i + 1]) * p.scale),
-                          tf32_rna(__uint_as_float(rk[i + 2]) * p.scale), tf32_rna(__uint_as_float(rk[i + 3]) * p.scale));
+          *reinterpret_cast<float4*>(dvp + i) = make_float4(tf32_rna(vv[i]), tf32_rna(vv[i + 1]), tf32_rna(vv[i + 2]), tf32_rna(vv[i + 3]));
+          *reinterpret_cast<float4*>(dkp + i) = make_float4(tf32_rna(vk[i]), tf32_rna(vk[i + 1]), tf32_rna(vk[i + 2]), tf32_rna(vk[i + 3]));
         }
       }
+      if (p.dbv) bias_colsum16(vv, p.dbv + h * DK + col0, lane);
+      if (p.dbk) bias_colsum16(vk, p.dbk + h * DK + col0, lane);
     }
   }
   tc_fence_before();

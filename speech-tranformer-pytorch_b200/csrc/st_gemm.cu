@@ -25,6 +25,7 @@
 // 128-byte row segments per instruction (bias and residual loads are coalesced the same way).
 #include "st_common.cuh"
 #include "st_gemm.cuh"
+#include "st_kernels.h"
 #include "st_host.h"
 
 namespace st {
@@ -131,10 +132,12 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
     for (int i = 0; i < 8; ++i) keys[i] = dropout_row_key(ep.drop_seed, static_cast<uint64_t>(row0 + 4 * i));
   }
   const int n_chunks = min(BN / 32, (p.N - n_blk * BN + 31) >> 5);
+  const bool do_colsum = ep.colsum != nullptr;
 #pragma unroll 1
   for (int c = half; c < n_chunks; c += EPI_WARPS / 4) {
     const int col = col0 + c * 32;
     const bool col_ok = col < p.N;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
     // residual / ReLU-mask operand and bias: issue the loads first, their latency hides behind the TMEM read and
     // the smem transpose
     float4 aux4[8];
@@ -180,6 +183,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
           v[2] = aux4[i].z > 0.f ? v[2] * ep.aux_scale : 0.f;
           v[3] = aux4[i].w > 0.f ? v[3] * ep.aux_scale : 0.f;
         }
+        cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
         if (ROUND) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) v[t] = tf32_rna(v[t]);
@@ -191,6 +195,14 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
           *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
+    }
+    if (do_colsum) {   // warp-uniform: the 4 lanes that share these columns (lane >> 3 = 0..3) combine, then one vector reduction
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], 8);
+        cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], 16);
+      }
+      if (lane < 8 && col_ok) red_add_v4(ep.colsum + col, cs[0], cs[1], cs[2], cs[3]);
     }
     __syncwarp();
   }
@@ -753,6 +765,14 @@ int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, c
   p.n_tiles = (N + BN - 1) / BN;
   p.ep = ep;
   p.flavour = pick_flavour(ep, C, ldc, N);
+  float* deferred_colsum = nullptr;
+  if (ep.colsum && (p.flavour == EPI_GENERIC || p.flavour == EPI_ATOMIC || (reinterpret_cast<uintptr_t>(ep.colsum) & 15))) {
+    deferred_colsum = ep.colsum;   // the generic epilogue has no fused column sums: separate pass below
+    p.ep.colsum = nullptr;
+  }
+  if (deferred_colsum) {
+    ST_REQUIRE(k_splits == 1 && !ep.atomic, "gemm_tf32: column sums of a split-K output are not supported");
+  }
   // Variant: 0 = independent CTAs, 2 = 2-CTA cluster with multicast B (opt-in: measured slower), 3 = CTA-pair MMA.
   // The pair MMA is used when the grid is full anyway (>= 2 tiles per SM): then bytes per SM, not latency, limit.
   int variant = 0;
@@ -779,18 +799,22 @@ int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, c
     else                 { dims[0] = N; dims[1] = K; box[0] = 32; box[1] = 32; }
     ST_TRY(make_tmap_f32(&tb, B, 2, dims, strides, box, (mode != GEMM_NT) ? 1 : 0));
   }
+  int status = ST_ERR_INVALID;
   if (variant == 3) {
     switch (mode) {
-      case GEMM_NT: return launch_gemm_2sm<false, false>(stream, ta, tb, p);
-      case GEMM_NN: return launch_gemm_2sm<false, true>(stream, ta, tb, p);
-      case GEMM_TN: return launch_gemm_2sm<true, true>(stream, ta, tb, p);
+      case GEMM_NT: status = launch_gemm_2sm<false, false>(stream, ta, tb, p); break;
+      case GEMM_NN: status = launch_gemm_2sm<false, true>(stream, ta, tb, p); break;
+      case GEMM_TN: status = launch_gemm_2sm<true, true>(stream, ta, tb, p); break;
+    }
+  } else {
+    switch (BN) {
+      case 256: status = variant == 2 ? dispatch_mode<256, 2>(stream, mode, ta, tb, p) : dispatch_mode<256, 1>(stream, mode, ta, tb, p); break;
+      case 128: status = dispatch_mode<128, 1>(stream, mode, ta, tb, p); break;
+      default:  status = dispatch_mode<64, 1>(stream, mode, ta, tb, p); break;
     }
   }
-  switch (BN) {
-    case 256: return variant == 2 ? dispatch_mode<256, 2>(stream, mode, ta, tb, p) : dispatch_mode<256, 1>(stream, mode, ta, tb, p);
-    case 128: return dispatch_mode<128, 1>(stream, mode, ta, tb, p);
-    default:  return dispatch_mode<64, 1>(stream, mode, ta, tb, p);
-  }
+  if (status == ST_OK && deferred_colsum) status = colsum_add(stream, C, ldc, M, N, deferred_colsum);
+  return status;
 }
 
 }  // namespace st

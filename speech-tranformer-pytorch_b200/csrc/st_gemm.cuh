@@ -25,6 +25,9 @@ struct GemmEpilogue {
   uint32_t drop_thresh = 0;
   float drop_scale = 1.f;
   uint64_t drop_seed = 0;
+  // optional [N]: column sums of the stored values are ACCUMULATED here (caller zeroes) — the bias gradient of the
+  // layer whose input gradient this GEMM produces, for free instead of a separate pass over the output
+  float* colsum = nullptr;
 };
 
 // k_splits > 1 requires ep.atomic and a zero-initialised C.

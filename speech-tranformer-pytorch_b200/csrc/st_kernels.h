@@ -80,7 +80,11 @@ struct AttnBwdArgs {
   float* dq; int64_t lddq;       // same indexing as q/k/v
   float* dk_; int64_t lddk;
   float* dv; int64_t lddv;
+  // optional [H*dk] each: column sums of dq / dk / dv are ACCUMULATED here (bias gradients of the Q/K/V projections,
+  // Attention.py:74-76); honoured by the pipelined kernels (d_k <= 64) — attn_bwd_fuses_bias() tells the caller
+  float* dbq = nullptr; float* dbk = nullptr; float* dbv = nullptr;
 };
+bool attn_bwd_fuses_bias(int dk);
 int attn_bwd(cudaStream_t stream, const AttnBwdArgs& a);
 
 }  // namespace st

@@ -255,6 +255,7 @@ def add_layer_norm(a, b, gamma, beta, eps: float = 1e-6, dropout_p: float = 0.0,
 class _AttentionCore(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, mask, n_head, dropout_p, seed, need_attn):
+        ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
         q, k, v = (_contig(_need(t, n)) for t, n in ((q, "q"), (k, "k"), (v, "v")))
         lib = _lib_for(q)
         B, Lq, d = q.shape
@@ -278,6 +279,8 @@ class _AttentionCore(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dattn):
+        if dout is None:      # only the auxiliary output was used downstream: no gradient flows
+            return (None,) * 8
         qr, kr, vr, out, lse, mask_t = ctx.saved_tensors
         B, H, Lq, Lk, dk, p, seed = ctx.cfg
         d = H * dk
@@ -310,6 +313,7 @@ class _MultiHeadAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, mask, wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b, n_head, residual, eps, dropout_p,
                 seed, need_attn, round_out):
+        ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
         q, k, v = (_need(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v")))
         same_qk, same_kv = _same(q, k), _same(k, v)
         qc = _contig(q)
@@ -358,6 +362,8 @@ class _MultiHeadAttention(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dattn):
+        if dout is None:      # only the auxiliary output was used downstream: no gradient flows
+            return (None,) * 21
         qc, kc, vc, mask_t, saved, *params = ctx.saved_tensors
         B, Lq, Lk, H, d, dk, residual, eps, p, seed, inputs_tf32, same_qk, same_kv = ctx.cfg
         lib = _lib_for(qc)
@@ -417,6 +423,7 @@ def multi_head_attention(q, k, v, mask, wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln
 class _PositionwiseFFN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, ln_g, ln_b, eps, dropout_p, seed, round_out):
+        ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
         x_clean = int(is_tf32_clean(x))
         xc = _contig(_need(x, "inputs"))
         lib = _lib_for(xc)
@@ -447,6 +454,8 @@ class _PositionwiseFFN(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dhidden):
+        if dout is None:      # only the auxiliary output was used downstream: no gradient flows
+            return (None,) * 11
         xc, saved, *params = ctx.saved_tensors
         rows, d, d_ff, eps, p, seed, x_clean = ctx.cfg
         lib = _lib_for(xc)
@@ -552,6 +561,7 @@ def soft_target_ce(logits, q, weight, size_average: bool = True):
 class _Frontend(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, ln_g, ln_b, pe, eps, dropout_p, seed, round_out):
+        ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
         xc = _contig(_need(x, "inputs"))
         if xc.dim() != 3:
             raise RuntimeError("frontend: inputs must be (batch, frames, feature_dim)")
@@ -586,6 +596,8 @@ class _Frontend(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dhidden):
+        if dout is None:      # only the auxiliary output was used downstream: no gradient flows
+            return (None,) * 10
         xc, saved, pe, *params = ctx.saved_tensors
         rows, T, k, d, eps, p, seed = ctx.cfg
         lib = _lib_for(xc)

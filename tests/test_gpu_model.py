@@ -210,14 +210,15 @@ def test_grad_sinks_equal_autograd_path(stb):
     crit(net(*batch)[0].view(-1, V), truth).backward()
     assert all(s.written for s in tr.fp.sinks), "every parameter gradient should have been written directly"
     for k, p in net.named_parameters():
-        assert p.grad.data_ptr() >= tr.fp.grad.data_ptr() and relerr(p.grad, want[k]) < 1e-6, k
+        # 1e-5: bias gradients are accumulated with fp32 reductions whose order varies from run to run
+        assert p.grad.data_ptr() >= tr.fp.grad.data_ptr() and relerr(p.grad, want[k]) < 1e-5, k
     # packed [Wq; Wk; Wv] layout inside the flat buffer
     a = net.encoder.layer_stack[0].slf_attn
     assert a.linear_k.weight.grad.data_ptr() == a.linear_q.weight.grad.data_ptr() + 4 * a.linear_q.weight.numel()
     # second backward without zero_grad: sinks are spent, autograd accumulates -> exactly twice the gradient
     crit(net(*batch)[0].view(-1, V), truth).backward()
     for k, p in net.named_parameters():
-        assert relerr(p.grad, 2 * want[k]) < 1e-6, k
+        assert relerr(p.grad, 2 * want[k]) < 1e-5, k
     tr.zero_grad()
     assert float(tr.fp.grad.abs().max()) == 0.0 and not any(s.written for s in tr.fp.sinks)
 
