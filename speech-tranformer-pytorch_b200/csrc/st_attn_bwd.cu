@@ -36,6 +36,20 @@ __device__ unsigned long long g_trace[2 * TRACE_TILES * TRACE_EVENTS];
     if (trace_on && (tile) < TRACE_TILES) g_trace[((role) * TRACE_TILES + (tile)) * TRACE_EVENTS + (ev)] = clock64(); \
   } while (0)
 
+// per-CTA wall-clock record of the dK/dV kernel (option "attn_trace"): {globaltimer at entry, at exit, SM id, main-loop cycles}
+constexpr int TRACE_CTAS = 4096;
+__device__ unsigned long long g_cta_trace[TRACE_CTAS * 4];
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ uint32_t sm_id() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+  return r;
+}
+
 constexpr int BT = 64;                 // streamed tile height
 constexpr int NCOMP = 512;             // compute threads
 constexpr int NTHREADS = NCOMP + 64;   // + producer warp + MMA warp
@@ -346,6 +360,8 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
   const int n_q = (p.Lq + BT - 1) / BT;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (p.trace && tid == 0 && cta_lin < TRACE_CTAS) { g_cta_trace[cta_lin * 4] = global_ns(); g_cta_trace[cta_lin * 4 + 2] = sm_id(); }
   const bool trace_on = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
   if (tid == 0) {
@@ -449,8 +465,11 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
       tc_fence_after();
       issue_a(0);
       for (int t = 0; t < n_q; ++t) {
+        if (t < 8) ST_TRACE(0, 16 + t, 0);
         if (t + 1 < n_q) issue_a(t + 1);
+        if (t < 8) ST_TRACE(0, 16 + t, 1);
         issue_b(t);
+        if (t < 8) ST_TRACE(0, 16 + t, 2);
       }
       if (elect_one()) umma_commit(&acc_full);
     }
@@ -539,6 +558,7 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
       if (p.dbk) bias_colsum16(vk, p.dbk + h * DK + col0, lane);
     }
   }
+  if (p.trace && tid == 0 && cta_lin < TRACE_CTAS) g_cta_trace[cta_lin * 4 + 1] = global_ns();
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
@@ -603,6 +623,10 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
 int attn_read_trace(unsigned long long* host_out, int n) {
   const int total = 2 * TRACE_TILES * TRACE_EVENTS;
   ST_CHECK_CUDA(cudaDeviceSynchronize());
+  if (n > total) {   // the per-CTA records follow the tile timeline
+    const int extra = n - total < TRACE_CTAS * 4 ? n - total : TRACE_CTAS * 4;
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(host_out + total, g_cta_trace, sizeof(unsigned long long) * extra));
+  }
   ST_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * (n < total ? n : total)));
   return total;
 }

@@ -27,8 +27,28 @@ print("MMA warp : tile | A: wait ld_full start, ld_full ok, A issued+commit | B:
 for t in range(16):
     r = [buf[(0 * TT + t) * EV + e] - t0 for e in range(EV)]
     print(f"  {t:2d} | {r[0]:7d} {r[1]:7d} {r[2]:7d} | {r[3]:7d} {r[4]:7d} {r[5]:7d}")
+print("MMA warp loop: t | loop top, after issue_a(t+1), after issue_b(t)")
+for t in range(8):
+    r = [buf[(0 * TT + 16 + t) * EV + e] - t0 for e in range(3)]
+    print(f"  {t:2d} | {r[0]:7d} {r[1]:7d} {r[2]:7d}")
 print("compute thread 0: tile | wait s_full start, s_full ok, tmem ld done, math done, tmem st done, arrived")
 prev = None
 for t in range(16):
     r = [buf[(1 * TT + t) * EV + e] - t0 for e in range(EV)]
     print(f"  {t:2d} | {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} {r[4]:7d} {r[5]:7d}   wait {r[1]-r[0]:5d} ld {r[2]-r[1]:5d} math {r[3]-r[2]:5d} st {r[4]-r[3]:5d}")
+# ---- per-CTA wall clock: duration of every CTA and idle gaps per SM
+NC = 2048
+big = (C.c_uint64 * (2 * TT * EV + NC * 4))()
+lib.st_debug_read_trace(big, 2 * TT * EV + NC * 4)
+recs = [(big[2 * TT * EV + 4 * i], big[2 * TT * EV + 4 * i + 1], big[2 * TT * EV + 4 * i + 2]) for i in range(NC)]
+recs = [r for r in recs if r[0] and r[1]]
+g0 = min(r[0] for r in recs)
+durs = sorted(r[1] - r[0] for r in recs)
+print(f"CTAs {len(recs)}  duration ns: min {durs[0]} median {durs[len(durs)//2]} p90 {durs[int(.9*len(durs))]} max {durs[-1]}  kernel span {max(r[1] for r in recs) - g0} ns")
+by = {}
+for s_, e_, sm in recs: by.setdefault(sm, []).append((s_ - g0, e_ - g0))
+sm0 = sorted(by)[0]
+seq = sorted(by[sm0])
+print(f"SM {sm0}: {len(seq)} CTAs:", [(a, b - a) for a, b in seq][:16])
+gaps = [seq[i + 1][0] - seq[i][1] for i in range(len(seq) - 1)]
+print("gaps between consecutive CTAs on that SM (ns):", gaps)
