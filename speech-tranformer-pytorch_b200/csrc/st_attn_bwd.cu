@@ -21,6 +21,8 @@
 // The kernels are bound by the bytes streamed into each SM (K-major + MN-major copies of every streamed tile);
 // the deep ring keeps those loads in flight behind the MMAs and the softmax arithmetic.
 // TMEM (512 columns): 2 x (64 + 64) double-buffered S/dP pair, the fp32 gradient accumulators, the resident tiles.
+#include <utility>
+
 #include "st_attn.cuh"
 
 namespace st {
@@ -49,6 +51,16 @@ __device__ __forceinline__ uint32_t sm_id() {
   asm volatile("mov.u32 %0, %smid;" : "=r"(r));
   return r;
 }
+
+// compile-time loop: f(IC<0>{}), f(IC<1>{}), ... — the MMA-issuer loops are unrolled over lcm(ring stages, 2) tiles so that
+// the ring stage and the TMEM buffer of every phase are compile-time constants: descriptors and barrier addresses become
+// `base + constant`, which keeps the issuing warp's instruction count (it shares a scheduler with four compute warps that
+// saturate it) to a few dozen per phase instead of ~150.
+template <int V> struct IC { static constexpr int value = V; };
+template <class F, int... I>
+__device__ __forceinline__ void cfor_impl(F& f, std::integer_sequence<int, I...>) { (f(IC<I>{}), ...); }
+template <int N, class F>
+__device__ __forceinline__ void cfor(F& f) { cfor_impl(f, std::make_integer_sequence<int, N>{}); }
 
 constexpr int BT = 64;                 // streamed tile height
 constexpr int NCOMP = 512;             // compute threads
@@ -217,49 +229,59 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
       const uint32_t st0 = smem_u32(sStage);
       const uint32_t rq = smem_u32(sRes), rdo = rq + RES_BYTES;
       auto koff = [](int ks, int rows) { return static_cast<uint64_t>(((ks / 4) * (rows * 128) + (ks % 4) * 32) >> 4); };
-      auto issue_a = [&](int t) {   // S(t) = Q K^T, dP(t) = dO V^T   (A = resident tile, B K-major)
-        const int s = t % STAGES, tb = t & 1;
-        mbar_wait(&ld_full[s], (t / STAGES) & 1);
+      constexpr int U = (STAGES % 2 == 0) ? STAGES : 2 * STAGES;   // tiles per unrolled round: stage and buffer indices are constants
+      const uint64_t dk0 = umma_desc_kmajor(st0), dkm0 = umma_desc_mnmajor(st0 + T_BYTES, BT * 128), dv0 = umma_desc_kmajor(st0 + 2 * T_BYTES);
+      const uint64_t aq0 = umma_desc_kmajor(rq), ado0 = umma_desc_kmajor(rdo);
+      auto issue_a = [&](uint32_t ld_parity, auto S, auto TB) {   // S(t) = Q K^T, dP(t) = dO V^T   (A = resident tile, B K-major)
+        constexpr int s = decltype(S)::value, tb = decltype(TB)::value;
+        mbar_wait(&ld_full[s], ld_parity);
         tc_fence_after();
         if (elect_one()) {
           constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
-          const uint64_t bk0 = umma_desc_kmajor(st0 + s * STAGE_BYTES), bv0 = umma_desc_kmajor(st0 + s * STAGE_BYTES + 2 * T_BYTES);
-          const uint64_t aq0 = umma_desc_kmajor(rq), ado0 = umma_desc_kmajor(rdo);
+          constexpr uint64_t so = static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
 #pragma unroll
           for (int ks = 0; ks < DK / 8; ++ks) {
-            if (RS) umma_tf32_ss(tmem + T_S + tb * BT, aq0 + koff(ks, BQ), bk0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
-            else umma_tf32_ts(tmem + T_S + tb * BT, tmem + T_Q + ks * 8, bk0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            if (RS) umma_tf32_ss(tmem + T_S + tb * BT, aq0 + koff(ks, BQ), dk0 + so + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            else umma_tf32_ts(tmem + T_S + tb * BT, tmem + T_Q + ks * 8, dk0 + so + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
           }
 #pragma unroll
           for (int ks = 0; ks < DK / 8; ++ks) {
-            if (RS) umma_tf32_ss(tmem + T_DP + tb * BT, ado0 + koff(ks, BQ), bv0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
-            else umma_tf32_ts(tmem + T_DP + tb * BT, tmem + T_DO + ks * 8, bv0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            if (RS) umma_tf32_ss(tmem + T_DP + tb * BT, ado0 + koff(ks, BQ), dv0 + so + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            else umma_tf32_ts(tmem + T_DP + tb * BT, tmem + T_DO + ks * 8, dv0 + so + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
           }
           umma_commit(&s_full[tb]);
         }
         __syncwarp();
       };
-      auto issue_b = [&](int t) {   // dQ += dS(t) K(t)   (A = dS in TMEM, B = K MN-major)
-        const int s = t % STAGES, tb = t & 1;
-        mbar_wait(&ds_full[tb], (t >> 1) & 1);
+      auto issue_b = [&](uint32_t ds_parity, bool first, auto S, auto TB) {   // dQ += dS(t) K(t)   (A = dS in TMEM, B = K MN-major)
+        constexpr int s = decltype(S)::value, tb = decltype(TB)::value;
+        mbar_wait(&ds_full[tb], ds_parity);
         tc_fence_after();
         if (elect_one()) {
           constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
-          const uint64_t bkm0 = umma_desc_mnmajor(st0 + s * STAGE_BYTES + T_BYTES, BT * 128);
+          constexpr uint64_t so = static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
 #pragma unroll
           for (int ks = 0; ks < BT / 8; ++ks)
-            umma_tf32_ts(tmem + T_DQ, tmem + T_DP + tb * BT + ks * 8, bkm0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
-                         (t > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32_ts(tmem + T_DQ, tmem + T_DP + tb * BT + ks * 8, dkm0 + so + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+                         (!first || ks > 0) ? 1u : 0u);
           umma_commit(&ld_empty[s]);   // stage s free once everything issued so far has retired
         }
         __syncwarp();
       };
       mbar_wait(&res_ready, 0);
       tc_fence_after();
-      issue_a(0);
-      for (int t = 0; t < n_kv; ++t) {
-        if (t + 1 < n_kv) issue_a(t + 1);
-        issue_b(t);
+      issue_a(0u, IC<0>{}, IC<0>{});
+      for (int t0 = 0; t0 < n_kv; t0 += U) {
+        const uint32_t ldp = static_cast<uint32_t>(t0 / STAGES), dsp = static_cast<uint32_t>(t0 >> 1);
+        auto round = [&](auto Uc) {
+          constexpr int u = decltype(Uc)::value;
+          const int t = t0 + u;
+          if (t < n_kv) {
+            if (t + 1 < n_kv) issue_a((ldp + (u + 1) / STAGES) & 1u, IC<(u + 1) % STAGES>{}, IC<(u + 1) & 1>{});
+            issue_b((dsp + (u >> 1)) & 1u, t == 0, IC<u % STAGES>{}, IC<(u & 1)>{});
+          }
+        };
+        cfor<U>(round);
       }
       if (elect_one()) umma_commit(&acc_full);
     }
@@ -413,48 +435,50 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
       const uint32_t st0 = smem_u32(sStage);
       const uint32_t rk = smem_u32(sRes), rv = rk + RES_BYTES;
       auto koff = [](int ks, int rows) { return static_cast<uint64_t>(((ks / 4) * (rows * 128) + (ks % 4) * 32) >> 4); };
-      auto issue_a = [&](int t) {   // S^T(t) = K Q^T, dP^T(t) = V dO^T   (A = resident tile, B K-major)
-        const int s = t % STAGES, tb = t & 1;
+      constexpr int U = (STAGES % 2 == 0) ? STAGES : 2 * STAGES;   // tiles per unrolled round (see the dQ kernel)
+      const uint64_t dq0 = umma_desc_kmajor(st0), dqm0 = umma_desc_mnmajor(st0 + T_BYTES, BT * 128);
+      const uint64_t ddo0 = umma_desc_kmajor(st0 + 2 * T_BYTES), ddom0 = umma_desc_mnmajor(st0 + 3 * T_BYTES, BT * 128);
+      const uint64_t ak0 = umma_desc_kmajor(rk), av0 = umma_desc_kmajor(rv);
+      auto issue_a = [&](int t, uint32_t ld_parity, auto S, auto TB) {   // S^T(t) = K Q^T, dP^T(t) = V dO^T   (A = resident tile, B K-major)
+        constexpr int s = decltype(S)::value, tb = decltype(TB)::value;
         ST_TRACE(0, t, 0);
-        mbar_wait(&ld_full[s], (t / STAGES) & 1);
+        mbar_wait(&ld_full[s], ld_parity);
         ST_TRACE(0, t, 1);
         tc_fence_after();
         if (elect_one()) {
           constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
-          const uint64_t bq0 = umma_desc_kmajor(st0 + s * STAGE_BYTES), bdo0 = umma_desc_kmajor(st0 + s * STAGE_BYTES + 2 * T_BYTES);
-          const uint64_t ak0 = umma_desc_kmajor(rk), av0 = umma_desc_kmajor(rv);
+          constexpr uint64_t so = static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
 #pragma unroll
           for (int ks = 0; ks < DK / 8; ++ks) {
-            if (RS) umma_tf32_ss(tmem + T_ST + tb * BT, ak0 + koff(ks, BKV), bq0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
-            else umma_tf32_ts(tmem + T_ST + tb * BT, tmem + T_K + ks * 8, bq0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            if (RS) umma_tf32_ss(tmem + T_ST + tb * BT, ak0 + koff(ks, BKV), dq0 + so + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            else umma_tf32_ts(tmem + T_ST + tb * BT, tmem + T_K + ks * 8, dq0 + so + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
           }
 #pragma unroll
           for (int ks = 0; ks < DK / 8; ++ks) {
-            if (RS) umma_tf32_ss(tmem + T_DPT + tb * BT, av0 + koff(ks, BKV), bdo0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
-            else umma_tf32_ts(tmem + T_DPT + tb * BT, tmem + T_V + ks * 8, bdo0 + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            if (RS) umma_tf32_ss(tmem + T_DPT + tb * BT, av0 + koff(ks, BKV), ddo0 + so + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+            else umma_tf32_ts(tmem + T_DPT + tb * BT, tmem + T_V + ks * 8, ddo0 + so + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
           }
           umma_commit(&s_full[tb]);
         }
         __syncwarp();
         ST_TRACE(0, t, 2);
       };
-      auto issue_b = [&](int t) {   // dV += P^T dO, dK += dS^T Q   (A in TMEM, B MN-major)
-        const int s = t % STAGES, tb = t & 1;
+      auto issue_b = [&](int t, uint32_t ds_parity, auto S, auto TB) {   // dV += P^T dO, dK += dS^T Q   (A in TMEM, B MN-major)
+        constexpr int s = decltype(S)::value, tb = decltype(TB)::value;
         ST_TRACE(0, t, 3);
-        mbar_wait(&ds_full[tb], (t >> 1) & 1);
+        mbar_wait(&ds_full[tb], ds_parity);
         ST_TRACE(0, t, 4);
         tc_fence_after();
         if (elect_one()) {
           constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
-          const uint64_t bqm0 = umma_desc_mnmajor(st0 + s * STAGE_BYTES + T_BYTES, BT * 128);
-          const uint64_t bdom0 = umma_desc_mnmajor(st0 + s * STAGE_BYTES + 3 * T_BYTES, BT * 128);
+          constexpr uint64_t so = static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
 #pragma unroll
           for (int ks = 0; ks < BT / 8; ++ks)
-            umma_tf32_ts(tmem + T_DV, tmem + T_ST + tb * BT + ks * 8, bdom0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+            umma_tf32_ts(tmem + T_DV, tmem + T_ST + tb * BT + ks * 8, ddom0 + so + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
                          (t > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < BT / 8; ++ks)
-            umma_tf32_ts(tmem + T_DK, tmem + T_DPT + tb * BT + ks * 8, bqm0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+            umma_tf32_ts(tmem + T_DK, tmem + T_DPT + tb * BT + ks * 8, dqm0 + so + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
                          (t > 0 || ks > 0) ? 1u : 0u);
           umma_commit(&ld_empty[s]);
         }
@@ -463,13 +487,18 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
       };
       mbar_wait(&res_ready, 0);
       tc_fence_after();
-      issue_a(0);
-      for (int t = 0; t < n_q; ++t) {
-        if (t < 8) ST_TRACE(0, 16 + t, 0);
-        if (t + 1 < n_q) issue_a(t + 1);
-        if (t < 8) ST_TRACE(0, 16 + t, 1);
-        issue_b(t);
-        if (t < 8) ST_TRACE(0, 16 + t, 2);
+      issue_a(0, 0u, IC<0>{}, IC<0>{});
+      for (int t0 = 0; t0 < n_q; t0 += U) {
+        const uint32_t ldp = static_cast<uint32_t>(t0 / STAGES), dsp = static_cast<uint32_t>(t0 >> 1);
+        auto round = [&](auto Uc) {
+          constexpr int u = decltype(Uc)::value;
+          const int t = t0 + u;
+          if (t < n_q) {
+            if (t + 1 < n_q) issue_a(t + 1, (ldp + (u + 1) / STAGES) & 1u, IC<(u + 1) % STAGES>{}, IC<(u + 1) & 1>{});
+            issue_b(t, (dsp + (u >> 1)) & 1u, IC<u % STAGES>{}, IC<(u & 1)>{});
+          }
+        };
+        cfor<U>(round);
       }
       if (elect_one()) umma_commit(&acc_full);
     }

@@ -27,10 +27,6 @@ print("MMA warp : tile | A: wait ld_full start, ld_full ok, A issued+commit | B:
 for t in range(16):
     r = [buf[(0 * TT + t) * EV + e] - t0 for e in range(EV)]
     print(f"  {t:2d} | {r[0]:7d} {r[1]:7d} {r[2]:7d} | {r[3]:7d} {r[4]:7d} {r[5]:7d}")
-print("MMA warp loop: t | loop top, after issue_a(t+1), after issue_b(t)")
-for t in range(8):
-    r = [buf[(0 * TT + 16 + t) * EV + e] - t0 for e in range(3)]
-    print(f"  {t:2d} | {r[0]:7d} {r[1]:7d} {r[2]:7d}")
 print("compute thread 0: tile | wait s_full start, s_full ok, tmem ld done, math done, tmem st done, arrived")
 prev = None
 for t in range(16):
