@@ -309,10 +309,17 @@ def main_b200(args):
                     "rate": w.value / (t.value * 1e-3) / 1e12 if t.value > 0 else None}
         lib.st_profile_reset()
         g = breakdown.get("gemm_tf32")
+        traffic, traffic_note = None, None
+        try:   # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+                tj = json.load(f)
+            traffic, traffic_note = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         if g:
             roofline = {"kernel": "gemm_tf32_kernel (tcgen05 kind::tf32, all projection / FFN / gradient GEMMs)",
                         "bound": "tensor", "achieved": g["rate"], "peak": peak, "unit": "TFLOP/s",
-                        "frac": g["rate"] / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": g["rate"] / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                         "peak_tf32_measured": tf32_peak, "frac_of_tf32_peak": g["rate"] / tf32_peak,
                         "flops_per_launch": g["work_per_step"] / g["launches_per_step"],
                         "avg_launch_ms": g["ms_per_step"] / g["launches_per_step"],
