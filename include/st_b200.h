@@ -266,6 +266,25 @@ typedef struct {
 } st_linear_bwd_args;
 int st_linear_bwd(const st_linear_bwd_args* a /* host */, cudaStream_t stream);
 
+/* ---- CTC head of the joint CTC / attention objective (train_attn_and_ctc.py is empty in the
+ * reference, semantics are those of torch.nn.functional.ctc_loss) ------------------------------------------------
+ * logits: (B, T, V) unnormalised scores, row (b, t) at logits + (b*T + t) * ld_logits; the log-softmax is taken
+ * inside.  targets: (B, >= L_max) int64 labels (no blanks), row stride ld_targets; input_lengths / target_lengths:
+ * (B,) int64.  nll: (B,) receives -log p(targets_b | logits_b) (+inf when no alignment exists).  grad: NULL, or
+ * (B, T, ld_grad) receiving scale[b] * d nll[b] / d logits (scale NULL = 1; frames beyond input_lengths[b] and
+ * infeasible utterances get 0).  ws: st_ctc_ws_floats(B, T, L_max) floats of scratch.  L_max <= 511.            */
+int64_t st_ctc_ws_floats(int B, int T, int L_max);
+int st_ctc_fwd_bwd(const float* logits, int64_t ld_logits, const int64_t* targets, int64_t ld_targets,
+                   const int64_t* input_lengths, const int64_t* target_lengths, int blank, int B, int T, int V, int L_max,
+                   float* nll, const float* scale, float* grad, int64_t ld_grad, float* ws, int64_t ws_floats,
+                   cudaStream_t stream);
+/* The gradient alone, from the `ws` contents and `nll` a previous st_ctc_fwd_bwd call (same arguments) left behind:
+ * lets a caller run the forward without knowing the upstream gradient and apply `scale` in its backward.      */
+int st_ctc_grad(const float* logits, int64_t ld_logits, const int64_t* targets, int64_t ld_targets,
+                const int64_t* input_lengths, const int64_t* target_lengths, int blank, int B, int T, int V, int L_max,
+                const float* nll, const float* scale, float* grad, int64_t ld_grad, float* ws, int64_t ws_floats,
+                cudaStream_t stream);
+
 /* ---- flat-buffer optimizer step (train.py:45-46, Optim.py:9-14,36-45) --------------------------------
  * st_sumsq: *out += sum(x[i]^2) (caller zeroes `out`, a device float).
  * st_adam_step: g' = grad * grad_scale * min(1, max_grad_norm / (sqrt(*norm_ws) * grad_scale + 1e-6))

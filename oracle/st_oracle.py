@@ -203,3 +203,16 @@ def synthetic_batch(batch: int, t_max: int, l_max: int, feat: int, vocab: int, s
         truth[b, :n] = labels
         truth[b, n] = BOS                       # labels + [BOS] (sic, Dataset.py:36-37)
     return inputs, targets, in_len, tgt_len, truth
+
+
+# ---------------------------------------------------------------------------------------------
+# CTC.  The reference's train_attn_and_ctc.py is an EMPTY file: there is no reference code for
+# this row.  The algorithm lives in a third-party dependency the reference would have called — PyTorch ATen's
+# ctc_loss (torch 2.11.0 in this image; Graves et al. 2006 forward-backward in the log domain).  The oracle is that
+# implementation run on CPU in float64; parity of the CUDA kernels is anchored on it (tests/test_gpu_ctc.py).
+# ---------------------------------------------------------------------------------------------
+def ctc_nll(logits: Tensor, targets: Tensor, input_lengths: Tensor, target_lengths: Tensor, blank: int = 0) -> Tensor:
+    """Per-utterance -log p(targets | logits); logits (B, T, V) unnormalised, targets (B, L_max) padded."""
+    logp = torch.log_softmax(logits, dim=-1).transpose(0, 1)       # (T, B, V) as F.ctc_loss expects
+    return torch.nn.functional.ctc_loss(logp, targets, input_lengths, target_lengths, blank=blank, reduction="none",
+                                        zero_infinity=False)

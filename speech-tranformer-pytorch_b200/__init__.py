@@ -9,7 +9,7 @@ drop-in nn.Modules with the reference's interface.
 from . import _lib, functional, transformer  # noqa: F401
 from .build import build  # noqa: F401
 from .install import install, uninstall  # noqa: F401
-from .transformer import (CrossEntropyLoss, LabelSmoothingLoss, MultiHeadAttention,  # noqa: F401
+from .transformer import (CrossEntropyLoss, CTCLoss, JointCTCAttentionLoss, LabelSmoothingLoss, MultiHeadAttention,  # noqa: F401
                           PositionwiseFeedForward, ScaledDotProductAttention)
 
 __version__ = "0.1.0"

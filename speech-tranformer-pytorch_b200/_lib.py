@@ -151,6 +151,9 @@ SIGNATURES = {
     "st_linear_ws_floats": (i64, [i64, C.c_int, C.c_int]),
     "st_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _S]),
     "st_linear_bwd": (C.c_int, [C.POINTER(LinearBwdArgs), _S]),
+    "st_ctc_ws_floats": (i64, [C.c_int, C.c_int, C.c_int]),
+    "st_ctc_fwd_bwd": (C.c_int, [_P, i64, _P, i64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, i64, _P, i64, _S]),
+    "st_ctc_grad": (C.c_int, [_P, i64, _P, i64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, i64, _P, i64, _S]),
     "st_sumsq": (C.c_int, [_P, i64, _P, _S]),
     "st_adam_step": (C.c_int, [C.POINTER(AdamArgs), _S]),
 }

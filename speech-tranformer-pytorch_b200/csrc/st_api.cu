@@ -202,7 +202,7 @@ int st_profile_dump(const char* path) { return profile_dump(path); }
 int st_profile_classes(void) { return PROF_NUM; }
 const char* st_profile_class_name(int cls) {
   static const char* names[PROF_NUM] = {"gemm_tf32", "attn_fwd", "attn_bwd_dkv", "attn_bwd_dq", "attn_bwd_delta", "add_ln_fwd",
-                                        "add_ln_bwd", "round_tf32", "colsum", "lsce", "sumsq", "adam", "embed"};
+                                        "add_ln_bwd", "round_tf32", "colsum", "lsce", "sumsq", "adam", "embed", "ctc"};
   return (cls >= 0 && cls < PROF_NUM) ? names[cls] : "?";
 }
 int st_profile_read(int cls, double* ms, double* work, int64_t* launches) {
@@ -724,6 +724,25 @@ int st_linear_bwd(const st_linear_bwd_args* bp, cudaStream_t s) {
     ST_TRY(colsum_add(s, dy_r, ldr, M, n, b.db));
   }
   return ST_OK;
+}
+
+// gradient alone, from the workspace (log-sum-exp, alpha, beta) and nll a previous st_ctc_fwd_bwd call left behind
+int st_ctc_grad(const float* logits, int64_t ld_logits, const int64_t* targets, int64_t ld_targets,
+                const int64_t* input_lengths, const int64_t* target_lengths, int blank, int B, int T, int V, int L_max,
+                const float* nll, const float* scale, float* grad, int64_t ld_grad, float* ws, int64_t ws_floats,
+                cudaStream_t stream) {
+  return ctc_fwd_bwd(stream, logits, ld_logits, targets, ld_targets, input_lengths, target_lengths, blank, B, T, V, L_max,
+                     const_cast<float*>(nll), scale, grad, ld_grad, ws, ws_floats, 1);
+}
+
+// ------------------------------------------------------------------ CTC head of the joint CTC / attention loss
+int64_t st_ctc_ws_floats(int B, int T, int L_max) { return ctc_ws_floats(B, T, 2 * L_max + 1); }
+int st_ctc_fwd_bwd(const float* logits, int64_t ld_logits, const int64_t* targets, int64_t ld_targets,
+                   const int64_t* input_lengths, const int64_t* target_lengths, int blank, int B, int T, int V, int L_max,
+                   float* nll, const float* scale, float* grad, int64_t ld_grad, float* ws, int64_t ws_floats,
+                   cudaStream_t stream) {
+  return ctc_fwd_bwd(stream, logits, ld_logits, targets, ld_targets, input_lengths, target_lengths, blank, B, T, V, L_max, nll,
+                     scale, grad, ld_grad, ws, ws_floats);
 }
 
 }  // extern "C"

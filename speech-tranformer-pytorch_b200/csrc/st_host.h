@@ -61,7 +61,7 @@ int num_sms();
 // roofline numbers.  Disabled by default; when disabled a ProfScope costs one relaxed atomic load.
 enum ProfClass : int {
   PROF_GEMM = 0, PROF_ATTN_FWD, PROF_ATTN_DKV, PROF_ATTN_DQ, PROF_ATTN_DELTA, PROF_LN_FWD, PROF_LN_BWD, PROF_ROUND,
-  PROF_COLSUM, PROF_LSCE, PROF_SUMSQ, PROF_ADAM, PROF_EMBED, PROF_NUM
+  PROF_COLSUM, PROF_LSCE, PROF_SUMSQ, PROF_ADAM, PROF_EMBED, PROF_CTC, PROF_NUM
 };
 struct ProfScope {
   ProfScope(cudaStream_t s, ProfClass cls, double work, long long tag = 0);   // tag: free-form id kept in the dump  // work: algorithmic FLOPs (tensor kernels) or bytes (HBM kernels)

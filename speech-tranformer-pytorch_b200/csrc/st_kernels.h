@@ -32,6 +32,12 @@ int embed_fwd(cudaStream_t stream, const int64_t* idx, const float* table, const
 int embed_bwd(cudaStream_t stream, const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab,
               int64_t padding_idx, int zero_first);
 
+// ---- st_ctc.cu
+int64_t ctc_ws_floats(int B, int T, int S_max);
+int ctc_fwd_bwd(cudaStream_t stream, const float* logits, int64_t ld, const int64_t* targets, int64_t ld_tgt,
+                const int64_t* in_len, const int64_t* tgt_len, int blank, int B, int T, int V, int L_max, float* nll,
+                const float* scale, float* grad, int64_t ldg, float* ws, int64_t ws_floats, int grad_only = 0);
+
 // ---- st_optim.cu
 int sumsq_add(cudaStream_t s, const float* x, int64_t n, float* out);
 int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,

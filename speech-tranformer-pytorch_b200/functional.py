@@ -17,7 +17,7 @@ from ._lib import StError, check
 
 __all__ = ["add_layer_norm", "multi_head_attention", "positionwise_ffn", "label_smoothing_ce", "soft_target_ce",
            "attention_core", "linear_tf32", "round_tf32", "is_tf32_clean", "mark_tf32_clean", "next_seed",
-           "frontend", "linear", "embedding", "GradSink", "attach_grad_sink", "attach_tf32_twin"]
+           "frontend", "linear", "embedding", "ctc_loss", "GradSink", "attach_grad_sink", "attach_tf32_twin"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -722,3 +722,58 @@ class _Embedding(torch.autograd.Function):
 def embedding(idx, table, pe=None, padding_idx: int = -1, round_out: bool = None):
     """table[idx] + pe[:L] (Models.py:84-87); the padding row receives no gradient (nn.Embedding padding_idx)."""
     return _Embedding.apply(idx, table, pe, padding_idx, ROUND_OUT if round_out is None else round_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# CTC head of the joint CTC / attention objective (SURVEY.md §8 f-4)
+# ------------------------------------------------------------------------------------------------
+class _CTCLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, input_lengths, target_lengths, blank):
+        logits = _need(logits, "logits")
+        if logits.dim() != 3:
+            raise RuntimeError("ctc_loss: logits must be (batch, frames, vocab)")
+        B, T, V = logits.shape
+        if not (logits.stride(2) == 1 and logits.stride(0) == T * logits.stride(1) and logits.stride(1) >= V):
+            logits = logits.contiguous()           # row-padded projections (functional.linear) are read in place
+        lib = _lib_for(logits)
+        targets = _contig(_need(targets, "targets", torch.int64))
+        input_lengths = _contig(_need(input_lengths, "input_lengths", torch.int64))
+        target_lengths = _contig(_need(target_lengths, "target_lengths", torch.int64))
+        if targets.dim() != 2 or targets.shape[0] != B or input_lengths.shape != (B,) or target_lengths.shape != (B,):
+            raise RuntimeError("ctc_loss: targets must be (batch, max_target_length), lengths (batch,)")
+        L_max = targets.shape[1]
+        n_ws = lib.st_ctc_ws_floats(B, T, L_max)
+        ws = torch.empty(n_ws, device=logits.device, dtype=torch.float32)
+        nll = torch.empty(B, device=logits.device, dtype=torch.float32)
+        check(lib.st_ctc_fwd_bwd(_p(logits), logits.stride(1), _p(targets), max(L_max, 1), _p(input_lengths), _p(target_lengths),
+                                 int(blank), B, T, V, L_max, _p(nll), None, None, 0, _p(ws), n_ws, _stream()))
+        ctx.save_for_backward(logits, targets, input_lengths, target_lengths, nll, ws)
+        ctx.cfg = (B, T, V, L_max, int(blank))
+        return nll
+
+    @staticmethod
+    def backward(ctx, dnll):
+        logits, targets, input_lengths, target_lengths, nll, ws = ctx.saved_tensors
+        B, T, V, L_max, blank = ctx.cfg
+        lib = _lib_for(logits)
+        ldg = (V + 3) // 4 * 4
+        grad = torch.empty(B, T, ldg, device=logits.device, dtype=torch.float32)
+        scale = _contig(dnll.to(torch.float32))
+        check(lib.st_ctc_grad(_p(logits), logits.stride(1), _p(targets), max(L_max, 1), _p(input_lengths), _p(target_lengths),
+                              blank, B, T, V, L_max, _p(nll), _p(scale), _p(grad), ldg, _p(ws), ws.numel(), _stream()))
+        return grad[:, :, :V], None, None, None, None
+
+
+def ctc_loss(logits, targets, input_lengths, target_lengths, blank: int = 0, reduction: str = "mean"):
+    """CTC negative log-likelihood of `targets` (B, L_max; no blanks) given frame logits (B, T, V); log-softmax inside.
+    Reductions as torch.nn.functional.ctc_loss: 'none' (B,), 'sum', 'mean' (each loss divided by its target length,
+    then the batch mean).  Utterances without a feasible alignment give +inf and a zero gradient."""
+    nll = _CTCLoss.apply(logits, targets, input_lengths, target_lengths, blank)
+    if reduction == "none":
+        return nll
+    if reduction == "sum":
+        return nll.sum()
+    if reduction == "mean":
+        return (nll / target_lengths.clamp(min=1).to(nll.dtype)).mean()
+    raise ValueError("reduction must be 'none', 'sum' or 'mean'")

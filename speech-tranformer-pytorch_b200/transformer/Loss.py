@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from .. import functional as F
 
-__all__ = ["LabelSmoothingLoss", "CrossEntropyLoss"]
+__all__ = ["LabelSmoothingLoss", "CrossEntropyLoss", "CTCLoss", "JointCTCAttentionLoss"]
 
 
 class LabelSmoothingLoss(nn.Module):
@@ -57,3 +57,31 @@ class CrossEntropyLoss(nn.Module):
             raise AttributeError("'NoneType' object has no attribute 'repeat'")
         weight = self.weight if self.weight.device == inputs.device else self.weight.to(inputs.device)
         return F.soft_target_ce(inputs, target, weight, self.size_average)
+
+
+
+class CTCLoss(nn.Module):
+    """CTC head for the joint CTC / attention objective of BASELINE.json configs[3].  The reference's
+    train_attn_and_ctc.py is an empty file, so the interface follows torch.nn.CTCLoss with batch-first frame LOGITS
+    (B, T, V) — the log-softmax is fused — and padded (B, L_max) targets."""
+
+    def __init__(self, blank=0, reduction="mean"):
+        super(CTCLoss, self).__init__()
+        self.blank, self.reduction = blank, reduction
+
+    def forward(self, logits, targets, input_lengths, target_lengths):
+        return F.ctc_loss(logits, targets, input_lengths, target_lengths, blank=self.blank, reduction=self.reduction)
+
+
+class JointCTCAttentionLoss(nn.Module):
+    """loss = ctc_weight * CTC(encoder-side logits) + (1 - ctc_weight) * attention criterion(decoder logits)."""
+
+    def __init__(self, attention_criterion, ctc_weight=0.3, blank=0, ctc_reduction="mean"):
+        super(JointCTCAttentionLoss, self).__init__()
+        assert 0.0 <= ctc_weight <= 1.0
+        self.att, self.ctc, self.ctc_weight = attention_criterion, CTCLoss(blank, ctc_reduction), ctc_weight
+
+    def forward(self, dec_logits, dec_truth, ctc_logits, ctc_targets, input_lengths, target_lengths):
+        att = self.att(dec_logits, dec_truth)
+        ctc = self.ctc(ctc_logits, ctc_targets, input_lengths, target_lengths)
+        return self.ctc_weight * ctc + (1.0 - self.ctc_weight) * att
