@@ -34,6 +34,17 @@ __device__ __forceinline__ double log_add(double a, double b) {
   const float d = static_cast<float>(fabs(a - b));
   return m + static_cast<double>(log1pf(__expf(-d)));
 }
+// log(exp(a) + exp(b) + [use_c] exp(c)) on the recursion's critical path: one warp per scheduler runs a dependent chain
+// per frame, so instruction count is latency.  The sum of the shifted exponentials lies in [1, 3]: MUFU ex2 / lg2
+// (absolute error ~1e-7) are exact enough because the result is ADDED to the running maximum.
+__device__ __forceinline__ double log_add3(double a, double b, double c, bool use_c) {
+  double m = fmax(a, b);
+  if (use_c) m = fmax(m, c);
+  if (m == -INFINITY) return -INFINITY;
+  float sum = __expf(static_cast<float>(a - m)) + __expf(static_cast<float>(b - m));
+  if (use_c) sum += __expf(static_cast<float>(c - m));
+  return m + static_cast<double>(__logf(sum));
+}
 
 __global__ void __launch_bounds__(CTC_THREADS)
 ctc_lse_kernel(const float* __restrict__ logits, int64_t ld, int64_t rows, int V, float* __restrict__ lse) {
@@ -103,35 +114,48 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logits, int64_t 
   }
   const float* xb = logits + static_cast<int64_t>(b) * T * ld;
   const float* lb = lse + static_cast<int64_t>(b) * T;
-  auto emit = [&](int t) -> float { return live ? xb[static_cast<int64_t>(t) * ld + lab] - lb[t] : -INFINITY; };
+  // Emissions are gathered PF frames ahead of their use.  The raw loads (logit, log-sum-exp) sit in registers until then:
+  // combining them at issue time would stall the warp on the load latency every frame (in-order issue).
   auto frame = [&](int i) { return is_beta ? Tb - 1 - i : i; };   // i-th frame in recursion order
-  float pf[PF];
+  float px[PF], pl[PF];
 #pragma unroll
-  for (int i = 0; i < PF; ++i) pf[i] = (i < Tb) ? emit(frame(i)) : 0.f;
+  for (int i = 0; i < PF; ++i) {
+    const bool ok = live && i < Tb;
+    px[i] = ok ? xb[static_cast<int64_t>(frame(i)) * ld + lab] : 0.f;
+    pl[i] = ok ? lb[frame(i)] : 0.f;
+  }
   double* prev = row0;
   double* cur = row1;
-  for (int i = 0; i < Tb; ++i) {
-    const int t = frame(i);
-    const float e = pf[0];
+  // unrolled by PF: prefetch slot k is a fixed register pair, consumed and immediately refilled (no register shifting,
+  // which would read registers whose loads are still in flight)
+  for (int i0 = 0; i0 < Tb; i0 += PF) {
 #pragma unroll
-    for (int k = 0; k + 1 < PF; ++k) pf[k] = pf[k + 1];
-    pf[PF - 1] = (i + PF < Tb) ? emit(frame(i + PF)) : 0.f;
-    double v;
-    if (i == 0) {
-      if (!is_beta) v = (s < 2 && live) ? e : -INFINITY;                    // alpha_0: states 0 and 1
-      else v = (live && s >= S - 2) ? e : -INFINITY;                        // beta_{T-1}: states S-1 and S-2
-    } else if (live) {        // threads beyond the last state never touch the rows (they would read past the pads)
-      const double a0 = prev[s];
-      const double a1 = is_beta ? prev[s + 1] : prev[s - 1];
-      double acc = log_add(a0, a1);
-      if (skip) acc = log_add(acc, is_beta ? prev[s + 2] : prev[s - 2]);
-      v = acc + e;
-    } else {
-      v = -INFINITY;
+    for (int k = 0; k < PF; ++k) {
+      const int i = i0 + k;
+      if (i >= Tb) break;                 // uniform across the block
+      const int t = frame(i);
+      const float e = live ? px[k] - pl[k] : -INFINITY;
+      {
+        const bool ok = live && i + PF < Tb;
+        px[k] = ok ? xb[static_cast<int64_t>(frame(i + PF)) * ld + lab] : 0.f;
+        pl[k] = ok ? lb[frame(i + PF)] : 0.f;
+      }
+      double v;
+      if (i == 0) {
+        if (!is_beta) v = (s < 2 && live) ? e : -INFINITY;                    // alpha_0: states 0 and 1
+        else v = (live && s >= S - 2) ? e : -INFINITY;                        // beta_{T-1}: states S-1 and S-2
+      } else if (live) {      // threads beyond the last state never touch the rows (they would read past the pads)
+        const double a0 = prev[s];
+        const double a1 = is_beta ? prev[s + 1] : prev[s - 1];
+        const double a2 = is_beta ? prev[s + 2] : prev[s - 2];    // a pad (-inf) or a real state; ignored unless `skip`
+        v = log_add3(a0, a1, a2, skip) + e;
+      } else {
+        v = -INFINITY;
+      }
+      if (s < S_max) { cur[s] = v; out[static_cast<int64_t>(t) * S_max + s] = v; }
+      __syncthreads();
+      double* tmp = prev; prev = cur; cur = tmp;
     }
-    if (s < S_max) { cur[s] = v; out[static_cast<int64_t>(t) * S_max + s] = v; }
-    __syncthreads();
-    double* tmp = prev; prev = cur; cur = tmp;
   }
   if (!is_beta && s == 0) {
     const double a_last = prev[S - 1];
