@@ -234,3 +234,30 @@ def test_trainer_step_reduces_loss(stb):
     crit = stb.LabelSmoothingLoss(0.1, V, weight=torch.ones(V, device=DEV), size_average=True, ignore_index=0).to(DEV)
     losses = [float(tr.train_step(lambda: crit(net(*batch)[0].view(-1, V), truth))) for _ in range(30)]
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+# ------------------------------------------------------------------------------------------------ ragged long batches
+def test_padding_invariance_long_ragged_batch(stb):
+    """BASELINE.json configs[2] structure (variable-length padded batch, T up to 2000) at full width (d_model 512, 8 heads):
+    size-independent property — the encoder output of an utterance's valid frames does not depend on how much padding
+    the batch adds around it, nor on what the padded frames contain (key-padding mask => exactly zero weight)."""
+    from speech_tranformer_pytorch_b200 import model as smodel
+    torch.manual_seed(11)
+    cfg = smodel.headline_config(num_enc_layer=2, num_dec_layer=1)
+    net = smodel.Transformer(cfg)
+    smodel.init_parameters(net)
+    enc = net.encoder.to(DEV).eval()
+    lens = torch.tensor([2000, 777, 200, 1333])
+    x = torch.randn(4, 2000, 80)
+    for b, l in enumerate(lens.tolist()):
+        x[b, l:] = 0
+    with torch.no_grad():
+        full, _ = enc(x.to(DEV), lens.to(DEV))
+        noisy = x.clone()
+        for b, l in enumerate(lens.tolist()):
+            noisy[b, l:] = 50.0 * torch.randn(2000 - l, 80)            # garbage in the padded frames
+        full_noisy, _ = enc(noisy.to(DEV), lens.to(DEV))
+        for b, l in enumerate(lens.tolist()):
+            alone, _ = enc(x[b:b + 1, :l].to(DEV), lens[b:b + 1].to(DEV))
+            assert relerr(full[b, :l], alone[0]) < 1e-4, (b, l)        # only the tile decomposition / summation order differs
+            assert torch.equal(full[b, :l], full_noisy[b, :l]), (b, l)  # masked keys contribute exactly nothing
