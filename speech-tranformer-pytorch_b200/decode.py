@@ -13,7 +13,10 @@ decode path those files describe, built for the B200 library:
   * one decoder step = the new token only: 5 projection GEMMs + 2 attention calls + 2 residual-LayerNorms + the fused
     FFN per layer, all from libst_b200.so (st_gemm / st_attn_fwd / st_add_ln_fwd / st_ffn_fwd / st_embed_fwd);
   * beam bookkeeping (Beam.advance: add scores, top-k over beam x vocab, integer-floor back-pointer, Beam.py:43-74)
-    stays on the device; the host only polls an "all finished" flag.
+    stays on the device; the host only polls an "all finished" flag;
+  * a decode step is ~95 small launches (launch-bound), so a decoder object kept across batches of one shape
+    (`use_graphs=True`) captures each position's launches — cache re-parenting included — into a CUDA graph the
+    second time it sees that shape and replays it from then on (inputs / outputs are static buffers).
 
 There is no CPU fallback.  Parity: tests/test_gpu_decode.py checks step logits against the full-prefix decoder and
 the beam result against oracle/decode_port.py (the reference's algorithm on the CPU oracle model).
@@ -74,7 +77,9 @@ class _LayerWeights:
 class IncrementalDecoder:
     """Decoder of a `model.Transformer` that advances one target position per call, reusing cached K/V."""
 
-    def __init__(self, net, max_len: Optional[int] = None):
+    def __init__(self, net, max_len: Optional[int] = None, use_graphs: bool = False):
+        self.use_graphs = use_graphs
+        self._graphs, self._shape, self._starts = {}, None, 0
         self.net = net
         self.lib = _lib.load()
         dec = net.decoder
@@ -101,17 +106,25 @@ class IncrementalDecoder:
             enc2 = F.round_tf32(enc2)
         dev = enc.device
         n = B * beam
-        kv = []
-        for lw in self.layers:
-            buf = torch.empty(B * T, 2 * d, device=dev, dtype=torch.float32)
+        if self._shape != (B, beam, T):      # (re)allocate the static state; graphs captured for another shape are dropped
+            self._shape, self._graphs, self._starts = (B, beam, T), {}, 0
+            self.state = {
+                "B": B, "beam": beam, "T": T, "t": 0,
+                "cross_kv": [torch.empty(B * T, 2 * d, device=dev, dtype=torch.float32) for _ in self.layers],
+                "mask_buf": torch.zeros(B, 1, T, dtype=torch.bool, device=dev),
+                "k": [torch.zeros(self.max_len, n, d, device=dev) for _ in self.layers],
+                "v": [torch.zeros(self.max_len, n, d, device=dev) for _ in self.layers],
+            }
+            self.state["cross_mask"] = self.state["mask_buf"].expand(-1, beam, -1)      # (B, beam, T), stride 0 over beams
+            self._tok = torch.zeros(n, dtype=torch.int64, device=dev)
+            self._parent = torch.arange(n, dtype=torch.int64, device=dev)
+            self._identity = torch.arange(n, dtype=torch.int64, device=dev)
+        st = self.state
+        st["t"] = 0
+        st["mask_buf"].copy_(key_padding_mask(input_lengths, 1, T))
+        for lw, buf in zip(self.layers, st["cross_kv"]):
             lw.ckv(self.lib, enc2, buf)                       # [K | V] of the encoder output, Attention.py:75-76
-            kv.append(buf)
-        self.state = {
-            "B": B, "beam": beam, "T": T, "t": 0, "cross_kv": kv,
-            "cross_mask": key_padding_mask(input_lengths, beam, T),          # (B, beam, T), stride 0 over beams
-            "k": [torch.zeros(self.max_len, n, d, device=dev) for _ in self.layers],
-            "v": [torch.zeros(self.max_len, n, d, device=dev) for _ in self.layers],
-        }
+        self._starts += 1
 
     # ---- attention helpers -----------------------------------------------------------------------------------
     def _attn(self, B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, mask, out):
@@ -136,8 +149,33 @@ class IncrementalDecoder:
 
     # ---- one target position -----------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, tokens: torch.Tensor) -> torch.Tensor:
-        """tokens: (B*beam,) int64, the symbols at position t.  Returns the logits (B*beam, V) for position t + 1."""
+    def step(self, tokens: torch.Tensor, parent: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tokens: (B*beam,) int64, the symbols at position t; parent: optional (B*beam,) int64 — hypothesis j continues
+        hypothesis parent[j] (applied to the caches before the step).  Returns the logits (B*beam, V) for position t + 1
+        (valid until the next call for the same position when graphs are in use)."""
+        if not (self.use_graphs and self._starts >= 2):
+            if parent is not None:
+                self.reorder(parent)
+            return self._step(tokens)
+        st = self.state
+        t = st["t"]
+        self._tok.copy_(tokens)
+        self._parent.copy_(self._identity if parent is None else parent)
+        entry = self._graphs.get(t)
+        if entry is None:                       # capture this position's launches (nothing executes during capture)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                if t > 0:
+                    self.reorder(self._parent)
+                out = self._step(self._tok)
+            st["t"] = t
+            entry = self._graphs[t] = (graph, out)
+        entry[0].replay()
+        st["t"] = t + 1
+        return entry[1]
+
+    @torch.no_grad()
+    def _step(self, tokens: torch.Tensor) -> torch.Tensor:
         st, lib, d = self.state, self.lib, self.d
         B, beam, T, t = st["B"], st["beam"], st["T"], st["t"]
         n = B * beam
@@ -184,12 +222,14 @@ class IncrementalDecoder:
 
 @torch.no_grad()
 def beam_search(net, inputs: torch.Tensor, input_lengths: torch.Tensor, beam: int = 10, max_len: int = 50,
-                n_best: int = 1, eos: int = EOS) -> Tuple[List[List[List[int]]], torch.Tensor]:
+                n_best: int = 1, eos: int = EOS, decoder: Optional[IncrementalDecoder] = None
+                ) -> Tuple[List[List[List[int]]], torch.Tensor]:
     """Beam decode a batch (Decode.decode_batch, Decode.py:48-179, with Beam.advance semantics, Beam.py:43-74):
     every step adds log-probabilities to the running beam scores, keeps the `beam` best of beam x vocab, records
     the integer back-pointer and symbol; an utterance is finished when its best hypothesis ends in EOS.
-    Returns (hypotheses[b][k] = token list without BOS, scores (B, n_best))."""
-    dec = IncrementalDecoder(net, max_len=max_len)
+    Returns (hypotheses[b][k] = token list without BOS, scores (B, n_best)).  Pass a persistent `decoder`
+    (IncrementalDecoder(net, max_len, use_graphs=True)) to replay CUDA graphs across batches of one shape."""
+    dec = decoder if decoder is not None else IncrementalDecoder(net, max_len=max_len)
     dec.start(inputs, input_lengths, beam)
     B, V, dev = inputs.size(0), dec.vocab, inputs.device
     scores = torch.zeros(B, beam, device=dev)
@@ -197,8 +237,9 @@ def beam_search(net, inputs: torch.Tensor, input_lengths: torch.Tensor, beam: in
     done = torch.zeros(B, dtype=torch.bool, device=dev)
     base = (torch.arange(B, device=dev) * beam).unsqueeze(1)
     prev_ks, next_ys = [], []
+    parent = None
     for t in range(max_len):
-        logp = torch.log_softmax(dec.step(tokens), dim=-1).view(B, beam, V)
+        logp = torch.log_softmax(dec.step(tokens, parent), dim=-1).view(B, beam, V)
         cand = logp + scores.unsqueeze(2) if t > 0 else logp[:, :1]      # first step: all beams are identical (Beam.py:49-52)
         best, idx = cand.reshape(B, -1).topk(beam, dim=1)
         prev_k = torch.div(idx, V, rounding_mode="floor")                # integer back-pointer (Beam.py:66)
@@ -213,7 +254,7 @@ def beam_search(net, inputs: torch.Tensor, input_lengths: torch.Tensor, beam: in
         done = done | (y[:, 0] == eos)                                   # Beam.py:70-72
         if bool(done.all()):
             break
-        dec.reorder((base + prev_k).reshape(-1))
+        parent = (base + prev_k).reshape(-1)
         tokens = y.reshape(-1)
     # back-track (Beam.get_hypothesis, Beam.py:100-118) for the n_best final beams, best score first
     order = scores.sort(dim=1, descending=True)

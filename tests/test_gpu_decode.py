@@ -78,3 +78,21 @@ def test_decode_requires_eval_mode(stb):
     net.train()
     with pytest.raises(RuntimeError):
         IncrementalDecoder(net).start(t(g["inputs"]).to(DEV), t(g["in_len"]).to(DEV))
+
+
+def test_cuda_graph_replay_is_bit_identical(stb):
+    """A persistent decoder captures each position into a CUDA graph the second time it sees a shape; results of the
+    eager pass, the capturing pass and the replaying pass must be identical, including after new inputs."""
+    from speech_tranformer_pytorch_b200.decode import IncrementalDecoder, beam_search
+    g = golden("transformer_small")
+    net, _ = _model(stb, g, sharpen=12.0)
+    inputs, in_len = t(g["inputs"]).to(DEV), t(g["in_len"]).to(DEV)
+    dec = IncrementalDecoder(net, max_len=10, use_graphs=True)
+    runs = [beam_search(net, inputs, in_len, beam=4, max_len=10, n_best=2, eos=3, decoder=dec) for _ in range(3)]
+    assert len(dec._graphs) > 0
+    for hyps, scores in runs[1:]:
+        assert hyps == runs[0][0] and torch.equal(scores, runs[0][1])
+    other = inputs.flip(0).contiguous()                                   # same shape, different utterances: graphs are reused
+    want = beam_search(net, other, in_len.flip(0).contiguous(), beam=4, max_len=10, n_best=2, eos=3)
+    got = beam_search(net, other, in_len.flip(0).contiguous(), beam=4, max_len=10, n_best=2, eos=3, decoder=dec)
+    assert got[0] == want[0] and torch.equal(got[1], want[1])
