@@ -47,7 +47,8 @@ def test_ctypes_struct_layout_matches_header(stb, tmp_path):
     L = stb._lib
     pairs = {"st_gemm_epilogue": L.GemmEpilogue, "st_attn_args": L.AttnArgs, "st_attn_bwd_args": L.AttnBwdArgs,
              "st_mha_args": L.MhaArgs, "st_mha_bwd_args": L.MhaBwdArgs, "st_ffn_args": L.FfnArgs,
-             "st_ffn_bwd_args": L.FfnBwdArgs, "st_adam_args": L.AdamArgs}
+             "st_ffn_bwd_args": L.FfnBwdArgs, "st_adam_args": L.AdamArgs, "st_frontend_args": L.FrontendArgs,
+             "st_frontend_bwd_args": L.FrontendBwdArgs, "st_linear_args": L.LinearArgs, "st_linear_bwd_args": L.LinearBwdArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "st_b200.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
