@@ -164,3 +164,30 @@ def test_model_port_matches_reference_model():
             got = P[k[2:]].grad
             assert got is not None, k
             assert (got.numpy() - v).__abs__().max() / scale < 2e-5, k
+
+
+def test_decode_port_beam1_is_greedy_and_scores_are_sorted():
+    """oracle/decode_port.py self-consistency on the reference-pinned model port: width 1 equals greedy arg-max
+    decoding with the summed log-probability as its score; wider beams return scores in descending order that are
+    at least as good as greedy."""
+    from oracle import decode_port, model_port
+    g = golden("transformer_small")
+    cfg = dict(d_model=64, n_heads=2, num_enc_layer=2, num_dec_layer=2, vocab_size=31)
+    P = {k[2:]: t(v).double() for k, v in g.items() if k.startswith("p.") and not k.endswith(".pe")}
+    P["tgt_word_proj.weight"] = P["tgt_word_proj.weight"] * 12
+    inputs, in_len = t(g["inputs"]).double(), t(g["in_len"])
+    hyps, scores = decode_port.beam_search(P, cfg, inputs, in_len, beam=1, max_len=6)
+    for b in range(inputs.size(0)):
+        prefix, total = [decode_port.BOS], 0.0
+        for _ in range(6):
+            lp = torch.log_softmax(decode_port.step_logits(P, cfg, inputs[b:b + 1, :int(in_len[b])], in_len[b:b + 1], torch.tensor([prefix])), -1)[0]
+            y = int(lp.argmax())
+            total += float(lp[y])
+            prefix.append(y)
+            if y == decode_port.EOS:
+                break
+        assert hyps[b][0] == prefix[1:]
+        assert abs(float(scores[b, 0]) - total) < 1e-9
+    wide_h, wide_s = decode_port.beam_search(P, cfg, inputs, in_len, beam=4, max_len=6, n_best=4)
+    assert bool((wide_s[:, :-1] >= wide_s[:, 1:]).all())
+    assert bool((wide_s[:, 0] >= scores[:, 0] - 1e-9).all())
