@@ -144,16 +144,39 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
     acc_g[i] = acc_b[i] = acc_z[i] = make_float4(0, 0, 0, 0);
   }
 
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp; row < rows;
-       row += static_cast<int64_t>(gridDim.x) * LN_WARPS) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
+  // next row's dy / z / statistics are in flight while the current row is reduced (see the forward kernel)
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * LN_WARPS;
+  const int64_t row_first = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp;
+  float4 dyn[VPL], zn[VPL];
+  float mean_n = 0.f, rstd_n = 0.f;
+  if (row_first < rows) {
+    mean_n = mean_in[row_first]; rstd_n = rstd_in[row_first];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) { dyn[i] = ld4(dy + row_first * d + c); zn[i] = ld4(z + row_first * d + c); }
+    }
+  }
+  for (int64_t row = row_first; row < rows; row += stride) {
+    const float mean = mean_n, rstd = rstd_n;
+    float4 dyc[VPL], zc[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { dyc[i] = dyn[i]; zc[i] = zn[i]; }
+    if (row + stride < rows) {
+      mean_n = mean_in[row + stride]; rstd_n = rstd_in[row + stride];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) { dyn[i] = ld4(dy + (row + stride) * d + c); zn[i] = ld4(z + (row + stride) * d + c); }
+      }
+    }
     float4 xh[VPL], gy[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < d) {
-        float4 dyv = ld4(dy + row * d + c);
+        float4 dyv = dyc[i];
         if (drop_thresh) {
           float* e = reinterpret_cast<float*>(&dyv);
           const uint32_t key = dropout_row_key(drop_seed, static_cast<uint64_t>(row));
@@ -164,7 +187,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
             e[t + 1] = dropout_keep(bits, 1, drop_thresh) ? e[t + 1] * drop_scale : 0.f;
           }
         }
-        const float4 zv = ld4(z + row * d + c);
+        const float4 zv = zc[i];
         xh[i] = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
         gy[i] = make_float4(dyv.x * g[i].x, dyv.y * g[i].y, dyv.z * g[i].z, dyv.w * g[i].w);
         s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
