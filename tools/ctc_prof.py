@@ -1,3 +1,5 @@
+"""Per-kernel CUDA-event times of the CTC head at the headline shape (B=32, T=1000, V=4337, L<=50): log-sum-exp,
+alpha/beta recursion, gradient.  python tools/ctc_prof.py"""
 import torch, sys, ctypes as C
 sys.path.insert(0,".")
 import speech_tranformer_pytorch_b200 as stb

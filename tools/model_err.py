@@ -1,3 +1,5 @@
+"""Whole-model logits error against the reference fixture, with TF32-rounded (default) or exact-fp32 (ST_ROUND_OUT=0)
+residual streams — the measurement behind TOL_MODEL in tests/test_gpu_model.py.  python tools/model_err.py"""
 import sys, torch
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 import speech_tranformer_pytorch_b200 as stb
