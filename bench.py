@@ -195,7 +195,10 @@ def main_b200(args):
 
     import speech_tranformer_pytorch_b200 as stb
     from speech_tranformer_pytorch_b200 import data as sdata, model as smodel, parallel as spar
-    stb.build()
+    if local == 0:
+        stb.build()                      # one builder per node: ranks must not run nvcc into the same objects concurrently
+    if world > 1:
+        dist.barrier()
     lib = stb._lib.load()
     stb._lib.check(lib.st_device_check(local))
 
