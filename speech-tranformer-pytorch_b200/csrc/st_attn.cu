@@ -233,58 +233,88 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   k_loads = 1;
 
-  float o[OH];
-#pragma unroll
-  for (int i = 0; i < OH; ++i) o[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  // Online softmax, ONE read of S per tile.  The output accumulates in TMEM (P·V with the accumulate flag) in units of
+  // exp2(-m_ref): the reference maximum m_ref is only advanced — and O / l rescaled — when a tile's maximum exceeds it by
+  // more than TAU (probabilities stay <= 2^TAU, harmless in fp32 / TF32), which after the first tiles is rare.  This
+  // removes the second tcgen05.ld sweep over S, the per-tile read-back of O and its 32-FMA register update, and lets
+  // S(j+1) be queued right behind P·V(j) on the tensor pipe.
+  constexpr float TAU = 8.f;
+  float m_ref = -INFINITY, l_run = 0.f;
   const uint64_t rng_row = (static_cast<uint64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
   const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, rng_row) : 0u;
 
   for (int j = 0; j < n_kv; ++j) {
-    mbar_wait(&bar_s, s_count & 1);
+    mbar_wait(&bar_s, s_count & 1);   // S_j complete; the tensor pipe is in order, so P·V(j-1) has completed too
     ++s_count;
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) load_k(j + 1);  // S_j has consumed K_j
+    if (warp == 0) {
+      if (elect_one()) {
+        if (j + 1 < n_kv) load_k(j + 1);   // S_j has consumed K_j
+        if (j > 0) load_v(j);              // P·V(j-1) has consumed V_{j-1}
+      }
+      __syncwarp();
+    }
     if (p.drop_thresh && tid < BKV) s_ckey[tid] = dropout_col_key(p.drop_seed, static_cast<uint32_t>(j * BKV + tid));
     if (shared_mask && tid < BKV / 32 && j + 1 < n_kv)
       s_mb[(j + 1) & 1][tid] = mask_bits_row(p, b, 0, true, (j + 1) * BKV + tid * 32);
 
-    // ---- pass 1: row max over this thread's half of the tile, combined through smem
+    // ---- this thread's half of the score row, read once
     uint32_t mbits[NCH];
+    uint32_t r[NCH][32];
     float mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col0 = half * SH + c * 32;
       mbits[c] = shared_mask ? s_mb[j & 1][col0 / 32] : mask_bits_row(p, b, row, row_ok, j * BKV + col0);
-      uint32_t r[32];
-      tmem_ld32(t_lane + T_S + col0, r);
-      tmem_ld_wait();
-      mx = fmaxf(mx, chunk_max(r, mbits[c]));
+      tmem_ld32(t_lane + T_S + col0, r[c]);
     }
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) mx = fmaxf(mx, chunk_max(r[c], mbits[c]));
     s_part[half][rit] = mx;
     __syncthreads();
     mx = fmaxf(s_part[0][rit], s_part[1][rit]) * p.scale_log2;
-    const float m_new = fmaxf(m_run, mx);
-    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-    const float alpha = fast_exp2(m_run - m_use);  // m_run == -inf -> 0
-    // ---- pass 2: probabilities -> TMEM (A operand of P·V), row sum
+    // ---- advance the reference maximum only when needed; rescale l and (warp-collectively) this thread's half of O
+    const bool need = mx > m_ref + TAU || (m_ref == -INFINITY && mx > -INFINITY);
+    if (__any_sync(0xffffffffu, need)) {
+      const float alpha = need ? fast_exp2(m_ref - mx) : 1.f;   // m_ref == -inf -> 0
+      if (j > 0) {
+        if constexpr (OH >= 32) {
+#pragma unroll
+          for (int c = 0; c < OH / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_lane + T_O + half * OH + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(need ? __uint_as_float(o[i]) * alpha : __uint_as_float(o[i]));
+            tmem_st32(t_lane + T_O + half * OH + c * 32, o);
+          }
+        } else {
+          uint32_t o[16];
+          tmem_ld16(t_lane + T_O + half * OH, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(need ? __uint_as_float(o[i]) * alpha : __uint_as_float(o[i]));
+          tmem_st16(t_lane + T_O + half * OH, o);
+        }
+      }
+      if (need) { l_run *= alpha; m_ref = mx; }
+    }
+    const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+    // ---- probabilities -> TMEM (A operand of P·V), row sum
     float l_tile = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col0 = half * SH + c * 32;
-      uint32_t r[32];
-      tmem_ld32(t_lane + T_S + col0, r);
-      tmem_ld_wait();
-      l_tile += chunk_probs(r, mbits[c], p.scale_log2, m_use, p.drop_thresh, drop_key, s_ckey + col0);
-      tmem_st32(t_lane + T_S + col0, r);
+      l_tile += chunk_probs(r[c], mbits[c], p.scale_log2, m_use, p.drop_thresh, drop_key, s_ckey + col0);
+      tmem_st32(t_lane + T_S + col0, r[c]);
     }
-    l_run = l_run * alpha + l_tile;
-    m_run = m_new;
+    l_run += l_tile;
     tmem_st_wait();
     tc_fence_before();
     __syncthreads();
 
-    if (warp == 0) {  // O_tile = P V   (A = P in TMEM, B = V MN-major)
+    if (warp == 0) {  // O += P V   (A = P in TMEM, B = V MN-major), then S_{j+1} right behind it
       tc_fence_after();
       mbar_wait(&bar_v, j & 1);
       tc_fence_after();
@@ -293,55 +323,59 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint64_t bv0 = umma_desc_mnmajor(smem_u32(sV), BKV * 128);
 #pragma unroll
         for (int ks = 0; ks < BKV / 8; ++ks)
-          umma_tf32_ts(tmem + T_O, tmem + T_S + ks * 8, bv0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc, ks > 0 ? 1u : 0u);
-        umma_commit(&bar_o);
+          umma_tf32_ts(tmem + T_O, tmem + T_S + ks * 8, bv0 + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+                       (j > 0 || ks > 0) ? 1u : 0u);
+        if (j + 1 == n_kv) umma_commit(&bar_o);
       }
       __syncwarp();
-    }
-    mbar_wait(&bar_o, j & 1);
-    tc_fence_after();
-    if (warp == 0 && j + 1 < n_kv) {
-      if (elect_one()) load_v(j + 1);      // P·V has consumed V_j
-      __syncwarp();
-      mbar_wait(&bar_k, k_loads & 1);      // K_{j+1}
-      tc_fence_after();
-      if (elect_one()) issue_s();          // overlaps the O accumulation below
-      __syncwarp();
+      if (j + 1 < n_kv) {
+        mbar_wait(&bar_k, k_loads & 1);      // K_{j+1}
+        tc_fence_after();
+        if (elect_one()) issue_s();
+        __syncwarp();
+      }
     }
     if (j + 1 < n_kv) ++k_loads;
-    // ---- O += alpha-corrected accumulate in registers (this thread's half of the head dim)
-    if constexpr (OH >= 32) {
-#pragma unroll
-      for (int c = 0; c < OH / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_lane + T_O + half * OH + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
-      }
-    } else {
-      uint32_t r[16];
-      tmem_ld16(t_lane + T_O + half * OH, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(r[i]));
-    }
   }
 
   // ---- finalize: ctx = O / l (NaN for a fully masked row: 0 * inf), lse
+  mbar_wait(&bar_o, 0);
+  tc_fence_after();
   __syncthreads();
   s_part[half][rit] = l_run;
   __syncthreads();
   const float l_tot = s_part[0][rit] + s_part[1][rit];
   const float inv_l = (p.drop_thresh ? p.drop_scale : 1.f) / l_tot;   // inverted-dropout scale folded in here
-  const float lse2 = m_run + log2f(l_tot);
-  if (row_ok) {
-    float* dst = p.ctx + (static_cast<int64_t>(b) * p.Lq + row) * p.ldctx + h * DK + half * OH;
+  const float lse2 = m_ref + log2f(l_tot);
+  {
+    float* dst = p.ctx + (static_cast<int64_t>(b) * p.Lq + (row_ok ? row : 0)) * p.ldctx + h * DK + half * OH;
+    if constexpr (OH >= 32) {
 #pragma unroll
-    for (int i = 0; i < OH; i += 4)
-      *reinterpret_cast<float4*>(dst + i) = make_float4(tf32_rna(o[i] * inv_l), tf32_rna(o[i + 1] * inv_l),
-                                                        tf32_rna(o[i + 2] * inv_l), tf32_rna(o[i + 3] * inv_l));
-    if (half == 0) p.lse2[(static_cast<int64_t>(b) * p.H + h) * p.Lq + row] = lse2;
+      for (int c = 0; c < OH / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(t_lane + T_O + half * OH + c * 32, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + c * 32 + i) =
+                make_float4(tf32_rna(__uint_as_float(o[i]) * inv_l), tf32_rna(__uint_as_float(o[i + 1]) * inv_l),
+                            tf32_rna(__uint_as_float(o[i + 2]) * inv_l), tf32_rna(__uint_as_float(o[i + 3]) * inv_l));
+        }
+      }
+    } else {
+      uint32_t o[16];
+      tmem_ld16(t_lane + T_O + half * OH, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(dst + i) =
+              make_float4(tf32_rna(__uint_as_float(o[i]) * inv_l), tf32_rna(__uint_as_float(o[i + 1]) * inv_l),
+                          tf32_rna(__uint_as_float(o[i + 2]) * inv_l), tf32_rna(__uint_as_float(o[i + 3]) * inv_l));
+      }
+    }
+    if (row_ok && half == 0) p.lse2[(static_cast<int64_t>(b) * p.H + h) * p.Lq + row] = lse2;
   }
 
   // ---- optional second sweep: materialise the (post-dropout) probabilities the module returns
