@@ -44,6 +44,7 @@ const char* st_profile_class_name(int cls);
 int st_profile_read(int cls, double* ms /* host */, double* work /* host */, int64_t* launches /* host */);
 /* debug: clock64() timeline of one CTA of the attention dK/dV kernel (option "attn_trace"); returns the slot count */
 int st_debug_read_trace(uint64_t* host_out /* host */, int n);
+int st_debug_read_fwd_trace(uint64_t* host_out /* host */, int n);   /* same for thread 0 of the forward kernel: [tile][8 events] */
 /* debug: cycles per tcgen05.mma (M=128, N=n, K=8, kind::tf32) issued back to back by one CTA.
  * variant bit 0: A operand from TMEM (.ts) instead of shared memory; bit 1: B operand MN-major instead of K-major. */
 int st_debug_mma_bench(int variant, int n, int iters, double* clk_per_mma /* host */);

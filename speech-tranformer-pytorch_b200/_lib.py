@@ -119,6 +119,7 @@ SIGNATURES = {
     "st_profile_class_name": (C.c_char_p, [C.c_int]),
     "st_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
     "st_debug_read_trace": (C.c_int, [C.POINTER(u64), C.c_int]),
+    "st_debug_read_fwd_trace": (C.c_int, [C.POINTER(u64), C.c_int]),
     "st_debug_mma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "st_selftest_count": (C.c_int, []),
     "st_selftest": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),

@@ -211,6 +211,7 @@ int st_profile_read(int cls, double* ms, double* work, int64_t* launches) {
   *launches = n;
   return st;
 }
+int st_debug_read_fwd_trace(uint64_t* host_out, int n) { return attn_read_fwd_trace(reinterpret_cast<unsigned long long*>(host_out), n); }
 int st_debug_read_trace(uint64_t* host_out, int n) { return attn_read_trace(reinterpret_cast<unsigned long long*>(host_out), n); }
 int st_debug_mma_bench(int variant, int n, int iters, double* clk_per_mma) { return mma_bench(variant, n, iters, clk_per_mma); }
 int st_selftest_count(void) { return selftest_count(); }

@@ -32,6 +32,14 @@ namespace st {
 
 namespace {
 
+// in-kernel timeline of CTA (0,0,0), thread 0 of the forward kernel (option "attn_trace"): [tile][event] clock64 stamps
+constexpr int FTRACE_TILES = 16, FTRACE_EVENTS = 8;
+__device__ unsigned long long g_ftrace[FTRACE_TILES * FTRACE_EVENTS];
+#define ST_FTRACE(tile, ev)                                                                                   \
+  do {                                                                                                        \
+    if (ftrace_on && (tile) < FTRACE_TILES) g_ftrace[(tile) * FTRACE_EVENTS + (ev)] = clock64();              \
+  } while (0)
+
 __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], uint32_t mb) {
   float mx = -INFINITY;
   if (mb == 0u) {
@@ -240,13 +248,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // S(j+1) be queued right behind P·V(j) on the tensor pipe.
   constexpr float TAU = 8.f;
   float m_ref = -INFINITY, l_run = 0.f;
+  const bool ftrace_on = p.trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   const uint64_t rng_row = (static_cast<uint64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
   const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, rng_row) : 0u;
 
   for (int j = 0; j < n_kv; ++j) {
+    ST_FTRACE(j, 0);
     mbar_wait(&bar_s, s_count & 1);   // S_j complete; the tensor pipe is in order, so P·V(j-1) has completed too
     ++s_count;
     tc_fence_after();
+    ST_FTRACE(j, 1);
     if (warp == 0) {
       if (elect_one()) {
         if (j + 1 < n_kv) load_k(j + 1);   // S_j has consumed K_j
@@ -269,10 +280,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_ld32(t_lane + T_S + col0, r[c]);
     }
     tmem_ld_wait();
+    ST_FTRACE(j, 2);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) mx = fmaxf(mx, chunk_max(r[c], mbits[c]));
     s_part[half][rit] = mx;
     __syncthreads();
+    ST_FTRACE(j, 3);
     mx = fmaxf(s_part[0][rit], s_part[1][rit]) * p.scale_log2;
     // ---- advance the reference maximum only when needed; rescale l and (warp-collectively) this thread's half of O
     const bool need = mx > m_ref + TAU || (m_ref == -INFINITY && mx > -INFINITY);
@@ -311,13 +324,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     l_run += l_tile;
     tmem_st_wait();
+    ST_FTRACE(j, 4);
     tc_fence_before();
     __syncthreads();
+    ST_FTRACE(j, 5);
 
     if (warp == 0) {  // O += P V   (A = P in TMEM, B = V MN-major), then S_{j+1} right behind it
       tc_fence_after();
       mbar_wait(&bar_v, j & 1);
       tc_fence_after();
+      ST_FTRACE(j, 6);
       if (elect_one()) {
         constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
         const uint64_t bv0 = umma_desc_mnmajor(smem_u32(sV), BKV * 128);
@@ -335,6 +351,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
       }
     }
+    ST_FTRACE(j, 7);
     if (j + 1 < n_kv) ++k_loads;
   }
 
@@ -789,6 +806,13 @@ int check_attn(const AttnArgs& a, const char* who) {
 // Measured on B200 (6+6 x 512, B=32, T=1000): accumulating the bias column sums from the dK/dV and dQ epilogues costs more
 // (same-address L2 reductions from 2048 CTAs: dkv +14 %, dq +5 %) than the separate 35 us column-sum pass it replaces,
 // so it is opt-in (option "attn_fuse_bias"); the GEMM-epilogue fusion of the FFN bias gradient is always on.
+int attn_read_fwd_trace(unsigned long long* host_out, int n) {
+  const int total = FTRACE_TILES * FTRACE_EVENTS;
+  ST_CHECK_CUDA(cudaDeviceSynchronize());
+  ST_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_ftrace, sizeof(unsigned long long) * (n < total ? n : total)));
+  return total;
+}
+
 bool attn_bwd_fuses_bias(int dk) { return get_option("attn_fuse_bias") && dk <= 64 && !get_option("attn_bwd_simple"); }
 
 AttnDev attn_to_dev(const AttnArgs& a) {
@@ -816,7 +840,9 @@ int launch_fwd(cudaStream_t s, const AttnArgs& a) {
   if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
   dim3 grid((a.Lq + 127) / 128, a.H, a.B);
   ProfScope prof(s, PROF_ATTN_FWD, 4.0 * a.B * a.H * static_cast<double>(a.Lq) * a.Lk * DK);
-  kern<<<grid, 256, SMEM, s>>>(tq, tk, tv, attn_to_dev(a));
+  AttnDev dev = attn_to_dev(a);
+  dev.trace = get_option("attn_trace");
+  kern<<<grid, 256, SMEM, s>>>(tq, tk, tv, dev);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }

@@ -62,5 +62,6 @@ AttnDev attn_to_dev(const AttnArgs& a);
 // st_attn_bwd.cu: pipelined dQ and dK/dV kernels for d_k in {32, 64}; p already carries the backward pointers
 int attn_bwd_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p);
 int attn_read_trace(unsigned long long* host_out, int n);   // returns the number of slots
+int attn_read_fwd_trace(unsigned long long* host_out, int n);
 
 }  // namespace st
