@@ -217,6 +217,13 @@ int st_embed_fwd(const int64_t* idx, const float* table, const float* pe, int64_
 int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab, int64_t padding_idx,
                  int zero_first, cudaStream_t stream);
 
+/* Incremental-decode self-attention (Decode.py:48-179 decodes the full prefix every step; this is the K/V-reuse form):
+ * qkv (n, 3*H*dk) = [q | k | v] projections of the ONE new position of each of the n hypotheses.  Appends k, v as
+ * row t of the time-major caches (L_max, n, H*dk) and writes ctx (n, H*dk) = softmax(q K[0..t]^T / sqrt(dk)) V[0..t]
+ * per head (Attention.py:78-90 with Lq = 1; no mask: every cached position is in the past).                      */
+int st_decode_self_attn(const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk, float* ctx,
+                        int round_tf32, cudaStream_t stream);
+
 /* Encoder input front-end (Models.py:28-33,42-44):
  *   out = LayerNorm(Dropout(ReLU(x W^T + b))) * gamma + beta + pe[frame index]
  * x: (rows, in_dim) with rows = B*T and frame index = row mod T; in_dim a multiple of 4 (80 for fbank).

@@ -590,6 +590,11 @@ int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n
   return embed_bwd(stream, idx, dout, dtable, n, d, vocab, padding_idx, zero_first);
 }
 
+int st_decode_self_attn(const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk, float* ctx,
+                        int round_tf32, cudaStream_t stream) {
+  return decode_self_attn(stream, qkv, k_cache, v_cache, t, n, H, dk, ctx, round_tf32);
+}
+
 // ------------------------------------------------------------------ encoder input front-end (Models.py:28-33,42-44)
 namespace {
 struct FrontPlan { float *x_r, *w_r, *h, *mean, *rstd; };

@@ -77,3 +77,82 @@ int embed_bwd(cudaStream_t stream, const int64_t* idx, const float* dout, float*
 }
 
 }  // namespace st
+
+// ------------------------------------------------------------------------------------------------------------------
+// Incremental-decode self-attention: ONE new query position per hypothesis attends to the cached
+// keys / values of positions 0..t (Attention.py:78-90 with Lq = 1; no mask is needed — everything cached is in the
+// past).  The tensor-core kernel would run a 128-row tile for a single valid row; here one warp owns one
+// (hypothesis, head): it appends the new K / V rows to the time-major caches (L_max, n, d), then streams the t + 1
+// cached rows with an online softmax in fp32.  qkv is the packed projection output (n, 3d) = [q | k | v].
+namespace st {
+namespace {
+
+template <int DK>
+__global__ void __launch_bounds__(256)
+decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ k_cache, float* __restrict__ v_cache, int t, int n,
+                        int H, float scale_log2, float* __restrict__ ctx, int round_out) {
+  constexpr int E = DK / 32;                       // elements per lane
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= n * H) return;                          // warp-uniform
+  const int hyp = w / H, h = w - hyp * H;
+  const int d = H * DK;
+  const int64_t row_stride = static_cast<int64_t>(n) * d;          // cache row (one position, all hypotheses)
+  const int64_t off = static_cast<int64_t>(hyp) * d + h * DK + lane * E;
+  float q[E], kn[E], vn[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    q[e] = qkv[static_cast<int64_t>(hyp) * 3 * d + h * DK + lane * E + e];
+    kn[e] = qkv[static_cast<int64_t>(hyp) * 3 * d + d + h * DK + lane * E + e];
+    vn[e] = qkv[static_cast<int64_t>(hyp) * 3 * d + 2 * d + h * DK + lane * E + e];
+    k_cache[t * row_stride + off + e] = kn[e];
+    v_cache[t * row_stride + off + e] = vn[e];
+  }
+  float m = -INFINITY, l = 0.f, acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+  for (int j = 0; j <= t; ++j) {
+    float kk[E], vv[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      kk[e] = (j == t) ? kn[e] : k_cache[j * row_stride + off + e];
+      vv[e] = (j == t) ? vn[e] : v_cache[j * row_stride + off + e];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s = fmaf(q[e], kk[e], s);
+    s = warp_sum(s) * scale_log2;
+    const float m_new = fmaxf(m, s);
+    const float alpha = exp2f(m - m_new);          // m == -inf -> 0
+    const float p = exp2f(s - m_new);
+    l = l * alpha + p;
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = fmaf(acc[e], alpha, p * vv[e]);
+    m = m_new;
+  }
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const float o = acc[e] * inv;
+    ctx[off + e] = round_out ? tf32_rna(o) : o;
+  }
+}
+
+}  // namespace
+
+int decode_self_attn(cudaStream_t stream, const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk,
+                     float* ctx, int round_out) {
+  ST_REQUIRE(n > 0 && H > 0 && t >= 0, "decode_self_attn: bad shape (n=%d H=%d t=%d)", n, H, t);
+  ST_REQUIRE(dk == 32 || dk == 64 || dk == 128, "decode_self_attn: d_k must be 32, 64 or 128 (got %d)", dk);
+  const int warps = n * H;
+  const int grid = (warps + 7) / 8;
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
+  ProfScope prof(stream, PROF_ATTN_FWD, 4.0 * n * H * static_cast<double>(t + 1) * dk);
+  if (dk == 32) decode_self_attn_kernel<32><<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out);
+  else if (dk == 64) decode_self_attn_kernel<64><<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out);
+  else decode_self_attn_kernel<128><<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+}  // namespace st

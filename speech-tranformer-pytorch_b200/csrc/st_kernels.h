@@ -32,6 +32,9 @@ int embed_fwd(cudaStream_t stream, const int64_t* idx, const float* table, const
 int embed_bwd(cudaStream_t stream, const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab,
               int64_t padding_idx, int zero_first);
 
+int decode_self_attn(cudaStream_t stream, const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk,
+                     float* ctx, int round_out);
+
 // ---- st_ctc.cu
 int64_t ctc_ws_floats(int B, int T, int S_max);
 int ctc_fwd_bwd(cudaStream_t stream, const float* logits, int64_t ld, const int64_t* targets, int64_t ld_tgt,

@@ -10,8 +10,10 @@ decode path those files describe, built for the B200 library:
   * self-attention K/V of already decoded positions live in a time-major cache (L_max, B*beam, d); appending a step
     writes one contiguous row, and a step attends with Lq = 1 over Lk = t + 1 by presenting the (hypothesis, head)
     pairs as B*beam*h heads of a single batch — no re-packing, no mask;
-  * one decoder step = the new token only: 5 projection GEMMs + 2 attention calls + 2 residual-LayerNorms + the fused
-    FFN per layer, all from libst_b200.so (st_gemm / st_attn_fwd / st_add_ln_fwd / st_ffn_fwd / st_embed_fwd);
+  * one decoder step = the new token only: per layer one packed QKV GEMM, the single-query self-attention kernel
+    (st_decode_self_attn: a warp per (hypothesis, head) appends K/V and streams the cache), 3 more projection GEMMs, the
+    tensor-core cross-attention, 2 residual-LayerNorms and the fused FFN, all from libst_b200.so; weights are rounded
+    to TF32 ONCE when the decoder is built (they are a snapshot: rebuild the decoder after further training);
   * beam bookkeeping (Beam.advance: add scores, top-k over beam x vocab, integer-floor back-pointer, Beam.py:43-74)
     stays on the device; the host only polls an "all finished" flag;
   * a decode step is ~95 small launches (launch-bound), so a decoder object kept across batches of one shape
@@ -63,7 +65,8 @@ class _Linear:
 class _LayerWeights:
     def __init__(self, layer):
         sa, ca, ff = layer.slf_attn, layer.enc_attn, layer.pos_ffn
-        self.q, self.k, self.v = (_Linear(m.weight, m.bias) for m in (sa.linear_q, sa.linear_k, sa.linear_v))
+        self.qkv = _Linear(torch.cat([sa.linear_q.weight, sa.linear_k.weight, sa.linear_v.weight], 0),
+                           torch.cat([sa.linear_q.bias, sa.linear_k.bias, sa.linear_v.bias], 0))      # one GEMM, N = 3d
         self.so = _Linear(sa.output_linear.weight, sa.output_linear.bias)
         self.s_ln = (sa.layernorm.weight.detach(), sa.layernorm.bias.detach(), sa.layernorm.eps)
         self.cq = _Linear(ca.linear_q.weight, ca.linear_q.bias)
@@ -71,6 +74,7 @@ class _LayerWeights:
         self.co = _Linear(ca.output_linear.weight, ca.output_linear.bias)
         self.c_ln = (ca.layernorm.weight.detach(), ca.layernorm.bias.detach(), ca.layernorm.eps)
         self.ffn = ff
+        self.w1_r, self.w2_r = F.round_tf32(ff.fc1.weight.detach()), F.round_tf32(ff.fc2.weight.detach())
         self.n_head = sa.n_head
 
 
@@ -147,6 +151,20 @@ class IncrementalDecoder:
                                      F._stream()))
         return F.mark_tf32_clean(out)
 
+    def _ffn(self, lw, x):
+        f, lib = lw.ffn, self.lib
+        rows, d = x.shape
+        d_ff = f.fc1.weight.shape[0]
+        n_saved = lib.st_ffn_saved_floats(rows, d, d_ff, 1)
+        saved = torch.empty(n_saved, device=x.device, dtype=torch.float32)
+        out = torch.empty_like(x)
+        a = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(x), w1=_p(f.fc1.weight), b1=_p(f.fc1.bias), w2=_p(f.fc2.weight),
+                         b2=_p(f.fc2.bias), ln_g=_p(f.layernorm.weight), ln_b=_p(f.layernorm.bias), eps=float(f.layernorm.eps),
+                         dropout_p=0.0, seed=0, x_is_tf32=1, round_out=1, out=_p(out), saved=_p(saved), saved_floats=n_saved,
+                         ws=None, ws_floats=0, w1_tf32=_p(lw.w1_r), w2_tf32=_p(lw.w2_r))
+        check(lib.st_ffn_fwd(C.byref(a), F._stream()))
+        return F.mark_tf32_clean(out)
+
     # ---- one target position -----------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, tokens: torch.Tensor, parent: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -190,20 +208,17 @@ class IncrementalDecoder:
         for i, lw in enumerate(self.layers):
             H = lw.n_head
             # masked self-attention over the cached positions 0..t (Layers.py:37-38): q of the new token only
-            q = lw.q(lib, x, new(n, d))
-            lw.k(lib, x, st["k"][i][t])                      # append: one contiguous (n, d) row of the time-major cache
-            lw.v(lib, x, st["v"][i][t])
-            ctx = self._attn(1, n * H, 1, t + 1, q, n * d, st["k"][i], n * d, st["v"][i], n * d, None, new(n, d))
+            qkv = lw.qkv(lib, x, new(n, 3 * d))
+            ctx = new(n, d)
+            check(lib.st_decode_self_attn(_p(qkv), _p(st["k"][i]), _p(st["v"][i]), t, n, H, d // H, _p(ctx), 1, F._stream()))
             a = self._ln(lw.so(lib, ctx, new(n, d), residual=x, round_out=False), lw.s_ln, new(n, d))
             # cross-attention: the beams of an utterance are the query rows; K/V of the encoder output are shared
             q2 = lw.cq(lib, a, new(n, d))
             kv = st["cross_kv"][i]
             ctx2 = self._attn(B, H, beam, T, q2, d, kv, 2 * d, kv[:, d:], 2 * d, st["cross_mask"], new(n, d))
             c = self._ln(lw.co(lib, ctx2, new(n, d), residual=a, round_out=False), lw.c_ln, new(n, d))
-            # position-wise FFN (fused operator, SubLayers.py:24-28)
-            f = lw.ffn
-            x = F.positionwise_ffn(c, f.fc1.weight, f.fc1.bias, f.fc2.weight, f.fc2.bias, f.layernorm.weight, f.layernorm.bias,
-                                   eps=f.layernorm.eps, dropout_p=0.0, seed=0, round_out=True)
+            # position-wise FFN (fused operator, SubLayers.py:24-28) with the decoder's pre-rounded weights
+            x = self._ffn(lw, c)
         st["t"] = t + 1
         ldy = (self.vocab + 3) // 4 * 4
         logits = torch.empty(n, ldy, device=dev, dtype=torch.float32)
