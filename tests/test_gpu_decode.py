@@ -96,3 +96,29 @@ def test_cuda_graph_replay_is_bit_identical(stb):
     want = beam_search(net, other, in_len.flip(0).contiguous(), beam=4, max_len=10, n_best=2, eos=3)
     got = beam_search(net, other, in_len.flip(0).contiguous(), beam=4, max_len=10, n_best=2, eos=3, decoder=dec)
     assert got[0] == want[0] and torch.equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("n,H,dk,t", [(6, 2, 32, 0), (20, 8, 64, 17), (3, 4, 128, 49)])
+def test_decode_self_attention_kernel(stb, n, H, dk, t):
+    """st_decode_self_attn (one new query per hypothesis over the time-major K/V cache) against softmax(q K^T / sqrt(dk)) V
+    in float64, for every supported head width; also checks that the new K/V rows were appended at position t."""
+    import ctypes as C
+    lib = stb._lib.load()
+    d = H * dk
+    g = torch.Generator().manual_seed(n + t)
+    L_max = 50
+    kc = torch.randn(L_max, n, d, generator=g)
+    vc = torch.randn(L_max, n, d, generator=g)
+    qkv = torch.randn(n, 3 * d, generator=g)
+    kcd, vcd, qd = kc.to(DEV), vc.to(DEV), qkv.to(DEV)
+    ctx = torch.empty(n, d, device=DEV)
+    stb._lib.check(lib.st_decode_self_attn(qd.data_ptr(), kcd.data_ptr(), vcd.data_ptr(), t, n, H, dk, ctx.data_ptr(), 0,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(kcd[t].cpu(), qkv[:, d:2 * d]) and torch.equal(vcd[t].cpu(), qkv[:, 2 * d:])
+    assert torch.equal(kcd[:t].cpu(), kc[:t]) and torch.equal(vcd[t + 1:].cpu(), vc[t + 1:])      # nothing else touched
+    K = torch.cat([kc[:t], qkv[None, :, d:2 * d]], 0).double().view(t + 1, n, H, dk)
+    V = torch.cat([vc[:t], qkv[None, :, 2 * d:]], 0).double().view(t + 1, n, H, dk)
+    q = qkv[:, :d].double().view(n, H, dk)
+    s = torch.einsum("nhd,tnhd->nht", q, K) / dk ** 0.5
+    ref = torch.einsum("nht,tnhd->nhd", torch.softmax(s, -1), V).reshape(n, d)
+    assert relerr(ctx, ref) < 1e-5
