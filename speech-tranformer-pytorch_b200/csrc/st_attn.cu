@@ -184,7 +184,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int row = q0 + rit;
   const bool row_ok = row < p.Lq;
-  const int n_kv = (p.Lk + BKV - 1) / BKV;
+  const int n_kv_all = (p.Lk + BKV - 1) / BKV;
+  __shared__ int s_extent;
+  const int extent = block_key_extent(p, b, &s_extent);
+  // key tiles that lie entirely in the padding of this utterance contribute exactly nothing: skip them (at least one
+  // tile is always processed so that a fully masked row still produces the reference's NaN)
+  const int n_kv = extent >= p.Lk ? n_kv_all : max(1, (extent + BKV - 1) / BKV);
   // key-padding masks (stride 0 over queries, Utils.py:53-54) and "no mask" give every row of the tile the same
   // bits: compute them once per tile (one thread per 32-key chunk), one tile ahead
   const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
@@ -397,7 +402,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   // ---- optional second sweep: materialise the (post-dropout) probabilities the module returns
   if (p.attn != nullptr) {
-    for (int j = 0; j < n_kv; ++j) {
+    for (int j = 0; j < n_kv_all; ++j) {   // every key tile: masked columns of the returned weights are written as zeros
       tc_fence_before();
       __syncthreads();  // every thread is done with the S region / previous sweep step
       if (warp == 0) {

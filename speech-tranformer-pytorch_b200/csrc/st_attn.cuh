@@ -55,6 +55,24 @@ __device__ __forceinline__ uint32_t mask_bits_row(const AttnDev& p, int b, int r
   return bits;
 }
 
+// Key extent of batch `b` under a key-padding mask (one mask row shared by all queries, ms_q == 0 — what
+// Utils.padding_info_mask builds): 1 + index of the last unmasked key, 0 if every key is masked; Lk when there is no
+// mask or the mask depends on the query.  Keys at or beyond the extent have probability exactly 0 for every query, so
+// whole key tiles beyond it can be skipped without changing any result (ragged batches: utterances shorter than T_max).
+// Called by ALL threads of the block (two __syncthreads inside); `slot` is a shared int.
+__device__ __forceinline__ int block_key_extent(const AttnDev& p, int b, int* slot) {
+  if (p.mask == nullptr || p.ms_q != 0) return p.Lk;
+  if (threadIdx.x == 0) *slot = 0;
+  __syncthreads();
+  const uint8_t* m = p.mask + b * p.ms_b;
+  int last = 0;
+  for (int j = threadIdx.x; j < p.Lk; j += blockDim.x)
+    if (m[static_cast<int64_t>(j) * p.ms_k] == 0) last = j + 1;
+  if (last) atomicMax(slot, last);
+  __syncthreads();
+  return *slot;
+}
+
 // host helpers (st_attn.cu)
 int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32, int dk);
 AttnDev attn_to_dev(const AttnArgs& a);

@@ -180,7 +180,10 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (p.Lk + BT - 1) / BT;
+  __shared__ int s_extent;
+  const int extent = block_key_extent(p, b, &s_extent);
+  // key tiles entirely inside this utterance's padding have dS == 0: skipped (see block_key_extent)
+  const int n_kv = extent >= p.Lk ? (p.Lk + BT - 1) / BT : max(1, (extent + BT - 1) / BT);
   const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
 
   if (tid == 0) {
@@ -384,6 +387,22 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
   const int n_q = (p.Lq + BT - 1) / BT;
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   if (p.trace && tid == 0 && cta_lin < TRACE_CTAS) { g_cta_trace[cta_lin * 4] = global_ns(); g_cta_trace[cta_lin * 4 + 2] = sm_id(); }
+  {
+    // a key tile entirely inside this utterance's padding: dK = dV = 0 for its rows, nothing to compute
+    __shared__ int s_extent;
+    const int extent = block_key_extent(p, b, &s_extent);
+    if (extent > 0 && kv0 >= extent) {
+      const int rows = min(BKV, p.Lk - kv0);
+      for (int i = tid; i < rows * (DK / 4); i += NTHREADS) {
+        const int r = i / (DK / 4), c = (i - r * (DK / 4)) * 4;
+        const int64_t grow = static_cast<int64_t>(b) * p.Lk + kv0 + r;
+        *reinterpret_cast<float4*>(p.dk + grow * p.lddk + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(p.dv + grow * p.lddv + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (p.trace && tid == 0 && cta_lin < TRACE_CTAS) g_cta_trace[cta_lin * 4 + 1] = global_ns();
+      return;
+    }
+  }
   const bool trace_on = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
   if (tid == 0) {
