@@ -189,6 +189,41 @@ def test_attention_core(stb, B, H, Lq, Lk, dk, kind):
         assert relerr(a, b) < TOL_ATTN, n
 
 
+@pytest.mark.parametrize("Lq,Lk,klens,H,dk", [(300, 300, [300, 40, 129], 2, 64), (20, 700, [700, 65, 1], 4, 64),
+                                                 (260, 260, [260, 128, 0], 2, 32), (70, 400, [400, 3, 257], 2, 128)])
+def test_attention_skips_padded_key_tiles_exactly(stb, Lq, Lk, klens, H, dk):
+    """Very ragged key-padding masks: the kernels stop at the utterance's last valid key tile (block_key_extent) — the
+    results must still match the oracle everywhere, including an utterance with a single valid key and one with none
+    (all keys masked: NaN outputs like the reference; its gradients are not compared)."""
+    F = stb.functional
+    B, d = len(klens), H * dk
+    gen = torch.Generator().manual_seed(Lq + Lk)
+    q, k, v, g = (torch.randn(B, L, d, generator=gen) for L in (Lq, Lk, Lk, Lq))
+    mask = O.padding_info_mask(torch.full((B,), Lq), torch.tensor([max(x, 1) for x in klens])).bool()
+    if Lk != mask.shape[2]:                      # the reference builds the mask only up to the longest length: pad to Lk
+        mask = torch.cat([mask, torch.ones(B, Lq, Lk - mask.shape[2], dtype=torch.bool)], 2)
+    for b, x in enumerate(klens):
+        if x == 0:
+            mask[b] = True
+    sh = lambda x: x.view(B, -1, H, dk).transpose(1, 2).reshape(B * H, -1, dk)
+    rq, rk, rv = (x.clone().double().requires_grad_() for x in (q, k, v))
+    o, w = O.scaled_dot_product_attention(sh(rq), sh(rk), sh(rv), mask.unsqueeze(1).expand(B, H, Lq, Lk).reshape(B * H, Lq, Lk), dk)
+    ro = o.view(B, H, Lq, dk).transpose(1, 2).reshape(B, Lq, d)
+    ok = torch.tensor([x > 0 for x in klens])
+    ro[ok].backward(g[ok].double())
+    cq, ck, cv = (x.to(DEV).requires_grad_() for x in (q, k, v))
+    co, cw = F.attention_core(cq, ck, cv, mask.to(DEV), n_head=H, need_attn=True)
+    co[ok.to(DEV)].backward(g[ok].to(DEV))
+    assert relerr(co, ro) < TOL_ATTN                     # NaN rows must coincide (relerr checks the NaN pattern)
+    assert relerr(cw, w.view(B, H, Lq, Lk)) < TOL_ATTN
+    assert torch.all(cw.cpu()[ok][mask[ok].unsqueeze(1).expand(-1, H, -1, -1)] == 0)
+    for a, b_, n in ((cq.grad, rq.grad, "dq"), (ck.grad, rk.grad, "dk"), (cv.grad, rv.grad, "dv")):
+        assert relerr(a[ok.to(DEV)], b_[ok]) < TOL_ATTN, n
+        for b, x in enumerate(klens):                    # keys beyond the extent: exactly zero gradient
+            if x > 0 and n != "dq":
+                assert torch.count_nonzero(a[b, x:]).item() == 0, (n, b)
+
+
 @pytest.mark.parametrize("B,H,L,dk", [(2, 4, 200, 64), (1, 2, 130, 32), (1, 2, 70, 128)])
 def test_attention_dropout_forward_backward_consistent(stb, B, H, L, dk):
     """Dropout on the attention probabilities (Attention.py:89): the reference RNG stream cannot be matched, so
