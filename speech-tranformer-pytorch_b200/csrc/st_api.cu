@@ -670,24 +670,24 @@ int st_frontend_bwd(const st_frontend_bwd_args* bp, cudaStream_t s) {
 
 // ------------------------------------------------------------------ plain linear layer (vocabulary projection, Models.py:145,151)
 namespace {
+int64_t pad4(int64_t n) { return (n + 3) & ~int64_t(3); }
 struct LinPlan { float *x_r, *w_r; };
 int plan_linear(const st_linear_args& a, LinPlan& p) {
   ST_REQUIRE(a.rows > 0 && a.rows < (1ll << 31) && a.in_dim > 0 && (a.in_dim & 3) == 0 && a.out_dim > 0,
              "st_linear: bad shape (rows=%lld in_dim=%d must be a multiple of 4, out_dim=%d)", (long long)a.rows, a.in_dim, a.out_dim);
   Carver c(a.saved, a.saved_floats);
   p.x_r = a.x_is_tf32 ? const_cast<float*>(a.x) : c.take(a.rows * a.in_dim);
-  p.w_r = c.take(static_cast<int64_t>(a.out_dim) * a.in_dim);
+  p.w_r = c.take(pad4(a.out_dim) * a.in_dim);          // rows up to a multiple of 4 (zero-filled): see st_linear_fwd
   if (!c.ok()) {
     set_error("st_linear: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
     return ST_ERR_WORKSPACE;
   }
   return ST_OK;
 }
-int64_t pad4(int64_t n) { return (n + 3) & ~int64_t(3); }
 }  // namespace
 
 int64_t st_linear_saved_floats(int64_t rows, int in_dim, int out_dim, int x_is_tf32) {
-  return (x_is_tf32 ? 0 : pad64(rows * in_dim)) + pad64(static_cast<int64_t>(out_dim) * in_dim);
+  return (x_is_tf32 ? 0 : pad64(rows * in_dim)) + pad64(pad4(out_dim) * in_dim);
 }
 int64_t st_linear_ws_floats(int64_t rows, int in_dim, int out_dim) { (void)in_dim; return pad64(rows * pad4(out_dim)) + 64; }
 
@@ -702,7 +702,14 @@ int st_linear_fwd(const st_linear_args* ap, cudaStream_t s) {
   ST_TRY(round_tf32_2d(s, a.w, k, p.w_r, k, n, k));
   GemmEpilogue e;
   e.bias = a.b;
-  return gemm_tf32(s, GEMM_NT, p.x_r, k, p.w_r, k, a.y, a.ldy, M, n, k, e);
+  // A width that is not a multiple of 4 (V = 4337) would force the scalar epilogue.  Without a bias the GEMM can run on
+  // the width rounded up instead: the extra weight rows are zeros and land in the padding columns of the row-padded y.
+  int n_eff = n;
+  if (!a.b && pad4(n) != n && a.ldy >= pad4(n)) {
+    n_eff = static_cast<int>(pad4(n));
+    ST_CHECK_CUDA(cudaMemsetAsync(p.w_r + static_cast<int64_t>(n) * k, 0, static_cast<size_t>(n_eff - n) * k * sizeof(float), s));
+  }
+  return gemm_tf32(s, GEMM_NT, p.x_r, k, p.w_r, k, a.y, a.ldy, M, n_eff, k, e);
 }
 
 int st_linear_bwd(const st_linear_bwd_args* bp, cudaStream_t s) {

@@ -74,7 +74,8 @@ enum EpiFlavour : int {
   EPI_RELU_DROP_ROUND = 3,  // C = tf32(dropout(relu(acc + bias)))                  fc1
   EPI_AUX_MASK_ROUND = 4,   // C = tf32(aux > 0 ? acc * aux_scale : 0)              dgrad through relu + dropout
   EPI_ATOMIC = 5,           // C += acc (red.global.add)                            split-K wgrad
-  EPI_GENERIC = 6
+  EPI_GENERIC = 6,
+  EPI_RELU_DROP = 7         // C = dropout(relu(acc + bias)), not rounded               front-end linear (feeds a LayerNorm)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
@@ -110,8 +111,8 @@ __device__ __forceinline__ void prefetch_aux_tile(const GemmParams& p, int m_blk
 template <int BN, int F>
 __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_s, uint32_t tmem_acc, int m_blk, int n_blk,
                                               int quarter, int half, int lane) {
-  constexpr bool RELU = (F == EPI_RELU_DROP_ROUND);
-  constexpr bool DROP = (F == EPI_RELU_DROP_ROUND);
+  constexpr bool RELU = (F == EPI_RELU_DROP_ROUND || F == EPI_RELU_DROP);
+  constexpr bool DROP = (F == EPI_RELU_DROP_ROUND || F == EPI_RELU_DROP);
   constexpr int AUX = (F == EPI_AUX_ADD) ? 1 : (F == EPI_AUX_MASK_ROUND ? 2 : 0);
   constexpr bool ROUND = (F == EPI_ROUND || F == EPI_RELU_DROP_ROUND || F == EPI_AUX_MASK_ROUND);
   constexpr bool ATOMIC = (F == EPI_ATOMIC);
@@ -293,6 +294,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* stg, u
     case EPI_ROUND:           epilogue_fast<BN, EPI_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     case EPI_AUX_ADD:         epilogue_fast<BN, EPI_AUX_ADD>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     case EPI_RELU_DROP_ROUND: epilogue_fast<BN, EPI_RELU_DROP_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
+    case EPI_RELU_DROP: epilogue_fast<BN, EPI_RELU_DROP>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     case EPI_AUX_MASK_ROUND:  epilogue_fast<BN, EPI_AUX_MASK_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     case EPI_ATOMIC:          epilogue_fast<BN, EPI_ATOMIC>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     default:                  epilogue_generic<BN>(p, stg, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
@@ -736,7 +738,7 @@ int pick_flavour(const GemmEpilogue& ep, const float* C, int64_t ldc, int N) {
   if (!vec_ok || get_option("gemm_generic_epilogue")) return EPI_GENERIC;
   const bool drop = ep.drop_thresh != 0;
   if (ep.atomic) return (!ep.bias && !ep.aux_mode && !ep.relu && !drop && !ep.round_tf32) ? EPI_ATOMIC : EPI_GENERIC;
-  if (ep.relu) return (ep.aux_mode == 0 && ep.round_tf32) ? EPI_RELU_DROP_ROUND : EPI_GENERIC;   // thresh 0 keeps everything
+  if (ep.relu) return ep.aux_mode != 0 ? EPI_GENERIC : (ep.round_tf32 ? EPI_RELU_DROP_ROUND : EPI_RELU_DROP);   // thresh 0 keeps everything
   if (drop) return EPI_GENERIC;
   if (ep.aux_mode == 1) return ep.round_tf32 ? EPI_GENERIC : EPI_AUX_ADD;
   if (ep.aux_mode == 2) return ep.round_tf32 ? EPI_AUX_MASK_ROUND : EPI_GENERIC;
