@@ -612,6 +612,236 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
   if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
 }
 
+
+// ================================================================================ dK, dV for ONE query tile (Lq <= 64)
+// Decoder cross-attention (50 target positions against 1000 encoder frames) and decoder self-attention.  With a single
+// query tile the generic kernel above is one short tile per CTA — barrier / TMEM set-up, operand latency and the output
+// write are all exposed (2048 CTAs x ~9 us at B=32, h=8, Lk=1000).  Here a CTA keeps the query-side tiles (Q, dO in both
+// layouts, log-sum-exp, delta, dropout keys) resident and walks over SEVERAL key tiles: K/V tiles double-buffered in shared
+// memory (TMA), S^T / dP^T and the dV / dK accumulators double-buffered in TMEM, so the loads of tile i+1, the MMAs of
+// tile i and the output write of tile i-1 overlap.  Same mathematics and thread mapping as attn_bwd_dkv_pipe.
+template <int DK>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q_k, const __grid_constant__ CUtensorMap tmap_q_mn,
+                   const __grid_constant__ CUtensorMap tmap_do_k, const __grid_constant__ CUtensorMap tmap_do_mn,
+                   const __grid_constant__ CUtensorMap tmap_k_res, const __grid_constant__ CUtensorMap tmap_v_res,
+                   const AttnDev p) {
+  constexpr int BKV = 128;
+  constexpr int G = DK / 32;
+  constexpr int T_BYTES = BT * DK * 4;
+  constexpr int RES_BYTES = BKV * DK * 4;
+  constexpr uint32_t TCOLS = 512;
+  // TMEM: S^T x2 | dP^T x2 | dV x2 | dK x2
+  constexpr uint32_t T_ST = 0, T_DPT = 2 * BT, T_DV = 4 * BT, T_DK = 4 * BT + 2 * DK;
+  static_assert(4 * BT + 4 * DK <= 512, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sBase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sRes = sBase;                                  // [2 buffers][K | V]
+  uint8_t* sQ = sBase + 4 * RES_BYTES;                    // Qk | Qm | dOk | dOm
+  __shared__ uint64_t q_full, res_full[2], res_empty[2], s_full[2], ds_full[2], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_lse[BT];
+  __shared__ __align__(16) float s_delta[BT];
+  __shared__ __align__(16) uint32_t s_rkey[BT];
+  __shared__ int s_extent;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_kt_all = (p.Lk + BKV - 1) / BKV;
+  const int extent = block_key_extent(p, b, &s_extent);
+  // key tiles up to the utterance's last valid key are computed; tiles entirely inside its padding get zeros (below)
+  const int n_kt = (extent > 0 && extent < p.Lk) ? (extent + BKV - 1) / BKV : n_kt_all;
+  const int first = blockIdx.x, step = gridDim.x;
+  const int n_it = first < n_kt ? (n_kt - first + step - 1) / step : 0;   // key tiles of this CTA: first, first + step, ...
+
+  if (tid == 0) {
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], NCOMP);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NCOMP);
+    }
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == W_PROD) {
+    // ===================== producer =====================
+    if (n_it > 0) {
+#pragma unroll
+      for (int e = lane; e < BT; e += 32) {   // per-query statistics of the single query tile
+        const int64_t o = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (e < p.Lq ? e : 0);
+        s_lse[e] = e < p.Lq ? p.lse2[o] : INFINITY;   // +inf => probability 0 for padded query rows
+        s_delta[e] = e < p.Lq ? p.delta[o] : 0.f;
+        s_rkey[e] = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(o)) : 0u;
+      }
+      __syncwarp();
+      if (elect_one()) {
+        tma_prefetch_desc(&tmap_q_k); tma_prefetch_desc(&tmap_k_res); tma_prefetch_desc(&tmap_v_res);
+        mbar_arrive_expect_tx(&q_full, 4 * T_BYTES);   // release: the statistics above become visible with it
+        tma_load_4d(sQ, &tmap_q_k, &q_full, 0, 0, h * G, b);
+        tma_load_4d(sQ + T_BYTES, &tmap_q_mn, &q_full, 0, 0, h * G, b);
+        tma_load_4d(sQ + 2 * T_BYTES, &tmap_do_k, &q_full, 0, 0, h * G, b);
+        tma_load_4d(sQ + 3 * T_BYTES, &tmap_do_mn, &q_full, 0, 0, h * G, b);
+      }
+      __syncwarp();
+      for (int it = 0; it < n_it; ++it) {
+        const int rb = it & 1, kv0 = (first + it * step) * BKV;
+        if (it >= 2) mbar_wait(&res_empty[rb], ((it >> 1) - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&res_full[rb], 2 * RES_BYTES);
+          tma_load_4d(sRes + rb * 2 * RES_BYTES, &tmap_k_res, &res_full[rb], 0, kv0, h * G, b);               // rows >= Lk: zeros
+          tma_load_4d(sRes + rb * 2 * RES_BYTES + RES_BYTES, &tmap_v_res, &res_full[rb], 0, kv0, h * G, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer (converged warp + elect.sync) =====================
+    if (n_it > 0) {
+      const uint32_t sq0 = smem_u32(sQ), sr0 = smem_u32(sRes);
+      auto koff = [](int ks, int rows) { return static_cast<uint64_t>(((ks / 4) * (rows * 128) + (ks % 4) * 32) >> 4); };
+      const uint64_t dqk = umma_desc_kmajor(sq0), dqm = umma_desc_mnmajor(sq0 + T_BYTES, BT * 128);
+      const uint64_t ddok = umma_desc_kmajor(sq0 + 2 * T_BYTES), ddom = umma_desc_mnmajor(sq0 + 3 * T_BYTES, BT * 128);
+      auto issue_a = [&](int it) {   // S^T = K Q^T, dP^T = V dO^T   (A = K / V tile in shared memory, B = Q / dO K-major)
+        const int rb = it & 1;
+        mbar_wait(&res_full[rb], (it >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc_tf32(128, BT, false, false);
+          const uint64_t ak0 = umma_desc_kmajor(sr0 + rb * 2 * RES_BYTES), av0 = umma_desc_kmajor(sr0 + rb * 2 * RES_BYTES + RES_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < DK / 8; ++ks)
+            umma_tf32_ss(tmem + T_ST + rb * BT, ak0 + koff(ks, BKV), dqk + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < DK / 8; ++ks)
+            umma_tf32_ss(tmem + T_DPT + rb * BT, av0 + koff(ks, BKV), ddok + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+          umma_commit(&s_full[rb]);
+          umma_commit(&res_empty[rb]);   // only these two products read the K / V tile: its buffer is free as soon as they retire,
+        }                                // so the producer runs two key tiles ahead and the TMA latency stays hidden
+        __syncwarp();
+      };
+      auto issue_b = [&](int it) {   // dV = P^T dO, dK = dS^T Q   (A in TMEM, B MN-major)
+        const int rb = it & 1;
+        mbar_wait(&ds_full[rb], (it >> 1) & 1);
+        if (it >= 2) mbar_wait(&acc_empty[rb], ((it >> 1) - 1) & 1);   // the epilogue of tile it-2 has drained this accumulator pair
+        tc_fence_after();
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc_tf32(128, DK, false, true);
+#pragma unroll
+          for (int ks = 0; ks < BT / 8; ++ks)
+            umma_tf32_ts(tmem + T_DV + rb * DK, tmem + T_ST + rb * BT + ks * 8, ddom + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+                         ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < BT / 8; ++ks)
+            umma_tf32_ts(tmem + T_DK + rb * DK, tmem + T_DPT + rb * BT + ks * 8, dqm + static_cast<uint64_t>((ks * 1024) >> 4), idesc,
+                         ks > 0 ? 1u : 0u);
+          umma_commit(&acc_full[rb]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(&q_full, 0);
+      tc_fence_after();
+      issue_a(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_a(it + 1);
+        issue_b(it);
+      }
+    }
+  } else {
+    // ===================== compute warps =====================
+    const int quarter = warp & 3, slice = warp >> 2;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int col0 = slice * 16;
+    const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
+    const bool mask_dense = (p.mask != nullptr) && !mask_per_key;
+    const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
+    auto epilogue = [&](int it) {   // dV = dropout-scale * acc, dK = softmax-scale * acc for the key tile of iteration `it`
+      const int rb = it & 1;
+      const int key = (first + it * step) * BKV + quarter * 32 + lane;
+      const bool key_ok = key < p.Lk;
+      mbar_wait(&acc_full[rb], (it >> 1) & 1);
+      tc_fence_after();
+      if (col0 < DK) {
+        uint32_t rv[16], rk[16];
+        tmem_ld16(t_lane + T_DV + rb * DK + col0, rv);
+        tmem_ld16(t_lane + T_DK + rb * DK + col0, rk);
+        tmem_ld_wait();
+        if (key_ok) {
+          float* dvp = p.dv + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + col0;
+          float* dkp = p.dk + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + col0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            *reinterpret_cast<float4*>(dvp + i) =
+                make_float4(tf32_rna(__uint_as_float(rv[i]) * dscale), tf32_rna(__uint_as_float(rv[i + 1]) * dscale),
+                            tf32_rna(__uint_as_float(rv[i + 2]) * dscale), tf32_rna(__uint_as_float(rv[i + 3]) * dscale));
+            *reinterpret_cast<float4*>(dkp + i) =
+                make_float4(tf32_rna(__uint_as_float(rk[i]) * p.scale), tf32_rna(__uint_as_float(rk[i + 1]) * p.scale),
+                            tf32_rna(__uint_as_float(rk[i + 2]) * p.scale), tf32_rna(__uint_as_float(rk[i + 3]) * p.scale));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[rb]);
+    };
+    if (n_it > 0) mbar_wait(&q_full, 0);   // the statistics in shared memory are valid from here on
+    for (int it = 0; it < n_it; ++it) {
+      const int rb = it & 1;
+      const int key = (first + it * step) * BKV + quarter * 32 + lane;
+      const bool key_ok = key < p.Lk;
+      bool key_masked = !key_ok;
+      if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
+      const uint8_t* mrow = mask_dense ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
+      const uint32_t my_ckey = p.drop_thresh ? dropout_col_key(p.drop_seed, static_cast<uint32_t>(key_ok ? key : 0)) : 0u;
+      mbar_wait(&s_full[rb], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t rs[16], rd[16];
+      tmem_ld16(t_lane + T_ST + rb * BT + col0, rs);
+      tmem_ld16(t_lane + T_DPT + rb * BT + col0, rd);
+      tmem_ld_wait();
+      if (!mask_dense && key_masked) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { rs[i] = 0u; rd[i] = 0u; }
+      } else {
+        const float* ls = s_lse + col0;
+        const float* de = s_delta + col0;
+        const uint32_t* rk = s_rkey + col0;
+        if (mask_dense) {
+          if (p.drop_thresh) dkv16_t<true, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, key_ok);
+          else dkv16_t<true, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, key_ok);
+        } else {
+          if (p.drop_thresh) dkv16_t<false, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, key_ok);
+          else dkv16_t<false, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, key_ok);
+        }
+      }
+      tmem_st16(t_lane + T_ST + rb * BT + col0, rs);
+      tmem_st16(t_lane + T_DPT + rb * BT + col0, rd);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&ds_full[rb]);
+      if (it > 0) epilogue(it - 1);       // overlaps the gradient MMAs of this tile
+    }
+    if (n_it > 0) epilogue(n_it - 1);
+    // key tiles entirely inside the utterance's padding: zero gradients
+    for (int kt = n_kt + first; kt < n_kt_all; kt += step) {
+      const int rows = min(BKV, p.Lk - kt * BKV);
+      for (int i = tid; i < rows * (DK / 4); i += NCOMP) {
+        const int r = i / (DK / 4), c = (i - r * (DK / 4)) * 4;
+        const int64_t grow = static_cast<int64_t>(b) * p.Lk + kt * BKV + r;
+        *reinterpret_cast<float4*>(p.dk + grow * p.lddk + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(p.dv + grow * p.lddv + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
+}
+
 template <int DK>
 int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
   const AttnArgs& f = a.f;
@@ -630,6 +860,19 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     // query tiles the third ring stage matters more.  Option: 0 = this heuristic, 1 = always shared memory, 2 = always TMEM.
     const int rs_opt = get_option("attn_dkv_res_smem");
     const bool rs = rs_opt == 1 || (rs_opt == 0 && f.Lq <= 2 * BT);
+    if (f.Lq <= BT && !get_option("attn_dkv_no_small")) {   // single query tile: the persistent multi-key-tile kernel
+      constexpr int SMEM_SMALL = 4 * 128 * DK * 4 + 4 * BT * DK * 4 + 1024;
+      auto ks = attn_bwd_dkv_small<DK>;
+      static bool attr_small = false;
+      if (!attr_small) { ST_CHECK_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL)); attr_small = true; }
+      const int n_kt = (f.Lk + 127) / 128;
+      int split = get_option("attn_dkv_small_split");
+      if (split <= 0) split = 1;
+      dim3 grid(n_kt < split ? n_kt : split, f.H, f.B);
+      ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
+      ks<<<grid, NTHREADS, SMEM_SMALL, s>>>(tqk, tqm, tdk, tdm, tkr, tvr, p);
+      ST_CHECK_LAUNCH();
+    } else {
     constexpr int SMEM_TS = 3 * 4 * BT * DK * 4 + 1024;
     constexpr int SMEM_RS = (DK == 64 ? 2 : 3) * 4 * BT * DK * 4 + 2 * 128 * DK * 4 + 1024;
     const int SMEM = rs ? SMEM_RS : SMEM_TS;
@@ -641,6 +884,7 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
     kern<<<grid, NTHREADS, SMEM, s>>>(f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, tkr, tvr, p);
     ST_CHECK_LAUNCH();
+    }
   }
   {
     CUtensorMap tkk, tkm, tvk;

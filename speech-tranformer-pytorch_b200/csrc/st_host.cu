@@ -40,6 +40,8 @@ Option g_options[] = {
     {"gemm_generic_epilogue", 0},   // 1 = force the generic (runtime-flag) GEMM epilogue (tests)
     {"gemm_bn", 0},       // 0 = heuristic; 64/128/256 forces the GEMM tile width (tuning / tests)
     {"attn_trace", 0},         // 1 = dK/dV kernel CTA (0,0,0) records its pipeline timeline (st_debug_read_trace)
+    {"attn_dkv_small_split", 0},   // CTAs per (batch, head) of the single-query-tile dK/dV kernel (0 = default 1)
+    {"attn_dkv_no_small", 0},  // 1 = never use the single-query-tile dK/dV kernel (A/B testing)
     {"attn_fuse_bias", 0},     // 1 = dq/dk/dv bias column sums from the attention-backward epilogues (measured slower)
     {"attn_dq_res_smem", 0},   // 1 = dQ kernel keeps its resident Q/dO tiles in shared memory (.ss MMAs) instead of TMEM
     {"attn_dkv_res_smem", 0},  // resident K/V tiles of the dK/dV kernel: 0 = heuristic (smem when Lq <= 128), 1 = smem, 2 = TMEM

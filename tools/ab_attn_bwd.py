@@ -46,7 +46,8 @@ for name, shape in (("enc self 32x8x1000x1000", (32, 8, 1000, 1000, 64)), ("dec 
                     ("dec self 32x8x50x50", (32, 8, 50, 50, 64)), ("dk32 8x2x300x300", (8, 2, 300, 300, 32))):
     base, gb = run(*shape, {})
     print(f"{name}: base {({k: round(v, 1) for k, v in base.items() if k.startswith('attn')})} us")
-    for opts in ({"attn_dq_res_smem": 1}, {"attn_dkv_res_smem": 1}, {"attn_dkv_res_smem": 2}):
+    for opts in ({"attn_dq_res_smem": 1}, {"attn_dkv_res_smem": 1}, {"attn_dkv_res_smem": 2}, {"attn_dkv_no_small": 1},
+                 {"attn_dkv_small_split": 1}, {"attn_dkv_small_split": 2}, {"attn_dkv_small_split": 8}):
         r, g = run(*shape, opts)
         diff = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(g, gb))
         print(f"   {opts}: {({k: round(v, 1) for k, v in r.items() if k.startswith('attn')})} us  max rel diff vs base {diff:.2e}")
