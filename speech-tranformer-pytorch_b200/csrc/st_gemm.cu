@@ -725,7 +725,9 @@ int pick_bn(int M, int N, int k_splits) {
   const int sms = num_sms();
   const int forced = get_option("gemm_bn");
   if (forced == 64 || forced == 128 || forced == 256) return (forced > 64 && N <= 64) ? 64 : forced;
-  if (N > 128 && m_tiles * ((N + 255) / 256) * k_splits >= sms) return 256;
+  // measured (tools/gemm_small_sweep.py): the wide tile wins as soon as it gives half the SMs a tile — its MMAs amortise the
+  // fixed per-instruction cost over 4x the columns (M = 1600, N = 1536 / 2048: 14.7 us against 16.8 us with 128-wide tiles)
+  if (N > 128 && 2 * m_tiles * ((N + 255) / 256) * k_splits >= sms) return 256;
   if (N > 64 && m_tiles * ((N + 127) / 128) * k_splits >= sms) return 128;
   return 64;
 }
