@@ -175,6 +175,8 @@ typedef struct {
                            that tensor is the residual (then the sum is formed) */
   float* dwq; float* dbq; float* dwk; float* dbk; float* dwv; float* dbv; float* dwo; float* dbo;
   float* dln_g; float* dln_b;                 /* all parameter gradients are OVERWRITTEN */
+  int grads_zeroed;     /* the parameter-gradient buffers already hold zeros (slices of a gradient buffer the caller cleared in
+                           one pass, parallel.FlatParams.zero_grad): skip the per-tensor clears (~200 memsets per step) */
 } st_mha_bwd_args;
 int st_mha_bwd(const st_mha_bwd_args* a /* host */, cudaStream_t stream);
 
@@ -204,6 +206,7 @@ typedef struct {
   const float* dout;
   float* dx;
   float* dw1; float* db1; float* dw2; float* db2; float* dln_g; float* dln_b;   /* OVERWRITTEN */
+  int grads_zeroed;     /* see st_mha_bwd_args */
 } st_ffn_bwd_args;
 int st_ffn_bwd(const st_ffn_bwd_args* a /* host */, cudaStream_t stream);
 
@@ -250,6 +253,7 @@ typedef struct {
   const float* dout;
   float* dx;                       /* may be NULL: acoustic features need no gradient */
   float* dw; float* db; float* dln_g; float* dln_b;   /* OVERWRITTEN */
+  int grads_zeroed;                /* see st_mha_bwd_args */
 } st_frontend_bwd_args;
 int st_frontend_bwd(const st_frontend_bwd_args* a /* host */, cudaStream_t stream);
 
@@ -271,6 +275,7 @@ typedef struct {
   st_linear_args f;
   const float* dy; int64_t lddy;
   float* dx; float* dw; float* db;                    /* OVERWRITTEN */
+  int grads_zeroed;                                   /* see st_mha_bwd_args */
 } st_linear_bwd_args;
 int st_linear_bwd(const st_linear_bwd_args* a /* host */, cudaStream_t stream);
 

@@ -54,7 +54,7 @@ class MhaBwdArgs(C.Structure):
                 ("dq_in", C.c_void_p), ("dk_in", C.c_void_p), ("dv_in", C.c_void_p), ("dresidual", C.c_void_p),
                 ("dwq", C.c_void_p), ("dbq", C.c_void_p), ("dwk", C.c_void_p), ("dbk", C.c_void_p),
                 ("dwv", C.c_void_p), ("dbv", C.c_void_p), ("dwo", C.c_void_p), ("dbo", C.c_void_p),
-                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p)]
+                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p), ("grads_zeroed", C.c_int)]
 
 
 class FfnArgs(C.Structure):
@@ -70,7 +70,7 @@ class FfnArgs(C.Structure):
 class FfnBwdArgs(C.Structure):
     _fields_ = [("f", FfnArgs), ("dout", C.c_void_p), ("dx", C.c_void_p),
                 ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
-                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p)]
+                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p), ("grads_zeroed", C.c_int)]
 
 
 class FrontendArgs(C.Structure):
@@ -82,7 +82,7 @@ class FrontendArgs(C.Structure):
 
 class FrontendBwdArgs(C.Structure):
     _fields_ = [("f", FrontendArgs), ("dout", C.c_void_p), ("dx", C.c_void_p), ("dw", C.c_void_p), ("db", C.c_void_p),
-                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p)]
+                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p), ("grads_zeroed", C.c_int)]
 
 
 class LinearArgs(C.Structure):
@@ -93,7 +93,7 @@ class LinearArgs(C.Structure):
 
 class LinearBwdArgs(C.Structure):
     _fields_ = [("f", LinearArgs), ("dy", C.c_void_p), ("lddy", i64), ("dx", C.c_void_p), ("dw", C.c_void_p),
-                ("db", C.c_void_p)]
+                ("db", C.c_void_p), ("grads_zeroed", C.c_int)]
 
 
 class AdamArgs(C.Structure):

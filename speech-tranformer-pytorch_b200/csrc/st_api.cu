@@ -52,13 +52,20 @@ int wgrad_splits(int m_out, int n_out, int64_t k_len) {
 }
 
 // dW[out,in] = dY[rows,out]^T * X[rows,in]   (overwrites dW)
+// zeroed: dW already holds zeros (st_*_bwd_args.grads_zeroed) — no clear needed before the split-K reductions
 int wgrad(cudaStream_t s, const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, int rows, int n_out,
-          int n_in) {
-  ST_CHECK_CUDA(cudaMemsetAsync(dw, 0, static_cast<size_t>(n_out) * n_in * sizeof(float), s));
+          int n_in, bool zeroed = false) {
+  if (!zeroed) ST_CHECK_CUDA(cudaMemsetAsync(dw, 0, static_cast<size_t>(n_out) * n_in * sizeof(float), s));
   GemmEpilogue ep;
   ep.atomic = 1;
   return gemm_tf32(s, GEMM_TN, dy, lddy, x, ldx, dw, n_in, n_out, n_in, rows, ep, wgrad_splits(n_out, n_in, rows));
 }
+
+// clear a gradient vector unless the caller says it is already zero
+#define ST_CLEAR(ptr, n)                                                                  \
+  do {                                                                                    \
+    if (!zeroed) ST_CHECK_CUDA(cudaMemsetAsync((ptr), 0, (n) * sizeof(float), s));        \
+  } while (0)
 
 struct Carver {
   float* base;
@@ -384,6 +391,7 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
 int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   ST_REQUIRE(bp != nullptr, "st_mha_bwd: null args");
   const st_mha_bwd_args& b = *bp;
+  const bool zeroed = b.grads_zeroed != 0;
   const st_mha_args& a = b.f;
   ST_TRY(check_mha(a));
   MhaPlan p;
@@ -405,15 +413,15 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   const bool fused_bias = attn_bwd_fuses_bias(a.dk);
 
   // LayerNorm backward; dbo = column sums of dz
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_g, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_b, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dbo, 0, d * sizeof(float), s));
+  ST_CLEAR(b.dln_g, d);
+  ST_CLEAR(b.dln_b, d);
+  ST_CLEAR(b.dbo, d);
   ST_TRY(add_ln_bwd(s, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d, 1, DropoutCfg{}));
   // output projection backward
   {
     GemmEpilogue e; e.round_tf32 = 1;
     ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.wo_r, d, dctx, d, M, d, d, e));
-    ST_TRY(wgrad(s, dz, d, p.ctx, d, b.dwo, M, d, d));
+    ST_TRY(wgrad(s, dz, d, p.ctx, d, b.dwo, M, d, d, zeroed));
   }
   // attention core backward
   {
@@ -428,9 +436,9 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
     ab.dctx = dctx; ab.lddctx = d; ab.delta = delta;
     ab.dq = dpq; ab.lddq = p.ldpq; ab.dk_ = dpk; ab.lddk = p.ldpk; ab.dv = dpv; ab.lddv = p.ldpv;
     if (fused_bias) {   // dbq / dbk / dbv = column sums of dq / dk / dv, accumulated by the kernels' epilogues
-      ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, d * sizeof(float), s));
-      ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, d * sizeof(float), s));
-      ST_CHECK_CUDA(cudaMemsetAsync(b.dbv, 0, d * sizeof(float), s));
+      ST_CLEAR(b.dbq, d);
+      ST_CLEAR(b.dbk, d);
+      ST_CLEAR(b.dbv, d);
       ab.dbq = b.dbq; ab.dbk = b.dbk; ab.dbv = b.dbv;
     }
     ST_TRY(attn_bwd(s, ab));
@@ -442,31 +450,31 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   const bool pack_qkv = p.same_qkv && pack_kv && b.dwk == b.dwq + dd && b.dbk == b.dbq + d;
   if (pack_qkv) {
     if (!fused_bias) {
-      ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, 3 * d * sizeof(float), s));
+      ST_CLEAR(b.dbq, 3 * d);
       ST_TRY(colsum_add(s, dpq, p.ldpq, M, 3 * d, b.dbq));
     }
-    ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d));
+    ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d, zeroed));
   } else {
     if (!fused_bias) {
-      ST_CHECK_CUDA(cudaMemsetAsync(b.dbq, 0, d * sizeof(float), s));
+      ST_CLEAR(b.dbq, d);
       ST_TRY(colsum_add(s, dpq, p.ldpq, M, d, b.dbq));
     }
-    ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d));
+    ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d, zeroed));
     if (pack_kv) {
       if (!fused_bias) {
-        ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, 2 * d * sizeof(float), s));
+        ST_CLEAR(b.dbk, 2 * d);
         ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, 2 * d, b.dbk));
       }
-      ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d));
+      ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d, zeroed));
     } else {
       if (!fused_bias) {
-        ST_CHECK_CUDA(cudaMemsetAsync(b.dbk, 0, d * sizeof(float), s));
-        ST_CHECK_CUDA(cudaMemsetAsync(b.dbv, 0, d * sizeof(float), s));
+        ST_CLEAR(b.dbk, d);
+        ST_CLEAR(b.dbv, d);
         ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, d, b.dbk));
         ST_TRY(colsum_add(s, dpv, p.ldpv, Mk, d, b.dbv));
       }
-      ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d));
-      ST_TRY(wgrad(s, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d));
+      ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d, zeroed));
+      ST_TRY(wgrad(s, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d, zeroed));
     }
   }
   // input gradients; the residual branch contributes dz to whichever input it aliased
@@ -552,6 +560,7 @@ int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
 int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   ST_REQUIRE(bp != nullptr, "st_ffn_bwd: null args");
   const st_ffn_bwd_args& b = *bp;
+  const bool zeroed = b.grads_zeroed != 0;
   const st_ffn_args& a = b.f;
   FfnPlan p;
   ST_TRY(plan_ffn(a, p));
@@ -560,10 +569,10 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   Carver w(a.ws, a.ws_floats);
   float* dz = w.take(a.rows * d);
   float* dh = w.take(a.rows * f);
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_g, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_b, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.db2, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.db1, 0, f * sizeof(float), s));
+  ST_CLEAR(b.dln_g, d);
+  ST_CLEAR(b.dln_b, d);
+  ST_CLEAR(b.db2, d);
+  ST_CLEAR(b.db1, f);
   ST_TRY(add_ln_bwd(s, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d, 1,
                     make_dropout(a.dropout_p, a.seed ^ kSeedMix2)));
   // dh = (dz W2) * [h > 0] * dropout1 scale
@@ -572,8 +581,8 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   e.aux_scale = make_dropout(a.dropout_p, 0).scale;
   e.colsum = b.db1;   // db1 = column sums of dh, accumulated by the epilogue that produces dh
   ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.w2_r, f, dh, f, M, f, d, e));
-  ST_TRY(wgrad(s, dz, d, p.h, f, b.dw2, M, d, f));
-  ST_TRY(wgrad(s, dh, f, p.x_r, d, b.dw1, M, f, d));
+  ST_TRY(wgrad(s, dz, d, p.h, f, b.dw2, M, d, f, zeroed));
+  ST_TRY(wgrad(s, dh, f, p.x_r, d, b.dw1, M, f, d, zeroed));
   GemmEpilogue ex;
   ex.aux = dz; ex.ldaux = d; ex.aux_mode = 1;
   return gemm_tf32(s, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, M, d, f, ex);
@@ -647,6 +656,7 @@ int st_frontend_fwd(const st_frontend_args* ap, cudaStream_t s) {
 int st_frontend_bwd(const st_frontend_bwd_args* bp, cudaStream_t s) {
   ST_REQUIRE(bp != nullptr, "st_frontend_bwd: null args");
   const st_frontend_bwd_args& b = *bp;
+  const bool zeroed = b.grads_zeroed != 0;
   const st_frontend_args& a = b.f;
   FrontPlan p;
   ST_TRY(plan_front(a, p));
@@ -654,13 +664,13 @@ int st_frontend_bwd(const st_frontend_bwd_args* bp, cudaStream_t s) {
   ST_REQUIRE(a.ws != nullptr && a.ws_floats >= st_frontend_ws_floats(a.rows, k, d), "st_frontend_bwd: workspace too small");
   Carver w(a.ws, a.ws_floats);
   float* dz = w.take(a.rows * d);
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_g, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.dln_b, 0, d * sizeof(float), s));
-  ST_CHECK_CUDA(cudaMemsetAsync(b.db, 0, d * sizeof(float), s));
+  ST_CLEAR(b.dln_g, d);
+  ST_CLEAR(b.dln_b, d);
+  ST_CLEAR(b.db, d);
   // LayerNorm backward, then the gate of dropout(relu(.)) (h > 0 <=> kept and positive); db = column sums of the result
   ST_TRY(add_ln_bwd(s, b.dout, p.h, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db, M, d, 1, DropoutCfg{}, p.h,
                     make_dropout(a.dropout_p, 0).scale));
-  ST_TRY(wgrad(s, dz, d, p.x_r, k, b.dw, M, d, k));
+  ST_TRY(wgrad(s, dz, d, p.x_r, k, b.dw, M, d, k, zeroed));
   if (b.dx) {
     GemmEpilogue e;
     ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.w_r, k, b.dx, k, M, k, d, e));
@@ -715,6 +725,7 @@ int st_linear_fwd(const st_linear_args* ap, cudaStream_t s) {
 int st_linear_bwd(const st_linear_bwd_args* bp, cudaStream_t s) {
   ST_REQUIRE(bp != nullptr, "st_linear_bwd: null args");
   const st_linear_bwd_args& b = *bp;
+  const bool zeroed = b.grads_zeroed != 0;
   const st_linear_args& a = b.f;
   LinPlan p;
   ST_TRY(plan_linear(a, p));
@@ -731,9 +742,9 @@ int st_linear_bwd(const st_linear_bwd_args* bp, cudaStream_t s) {
     GemmEpilogue e;
     ST_TRY(gemm_tf32(s, GEMM_NN, dy_r, ldr, p.w_r, k, b.dx, k, M, k, n, e));
   }
-  if (b.dw) ST_TRY(wgrad(s, dy_r, ldr, p.x_r, k, b.dw, M, n, k));
+  if (b.dw) ST_TRY(wgrad(s, dy_r, ldr, p.x_r, k, b.dw, M, n, k, zeroed));
   if (b.db && a.b) {
-    ST_CHECK_CUDA(cudaMemsetAsync(b.db, 0, n * sizeof(float), s));
+    ST_CLEAR(b.db, n);
     ST_TRY(colsum_add(s, dy_r, ldr, M, n, b.db));
   }
   return ST_OK;

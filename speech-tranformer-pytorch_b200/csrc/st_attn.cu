@@ -186,6 +186,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const bool row_ok = row < p.Lq;
   const int n_kv_all = (p.Lk + BKV - 1) / BKV;
   __shared__ int s_extent;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+    mbar_init(&bar_q, 1); mbar_init(&bar_k, 1); mbar_init(&bar_v, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  pdl_wait();      // nothing above reads or writes global memory (programmatic dependent launch, st_host.h)
+  pdl_trigger();
+
   const int extent = block_key_extent(p, b, &s_extent);
   // key tiles that lie entirely in the padding of this utterance contribute exactly nothing: skip them (at least one
   // tile is always processed so that a fully masked row still produces the reference's NaN)
@@ -194,13 +204,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // bits: compute them once per tile (one thread per 32-key chunk), one tile ahead
   const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
   if (shared_mask && tid < BKV / 32) s_mb[0][tid] = mask_bits_row(p, b, 0, true, tid * 32);
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
-    mbar_init(&bar_q, 1); mbar_init(&bar_k, 1); mbar_init(&bar_v, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -450,6 +453,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const float* __restrict__ dctx, int64_t lddctx, const float* __restrict__ ctx, int64_t ldctx,
                   float* __restrict__ delta, int B, int H, int Lq, int dk) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t rows = static_cast<int64_t>(B) * Lq;
   const int d = H * dk;
@@ -847,7 +852,7 @@ int launch_fwd(cudaStream_t s, const AttnArgs& a) {
   ProfScope prof(s, PROF_ATTN_FWD, 4.0 * a.B * a.H * static_cast<double>(a.Lq) * a.Lk * DK);
   AttnDev dev = attn_to_dev(a);
   dev.trace = get_option("attn_trace");
-  kern<<<grid, 256, SMEM, s>>>(tq, tk, tv, dev);
+  ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(256), SMEM, s, tq, tk, tv, dev));
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -865,8 +870,8 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
     const int64_t blocks = (rows + 7) / 8;
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
     ProfScope prof(s, PROF_ATTN_DELTA, 2.0 * rows * cols * 4);
-    attn_delta_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(a.dctx, a.lddctx, f.ctx, f.ldctx,
-                                                                                    a.delta, f.B, f.H, f.Lq, DK);
+    ST_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(blocks < cap ? blocks : cap)), dim3(256), 0, s,
+                             a.dctx, a.lddctx, f.ctx, f.ldctx, a.delta, f.B, f.H, f.Lq, DK));
     ST_CHECK_LAUNCH();
   }
   if (DK <= 64 && !get_option("attn_bwd_simple")) return attn_bwd_pipelined(s, a, p);  // st_attn_bwd.cu

@@ -181,10 +181,6 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   __shared__ int s_extent;
-  const int extent = block_key_extent(p, b, &s_extent);
-  // key tiles entirely inside this utterance's padding have dS == 0: skipped (see block_key_extent)
-  const int n_kv = extent >= p.Lk ? (p.Lk + BT - 1) / BT : max(1, (extent + BT - 1) / BT);
-  const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
 
   if (tid == 0) {
     mbar_init(&res_ready, RS ? 1 : NCOMP); mbar_init(&acc_full, 1);
@@ -193,6 +189,13 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
     fence_mbar_init();
   }
   if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  pdl_wait();      // nothing above reads or writes global memory (programmatic dependent launch, st_host.h)
+  pdl_trigger();
+
+  const int extent = block_key_extent(p, b, &s_extent);
+  // key tiles entirely inside this utterance's padding have dS == 0: skipped (see block_key_extent)
+  const int n_kv = extent >= p.Lk ? (p.Lk + BT - 1) / BT : max(1, (extent + BT - 1) / BT);
+  const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -386,6 +389,8 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
   const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
   const int n_q = (p.Lq + BT - 1) / BT;
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  pdl_wait();      // before the first global access and before the early exit below (programmatic dependent launch)
+  pdl_trigger();
   if (p.trace && tid == 0 && cta_lin < TRACE_CTAS) { g_cta_trace[cta_lin * 4] = global_ns(); g_cta_trace[cta_lin * 4 + 2] = sm_id(); }
   {
     // a key tile entirely inside this utterance's padding: dK = dV = 0 for its rows, nothing to compute
@@ -649,11 +654,6 @@ attn_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q_k, const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_kt_all = (p.Lk + BKV - 1) / BKV;
-  const int extent = block_key_extent(p, b, &s_extent);
-  // key tiles up to the utterance's last valid key are computed; tiles entirely inside its padding get zeros (below)
-  const int n_kt = (extent > 0 && extent < p.Lk) ? (extent + BKV - 1) / BKV : n_kt_all;
-  const int first = blockIdx.x, step = gridDim.x;
-  const int n_it = first < n_kt ? (n_kt - first + step - 1) / step : 0;   // key tiles of this CTA: first, first + step, ...
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
@@ -664,6 +664,14 @@ attn_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q_k, const __grid_co
     fence_mbar_init();
   }
   if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  pdl_wait();      // nothing above reads or writes global memory (programmatic dependent launch, st_host.h)
+  pdl_trigger();
+
+  const int extent = block_key_extent(p, b, &s_extent);
+  // key tiles up to the utterance's last valid key are computed; tiles entirely inside its padding get zeros (below)
+  const int n_kt = (extent > 0 && extent < p.Lk) ? (extent + BKV - 1) / BKV : n_kt_all;
+  const int first = blockIdx.x, step = gridDim.x;
+  const int n_it = first < n_kt ? (n_kt - first + step - 1) / step : 0;   // key tiles of this CTA: first, first + step, ...
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -870,7 +878,7 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
       if (split <= 0) split = 1;
       dim3 grid(n_kt < split ? n_kt : split, f.H, f.B);
       ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-      ks<<<grid, NTHREADS, SMEM_SMALL, s>>>(tqk, tqm, tdk, tdm, tkr, tvr, p);
+      ST_CHECK_CUDA(launch_pdl(ks, grid, dim3(NTHREADS), SMEM_SMALL, s, tqk, tqm, tdk, tdm, tkr, tvr, p));
       ST_CHECK_LAUNCH();
     } else {
     constexpr int SMEM_TS = 3 * 4 * BT * DK * 4 + 1024;
@@ -882,7 +890,7 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     dim3 grid((f.Lk + 127) / 128, f.H, f.B);
     // algorithmic share of the attention backward carried by this kernel: dV and dK (S, dP recompute not counted)
     ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    kern<<<grid, NTHREADS, SMEM, s>>>(f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, tkr, tvr, p);
+    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, tkr, tvr, p));
     ST_CHECK_LAUNCH();
     }
   }
@@ -904,7 +912,7 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     dim3 grid((f.Lq + 127) / 128, f.H, f.B);
     // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
     ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    kern<<<grid, NTHREADS, SMEM, s>>>(f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, tqr, tdr, p);
+    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, tqr, tdr, p));
     ST_CHECK_LAUNCH();
   }
   return ST_OK;

@@ -22,6 +22,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// programmatic dependent launch (see launch_pdl in st_host.h): block until the preceding kernel of the stream has completed
+// and its memory operations are visible; a no-op for an ordinary launch.  pdl_trigger lets the NEXT kernel's CTAs be
+// scheduled (they then sit in their own pdl_wait) as soon as every CTA of this grid has issued it or exited.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -346,6 +346,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the prologue above touched only shared memory, TMEM and kernel parameters
+  pdl_trigger();
 
   // work units: CL vertically adjacent tiles; CTA `crank` of the cluster takes tile m = unit_m * CL + crank
   const int crank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
@@ -528,6 +530,8 @@ gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the prologue above touched only shared memory, TMEM and kernel parameters
+  pdl_trigger();
 
   const int m_units = (p.m_tiles + 1) / 2;
   const int tiles_mn = m_units * p.n_tiles;
@@ -653,11 +657,13 @@ int launch_clustered(Kern kern, int grid, int smem, int cluster, cudaStream_t st
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_allowed(stream);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return ST_OK;
 }
@@ -678,7 +684,7 @@ int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& t
   const int grid = (units < cap ? units : cap) * CL;
   ProfScope prof(stream, PROF_GEMM, 2.0 * p.M * static_cast<double>(p.N) * p.K, gemm_tag(p, A_MN, B_MN, BN, CL));
   if (CL == 1) {
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    ST_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, p));
   } else {
     ST_TRY(launch_clustered(kern, grid, Cfg::SMEM_BYTES, CL, stream, ta, tb, p));
   }

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -44,6 +45,7 @@ Option g_options[] = {
     {"attn_dkv_no_small", 0},  // 1 = never use the single-query-tile dK/dV kernel (A/B testing)
     {"attn_fuse_bias", 0},     // 1 = dq/dk/dv bias column sums from the attention-backward epilogues (measured slower)
     {"attn_dq_res_smem", 0},   // 1 = dQ kernel keeps its resident Q/dO tiles in shared memory (.ss MMAs) instead of TMEM
+    {"pdl", -1},               // programmatic dependent launch: 1 = on, 0 = off, -1 = unset (on unless ST_PDL=0 in the environment)
     {"attn_dkv_res_smem", 0},  // resident K/V tiles of the dK/dV kernel: 0 = heuristic (smem when Lq <= 128), 1 = smem, 2 = TMEM
 };
 }  // namespace
@@ -58,6 +60,23 @@ int get_option(const char* name) {
   for (auto& o : g_options)
     if (strcmp(o.name, name) == 0) return o.value;
   return 0;
+}
+
+int pdl_allowed(cudaStream_t s) {
+  static Option* opt = [] {
+    Option* o = nullptr;
+    for (auto& x : g_options)
+      if (strcmp(x.name, "pdl") == 0) o = &x;
+    if (o->value < 0) {
+      const char* e = getenv("ST_PDL");
+      o->value = (e && e[0] == '0') ? 0 : 1;
+    }
+    return o;
+  }();
+  if (opt->value <= 0) return 0;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return st == cudaStreamCaptureStatusNone ? 1 : 0;
 }
 
 // ---- per-kernel-class event timing

@@ -57,6 +57,28 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 int num_sms();
 
+// ---- programmatic dependent launch (PDL).  A kernel launched through launch_pdl may start while its predecessor in
+// the stream is still draining: its CTAs run their prologue (mbarrier init, TMEM allocation, descriptor prefetch) and
+// then block in pdl_wait() (griddepcontrol.wait, st_common.cuh) until the predecessor has completed and its writes are
+// visible.  EVERY thread of such a kernel must execute pdl_wait() before its first global-memory access and before any
+// early exit (a kernel that finished without waiting would let its successor overtake the predecessor's writes).
+// pdl_allowed: option "pdl" (default 1, environment ST_PDL=0 disables) and the stream is not being captured.
+int pdl_allowed(cudaStream_t s);
+template <typename... P, typename... A>
+cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_allowed(s);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
 // ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py for the
 // roofline numbers.  Disabled by default; when disabled a ProfScope costs one relaxed atomic load.
 enum ProfClass : int {

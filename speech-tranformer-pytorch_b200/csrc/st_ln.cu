@@ -28,6 +28,8 @@ add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int d, float eps,
                   int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
                   const float* __restrict__ post, int64_t post_rows) {
+  pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const float inv_d = 1.f / static_cast<float>(d);
@@ -130,6 +132,8 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dzsum, int64_t rows,
                   int d, int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
                   const float* __restrict__ gate, float gate_scale) {
+  pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
+  pdl_trigger();
   __shared__ float red[LN_WARPS][32 * 4 + 4];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -247,6 +251,8 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
 __global__ void __launch_bounds__(256)
 round_tf32_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
                   int cols4) {
+  pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
+  pdl_trigger();
   const int64_t total = rows * cols4;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -262,6 +268,8 @@ round_tf32_kernel(const float* __restrict__ src, int64_t lds, float* __restrict_
 __global__ void __launch_bounds__(256)
 round_tf32_scalar_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
                          int cols) {
+  pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
+  pdl_trigger();
   const int64_t total = rows * cols;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -274,6 +282,8 @@ round_tf32_scalar_kernel(const float* __restrict__ src, int64_t lds, float* __re
 // ---------------------------------------------------------------- column sums: out[c] += sum_r X[r,c]
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
+  pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
+  pdl_trigger();
   __shared__ float red[8][132];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + lane * 4;
@@ -317,9 +327,8 @@ int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float*
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 8);
   ProfScope prof(stream, PROF_LN_FWD, (b ? 3.0 : 2.0) * rows * d * 4 + (z_out ? 1.0 * rows * d * 4 : 0.0));
 #define ST_LAUNCH(VPL)                                                                                            \
-  add_ln_fwd_kernel<VPL><<<grid, LN_THREADS, 0, stream>>>(a, b, gamma, beta, out, z_out, mean_out, rstd_out, rows, \
-                                                          d, eps, round_out, drop.thresh, drop.scale, drop.seed, post, \
-                                                          post_rows)
+  ST_CHECK_CUDA(launch_pdl(add_ln_fwd_kernel<VPL>, dim3(grid), dim3(LN_THREADS), 0, stream, a, b, gamma, beta, out, z_out, \
+                           mean_out, rstd_out, rows, d, eps, round_out, drop.thresh, drop.scale, drop.seed, post, post_rows))
   if (d <= 128) ST_LAUNCH(1);
   else if (d <= 256) ST_LAUNCH(2);
   else if (d <= 512) ST_LAUNCH(4);
@@ -339,9 +348,8 @@ int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 4);
   ProfScope prof(stream, PROF_LN_BWD, 3.0 * rows * d * 4);
 #define ST_LAUNCH(VPL)                                                                                         \
-  add_ln_bwd_kernel<VPL><<<grid, LN_THREADS, 0, stream>>>(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum,  \
-                                                          rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, \
-                                                          gate_scale)
+  ST_CHECK_CUDA(launch_pdl(add_ln_bwd_kernel<VPL>, dim3(grid), dim3(LN_THREADS), 0, stream, dy, z, mean, rstd, gamma, dz, \
+                           dgamma, dbeta, dzsum, rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, gate_scale))
   if (d <= 128) ST_LAUNCH(1);
   else if (d <= 256) ST_LAUNCH(2);
   else if (d <= 512) ST_LAUNCH(4);
@@ -358,14 +366,15 @@ int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst
   if (!((cols & 3) == 0 && (lds & 3) == 0 && (ldd & 3) == 0 && aligned16(src) && aligned16(dst))) {
     const int64_t n = rows * cols;
     ProfScope prof(stream, PROF_ROUND, 2.0 * rows * cols * 4);
-    round_tf32_scalar_kernel<<<persistent_grid((n + 255) / 256, 16), 256, 0, stream>>>(src, lds, dst, ldd, rows, cols);
+    ST_CHECK_CUDA(launch_pdl(round_tf32_scalar_kernel, dim3(persistent_grid((n + 255) / 256, 16)), dim3(256), 0, stream, src,
+                             lds, dst, ldd, rows, cols));
     ST_CHECK_LAUNCH();
     return ST_OK;
   }
   const int64_t total = rows * (cols / 4);
   const int grid = persistent_grid((total + 255) / 256, 16);
   ProfScope prof(stream, PROF_ROUND, 2.0 * rows * cols * 4);
-  round_tf32_kernel<<<grid, 256, 0, stream>>>(src, lds, dst, ldd, rows, cols / 4);
+  ST_CHECK_CUDA(launch_pdl(round_tf32_kernel, dim3(grid), dim3(256), 0, stream, src, lds, dst, ldd, rows, cols / 4));
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -380,7 +389,7 @@ int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, in
   const int64_t cap = (static_cast<int64_t>(num_sms()) * 8 + grid.x - 1) / grid.x;
   grid.y = static_cast<unsigned>(ychunks < cap ? ychunks : cap);
   ProfScope prof(stream, PROF_COLSUM, 1.0 * rows * cols * 4);
-  colsum_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, cols, out);
+  ST_CHECK_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, stream, x, ld, rows, cols, out));
   ST_CHECK_LAUNCH();
   return ST_OK;
 }

@@ -81,11 +81,13 @@ class GradSink:
     The composite backward kernels OVERWRITE their parameter gradients, so when every parameter of an operator
     carries a sink they write straight into the flat gradient buffer and return None to autograd — no temporary, no
     AccumulateGrad `+=` kernel (263 of them per step in the 6+6 model).  `written` guards weight sharing: a second
-    use of the same parameter within one step falls back to the ordinary accumulate path."""
-    __slots__ = ("view", "written")
+    use of the same parameter within one step falls back to the ordinary accumulate path.  `zeroed` is set by the owner of
+    the buffer (FlatParams.zero_grad) after it cleared the whole buffer in one pass: the backward operators then skip their
+    own per-tensor clears (grads_zeroed in the st_*_bwd_args; ~200 memset nodes per training step otherwise)."""
+    __slots__ = ("view", "written", "zeroed")
 
     def __init__(self, view: torch.Tensor):
-        self.view, self.written = view, False
+        self.view, self.written, self.zeroed = view, False, False
 
 
 _SINK_ATTR = "_st_grad_sink"
@@ -131,13 +133,16 @@ def _sinks_of(params):
 
 
 def _claim(sinks):
-    """Inside backward: take the sinks (None if any was written meanwhile) and mark them written."""
+    """Inside backward: take the sinks (None if any was written meanwhile) and mark them written.  Returns
+    (views or None, zeroed): zeroed = 1 when every view is known to hold zeros (see GradSink)."""
     if sinks is None or any(s is not None and s.written for s in sinks):
-        return None
+        return None, 0
+    zeroed = 1
     for s in sinks:
         if s is not None:
-            s.written = True
-    return [None if s is None else s.view for s in sinks]
+            zeroed &= int(s.zeroed)
+            s.written, s.zeroed = True, False
+    return [None if s is None else s.view for s in sinks], zeroed
 
 
 _seed_state = [0]
@@ -377,7 +382,7 @@ class _MultiHeadAttention(torch.autograd.Function):
         dq_in = torch.empty_like(qc)
         dk_in = dq_in if same_qkv else torch.empty_like(kc)
         dv_in = dk_in if same_kv else torch.empty_like(vc)
-        direct = _claim(ctx.sinks)
+        direct, zeroed = _claim(ctx.sinks)
         grads = direct if direct is not None else [torch.empty_like(t) for t in params]
         if direct is None and params[0].shape == params[2].shape == params[4].shape == (d, d):
             # dW / db of the three projections as slices of one packed buffer: st_mha_bwd then computes projections that
@@ -396,7 +401,7 @@ class _MultiHeadAttention(torch.autograd.Function):
         a = _lib.MhaBwdArgs(f=f, dout=_p(dout), dq_in=_p(dq_in), dk_in=_p(dk_in), dv_in=_p(dv_in), dresidual=None,
                             dwq=_p(grads[0]), dbq=_p(grads[1]), dwk=_p(grads[2]), dbk=_p(grads[3]), dwv=_p(grads[4]),
                             dbv=_p(grads[5]), dwo=_p(grads[6]), dbo=_p(grads[7]), dln_g=_p(grads[8]),
-                            dln_b=_p(grads[9]))
+                            dln_b=_p(grads[9]), grads_zeroed=zeroed)
         check(lib.st_mha_bwd(C.byref(a), _stream()))
         # aliased inputs received ONE combined gradient; hand it to the first alias only
         gq, gk, gv = dq_in, (None if same_qkv else dk_in), (None if same_kv else dv_in)
@@ -463,7 +468,7 @@ class _PositionwiseFFN(torch.autograd.Function):
         n_ws = lib.st_ffn_ws_floats(rows, d, d_ff)
         ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
         dx = torch.empty_like(xc)
-        direct = _claim(ctx.sinks)
+        direct, zeroed = _claim(ctx.sinks)
         grads = direct if direct is not None else [torch.empty_like(t) for t in params]
         f = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(xc), w1=_p(params[0]), b1=_p(params[1]),
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=eps,
@@ -471,7 +476,7 @@ class _PositionwiseFFN(torch.autograd.Function):
                          saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws, w1_tf32=_p(ctx.twins[0]),
                          w2_tf32=_p(ctx.twins[1]))
         a = _lib.FfnBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw1=_p(grads[0]), db1=_p(grads[1]), dw2=_p(grads[2]),
-                            db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]))
+                            db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]), grads_zeroed=zeroed)
         check(lib.st_ffn_bwd(C.byref(a), _stream()))
         if direct is not None:
             grads = [None] * len(params)
@@ -605,14 +610,14 @@ class _Frontend(torch.autograd.Function):
         n_ws = lib.st_frontend_ws_floats(rows, k, d)
         ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
         dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
-        direct = _claim(ctx.sinks)
+        direct, zeroed = _claim(ctx.sinks)
         grads = direct if direct is not None else [torch.empty_like(t) for t in params]
         f = _lib.FrontendArgs(rows=rows, T=T, in_dim=k, d_model=d, x=_p(xc), w=_p(params[0]), b=_p(params[1]),
                               ln_g=_p(params[2]), ln_b=_p(params[3]), pe=_p(pe), eps=eps, dropout_p=p, seed=seed,
                               round_out=0, out=None, saved=_p(saved), saved_floats=saved.numel(), ws=_p(ws),
                               ws_floats=n_ws)
         a = _lib.FrontendBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw=_p(grads[0]), db=_p(grads[1]), dln_g=_p(grads[2]),
-                                 dln_b=_p(grads[3]))
+                                 dln_b=_p(grads[3]), grads_zeroed=zeroed)
         check(lib.st_frontend_bwd(C.byref(a), _stream()))
         if direct is not None:
             grads = [None] * 4
@@ -664,7 +669,7 @@ class _Linear(torch.autograd.Function):
         n_ws = lib.st_linear_ws_floats(rows, k, n)
         ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
         dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
-        direct = _claim(ctx.sinks)
+        direct, zeroed = _claim(ctx.sinks)
         if direct is not None:
             dw, db = direct[0], (direct[1] if bc is not None else None)
         else:
@@ -672,7 +677,7 @@ class _Linear(torch.autograd.Function):
             db = torch.empty_like(bc) if (bc is not None and ctx.needs_input_grad[2]) else None
         f = _lib.LinearArgs(rows=rows, in_dim=k, out_dim=n, x=_p(xc), x_is_tf32=x_clean, w=_p(wc), b=_p(bc), y=None, ldy=n,
                             saved=_p(saved), saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws)
-        a = _lib.LinearBwdArgs(f=f, dy=_p(dy2), lddy=lddy, dx=_p(dx), dw=_p(dw), db=_p(db))
+        a = _lib.LinearBwdArgs(f=f, dy=_p(dy2), lddy=lddy, dx=_p(dx), dw=_p(dw), db=_p(db), grads_zeroed=zeroed)
         check(lib.st_linear_bwd(C.byref(a), _stream()))
         if direct is not None:
             dw = db = None
@@ -713,9 +718,10 @@ class _Embedding(torch.autograd.Function):
         vocab, d, padding_idx = ctx.cfg
         dout = _contig(dout)
         lib = _lib_for(dout)
-        direct = _claim(ctx.sinks)
+        direct, zeroed = _claim(ctx.sinks)
         dtable = direct[0] if direct is not None else torch.empty(vocab, d, device=dout.device, dtype=torch.float32)
-        check(lib.st_embed_bwd(_p(idx), _p(dout), _p(dtable), idx.numel(), d, vocab, padding_idx, 1, _stream()))
+        check(lib.st_embed_bwd(_p(idx), _p(dout), _p(dtable), idx.numel(), d, vocab, padding_idx, 0 if zeroed else 1,
+                               _stream()))
         return None, (None if direct is not None else dtable), None, None, None
 
 

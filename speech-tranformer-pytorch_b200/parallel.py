@@ -94,7 +94,7 @@ class FlatParams:
     def zero_grad(self) -> None:
         self.grad.zero_()                                # one memset; direct writers overwrite, autograd accumulates
         for p, o, s in zip(self.params, self.offsets, self.sinks):
-            s.written = False
+            s.written, s.zeroed = False, True            # operators skip their own per-tensor clears this step
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
                 s.view = p.grad
