@@ -256,8 +256,10 @@ def main_b200(args):
     if sampler:
         sampler.start()
     launches0 = lib.st_launch_count()
+    early0 = trainer.early_launches
     ms = timed(step_resident, args.steps)
     launches = lib.st_launch_count() - launches0
+    early = (trainer.early_launches - early0) / args.steps
     clocks = sampler.stop() if sampler else None
     frames = args.batch * args.frames * n * args.steps
     value = frames / (ms * 1e-3)
@@ -267,6 +269,26 @@ def main_b200(args):
     ms_e2e = timed(step_e2e, args.steps)
     e2e = {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "ms_per_step": ms_e2e / args.steps}
+
+    # ---- N > 1: the gradient exchange (bucketed all-reduce started under backward, parallel.py).  One untimed step checks
+    # that every rank holds the SAME reduced gradient: a bucket reduced before its last local write would differ.
+    dp = None
+    if world > 1:
+        trainer.zero_grad()
+        inputs, targets, in_len, tgt_len, truth = resident
+        logits, _ = net(inputs, in_len, targets, tgt_len)
+        crit(logits.view(-1, V), truth.view(-1)).backward()
+        trainer.allreduce_gradients()
+        ref = trainer.fp.grad.clone()
+        dist.broadcast(ref, 0)
+        diff = (ref - trainer.fp.grad).abs().max()
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        dp = {"collective": "NCCL all-reduce(SUM) of the flat fp32 gradient buffer", "bytes_per_step": 4 * trainer.fp.numel,
+              "buckets": len(trainer.buckets.items), "buckets_started_under_backward_per_step": early,
+              "replica_grad_max_abs_diff": float(diff.item())}
+        if dp["replica_grad_max_abs_diff"] != 0.0:
+            print(f"bench.py: WARNING replicas disagree on the reduced gradient ({dp['replica_grad_max_abs_diff']:.3e})",
+                  file=sys.stderr, flush=True)
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream
     roofline, breakdown = None, None
@@ -384,7 +406,7 @@ def main_b200(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic", "config": workload_config(args, n),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "kernel_breakdown": breakdown, "encoder_layer": enc_layer, "cpu_baseline": cpu}
+                "kernel_breakdown": breakdown, "encoder_layer": enc_layer, "cpu_baseline": cpu, "data_parallel": dp}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

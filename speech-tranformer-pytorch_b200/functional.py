@@ -84,10 +84,14 @@ class GradSink:
     use of the same parameter within one step falls back to the ordinary accumulate path.  `zeroed` is set by the owner of
     the buffer (FlatParams.zero_grad) after it cleared the whole buffer in one pass: the backward operators then skip their
     own per-tensor clears (grads_zeroed in the st_*_bwd_args; ~200 memset nodes per training step otherwise)."""
-    __slots__ = ("view", "written", "zeroed")
+    __slots__ = ("view", "written", "zeroed", "uses", "done")
 
     def __init__(self, view: torch.Tensor):
         self.view, self.written, self.zeroed = view, False, False
+        # uses: forward operators that took this parameter since the last zero_grad; done: backward operators that have
+        # since written its gradient directly (kernels enqueued).  done == uses >= 1 means the slice is final for this step
+        # (stream order) — what parallel.DataParallelTrainer needs to start a bucket's all-reduce under the backward pass.
+        self.uses, self.done = 0, 0
 
 
 _SINK_ATTR = "_st_grad_sink"
@@ -120,16 +124,39 @@ def attach_grad_sink(param: torch.Tensor, view: torch.Tensor) -> GradSink:
 
 def _sinks_of(params):
     """The params' sinks if ALL of them have an unwritten sink of the right shape, else None."""
+    found = [None if p is None else getattr(p, _SINK_ATTR, None) for p in params]
+    for s in found:
+        if s is not None:
+            s.uses += 1
     out = []
-    for p in params:
+    for p, s in zip(params, found):
         if p is None:
             out.append(None)
             continue
-        s = getattr(p, _SINK_ATTR, None)
         if s is None or s.written or s.view.shape != p.shape or not s.view.is_contiguous():
             return None
         out.append(s)
     return out
+
+
+_grad_ready_cb = None
+
+
+def set_grad_ready_callback(fn) -> None:
+    """fn(sinks) is called from inside backward right after an operator has ENQUEUED the kernels that write those
+    sinks' gradients (None removes it).  Used by parallel.DataParallelTrainer to overlap the gradient all-reduce."""
+    global _grad_ready_cb
+    _grad_ready_cb = fn
+
+
+def _notify(sinks, direct) -> None:
+    if direct is None or not sinks:
+        return
+    for s in sinks:
+        if s is not None:
+            s.done += 1
+    if _grad_ready_cb is not None:
+        _grad_ready_cb([s for s in sinks if s is not None])
 
 
 def _claim(sinks):
@@ -403,6 +430,7 @@ class _MultiHeadAttention(torch.autograd.Function):
                             dbv=_p(grads[5]), dwo=_p(grads[6]), dbo=_p(grads[7]), dln_g=_p(grads[8]),
                             dln_b=_p(grads[9]), grads_zeroed=zeroed)
         check(lib.st_mha_bwd(C.byref(a), _stream()))
+        _notify(ctx.sinks, direct)
         # aliased inputs received ONE combined gradient; hand it to the first alias only
         gq, gk, gv = dq_in, (None if same_qkv else dk_in), (None if same_kv else dv_in)
         if same_qk and not same_kv:   # q is k but v differs: separate buffers were filled, combine them
@@ -478,6 +506,7 @@ class _PositionwiseFFN(torch.autograd.Function):
         a = _lib.FfnBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw1=_p(grads[0]), db1=_p(grads[1]), dw2=_p(grads[2]),
                             db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]), grads_zeroed=zeroed)
         check(lib.st_ffn_bwd(C.byref(a), _stream()))
+        _notify(ctx.sinks, direct)
         if direct is not None:
             grads = [None] * len(params)
         return (dx, *grads, None, None, None, None)
@@ -619,6 +648,7 @@ class _Frontend(torch.autograd.Function):
         a = _lib.FrontendBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw=_p(grads[0]), db=_p(grads[1]), dln_g=_p(grads[2]),
                                  dln_b=_p(grads[3]), grads_zeroed=zeroed)
         check(lib.st_frontend_bwd(C.byref(a), _stream()))
+        _notify(ctx.sinks, direct)
         if direct is not None:
             grads = [None] * 4
         return (dx, *grads, None, None, None, None, None)
@@ -679,6 +709,7 @@ class _Linear(torch.autograd.Function):
                             saved=_p(saved), saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws)
         a = _lib.LinearBwdArgs(f=f, dy=_p(dy2), lddy=lddy, dx=_p(dx), dw=_p(dw), db=_p(db), grads_zeroed=zeroed)
         check(lib.st_linear_bwd(C.byref(a), _stream()))
+        _notify(ctx.sinks, direct)
         if direct is not None:
             dw = db = None
         return dx, dw, db
@@ -722,6 +753,7 @@ class _Embedding(torch.autograd.Function):
         dtable = direct[0] if direct is not None else torch.empty(vocab, d, device=dout.device, dtype=torch.float32)
         check(lib.st_embed_bwd(_p(idx), _p(dout), _p(dtable), idx.numel(), d, vocab, padding_idx, 0 if zeroed else 1,
                                _stream()))
+        _notify(ctx.sinks, direct)
         return None, (None if direct is not None else dtable), None, None, None
 
 

@@ -3,9 +3,13 @@
 Mirrors the reference's only parallelism strategy, train_multi.py: one process per GPU (:128), parameters
 broadcast from rank 0 once (:176-177), every step the gradients are all-reduced (average) across ranks
 (Horovod DistributedOptimizer, :161-163), then clip + Noam-Adam (train.py:45-46, Optim.py:9-45).  Here all
-parameters live in ONE contiguous fp32 buffer and all gradients in another, so a step issues exactly one
-NCCL all-reduce over NVLink/NVSwitch and two HBM-bound kernels (squared norm, fused clip+Adam) from
-libst_b200.so.  The clip uses the REDUCED gradient (the reference clips local gradients before Horovod has
+parameters live in ONE contiguous fp32 buffer and all gradients in another, so the gradient exchange is an
+NCCL all-reduce over NVLink/NVSwitch of that buffer and the update is two HBM-bound kernels (squared norm,
+fused clip+Adam) from libst_b200.so.  The buffer is reduced in a few contiguous buckets (~13 MB): a bucket's
+all-reduce starts on NCCL's stream as soon as the backward operators that write its slice have been enqueued
+(functional.set_grad_ready_callback), so the exchange runs under the rest of the backward pass and only the
+last bucket (front-end + first encoder layer) is exposed; whatever was not started early is reduced after
+backward.  The clip uses the REDUCED gradient (the reference clips local gradients before Horovod has
 synchronised them, train_multi.py:66 — a bug not reproduced here).
 
 The flattening / bucketing logic is device-agnostic and is exercised on CPU with gloo (tests/test_dp_gloo.py);
@@ -95,16 +99,72 @@ class FlatParams:
         self.grad.zero_()                                # one memset; direct writers overwrite, autograd accumulates
         for p, o, s in zip(self.params, self.offsets, self.sinks):
             s.written, s.zeroed = False, True            # operators skip their own per-tensor clears this step
+            s.uses = s.done = 0
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
                 s.view = p.grad
+
+
+class _Bucket:
+    __slots__ = ("lo", "hi", "sinks", "remaining", "started", "work")
+
+    def __init__(self, lo: int, hi: int, sinks):
+        self.lo, self.hi, self.sinks = lo, hi, sinks
+        self.remaining, self.started, self.work = len(sinks), False, None
+
+
+class GradBuckets:
+    """Contiguous slices of the flat gradient buffer (whole parameters, >= `bucket_floats` each except the last) with
+    the bookkeeping that tells when a slice is final during backward.  Pure host logic (tested on CPU)."""
+
+    def __init__(self, fp: FlatParams, bucket_floats: int):
+        self.items: List[_Bucket] = []
+        self.numel = fp.numel
+        lo, sinks = 0, []
+        for i, (p, o, s) in enumerate(zip(fp.params, fp.offsets, fp.sinks)):
+            sinks.append(s)
+            end = fp.offsets[i + 1] if i + 1 < len(fp.params) else fp.numel
+            if end - lo >= bucket_floats or i + 1 == len(fp.params):
+                self.items.append(_Bucket(lo, end, sinks))
+                lo, sinks = end, []
+        self.of = {id(s): b for b in self.items for s in b.sinks}
+
+    def reset(self) -> None:
+        for b in self.items:
+            b.remaining, b.started, b.work = len(b.sinks), False, None
+
+    def mark_done(self, sinks) -> List[_Bucket]:
+        """Record that these sinks were written directly; returns the buckets that thereby became final: every parameter
+        in them was used by a forward operator and each use has been written (GradSink.done == uses >= 1)."""
+        ready = []
+        for s in sinks:
+            b = self.of.get(id(s))
+            if b is None or b.started or s.done != s.uses:
+                continue
+            b.remaining -= 1
+            if b.remaining == 0:
+                b.started = True
+                ready.append(b)
+        return ready
+
+    def pending_ranges(self):
+        """Maximal contiguous [lo, hi) ranges of buckets whose reduction has not been started."""
+        out = []
+        for b in self.items:
+            if b.started:
+                continue
+            if out and out[-1][1] == b.lo:
+                out[-1][1] = b.hi
+            else:
+                out.append([b.lo, b.hi])
+        return [(lo, hi) for lo, hi in out]
 
 
 class DataParallelTrainer:
     """zero_grad -> (caller: forward + backward) -> allreduce -> clip + Adam, on flat buffers."""
 
     def __init__(self, module: torch.nn.Module, d_model: int, n_warmup_steps: int = 12000, max_grad_norm: float = 5.0,
-                 betas=(0.9, 0.98), eps: float = 1e-9, process_group=None):
+                 betas=(0.9, 0.98), eps: float = 1e-9, process_group=None, overlap: bool = True, bucket_mb: float = 13.0):
         self.module = module
         self.fp = FlatParams(ordered_parameters(module))
         self.exp_avg = torch.zeros_like(self.fp.flat)
@@ -116,6 +176,22 @@ class DataParallelTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.global_step = 0
         self.lr = 0.0
+        self.buckets = GradBuckets(self.fp, int(bucket_mb * (1 << 20) / 4))
+        self.overlap = bool(overlap) and self.world > 1
+        self.early_launches = 0                          # buckets whose all-reduce started under backward (diagnostic)
+        if self.overlap:
+            from .functional import set_grad_ready_callback
+            set_grad_ready_callback(self._on_grads_ready)
+
+    def _reduce(self, lo: int, hi: int, async_op: bool):
+        return dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+
+    def _on_grads_ready(self, sinks) -> None:
+        """Called inside backward after an operator enqueued the kernels writing `sinks`: start the all-reduce of every
+        bucket that became final.  Every rank runs the same graph in the same order, so the collectives line up."""
+        for b in self.buckets.mark_done(sinks):
+            b.work = self._reduce(b.lo, b.hi, async_op=True)   # NCCL's stream waits for the kernels enqueued so far
+            self.early_launches += 1
 
     # --- train_multi.py:176-177
     def broadcast_parameters(self, src: int = 0) -> None:
@@ -125,11 +201,19 @@ class DataParallelTrainer:
 
     def zero_grad(self) -> None:
         self.fp.zero_grad()
+        self.buckets.reset()
 
-    # --- train_multi.py:161-163 (one collective for the whole model)
+    # --- train_multi.py:161-163 (the whole model, in flat-buffer order)
     def allreduce_gradients(self):
+        """After backward: reduce what the overlap path has not started (everything when overlap is off: ONE collective
+        over the whole buffer), then make the compute stream wait for the early collectives."""
         if self.world > 1:
-            return dist.all_reduce(self.fp.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=False)
+            for lo, hi in self.buckets.pending_ranges():
+                self._reduce(lo, hi, async_op=False)
+            for b in self.buckets.items:
+                if b.work is not None:
+                    b.work.wait()
+                    b.work = None
         return None
 
     # --- train.py:45-46

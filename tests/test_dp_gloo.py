@@ -68,6 +68,73 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_overlap(rank, world, port, q):
+    """Bucketed, overlapped gradient exchange: buckets whose parameters were all written directly are reduced early
+    (asynchronously, in backward order), the rest after backward; the result equals one all-reduce of the buffer."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from speech_tranformer_pytorch_b200 import parallel as P, functional as F
+        torch.manual_seed(5)
+        net = torch.nn.Sequential(*[torch.nn.Linear(16, 16) for _ in range(6)])
+        tr = P.DataParallelTrainer(net, d_model=512, bucket_mb=4 * 272 / (1 << 20))      # 272 floats: one layer (weight + bias) per bucket
+        assert tr.overlap and len(tr.buckets.items) >= 5
+        assert tr.buckets.items[0].lo == 0 and tr.buckets.items[-1].hi == tr.fp.numel
+        assert all(a.hi == b.lo for a, b in zip(tr.buckets.items, tr.buckets.items[1:])), "buckets tile the buffer"
+        tr.zero_grad()
+        torch.manual_seed(50 + rank)
+        tr.fp.grad.copy_(torch.randn(tr.fp.numel))                     # this rank's local gradient
+        local = tr.fp.grad.clone()
+        # forward used every parameter once, except the first layer's weight twice (second use = autograd fallback)
+        for s in tr.fp.sinks:
+            s.uses = 1
+        tr.fp.sinks[0].uses = 2
+        # backward order = reverse registration order; each operator writes (weight, bias) then notifies
+        early_before = tr.early_launches
+        for i in reversed(range(0, len(tr.fp.sinks), 2)):
+            F._notify(tr.fp.sinks[i:i + 2], direct=[s.view for s in tr.fp.sinks[i:i + 2]])
+        started = [b.started for b in tr.buckets.items]
+        assert not started[0], "a bucket holding a parameter with an outstanding use must wait for the end"
+        assert all(started[1:]) and tr.early_launches - early_before == len(started) - 1
+        assert tr.buckets.pending_ranges() == [(0, tr.buckets.items[0].hi)]
+        tr.allreduce_gradients()
+        assert all(b.work is None for b in tr.buckets.items)
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        assert torch.allclose(tr.fp.grad, sum(parts), atol=1e-6), "bucketed exchange == one all-reduce(SUM)"
+        # next step: bookkeeping is reset, nothing is early when no operator notifies
+        tr.zero_grad()
+        assert all(s.uses == 0 and s.done == 0 for s in tr.fp.sinks)
+        assert tr.buckets.pending_ranges() == [(0, tr.fp.numel)]
+        F.set_grad_ready_callback(None)
+        q.put((rank, "ok", 0.0))
+    except Exception:
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_world2(worker):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in results:
+        assert status == "ok", f"rank {rank}: {info}"
+
+
+def test_overlapped_bucketed_allreduce_world2():
+    _run_world2(_worker_overlap)
+
+
 def test_flat_buffer_data_parallel_world2():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
