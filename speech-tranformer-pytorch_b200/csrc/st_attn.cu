@@ -865,7 +865,12 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
   p.trace = get_option("attn_trace");
   p.dbq = a.dbq; p.dbk = a.dbk; p.dbv = a.dbv;
   p.delta = a.delta; p.dq = a.dq; p.lddq = a.lddq; p.dk = a.dk_; p.lddk = a.lddk; p.dv = a.dv; p.lddv = a.lddv;
-  {
+  // delta = rowsum(dO * O): the pipelined dQ kernel forms it from the dO rows it stages into TMEM anyway (and publishes it
+  // for the dK/dV kernel); the other paths (d_k = 128, shared-memory resident tiles, option attn_delta_kernel) run this pass
+  const bool pipelined = DK <= 64 && !get_option("attn_bwd_simple");
+  const bool fused_delta = pipelined && !get_option("attn_dq_res_smem") && !get_option("attn_delta_kernel");
+  if (fused_delta) p.delta_out = a.delta;
+  else {
     const int64_t rows = static_cast<int64_t>(f.B) * f.Lq;
     const int64_t blocks = (rows + 7) / 8;
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
@@ -874,7 +879,7 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
                              a.dctx, a.lddctx, f.ctx, f.ldctx, a.delta, f.B, f.H, f.Lq, DK));
     ST_CHECK_LAUNCH();
   }
-  if (DK <= 64 && !get_option("attn_bwd_simple")) return attn_bwd_pipelined(s, a, p);  // st_attn_bwd.cu
+  if (pipelined) return attn_bwd_pipelined(s, a, p);  // st_attn_bwd.cu
   {
     CUtensorMap tk, tv, tqk, tqm, tdk, tdm;
     ST_TRY(make_act_tmap(&tk, f.k, f.ldk, cols, f.Lk, f.B, 128, 0, DK));

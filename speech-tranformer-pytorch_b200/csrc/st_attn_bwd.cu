@@ -130,10 +130,14 @@ __device__ __forceinline__ void bias_colsum16(const float (&v)[16], float* out, 
 
 // Resident tiles -> TMEM: compute slice `slice` (0..3) owns one 32-column chunk of one of the two resident tensors
 // (x0 at columns [t_x0, t_x0+DK), x1 at [t_x1, ...)); the thread writes its row's 32 floats (zeros for rows >= L).
+// `dot` (optional, same indexing as x1 with leading dimension ld_dot): the slices that carry an x1 chunk return the dot
+// product of their 32 columns with it (dQ kernel: x1 = dO, dot = O, the partial sums of delta = rowsum(dO * O)); 0 otherwise.
 template <int DK>
-__device__ __forceinline__ void resident_to_tmem(const float* x0, int64_t ld0, const float* x1, int64_t ld1, int64_t row,
-                                                 bool row_ok, int h, int slice, uint32_t t_lane, uint32_t t_x0, uint32_t t_x1) {
+__device__ __forceinline__ float resident_to_tmem(const float* x0, int64_t ld0, const float* x1, int64_t ld1, int64_t row,
+                                                  bool row_ok, int h, int slice, uint32_t t_lane, uint32_t t_x0, uint32_t t_x1,
+                                                  const float* dot = nullptr, int64_t ld_dot = 0) {
   constexpr int CH = DK / 32;            // 32-column chunks per tensor
+  float part = 0.f;
   if (slice < 2 * CH) {                  // warp-uniform
     const int which = slice / CH, c = slice % CH;
     const float* src = (which == 0 ? x0 + row * ld0 : x1 + row * ld1) + h * DK + c * 32;
@@ -144,9 +148,21 @@ __device__ __forceinline__ void resident_to_tmem(const float* x0, int64_t ld0, c
       if (row_ok) v = __ldg(reinterpret_cast<const float4*>(src + i));
       r[i] = __float_as_uint(v.x); r[i + 1] = __float_as_uint(v.y); r[i + 2] = __float_as_uint(v.z); r[i + 3] = __float_as_uint(v.w);
     }
+    if (dot != nullptr && which == 1 && row_ok) {
+      const float* o = dot + row * ld_dot + h * DK + c * 32;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(o + i));
+        acc[0] = fmaf(__uint_as_float(r[i]), v.x, acc[0]); acc[1] = fmaf(__uint_as_float(r[i + 1]), v.y, acc[1]);
+        acc[2] = fmaf(__uint_as_float(r[i + 2]), v.z, acc[2]); acc[3] = fmaf(__uint_as_float(r[i + 3]), v.w, acc[3]);
+      }
+      part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
     tmem_st32(t_lane + (which == 0 ? t_x0 : t_x1) + c * 32, r);
     tmem_st_wait();
   }
+  return part;
 }
 
 // ================================================================================ dQ
@@ -177,6 +193,7 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) uint32_t s_ckey[STAGES][BT];
   __shared__ uint32_t s_mb[STAGES][BT / 32];
+  __shared__ float s_dpart[2][BQ];         // fused delta: per-row partial sums of dO * O, one per 32-column chunk
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -300,14 +317,28 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int col0 = slice * 16;
     const int64_t grow = static_cast<int64_t>(b) * p.Lq + (row_ok ? row : 0);
+    const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
+    float delta;
     if (!RS) {
-      resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO);
+      // delta = rowsum(dO * O) is formed here, from the dO chunk this thread stages into TMEM anyway plus one read of the
+      // matching O chunk, and published for the dK/dV kernel that follows (p.delta_out): no separate delta pass
+      constexpr int CH = DK / 32;
+      const float part = resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO,
+                                              p.delta_out ? p.ctx : nullptr, p.ldctx);
+      if (p.delta_out && slice >= CH && slice < 2 * CH) s_dpart[slice - CH][quarter * 32 + lane] = part;
       tc_fence_before();
       mbar_arrive(&res_ready);
+      if (p.delta_out) {
+        asm volatile("bar.sync 1, %0;" ::"n"(NCOMP) : "memory");   // the compute warps only
+        delta = s_dpart[0][quarter * 32 + lane] + (CH == 2 ? s_dpart[1][quarter * 32 + lane] : 0.f);
+        if (slice == 0 && row_ok) p.delta_out[stat] = delta;
+      } else {
+        delta = row_ok ? p.delta[stat] : 0.f;
+      }
+    } else {
+      delta = row_ok ? p.delta[stat] : 0.f;
     }
-    const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
     const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
-    const float delta = row_ok ? p.delta[stat] : 0.f;
     const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(stat)) : 0u;
     const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
     for (int t = 0; t < n_kv; ++t) {
@@ -854,6 +885,28 @@ template <int DK>
 int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
   const AttnArgs& f = a.f;
   const int cols = f.H * DK;
+  // dQ first: with the resident tiles in TMEM it also produces delta (p.delta_out) for the dK/dV kernel behind it
+  {
+    CUtensorMap tkk, tkm, tvk;
+    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BT, 0, DK));
+    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BT, 1, DK));
+    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BT, 0, DK));
+    CUtensorMap tqr, tdr;
+    ST_TRY(make_act_tmap(&tqr, f.q, f.ldq, cols, f.Lq, f.B, 128, 0, DK));
+    ST_TRY(make_act_tmap(&tdr, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0, DK));
+    const bool rs = get_option("attn_dq_res_smem") != 0;
+    constexpr int SMEM_TS = 4 * 3 * BT * DK * 4 + 1024;
+    constexpr int SMEM_RS = 3 * 3 * BT * DK * 4 + 2 * 128 * DK * 4 + 1024;
+    const int SMEM = rs ? SMEM_RS : SMEM_TS;
+    auto kern = rs ? attn_bwd_dq_pipe<DK, true> : attn_bwd_dq_pipe<DK, false>;
+    static bool attr[2] = {false, false};
+    if (!attr[rs]) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr[rs] = true; }
+    dim3 grid((f.Lq + 127) / 128, f.H, f.B);
+    // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
+    ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
+    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, tqr, tdr, p));
+    ST_CHECK_LAUNCH();
+  }
   {
     CUtensorMap tqk, tqm, tdk, tdm;
     ST_TRY(make_act_tmap(&tqk, f.q, f.ldq, cols, f.Lq, f.B, BT, 0, DK));
@@ -893,27 +946,6 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, tkr, tvr, p));
     ST_CHECK_LAUNCH();
     }
-  }
-  {
-    CUtensorMap tkk, tkm, tvk;
-    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BT, 0, DK));
-    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BT, 1, DK));
-    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BT, 0, DK));
-    CUtensorMap tqr, tdr;
-    ST_TRY(make_act_tmap(&tqr, f.q, f.ldq, cols, f.Lq, f.B, 128, 0, DK));
-    ST_TRY(make_act_tmap(&tdr, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0, DK));
-    const bool rs = get_option("attn_dq_res_smem") != 0;
-    constexpr int SMEM_TS = 4 * 3 * BT * DK * 4 + 1024;
-    constexpr int SMEM_RS = 3 * 3 * BT * DK * 4 + 2 * 128 * DK * 4 + 1024;
-    const int SMEM = rs ? SMEM_RS : SMEM_TS;
-    auto kern = rs ? attn_bwd_dq_pipe<DK, true> : attn_bwd_dq_pipe<DK, false>;
-    static bool attr[2] = {false, false};
-    if (!attr[rs]) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr[rs] = true; }
-    dim3 grid((f.Lq + 127) / 128, f.H, f.B);
-    // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
-    ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, tqr, tdr, p));
-    ST_CHECK_LAUNCH();
   }
   return ST_OK;
 }

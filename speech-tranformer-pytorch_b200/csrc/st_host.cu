@@ -45,6 +45,7 @@ Option g_options[] = {
     {"attn_dkv_no_small", 0},  // 1 = never use the single-query-tile dK/dV kernel (A/B testing)
     {"attn_fuse_bias", 0},     // 1 = dq/dk/dv bias column sums from the attention-backward epilogues (measured slower)
     {"attn_dq_res_smem", 0},   // 1 = dQ kernel keeps its resident Q/dO tiles in shared memory (.ss MMAs) instead of TMEM
+    {"attn_delta_kernel", 0},  // 1 = separate delta = rowsum(dO * O) pass instead of forming it inside the dQ kernel (A/B testing)
     {"pdl", -1},               // programmatic dependent launch: 1 = on, 0 = off, -1 = unset (on unless ST_PDL=0 in the environment)
     {"attn_dkv_res_smem", 0},  // resident K/V tiles of the dK/dV kernel: 0 = heuristic (smem when Lq <= 128), 1 = smem, 2 = TMEM
 };
