@@ -226,8 +226,13 @@ def main_b200(args):
 
     h2d = sum(t.numel() * t.element_size() for t in host)
 
+    prefetch = sdata.DevicePrefetcher(dev)
+
     def step_e2e():
-        batch = [t.to(dev, non_blocking=True) for t in host]      # pinned host -> device, every step
+        # every step copies ITS inputs from pinned host memory (submitted one step ahead on a side stream, so the PCIe
+        # transfer runs under the previous step, as a pin_memory DataLoader does) and reads its loss back to the host
+        batch = prefetch.get()
+        prefetch.submit(host)
         loss = step_on(*batch)
         return loss.item()                                        # device -> host read of the step's result
 
@@ -264,11 +269,15 @@ def main_b200(args):
     frames = args.batch * args.frames * n * args.steps
     value = frames / (ms * 1e-3)
 
+    prefetch.submit(host)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    prefetch.get()                                                # drain the one batch in flight
     e2e = {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-           "ms_per_step": ms_e2e / args.steps}
+           "ms_per_step": ms_e2e / args.steps,
+           "note": "public API (model + loss modules + DataParallelTrainer.train_step) on a pinned host batch: H2D copy of every "
+                   "step's inputs on a side stream one step ahead (data.DevicePrefetcher), loss.item() every step"}
 
     # ---- N > 1: the gradient exchange (bucketed all-reduce started under backward, parallel.py).  One untimed step checks
     # that every rank holds the SAME reduced gradient: a bucket reduced before its last local write would differ.

@@ -32,3 +32,34 @@ def synthetic_batch(batch: int, t_max: int, l_max: int, feat: int, vocab: int, s
     if pin and torch.cuda.is_available():
         out = tuple(t.pin_memory() for t in out)
     return out
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device input pipeline (what a DataLoader with pin_memory feeds, train.py:29-36): `submit`
+    starts the copy of a pinned host batch on a side stream, `get` hands the tensors to the compute stream once the
+    copy has landed.  Submitting batch k+1 before running step k hides the PCIe transfer under the step."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._pending = None
+
+    def submit(self, host_batch) -> None:
+        if self._pending is not None:
+            raise RuntimeError("DevicePrefetcher: the previous batch has not been taken")
+        with torch.cuda.stream(self.stream):
+            batch = [t.to(self.device, non_blocking=True) for t in host_batch]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending = (batch, ev)
+
+    def get(self):
+        if self._pending is None:
+            raise RuntimeError("DevicePrefetcher: nothing submitted")
+        batch, ev = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in batch:
+            t.record_stream(cur)       # allocated on the side stream, consumed on the compute stream
+        return batch
