@@ -232,8 +232,8 @@ def main_b200(args):
         # every step copies ITS inputs from pinned host memory (submitted one step ahead on a side stream, so the PCIe
         # transfer runs under the previous step, as a pin_memory DataLoader does) and reads its loss back to the host
         batch = prefetch.get()
-        prefetch.submit(host)
-        loss = step_on(*batch)
+        loss = step_on(*batch)                                    # enqueue the step first: the GPU is idle after the last .item()
+        prefetch.submit(host)                                     # next step's inputs, copied under this step
         return loss.item()                                        # device -> host read of the step's result
 
     def barrier():

@@ -97,10 +97,12 @@ class FlatParams:
 
     def zero_grad(self) -> None:
         self.grad.zero_()                                # one memset; direct writers overwrite, autograd accumulates
-        for p, o, s in zip(self.params, self.offsets, self.sinks):
-            s.written, s.zeroed = False, True            # operators skip their own per-tensor clears this step
+        for s in self.sinks:                             # (kept lean: in a synchronous loop the GPU idles behind this)
+            s.written = False
+            s.zeroed = True                              # operators skip their own per-tensor clears this step
             s.uses = s.done = 0
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+        for p, o, s in zip(self.params, self.offsets, self.sinks):
+            if p.grad is not s.view:                     # someone replaced / dropped .grad (zero_grad(set_to_none=True), ...)
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
                 s.view = p.grad
 
