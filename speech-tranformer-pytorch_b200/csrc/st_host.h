@@ -62,7 +62,7 @@ int num_sms();
 // then block in pdl_wait() (griddepcontrol.wait, st_common.cuh) until the predecessor has completed and its writes are
 // visible.  EVERY thread of such a kernel must execute pdl_wait() before its first global-memory access and before any
 // early exit (a kernel that finished without waiting would let its successor overtake the predecessor's writes).
-// pdl_allowed: option "pdl" (default 1, environment ST_PDL=0 disables) and the stream is not being captured.
+// pdl_allowed: option "pdl" (default 1, environment ST_PDL=0 disables); under stream capture option "pdl_graphs" (default 1).
 int pdl_allowed(cudaStream_t s);
 template <typename... P, typename... A>
 cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {

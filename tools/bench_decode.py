@@ -9,7 +9,11 @@ from speech_tranformer_pytorch_b200 import data as sdata, decode, model as smode
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32); ap.add_argument("--frames", type=int, default=1000)
 ap.add_argument("--graphs", action="store_true"); ap.add_argument("--beam", type=int, default=10); ap.add_argument("--steps", type=int, default=50)
+ap.add_argument("--opt", action="append", default=[], help="library option name=value (st_set_option), repeatable")
 a = ap.parse_args()
+for kv in a.opt:
+    k, v = kv.split("=")
+    stb._lib.check(stb._lib.load().st_set_option(k.encode(), int(v)))
 dev = torch.device("cuda", 0)
 torch.manual_seed(2018)
 net = smodel.Transformer(smodel.headline_config()); smodel.init_parameters(net); net = net.to(dev).eval()
