@@ -130,14 +130,10 @@ __device__ __forceinline__ void bias_colsum16(const float (&v)[16], float* out, 
 
 // Resident tiles -> TMEM: compute slice `slice` (0..3) owns one 32-column chunk of one of the two resident tensors
 // (x0 at columns [t_x0, t_x0+DK), x1 at [t_x1, ...)); the thread writes its row's 32 floats (zeros for rows >= L).
-// `dot` (optional, same indexing as x1 with leading dimension ld_dot): the slices that carry an x1 chunk return the dot
-// product of their 32 columns with it (dQ kernel: x1 = dO, dot = O, the partial sums of delta = rowsum(dO * O)); 0 otherwise.
 template <int DK>
-__device__ __forceinline__ float resident_to_tmem(const float* x0, int64_t ld0, const float* x1, int64_t ld1, int64_t row,
-                                                  bool row_ok, int h, int slice, uint32_t t_lane, uint32_t t_x0, uint32_t t_x1,
-                                                  const float* dot = nullptr, int64_t ld_dot = 0) {
+__device__ __forceinline__ void resident_to_tmem(const float* x0, int64_t ld0, const float* x1, int64_t ld1, int64_t row,
+                                                 bool row_ok, int h, int slice, uint32_t t_lane, uint32_t t_x0, uint32_t t_x1) {
   constexpr int CH = DK / 32;            // 32-column chunks per tensor
-  float part = 0.f;
   if (slice < 2 * CH) {                  // warp-uniform
     const int which = slice / CH, c = slice % CH;
     const float* src = (which == 0 ? x0 + row * ld0 : x1 + row * ld1) + h * DK + c * 32;
@@ -148,21 +144,27 @@ __device__ __forceinline__ float resident_to_tmem(const float* x0, int64_t ld0, 
       if (row_ok) v = __ldg(reinterpret_cast<const float4*>(src + i));
       r[i] = __float_as_uint(v.x); r[i + 1] = __float_as_uint(v.y); r[i + 2] = __float_as_uint(v.z); r[i + 3] = __float_as_uint(v.w);
     }
-    if (dot != nullptr && which == 1 && row_ok) {
-      const float* o = dot + row * ld_dot + h * DK + c * 32;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(o + i));
-        acc[0] = fmaf(__uint_as_float(r[i]), v.x, acc[0]); acc[1] = fmaf(__uint_as_float(r[i + 1]), v.y, acc[1]);
-        acc[2] = fmaf(__uint_as_float(r[i + 2]), v.z, acc[2]); acc[3] = fmaf(__uint_as_float(r[i + 3]), v.w, acc[3]);
-      }
-      part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    }
     tmem_st32(t_lane + (which == 0 ? t_x0 : t_x1) + c * 32, r);
     tmem_st_wait();
   }
-  return part;
+}
+
+// Partial sum of delta = rowsum(dO * O) over quarter `part` (DK / 4 columns) of head h for one row: the four compute
+// threads that share a row each take a quarter (the dO row was read a moment ago by resident_to_tmem: an L1 / L2 hit).
+template <int DK>
+__device__ __forceinline__ float delta_partial(const float* dctx, int64_t lddctx, const float* ctx, int64_t ldctx, int64_t row,
+                                               int h, int part) {
+  constexpr int W = DK / 4;
+  const float* a = dctx + row * lddctx + h * DK + part * W;
+  const float* o = ctx + row * ldctx + h * DK + part * W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < W; i += 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a + i));
+    const float4 y = __ldg(reinterpret_cast<const float4*>(o + i));
+    acc[0] = fmaf(x.x, y.x, acc[0]); acc[1] = fmaf(x.y, y.y, acc[1]); acc[2] = fmaf(x.z, y.z, acc[2]); acc[3] = fmaf(x.w, y.w, acc[3]);
+  }
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 // ================================================================================ dQ
@@ -193,7 +195,7 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) uint32_t s_ckey[STAGES][BT];
   __shared__ uint32_t s_mb[STAGES][BT / 32];
-  __shared__ float s_dpart[2][BQ];         // fused delta: per-row partial sums of dO * O, one per 32-column chunk
+  __shared__ float s_dpart[4][BQ];         // fused delta: per-row partial sums of dO * O, one per compute slice (DK / 4 columns)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -320,17 +322,16 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
     float delta;
     if (!RS) {
-      // delta = rowsum(dO * O) is formed here, from the dO chunk this thread stages into TMEM anyway plus one read of the
-      // matching O chunk, and published for the dK/dV kernel that follows (p.delta_out): no separate delta pass
-      constexpr int CH = DK / 32;
-      const float part = resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO,
-                                              p.delta_out ? p.ctx : nullptr, p.ldctx);
-      if (p.delta_out && slice >= CH && slice < 2 * CH) s_dpart[slice - CH][quarter * 32 + lane] = part;
+      // delta = rowsum(dO * O) is formed here (and published for the dK/dV kernel that follows, p.delta_out) instead of by a
+      // separate pass: AFTER the resident tiles are handed to the MMA warp, so the extra O read runs under S(0) / dP(0)
+      resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO);
       tc_fence_before();
       mbar_arrive(&res_ready);
       if (p.delta_out) {
+        const int rit = quarter * 32 + lane;
+        s_dpart[slice][rit] = row_ok ? delta_partial<DK>(dctx, lddctx, p.ctx, p.ldctx, grow, h, slice) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(NCOMP) : "memory");   // the compute warps only
-        delta = s_dpart[0][quarter * 32 + lane] + (CH == 2 ? s_dpart[1][quarter * 32 + lane] : 0.f);
+        delta = (s_dpart[0][rit] + s_dpart[1][rit]) + (s_dpart[2][rit] + s_dpart[3][rit]);
         if (slice == 0 && row_ok) p.delta_out[stat] = delta;
       } else {
         delta = row_ok ? p.delta[stat] : 0.f;

@@ -178,6 +178,7 @@ class DataParallelTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.global_step = 0
         self.lr = 0.0
+        self._grads_clean = False
         self.buckets = GradBuckets(self.fp, int(bucket_mb * (1 << 20) / 4))
         self.overlap = bool(overlap) and self.world > 1
         self.early_launches = 0                          # buckets whose all-reduce started under backward (diagnostic)
@@ -204,6 +205,7 @@ class DataParallelTrainer:
     def zero_grad(self) -> None:
         self.fp.zero_grad()
         self.buckets.reset()
+        self._grads_clean = False                         # only train_step may vouch for a clean buffer
 
     # --- train_multi.py:161-163 (the whole model, in flat-buffer order)
     def allreduce_gradients(self):
@@ -237,10 +239,17 @@ class DataParallelTrainer:
         _lib.check(lib.st_adam_step(C.byref(a), s))
 
     def train_step(self, loss_fn) -> torch.Tensor:
-        """One full step: loss_fn() must run forward and return the scalar loss."""
-        self.zero_grad()
+        """One full step: loss_fn() must run forward and return the scalar loss.  The gradient buffer is cleared for the
+        NEXT step right after the optimizer kernels are enqueued (so the bookkeeping runs while the GPU is busy even in a
+        loop that synchronises on the loss every step): parameter .grad reads zero after this call — use zero_grad /
+        backward / allreduce_gradients / step directly to inspect gradients."""
+        if not self._grads_clean:
+            self.zero_grad()
+        self._grads_clean = False
         loss = loss_fn()
         loss.backward()
         self.allreduce_gradients()
         self.step()
+        self.zero_grad()
+        self._grads_clean = True
         return loss
