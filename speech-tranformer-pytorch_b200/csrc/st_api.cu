@@ -500,10 +500,7 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
 
 // ------------------------------------------------------------------ PositionwiseFeedForward
 namespace {
-// gate: 1-bit-per-element mask of h > 0 (GemmEpilogue::gate_bits layout), written by the fc1 epilogue and read by the
-// fc2 data-gradient epilogue instead of the 4-byte-per-element h (262 MB per layer at the headline shape); d_ff % 32 == 0
-struct FfnPlan { float *x_r, *h, *z, *mean, *rstd, *w1_r, *w2_r; uint32_t* gate; };
-bool ffn_uses_gate_bits(int d_ff) { return (d_ff & 31) == 0; }
+struct FfnPlan { float *x_r, *h, *z, *mean, *rstd, *w1_r, *w2_r; };
 int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
   Carver c(a.saved, a.saved_floats);
   p.x_r = a.x_is_tf32 ? const_cast<float*>(a.x) : c.take(a.rows * a.d_model);
@@ -513,7 +510,6 @@ int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
   p.rstd = c.take(a.rows);
   p.w1_r = c.take(static_cast<int64_t>(a.d_ff) * a.d_model);
   p.w2_r = c.take(static_cast<int64_t>(a.d_ff) * a.d_model);
-  p.gate = ffn_uses_gate_bits(a.d_ff) ? reinterpret_cast<uint32_t*>(c.take(gate_bits_words(a.rows, a.d_ff))) : nullptr;
   if (a.w1_tf32 && a.w2_tf32) { p.w1_r = const_cast<float*>(a.w1_tf32); p.w2_r = const_cast<float*>(a.w2_tf32); }
   if (!c.ok()) {
     set_error("st_ffn: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
@@ -526,7 +522,7 @@ constexpr uint64_t kSeedMix1 = 0x5DEECE66Dull, kSeedMix2 = 0xB5297A4D3F84D5B5ull
 
 int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32) {
   return (x_is_tf32 ? 0 : pad64(rows * d_model)) + pad64(rows * d_ff) + pad64(rows * d_model) + 2 * pad64(rows) +
-         2 * pad64(static_cast<int64_t>(d_ff) * d_model) + (ffn_uses_gate_bits(d_ff) ? pad64(gate_bits_words(rows, d_ff)) : 0);
+         2 * pad64(static_cast<int64_t>(d_ff) * d_model);
 }
 int64_t st_ffn_hidden_offset(int64_t rows, int d_model, int d_ff, int x_is_tf32) {
   (void)d_ff;
@@ -551,7 +547,6 @@ int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
   e1.bias = a.b1; e1.relu = 1; e1.round_tf32 = 1;
   const DropoutCfg d1 = make_dropout(a.dropout_p, a.seed ^ kSeedMix1);
   e1.drop_thresh = d1.thresh; e1.drop_scale = d1.scale; e1.drop_seed = d1.seed;
-  e1.gate_bits_out = p.gate;
   ST_TRY(gemm_tf32(s, GEMM_NT, p.x_r, d, p.w1_r, d, p.h, f, M, f, d, e1));
   // z = x + fc2(h)                                                       SubLayers.py:26-27
   GemmEpilogue e2;
@@ -582,7 +577,7 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
                     make_dropout(a.dropout_p, a.seed ^ kSeedMix2)));
   // dh = (dz W2) * [h > 0] * dropout1 scale
   GemmEpilogue e;
-  e.aux = p.h; e.ldaux = f; e.aux_mode = (p.gate && !get_option("ffn_gate_dense")) ? 3 : 2; e.gate_bits = p.gate; e.round_tf32 = 1;
+  e.aux = p.h; e.ldaux = f; e.aux_mode = 2; e.round_tf32 = 1;
   e.aux_scale = make_dropout(a.dropout_p, 0).scale;
   e.colsum = b.db1;   // db1 = column sums of dh, accumulated by the epilogue that produces dh
   ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.w2_r, f, dh, f, M, f, d, e));

@@ -865,13 +865,8 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
   p.trace = get_option("attn_trace");
   p.dbq = a.dbq; p.dbk = a.dbk; p.dbv = a.dbv;
   p.delta = a.delta; p.dq = a.dq; p.lddq = a.lddq; p.dk = a.dk_; p.lddk = a.lddk; p.dv = a.dv; p.lddv = a.lddv;
-  // delta = rowsum(dO * O): a separate HBM pass.  Option attn_fused_delta = 1 lets the pipelined dQ kernel (TMEM-resident
-  // tiles) form it instead and publish it for the dK/dV kernel — measured SLOWER: the dQ kernel runs 14 CTAs per SM back
-  // to back and every microsecond added to a CTA's start-up is paid 14 times (dQ 341 -> 398-418 us against the 35 us pass)
   const bool pipelined = DK <= 64 && !get_option("attn_bwd_simple");
-  const bool fused_delta = pipelined && !get_option("attn_dq_res_smem") && get_option("attn_fused_delta");
-  if (fused_delta) p.delta_out = a.delta;
-  else {
+  {   // delta = rowsum(dO * O): a separate HBM pass (forming it inside the dQ kernel measured slower)
     const int64_t rows = static_cast<int64_t>(f.B) * f.Lq;
     const int64_t blocks = (rows + 7) / 8;
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;

@@ -23,7 +23,6 @@ struct AttnDev {
   float* attn;
   // backward
   const float* delta;
-  float* delta_out;   // dQ kernel (pipelined, resident tiles in TMEM): compute delta = rowsum(dO * O) itself and store it here
   float* dq; int64_t lddq;
   float* dk; int64_t lddk;
   float* dv; int64_t lddv;

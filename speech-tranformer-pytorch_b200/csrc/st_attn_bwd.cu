@@ -149,24 +149,6 @@ __device__ __forceinline__ void resident_to_tmem(const float* x0, int64_t ld0, c
   }
 }
 
-// Partial sum of delta = rowsum(dO * O) over quarter `part` (DK / 4 columns) of head h for one row: the four compute
-// threads that share a row each take a quarter (the dO row was read a moment ago by resident_to_tmem: an L1 / L2 hit).
-template <int DK>
-__device__ __forceinline__ float delta_partial(const float* dctx, int64_t lddctx, const float* ctx, int64_t ldctx, int64_t row,
-                                               int h, int part) {
-  constexpr int W = DK / 4;
-  const float* a = dctx + row * lddctx + h * DK + part * W;
-  const float* o = ctx + row * ldctx + h * DK + part * W;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < W; i += 4) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(a + i));
-    const float4 y = __ldg(reinterpret_cast<const float4*>(o + i));
-    acc[0] = fmaf(x.x, y.x, acc[0]); acc[1] = fmaf(x.y, y.y, acc[1]); acc[2] = fmaf(x.z, y.z, acc[2]); acc[3] = fmaf(x.w, y.w, acc[3]);
-  }
-  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
-}
-
 // ================================================================================ dQ
 // RS = true: the resident Q / dO tiles live in SHARED memory (one TMA box each) and the recompute MMAs use the .ss form.
 // The tensor-memory read port (tcgen05.ld of S / dP by the compute warps + the A operands of .ts MMAs) is the busiest
@@ -195,7 +177,6 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) uint32_t s_ckey[STAGES][BT];
   __shared__ uint32_t s_mb[STAGES][BT / 32];
-  __shared__ float s_dpart[4][BQ];         // fused delta: per-row partial sums of dO * O, one per compute slice (DK / 4 columns)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -320,25 +301,12 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
     const int col0 = slice * 16;
     const int64_t grow = static_cast<int64_t>(b) * p.Lq + (row_ok ? row : 0);
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
-    float delta;
     if (!RS) {
-      // delta = rowsum(dO * O) is formed here (and published for the dK/dV kernel that follows, p.delta_out) instead of by a
-      // separate pass: AFTER the resident tiles are handed to the MMA warp, so the extra O read runs under S(0) / dP(0)
       resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO);
       tc_fence_before();
       mbar_arrive(&res_ready);
-      if (p.delta_out) {
-        const int rit = quarter * 32 + lane;
-        s_dpart[slice][rit] = row_ok ? delta_partial<DK>(dctx, lddctx, p.ctx, p.ldctx, grow, h, slice) : 0.f;
-        asm volatile("bar.sync 1, %0;" ::"n"(NCOMP) : "memory");   // the compute warps only
-        delta = (s_dpart[0][rit] + s_dpart[1][rit]) + (s_dpart[2][rit] + s_dpart[3][rit]);
-        if (slice == 0 && row_ok) p.delta_out[stat] = delta;
-      } else {
-        delta = row_ok ? p.delta[stat] : 0.f;
-      }
-    } else {
-      delta = row_ok ? p.delta[stat] : 0.f;
     }
+    const float delta = row_ok ? p.delta[stat] : 0.f;
     const float lse2 = row_ok ? p.lse2[stat] : INFINITY;
     const uint32_t drop_key = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(stat)) : 0u;
     const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
@@ -886,28 +854,6 @@ template <int DK>
 int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
   const AttnArgs& f = a.f;
   const int cols = f.H * DK;
-  // dQ first: with the resident tiles in TMEM it also produces delta (p.delta_out) for the dK/dV kernel behind it
-  {
-    CUtensorMap tkk, tkm, tvk;
-    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BT, 0, DK));
-    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BT, 1, DK));
-    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BT, 0, DK));
-    CUtensorMap tqr, tdr;
-    ST_TRY(make_act_tmap(&tqr, f.q, f.ldq, cols, f.Lq, f.B, 128, 0, DK));
-    ST_TRY(make_act_tmap(&tdr, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0, DK));
-    const bool rs = get_option("attn_dq_res_smem") != 0;
-    constexpr int SMEM_TS = 4 * 3 * BT * DK * 4 + 1024;
-    constexpr int SMEM_RS = 3 * 3 * BT * DK * 4 + 2 * 128 * DK * 4 + 1024;
-    const int SMEM = rs ? SMEM_RS : SMEM_TS;
-    auto kern = rs ? attn_bwd_dq_pipe<DK, true> : attn_bwd_dq_pipe<DK, false>;
-    static bool attr[2] = {false, false};
-    if (!attr[rs]) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr[rs] = true; }
-    dim3 grid((f.Lq + 127) / 128, f.H, f.B);
-    // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
-    ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, tqr, tdr, p));
-    ST_CHECK_LAUNCH();
-  }
   {
     CUtensorMap tqk, tqm, tdk, tdm;
     ST_TRY(make_act_tmap(&tqk, f.q, f.ldq, cols, f.Lq, f.B, BT, 0, DK));
@@ -947,6 +893,27 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, tkr, tvr, p));
     ST_CHECK_LAUNCH();
     }
+  }
+  {
+    CUtensorMap tkk, tkm, tvk;
+    ST_TRY(make_act_tmap(&tkk, f.k, f.ldk, cols, f.Lk, f.B, BT, 0, DK));
+    ST_TRY(make_act_tmap(&tkm, f.k, f.ldk, cols, f.Lk, f.B, BT, 1, DK));
+    ST_TRY(make_act_tmap(&tvk, f.v, f.ldv, cols, f.Lk, f.B, BT, 0, DK));
+    CUtensorMap tqr, tdr;
+    ST_TRY(make_act_tmap(&tqr, f.q, f.ldq, cols, f.Lq, f.B, 128, 0, DK));
+    ST_TRY(make_act_tmap(&tdr, a.dctx, a.lddctx, cols, f.Lq, f.B, 128, 0, DK));
+    const bool rs = get_option("attn_dq_res_smem") != 0;
+    constexpr int SMEM_TS = 4 * 3 * BT * DK * 4 + 1024;
+    constexpr int SMEM_RS = 3 * 3 * BT * DK * 4 + 2 * 128 * DK * 4 + 1024;
+    const int SMEM = rs ? SMEM_RS : SMEM_TS;
+    auto kern = rs ? attn_bwd_dq_pipe<DK, true> : attn_bwd_dq_pipe<DK, false>;
+    static bool attr[2] = {false, false};
+    if (!attr[rs]) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr[rs] = true; }
+    dim3 grid((f.Lq + 127) / 128, f.H, f.B);
+    // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
+    ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
+    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, tqr, tdr, p));
+    ST_CHECK_LAUNCH();
   }
   return ST_OK;
 }

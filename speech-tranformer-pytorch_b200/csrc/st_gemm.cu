@@ -75,8 +75,7 @@ enum EpiFlavour : int {
   EPI_AUX_MASK_ROUND = 4,   // C = tf32(aux > 0 ? acc * aux_scale : 0)              dgrad through relu + dropout
   EPI_ATOMIC = 5,           // C += acc (red.global.add)                            split-K wgrad
   EPI_GENERIC = 6,
-  EPI_RELU_DROP = 7,        // C = dropout(relu(acc + bias)), not rounded               front-end linear (feeds a LayerNorm)
-  EPI_BITS_MASK_ROUND = 8   // C = tf32(gate bit ? acc * aux_scale : 0)             dgrad through relu + dropout, 1-bit gate
+  EPI_RELU_DROP = 7         // C = dropout(relu(acc + bias)), not rounded               front-end linear (feeds a LayerNorm)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
@@ -115,9 +114,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
   constexpr bool RELU = (F == EPI_RELU_DROP_ROUND || F == EPI_RELU_DROP);
   constexpr bool DROP = (F == EPI_RELU_DROP_ROUND || F == EPI_RELU_DROP);
   constexpr int AUX = (F == EPI_AUX_ADD) ? 1 : (F == EPI_AUX_MASK_ROUND ? 2 : 0);
-  constexpr bool BITS_IN = (F == EPI_BITS_MASK_ROUND);
-  constexpr bool BITS_OUT = (F == EPI_RELU_DROP_ROUND);   // optional (ep.gate_bits_out)
-  constexpr bool ROUND = (F == EPI_ROUND || F == EPI_RELU_DROP_ROUND || F == EPI_AUX_MASK_ROUND || F == EPI_BITS_MASK_ROUND);
+  constexpr bool ROUND = (F == EPI_ROUND || F == EPI_RELU_DROP_ROUND || F == EPI_AUX_MASK_ROUND);
   constexpr bool ATOMIC = (F == EPI_ATOMIC);
   const GemmEpilogue& ep = p.ep;
   const int lcol = (lane & 7) * 4;   // this lane's 4 columns inside a 32-column chunk
@@ -137,24 +134,11 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
   }
   const int n_chunks = min(BN / 32, (p.N - n_blk * BN + 31) >> 5);
   const bool do_colsum = ep.colsum != nullptr;
-  // gate bit-mask (see GemmEpilogue): this warp's rows are the 8 groups of 4 starting at group grp0; N % 32 == 0 here
-  const int grp0 = (m_blk * BM + quarter * 32) >> 2;
-  const int n32 = p.N >> 5;
-  const bool bits_out = BITS_OUT && ep.gate_bits_out != nullptr;   // warp-uniform
-  const int bit_pos = lrow * 8 + (lane & 7);
 #pragma unroll 1
   for (int c = half; c < n_chunks; c += EPI_WARPS / 4) {
     const int col = col0 + c * 32;
     const bool col_ok = col < p.N;
     float cs[4] = {0.f, 0.f, 0.f, 0.f};
-    const int chunk = (n_blk * BN >> 5) + c;
-    uint4 gw[8];
-    if (BITS_IN) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        gw[i] = ((grp0 + i) * 4 < p.M) ? __ldg(reinterpret_cast<const uint4*>(ep.gate_bits) + (static_cast<int64_t>(grp0 + i) * n32 + chunk))
-                                       : make_uint4(0u, 0u, 0u, 0u);
-    }
     // residual / ReLU-mask operand and bias: issue the loads first, their latency hides behind the TMEM read and
     // the smem transpose
     float4 aux4[8];
@@ -178,7 +162,6 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      bool pos[4] = {false, false, false, false};
       if (col_ok && i * 4 < rows_left) {
         const float4 s4 = lds128(stg_s + epi_swz(i * 4 + lrow, lane & 7) * 4);
         float v[4] = {s4.x + b4.x, s4.y + b4.y, s4.z + b4.z, s4.w + b4.w};
@@ -201,12 +184,6 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
           v[2] = aux4[i].z > 0.f ? v[2] * ep.aux_scale : 0.f;
           v[3] = aux4[i].w > 0.f ? v[3] * ep.aux_scale : 0.f;
         }
-        if (BITS_IN) {
-          v[0] = ((gw[i].x >> bit_pos) & 1u) ? v[0] * ep.aux_scale : 0.f;
-          v[1] = ((gw[i].y >> bit_pos) & 1u) ? v[1] * ep.aux_scale : 0.f;
-          v[2] = ((gw[i].z >> bit_pos) & 1u) ? v[2] * ep.aux_scale : 0.f;
-          v[3] = ((gw[i].w >> bit_pos) & 1u) ? v[3] * ep.aux_scale : 0.f;
-        }
         cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
         if (ROUND) {
 #pragma unroll
@@ -218,13 +195,6 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
         } else {
           *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
         }
-        if (BITS_OUT) { pos[0] = v[0] > 0.f; pos[1] = v[1] > 0.f; pos[2] = v[2] > 0.f; pos[3] = v[3] > 0.f; }
-      }
-      if (bits_out) {   // converged here: one ballot per column residue, lane 0 stores the four words of this (row group, chunk)
-        const uint32_t w0 = __ballot_sync(0xffffffffu, pos[0]), w1 = __ballot_sync(0xffffffffu, pos[1]);
-        const uint32_t w2 = __ballot_sync(0xffffffffu, pos[2]), w3 = __ballot_sync(0xffffffffu, pos[3]);
-        if (lane == 0 && (grp0 + i) * 4 < p.M)
-          *(reinterpret_cast<uint4*>(ep.gate_bits_out) + (static_cast<int64_t>(grp0 + i) * n32 + chunk)) = make_uint4(w0, w1, w2, w3);
       }
     }
     if (do_colsum) {   // warp-uniform: the 4 lanes that share these columns (lane >> 3 = 0..3) combine, then one vector reduction
@@ -327,7 +297,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* stg, u
     case EPI_RELU_DROP: epilogue_fast<BN, EPI_RELU_DROP>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     case EPI_AUX_MASK_ROUND:  epilogue_fast<BN, EPI_AUX_MASK_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     case EPI_ATOMIC:          epilogue_fast<BN, EPI_ATOMIC>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
-    case EPI_BITS_MASK_ROUND: epilogue_fast<BN, EPI_BITS_MASK_ROUND>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     default:                  epilogue_generic<BN>(p, stg, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
   }
 }
@@ -672,27 +641,6 @@ gemm_tf32_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
 }
 
-// Gate bit-mask of a dense matrix (bit = x > 0) in the GemmEpilogue layout: the fallback producer when the GEMM that
-// writes x does not run the fast fc1 epilogue (generic epilogue forced / unaligned operands).  One warp per
-// (4-row group, 32-column chunk): lane = (row % 4) * 8 + (col % 32) / 4 holds one float4.
-__global__ void __launch_bounds__(256)
-gate_bits_kernel(const float* __restrict__ x, int64_t ld, int rows, int n32, uint32_t* __restrict__ bits) {
-  pdl_wait();
-  pdl_trigger();
-  const int lane = threadIdx.x & 31;
-  const int64_t units = static_cast<int64_t>((rows + 3) >> 2) * n32;
-  for (int64_t u = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); u < units; u += static_cast<int64_t>(gridDim.x) * 8) {
-    const int64_t grp = u / n32;
-    const int chunk = static_cast<int>(u - grp * n32);
-    const int64_t row = grp * 4 + (lane >> 3);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < rows) v = *reinterpret_cast<const float4*>(x + row * ld + chunk * 32 + (lane & 7) * 4);
-    const uint32_t w0 = __ballot_sync(0xffffffffu, v.x > 0.f), w1 = __ballot_sync(0xffffffffu, v.y > 0.f);
-    const uint32_t w2 = __ballot_sync(0xffffffffu, v.z > 0.f), w3 = __ballot_sync(0xffffffffu, v.w > 0.f);
-    if (lane == 0) *(reinterpret_cast<uint4*>(bits) + u) = make_uint4(w0, w1, w2, w3);
-  }
-}
-
 // ================================================================================ host side
 // profile tag bit fields: bn/64 [0,4)  variant [4,8)  flavour [8,12)  mode [12,16)  K [16,34)  N [34,48)  M [48,63)... M, K in units of 8
 long long gemm_tag(const GemmParams& p, bool a_mn, bool b_mn, int bn, int variant) {
@@ -802,7 +750,6 @@ int pick_flavour(const GemmEpilogue& ep, const float* C, int64_t ldc, int N) {
   if (drop) return EPI_GENERIC;
   if (ep.aux_mode == 1) return ep.round_tf32 ? EPI_GENERIC : EPI_AUX_ADD;
   if (ep.aux_mode == 2) return ep.round_tf32 ? EPI_AUX_MASK_ROUND : EPI_GENERIC;
-  if (ep.aux_mode == 3) return (ep.round_tf32 && (N & 31) == 0 && ep.gate_bits && al16(ep.gate_bits)) ? EPI_BITS_MASK_ROUND : EPI_GENERIC;
   return ep.round_tf32 ? EPI_ROUND : EPI_PLAIN;
 }
 
@@ -828,20 +775,6 @@ int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, c
   p.n_tiles = (N + BN - 1) / BN;
   p.ep = ep;
   p.flavour = pick_flavour(ep, C, ldc, N);
-  if (ep.aux_mode == 3 && p.flavour != EPI_BITS_MASK_ROUND) {   // no fast 1-bit gate here: fall back to the dense operand
-    ST_REQUIRE(ep.aux != nullptr, "gemm_tf32: aux_mode 3 needs the dense aux operand as a fallback");
-    p.ep.aux_mode = 2;
-    p.flavour = pick_flavour(p.ep, C, ldc, N);
-  }
-  uint32_t* deferred_bits = nullptr;
-  if (ep.gate_bits_out) {
-    ST_REQUIRE((N & 31) == 0 && (reinterpret_cast<uintptr_t>(ep.gate_bits_out) & 15) == 0 && !ep.atomic,
-               "gemm_tf32: gate bits need N %% 32 == 0 (N=%d), a 16-byte aligned buffer and a non-atomic epilogue", N);
-    if (p.flavour != EPI_RELU_DROP_ROUND) {   // only the fast fc1 epilogue writes them itself: separate pass over C below
-      deferred_bits = ep.gate_bits_out;
-      p.ep.gate_bits_out = nullptr;
-    }
-  }
   float* deferred_colsum = nullptr;
   if (ep.colsum && (p.flavour == EPI_GENERIC || p.flavour == EPI_ATOMIC || (reinterpret_cast<uintptr_t>(ep.colsum) & 15))) {
     deferred_colsum = ep.colsum;   // the generic epilogue has no fused column sums: separate pass below
@@ -891,14 +824,6 @@ int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, c
     }
   }
   if (status == ST_OK && deferred_colsum) status = colsum_add(stream, C, ldc, M, N, deferred_colsum);
-  if (status == ST_OK && deferred_bits) {
-    ST_REQUIRE((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_tf32: gate bits need a 16-byte aligned C");
-    const int64_t units = static_cast<int64_t>((M + 3) >> 2) * (N >> 5);
-    const int64_t blocks = (units + 7) / 8, cap = static_cast<int64_t>(num_sms()) * 8;
-    ST_CHECK_CUDA(launch_pdl(gate_bits_kernel, dim3(static_cast<unsigned>(blocks < cap ? blocks : cap)), dim3(256), 0, stream, C,
-                             ldc, M, N >> 5, deferred_bits));
-    ST_CHECK_LAUNCH();
-  }
   return status;
 }
 

@@ -17,8 +17,6 @@ struct GemmEpilogue {
   const float* aux = nullptr;   // [M, ldaux]
   int64_t ldaux = 0;
   int aux_mode = 0;    // 0: none   1: out += aux (residual)   2: out = aux > 0 ? out * aux_scale : 0 (ReLU backward)
-                       // 3: as 2, but the predicate "aux > 0" is read from `gate_bits` (1 bit per element instead of 4 bytes;
-                       //    needs N % 32 == 0; `aux` must still be given — the generic epilogue falls back to it)
   float aux_scale = 1.f;
   int relu = 0;        // out = max(out, 0) (after bias)
   int round_tf32 = 0;  // round the stored value to TF32 (round-to-nearest) — the value feeds another MMA
@@ -30,14 +28,7 @@ struct GemmEpilogue {
   // optional [N]: column sums of the stored values are ACCUMULATED here (caller zeroes) — the bias gradient of the
   // layer whose input gradient this GEMM produces, for free instead of a separate pass over the output
   float* colsum = nullptr;
-  // Gate bit-mask of the stored values (bit = value > 0), N % 32 == 0.  Layout, independent of the tile shape: rows in
-  // groups of 4, columns in chunks of 32; word ((row / 4) * (N / 32) + col / 32) * 4 + (col % 4), bit (row % 4) * 8 +
-  // (col % 32) / 4 — i.e. one warp ballot per column residue over the 4 x 8 lane arrangement of the epilogue.
-  // gate_bits_out: written for the output of this GEMM (fc1 forward).  gate_bits: read with aux_mode 3 (fc2 data gradient).
-  uint32_t* gate_bits_out = nullptr;
-  const uint32_t* gate_bits = nullptr;
 };
-inline int64_t gate_bits_words(int64_t rows, int n) { return ((rows + 3) / 4) * (n / 32) * 4; }
 
 // k_splits > 1 requires ep.atomic and a zero-initialised C.
 int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,

@@ -45,8 +45,6 @@ Option g_options[] = {
     {"attn_dkv_no_small", 0},  // 1 = never use the single-query-tile dK/dV kernel (A/B testing)
     {"attn_fuse_bias", 0},     // 1 = dq/dk/dv bias column sums from the attention-backward epilogues (measured slower)
     {"attn_dq_res_smem", 0},   // 1 = dQ kernel keeps its resident Q/dO tiles in shared memory (.ss MMAs) instead of TMEM
-    {"attn_fused_delta", 0},   // 1 = delta = rowsum(dO * O) formed inside the pipelined dQ kernel instead of a separate pass (measured slower)
-    {"ffn_gate_dense", 0},     // 1 = the fc2 data gradient reads its ReLU/dropout gate from the dense hidden activation (A/B testing)
     {"pdl", -1},
     {"pdl_graphs", 1},         // keep programmatic dependent launch while the stream is being captured into a CUDA graph (decode:
                                // 73.8 -> 71.0 ms per beam search); 0 / ST_PDL_GRAPHS=0 = plain launches under capture               // programmatic dependent launch: 1 = on, 0 = off, -1 = unset (on unless ST_PDL=0 in the environment)

@@ -289,16 +289,7 @@ colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols, f
   const int c = blockIdx.x * 128 + lane * 4;
   float4 acc = make_float4(0, 0, 0, 0);
   if (c < cols) {
-    // four rows in flight per lane: one 16-byte load per thread leaves the pass latency-bound (4.7 of 6.5 TB/s)
-    const int64_t step = static_cast<int64_t>(gridDim.y) * 8;
-    int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + warp;
-    for (; r + 3 * step < rows; r += 4 * step) {
-      const float4 v0 = ld4(x + r * ld + c), v1 = ld4(x + (r + step) * ld + c);
-      const float4 v2 = ld4(x + (r + 2 * step) * ld + c), v3 = ld4(x + (r + 3 * step) * ld + c);
-      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
-      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
-    }
-    for (; r < rows; r += step) {
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + warp; r < rows; r += static_cast<int64_t>(gridDim.y) * 8) {
       const float4 v = ld4(x + r * ld + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }

@@ -449,76 +449,3 @@ def test_dropout_train_mode_runs_and_is_unbiased(stb):
     assert torch.isfinite(y).all() and torch.isfinite(x.grad).all()
     frac_zero = (y == 0).float().mean().item()
     assert abs(frac_zero - 0.1) < 0.01, frac_zero   # dropout2 after the FFN LayerNorm (SubLayers.py:27)
-
-
-@pytest.mark.gpu
-def test_ffn_gate_bitmask_matches_dense_gate(stb):
-    """The fc2 data gradient reads its ReLU/dropout gate from a 1-bit mask written by the fc1 epilogue (or, when the
-    generic epilogue runs, by the fallback pass over h).  All three routes give the same gradients bit for bit
-    (the gate only selects; SubLayers.py:25)."""
-    import torch
-    lib = stb._lib.load()
-    dev = "cuda:0"
-    torch.manual_seed(11)
-    rows, d, f = 2 * 173, 64, 160           # rows not a multiple of 4 * 32, d_ff a multiple of 32 but not of 64
-    x = torch.randn(2, 173, d, device=dev)
-    P = [torch.randn(f, d, device=dev) * 0.2, torch.randn(f, device=dev) * 0.1, torch.randn(d, f, device=dev) * 0.2,
-         torch.randn(d, device=dev) * 0.1, torch.rand(d, device=dev) + 0.5, torch.randn(d, device=dev) * 0.1]
-    dy = torch.randn(2, 173, d, device=dev)
-
-    def run(fwd_opts, bwd_opts=None):
-        bwd_opts = fwd_opts if bwd_opts is None else bwd_opts
-
-        def set_all(opts, on):
-            for k, v in opts.items():
-                stb._lib.check(lib.st_set_option(k.encode(), v if on else 0))
-        try:
-            set_all(fwd_opts, True)
-            xs = x.clone().requires_grad_()
-            ps = [p.clone().requires_grad_() for p in P]
-            y = stb.functional.positionwise_ffn(xs, *ps, dropout_p=0.3, seed=77)
-            set_all(fwd_opts, False)
-            set_all(bwd_opts, True)
-            y.backward(dy)
-            return [y.detach(), xs.grad] + [p.grad for p in ps]
-        finally:
-            set_all(fwd_opts, False)
-            set_all(bwd_opts, False)
-
-    ref = run({"ffn_gate_dense": 1})
-    bits = run({})
-    # forward on the generic epilogue (bits from the fallback pass over h), backward on the fast 1-bit epilogue
-    fallback = run({"gemm_generic_epilogue": 1}, {})
-    for a, b in zip(ref[:2], bits[:2]):
-        assert torch.equal(a, b)
-    for a, b in zip(ref, fallback):                      # generic vs fast epilogue: same arithmetic up to reduction order
-        assert (a - b).abs().max() <= 1e-5 * max(1.0, float(a.abs().max()))
-    for a, b in zip(ref[2:], bits[2:]):                  # parameter gradients use atomics: equal up to summation order
-        assert (a - b).abs().max() <= 1e-5 * max(1.0, float(a.abs().max()))
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("B,H,Lq,Lk,dk", [(2, 4, 200, 200, 64), (2, 2, 50, 333, 32)])
-def test_attention_backward_fused_delta_option(stb, B, H, Lq, Lk, dk):
-    """Option attn_fused_delta (delta = rowsum(dO * O) formed inside the dQ kernel instead of the separate pass; off by
-    default because it measured slower) gives the same gradients as the default path."""
-    F = stb.functional
-    lib = stb._lib.load()
-    d = H * dk
-    gen = torch.Generator().manual_seed(5)
-    q, k, v, g = (torch.randn(B, L, d, generator=gen).to(DEV) for L in (Lq, Lk, Lk, Lq))
-    kl = torch.tensor([Lk, Lk // 2][:B])
-    mask = O.padding_info_mask(torch.full((B,), Lq), kl).bool().to(DEV)
-
-    def grads(fused):
-        stb._lib.check(lib.st_set_option(b"attn_fused_delta", fused))
-        try:
-            cq, ck, cv = (x.clone().requires_grad_() for x in (q, k, v))
-            out, _ = F.attention_core(cq, ck, cv, mask, n_head=H)
-            out.backward(g)
-            return cq.grad, ck.grad, cv.grad
-        finally:
-            lib.st_set_option(b"attn_fused_delta", 0)
-
-    for a, b in zip(grads(0), grads(1)):     # gradients are stored TF32-rounded: a different summation order of delta can
-        assert relerr(a, b) < 2e-4           # move a value across one rounding boundary (2^-11 of that value)
