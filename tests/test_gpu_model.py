@@ -261,3 +261,23 @@ def test_padding_invariance_long_ragged_batch(stb):
             alone, _ = enc(x[b:b + 1, :l].to(DEV), lens[b:b + 1].to(DEV))
             assert relerr(full[b, :l], alone[0]) < 1e-4, (b, l)        # only the tile decomposition / summation order differs
             assert torch.equal(full[b, :l], full_noisy[b, :l]), (b, l)  # masked keys contribute exactly nothing
+
+
+def test_device_prefetcher_double_buffers_in_order(stb):
+    """data.DevicePrefetcher: batches submitted from pinned host memory on the side stream arrive unchanged and in order,
+    one in flight at a time (the input side of bench.py's end-to-end loop)."""
+    from speech_tranformer_pytorch_b200 import data as sdata
+    pf = sdata.DevicePrefetcher(DEV)
+    host = [[torch.full((257, 33), float(i)).pin_memory(), torch.arange(i, i + 5).pin_memory()] for i in range(4)]
+    with pytest.raises(RuntimeError):
+        pf.get()
+    pf.submit(host[0])
+    with pytest.raises(RuntimeError):
+        pf.submit(host[1])
+    for i in range(4):
+        x, idx = pf.get()
+        if i + 1 < 4:
+            pf.submit(host[i + 1])
+        y = (x * 2).sum()                      # consume on the compute stream while the next copy runs
+        assert x.device.type == "cuda" and torch.equal(x.cpu(), host[i][0]) and torch.equal(idx.cpu(), host[i][1])
+        assert float(y) == 2.0 * i * 257 * 33
