@@ -227,6 +227,17 @@ int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n
 int st_decode_self_attn(const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk, float* ctx,
                         int round_tf32, cudaStream_t stream);
 
+/* One position of beam-search bookkeeping on the device (Beam.advance, Beam.py:43-74, as driven by Decode.py:120-160) for B
+ * utterances x `beam` live hypotheses.  logits: (B*beam, >= V) scores of the next symbol, row stride ld_logits.  Per
+ * utterance: cand[k][v] = scores[k] + log_softmax(logits[k])[v] (first != 0: only hypothesis 0 is expanded — all beams are
+ * identical at the first position, Beam.py:49-52); the `beam` best candidates, best first (ties: lower k*V + v first), give
+ * scores (B, beam) in/out, prev_k (B, beam) integer back-pointers k (Beam.py:66), next_y (B, beam) symbols v, parent
+ * (B*beam) = b*beam + prev_k (cache re-parenting for st_decode_self_attn's caches), tokens (B*beam) = next_y.  done (B)
+ * bytes in/out: a finished utterance is frozen (scores kept, prev_k = identity, next_y = pad); an utterance becomes
+ * finished when its best hypothesis emits eos (Beam.py:70-72).  beam <= 32.                                      */
+int st_beam_step(const float* logits, int64_t ld_logits, int B, int beam, int V, int first, int eos, int pad, float* scores,
+                 uint8_t* done, int64_t* prev_k, int64_t* next_y, int64_t* parent, int64_t* tokens, cudaStream_t stream);
+
 /* Encoder input front-end (Models.py:28-33,42-44):
  *   out = LayerNorm(Dropout(ReLU(x W^T + b))) * gamma + beta + pe[frame index]
  * x: (rows, in_dim) with rows = B*T and frame index = row mod T; in_dim a multiple of 4 (80 for fbank).

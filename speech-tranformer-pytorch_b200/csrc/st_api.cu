@@ -604,6 +604,11 @@ int st_decode_self_attn(const float* qkv, float* k_cache, float* v_cache, int t,
   return decode_self_attn(stream, qkv, k_cache, v_cache, t, n, H, dk, ctx, round_tf32);
 }
 
+int st_beam_step(const float* logits, int64_t ld_logits, int B, int beam, int V, int first, int eos, int pad, float* scores,
+                 uint8_t* done, int64_t* prev_k, int64_t* next_y, int64_t* parent, int64_t* tokens, cudaStream_t stream) {
+  return beam_step(stream, logits, ld_logits, B, beam, V, first, eos, pad, scores, done, prev_k, next_y, parent, tokens);
+}
+
 // ------------------------------------------------------------------ encoder input front-end (Models.py:28-33,42-44)
 namespace {
 struct FrontPlan { float *x_r, *w_r, *h, *mean, *rstd; };

@@ -250,27 +250,22 @@ def beam_search(net, inputs: torch.Tensor, input_lengths: torch.Tensor, beam: in
     scores = torch.zeros(B, beam, device=dev)
     tokens = torch.full((B * beam,), BOS, dtype=torch.int64, device=dev)
     done = torch.zeros(B, dtype=torch.bool, device=dev)
-    base = (torch.arange(B, device=dev) * beam).unsqueeze(1)
-    prev_ks, next_ys = [], []
-    parent = None
+    # one library kernel per position does the bookkeeping (st_beam_step): log-softmax, score update, top-`beam` of
+    # beam x V with integer back-pointers (Beam.py:66), freezing of finished utterances, re-parenting / next-token vectors
+    prev_all = torch.empty(max_len, B, beam, dtype=torch.int64, device=dev)
+    ys_all = torch.empty(max_len, B, beam, dtype=torch.int64, device=dev)
+    parent_buf = torch.empty(B * beam, dtype=torch.int64, device=dev)
+    parent, steps = None, 0
+    lib = dec.lib
     for t in range(max_len):
-        logp = torch.log_softmax(dec.step(tokens, parent), dim=-1).view(B, beam, V)
-        cand = logp + scores.unsqueeze(2) if t > 0 else logp[:, :1]      # first step: all beams are identical (Beam.py:49-52)
-        best, idx = cand.reshape(B, -1).topk(beam, dim=1)
-        prev_k = torch.div(idx, V, rounding_mode="floor")                # integer back-pointer (Beam.py:66)
-        y = idx - prev_k * V
-        # finished utterances are frozen: their beams keep their scores and repeat themselves
-        keep = done.unsqueeze(1)
-        prev_k = torch.where(keep, torch.arange(beam, device=dev).expand(B, -1), prev_k)
-        y = torch.where(keep, torch.full_like(y, PAD), y)
-        scores = torch.where(keep, scores, best)
-        prev_ks.append(prev_k)
-        next_ys.append(y)
-        done = done | (y[:, 0] == eos)                                   # Beam.py:70-72
+        logits = dec.step(tokens, parent)                                # (B*beam, V) view of row-padded storage
+        check(lib.st_beam_step(_p(logits), logits.stride(0), B, beam, V, int(t == 0), eos, PAD, _p(scores), _p(done),
+                               _p(prev_all[t]), _p(ys_all[t]), _p(parent_buf), _p(tokens), F._stream()))
+        steps = t + 1
         if (t % 4 == 3 or t + 1 == max_len) and bool(done.all()):   # host poll (a sync) only every 4th position:
             break                                                    # finished utterances are frozen, extra steps change nothing
-        parent = (base + prev_k).reshape(-1)
-        tokens = y.reshape(-1)
+        parent = parent_buf
+    prev_ks, next_ys = list(prev_all[:steps]), list(ys_all[:steps])
     # back-track (Beam.get_hypothesis, Beam.py:100-118) for the n_best final beams, best score first
     order = scores.sort(dim=1, descending=True)
     prev = torch.stack(prev_ks).cpu()      # (steps, B, beam)

@@ -122,3 +122,48 @@ def test_decode_self_attention_kernel(stb, n, H, dk, t):
     s = torch.einsum("nhd,tnhd->nht", q, K) / dk ** 0.5
     ref = torch.einsum("nht,tnhd->nhd", torch.softmax(s, -1), V).reshape(n, d)
     assert relerr(ctx, ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,beam,V,first", [(5, 10, 4337, 0), (3, 4, 31, 0), (4, 10, 4337, 1), (2, 1, 57, 0), (2, 32, 101, 0)])
+def test_beam_step_kernel_matches_torch_bookkeeping(stb, B, beam, V, first):
+    """st_beam_step against the tensor formulation of Beam.advance (Beam.py:43-74): scores within 1e-5, back-pointers /
+    symbols / done flags / re-parenting vectors exactly, including frozen (finished) utterances and the first position."""
+    import ctypes as C
+    lib = stb._lib.load()
+    g = torch.Generator().manual_seed(B * 100 + beam)
+    ld = (V + 3) // 4 * 4
+    store = torch.randn(B * beam, ld, generator=g).mul_(3).to(DEV)
+    logits = store[:, :V]
+    scores0 = (torch.randn(B, beam, generator=g).abs().neg() if not first else torch.zeros(B, beam)).to(DEV)
+    done0 = torch.zeros(B, dtype=torch.bool)
+    done0[B // 2] = True
+    done0 = done0.to(DEV)
+    EOS_, PAD_ = 3, 0
+    if not first:   # make utterance 0's best continuation EOS
+        logits[0 * beam + int(scores0[0].argmax()), EOS_] = 50.0
+    # reference (decode.beam_search before the kernel existed)
+    logp = torch.log_softmax(logits.double(), dim=-1).view(B, beam, V)
+    cand = logp + scores0.double().unsqueeze(2) if not first else logp[:, :1]
+    best, idx = cand.reshape(B, -1).topk(beam, dim=1)
+    pk = torch.div(idx, V, rounding_mode="floor")
+    y = idx - pk * V
+    keep = done0.unsqueeze(1)
+    pk = torch.where(keep, torch.arange(beam, device=DEV).expand(B, -1), pk)
+    y = torch.where(keep, torch.full_like(y, PAD_), y)
+    want_scores = torch.where(keep, scores0.double(), best)
+    want_done = done0 | (y[:, 0] == EOS_)
+    # kernel
+    scores, done = scores0.clone(), done0.clone()
+    prev_k = torch.empty(B, beam, dtype=torch.int64, device=DEV)
+    next_y = torch.empty_like(prev_k)
+    parent = torch.empty(B * beam, dtype=torch.int64, device=DEV)
+    tokens = torch.empty_like(parent)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    stb._lib.check(lib.st_beam_step(p(logits), ld, B, beam, V, first, EOS_, PAD_, p(scores), p(done), p(prev_k), p(next_y),
+                                    p(parent), p(tokens), None))
+    torch.cuda.synchronize()
+    assert torch.equal(prev_k, pk) and torch.equal(next_y, y)
+    assert torch.equal(done, want_done) and (first or bool(done[0]))
+    assert (scores.double() - want_scores).abs().max() < 1e-5
+    base = (torch.arange(B, device=DEV) * beam).unsqueeze(1)
+    assert torch.equal(parent, (base + pk).reshape(-1)) and torch.equal(tokens, y.reshape(-1))
