@@ -223,9 +223,12 @@ int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n
 /* Incremental-decode self-attention (Decode.py:48-179 decodes the full prefix every step; this is the K/V-reuse form):
  * qkv (n, 3*H*dk) = [q | k | v] projections of the ONE new position of each of the n hypotheses.  Appends k, v as
  * row t of the time-major caches (L_max, n, H*dk) and writes ctx (n, H*dk) = softmax(q K[0..t]^T / sqrt(dk)) V[0..t]
- * per head (Attention.py:78-90 with Lq = 1; no mask: every cached position is in the past).                      */
+ * per head (Attention.py:78-90 with Lq = 1; no mask: every cached position is in the past).
+ * slot_of: NULL, or a time-major (L_max, n) int32 table: position j of hypothesis i's history lives in cache slot
+ * slot_of[j*n + i].  The call records slot_of[t*n + i] = i for the rows it appends; beam search re-parents hypotheses by
+ * permuting the table (slot_of[:t] <- slot_of[:t][:, parent]) instead of the caches themselves.                    */
 int st_decode_self_attn(const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk, float* ctx,
-                        int round_tf32, cudaStream_t stream);
+                        int round_tf32, int32_t* slot_of, cudaStream_t stream);
 
 /* One position of beam-search bookkeeping on the device (Beam.advance, Beam.py:43-74, as driven by Decode.py:120-160) for B
  * utterances x `beam` live hypotheses.  logits: (B*beam, >= V) scores of the next symbol, row stride ld_logits.  Per

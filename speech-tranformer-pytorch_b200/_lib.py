@@ -143,7 +143,7 @@ SIGNATURES = {
     "st_ffn_bwd": (C.c_int, [C.POINTER(FfnBwdArgs), _S]),
     "st_embed_fwd": (C.c_int, [_P, _P, _P, i64, _P, i64, C.c_int, C.c_int, C.c_int, _S]),
     "st_embed_bwd": (C.c_int, [_P, _P, _P, i64, C.c_int, C.c_int, i64, C.c_int, _S]),
-    "st_decode_self_attn": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _S]),
+    "st_decode_self_attn": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _S]),
     "st_beam_step": (C.c_int, [_P, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _S]),
     "st_frontend_saved_floats": (i64, [i64, C.c_int, C.c_int]),
     "st_frontend_ws_floats": (i64, [i64, C.c_int, C.c_int]),

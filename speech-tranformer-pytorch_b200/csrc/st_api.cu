@@ -600,8 +600,8 @@ int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n
 }
 
 int st_decode_self_attn(const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk, float* ctx,
-                        int round_tf32, cudaStream_t stream) {
-  return decode_self_attn(stream, qkv, k_cache, v_cache, t, n, H, dk, ctx, round_tf32);
+                        int round_tf32, int32_t* slot_of, cudaStream_t stream) {
+  return decode_self_attn(stream, qkv, k_cache, v_cache, t, n, H, dk, ctx, round_tf32, slot_of);
 }
 
 int st_beam_step(const float* logits, int64_t ld_logits, int B, int beam, int V, int first, int eos, int pad, float* scores,

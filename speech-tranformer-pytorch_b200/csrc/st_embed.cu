@@ -87,10 +87,16 @@ int embed_bwd(cudaStream_t stream, const int64_t* idx, const float* dout, float*
 namespace st {
 namespace {
 
+// slot_of (optional, time-major (L_max, n) int32): the cache slot that holds position j of hypothesis `hyp`'s history.
+// Beam search re-parents hypotheses every step; with the table only its 4-byte entries are permuted (by the caller:
+// slot_of[:t] <- slot_of[:t][:, parent]) instead of the 12 K/V caches (≈ 0.4 GB per position at width 10, 50 positions).
+// The kernel records slot_of[t][hyp] = hyp for the row it appends.  NULL = every hypothesis owns slot `hyp` throughout.
 template <int DK>
 __global__ void __launch_bounds__(256)
 decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ k_cache, float* __restrict__ v_cache, int t, int n,
-                        int H, float scale_log2, float* __restrict__ ctx, int round_out) {
+                        int H, float scale_log2, float* __restrict__ ctx, int round_out, int* __restrict__ slot_of) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int E = DK / 32;                       // elements per lane
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -98,7 +104,8 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ k_cac
   const int hyp = w / H, h = w - hyp * H;
   const int d = H * DK;
   const int64_t row_stride = static_cast<int64_t>(n) * d;          // cache row (one position, all hypotheses)
-  const int64_t off = static_cast<int64_t>(hyp) * d + h * DK + lane * E;
+  const int64_t col = static_cast<int64_t>(h) * DK + lane * E;
+  const int64_t off = static_cast<int64_t>(hyp) * d + col;
   float q[E], kn[E], vn[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -108,15 +115,20 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ k_cac
     k_cache[t * row_stride + off + e] = kn[e];
     v_cache[t * row_stride + off + e] = vn[e];
   }
+  if (slot_of != nullptr && h == 0 && lane == 0) slot_of[static_cast<int64_t>(t) * n + hyp] = hyp;
   float m = -INFINITY, l = 0.f, acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
+  int slots = hyp;                                 // lane i: slot of position (j & ~31) + i, refreshed every 32 positions
   for (int j = 0; j <= t; ++j) {
+    if (slot_of != nullptr && (j & 31) == 0) slots = (j + lane < t) ? slot_of[static_cast<int64_t>(j + lane) * n + hyp] : hyp;
+    const int slot = __shfl_sync(0xffffffffu, slots, j & 31);
+    const int64_t src = j * row_stride + static_cast<int64_t>(slot) * d + col;
     float kk[E], vv[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      kk[e] = (j == t) ? kn[e] : k_cache[j * row_stride + off + e];
-      vv[e] = (j == t) ? vn[e] : v_cache[j * row_stride + off + e];
+      kk[e] = (j == t) ? kn[e] : k_cache[src + e];
+      vv[e] = (j == t) ? vn[e] : v_cache[src + e];
     }
     float s = 0.f;
 #pragma unroll
@@ -141,16 +153,16 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ k_cac
 }  // namespace
 
 int decode_self_attn(cudaStream_t stream, const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk,
-                     float* ctx, int round_out) {
+                     float* ctx, int round_out, int* slot_of) {
   ST_REQUIRE(n > 0 && H > 0 && t >= 0, "decode_self_attn: bad shape (n=%d H=%d t=%d)", n, H, t);
   ST_REQUIRE(dk == 32 || dk == 64 || dk == 128, "decode_self_attn: d_k must be 32, 64 or 128 (got %d)", dk);
   const int warps = n * H;
-  const int grid = (warps + 7) / 8;
+  const dim3 grid((warps + 7) / 8), block(256);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
   ProfScope prof(stream, PROF_ATTN_FWD, 4.0 * n * H * static_cast<double>(t + 1) * dk);
-  if (dk == 32) decode_self_attn_kernel<32><<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out);
-  else if (dk == 64) decode_self_attn_kernel<64><<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out);
-  else decode_self_attn_kernel<128><<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out);
+  if (dk == 32) ST_CHECK_CUDA(launch_pdl(decode_self_attn_kernel<32>, grid, block, 0, stream, qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out, slot_of));
+  else if (dk == 64) ST_CHECK_CUDA(launch_pdl(decode_self_attn_kernel<64>, grid, block, 0, stream, qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out, slot_of));
+  else ST_CHECK_CUDA(launch_pdl(decode_self_attn_kernel<128>, grid, block, 0, stream, qkv, k_cache, v_cache, t, n, H, scale_log2, ctx, round_out, slot_of));
   ST_CHECK_LAUNCH();
   return ST_OK;
 }

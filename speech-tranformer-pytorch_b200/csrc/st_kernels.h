@@ -33,7 +33,7 @@ int embed_bwd(cudaStream_t stream, const int64_t* idx, const float* dout, float*
               int64_t padding_idx, int zero_first);
 
 int decode_self_attn(cudaStream_t stream, const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk,
-                     float* ctx, int round_out);
+                     float* ctx, int round_out, int* slot_of);
 // st_beam.cu: one position of beam-search bookkeeping (log-softmax, score update, top-`beam` of beam x V, back-pointers)
 int beam_step(cudaStream_t stream, const float* logits, int64_t ld, int B, int beam, int V, int first, int eos, int pad,
               float* scores, uint8_t* done, int64_t* prev_k, int64_t* next_y, int64_t* parent, int64_t* tokens);

@@ -118,6 +118,9 @@ class IncrementalDecoder:
                 "mask_buf": torch.zeros(B, 1, T, dtype=torch.bool, device=dev),
                 "k": [torch.zeros(self.max_len, n, d, device=dev) for _ in self.layers],
                 "v": [torch.zeros(self.max_len, n, d, device=dev) for _ in self.layers],
+                # which cache slot holds position j of hypothesis i's history (one table for all layers): re-parenting
+                # permutes these 4-byte entries instead of the 2 x n_layers K/V caches (st_decode_self_attn)
+                "slot_of": torch.zeros(self.max_len, n, dtype=torch.int32, device=dev),
             }
             self.state["cross_mask"] = self.state["mask_buf"].expand(-1, beam, -1)      # (B, beam, T), stride 0 over beams
             self._tok = torch.zeros(n, dtype=torch.int64, device=dev)
@@ -210,7 +213,8 @@ class IncrementalDecoder:
             # masked self-attention over the cached positions 0..t (Layers.py:37-38): q of the new token only
             qkv = lw.qkv(lib, x, new(n, 3 * d))
             ctx = new(n, d)
-            check(lib.st_decode_self_attn(_p(qkv), _p(st["k"][i]), _p(st["v"][i]), t, n, H, d // H, _p(ctx), 1, F._stream()))
+            check(lib.st_decode_self_attn(_p(qkv), _p(st["k"][i]), _p(st["v"][i]), t, n, H, d // H, _p(ctx), 1, _p(st["slot_of"]),
+                                          F._stream()))
             a = self._ln(lw.so(lib, ctx, new(n, d), residual=x, round_out=False), lw.s_ln, new(n, d))
             # cross-attention: the beams of an utterance are the query rows; K/V of the encoder output are shared
             q2 = lw.cq(lib, a, new(n, d))
@@ -230,9 +234,8 @@ class IncrementalDecoder:
         """Beam search re-parenting: hypothesis j continues hypothesis parent[j] (global indices into B*beam)."""
         st = self.state
         t = st["t"]
-        for i in range(len(self.layers)):
-            st["k"][i][:t] = st["k"][i][:t].index_select(1, parent)
-            st["v"][i][:t] = st["v"][i][:t].index_select(1, parent)
+        if t > 0:
+            st["slot_of"][:t] = st["slot_of"][:t].index_select(1, parent)
 
 
 @torch.no_grad()

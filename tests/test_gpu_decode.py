@@ -112,7 +112,7 @@ def test_decode_self_attention_kernel(stb, n, H, dk, t):
     qkv = torch.randn(n, 3 * d, generator=g)
     kcd, vcd, qd = kc.to(DEV), vc.to(DEV), qkv.to(DEV)
     ctx = torch.empty(n, d, device=DEV)
-    stb._lib.check(lib.st_decode_self_attn(qd.data_ptr(), kcd.data_ptr(), vcd.data_ptr(), t, n, H, dk, ctx.data_ptr(), 0,
+    stb._lib.check(lib.st_decode_self_attn(qd.data_ptr(), kcd.data_ptr(), vcd.data_ptr(), t, n, H, dk, ctx.data_ptr(), 0, None,
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     assert torch.equal(kcd[t].cpu(), qkv[:, d:2 * d]) and torch.equal(vcd[t].cpu(), qkv[:, 2 * d:])
     assert torch.equal(kcd[:t].cpu(), kc[:t]) and torch.equal(vcd[t + 1:].cpu(), vc[t + 1:])      # nothing else touched
@@ -121,6 +121,20 @@ def test_decode_self_attention_kernel(stb, n, H, dk, t):
     q = qkv[:, :d].double().view(n, H, dk)
     s = torch.einsum("nhd,tnhd->nht", q, K) / dk ** 0.5
     ref = torch.einsum("nht,tnhd->nhd", torch.softmax(s, -1), V).reshape(n, d)
+    assert relerr(ctx, ref) < 1e-5
+    # with a slot table: position j of hypothesis i's history is read from slot perm[j][i] (beam-search re-parenting
+    # without moving the caches); the appended row goes to the hypothesis' own slot and is recorded in the table
+    perm = torch.stack([torch.randperm(n, generator=g) for _ in range(L_max)]).to(torch.int32)
+    slot = perm.to(DEV)
+    kcd, vcd = kc.to(DEV), vc.to(DEV)
+    stb._lib.check(lib.st_decode_self_attn(qd.data_ptr(), kcd.data_ptr(), vcd.data_ptr(), t, n, H, dk, ctx.data_ptr(), 0,
+                                           slot.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(slot[t].cpu(), torch.arange(n, dtype=torch.int32)) and torch.equal(slot[:t].cpu(), perm[:t])
+    idx = perm[:t].long()
+    Kp = torch.cat([torch.gather(kc[:t], 1, idx[:, :, None].expand(-1, -1, d)), qkv[None, :, d:2 * d]], 0).double().view(t + 1, n, H, dk)
+    Vp = torch.cat([torch.gather(vc[:t], 1, idx[:, :, None].expand(-1, -1, d)), qkv[None, :, 2 * d:]], 0).double().view(t + 1, n, H, dk)
+    s = torch.einsum("nhd,tnhd->nht", q, Kp) / dk ** 0.5
+    ref = torch.einsum("nht,tnhd->nhd", torch.softmax(s, -1), Vp).reshape(n, d)
     assert relerr(ctx, ref) < 1e-5
 
 
