@@ -260,13 +260,23 @@ def beam_search(net, inputs: torch.Tensor, input_lengths: torch.Tensor, beam: in
     parent_buf = torch.empty(B * beam, dtype=torch.int64, device=dev)
     parent, steps = None, 0
     lib = dec.lib
+    flag_host, pending = torch.zeros(1, dtype=torch.bool).pin_memory(), None
     for t in range(max_len):
         logits = dec.step(tokens, parent)                                # (B*beam, V) view of row-padded storage
         check(lib.st_beam_step(_p(logits), logits.stride(0), B, beam, V, int(t == 0), eos, PAD, _p(scores), _p(done),
                                _p(prev_all[t]), _p(ys_all[t]), _p(parent_buf), _p(tokens), F._stream()))
         steps = t + 1
-        if (t % 4 == 3 or t + 1 == max_len) and bool(done.all()):   # host poll (a sync) only every 4th position:
-            break                                                    # finished utterances are frozen, extra steps change nothing
+        # "all finished?" without stalling the pipeline: every 4th position the flag is copied to pinned host memory
+        # asynchronously and looked at once the copy has landed.  Stopping a few positions late is harmless: finished
+        # utterances are frozen (they emit PAD, which the back-tracking skips)
+        if pending is not None and pending.query():
+            pending = None
+            if bool(flag_host.item()):
+                break
+        if t % 4 == 3 and pending is None and t + 1 < max_len:
+            flag_host.copy_(done.all().view(1), non_blocking=True)
+            pending = torch.cuda.Event()
+            pending.record()
         parent = parent_buf
     prev_ks, next_ys = list(prev_all[:steps]), list(ys_all[:steps])
     # back-track (Beam.get_hypothesis, Beam.py:100-118) for the n_best final beams, best score first
