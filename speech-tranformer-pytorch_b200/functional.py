@@ -84,10 +84,11 @@ class GradSink:
     use of the same parameter within one step falls back to the ordinary accumulate path.  `zeroed` is set by the owner of
     the buffer (FlatParams.zero_grad) after it cleared the whole buffer in one pass: the backward operators then skip their
     own per-tensor clears (grads_zeroed in the st_*_bwd_args; ~200 memset nodes per training step otherwise)."""
-    __slots__ = ("view", "written", "zeroed", "uses", "done")
+    __slots__ = ("view", "written", "zeroed", "uses", "done", "owner")
 
     def __init__(self, view: torch.Tensor):
         self.view, self.written, self.zeroed = view, False, False
+        self.owner = None      # callable(sinks) of the buffer's owner, told when backward operators have written slices
         # uses: forward operators that took this parameter since the last zero_grad; done: backward operators that have
         # since written its gradient directly (kernels enqueued).  done == uses >= 1 means the slice is final for this step
         # (stream order) — what parallel.DataParallelTrainer needs to start a bucket's all-reduce under the backward pass.
@@ -139,37 +140,20 @@ def _sinks_of(params):
     return out
 
 
-_grad_ready_cb = None
-
-
-def set_grad_ready_callback(fn) -> None:
-    """fn(sinks) is called from inside backward right after an operator has ENQUEUED the kernels that write those
-    sinks' gradients (None removes it).  Used by parallel.DataParallelTrainer to overlap the gradient all-reduce."""
-    global _grad_ready_cb
-    _grad_ready_cb = fn
-
-
 def _notify(sinks, direct) -> None:
+    """Inside backward, right after an operator has ENQUEUED the kernels that write these sinks' gradients: count the
+    write and tell each sink's owner (parallel.DataParallelTrainer uses this to start a bucket's all-reduce under the
+    rest of the backward pass).  Nothing happens on the autograd-accumulate fallback path (direct is None)."""
     if direct is None or not sinks:
         return
+    owners = {}
     for s in sinks:
         if s is not None:
             s.done += 1
-    if _grad_ready_cb is not None:
-        _grad_ready_cb([s for s in sinks if s is not None])
-
-
-def _claim(sinks):
-    """Inside backward: take the sinks (None if any was written meanwhile) and mark them written.  Returns
-    (views or None, zeroed): zeroed = 1 when every view is known to hold zeros (see GradSink)."""
-    if sinks is None or any(s is not None and s.written for s in sinks):
-        return None, 0
-    zeroed = 1
-    for s in sinks:
-        if s is not None:
-            zeroed &= int(s.zeroed)
-            s.written, s.zeroed = True, False
-    return [None if s is None else s.view for s in sinks], zeroed
+            if s.owner is not None:
+                owners.setdefault(id(s.owner), (s.owner, []))[1].append(s)
+    for cb, group in owners.values():
+        cb(group)
 
 
 _seed_state = [0]

@@ -7,7 +7,7 @@ parameters live in ONE contiguous fp32 buffer and all gradients in another, so t
 NCCL all-reduce over NVLink/NVSwitch of that buffer and the update is two HBM-bound kernels (squared norm,
 fused clip+Adam) from libst_b200.so.  The buffer is reduced in a few contiguous buckets (~13 MB): a bucket's
 all-reduce starts on NCCL's stream as soon as the backward operators that write its slice have been enqueued
-(functional.set_grad_ready_callback), so the exchange runs under the rest of the backward pass and only the
+(`GradSink.owner`, `functional._notify`), so the exchange runs under the rest of the backward pass and only the
 last bucket (front-end + first encoder layer) is exposed; whatever was not started early is reduced after
 backward.  The clip uses the REDUCED gradient (the reference clips local gradients before Horovod has
 synchronised them, train_multi.py:66 — a bug not reproduced here).
@@ -183,8 +183,8 @@ class DataParallelTrainer:
         self.overlap = bool(overlap) and self.world > 1
         self.early_launches = 0                          # buckets whose all-reduce started under backward (diagnostic)
         if self.overlap:
-            from .functional import set_grad_ready_callback
-            set_grad_ready_callback(self._on_grads_ready)
+            for s in self.fp.sinks:
+                s.owner = self._on_grads_ready        # per-sink notification: several trainers can coexist
 
     def _reduce(self, lo: int, hi: int, async_op: bool):
         return dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)

@@ -108,7 +108,6 @@ def _worker_overlap(rank, world, port, q):
         tr.zero_grad()
         assert all(s.uses == 0 and s.done == 0 for s in tr.fp.sinks)
         assert tr.buckets.pending_ranges() == [(0, tr.fp.numel)]
-        F.set_grad_ready_callback(None)
         q.put((rank, "ok", 0.0))
     except Exception:
         import traceback
