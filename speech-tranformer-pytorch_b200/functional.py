@@ -156,6 +156,19 @@ def _notify(sinks, direct) -> None:
         cb(group)
 
 
+def _claim(sinks):
+    """Inside backward: take the sinks (None if any was written meanwhile) and mark them written.  Returns
+    (views or None, zeroed): zeroed = 1 when every view is known to hold zeros (see GradSink)."""
+    if sinks is None or any(s is not None and s.written for s in sinks):
+        return None, 0
+    zeroed = 1
+    for s in sinks:
+        if s is not None:
+            zeroed &= int(s.zeroed)
+            s.written, s.zeroed = True, False
+    return [None if s is None else s.view for s in sinks], zeroed
+
+
 _seed_state = [0]
 
 

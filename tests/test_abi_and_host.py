@@ -180,3 +180,32 @@ def test_synthetic_batch_matches_oracle_generator(stb):
     b = O.synthetic_batch(3, 40, 12, 80, 100, seed=5, fixed_len=False, t_min=10, l_min=3)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_python_sources_reference_only_defined_names():
+    """The GPU-only code paths (autograd backward functions, trainers, bench) cannot run in the CPU suite; at least make
+    sure every name they load is defined somewhere in their module (a deleted helper shows up here, not on the GPU box)."""
+    import ast
+    import builtins
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "speech-tranformer-pytorch_b200", "**", "*.py"), recursive=True)
+    files += [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "tools", "*.py"))
+    bad = []
+    for path in files:
+        tree = ast.parse(open(path).read())
+        known = set(dir(builtins)) | {"__file__", "__name__"}
+        for n in ast.walk(tree):
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef, ast.AsyncFunctionDef)):
+                known.add(n.name)
+            elif isinstance(n, (ast.Import, ast.ImportFrom)):
+                known.update((a.asname or a.name).split(".")[0] for a in n.names)
+            elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+                known.add(n.id)
+            elif isinstance(n, ast.arg):
+                known.add(n.arg)
+            elif isinstance(n, ast.ExceptHandler) and n.name:
+                known.add(n.name)
+        bad += [f"{os.path.relpath(path, root)}:{n.lineno} {n.id}" for n in ast.walk(tree)
+                if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in known]
+    assert not bad, bad
