@@ -449,3 +449,40 @@ def test_dropout_train_mode_runs_and_is_unbiased(stb):
     assert torch.isfinite(y).all() and torch.isfinite(x.grad).all()
     frac_zero = (y == 0).float().mean().item()
     assert abs(frac_zero - 0.1) < 0.01, frac_zero   # dropout2 after the FFN LayerNorm (SubLayers.py:27)
+
+
+def test_programmatic_dependent_launch_changes_nothing(stb):
+    """Kernels chained with programmatic dependent launch (every thread waits with griddepcontrol.wait before its first
+    global access) must compute exactly what ordinary stream-ordered launches compute: an EncoderLayer forward + backward
+    in train mode (dropout on, fixed seeds), repeated, with the option off and on — outputs and input gradients bit for
+    bit (no atomics on that path), parameter gradients up to the summation order of their reductions."""
+    lib = stb._lib.load()
+    gen = torch.Generator().manual_seed(3)
+    B, L, d, H, dff = 4, 333, 512, 8, 2048
+    m = _EncoderLayer(stb, d, dff, H).to(DEV).train()
+    x = torch.randn(B, L, d, generator=gen).to(DEV)
+    g = torch.randn(B, L, d, generator=gen).to(DEV)
+    lens = torch.tensor([L, L - 100, 17, L - 1])
+    mask = O.padding_info_mask(lens, lens).bool().to(DEV)
+
+    def run(pdl):
+        stb._lib.check(lib.st_set_option(b"pdl", pdl))
+        try:
+            stb.functional._seed_state[0] = 0
+            torch.manual_seed(1234)                      # dropout seeds derive from torch's CPU generator
+            for p in m.parameters():
+                p.grad = None
+            cx = x.clone().requires_grad_()
+            cy, _ = m(cx, mask)
+            cy.backward(g)
+            torch.cuda.synchronize()
+            return cy.detach().clone(), cx.grad.clone(), [p.grad.clone() for p in m.parameters()]
+        finally:
+            lib.st_set_option(b"pdl", 1)
+
+    ref = run(0)
+    for _ in range(3):
+        out = run(1)
+        assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
+        for a, b in zip(out[2], ref[2]):
+            assert (a - b).abs().max() <= 1e-5 * max(1.0, float(b.abs().max()))
