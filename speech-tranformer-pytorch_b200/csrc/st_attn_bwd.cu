@@ -149,6 +149,33 @@ __device__ __forceinline__ void resident_to_tmem(const float* x0, int64_t ld0, c
   }
 }
 
+// The same in two halves, so that a kernel can issue the global loads early (they then fly under its mask scan and
+// start-up barrier) and write the rows to TMEM once the allocation is known.
+template <int DK>
+__device__ __forceinline__ void resident_load(const float* x0, int64_t ld0, const float* x1, int64_t ld1, int64_t row, bool row_ok,
+                                              int h, int slice, uint32_t (&r)[32]) {
+  constexpr int CH = DK / 32;
+  if (slice < 2 * CH) {                  // warp-uniform
+    const int which = slice / CH, c = slice % CH;
+    const float* src = (which == 0 ? x0 + row * ld0 : x1 + row * ld1) + h * DK + c * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok) v = __ldg(reinterpret_cast<const float4*>(src + i));
+      r[i] = __float_as_uint(v.x); r[i + 1] = __float_as_uint(v.y); r[i + 2] = __float_as_uint(v.z); r[i + 3] = __float_as_uint(v.w);
+    }
+  }
+}
+template <int DK>
+__device__ __forceinline__ void resident_store(int slice, uint32_t t_lane, uint32_t t_x0, uint32_t t_x1, const uint32_t (&r)[32]) {
+  constexpr int CH = DK / 32;
+  if (slice < 2 * CH) {
+    const int which = slice / CH, c = slice % CH;
+    tmem_st32(t_lane + (which == 0 ? t_x0 : t_x1) + c * 32, r);
+    tmem_st_wait();
+  }
+}
+
 // ================================================================================ dQ
 // RS = true: the resident Q / dO tiles live in SHARED memory (one TMA box each) and the recompute MMAs use the .ss form.
 // The tensor-memory read port (tcgen05.ld of S / dP by the compute warps + the A operands of .ts MMAs) is the busiest
@@ -191,6 +218,14 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
   if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
   pdl_wait();      // nothing above reads or writes global memory (programmatic dependent launch, st_host.h)
   pdl_trigger();
+
+  // the compute threads' resident Q / dO rows: loads issued now, written to TMEM after the barrier below — this kernel runs
+  // 14 CTAs per SM back to back, so a microsecond of start-up latency is paid 14 times per launch
+  uint32_t rres[32];
+  const int r_row = q0 + (warp & 3) * 32 + lane;
+  const bool r_ok = r_row < p.Lq;
+  if (!RS && warp < W_PROD)
+    resident_load<DK>(q, ldq, dctx, lddctx, static_cast<int64_t>(b) * p.Lq + (r_ok ? r_row : 0), r_ok, h, warp >> 2, rres);
 
   const int extent = block_key_extent(p, b, &s_extent);
   // key tiles entirely inside this utterance's padding have dS == 0: skipped (see block_key_extent)
@@ -299,10 +334,9 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
     const bool row_ok = row < p.Lq;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int col0 = slice * 16;
-    const int64_t grow = static_cast<int64_t>(b) * p.Lq + (row_ok ? row : 0);
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (row_ok ? row : 0);
     if (!RS) {
-      resident_to_tmem<DK>(q, ldq, dctx, lddctx, grow, row_ok, h, slice, t_lane, T_Q, T_DO);
+      resident_store<DK>(slice, t_lane, T_Q, T_DO, rres);
       tc_fence_before();
       mbar_arrive(&res_ready);
     }
