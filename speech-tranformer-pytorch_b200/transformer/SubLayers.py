@@ -11,20 +11,19 @@ class PositionwiseFeedForward(nn.Module):
     """dropout2(LayerNorm(x + fc2(dropout1(relu(fc1(x)))))) — SubLayers.py:24-28, one fused operator."""
 
     def __init__(self, d_model, d_ff, dropout=0.1):
-        super(PositionwiseFeedForward, self).__init__()
-        self.fc1 = nn.Linear(d_model, d_ff, bias=True)
-        self.fc2 = nn.Linear(d_ff, d_model, bias=True)
-        self.relu = nn.ReLU()
-        self.dropout1 = nn.Dropout(dropout)
-        self.dropout2 = nn.Dropout(dropout)
+        super().__init__()
+        # member names, registration order, shapes and the order in which the initialisers draw random numbers are the
+        # reference's (SubLayers.py:13-22): state_dict / init_parameters / same-seed construction stay interchangeable
+        projections = {"fc1": (d_model, d_ff), "fc2": (d_ff, d_model)}
+        for name, (fan_in, fan_out) in projections.items():
+            setattr(self, name, nn.Linear(fan_in, fan_out))
+        self.relu = nn.ReLU()                                   # parameter-free members kept for attribute compatibility
+        self.dropout1, self.dropout2 = nn.Dropout(dropout), nn.Dropout(dropout)
         self.layernorm = nn.LayerNorm(d_model, eps=1e-6)
-
+        for name in projections:
+            init.xavier_normal_(getattr(self, name).weight)
         self.keep_hidden = False     # test hook: keep the hidden activation of the last forward in .last_hidden
         self.last_hidden = None
-
-        # initialization (SubLayers.py:21-22)
-        init.xavier_normal_(self.fc1.weight.data)
-        init.xavier_normal_(self.fc2.weight.data)
 
     def forward(self, inputs):
         p = self.dropout1.p if self.training else 0.0
