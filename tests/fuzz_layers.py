@@ -1,5 +1,5 @@
 """Randomised shape sweep: EncoderLayer and DecoderLayer (self + cross attention, FFN) forward / backward against the
-float64 oracle over random (B, L, T, d_model, heads, d_ff, lengths).  python tools/fuzz_layers.py [n_cases] [seed]"""
+float64 oracle over random (B, L, T, d_model, heads, d_ff, lengths).  python tests/fuzz_layers.py [n_cases] [seed]"""
 import os, sys, random, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
