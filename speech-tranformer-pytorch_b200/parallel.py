@@ -141,7 +141,7 @@ class GradBuckets:
         ready = []
         for s in sinks:
             b = self.of.get(id(s))
-            if b is None or b.started or s.done != s.uses:
+            if b is None or b.started or s.uses < 1 or s.done != s.uses:
                 continue
             b.remaining -= 1
             if b.remaining == 0:

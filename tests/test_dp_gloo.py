@@ -156,3 +156,36 @@ def test_noam_schedule_matches_reference_formula():
     for step in (1, 10, 11999, 12000, 12001, 50000):       # Optim.py:39-41
         ref = np.power(512, -0.5) * np.min([np.power(step, -0.5), np.power(12000, -1.5) * step])
         assert abs(P.noam_lr(512, 12000, step) - ref) < 1e-12
+
+
+def test_grad_buckets_tile_the_buffer_for_any_bucket_size():
+    """parallel.GradBuckets: contiguous, whole parameters, cover [0, numel) exactly for tiny / huge bucket sizes; the
+    readiness bookkeeping only fires when every parameter of a bucket was used and written (host logic, no process group)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from speech_tranformer_pytorch_b200 import parallel as P
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    tr = P.DataParallelTrainer(net, d_model=512)
+    fp = tr.fp
+    for floats in (1, 8, 40, 10 ** 9):
+        gb = P.GradBuckets(fp, floats)
+        assert gb.items[0].lo == 0 and gb.items[-1].hi == fp.numel
+        assert all(a.hi == b.lo for a, b in zip(gb.items, gb.items[1:]))
+        assert sum(len(b.sinks) for b in gb.items) == len(fp.sinks)
+        starts = set(fp.offsets) | {fp.numel}
+        assert all(b.lo in starts and b.hi in starts for b in gb.items), "buckets hold whole parameters"
+        assert all(b.hi - b.lo >= floats for b in gb.items[:-1])
+        assert gb.pending_ranges() == [(0, fp.numel)]
+    gb = P.GradBuckets(fp, 1)                       # one parameter per bucket
+    tr.zero_grad()
+    s_last = fp.sinks[-1]
+    assert gb.mark_done([s_last]) == []             # not used by any forward operator: never "final"
+    s_last.uses, s_last.done = 2, 1
+    assert gb.mark_done([s_last]) == []             # one of two uses still outstanding
+    s_last.done = 2
+    ready = gb.mark_done([s_last])
+    assert [(b.lo, b.hi) for b in ready] == [(fp.offsets[-1], fp.numel)] and ready[0].started
+    assert gb.mark_done([s_last]) == []             # a started bucket is not handed out twice
+    assert gb.pending_ranges() == [(0, fp.offsets[-1])]
+    gb.reset()
+    assert gb.pending_ranges() == [(0, fp.numel)]
