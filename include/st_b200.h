@@ -28,6 +28,14 @@ typedef struct CUstream_st* cudaStream_t;
 #define ST_ERR_DEVICE (-3)
 #define ST_ERR_WORKSPACE (-4)
 
+/* Element type of ACTIVATION tensors (module inputs / outputs and their gradients).  F32 is the fp32 / TF32 path every
+ * entry point defaults to.  F16 / BF16 select 16-bit operands on the tensor cores (tcgen05 kind::f16, fp32 accumulate;
+ * LayerNorm statistics, softmax statistics, parameters, parameter gradients and optimizer state stay fp32):
+ * BASELINE.json configs[2].  Arguments declared `void*` below are of this type; `float*` ones are always fp32.   */
+#define ST_DTYPE_F32 0
+#define ST_DTYPE_F16 1
+#define ST_DTYPE_BF16 2
+
 /* ---- library ------------------------------------------------------------------------------- */
 int st_version(void);                       /* 10000*major + 100*minor + patch */
 const char* st_last_error(void);            /* host string, valid until the next failing call */

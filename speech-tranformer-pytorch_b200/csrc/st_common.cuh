@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -290,6 +292,123 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t targ
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(target_rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+
+// ------------------------------------------------------------------------------------------
+// 16-bit operands (kind::f16: fp16 or bf16 inputs, fp32 accumulate).  One MMA consumes K = 16 elements = the same
+// 32 bytes of a 128-byte swizzle row as a K = 8 TF32 MMA, so K-major tiles keep their byte layout.  MN-major 16-bit
+// tiles use the plain 128-byte swizzle (64 elements of MN per row, 8-row K groups 1024 B apart): the SAME bytes a
+// K-major load of a [rows][64] tile produces, so one TMA box can feed both operand forms.
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr bool k16 = false;
+  static constexpr int BYTES = 4;
+  static constexpr int ROW = 32;           // elements per 128-byte swizzle row
+  static constexpr int UMMA_K = 8;
+  static constexpr uint32_t FMT = 2;       // idesc a/b format (TF32)
+  static constexpr int MN_BOX_ROWS = 32;   // K rows per MN-major TMA box (32-byte-atom swizzle)
+  static constexpr int MN_K_ADV = 1024;    // bytes between the K slices of consecutive MMAs in an MN-major tile
+};
+template <> struct Elem<__half> {
+  static constexpr bool k16 = true;
+  static constexpr int BYTES = 2;
+  static constexpr int ROW = 64;
+  static constexpr int UMMA_K = 16;
+  static constexpr uint32_t FMT = 0;       // F16
+  static constexpr int MN_BOX_ROWS = 64;
+  static constexpr int MN_K_ADV = 2048;
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr bool k16 = true;
+  static constexpr int BYTES = 2;
+  static constexpr int ROW = 64;
+  static constexpr int UMMA_K = 16;
+  static constexpr uint32_t FMT = 1;       // BF16
+  static constexpr int MN_BOX_ROWS = 64;
+  static constexpr int MN_K_ADV = 2048;
+};
+
+// instruction descriptor, fp32 accumulate; fmt: 0 = F16, 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
+__host__ __device__ constexpr uint32_t umma_idesc_fmt(uint32_t fmt, int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+template <typename T>
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return umma_idesc_fmt(Elem<T>::FMT, M, N, a_mn_major, b_mn_major);
+}
+// MN-major operand tile of element type T whose 32/64-wide MN groups are `lbo` bytes apart
+template <typename T>
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return Elem<T>::k16 ? umma_desc(smem_addr, lbo_bytes, 1024, 2) : umma_desc(smem_addr, lbo_bytes, 512, 1);
+}
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A in TMEM: lane = row, each 32-bit column holds two consecutive K elements (low half first)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (Elem<T>::k16) umma_f16_ss(d, a, b, idesc, acc); else umma_tf32_ss(d, a, b, idesc, acc);
+}
+template <typename T>
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (Elem<T>::k16) umma_f16_ts(d, a, b, idesc, acc); else umma_tf32_ts(d, a, b, idesc, acc);
+}
+template <typename T>
+__device__ __forceinline__ void umma_ss_2sm(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (Elem<T>::k16) umma_f16_ss_2sm(d, a, b, idesc, acc); else umma_tf32_ss_2sm(d, a, b, idesc, acc);
+}
+
+// two fp32 -> one 32-bit word of two T (round-to-nearest-even), `lo` in the low half; and back
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+// scalar conversions through the same roundings
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
 
 // ------------------------------------------------------------------------------------------
 // TMEM <-> registers. 32x32b: thread t of the warp owns TMEM lane (warp%4)*32 + t and receives

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/st_b200.h"
+
 namespace st {
 
 // Operand layouts (all row-major fp32 in HBM):
@@ -14,7 +16,7 @@ enum GemmMode : int { GEMM_NT = 0, GEMM_NN = 1, GEMM_TN = 2 };
 
 struct GemmEpilogue {
   const float* bias = nullptr;  // [N], added to every row
-  const float* aux = nullptr;   // [M, ldaux]
+  const void* aux = nullptr;    // [M, ldaux], fp32 for the TF32 GEMM, the operand type for 16-bit GEMMs
   int64_t ldaux = 0;
   int aux_mode = 0;    // 0: none   1: out += aux (residual)   2: out = aux > 0 ? out * aux_scale : 0 (ReLU backward)
   float aux_scale = 1.f;
@@ -33,5 +35,11 @@ struct GemmEpilogue {
 // k_splits > 1 requires ep.atomic and a zero-initialised C.
 int gemm_tf32(cudaStream_t stream, GemmMode mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
               int64_t ldc, int M, int N, int K, const GemmEpilogue& ep, int k_splits = 1);
+
+// Any operand type (ST_DTYPE_F32 = the TF32 GEMM above; ST_DTYPE_F16 / ST_DTYPE_BF16 = kind::f16 with fp32 accumulate).
+// A, B and ep.aux are of the operand type; C is fp32, or the operand type when c_lp != 0.  Leading dimensions in elements
+// (multiples of 16 bytes).  ep.round_tf32 is meaningless for 16-bit operands (the output conversion rounds).
+int gemm_any(cudaStream_t stream, int dtype, GemmMode mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+             int64_t ldc, int c_lp, int M, int N, int K, const GemmEpilogue& ep, int k_splits = 1);
 
 }  // namespace st

@@ -170,6 +170,11 @@ int num_sms() {
 
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int atom32) {
+  return make_tmap(out, 0, base, rank, dims, strides_bytes, box, atom32);
+}
+
+int make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int atom32) {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -191,7 +196,9 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     estr[i] = 1;
     if (i + 1 < rank) gstrides[i] = strides_bytes[i];
   }
-  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+  const CUtensorMapDataType cu_dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                  : (dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult r = encode(out, cu_dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                       gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -54,6 +54,10 @@ const char* last_error();
 // layout tcgen05 accepts for MN-major TF32 operands, UMMA layout type SWIZZLE_128B_BASE32B).
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int atom32 = 0);
+// Same for any element type: dtype 0 = fp32, 1 = fp16, 2 = bf16 (ST_DTYPE_*).  16-bit operands always use the plain
+// 128-byte swizzle (atom32 = 0): box[0] = 64 elements.
+int make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int atom32 = 0);
 
 int num_sms();
 
