@@ -111,6 +111,13 @@ typedef struct {
 } st_gemm_epilogue;
 int st_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
             int K, const st_gemm_epilogue* ep /* host, may be NULL */, cudaStream_t stream);
+/* The same GEMM for any operand type: A, B and ep->aux are of `dtype` (ST_DTYPE_F32 = st_gemm; F16 / BF16 = tcgen05
+ * kind::f16, fp32 accumulate, leading dimensions in elements and multiples of 8); C is fp32, or `dtype` when c_lp != 0. */
+int st_gemm_dt(int dtype, int mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int c_lp,
+               int M, int N, int K, const st_gemm_epilogue* ep /* host, may be NULL */, cudaStream_t stream);
+/* dst = (dst_dtype)(src * scale): 2-D strided element-type conversion; one of the two types is fp32.              */
+int st_cast(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd, int64_t rows, int cols,
+            float scale, cudaStream_t stream);
 
 /* ---- (A) attention core: softmax(mask(Q K^T / sqrt(d_k))) V for all heads ------------------------
  * Attention.py:78-90 (split heads, scores, masked_fill_(-inf), softmax, dropout, P·V, merge heads)
@@ -123,24 +130,29 @@ int st_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, 
  * attn: NULL, or (B,H,Lq,Lk) to receive the post-dropout probabilities the module returns.        */
 typedef struct {
   int B, H, Lq, Lk, dk;
-  const float* q; int64_t ldq;
-  const float* k; int64_t ldk;
-  const float* v; int64_t ldv;
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
   const uint8_t* mask; int64_t ms_b, ms_q, ms_k;
   float dropout_p; uint64_t seed;
-  float* ctx; int64_t ldctx;
+  void* ctx; int64_t ldctx;
   float* lse;
   float* attn;
+  int dtype;              /* ST_DTYPE_*: element type of q, k, v, ctx (and dctx, dq, dk, dv); 16-bit types need dk = 64 */
+  /* Length-aware masking — no mask tensor is built or scanned (Utils.py:41-70, Models.py:46,89-97): keys j >= k_len[b]
+   * are masked (k_len: NULL or (B,) int64) and, when causal != 0, keys j > i.  ORed with `mask` when both are given. */
+  const int64_t* k_len;
+  int causal;
 } st_attn_args;
 int st_attn_fwd(const st_attn_args* a /* host */, cudaStream_t stream);
 
 typedef struct {
   st_attn_args f;       /* the forward problem: q,k,v,mask,dropout,ctx,lse exactly as given to / produced by st_attn_fwd */
-  const float* dctx; int64_t lddctx;   /* gradient w.r.t. ctx (TF32-representable) */
+  const void* dctx; int64_t lddctx;    /* gradient w.r.t. ctx (TF32-representable, or f.dtype) */
   float* delta;                        /* (B,H,Lq) workspace */
-  float* dq; int64_t lddq;             /* gradients, same indexing as q/k/v; rounded to TF32 */
-  float* dk; int64_t lddk;
-  float* dv; int64_t lddv;
+  void* dq; int64_t lddq;              /* gradients, same indexing as q/k/v; rounded to TF32 (or f.dtype) */
+  void* dk; int64_t lddk;
+  void* dv; int64_t lddv;
 } st_attn_bwd_args;
 int st_attn_bwd(const st_attn_bwd_args* a /* host */, cudaStream_t stream);
 
@@ -152,8 +164,8 @@ int st_attn_bwd(const st_attn_bwd_args* a /* host */, cudaStream_t stream);
  * backward reads; `ws` is scratch of st_mha_ws_floats() elements (contents undefined afterwards).  */
 typedef struct {
   int B, Lq, Lk, H, d_model, dk;
-  const float* q_in; const float* k_in; const float* v_in;
-  const float* residual;
+  const void* q_in; const void* k_in; const void* v_in;
+  const void* residual;
   const float* wq; const float* bq; const float* wk; const float* bk;
   const float* wv; const float* bv; const float* wo; const float* bo;
   const float* ln_g; const float* ln_b;
@@ -161,26 +173,33 @@ typedef struct {
   float eps; float dropout_p; uint64_t seed;
   int inputs_tf32;      /* q_in/k_in/v_in are already TF32-representable: skip the rounding copies */
   int round_out;        /* round the module output to TF32 (it feeds the next layer's GEMM) */
-  float* out;           /* (B*Lq, d) */
+  void* out;            /* (B*Lq, d) */
   float* attn;          /* NULL or (B,H,Lq,Lk) */
   float* saved; int64_t saved_floats;
   float* ws; int64_t ws_floats;
-  /* Optional TF32-rounded copies of the weights, maintained by the caller (st_adam_step writes them): when all four
-   * are given, [wq; wk; wv] are adjacent in memory (wk_tf32 == wq_tf32 + d*d, ...) and so are the biases
-   * (bk == bq + d, bv == bk + d), the per-call rounding / packing passes are skipped.  NULL = round internally. */
-  const float* wq_tf32; const float* wk_tf32; const float* wv_tf32; const float* wo_tf32;
+  /* Optional operand-precision copies of the weights (TF32-rounded fp32, or `dtype` when that is 16-bit), maintained by
+   * the caller (st_adam_step writes them): when all four are given, [wq; wk; wv] are adjacent in memory
+   * (wk_tf32 == wq_tf32 + d*d elements, ...) and so are the biases (bk == bq + d, bv == bk + d), the per-call rounding /
+   * packing passes are skipped.  NULL = round / convert internally. */
+  const void* wq_tf32; const void* wk_tf32; const void* wv_tf32; const void* wo_tf32;
+  int dtype;            /* ST_DTYPE_*: element type of q_in, k_in, v_in, residual, out (and of dout, dq_in, dk_in, dv_in,
+                           dresidual in the backward); parameters and their gradients are always fp32 */
+  const int64_t* k_len; /* see st_attn_args: key lengths (B,) or NULL */
+  int causal;
 } st_mha_args;
 int64_t st_mha_saved_floats(int B, int Lq, int Lk, int H, int d_model, int same_qkv, int same_kv, int inputs_tf32);
 int64_t st_mha_ws_floats(int B, int Lq, int Lk, int H, int d_model);
+int64_t st_mha_saved_floats_dt(int dtype, int B, int Lq, int Lk, int H, int d_model, int same_qkv, int same_kv, int inputs_tf32);
+int64_t st_mha_ws_floats_dt(int dtype, int B, int Lq, int Lk, int H, int d_model);
 int st_mha_fwd(const st_mha_args* a /* host */, cudaStream_t stream);
 
 typedef struct {
   st_mha_args f;        /* same problem description as forward (out/attn unused) */
-  const float* dout;    /* (B*Lq, d) */
-  float* dq_in; float* dk_in; float* dv_in;   /* (rows, d); when inputs alias (self-attention) pass the same
+  const void* dout;     /* (B*Lq, d) */
+  void* dq_in; void* dk_in; void* dv_in;      /* (rows, d); when inputs alias (self-attention) pass the same
                                                  pointer and the sum is written once */
-  float* dresidual;     /* (B*Lq, d) gradient of the residual input; may alias one of the above only if
-                           that tensor is the residual (then the sum is formed) */
+  void* dresidual;      /* (B*Lq, d) gradient of the residual input; needed only when the residual is none of the inputs
+                           (otherwise it is added to the FIRST of dq_in, dk_in, dv_in whose input is the residual) */
   float* dwq; float* dbq; float* dwk; float* dbk; float* dwv; float* dbv; float* dwo; float* dbo;
   float* dln_g; float* dln_b;                 /* all parameter gradients are OVERWRITTEN */
   int grads_zeroed;     /* the parameter-gradient buffers already hold zeros (slices of a gradient buffer the caller cleared in
@@ -192,27 +211,30 @@ int st_mha_bwd(const st_mha_bwd_args* a /* host */, cudaStream_t stream);
  * SubLayers.py:24-28:  dropout2(LN(x + fc2(dropout1(relu(fc1(x))))))                               */
 typedef struct {
   int64_t rows; int d_model, d_ff;
-  const float* x;
+  const void* x;
   const float* w1; const float* b1; const float* w2; const float* b2;
   const float* ln_g; const float* ln_b;
   float eps; float dropout_p; uint64_t seed;
   int x_is_tf32;        /* x is already TF32-representable (produced by this library with round_out) */
   int round_out;
-  float* out;
+  void* out;
   float* saved; int64_t saved_floats;
   float* ws; int64_t ws_floats;
-  const float* w1_tf32; const float* w2_tf32;   /* optional TF32-rounded weights (see st_mha_args); NULL = round internally */
+  const void* w1_tf32; const void* w2_tf32;   /* optional operand-precision weights (see st_mha_args); NULL = round internally */
+  int dtype;            /* ST_DTYPE_*: element type of x, out (and dout, dx) */
 } st_ffn_args;
 int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32);
 int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff);
+int64_t st_ffn_saved_floats_dt(int dtype, int64_t rows, int d_model, int d_ff, int x_is_tf32);
+int64_t st_ffn_ws_floats_dt(int dtype, int64_t rows, int d_model, int d_ff);
 /* float offset inside `saved` of the hidden activation h = dropout1(relu(fc1(x))), shape (rows, d_ff) — test hook */
 int64_t st_ffn_hidden_offset(int64_t rows, int d_model, int d_ff, int x_is_tf32);
 int st_ffn_fwd(const st_ffn_args* a /* host */, cudaStream_t stream);
 
 typedef struct {
   st_ffn_args f;
-  const float* dout;
-  float* dx;
+  const void* dout;
+  void* dx;
   float* dw1; float* db1; float* dw2; float* db2; float* dln_g; float* dln_b;   /* OVERWRITTEN */
   int grads_zeroed;     /* see st_mha_bwd_args */
 } st_ffn_bwd_args;
@@ -221,12 +243,12 @@ int st_ffn_bwd(const st_ffn_bwd_args* a /* host */, cudaStream_t stream);
 /* ---- callers either side of the path ------------------------------------------------
  * Decoder input (Models.py:84-87, Embedding.py:21-29): out[i] = table[idx[i]] + pe[i mod pe_rows]
  * (pe may be NULL).  idx are int64 token ids in [0, vocab).  round_tf32 rounds the result (it feeds a GEMM). */
-int st_embed_fwd(const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, float* out, int64_t n, int d,
-                 int vocab, int round_tf32, cudaStream_t stream);
+int st_embed_fwd(const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, void* out, int64_t n, int d,
+                 int vocab, int round_tf32, int dtype /* of out */, cudaStream_t stream);
 /* dtable[idx[i]] += dout[i] for idx[i] != padding_idx (nn.Embedding(padding_idx=PAD) semantics, Models.py:73);
  * zero_first clears the (vocab, d) gradient table before accumulating.                                     */
-int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab, int64_t padding_idx,
-                 int zero_first, cudaStream_t stream);
+int st_embed_bwd(const int64_t* idx, const void* dout, float* dtable, int64_t n, int d, int vocab, int64_t padding_idx,
+                 int zero_first, int dtype /* of dout */, cudaStream_t stream);
 
 /* Incremental-decode self-attention (Decode.py:48-179 decodes the full prefix every step; this is the K/V-reuse form):
  * qkv (n, 3*H*dk) = [q | k | v] projections of the ONE new position of each of the n hypotheses.  Appends k, v as
@@ -261,9 +283,10 @@ typedef struct {
   const float* pe;
   float eps; float dropout_p; uint64_t seed;
   int round_out;
-  float* out;
+  void* out;
   float* saved; int64_t saved_floats;
   float* ws; int64_t ws_floats;
+  int dtype;                       /* ST_DTYPE_*: element type of out (and dout); x, dx and the 80-wide GEMMs stay fp32 / TF32 */
 } st_frontend_args;
 int64_t st_frontend_saved_floats(int64_t rows, int in_dim, int d_model);
 int64_t st_frontend_ws_floats(int64_t rows, int in_dim, int d_model);
@@ -272,7 +295,7 @@ int64_t st_frontend_hidden_offset(int64_t rows, int in_dim, int d_model);
 int st_frontend_fwd(const st_frontend_args* a /* host */, cudaStream_t stream);
 typedef struct {
   st_frontend_args f;
-  const float* dout;
+  const void* dout;
   float* dx;                       /* may be NULL: acoustic features need no gradient */
   float* dw; float* db; float* dln_g; float* dln_b;   /* OVERWRITTEN */
   int grads_zeroed;                /* see st_mha_bwd_args */
@@ -284,19 +307,22 @@ int st_frontend_bwd(const st_frontend_bwd_args* a /* host */, cudaStream_t strea
  * Backward accepts dy with any leading dimension lddy >= out_dim; dx / dw / db may each be NULL.           */
 typedef struct {
   int64_t rows; int in_dim, out_dim;
-  const float* x; int x_is_tf32;
+  const void* x; int x_is_tf32;
   const float* w; const float* b;
   float* y; int64_t ldy;
   float* saved; int64_t saved_floats;
   float* ws; int64_t ws_floats;
+  int dtype;                       /* ST_DTYPE_*: element type of x (and dx); y and dy (logits) are always fp32 */
 } st_linear_args;
 int64_t st_linear_saved_floats(int64_t rows, int in_dim, int out_dim, int x_is_tf32);
 int64_t st_linear_ws_floats(int64_t rows, int in_dim, int out_dim);
+int64_t st_linear_saved_floats_dt(int dtype, int64_t rows, int in_dim, int out_dim, int x_is_tf32);
+int64_t st_linear_ws_floats_dt(int dtype, int64_t rows, int in_dim, int out_dim);
 int st_linear_fwd(const st_linear_args* a /* host */, cudaStream_t stream);
 typedef struct {
   st_linear_args f;
   const float* dy; int64_t lddy;
-  float* dx; float* dw; float* db;                    /* OVERWRITTEN */
+  void* dx; float* dw; float* db;                     /* OVERWRITTEN */
   int grads_zeroed;                                   /* see st_mha_bwd_args */
 } st_linear_bwd_args;
 int st_linear_bwd(const st_linear_bwd_args* a /* host */, cudaStream_t stream);
@@ -324,7 +350,8 @@ int st_ctc_grad(const float* logits, int64_t ld_logits, const int64_t* targets, 
  * st_sumsq: *out += sum(x[i]^2) (caller zeroes `out`, a device float).
  * st_adam_step: g' = grad * grad_scale * min(1, max_grad_norm / (sqrt(*norm_ws) * grad_scale + 1e-6))
  * (clip_grad_norm_ semantics; skipped when norm_ws is NULL or max_grad_norm <= 0), then torch.optim.Adam's
- * update with bias correction for `step` (1-based).  n must be a multiple of 4.                       */
+ * update with bias correction for `step` (1-based).  n must be a multiple of 4.  A non-finite *norm_ws (an fp16
+ * activation gradient overflowed under loss scaling) skips the update: nothing is written.             */
 int st_sumsq(const float* x, int64_t n, float* out, cudaStream_t stream);
 typedef struct {
   float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
@@ -333,7 +360,9 @@ typedef struct {
   int step;
   float max_grad_norm, grad_scale;
   const float* norm_ws;
-  float* param_tf32;    /* optional (n floats): receives round_to_tf32(updated param) for the next step's GEMMs */
+  void* param_tf32;     /* optional (n elements): receives the operand-precision copy of the updated parameters for the
+                           next step's GEMMs: round_to_tf32 (fp32) or, with twin_dtype F16 / BF16, the 16-bit conversion */
+  int twin_dtype;       /* ST_DTYPE_* of param_tf32 */
 } st_adam_args;
 int st_adam_step(const st_adam_args* a /* host */, cudaStream_t stream);
 

@@ -12,6 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libst_b200.so")
 
 c_float_p = C.c_void_p  # raw device pointers travel as integers
+
+# ST_DTYPE_* (include/st_b200.h): element type of activation tensors
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 i64 = C.c_int64
 u64 = C.c_uint64
 
@@ -27,7 +30,8 @@ class AttnArgs(C.Structure):
                 ("q", C.c_void_p), ("ldq", i64), ("k", C.c_void_p), ("ldk", i64), ("v", C.c_void_p), ("ldv", i64),
                 ("mask", C.c_void_p), ("ms_b", i64), ("ms_q", i64), ("ms_k", i64),
                 ("dropout_p", C.c_float), ("seed", u64),
-                ("ctx", C.c_void_p), ("ldctx", i64), ("lse", C.c_void_p), ("attn", C.c_void_p)]
+                ("ctx", C.c_void_p), ("ldctx", i64), ("lse", C.c_void_p), ("attn", C.c_void_p),
+                ("dtype", C.c_int), ("k_len", C.c_void_p), ("causal", C.c_int)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -46,7 +50,8 @@ class MhaArgs(C.Structure):
                 ("inputs_tf32", C.c_int), ("round_out", C.c_int),
                 ("out", C.c_void_p), ("attn", C.c_void_p),
                 ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64),
-                ("wq_tf32", C.c_void_p), ("wk_tf32", C.c_void_p), ("wv_tf32", C.c_void_p), ("wo_tf32", C.c_void_p)]
+                ("wq_tf32", C.c_void_p), ("wk_tf32", C.c_void_p), ("wv_tf32", C.c_void_p), ("wo_tf32", C.c_void_p),
+                ("dtype", C.c_int), ("k_len", C.c_void_p), ("causal", C.c_int)]
 
 
 class MhaBwdArgs(C.Structure):
@@ -64,7 +69,7 @@ class FfnArgs(C.Structure):
                 ("eps", C.c_float), ("dropout_p", C.c_float), ("seed", u64),
                 ("x_is_tf32", C.c_int), ("round_out", C.c_int),
                 ("out", C.c_void_p), ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64),
-                ("w1_tf32", C.c_void_p), ("w2_tf32", C.c_void_p)]
+                ("w1_tf32", C.c_void_p), ("w2_tf32", C.c_void_p), ("dtype", C.c_int)]
 
 
 class FfnBwdArgs(C.Structure):
@@ -77,7 +82,8 @@ class FrontendArgs(C.Structure):
     _fields_ = [("rows", i64), ("T", C.c_int), ("in_dim", C.c_int), ("d_model", C.c_int),
                 ("x", C.c_void_p), ("w", C.c_void_p), ("b", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
                 ("pe", C.c_void_p), ("eps", C.c_float), ("dropout_p", C.c_float), ("seed", u64), ("round_out", C.c_int),
-                ("out", C.c_void_p), ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64)]
+                ("out", C.c_void_p), ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64),
+                ("dtype", C.c_int)]
 
 
 class FrontendBwdArgs(C.Structure):
@@ -88,7 +94,7 @@ class FrontendBwdArgs(C.Structure):
 class LinearArgs(C.Structure):
     _fields_ = [("rows", i64), ("in_dim", C.c_int), ("out_dim", C.c_int), ("x", C.c_void_p), ("x_is_tf32", C.c_int),
                 ("w", C.c_void_p), ("b", C.c_void_p), ("y", C.c_void_p), ("ldy", i64),
-                ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64)]
+                ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64), ("dtype", C.c_int)]
 
 
 class LinearBwdArgs(C.Structure):
@@ -100,7 +106,7 @@ class AdamArgs(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("n", i64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("step", C.c_int), ("max_grad_norm", C.c_float), ("grad_scale", C.c_float),
-                ("norm_ws", C.c_void_p), ("param_tf32", C.c_void_p)]
+                ("norm_ws", C.c_void_p), ("param_tf32", C.c_void_p), ("twin_dtype", C.c_int)]
 
 
 # every symbol include/st_b200.h declares: name -> (restype, argtypes)
@@ -130,19 +136,26 @@ SIGNATURES = {
     "st_round_tf32": (C.c_int, [_P, i64, _P, i64, i64, C.c_int, _S]),
     "st_colsum_add": (C.c_int, [_P, i64, i64, C.c_int, _P, _S]),
     "st_gemm": (C.c_int, [C.c_int, _P, i64, _P, i64, _P, i64, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), _S]),
+    "st_gemm_dt": (C.c_int, [C.c_int, C.c_int, _P, i64, _P, i64, _P, i64, C.c_int, C.c_int, C.c_int, C.c_int,
+                             C.POINTER(GemmEpilogue), _S]),
+    "st_cast": (C.c_int, [_P, C.c_int, i64, _P, C.c_int, i64, i64, C.c_int, C.c_float, _S]),
     "st_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _S]),
     "st_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), _S]),
     "st_mha_saved_floats": (i64, [C.c_int] * 8),
     "st_mha_ws_floats": (i64, [C.c_int] * 5),
+    "st_mha_saved_floats_dt": (i64, [C.c_int] * 9),
+    "st_mha_ws_floats_dt": (i64, [C.c_int] * 6),
     "st_mha_fwd": (C.c_int, [C.POINTER(MhaArgs), _S]),
     "st_mha_bwd": (C.c_int, [C.POINTER(MhaBwdArgs), _S]),
     "st_ffn_saved_floats": (i64, [i64, C.c_int, C.c_int, C.c_int]),
     "st_ffn_ws_floats": (i64, [i64, C.c_int, C.c_int]),
+    "st_ffn_saved_floats_dt": (i64, [C.c_int, i64, C.c_int, C.c_int, C.c_int]),
+    "st_ffn_ws_floats_dt": (i64, [C.c_int, i64, C.c_int, C.c_int]),
     "st_ffn_hidden_offset": (i64, [i64, C.c_int, C.c_int, C.c_int]),
     "st_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), _S]),
     "st_ffn_bwd": (C.c_int, [C.POINTER(FfnBwdArgs), _S]),
-    "st_embed_fwd": (C.c_int, [_P, _P, _P, i64, _P, i64, C.c_int, C.c_int, C.c_int, _S]),
-    "st_embed_bwd": (C.c_int, [_P, _P, _P, i64, C.c_int, C.c_int, i64, C.c_int, _S]),
+    "st_embed_fwd": (C.c_int, [_P, _P, _P, i64, _P, i64, C.c_int, C.c_int, C.c_int, C.c_int, _S]),
+    "st_embed_bwd": (C.c_int, [_P, _P, _P, i64, C.c_int, C.c_int, i64, C.c_int, C.c_int, _S]),
     "st_decode_self_attn": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _S]),
     "st_beam_step": (C.c_int, [_P, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _S]),
     "st_frontend_saved_floats": (i64, [i64, C.c_int, C.c_int]),
@@ -152,6 +165,8 @@ SIGNATURES = {
     "st_frontend_bwd": (C.c_int, [C.POINTER(FrontendBwdArgs), _S]),
     "st_linear_saved_floats": (i64, [i64, C.c_int, C.c_int, C.c_int]),
     "st_linear_ws_floats": (i64, [i64, C.c_int, C.c_int]),
+    "st_linear_saved_floats_dt": (i64, [C.c_int, i64, C.c_int, C.c_int, C.c_int]),
+    "st_linear_ws_floats_dt": (i64, [C.c_int, i64, C.c_int, C.c_int]),
     "st_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), _S]),
     "st_linear_bwd": (C.c_int, [C.POINTER(LinearBwdArgs), _S]),
     "st_ctc_ws_floats": (i64, [C.c_int, C.c_int, C.c_int]),

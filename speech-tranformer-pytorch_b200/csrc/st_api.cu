@@ -40,25 +40,34 @@ int selftest_count();
 
 namespace {
 
+inline size_t esz(int dt) { return dt == ST_DTYPE_F32 ? 4 : 2; }
+inline bool is16(int dt) { return dt == ST_DTYPE_F16 || dt == ST_DTYPE_BF16; }
+// floats occupied by n activation elements of type dt
+inline int64_t act_floats(int dt, int64_t n) { return dt == ST_DTYPE_F32 ? n : (n + 1) / 2; }
+// pointer to element `off` of an activation buffer
+inline void* at(void* p, int dt, int64_t off) { return static_cast<char*>(p) + off * static_cast<int64_t>(esz(dt)); }
+inline const void* at(const void* p, int dt, int64_t off) { return static_cast<const char*>(p) + off * static_cast<int64_t>(esz(dt)); }
+
 // split-K factor for a weight-gradient GEMM: enough CTAs to fill the machine ~2x, at least 4 k-blocks each
-int wgrad_splits(int m_out, int n_out, int64_t k_len) {
+int wgrad_splits(int m_out, int n_out, int64_t k_len, int dt) {
   const int bn = n_out > 128 ? 256 : (n_out > 64 ? 128 : 64);
   const int tiles = ((m_out + 127) / 128) * ((n_out + bn - 1) / bn);
-  const int64_t kblocks = (k_len + 31) / 32;
+  const int bk = dt == ST_DTYPE_F32 ? 32 : 64;
+  const int64_t kblocks = (k_len + bk - 1) / bk;
   int s = (2 * num_sms() + tiles - 1) / tiles;
   const int64_t max_s = kblocks / 4 > 0 ? kblocks / 4 : 1;
   if (s > max_s) s = static_cast<int>(max_s);
   return s < 1 ? 1 : s;
 }
 
-// dW[out,in] = dY[rows,out]^T * X[rows,in]   (overwrites dW)
+// dW[out,in] (fp32) = dY[rows,out]^T * X[rows,in]   (overwrites dW); dY and X of type dt
 // zeroed: dW already holds zeros (st_*_bwd_args.grads_zeroed) — no clear needed before the split-K reductions
-int wgrad(cudaStream_t s, const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, int rows, int n_out,
+int wgrad(cudaStream_t s, int dt, const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int rows, int n_out,
           int n_in, bool zeroed = false) {
   if (!zeroed) ST_CHECK_CUDA(cudaMemsetAsync(dw, 0, static_cast<size_t>(n_out) * n_in * sizeof(float), s));
   GemmEpilogue ep;
   ep.atomic = 1;
-  return gemm_tf32(s, GEMM_TN, dy, lddy, x, ldx, dw, n_in, n_out, n_in, rows, ep, wgrad_splits(n_out, n_in, rows));
+  return gemm_any(s, dt, GEMM_TN, dy, lddy, x, ldx, dw, n_in, 0, n_out, n_in, rows, ep, wgrad_splits(n_out, n_in, rows, dt));
 }
 
 // clear a gradient vector unless the caller says it is already zero
@@ -78,41 +87,53 @@ struct Carver {
     used += n;
     return p;
   }
+  void* take_act(int dt, int64_t n) { return take(act_floats(dt, n)); }
   bool ok() const { return base != nullptr && used <= cap; }
 };
 int64_t pad64(int64_t n) { return (n + 63) & ~int64_t(63); }
+int64_t pad64a(int dt, int64_t n) { return pad64(act_floats(dt, n)); }
+
+// operand-precision copy of an fp32 weight matrix: TF32 rounding (fp32 path) or conversion to the 16-bit type
+int weight_copy(cudaStream_t s, int dt, const float* w, void* dst, int64_t rows, int cols) {
+  if (dt == ST_DTYPE_F32) return round_tf32_2d(s, w, cols, static_cast<float*>(dst), cols, rows, cols);
+  return cast_2d(s, w, ST_DTYPE_F32, cols, dst, dt, cols, rows, cols);
+}
 
 // ------------------------------------------------------------------ MHA buffer plans
 struct MhaPlan {
   bool same_qkv, same_kv;
   int64_t M, Mk;
-  int d;
+  int d, dt;
   // saved
-  float *xq_r, *xk_r, *xv_r;  // rounded inputs (alias the inputs when inputs_tf32)
-  float *projq, *projk, *projv;
+  const void *xq_r, *xk_r, *xv_r;   // GEMM-ready inputs (alias the inputs when inputs_tf32 or 16-bit)
+  void *projq, *projk, *projv;
   int64_t ldpq, ldpk, ldpv;
-  float *ctx, *lse, *z, *mean, *rstd, *w_r /*[3d,d] q,k,v*/, *b_pack /*[3d]*/, *wo_r;
+  void* ctx;
+  float *lse, *z, *mean, *rstd;
+  void *w_r /*[3d,d] q,k,v*/, *wo_r;
+  float* b_pack /*[3d]*/;
   bool pre_rounded;
 };
 
 bool mha_pre_rounded(const st_mha_args& a) {
   const int64_t dd = static_cast<int64_t>(a.d_model) * a.d_model;
-  return a.wq_tf32 && a.wk_tf32 && a.wv_tf32 && a.wo_tf32 && a.wk_tf32 == a.wq_tf32 + dd && a.wv_tf32 == a.wk_tf32 + dd &&
+  const int dt = a.dtype;
+  return a.wq_tf32 && a.wk_tf32 && a.wv_tf32 && a.wo_tf32 && a.wk_tf32 == at(a.wq_tf32, dt, dd) && a.wv_tf32 == at(a.wk_tf32, dt, dd) &&
          a.bk == a.bq + a.d_model && a.bv == a.bk + a.d_model;
 }
 
-int64_t mha_saved_floats(int B, int Lq, int Lk, int H, int d, bool same_qkv, bool same_kv, bool inputs_tf32) {
+int64_t mha_saved_floats(int dt, int B, int Lq, int Lk, int H, int d, bool same_qkv, bool same_kv, bool inputs_tf32) {
   const int64_t M = static_cast<int64_t>(B) * Lq, Mk = static_cast<int64_t>(B) * Lk;
   int64_t n = 0;
-  if (!inputs_tf32) {
+  if (dt == ST_DTYPE_F32 && !inputs_tf32) {
     n += pad64(M * d);
     if (!same_qkv) { n += pad64(Mk * d); if (!same_kv) n += pad64(Mk * d); }
   }
-  n += same_qkv ? pad64(M * 3 * d) : pad64(M * d) + (same_kv ? pad64(Mk * 2 * d) : 2 * pad64(Mk * d));
-  n += pad64(M * d);                               // ctx
+  n += same_qkv ? pad64a(dt, M * 3 * d) : pad64a(dt, M * d) + (same_kv ? pad64a(dt, Mk * 2 * d) : 2 * pad64a(dt, Mk * d));
+  n += pad64a(dt, M * d);                          // ctx
   n += pad64(static_cast<int64_t>(B) * H * Lq);    // lse
   n += pad64(M * d) + 2 * pad64(M);                // z, mean, rstd
-  n += pad64(3ll * d * d) + pad64(3 * d) + pad64(static_cast<int64_t>(d) * d);
+  n += pad64a(dt, 3ll * d * d) + pad64(3 * d) + pad64a(dt, static_cast<int64_t>(d) * d);
   return n;
 }
 
@@ -122,10 +143,11 @@ int plan_mha(const st_mha_args& a, MhaPlan& p) {
   p.M = static_cast<int64_t>(a.B) * a.Lq;
   p.Mk = static_cast<int64_t>(a.B) * a.Lk;
   p.d = a.d_model;
-  const int d = a.d_model;
+  p.dt = a.dtype;
+  const int d = a.d_model, dt = a.dtype;
   Carver c(a.saved, a.saved_floats);
-  if (a.inputs_tf32) {
-    p.xq_r = const_cast<float*>(a.q_in); p.xk_r = const_cast<float*>(a.k_in); p.xv_r = const_cast<float*>(a.v_in);
+  if (dt != ST_DTYPE_F32 || a.inputs_tf32) {
+    p.xq_r = a.q_in; p.xk_r = a.k_in; p.xv_r = a.v_in;
   } else {
     p.xq_r = c.take(p.M * d);
     if (p.same_qkv) { p.xk_r = p.xv_r = p.xq_r; }
@@ -135,31 +157,31 @@ int plan_mha(const st_mha_args& a, MhaPlan& p) {
     }
   }
   if (p.same_qkv) {
-    float* b = c.take(p.M * 3 * d);
-    p.projq = b; p.projk = b + d; p.projv = b + 2 * d;
+    void* b = c.take_act(dt, p.M * 3 * d);
+    p.projq = b; p.projk = at(b, dt, d); p.projv = at(b, dt, 2 * d);
     p.ldpq = p.ldpk = p.ldpv = 3 * d;
   } else {
-    p.projq = c.take(p.M * d); p.ldpq = d;
+    p.projq = c.take_act(dt, p.M * d); p.ldpq = d;
     if (p.same_kv) {
-      float* b = c.take(p.Mk * 2 * d);
-      p.projk = b; p.projv = b + d; p.ldpk = p.ldpv = 2 * d;
+      void* b = c.take_act(dt, p.Mk * 2 * d);
+      p.projk = b; p.projv = at(b, dt, d); p.ldpk = p.ldpv = 2 * d;
     } else {
-      p.projk = c.take(p.Mk * d); p.projv = c.take(p.Mk * d); p.ldpk = p.ldpv = d;
+      p.projk = c.take_act(dt, p.Mk * d); p.projv = c.take_act(dt, p.Mk * d); p.ldpk = p.ldpv = d;
     }
   }
-  p.ctx = c.take(p.M * d);
+  p.ctx = c.take_act(dt, p.M * d);
   p.lse = c.take(static_cast<int64_t>(a.B) * a.H * a.Lq);
   p.z = c.take(p.M * d);
   p.mean = c.take(p.M);
   p.rstd = c.take(p.M);
-  p.w_r = c.take(3ll * d * d);
+  p.w_r = c.take_act(dt, 3ll * d * d);
   p.b_pack = c.take(3 * d);
-  p.wo_r = c.take(static_cast<int64_t>(d) * d);
+  p.wo_r = c.take_act(dt, static_cast<int64_t>(d) * d);
   p.pre_rounded = mha_pre_rounded(a);
-  if (p.pre_rounded) {   // caller-maintained TF32 weights, already packed: nothing to round, copy or save
-    p.w_r = const_cast<float*>(a.wq_tf32);
+  if (p.pre_rounded) {   // caller-maintained operand-precision weights, already packed: nothing to round, copy or save
+    p.w_r = const_cast<void*>(a.wq_tf32);
     p.b_pack = const_cast<float*>(a.bq);
-    p.wo_r = const_cast<float*>(a.wo_tf32);
+    p.wo_r = const_cast<void*>(a.wo_tf32);
   }
   if (!c.ok()) {
     set_error("st_mha: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
@@ -168,17 +190,34 @@ int plan_mha(const st_mha_args& a, MhaPlan& p) {
   return ST_OK;
 }
 
-int check_mha(const st_mha_args& a) {
-  ST_REQUIRE(a.B > 0 && a.Lq > 0 && a.Lk > 0 && a.H > 0, "st_mha: empty problem");
-  ST_REQUIRE(a.d_model == a.H * a.dk, "st_mha: d_model (%d) != n_head (%d) * d_k (%d)", a.d_model, a.H, a.dk);
-  ST_REQUIRE(a.dk == 32 || a.dk == 64 || a.dk == 128, "st_mha: d_k must be 32, 64 or 128 (got %d)", a.dk);
+int check_dtype(int dt, const char* who) {
+  ST_REQUIRE(dt == ST_DTYPE_F32 || dt == ST_DTYPE_F16 || dt == ST_DTYPE_BF16, "%s: bad dtype %d", who, dt);
   return ST_OK;
 }
 
-int64_t mha_ws_floats(int B, int Lq, int Lk, int H, int d) {
+int check_mha(const st_mha_args& a) {
+  ST_TRY(check_dtype(a.dtype, "st_mha"));
+  ST_REQUIRE(a.B > 0 && a.Lq > 0 && a.Lk > 0 && a.H > 0, "st_mha: empty problem");
+  ST_REQUIRE(a.d_model == a.H * a.dk, "st_mha: d_model (%d) != n_head (%d) * d_k (%d)", a.d_model, a.H, a.dk);
+  if (is16(a.dtype)) ST_REQUIRE(a.dk == 64, "st_mha: 16-bit activations need d_k = 64 (got %d)", a.dk);
+  else ST_REQUIRE(a.dk == 32 || a.dk == 64 || a.dk == 128, "st_mha: d_k must be 32, 64 or 128 (got %d)", a.dk);
+  return ST_OK;
+}
+
+int64_t mha_ws_floats(int dt, int B, int Lq, int Lk, int H, int d) {
   const int64_t M = static_cast<int64_t>(B) * Lq, Mk = static_cast<int64_t>(B) * Lk;
   // backward: dz, dctx, dprojq, dprojk, dprojv, delta
-  return 2 * pad64(M * d) + pad64(M * 3 * d) + 2 * pad64(Mk * 2 * d) + pad64(static_cast<int64_t>(B) * H * Lq) + 64;
+  return 2 * pad64a(dt, M * d) + pad64a(dt, M * 3 * d) + 2 * pad64a(dt, Mk * 2 * d) + pad64(static_cast<int64_t>(B) * H * Lq) + 64;
+}
+
+void fill_attn(AttnArgs& at_, const st_mha_args& a, const MhaPlan& p) {
+  at_.B = a.B; at_.H = a.H; at_.Lq = a.Lq; at_.Lk = a.Lk; at_.dk = a.dk; at_.dtype = a.dtype;
+  at_.q = p.projq; at_.ldq = p.ldpq; at_.k = p.projk; at_.ldk = p.ldpk; at_.v = p.projv; at_.ldv = p.ldpv;
+  at_.mask = a.mask; at_.ms_b = a.ms_b; at_.ms_q = a.ms_q; at_.ms_k = a.ms_k;
+  at_.k_len = a.k_len; at_.causal = a.causal;
+  at_.scale = 1.f / sqrtf(static_cast<float>(a.dk));
+  at_.drop = make_dropout(a.dropout_p, a.seed);
+  at_.ctx = p.ctx; at_.ldctx = a.d_model; at_.lse = p.lse; at_.attn = nullptr;
 }
 
 }  // namespace
@@ -290,15 +329,16 @@ int st_sumsq(const float* x, int64_t n, float* out, cudaStream_t stream) { retur
 int st_adam_step(const st_adam_args* a, cudaStream_t stream) {
   ST_REQUIRE(a != nullptr, "st_adam_step: null args");
   return adam_step(stream, a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->n, a->lr, a->beta1, a->beta2, a->eps,
-                   a->step, a->max_grad_norm, a->grad_scale, a->norm_ws, a->param_tf32);
+                   a->step, a->max_grad_norm, a->grad_scale, a->norm_ws, a->param_tf32, a->twin_dtype);
 }
 
 // ------------------------------------------------------------------ attention core
 static AttnArgs to_attn(const st_attn_args& a) {
   AttnArgs r{};
-  r.B = a.B; r.H = a.H; r.Lq = a.Lq; r.Lk = a.Lk; r.dk = a.dk;
+  r.B = a.B; r.H = a.H; r.Lq = a.Lq; r.Lk = a.Lk; r.dk = a.dk; r.dtype = a.dtype;
   r.q = a.q; r.ldq = a.ldq; r.k = a.k; r.ldk = a.ldk; r.v = a.v; r.ldv = a.ldv;
   r.mask = a.mask; r.ms_b = a.ms_b; r.ms_q = a.ms_q; r.ms_k = a.ms_k;
+  r.k_len = a.k_len; r.causal = a.causal;
   r.scale = 1.f / sqrtf(static_cast<float>(a.dk));
   r.drop = make_dropout(a.dropout_p, a.seed);
   r.ctx = a.ctx; r.ldctx = a.ldctx; r.lse = a.lse; r.attn = a.attn;
@@ -307,11 +347,13 @@ static AttnArgs to_attn(const st_attn_args& a) {
 
 int st_attn_fwd(const st_attn_args* a, cudaStream_t stream) {
   ST_REQUIRE(a != nullptr, "st_attn_fwd: null args");
+  ST_TRY(check_dtype(a->dtype, "st_attn_fwd"));
   return attn_fwd(stream, to_attn(*a));
 }
 
 int st_attn_bwd(const st_attn_bwd_args* a, cudaStream_t stream) {
   ST_REQUIRE(a != nullptr, "st_attn_bwd: null args");
+  ST_TRY(check_dtype(a->f.dtype, "st_attn_bwd"));
   AttnBwdArgs b{};
   b.f = to_attn(a->f);
   b.dctx = a->dctx; b.lddctx = a->lddctx; b.delta = a->delta;
@@ -319,11 +361,38 @@ int st_attn_bwd(const st_attn_bwd_args* a, cudaStream_t stream) {
   return attn_bwd(stream, b);
 }
 
+int st_cast(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd, int64_t rows, int cols, float scale,
+            cudaStream_t stream) {
+  return cast_2d(stream, src, src_dtype, lds, dst, dst_dtype, ldd, rows, cols, scale);
+}
+
+int st_gemm_dt(int dtype, int mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int c_lp, int M,
+               int N, int K, const st_gemm_epilogue* e, cudaStream_t stream) {
+  ST_REQUIRE(mode >= 0 && mode <= 2, "st_gemm_dt: bad mode %d", mode);
+  ST_TRY(check_dtype(dtype, "st_gemm_dt"));
+  GemmEpilogue ep;
+  int splits = 1;
+  if (e) {
+    ep.bias = e->bias; ep.aux = e->aux; ep.ldaux = e->ldaux; ep.aux_mode = e->aux_mode; ep.relu = e->relu;
+    ep.round_tf32 = e->round_tf32;
+    const DropoutCfg dc = make_dropout(e->dropout_p, e->seed);
+    ep.drop_thresh = dc.thresh; ep.drop_scale = dc.scale; ep.drop_seed = dc.seed;
+    splits = e->k_splits > 1 ? e->k_splits : 1;
+    ep.atomic = splits > 1;
+    ST_REQUIRE(!ep.aux_mode || ep.aux, "st_gemm_dt: aux_mode set without aux");
+  }
+  return gemm_any(stream, dtype, static_cast<GemmMode>(mode), A, lda, B, ldb, C, ldc, c_lp, M, N, K, ep, splits);
+}
+
 // ------------------------------------------------------------------ MultiHeadAttention
 int64_t st_mha_saved_floats(int B, int Lq, int Lk, int H, int d_model, int same_qkv, int same_kv, int inputs_tf32) {
-  return mha_saved_floats(B, Lq, Lk, H, d_model, same_qkv != 0, same_kv != 0 || same_qkv != 0, inputs_tf32 != 0);
+  return mha_saved_floats(ST_DTYPE_F32, B, Lq, Lk, H, d_model, same_qkv != 0, same_kv != 0 || same_qkv != 0, inputs_tf32 != 0);
 }
-int64_t st_mha_ws_floats(int B, int Lq, int Lk, int H, int d_model) { return mha_ws_floats(B, Lq, Lk, H, d_model); }
+int64_t st_mha_ws_floats(int B, int Lq, int Lk, int H, int d_model) { return mha_ws_floats(ST_DTYPE_F32, B, Lq, Lk, H, d_model); }
+int64_t st_mha_saved_floats_dt(int dtype, int B, int Lq, int Lk, int H, int d_model, int same_qkv, int same_kv, int inputs_tf32) {
+  return mha_saved_floats(dtype, B, Lq, Lk, H, d_model, same_qkv != 0, same_kv != 0 || same_qkv != 0, inputs_tf32 != 0);
+}
+int64_t st_mha_ws_floats_dt(int dtype, int B, int Lq, int Lk, int H, int d_model) { return mha_ws_floats(dtype, B, Lq, Lk, H, d_model); }
 
 int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
   ST_REQUIRE(ap != nullptr, "st_mha_fwd: null args");
@@ -331,61 +400,60 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
   ST_TRY(check_mha(a));
   MhaPlan p;
   ST_TRY(plan_mha(a, p));
-  const int d = a.d_model;
+  const int d = a.d_model, dt = a.dtype;
   const int M = static_cast<int>(p.M), Mk = static_cast<int>(p.Mk);
+  const int64_t dd = static_cast<int64_t>(d) * d;
 
-  // 1. TF32 copies of the weights, packed [wq; wk; wv] so that shared inputs need one GEMM
+  // 1. operand-precision copies of the weights, packed [wq; wk; wv] so that shared inputs need one GEMM
   if (!p.pre_rounded) {
-    ST_TRY(round_tf32_2d(s, a.wq, d, p.w_r, d, d, d));
-    ST_TRY(round_tf32_2d(s, a.wk, d, p.w_r + static_cast<int64_t>(d) * d, d, d, d));
-    ST_TRY(round_tf32_2d(s, a.wv, d, p.w_r + 2ll * d * d, d, d, d));
-    ST_TRY(round_tf32_2d(s, a.wo, d, p.wo_r, d, d, d));
+    ST_TRY(weight_copy(s, dt, a.wq, p.w_r, d, d));
+    ST_TRY(weight_copy(s, dt, a.wk, at(p.w_r, dt, dd), d, d));
+    ST_TRY(weight_copy(s, dt, a.wv, at(p.w_r, dt, 2 * dd), d, d));
+    ST_TRY(weight_copy(s, dt, a.wo, p.wo_r, d, d));
     ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack, a.bq, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + d, a.bk, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + 2 * d, a.bv, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
-  // 2. TF32 copies of the inputs
-  if (!a.inputs_tf32) {
-    ST_TRY(round_tf32_2d(s, a.q_in, d, p.xq_r, d, M, d));
+  // 2. TF32 copies of the inputs (fp32 path only: 16-bit activations are GEMM operands as they are)
+  if (dt == ST_DTYPE_F32 && !a.inputs_tf32) {
+    ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.q_in), d, const_cast<float*>(static_cast<const float*>(p.xq_r)), d, M, d));
     if (!p.same_qkv) {
-      ST_TRY(round_tf32_2d(s, a.k_in, d, p.xk_r, d, Mk, d));
-      if (!p.same_kv) ST_TRY(round_tf32_2d(s, a.v_in, d, p.xv_r, d, Mk, d));
+      ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.k_in), d, const_cast<float*>(static_cast<const float*>(p.xk_r)), d, Mk, d));
+      if (!p.same_kv)
+        ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.v_in), d, const_cast<float*>(static_cast<const float*>(p.xv_r)), d, Mk, d));
     }
   }
-  // 3. projections (Attention.py:74-76), outputs rounded for the attention MMAs
+  // 3. projections (Attention.py:74-76), outputs in operand precision for the attention MMAs
   GemmEpilogue ep;
   ep.round_tf32 = 1;
   if (p.same_qkv) {
     ep.bias = p.b_pack;
-    ST_TRY(gemm_tf32(s, GEMM_NT, p.xq_r, d, p.w_r, d, p.projq, p.ldpq, M, 3 * d, d, ep));
+    ST_TRY(gemm_any(s, dt, GEMM_NT, p.xq_r, d, p.w_r, d, p.projq, p.ldpq, 1, M, 3 * d, d, ep));
   } else {
     ep.bias = p.b_pack;
-    ST_TRY(gemm_tf32(s, GEMM_NT, p.xq_r, d, p.w_r, d, p.projq, p.ldpq, M, d, d, ep));
+    ST_TRY(gemm_any(s, dt, GEMM_NT, p.xq_r, d, p.w_r, d, p.projq, p.ldpq, 1, M, d, d, ep));
     if (p.same_kv) {
       ep.bias = p.b_pack + d;
-      ST_TRY(gemm_tf32(s, GEMM_NT, p.xk_r, d, p.w_r + static_cast<int64_t>(d) * d, d, p.projk, p.ldpk, Mk, 2 * d, d, ep));
+      ST_TRY(gemm_any(s, dt, GEMM_NT, p.xk_r, d, at(p.w_r, dt, dd), d, p.projk, p.ldpk, 1, Mk, 2 * d, d, ep));
     } else {
       ep.bias = p.b_pack + d;
-      ST_TRY(gemm_tf32(s, GEMM_NT, p.xk_r, d, p.w_r + static_cast<int64_t>(d) * d, d, p.projk, p.ldpk, Mk, d, d, ep));
+      ST_TRY(gemm_any(s, dt, GEMM_NT, p.xk_r, d, at(p.w_r, dt, dd), d, p.projk, p.ldpk, 1, Mk, d, d, ep));
       ep.bias = p.b_pack + 2 * d;
-      ST_TRY(gemm_tf32(s, GEMM_NT, p.xv_r, d, p.w_r + 2ll * d * d, d, p.projv, p.ldpv, Mk, d, d, ep));
+      ST_TRY(gemm_any(s, dt, GEMM_NT, p.xv_r, d, at(p.w_r, dt, 2 * dd), d, p.projv, p.ldpv, 1, Mk, d, d, ep));
     }
   }
   // 4. attention core (Attention.py:78-90)
-  AttnArgs at{};
-  at.B = a.B; at.H = a.H; at.Lq = a.Lq; at.Lk = a.Lk; at.dk = a.dk;
-  at.q = p.projq; at.ldq = p.ldpq; at.k = p.projk; at.ldk = p.ldpk; at.v = p.projv; at.ldv = p.ldpv;
-  at.mask = a.mask; at.ms_b = a.ms_b; at.ms_q = a.ms_q; at.ms_k = a.ms_k;
-  at.scale = 1.f / sqrtf(static_cast<float>(a.dk));
-  at.drop = make_dropout(a.dropout_p, a.seed);
-  at.ctx = p.ctx; at.ldctx = d; at.lse = p.lse; at.attn = a.attn;
-  ST_TRY(attn_fwd(s, at));
-  // 5. output projection + bias + residual (Attention.py:92,94)
+  AttnArgs at_{};
+  fill_attn(at_, a, p);
+  at_.attn = a.attn;
+  ST_TRY(attn_fwd(s, at_));
+  // 5. output projection + bias + residual (Attention.py:92,94): the pre-LayerNorm sum stays fp32
   GemmEpilogue eo;
   eo.bias = a.bo; eo.aux = a.residual; eo.ldaux = d; eo.aux_mode = 1;
-  ST_TRY(gemm_tf32(s, GEMM_NT, p.ctx, d, p.wo_r, d, p.z, d, M, d, d, eo));
+  ST_TRY(gemm_any(s, dt, GEMM_NT, p.ctx, d, p.wo_r, d, p.z, d, 0, M, d, d, eo));
   // 6. LayerNorm (Attention.py:94)
-  return add_ln_fwd(s, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out, DropoutCfg{});
+  return add_ln_fwd_any(s, ST_DTYPE_F32, dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out,
+                        DropoutCfg{});
 }
 
 int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
@@ -396,43 +464,38 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   ST_TRY(check_mha(a));
   MhaPlan p;
   ST_TRY(plan_mha(a, p));
-  const int d = a.d_model;
+  const int d = a.d_model, dt = a.dtype;
   const int M = static_cast<int>(p.M), Mk = static_cast<int>(p.Mk);
-  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= mha_ws_floats(a.B, a.Lq, a.Lk, a.H, d), "st_mha_bwd: workspace too small");
+  const int64_t dd = static_cast<int64_t>(d) * d;
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= mha_ws_floats(dt, a.B, a.Lq, a.Lk, a.H, d), "st_mha_bwd: workspace too small");
   Carver w(a.ws, a.ws_floats);
-  float* dz = w.take(p.M * d);
-  float* dctx = w.take(p.M * d);
-  float *dpq, *dpk, *dpv;
-  if (p.same_qkv) { float* t = w.take(p.M * 3 * d); dpq = t; dpk = t + d; dpv = t + 2 * d; }
+  void* dz = w.take_act(dt, p.M * d);
+  void* dctx = w.take_act(dt, p.M * d);
+  void *dpq, *dpk, *dpv;
+  if (p.same_qkv) { void* t = w.take_act(dt, p.M * 3 * d); dpq = t; dpk = at(t, dt, d); dpv = at(t, dt, 2 * d); }
   else {
-    dpq = w.take(p.M * d);
-    if (p.same_kv) { float* t = w.take(p.Mk * 2 * d); dpk = t; dpv = t + d; }
-    else { dpk = w.take(p.Mk * d); dpv = w.take(p.Mk * d); }
+    dpq = w.take_act(dt, p.M * d);
+    if (p.same_kv) { void* t = w.take_act(dt, p.Mk * 2 * d); dpk = t; dpv = at(t, dt, d); }
+    else { dpk = w.take_act(dt, p.Mk * d); dpv = w.take_act(dt, p.Mk * d); }
   }
   float* delta = w.take(static_cast<int64_t>(a.B) * a.H * a.Lq);
-  const bool fused_bias = attn_bwd_fuses_bias(a.dk);
+  const bool fused_bias = dt == ST_DTYPE_F32 && attn_bwd_fuses_bias(a.dk);
 
   // LayerNorm backward; dbo = column sums of dz
   ST_CLEAR(b.dln_g, d);
   ST_CLEAR(b.dln_b, d);
   ST_CLEAR(b.dbo, d);
-  ST_TRY(add_ln_bwd(s, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d, 1, DropoutCfg{}));
+  ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d, 1, DropoutCfg{}));
   // output projection backward
   {
     GemmEpilogue e; e.round_tf32 = 1;
-    ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.wo_r, d, dctx, d, M, d, d, e));
-    ST_TRY(wgrad(s, dz, d, p.ctx, d, b.dwo, M, d, d, zeroed));
+    ST_TRY(gemm_any(s, dt, GEMM_NN, dz, d, p.wo_r, d, dctx, d, 1, M, d, d, e));
+    ST_TRY(wgrad(s, dt, dz, d, p.ctx, d, b.dwo, M, d, d, zeroed));
   }
   // attention core backward
   {
     AttnBwdArgs ab{};
-    AttnArgs& at = ab.f;
-    at.B = a.B; at.H = a.H; at.Lq = a.Lq; at.Lk = a.Lk; at.dk = a.dk;
-    at.q = p.projq; at.ldq = p.ldpq; at.k = p.projk; at.ldk = p.ldpk; at.v = p.projv; at.ldv = p.ldpv;
-    at.mask = a.mask; at.ms_b = a.ms_b; at.ms_q = a.ms_q; at.ms_k = a.ms_k;
-    at.scale = 1.f / sqrtf(static_cast<float>(a.dk));
-    at.drop = make_dropout(a.dropout_p, a.seed);
-    at.ctx = p.ctx; at.ldctx = d; at.lse = p.lse; at.attn = nullptr;
+    fill_attn(ab.f, a, p);
     ab.dctx = dctx; ab.lddctx = d; ab.delta = delta;
     ab.dq = dpq; ab.lddq = p.ldpq; ab.dk_ = dpk; ab.lddk = p.ldpk; ab.dv = dpv; ab.lddv = p.ldpv;
     if (fused_bias) {   // dbq / dbk / dbv = column sums of dq / dk / dv, accumulated by the kernels' epilogues
@@ -445,72 +508,74 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   }
   // projection bias / weight gradients.  When the caller hands out dW / db as slices of one packed [wq; wk; wv]
   // buffer (functional.py does) and the projections share their input, one GEMM / column sum covers all of them.
-  const int64_t dd = static_cast<int64_t>(d) * d;
   const bool pack_kv = p.same_kv && b.dwv == b.dwk + dd && b.dbv == b.dbk + d;
   const bool pack_qkv = p.same_qkv && pack_kv && b.dwk == b.dwq + dd && b.dbk == b.dbq + d;
   if (pack_qkv) {
     if (!fused_bias) {
       ST_CLEAR(b.dbq, 3 * d);
-      ST_TRY(colsum_add(s, dpq, p.ldpq, M, 3 * d, b.dbq));
+      ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, 3 * d, b.dbq));
     }
-    ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d, zeroed));
+    ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d, zeroed));
   } else {
     if (!fused_bias) {
       ST_CLEAR(b.dbq, d);
-      ST_TRY(colsum_add(s, dpq, p.ldpq, M, d, b.dbq));
+      ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, d, b.dbq));
     }
-    ST_TRY(wgrad(s, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d, zeroed));
+    ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d, zeroed));
     if (pack_kv) {
       if (!fused_bias) {
         ST_CLEAR(b.dbk, 2 * d);
-        ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, 2 * d, b.dbk));
+        ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, 2 * d, b.dbk));
       }
-      ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d, zeroed));
+      ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d, zeroed));
     } else {
       if (!fused_bias) {
         ST_CLEAR(b.dbk, d);
         ST_CLEAR(b.dbv, d);
-        ST_TRY(colsum_add(s, dpk, p.ldpk, Mk, d, b.dbk));
-        ST_TRY(colsum_add(s, dpv, p.ldpv, Mk, d, b.dbv));
+        ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, d, b.dbk));
+        ST_TRY(colsum_add_any(s, dt, dpv, p.ldpv, Mk, d, b.dbv));
       }
-      ST_TRY(wgrad(s, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d, zeroed));
-      ST_TRY(wgrad(s, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d, zeroed));
+      ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d, zeroed));
+      ST_TRY(wgrad(s, dt, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d, zeroed));
     }
   }
-  // input gradients; the residual branch contributes dz to whichever input it aliased
-  const bool res_q = (a.residual == a.q_in), res_k = (a.residual == a.k_in), res_v = (a.residual == a.v_in);
+  // input gradients; the residual branch contributes dz to EXACTLY ONE input buffer: the first of q, k, v that aliases the
+  // residual tensor (aliased inputs receive the sum of their buffers from the caller)
+  const bool res_q = (a.residual == a.q_in), res_k = !res_q && (a.residual == a.k_in),
+             res_v = !res_q && !res_k && (a.residual == a.v_in);
   auto with_res = [&](bool on) { GemmEpilogue e; if (on) { e.aux = dz; e.ldaux = d; e.aux_mode = 1; } return e; };
   if (p.same_qkv) {
-    ST_TRY(gemm_tf32(s, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, M, d, 3 * d, with_res(res_q)));
+    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, 1, M, d, 3 * d, with_res(res_q)));
   } else {
-    ST_TRY(gemm_tf32(s, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, M, d, d, with_res(res_q)));
+    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, 1, M, d, d, with_res(res_q)));
     if (p.same_kv) {
-      ST_TRY(gemm_tf32(s, GEMM_NN, dpk, p.ldpk, p.w_r + static_cast<int64_t>(d) * d, d, b.dk_in, d, Mk, d, 2 * d, with_res(res_k || res_v)));
+      ST_TRY(gemm_any(s, dt, GEMM_NN, dpk, p.ldpk, at(p.w_r, dt, dd), d, b.dk_in, d, 1, Mk, d, 2 * d, with_res(res_k || res_v)));
     } else {
-      ST_TRY(gemm_tf32(s, GEMM_NN, dpk, p.ldpk, p.w_r + static_cast<int64_t>(d) * d, d, b.dk_in, d, Mk, d, d, with_res(res_k)));
-      ST_TRY(gemm_tf32(s, GEMM_NN, dpv, p.ldpv, p.w_r + 2ll * d * d, d, b.dv_in, d, Mk, d, d, with_res(res_v && !res_k)));
+      ST_TRY(gemm_any(s, dt, GEMM_NN, dpk, p.ldpk, at(p.w_r, dt, dd), d, b.dk_in, d, 1, Mk, d, d, with_res(res_k)));
+      ST_TRY(gemm_any(s, dt, GEMM_NN, dpv, p.ldpv, at(p.w_r, dt, 2 * dd), d, b.dv_in, d, 1, Mk, d, d, with_res(res_v)));
     }
   }
   if (!(res_q || res_k || res_v)) {
     ST_REQUIRE(b.dresidual != nullptr, "st_mha_bwd: dresidual is required when residual is a separate tensor");
-    ST_CHECK_CUDA(cudaMemcpyAsync(b.dresidual, dz, p.M * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ST_CHECK_CUDA(cudaMemcpyAsync(b.dresidual, dz, p.M * d * esz(dt), cudaMemcpyDeviceToDevice, s));
   }
   return ST_OK;
 }
 
 // ------------------------------------------------------------------ PositionwiseFeedForward
 namespace {
-struct FfnPlan { float *x_r, *h, *z, *mean, *rstd, *w1_r, *w2_r; };
+struct FfnPlan { const void* x_r; void* h; float *z, *mean, *rstd; void *w1_r, *w2_r; };
 int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
+  const int dt = a.dtype;
   Carver c(a.saved, a.saved_floats);
-  p.x_r = a.x_is_tf32 ? const_cast<float*>(a.x) : c.take(a.rows * a.d_model);
-  p.h = c.take(a.rows * a.d_ff);
+  p.x_r = (dt != ST_DTYPE_F32 || a.x_is_tf32) ? a.x : c.take(a.rows * a.d_model);
+  p.h = c.take_act(dt, a.rows * a.d_ff);
   p.z = c.take(a.rows * a.d_model);
   p.mean = c.take(a.rows);
   p.rstd = c.take(a.rows);
-  p.w1_r = c.take(static_cast<int64_t>(a.d_ff) * a.d_model);
-  p.w2_r = c.take(static_cast<int64_t>(a.d_ff) * a.d_model);
-  if (a.w1_tf32 && a.w2_tf32) { p.w1_r = const_cast<float*>(a.w1_tf32); p.w2_r = const_cast<float*>(a.w2_tf32); }
+  p.w1_r = c.take_act(dt, static_cast<int64_t>(a.d_ff) * a.d_model);
+  p.w2_r = c.take_act(dt, static_cast<int64_t>(a.d_ff) * a.d_model);
+  if (a.w1_tf32 && a.w2_tf32) { p.w1_r = const_cast<void*>(a.w1_tf32); p.w2_r = const_cast<void*>(a.w2_tf32); }
   if (!c.ok()) {
     set_error("st_ffn: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
     return ST_ERR_WORKSPACE;
@@ -518,43 +583,53 @@ int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
   return ST_OK;
 }
 constexpr uint64_t kSeedMix1 = 0x5DEECE66Dull, kSeedMix2 = 0xB5297A4D3F84D5B5ull;
+int64_t ffn_saved_floats(int dt, int64_t rows, int d_model, int d_ff, int x_is_tf32) {
+  return ((dt != ST_DTYPE_F32 || x_is_tf32) ? 0 : pad64(rows * d_model)) + pad64a(dt, rows * d_ff) + pad64(rows * d_model) +
+         2 * pad64(rows) + 2 * pad64a(dt, static_cast<int64_t>(d_ff) * d_model);
+}
+int64_t ffn_ws_floats(int dt, int64_t rows, int d_model, int d_ff) { return pad64a(dt, rows * d_model) + pad64a(dt, rows * d_ff) + 64; }
 }  // namespace
 
 int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32) {
-  return (x_is_tf32 ? 0 : pad64(rows * d_model)) + pad64(rows * d_ff) + pad64(rows * d_model) + 2 * pad64(rows) +
-         2 * pad64(static_cast<int64_t>(d_ff) * d_model);
+  return ffn_saved_floats(ST_DTYPE_F32, rows, d_model, d_ff, x_is_tf32);
+}
+int64_t st_ffn_saved_floats_dt(int dtype, int64_t rows, int d_model, int d_ff, int x_is_tf32) {
+  return ffn_saved_floats(dtype, rows, d_model, d_ff, x_is_tf32);
 }
 int64_t st_ffn_hidden_offset(int64_t rows, int d_model, int d_ff, int x_is_tf32) {
   (void)d_ff;
   return x_is_tf32 ? 0 : pad64(rows * d_model);
 }
-int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff) { return pad64(rows * d_model) + pad64(rows * d_ff) + 64; }
+int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff) { return ffn_ws_floats(ST_DTYPE_F32, rows, d_model, d_ff); }
+int64_t st_ffn_ws_floats_dt(int dtype, int64_t rows, int d_model, int d_ff) { return ffn_ws_floats(dtype, rows, d_model, d_ff); }
 
 int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
   ST_REQUIRE(ap != nullptr, "st_ffn_fwd: null args");
   const st_ffn_args& a = *ap;
+  ST_TRY(check_dtype(a.dtype, "st_ffn"));
   ST_REQUIRE(a.rows > 0 && a.rows < (1ll << 31) && a.d_model > 0 && a.d_ff > 0, "st_ffn: bad shape");
   FfnPlan p;
   ST_TRY(plan_ffn(a, p));
-  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff;
+  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff, dt = a.dtype;
   if (!(a.w1_tf32 && a.w2_tf32)) {
-    ST_TRY(round_tf32_2d(s, a.w1, d, p.w1_r, d, f, d));
-    ST_TRY(round_tf32_2d(s, a.w2, f, p.w2_r, f, d, f));
+    ST_TRY(weight_copy(s, dt, a.w1, p.w1_r, f, d));
+    ST_TRY(weight_copy(s, dt, a.w2, p.w2_r, d, f));
   }
-  if (!a.x_is_tf32) ST_TRY(round_tf32_2d(s, a.x, d, p.x_r, d, M, d));
+  if (dt == ST_DTYPE_F32 && !a.x_is_tf32)
+    ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.x), d, const_cast<float*>(static_cast<const float*>(p.x_r)), d, M, d));
   // h = dropout1(relu(fc1(x)))                                           SubLayers.py:25
   GemmEpilogue e1;
   e1.bias = a.b1; e1.relu = 1; e1.round_tf32 = 1;
   const DropoutCfg d1 = make_dropout(a.dropout_p, a.seed ^ kSeedMix1);
   e1.drop_thresh = d1.thresh; e1.drop_scale = d1.scale; e1.drop_seed = d1.seed;
-  ST_TRY(gemm_tf32(s, GEMM_NT, p.x_r, d, p.w1_r, d, p.h, f, M, f, d, e1));
-  // z = x + fc2(h)                                                       SubLayers.py:26-27
+  ST_TRY(gemm_any(s, dt, GEMM_NT, p.x_r, d, p.w1_r, d, p.h, f, 1, M, f, d, e1));
+  // z = x + fc2(h)  (fp32)                                               SubLayers.py:26-27
   GemmEpilogue e2;
   e2.bias = a.b2; e2.aux = a.x; e2.ldaux = d; e2.aux_mode = 1;
-  ST_TRY(gemm_tf32(s, GEMM_NT, p.h, f, p.w2_r, f, p.z, d, M, d, f, e2));
+  ST_TRY(gemm_any(s, dt, GEMM_NT, p.h, f, p.w2_r, f, p.z, d, 0, M, d, f, e2));
   // out = dropout2(LN(z))                                                SubLayers.py:27
-  return add_ln_fwd(s, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out,
-                    make_dropout(a.dropout_p, a.seed ^ kSeedMix2));
+  return add_ln_fwd_any(s, ST_DTYPE_F32, dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out,
+                        make_dropout(a.dropout_p, a.seed ^ kSeedMix2));
 }
 
 int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
@@ -562,41 +637,44 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   const st_ffn_bwd_args& b = *bp;
   const bool zeroed = b.grads_zeroed != 0;
   const st_ffn_args& a = b.f;
+  ST_TRY(check_dtype(a.dtype, "st_ffn"));
   FfnPlan p;
   ST_TRY(plan_ffn(a, p));
-  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff;
-  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= st_ffn_ws_floats(a.rows, d, f), "st_ffn_bwd: workspace too small");
+  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff, dt = a.dtype;
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= ffn_ws_floats(dt, a.rows, d, f), "st_ffn_bwd: workspace too small");
   Carver w(a.ws, a.ws_floats);
-  float* dz = w.take(a.rows * d);
-  float* dh = w.take(a.rows * f);
+  void* dz = w.take_act(dt, a.rows * d);
+  void* dh = w.take_act(dt, a.rows * f);
   ST_CLEAR(b.dln_g, d);
   ST_CLEAR(b.dln_b, d);
   ST_CLEAR(b.db2, d);
   ST_CLEAR(b.db1, f);
-  ST_TRY(add_ln_bwd(s, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d, 1,
-                    make_dropout(a.dropout_p, a.seed ^ kSeedMix2)));
+  ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d, 1,
+                        make_dropout(a.dropout_p, a.seed ^ kSeedMix2)));
   // dh = (dz W2) * [h > 0] * dropout1 scale
   GemmEpilogue e;
   e.aux = p.h; e.ldaux = f; e.aux_mode = 2; e.round_tf32 = 1;
   e.aux_scale = make_dropout(a.dropout_p, 0).scale;
   e.colsum = b.db1;   // db1 = column sums of dh, accumulated by the epilogue that produces dh
-  ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.w2_r, f, dh, f, M, f, d, e));
-  ST_TRY(wgrad(s, dz, d, p.h, f, b.dw2, M, d, f, zeroed));
-  ST_TRY(wgrad(s, dh, f, p.x_r, d, b.dw1, M, f, d, zeroed));
+  ST_TRY(gemm_any(s, dt, GEMM_NN, dz, d, p.w2_r, f, dh, f, 1, M, f, d, e));
+  ST_TRY(wgrad(s, dt, dz, d, p.h, f, b.dw2, M, d, f, zeroed));
+  ST_TRY(wgrad(s, dt, dh, f, p.x_r, d, b.dw1, M, f, d, zeroed));
   GemmEpilogue ex;
   ex.aux = dz; ex.ldaux = d; ex.aux_mode = 1;
-  return gemm_tf32(s, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, M, d, f, ex);
+  return gemm_any(s, dt, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, 1, M, d, f, ex);
 }
 
 
 // ------------------------------------------------------------------ decoder input: embedding + positional encoding
-int st_embed_fwd(const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, float* out, int64_t n, int d,
-                 int vocab, int round_tf32, cudaStream_t stream) {
-  return embed_fwd(stream, idx, table, pe, pe_rows, out, n, d, vocab, round_tf32);
+int st_embed_fwd(const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, void* out, int64_t n, int d,
+                 int vocab, int round_tf32, int dtype, cudaStream_t stream) {
+  ST_TRY(check_dtype(dtype, "st_embed_fwd"));
+  return embed_fwd(stream, idx, table, pe, pe_rows, out, n, d, vocab, round_tf32, dtype);
 }
-int st_embed_bwd(const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab, int64_t padding_idx,
-                 int zero_first, cudaStream_t stream) {
-  return embed_bwd(stream, idx, dout, dtable, n, d, vocab, padding_idx, zero_first);
+int st_embed_bwd(const int64_t* idx, const void* dout, float* dtable, int64_t n, int d, int vocab, int64_t padding_idx,
+                 int zero_first, int dtype, cudaStream_t stream) {
+  ST_TRY(check_dtype(dtype, "st_embed_bwd"));
+  return embed_bwd(stream, idx, dout, dtable, n, d, vocab, padding_idx, zero_first, dtype);
 }
 
 int st_decode_self_attn(const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk, float* ctx,
@@ -637,7 +715,8 @@ int64_t st_frontend_saved_floats(int64_t rows, int in_dim, int d_model) {
 int64_t st_frontend_hidden_offset(int64_t rows, int in_dim, int d_model) {
   return pad64(rows * in_dim) + pad64(static_cast<int64_t>(d_model) * in_dim);
 }
-int64_t st_frontend_ws_floats(int64_t rows, int in_dim, int d_model) { (void)in_dim; return pad64(rows * d_model) + 64; }
+// backward scratch: dz, plus an fp32 copy of a 16-bit dout (the 80-wide input GEMMs of this layer stay on the TF32 path)
+int64_t st_frontend_ws_floats(int64_t rows, int in_dim, int d_model) { (void)in_dim; return 2 * pad64(rows * d_model) + 64; }
 
 int st_frontend_fwd(const st_frontend_args* ap, cudaStream_t s) {
   ST_REQUIRE(ap != nullptr, "st_frontend_fwd: null args");
@@ -645,6 +724,7 @@ int st_frontend_fwd(const st_frontend_args* ap, cudaStream_t s) {
   FrontPlan p;
   ST_TRY(plan_front(a, p));
   const int M = static_cast<int>(a.rows), d = a.d_model, k = a.in_dim;
+  ST_TRY(check_dtype(a.dtype, "st_frontend"));
   ST_TRY(round_tf32_2d(s, a.x, k, p.x_r, k, M, k));
   ST_TRY(round_tf32_2d(s, a.w, k, p.w_r, k, d, k));
   // h = Dropout(ReLU(Linear(x)))                                          Models.py:28-31
@@ -654,8 +734,8 @@ int st_frontend_fwd(const st_frontend_args* ap, cudaStream_t s) {
   e.drop_thresh = dc.thresh; e.drop_scale = dc.scale; e.drop_seed = dc.seed;
   ST_TRY(gemm_tf32(s, GEMM_NT, p.x_r, k, p.w_r, k, p.h, d, M, d, k, e));
   // out = LayerNorm(h) + positional encoding of the frame index          Models.py:32,42-44
-  return add_ln_fwd(s, p.h, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out, DropoutCfg{},
-                    a.pe, a.T);
+  return add_ln_fwd_any(s, ST_DTYPE_F32, a.dtype, p.h, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps,
+                        a.round_out, DropoutCfg{}, a.pe, a.T);
 }
 
 int st_frontend_bwd(const st_frontend_bwd_args* bp, cudaStream_t s) {
@@ -669,13 +749,19 @@ int st_frontend_bwd(const st_frontend_bwd_args* bp, cudaStream_t s) {
   ST_REQUIRE(a.ws != nullptr && a.ws_floats >= st_frontend_ws_floats(a.rows, k, d), "st_frontend_bwd: workspace too small");
   Carver w(a.ws, a.ws_floats);
   float* dz = w.take(a.rows * d);
+  const float* dout = static_cast<const float*>(b.dout);
+  if (a.dtype != ST_DTYPE_F32) {
+    float* dout32 = w.take(a.rows * d);
+    ST_TRY(cast_2d(s, b.dout, a.dtype, d, dout32, ST_DTYPE_F32, d, M, d));
+    dout = dout32;
+  }
   ST_CLEAR(b.dln_g, d);
   ST_CLEAR(b.dln_b, d);
   ST_CLEAR(b.db, d);
   // LayerNorm backward, then the gate of dropout(relu(.)) (h > 0 <=> kept and positive); db = column sums of the result
-  ST_TRY(add_ln_bwd(s, b.dout, p.h, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db, M, d, 1, DropoutCfg{}, p.h,
+  ST_TRY(add_ln_bwd(s, dout, p.h, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db, M, d, 1, DropoutCfg{}, p.h,
                     make_dropout(a.dropout_p, 0).scale));
-  ST_TRY(wgrad(s, dz, d, p.x_r, k, b.dw, M, d, k, zeroed));
+  ST_TRY(wgrad(s, ST_DTYPE_F32, dz, d, p.x_r, k, b.dw, M, d, k, zeroed));
   if (b.dx) {
     GemmEpilogue e;
     ST_TRY(gemm_tf32(s, GEMM_NN, dz, d, p.w_r, k, b.dx, k, M, k, d, e));
@@ -686,13 +772,17 @@ int st_frontend_bwd(const st_frontend_bwd_args* bp, cudaStream_t s) {
 // ------------------------------------------------------------------ plain linear layer (vocabulary projection, Models.py:145,151)
 namespace {
 int64_t pad4(int64_t n) { return (n + 3) & ~int64_t(3); }
-struct LinPlan { float *x_r, *w_r; };
+int64_t pad8(int64_t n) { return (n + 7) & ~int64_t(7); }
+int64_t lin_ldr(int dt, int n) { return dt == ST_DTYPE_F32 ? pad4(n) : pad8(n); }   // row stride of the operand-precision dy copy
+struct LinPlan { const void* x_r; void* w_r; };
 int plan_linear(const st_linear_args& a, LinPlan& p) {
-  ST_REQUIRE(a.rows > 0 && a.rows < (1ll << 31) && a.in_dim > 0 && (a.in_dim & 3) == 0 && a.out_dim > 0,
-             "st_linear: bad shape (rows=%lld in_dim=%d must be a multiple of 4, out_dim=%d)", (long long)a.rows, a.in_dim, a.out_dim);
+  ST_TRY(check_dtype(a.dtype, "st_linear"));
+  const int al = a.dtype == ST_DTYPE_F32 ? 4 : 8;
+  ST_REQUIRE(a.rows > 0 && a.rows < (1ll << 31) && a.in_dim > 0 && (a.in_dim % al) == 0 && a.out_dim > 0,
+             "st_linear: bad shape (rows=%lld in_dim=%d must be a multiple of %d, out_dim=%d)", (long long)a.rows, a.in_dim, al, a.out_dim);
   Carver c(a.saved, a.saved_floats);
-  p.x_r = a.x_is_tf32 ? const_cast<float*>(a.x) : c.take(a.rows * a.in_dim);
-  p.w_r = c.take(pad4(a.out_dim) * a.in_dim);          // rows up to a multiple of 4 (zero-filled): see st_linear_fwd
+  p.x_r = (a.dtype != ST_DTYPE_F32 || a.x_is_tf32) ? a.x : c.take(a.rows * a.in_dim);
+  p.w_r = c.take_act(a.dtype, pad4(a.out_dim) * a.in_dim);   // rows up to a multiple of 4 (zero-filled): see st_linear_fwd
   if (!c.ok()) {
     set_error("st_linear: saved buffer too small (%lld floats given, %lld needed)", (long long)a.saved_floats, (long long)c.used);
     return ST_ERR_WORKSPACE;
@@ -705,6 +795,13 @@ int64_t st_linear_saved_floats(int64_t rows, int in_dim, int out_dim, int x_is_t
   return (x_is_tf32 ? 0 : pad64(rows * in_dim)) + pad64(pad4(out_dim) * in_dim);
 }
 int64_t st_linear_ws_floats(int64_t rows, int in_dim, int out_dim) { (void)in_dim; return pad64(rows * pad4(out_dim)) + 64; }
+int64_t st_linear_saved_floats_dt(int dtype, int64_t rows, int in_dim, int out_dim, int x_is_tf32) {
+  return ((dtype != ST_DTYPE_F32 || x_is_tf32) ? 0 : pad64(rows * in_dim)) + pad64a(dtype, pad4(out_dim) * in_dim);
+}
+int64_t st_linear_ws_floats_dt(int dtype, int64_t rows, int in_dim, int out_dim) {
+  (void)in_dim;
+  return pad64a(dtype, rows * lin_ldr(dtype, out_dim)) + 64;
+}
 
 int st_linear_fwd(const st_linear_args* ap, cudaStream_t s) {
   ST_REQUIRE(ap != nullptr, "st_linear_fwd: null args");
@@ -712,9 +809,10 @@ int st_linear_fwd(const st_linear_args* ap, cudaStream_t s) {
   LinPlan p;
   ST_TRY(plan_linear(a, p));
   ST_REQUIRE(a.ldy >= a.out_dim, "st_linear_fwd: ldy (%lld) < out_dim (%d)", (long long)a.ldy, a.out_dim);
-  const int M = static_cast<int>(a.rows), k = a.in_dim, n = a.out_dim;
-  if (!a.x_is_tf32) ST_TRY(round_tf32_2d(s, a.x, k, p.x_r, k, M, k));
-  ST_TRY(round_tf32_2d(s, a.w, k, p.w_r, k, n, k));
+  const int M = static_cast<int>(a.rows), k = a.in_dim, n = a.out_dim, dt = a.dtype;
+  if (dt == ST_DTYPE_F32 && !a.x_is_tf32)
+    ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.x), k, const_cast<float*>(static_cast<const float*>(p.x_r)), k, M, k));
+  ST_TRY(weight_copy(s, dt, a.w, p.w_r, n, k));
   GemmEpilogue e;
   e.bias = a.b;
   // A width that is not a multiple of 4 (V = 4337) would force the scalar epilogue.  Without a bias the GEMM can run on
@@ -722,9 +820,9 @@ int st_linear_fwd(const st_linear_args* ap, cudaStream_t s) {
   int n_eff = n;
   if (!a.b && pad4(n) != n && a.ldy >= pad4(n)) {
     n_eff = static_cast<int>(pad4(n));
-    ST_CHECK_CUDA(cudaMemsetAsync(p.w_r + static_cast<int64_t>(n) * k, 0, static_cast<size_t>(n_eff - n) * k * sizeof(float), s));
+    ST_CHECK_CUDA(cudaMemsetAsync(at(p.w_r, dt, static_cast<int64_t>(n) * k), 0, static_cast<size_t>(n_eff - n) * k * esz(dt), s));
   }
-  return gemm_tf32(s, GEMM_NT, p.x_r, k, p.w_r, k, a.y, a.ldy, M, n_eff, k, e);
+  return gemm_any(s, dt, GEMM_NT, p.x_r, k, p.w_r, k, a.y, a.ldy, 0, M, n_eff, k, e);   // logits stay fp32
 }
 
 int st_linear_bwd(const st_linear_bwd_args* bp, cudaStream_t s) {
@@ -734,23 +832,24 @@ int st_linear_bwd(const st_linear_bwd_args* bp, cudaStream_t s) {
   const st_linear_args& a = b.f;
   LinPlan p;
   ST_TRY(plan_linear(a, p));
-  const int M = static_cast<int>(a.rows), k = a.in_dim, n = a.out_dim;
-  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= st_linear_ws_floats(a.rows, k, n), "st_linear_bwd: workspace too small");
+  const int M = static_cast<int>(a.rows), k = a.in_dim, n = a.out_dim, dt = a.dtype;
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= st_linear_ws_floats_dt(dt, a.rows, k, n), "st_linear_bwd: workspace too small");
   ST_REQUIRE(b.lddy >= n, "st_linear_bwd: lddy (%lld) < out_dim (%d)", (long long)b.lddy, n);
   Carver w(a.ws, a.ws_floats);
-  const int64_t ldr = pad4(n);
-  float* dy_r = w.take(a.rows * ldr);
-  if (ldr != n)   // the ragged tail columns are read by float4 column sums: keep them finite
-    ST_CHECK_CUDA(cudaMemsetAsync(dy_r, 0, static_cast<size_t>(a.rows) * ldr * sizeof(float), s));
-  ST_TRY(round_tf32_2d(s, b.dy, b.lddy, dy_r, ldr, M, n));
+  const int64_t ldr = lin_ldr(dt, n);
+  void* dy_r = w.take_act(dt, a.rows * ldr);
+  if (ldr != n)   // the ragged tail columns are read by vector column sums / TMA boxes: keep them finite
+    ST_CHECK_CUDA(cudaMemsetAsync(dy_r, 0, static_cast<size_t>(a.rows) * ldr * esz(dt), s));
+  if (dt == ST_DTYPE_F32) ST_TRY(round_tf32_2d(s, b.dy, b.lddy, static_cast<float*>(dy_r), ldr, M, n));
+  else ST_TRY(cast_2d(s, b.dy, ST_DTYPE_F32, b.lddy, dy_r, dt, ldr, M, n));
   if (b.dx) {
     GemmEpilogue e;
-    ST_TRY(gemm_tf32(s, GEMM_NN, dy_r, ldr, p.w_r, k, b.dx, k, M, k, n, e));
+    ST_TRY(gemm_any(s, dt, GEMM_NN, dy_r, ldr, p.w_r, k, b.dx, k, 1, M, k, n, e));
   }
-  if (b.dw) ST_TRY(wgrad(s, dy_r, ldr, p.x_r, k, b.dw, M, n, k, zeroed));
+  if (b.dw) ST_TRY(wgrad(s, dt, dy_r, ldr, p.x_r, k, b.dw, M, n, k, zeroed));
   if (b.db && a.b) {
     ST_CLEAR(b.db, n);
-    ST_TRY(colsum_add(s, dy_r, ldr, M, n, b.db));
+    ST_TRY(colsum_add_any(s, dt, dy_r, ldr, M, n, b.db));
   }
   return ST_OK;
 }

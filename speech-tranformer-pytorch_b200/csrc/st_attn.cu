@@ -126,7 +126,7 @@ template <bool DENSE, bool DROP>
 __device__ __forceinline__ void chunk_dkv_t(uint32_t (&rs)[32], uint32_t (&rd)[32], const float* lse, const float* delta,
                                             const uint32_t* rkey, float scale_log2, float dscale, uint32_t thresh,
                                             uint32_t my_ckey, const uint8_t* mrow, int64_t ms_q, int q_first, int Lq,
-                                            bool key_ok) {
+                                            bool key_ok, int causal_key = -1) {
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 lse4 = *reinterpret_cast<const float4*>(lse + i);
@@ -141,7 +141,7 @@ __device__ __forceinline__ void chunk_dkv_t(uint32_t (&rs)[32], uint32_t (&rd)[3
       float pr = fast_exp2(fmaf(__uint_as_float(rs[i + t]), scale_log2, -lses[t]));
       if (DENSE) {
         const int q = q_first + i + t;
-        if (!key_ok || (q < Lq && mrow[static_cast<int64_t>(q) * ms_q] != 0)) pr = 0.f;
+        if (!key_ok || q < causal_key || (mrow != nullptr && q < Lq && mrow[static_cast<int64_t>(q) * ms_q] != 0)) pr = 0.f;
       }
       float dp = __uint_as_float(rd[i + t]);
       float pd = pr;
@@ -202,7 +202,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int n_kv = extent >= p.Lk ? n_kv_all : max(1, (extent + BKV - 1) / BKV);
   // key-padding masks (stride 0 over queries, Utils.py:53-54) and "no mask" give every row of the tile the same
   // bits: compute them once per tile (one thread per 32-key chunk), one tile ahead
-  const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
+  const bool shared_mask = mask_is_row_invariant(p);
   if (shared_mask && tid < BKV / 32) s_mb[0][tid] = mask_bits_row(p, b, 0, true, tid * 32);
   tc_fence_before();
   __syncthreads();
@@ -373,7 +373,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const float inv_l = (p.drop_thresh ? p.drop_scale : 1.f) / l_tot;   // inverted-dropout scale folded in here
   const float lse2 = m_ref + log2f(l_tot);
   {
-    float* dst = p.ctx + (static_cast<int64_t>(b) * p.Lq + (row_ok ? row : 0)) * p.ldctx + h * DK + half * OH;
+    float* dst = static_cast<float*>(p.ctx) + (static_cast<int64_t>(b) * p.Lq + (row_ok ? row : 0)) * p.ldctx + h * DK + half * OH;
     if constexpr (OH >= 32) {
 #pragma unroll
       for (int c = 0; c < OH / 32; ++c) {
@@ -534,9 +534,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
   }
   // key-padding masks (stride 0 over queries) are a per-thread constant
   const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
-  bool key_masked = !key_ok;
-  if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
-  const bool mask_dense = (p.mask != nullptr) && !mask_per_key;
+  bool key_masked = !key_ok || key >= key_limit(p, b);
+  if (mask_per_key && !key_masked) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
+  const bool mask_dense = ((p.mask != nullptr) && !mask_per_key) || p.causal;
+  const int causal_key = p.causal ? key : -1;
   const uint32_t my_ckey = p.drop_thresh ? dropout_col_key(p.drop_seed, static_cast<uint32_t>(key_ok ? key : 0)) : 0u;
   const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
 
@@ -590,17 +591,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) { rs[i] = 0u; rd[i] = 0u; }
       } else {
-        const uint8_t* mrow = mask_dense ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
+        const uint8_t* mrow = (p.mask != nullptr && !mask_per_key) ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
         if (mask_dense) {
           if (p.drop_thresh) chunk_dkv_t<true, true>(rs, rd, s_lse + c * 32, s_delta + c * 32, s_key + c * 32, p.scale_log2, dscale,
-                                                    p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, key_ok);
+                                                    p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, !key_masked, causal_key);
           else chunk_dkv_t<true, false>(rs, rd, s_lse + c * 32, s_delta + c * 32, s_key + c * 32, p.scale_log2, dscale,
-                                        p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, key_ok);
+                                        p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, !key_masked, causal_key);
         } else {
           if (p.drop_thresh) chunk_dkv_t<false, true>(rs, rd, s_lse + c * 32, s_delta + c * 32, s_key + c * 32, p.scale_log2, dscale,
-                                                     p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, key_ok);
+                                                     p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, !key_masked, causal_key);
           else chunk_dkv_t<false, false>(rs, rd, s_lse + c * 32, s_delta + c * 32, s_key + c * 32, p.scale_log2, dscale,
-                                         p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, key_ok);
+                                         p.drop_thresh, my_ckey, mrow, p.ms_q, q0 + c * 32, p.Lq, !key_masked, causal_key);
         }
       }
       tmem_st32(t_lane + T_ST + c * 32, rs);
@@ -633,8 +634,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     tmem_ld32(t_lane + T_DK + c * 32, rk);
     tmem_ld_wait();
     if (key_ok) {
-      float* dvp = p.dv + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + c * 32;
-      float* dkp = p.dk + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + c * 32;
+      float* dvp = static_cast<float*>(p.dv) + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + c * 32;
+      float* dkp = static_cast<float*>(p.dk) + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + c * 32;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         *reinterpret_cast<float4*>(dvp + i) =
@@ -684,7 +685,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int row = q0 + quarter * 32 + lane;
   const bool row_ok = row < p.Lq;
   const int n_kv = (p.Lk + BKV - 1) / BKV;
-  const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
+  const bool shared_mask = mask_is_row_invariant(p);
   if (shared_mask && tid < BKV / 32) s_mb[0][tid] = mask_bits_row(p, b, 0, true, tid * 32);
 
   if (tid == 0) {
@@ -777,7 +778,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     tmem_ld32(t_lane + T_DQ + c * 32, r);
     tmem_ld_wait();
     if (row_ok) {
-      float* dst = p.dq + (static_cast<int64_t>(b) * p.Lq + row) * p.lddq + h * DK + c * 32;
+      float* dst = static_cast<float*>(p.dq) + (static_cast<int64_t>(b) * p.Lq + row) * p.lddq + h * DK + c * 32;
 #pragma unroll
       for (int i = 0; i < 32; i += 4)
         *reinterpret_cast<float4*>(dst + i) =
@@ -796,11 +797,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 // 4-D tensor map over a (B, L, H*dk) activation addressed as rows of `ld` floats, viewed as
 // {32 columns, L rows, H*dk/32 column groups, B}: one box {32, box_rows, dk/32, 1} fetches a whole head tile and lands it
 // as [column group][row][32 floats] — the canonical 128-byte-swizzled UMMA operand layout — with ONE TMA instruction.
-int make_act_tmap(CUtensorMap* m, const float* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32, int dk) {
+int make_act_tmap(CUtensorMap* m, const void* base, int64_t ld, int cols, int L, int B, int box_rows, int atom32, int dk) {
   const uint64_t dims[4] = {32, static_cast<uint64_t>(L), static_cast<uint64_t>(cols / 32), static_cast<uint64_t>(B)};
   const uint64_t strides[3] = {static_cast<uint64_t>(ld) * 4, 128, static_cast<uint64_t>(L) * static_cast<uint64_t>(ld) * 4};
   const uint32_t box[4] = {32, static_cast<uint32_t>(box_rows), static_cast<uint32_t>(dk / 32), 1};
   return make_tmap_f32(m, base, 4, dims, strides, box, atom32);
+}
+
+int make_act_tmap16(CUtensorMap* m, int dtype, const void* base, int64_t ld, int cols, int L, int B, int box_rows, int dk) {
+  const uint64_t dims[4] = {64, static_cast<uint64_t>(L), static_cast<uint64_t>(cols / 64), static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, 128, static_cast<uint64_t>(L) * static_cast<uint64_t>(ld) * 2};
+  const uint32_t box[4] = {64, static_cast<uint32_t>(box_rows), static_cast<uint32_t>(dk / 64), 1};
+  return make_tmap(m, dtype, base, 4, dims, strides, box, 0);
 }
 
 int check_attn(const AttnArgs& a, const char* who) {
@@ -829,6 +837,7 @@ AttnDev attn_to_dev(const AttnArgs& a) {
   AttnDev p{};
   p.B = a.B; p.H = a.H; p.Lq = a.Lq; p.Lk = a.Lk;
   p.mask = a.mask; p.ms_b = a.ms_b; p.ms_q = a.ms_q; p.ms_k = a.ms_k;
+  p.k_len = a.k_len; p.causal = a.causal; p.ds_boost = 1.f;
   p.scale = a.scale; p.scale_log2 = a.scale * kLog2e;
   p.drop_thresh = a.drop.thresh32; p.drop_scale = a.drop.scale32; p.drop_seed = a.drop.seed;
   p.ctx = a.ctx; p.ldctx = a.ldctx; p.lse2 = a.lse; p.attn = a.attn;
@@ -872,7 +881,8 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
     ProfScope prof(s, PROF_ATTN_DELTA, 2.0 * rows * cols * 4);
     ST_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(blocks < cap ? blocks : cap)), dim3(256), 0, s,
-                             a.dctx, a.lddctx, f.ctx, f.ldctx, a.delta, f.B, f.H, f.Lq, DK));
+                             static_cast<const float*>(a.dctx), a.lddctx, static_cast<const float*>(f.ctx), f.ldctx, a.delta, f.B,
+                             f.H, f.Lq, DK));
     ST_CHECK_LAUNCH();
   }
   if (pipelined) return attn_bwd_pipelined(s, a, p);  // st_attn_bwd.cu
@@ -917,6 +927,7 @@ int launch_bwd(cudaStream_t s, const AttnBwdArgs& a) {
 }  // namespace
 
 int attn_fwd(cudaStream_t s, const AttnArgs& a) {
+  if (a.dtype != ST_DTYPE_F32) return attn16_fwd(s, a);
   ST_TRY(check_attn(a, "attn_fwd"));
   ST_REQUIRE(a.lse != nullptr, "attn_fwd: lse buffer is required");
   switch (a.dk) {
@@ -927,6 +938,7 @@ int attn_fwd(cudaStream_t s, const AttnArgs& a) {
 }
 
 int attn_bwd(cudaStream_t s, const AttnBwdArgs& a) {
+  if (a.f.dtype != ST_DTYPE_F32) return attn16_bwd(s, a);
   ST_TRY(check_attn(a.f, "attn_bwd"));
   ST_REQUIRE(a.dctx && a.delta && a.dq && a.dk_ && a.dv && a.f.lse, "attn_bwd: null buffer");
   ST_REQUIRE((a.lddctx & 3) == 0 && (a.lddq & 3) == 0 && (a.lddk & 3) == 0 && (a.lddv & 3) == 0,

@@ -92,7 +92,8 @@ __device__ __forceinline__ void ds16_t(const uint32_t (&rs)[16], uint32_t (&rd)[
 template <bool DENSE, bool DROP>
 __device__ __forceinline__ void dkv16_t(uint32_t (&rs)[16], uint32_t (&rd)[16], const float* lse, const float* delta,
                                         const uint32_t* rkey, float scale_log2, float dscale, uint32_t thresh,
-                                        uint32_t my_ckey, const uint8_t* mrow, int64_t ms_q, int q_first, int Lq, bool key_ok) {
+                                        uint32_t my_ckey, const uint8_t* mrow, int64_t ms_q, int q_first, int Lq, bool key_ok,
+                                        int causal_key = -1) {
 #pragma unroll
   for (int i = 0; i < 16; i += 4) {
     const float4 lse4 = *reinterpret_cast<const float4*>(lse + i);
@@ -107,7 +108,7 @@ __device__ __forceinline__ void dkv16_t(uint32_t (&rs)[16], uint32_t (&rd)[16], 
       float pr = fast_exp2(fmaf(__uint_as_float(rs[i + t]), scale_log2, -lses[t]));
       if (DENSE) {
         const int q = q_first + i + t;
-        if (!key_ok || (q < Lq && mrow[static_cast<int64_t>(q) * ms_q] != 0)) pr = 0.f;
+        if (!key_ok || q < causal_key || (mrow != nullptr && q < Lq && mrow[static_cast<int64_t>(q) * ms_q] != 0)) pr = 0.f;
       }
       float dp = __uint_as_float(rd[i + t]);
       float pd = pr;
@@ -230,7 +231,7 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
   const int extent = block_key_extent(p, b, &s_extent);
   // key tiles entirely inside this utterance's padding have dS == 0: skipped (see block_key_extent)
   const int n_kv = extent >= p.Lk ? (p.Lk + BT - 1) / BT : max(1, (extent + BT - 1) / BT);
-  const bool shared_mask = (p.mask == nullptr) || (p.ms_q == 0);
+  const bool shared_mask = mask_is_row_invariant(p);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -378,7 +379,7 @@ attn_bwd_dq_pipe(const float* __restrict__ q, int64_t ldq, const float* __restri
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = row_ok ? __uint_as_float(r[i]) * p.scale : 0.f;
       if (row_ok) {
-        float* dst = p.dq + (static_cast<int64_t>(b) * p.Lq + row) * p.lddq + h * DK + col0;
+        float* dst = static_cast<float*>(p.dq) + (static_cast<int64_t>(b) * p.Lq + row) * p.lddq + h * DK + col0;
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
           *reinterpret_cast<float4*>(dst + i) = make_float4(tf32_rna(v[i]), tf32_rna(v[i + 1]), tf32_rna(v[i + 2]), tf32_rna(v[i + 3]));
@@ -435,8 +436,8 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
       for (int i = tid; i < rows * (DK / 4); i += NTHREADS) {
         const int r = i / (DK / 4), c = (i - r * (DK / 4)) * 4;
         const int64_t grow = static_cast<int64_t>(b) * p.Lk + kv0 + r;
-        *reinterpret_cast<float4*>(p.dk + grow * p.lddk + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(p.dv + grow * p.lddv + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(static_cast<float*>(p.dk) + grow * p.lddk + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(static_cast<float*>(p.dv) + grow * p.lddv + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (p.trace && tid == 0 && cta_lin < TRACE_CTAS) g_cta_trace[cta_lin * 4 + 1] = global_ns();
       return;
@@ -575,10 +576,11 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
       mbar_arrive(&res_ready);
     }
     const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
-    bool key_masked = !key_ok;
-    if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
-    const bool mask_dense = (p.mask != nullptr) && !mask_per_key;
-    const uint8_t* mrow = mask_dense ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
+    bool key_masked = !key_ok || key >= key_limit(p, b);
+    if (mask_per_key && !key_masked) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
+    const bool mask_dense = ((p.mask != nullptr) && !mask_per_key) || p.causal;
+    const int causal_key = p.causal ? key : -1;
+    const uint8_t* mrow = (p.mask != nullptr && !mask_per_key) ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
     const uint32_t my_ckey = p.drop_thresh ? dropout_col_key(p.drop_seed, static_cast<uint32_t>(key_ok ? key : 0)) : 0u;
     const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
     for (int t = 0; t < n_q; ++t) {
@@ -602,11 +604,11 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
         const uint32_t* rk = s_rkey[s] + col0;
         const int qf = t * BT + col0;
         if (mask_dense) {
-          if (p.drop_thresh) dkv16_t<true, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
-          else dkv16_t<true, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
+          if (p.drop_thresh) dkv16_t<true, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, !key_masked, causal_key);
+          else dkv16_t<true, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, !key_masked, causal_key);
         } else {
-          if (p.drop_thresh) dkv16_t<false, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
-          else dkv16_t<false, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, key_ok);
+          if (p.drop_thresh) dkv16_t<false, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, !key_masked, causal_key);
+          else dkv16_t<false, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, qf, p.Lq, !key_masked, causal_key);
         }
       }
       if (tid == 0) ST_TRACE(1, t, 3);
@@ -633,8 +635,8 @@ attn_bwd_dkv_pipe(const float* __restrict__ k, int64_t ldk, const float* __restr
         vk[i] = key_ok ? __uint_as_float(rk[i]) * p.scale : 0.f;
       }
       if (key_ok) {
-        float* dvp = p.dv + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + col0;
-        float* dkp = p.dk + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + col0;
+        float* dvp = static_cast<float*>(p.dv) + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + col0;
+        float* dkp = static_cast<float*>(p.dk) + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + col0;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           *reinterpret_cast<float4*>(dvp + i) = make_float4(tf32_rna(vv[i]), tf32_rna(vv[i + 1]), tf32_rna(vv[i + 2]), tf32_rna(vv[i + 3]));
@@ -800,7 +802,7 @@ attn_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q_k, const __grid_co
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const int col0 = slice * 16;
     const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
-    const bool mask_dense = (p.mask != nullptr) && !mask_per_key;
+    const bool mask_dense = ((p.mask != nullptr) && !mask_per_key) || p.causal;
     const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
     auto epilogue = [&](int it) {   // dV = dropout-scale * acc, dK = softmax-scale * acc for the key tile of iteration `it`
       const int rb = it & 1;
@@ -814,8 +816,8 @@ attn_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q_k, const __grid_co
         tmem_ld16(t_lane + T_DK + rb * DK + col0, rk);
         tmem_ld_wait();
         if (key_ok) {
-          float* dvp = p.dv + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + col0;
-          float* dkp = p.dk + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + col0;
+          float* dvp = static_cast<float*>(p.dv) + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + col0;
+          float* dkp = static_cast<float*>(p.dk) + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + col0;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             *reinterpret_cast<float4*>(dvp + i) =
@@ -835,9 +837,10 @@ attn_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q_k, const __grid_co
       const int rb = it & 1;
       const int key = (first + it * step) * BKV + quarter * 32 + lane;
       const bool key_ok = key < p.Lk;
-      bool key_masked = !key_ok;
-      if (mask_per_key && key_ok) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
-      const uint8_t* mrow = mask_dense ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
+      bool key_masked = !key_ok || key >= key_limit(p, b);
+      if (mask_per_key && !key_masked) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
+      const int causal_key = p.causal ? key : -1;
+      const uint8_t* mrow = (p.mask != nullptr && !mask_per_key) ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
       const uint32_t my_ckey = p.drop_thresh ? dropout_col_key(p.drop_seed, static_cast<uint32_t>(key_ok ? key : 0)) : 0u;
       mbar_wait(&s_full[rb], (it >> 1) & 1);
       tc_fence_after();
@@ -853,11 +856,11 @@ attn_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q_k, const __grid_co
         const float* de = s_delta + col0;
         const uint32_t* rk = s_rkey + col0;
         if (mask_dense) {
-          if (p.drop_thresh) dkv16_t<true, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, key_ok);
-          else dkv16_t<true, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, key_ok);
+          if (p.drop_thresh) dkv16_t<true, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, !key_masked, causal_key);
+          else dkv16_t<true, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, !key_masked, causal_key);
         } else {
-          if (p.drop_thresh) dkv16_t<false, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, key_ok);
-          else dkv16_t<false, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, key_ok);
+          if (p.drop_thresh) dkv16_t<false, true>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, !key_masked, causal_key);
+          else dkv16_t<false, false>(rs, rd, ls, de, rk, p.scale_log2, dscale, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, !key_masked, causal_key);
         }
       }
       tmem_st16(t_lane + T_ST + rb * BT + col0, rs);
@@ -874,8 +877,8 @@ attn_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q_k, const __grid_co
       for (int i = tid; i < rows * (DK / 4); i += NCOMP) {
         const int r = i / (DK / 4), c = (i - r * (DK / 4)) * 4;
         const int64_t grow = static_cast<int64_t>(b) * p.Lk + kt * BKV + r;
-        *reinterpret_cast<float4*>(p.dk + grow * p.lddk + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(p.dv + grow * p.lddv + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(static_cast<float*>(p.dk) + grow * p.lddk + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(static_cast<float*>(p.dv) + grow * p.lddv + h * DK + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
@@ -924,7 +927,7 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     dim3 grid((f.Lk + 127) / 128, f.H, f.B);
     // algorithmic share of the attention backward carried by this kernel: dV and dK (S, dP recompute not counted)
     ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.k, f.ldk, f.v, f.ldv, tqk, tqm, tdk, tdm, tkr, tvr, p));
+    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, static_cast<const float*>(f.k), f.ldk, static_cast<const float*>(f.v), f.ldv, tqk, tqm, tdk, tdm, tkr, tvr, p));
     ST_CHECK_LAUNCH();
     }
   }
@@ -946,7 +949,7 @@ int launch_pipelined(cudaStream_t s, const AttnBwdArgs& a, const AttnDev& p) {
     dim3 grid((f.Lq + 127) / 128, f.H, f.B);
     // algorithmic share: dQ plus the (single) S and dP products of the textbook backward
     ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, f.q, f.ldq, a.dctx, a.lddctx, tkk, tkm, tvk, tqr, tdr, p));
+    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, static_cast<const float*>(f.q), f.ldq, static_cast<const float*>(a.dctx), a.lddctx, tkk, tkm, tvk, tqr, tdr, p));
     ST_CHECK_LAUNCH();
   }
   return ST_OK;

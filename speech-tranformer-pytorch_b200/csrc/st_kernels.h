@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/st_b200.h"
+
 namespace st {
 
 // Inverted dropout with a stateless counter RNG: element idx is kept iff hash(seed, idx) >= thresh
@@ -23,14 +25,25 @@ int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float*
 int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd,
                const float* gamma, float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
                int round_out, const DropoutCfg& drop, const float* gate = nullptr, float gate_scale = 1.f);
+// the same with 16-bit activations (ST_DTYPE_*): see st_ln.cu
+int add_ln_fwd_any(cudaStream_t stream, int in_dt, int out_dt, const void* a, const void* b, const float* gamma, const float* beta,
+                   void* out, float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
+                   const DropoutCfg& drop, const float* post = nullptr, int64_t post_rows = 0);
+int add_ln_bwd_any(cudaStream_t stream, int dt, const void* dy, const float* z, const float* mean, const float* rstd,
+                   const float* gamma, void* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, int round_out,
+                   const DropoutCfg& drop, const float* gate = nullptr, float gate_scale = 1.f);
+int colsum_add_any(cudaStream_t stream, int dt, const void* x, int64_t ld, int64_t rows, int cols, float* out);
+int cast_2d(cudaStream_t stream, const void* src, int src_dt, int64_t lds, void* dst, int dst_dt, int64_t ldd, int64_t rows, int cols,
+            float scale = 1.f);
 int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols);
 int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, int cols, float* out);
 
 // ---- st_embed.cu
-int embed_fwd(cudaStream_t stream, const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, float* out,
-              int64_t n, int d, int vocab, int round_out);
-int embed_bwd(cudaStream_t stream, const int64_t* idx, const float* dout, float* dtable, int64_t n, int d, int vocab,
-              int64_t padding_idx, int zero_first);
+// dt: element type of out / dout (ST_DTYPE_*); the table, its gradient and pe are fp32
+int embed_fwd(cudaStream_t stream, const int64_t* idx, const float* table, const float* pe, int64_t pe_rows, void* out,
+              int64_t n, int d, int vocab, int round_out, int dt = 0);
+int embed_bwd(cudaStream_t stream, const int64_t* idx, const void* dout, float* dtable, int64_t n, int d, int vocab,
+              int64_t padding_idx, int zero_first, int dt = 0);
 
 int decode_self_attn(cudaStream_t stream, const float* qkv, float* k_cache, float* v_cache, int t, int n, int H, int dk,
                      float* ctx, int round_out, int* slot_of);
@@ -47,7 +60,7 @@ int ctc_fwd_bwd(cudaStream_t stream, const float* logits, int64_t ld, const int6
 // ---- st_optim.cu
 int sumsq_add(cudaStream_t s, const float* x, int64_t n, float* out);
 int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
-              float eps, int step, float max_norm, float gscale, const float* sumsq, float* p_tf32 = nullptr);
+              float eps, int step, float max_norm, float gscale, const float* sumsq, void* p_twin = nullptr, int twin_dt = 0);
 
 // ---- st_lsce.cu
 struct LsceArgs {
@@ -69,17 +82,22 @@ struct LsceArgs {
 };
 int lsce_fwd_bwd(cudaStream_t stream, const LsceArgs& a);
 
-// ---- st_attn.cu
+// ---- st_attn.cu (TF32 operands), st_attn16.cu (fp16 / bf16 operands)
 struct AttnArgs {
   int B, H, Lq, Lk, dk;
-  const float* q; int64_t ldq;   // row (b*Lq + i) at q + row*ldq, head h at column h*dk
-  const float* k; int64_t ldk;
-  const float* v; int64_t ldv;
+  int dtype = 0;                 // ST_DTYPE_*: element type of q, k, v, ctx (and dctx, dq, dk, dv in the backward)
+  const void* q; int64_t ldq;    // row (b*Lq + i) at q + row*ldq, head h at column h*dk
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
   const uint8_t* mask;           // nullable; element (b,i,j) at mask[b*ms_b + i*ms_q + j*ms_k]; nonzero = masked
   int64_t ms_b, ms_q, ms_k;
+  // length-aware masking (no mask tensor built or scanned): keys j >= k_len[b] are masked (Utils.padding_info_mask,
+  // Utils.py:41-57) and, with causal != 0, keys j > i (Utils.feature_info_mask, Utils.py:60-70).  Combine with `mask` by OR.
+  const int64_t* k_len = nullptr;
+  int causal = 0;
   float scale;                   // 1/sqrt(dk)
   DropoutCfg drop;               // dropout on the attention probabilities (Attention.py:89)
-  float* ctx; int64_t ldctx;     // (B*Lq, H*dk) merged heads
+  void* ctx; int64_t ldctx;      // (B*Lq, H*dk) merged heads
   float* lse;                    // (B, H, Lq) natural-log sum-exp of the scaled, masked scores
   float* attn;                   // nullable (B, H, Lq, Lk): post-dropout probabilities (return value of the module)
 };
@@ -87,16 +105,19 @@ int attn_fwd(cudaStream_t stream, const AttnArgs& a);
 
 struct AttnBwdArgs {
   AttnArgs f;                    // forward problem (q,k,v,mask,lse,ctx as produced by attn_fwd)
-  const float* dctx; int64_t lddctx;
+  const void* dctx; int64_t lddctx;
   float* delta;                  // (B, H, Lq) workspace: rowsum(dctx * ctx)
-  float* dq; int64_t lddq;       // same indexing as q/k/v
-  float* dk_; int64_t lddk;
-  float* dv; int64_t lddv;
+  void* dq; int64_t lddq;        // same indexing as q/k/v
+  void* dk_; int64_t lddk;
+  void* dv; int64_t lddv;
   // optional [H*dk] each: column sums of dq / dk / dv are ACCUMULATED here (bias gradients of the Q/K/V projections,
-  // Attention.py:74-76); honoured by the pipelined kernels (d_k <= 64) — attn_bwd_fuses_bias() tells the caller
+  // Attention.py:74-76); honoured by the pipelined TF32 kernels (d_k <= 64) — attn_bwd_fuses_bias() tells the caller
   float* dbq = nullptr; float* dbk = nullptr; float* dbv = nullptr;
 };
 bool attn_bwd_fuses_bias(int dk);
 int attn_bwd(cudaStream_t stream, const AttnBwdArgs& a);
+// st_attn16.cu: the 16-bit kernels (d_k = 64 or 128); called by attn_fwd / attn_bwd when dtype != ST_DTYPE_F32
+int attn16_fwd(cudaStream_t stream, const AttnArgs& a);
+int attn16_bwd(cudaStream_t stream, const AttnBwdArgs& a);
 
 }  // namespace st

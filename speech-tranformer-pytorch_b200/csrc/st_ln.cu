@@ -17,14 +17,16 @@ namespace {
 constexpr int LN_THREADS = 256;
 constexpr int LN_WARPS = LN_THREADS / 32;
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p) { return ldv4(p); }
+template <typename T> __device__ __forceinline__ void st4(T* p, float4 v) { stv4(p, v); }
 
 // ---------------------------------------------------------------- forward
-template <int VPL>
+// InT: element type of a and b (fp32, or the 16-bit activation type); OutT: element type of `out`.  z_out, the
+// statistics, gamma / beta and `post` are always fp32.
+template <int VPL, typename InT, typename OutT>
 __global__ void __launch_bounds__(LN_THREADS)
-add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, float* __restrict__ out, float* __restrict__ z_out,
+add_ln_fwd_kernel(const InT* __restrict__ a, const InT* __restrict__ b, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, OutT* __restrict__ out, float* __restrict__ z_out,
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int d, float eps,
                   int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
                   const float* __restrict__ post, int64_t post_rows) {
@@ -54,7 +56,7 @@ add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
     }
   }
   for (int64_t row = row_first; row < rows; row += stride) {
-    const float* br = b ? b + row * d : nullptr;
+    const InT* br = b ? b + row * d : nullptr;
     float4 x[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) x[i] = xn[i];
@@ -112,7 +114,7 @@ add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
           const float4 pv = ld4(post + (row % post_rows) * d + c);
           o[0] += pv.x; o[1] += pv.y; o[2] += pv.z; o[3] += pv.w;
         }
-        if (round_out) {
+        if (sizeof(OutT) == 4 && round_out) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) o[t] = tf32_rna(o[t]);
         }
@@ -125,10 +127,11 @@ add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
 // ---------------------------------------------------------------- backward
 // dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat;  dbeta += dy;
 // dzsum += dz (the bias gradient of the linear layer that produced z).
-template <int VPL>
+// ActT: element type of dy and dz (fp32, or the 16-bit activation type); z, statistics, gamma, gate are fp32.
+template <int VPL, typename ActT>
 __global__ void __launch_bounds__(LN_THREADS)
-add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
-                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dz,
+add_ln_bwd_kernel(const ActT* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
+                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, ActT* __restrict__ dz,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dzsum, int64_t rows,
                   int d, int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
                   const float* __restrict__ gate, float gate_scale) {
@@ -215,7 +218,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
           o[2] = gv.z > 0.f ? o[2] * gate_scale : 0.f; o[3] = gv.w > 0.f ? o[3] * gate_scale : 0.f;
         }
         acc_z[i].x += o[0]; acc_z[i].y += o[1]; acc_z[i].z += o[2]; acc_z[i].w += o[3];
-        if (round_out) {
+        if (sizeof(ActT) == 4 && round_out) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) o[t] = tf32_rna(o[t]);
         }
@@ -280,8 +283,9 @@ round_tf32_scalar_kernel(const float* __restrict__ src, int64_t lds, float* __re
 }
 
 // ---------------------------------------------------------------- column sums: out[c] += sum_r X[r,c]
+template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
+colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
   pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
   pdl_trigger();
   __shared__ float red[8][132];
@@ -312,22 +316,27 @@ int persistent_grid(int64_t work_blocks, int per_sm) {
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 
 }  // namespace
 
-int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float* gamma, const float* beta, float* out,
-               float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
-               const DropoutCfg& drop, const float* post, int64_t post_rows) {
+namespace {
+
+template <typename InT, typename OutT>
+int add_ln_fwd_t(cudaStream_t stream, const InT* a, const InT* b, const float* gamma, const float* beta, OutT* out,
+                 float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
+                 const DropoutCfg& drop, const float* post, int64_t post_rows) {
   if (rows == 0) return ST_OK;
   ST_REQUIRE(!post || (post_rows > 0 && aligned16(post)), "add_ln_fwd: post operand needs post_rows > 0 and 16-byte alignment");
   ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_fwd: d=%d must be a multiple of 4 and <= 1024", d);
-  ST_REQUIRE(aligned16(a) && (!b || aligned16(b)) && aligned16(gamma) && aligned16(beta) && aligned16(out) &&
-                 (!z_out || aligned16(z_out)),
+  ST_REQUIRE(aligned8(a) && (!b || aligned8(b)) && aligned16(gamma) && aligned16(beta) && aligned8(out) &&
+                 (!z_out || aligned16(z_out)) && (sizeof(InT) == 2 || (aligned16(a) && (!b || aligned16(b)))) &&
+                 (sizeof(OutT) == 2 || aligned16(out)),
              "add_ln_fwd: pointers must be 16-byte aligned");
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 8);
-  ProfScope prof(stream, PROF_LN_FWD, (b ? 3.0 : 2.0) * rows * d * 4 + (z_out ? 1.0 * rows * d * 4 : 0.0));
+  ProfScope prof(stream, PROF_LN_FWD, (b ? 2.0 : 1.0) * rows * d * sizeof(InT) + 1.0 * rows * d * sizeof(OutT) + (z_out ? 1.0 * rows * d * 4 : 0.0));
 #define ST_LAUNCH(VPL)                                                                                            \
-  ST_CHECK_CUDA(launch_pdl(add_ln_fwd_kernel<VPL>, dim3(grid), dim3(LN_THREADS), 0, stream, a, b, gamma, beta, out, z_out, \
+  ST_CHECK_CUDA(launch_pdl(add_ln_fwd_kernel<VPL, InT, OutT>, dim3(grid), dim3(LN_THREADS), 0, stream, a, b, gamma, beta, out, z_out, \
                            mean_out, rstd_out, rows, d, eps, round_out, drop.thresh, drop.scale, drop.seed, post, post_rows))
   if (d <= 128) ST_LAUNCH(1);
   else if (d <= 256) ST_LAUNCH(2);
@@ -338,17 +347,47 @@ int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float*
   return ST_OK;
 }
 
-int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd,
-               const float* gamma, float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
-               int round_out, const DropoutCfg& drop, const float* gate, float gate_scale) {
+}  // namespace
+
+int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float* gamma, const float* beta, float* out,
+               float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
+               const DropoutCfg& drop, const float* post, int64_t post_rows) {
+  return add_ln_fwd_t<float, float>(stream, a, b, gamma, beta, out, z_out, mean_out, rstd_out, rows, d, eps, round_out, drop, post,
+                                    post_rows);
+}
+
+// in_dt: element type of a / b (ST_DTYPE_F32 or out_dt); out_dt: element type of out
+int add_ln_fwd_any(cudaStream_t stream, int in_dt, int out_dt, const void* a, const void* b, const float* gamma, const float* beta,
+                   void* out, float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
+                   const DropoutCfg& drop, const float* post, int64_t post_rows) {
+#define ST_CALL(InT, OutT)                                                                                                   \
+  return add_ln_fwd_t<InT, OutT>(stream, static_cast<const InT*>(a), static_cast<const InT*>(b), gamma, beta, static_cast<OutT*>(out), \
+                                 z_out, mean_out, rstd_out, rows, d, eps, round_out, drop, post, post_rows)
+  if (in_dt == ST_DTYPE_F32 && out_dt == ST_DTYPE_F32) ST_CALL(float, float);
+  if (in_dt == ST_DTYPE_F32 && out_dt == ST_DTYPE_F16) ST_CALL(float, __half);
+  if (in_dt == ST_DTYPE_F32 && out_dt == ST_DTYPE_BF16) ST_CALL(float, __nv_bfloat16);
+  if (in_dt == ST_DTYPE_F16 && out_dt == ST_DTYPE_F16) ST_CALL(__half, __half);
+  if (in_dt == ST_DTYPE_BF16 && out_dt == ST_DTYPE_BF16) ST_CALL(__nv_bfloat16, __nv_bfloat16);
+#undef ST_CALL
+  set_error("add_ln_fwd: unsupported dtype combination (in %d, out %d)", in_dt, out_dt);
+  return ST_ERR_INVALID;
+}
+
+namespace {
+
+template <typename ActT>
+int add_ln_bwd_t(cudaStream_t stream, const ActT* dy, const float* z, const float* mean, const float* rstd,
+                 const float* gamma, ActT* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
+                 int round_out, const DropoutCfg& drop, const float* gate, float gate_scale) {
   if (rows == 0) return ST_OK;
   ST_REQUIRE(!gate || aligned16(gate), "add_ln_bwd: gate must be 16-byte aligned");
   ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_bwd: d=%d must be a multiple of 4 and <= 1024", d);
-  ST_REQUIRE(aligned16(dy) && aligned16(z) && aligned16(gamma) && aligned16(dz), "add_ln_bwd: pointers must be 16-byte aligned");
+  ST_REQUIRE(aligned8(dy) && aligned16(z) && aligned16(gamma) && aligned8(dz) && (sizeof(ActT) == 2 || (aligned16(dy) && aligned16(dz))),
+             "add_ln_bwd: pointers must be 16-byte aligned");
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 4);
-  ProfScope prof(stream, PROF_LN_BWD, 3.0 * rows * d * 4);
+  ProfScope prof(stream, PROF_LN_BWD, 1.0 * rows * d * 4 + 2.0 * rows * d * sizeof(ActT));
 #define ST_LAUNCH(VPL)                                                                                         \
-  ST_CHECK_CUDA(launch_pdl(add_ln_bwd_kernel<VPL>, dim3(grid), dim3(LN_THREADS), 0, stream, dy, z, mean, rstd, gamma, dz, \
+  ST_CHECK_CUDA(launch_pdl(add_ln_bwd_kernel<VPL, ActT>, dim3(grid), dim3(LN_THREADS), 0, stream, dy, z, mean, rstd, gamma, dz, \
                            dgamma, dbeta, dzsum, rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, gate_scale))
   if (d <= 128) ST_LAUNCH(1);
   else if (d <= 256) ST_LAUNCH(2);
@@ -357,6 +396,33 @@ int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float
 #undef ST_LAUNCH
   ST_CHECK_LAUNCH();
   return ST_OK;
+}
+
+}  // namespace
+
+int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd,
+               const float* gamma, float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
+               int round_out, const DropoutCfg& drop, const float* gate, float gate_scale) {
+  return add_ln_bwd_t<float>(stream, dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum, rows, d, round_out, drop, gate, gate_scale);
+}
+
+// dt: element type of dy and dz
+int add_ln_bwd_any(cudaStream_t stream, int dt, const void* dy, const float* z, const float* mean, const float* rstd,
+                   const float* gamma, void* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, int round_out,
+                   const DropoutCfg& drop, const float* gate, float gate_scale) {
+  switch (dt) {
+    case ST_DTYPE_F32:
+      return add_ln_bwd_t<float>(stream, static_cast<const float*>(dy), z, mean, rstd, gamma, static_cast<float*>(dz), dgamma, dbeta,
+                                 dzsum, rows, d, round_out, drop, gate, gate_scale);
+    case ST_DTYPE_F16:
+      return add_ln_bwd_t<__half>(stream, static_cast<const __half*>(dy), z, mean, rstd, gamma, static_cast<__half*>(dz), dgamma, dbeta,
+                                  dzsum, rows, d, round_out, drop, gate, gate_scale);
+    case ST_DTYPE_BF16:
+      return add_ln_bwd_t<__nv_bfloat16>(stream, static_cast<const __nv_bfloat16*>(dy), z, mean, rstd, gamma,
+                                         static_cast<__nv_bfloat16*>(dz), dgamma, dbeta, dzsum, rows, d, round_out, drop, gate, gate_scale);
+  }
+  set_error("add_ln_bwd: bad dtype %d", dt);
+  return ST_ERR_INVALID;
 }
 
 int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols) {
@@ -379,19 +445,98 @@ int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst
   return ST_OK;
 }
 
-int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, int cols, float* out) {
+namespace {
+template <typename T>
+int colsum_add_t(cudaStream_t stream, const T* x, int64_t ld, int64_t rows, int cols, float* out) {
   if (rows == 0 || cols == 0) return ST_OK;
-  // float4 loads: a ragged width is fine as long as the (padded) row is long enough to read the last group
-  ST_REQUIRE((ld & 3) == 0 && ld >= ((cols + 3) & ~3) && aligned16(x),
+  // 4-element vector loads: a ragged width is fine as long as the (padded) row is long enough to read the last group
+  ST_REQUIRE((ld & 3) == 0 && ld >= ((cols + 3) & ~3) && (sizeof(T) == 2 ? aligned8(x) : aligned16(x)),
              "colsum: ld must be a multiple of 4 and >= cols rounded up to 4 (cols=%d ld=%lld)", cols, (long long)ld);
   dim3 grid((cols + 127) / 128, 1);
   int64_t ychunks = (rows + 63) / 64;
   const int64_t cap = (static_cast<int64_t>(num_sms()) * 8 + grid.x - 1) / grid.x;
   grid.y = static_cast<unsigned>(ychunks < cap ? ychunks : cap);
-  ProfScope prof(stream, PROF_COLSUM, 1.0 * rows * cols * 4);
-  ST_CHECK_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, stream, x, ld, rows, cols, out));
+  ProfScope prof(stream, PROF_COLSUM, 1.0 * rows * cols * sizeof(T));
+  ST_CHECK_CUDA(launch_pdl(colsum_kernel<T>, grid, dim3(256), 0, stream, x, ld, rows, cols, out));
   ST_CHECK_LAUNCH();
   return ST_OK;
+}
+
+// element-type conversion copy (2-D, strided; cols and leading dimensions multiples of 4)
+template <typename S, typename D>
+__global__ void __launch_bounds__(256)
+cast_kernel(const S* __restrict__ src, int64_t lds, D* __restrict__ dst, int64_t ldd, int64_t rows, int cols4, float scale) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t total = rows * cols4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols4;
+    const int c = static_cast<int>(i - r * cols4) * 4;
+    float4 v = ldv4(src + r * lds + c);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    stv4(dst + r * ldd + c, v);
+  }
+}
+template <typename S, typename D>
+__global__ void __launch_bounds__(256)
+cast_scalar_kernel(const S* __restrict__ src, int64_t lds, D* __restrict__ dst, int64_t ldd, int64_t rows, int cols, float scale) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    dst[r * ldd + c] = from_f32<D>(to_f32(src[r * lds + c]) * scale);
+  }
+}
+template <typename S, typename D>
+int cast_t(cudaStream_t stream, const S* src, int64_t lds, D* dst, int64_t ldd, int64_t rows, int cols, float scale) {
+  ProfScope prof(stream, PROF_ROUND, 1.0 * rows * cols * (sizeof(S) + sizeof(D)));
+  const bool vec = (cols & 3) == 0 && (lds & 3) == 0 && (ldd & 3) == 0 && (sizeof(S) == 2 ? aligned8(src) : aligned16(src)) &&
+                   (sizeof(D) == 2 ? aligned8(dst) : aligned16(dst));
+  if (vec) {
+    const int64_t total = rows * (cols / 4);
+    ST_CHECK_CUDA(launch_pdl(cast_kernel<S, D>, dim3(persistent_grid((total + 255) / 256, 16)), dim3(256), 0, stream, src, lds, dst, ldd,
+                             rows, cols / 4, scale));
+  } else {
+    const int64_t total = rows * cols;
+    ST_CHECK_CUDA(launch_pdl(cast_scalar_kernel<S, D>, dim3(persistent_grid((total + 255) / 256, 16)), dim3(256), 0, stream, src, lds,
+                             dst, ldd, rows, cols, scale));
+  }
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+}  // namespace
+
+int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, int cols, float* out) {
+  return colsum_add_t<float>(stream, x, ld, rows, cols, out);
+}
+int colsum_add_any(cudaStream_t stream, int dt, const void* x, int64_t ld, int64_t rows, int cols, float* out) {
+  switch (dt) {
+    case ST_DTYPE_F32: return colsum_add_t<float>(stream, static_cast<const float*>(x), ld, rows, cols, out);
+    case ST_DTYPE_F16: return colsum_add_t<__half>(stream, static_cast<const __half*>(x), ld, rows, cols, out);
+    case ST_DTYPE_BF16: return colsum_add_t<__nv_bfloat16>(stream, static_cast<const __nv_bfloat16*>(x), ld, rows, cols, out);
+  }
+  set_error("colsum: bad dtype %d", dt);
+  return ST_ERR_INVALID;
+}
+
+// dst = (dst type)(src * scale); one of the two types is fp32
+int cast_2d(cudaStream_t stream, const void* src, int src_dt, int64_t lds, void* dst, int dst_dt, int64_t ldd, int64_t rows, int cols,
+            float scale) {
+  if (rows == 0 || cols == 0) return ST_OK;
+  ST_REQUIRE(lds >= cols && ldd >= cols, "cast: leading dimensions (%lld, %lld) smaller than cols=%d", (long long)lds, (long long)ldd, cols);
+#define ST_CAST(S, D) return cast_t<S, D>(stream, static_cast<const S*>(src), lds, static_cast<D*>(dst), ldd, rows, cols, scale)
+  if (src_dt == ST_DTYPE_F32 && dst_dt == ST_DTYPE_F16) ST_CAST(float, __half);
+  if (src_dt == ST_DTYPE_F32 && dst_dt == ST_DTYPE_BF16) ST_CAST(float, __nv_bfloat16);
+  if (src_dt == ST_DTYPE_F16 && dst_dt == ST_DTYPE_F32) ST_CAST(__half, float);
+  if (src_dt == ST_DTYPE_BF16 && dst_dt == ST_DTYPE_F32) ST_CAST(__nv_bfloat16, float);
+  if (src_dt == ST_DTYPE_F32 && dst_dt == ST_DTYPE_F32) ST_CAST(float, float);
+#undef ST_CAST
+  set_error("cast: unsupported conversion %d -> %d", src_dt, dst_dt);
+  return ST_ERR_INVALID;
 }
 
 }  // namespace st

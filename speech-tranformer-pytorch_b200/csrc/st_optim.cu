@@ -43,13 +43,17 @@ struct AdamParams {
   int64_t n;
   float lr, b1, b2, eps, bc1, bc2_rsqrt, max_norm, gscale;
   const float* sumsq;
-  float* p_tf32;   // optional: TF32-rounded copy of the updated parameters (what the next step's GEMMs consume)
+  void* p_twin;    // optional: operand-precision copy of the updated parameters (what the next step's GEMMs consume)
+  int twin_dt;     // ST_DTYPE_F32: TF32-rounded fp32; ST_DTYPE_F16 / ST_DTYPE_BF16: 16-bit
 };
 
 __global__ void __launch_bounds__(256)
 adam_kernel(const AdamParams a) {
   // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (total_norm + 1e-6), max=1)
   float coef = a.gscale;
+  // a non-finite gradient norm (an overflowed fp16 activation gradient under loss scaling) skips the update altogether:
+  // parameters, moments and twins stay as they are (the caller reads norm_ws to notice and lowers its loss scale)
+  if (a.sumsq && !isfinite(*a.sumsq)) return;
   if (a.sumsq && a.max_norm > 0.f) {
     const float total = sqrtf(*a.sumsq) * a.gscale;
     coef *= fminf(a.max_norm / (total + 1e-6f), 1.f);
@@ -74,8 +78,14 @@ adam_kernel(const AdamParams a) {
       pp[t] -= step_size * mm[t] / (sqrtf(vv[t]) * a.bc2_rsqrt + a.eps);
     }
     reinterpret_cast<float4*>(a.p)[i] = p;
-    if (a.p_tf32)
-      reinterpret_cast<float4*>(a.p_tf32)[i] = make_float4(tf32_rna(pp[0]), tf32_rna(pp[1]), tf32_rna(pp[2]), tf32_rna(pp[3]));
+    if (a.p_twin) {
+      if (a.twin_dt == ST_DTYPE_F32)
+        reinterpret_cast<float4*>(a.p_twin)[i] = make_float4(tf32_rna(pp[0]), tf32_rna(pp[1]), tf32_rna(pp[2]), tf32_rna(pp[3]));
+      else if (a.twin_dt == ST_DTYPE_F16)
+        reinterpret_cast<uint2*>(a.p_twin)[i] = make_uint2(pack2<__half>(pp[0], pp[1]), pack2<__half>(pp[2], pp[3]));
+      else
+        reinterpret_cast<uint2*>(a.p_twin)[i] = make_uint2(pack2<__nv_bfloat16>(pp[0], pp[1]), pack2<__nv_bfloat16>(pp[2], pp[3]));
+    }
     reinterpret_cast<float4*>(a.m)[i] = m;
     reinterpret_cast<float4*>(a.v)[i] = v;
   }
@@ -95,7 +105,7 @@ int sumsq_add(cudaStream_t s, const float* x, int64_t n, float* out) {
 }
 
 int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
-              float eps, int step, float max_norm, float gscale, const float* sumsq, float* p_tf32) {
+              float eps, int step, float max_norm, float gscale, const float* sumsq, void* p_twin, int twin_dt) {
   if (n == 0) return ST_OK;
   ST_REQUIRE((n & 3) == 0, "adam_step: flat buffer length must be a multiple of 4 (pad it)");
   ST_REQUIRE(step >= 1, "adam_step: step must be >= 1");
@@ -104,10 +114,10 @@ int adam_step(cudaStream_t s, float* p, const float* g, float* m, float* v, int6
   a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps;
   a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), step));
   a.bc2_rsqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), step)));
-  a.max_norm = max_norm; a.gscale = gscale; a.sumsq = sumsq; a.p_tf32 = p_tf32;
+  a.max_norm = max_norm; a.gscale = gscale; a.sumsq = sumsq; a.p_twin = p_twin; a.twin_dt = twin_dt;
   const int64_t blocks = (n / 4 + 255) / 256;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
-  ProfScope prof(s, PROF_ADAM, (p_tf32 ? 8.0 : 7.0) * 4.0 * n);  // read p,g,m,v + write p,m,v (+ TF32 copy)
+  ProfScope prof(s, PROF_ADAM, (p_twin ? (twin_dt == ST_DTYPE_F32 ? 8.0 : 7.5) : 7.0) * 4.0 * n);  // read p,g,m,v + write p,m,v (+ TF32 copy)
   adam_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, s>>>(a);
   ST_CHECK_LAUNCH();
   return ST_OK;

@@ -206,7 +206,7 @@ class IncrementalDecoder:
         x = torch.empty(n, d, device=dev, dtype=torch.float32)
         # embedding row + positional encoding of position t (Models.py:84-87)
         check(lib.st_embed_fwd(_p(tokens.contiguous()), _p(self.emb), _p(self.pe[t:t + 1]), 1, _p(x), n, d, self.vocab, 1,
-                               F._stream()))
+                               0, F._stream()))
         new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
         for i, lw in enumerate(self.layers):
             H = lw.n_head

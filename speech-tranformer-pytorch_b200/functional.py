@@ -17,7 +17,12 @@ from ._lib import StError, check
 
 __all__ = ["add_layer_norm", "multi_head_attention", "positionwise_ffn", "label_smoothing_ce", "soft_target_ce",
            "attention_core", "linear_tf32", "round_tf32", "is_tf32_clean", "mark_tf32_clean", "next_seed",
-           "frontend", "linear", "embedding", "ctc_loss", "GradSink", "attach_grad_sink", "attach_tf32_twin"]
+           "frontend", "linear", "embedding", "ctc_loss", "GradSink", "attach_grad_sink", "attach_tf32_twin",
+           "LengthMask", "cast", "ACT_DTYPES"]
+
+# activation element types and their ST_DTYPE_* codes (include/st_b200.h).  fp32 tensors take the fp32 / TF32 path; fp16 and
+# bf16 tensors take the 16-bit path (tcgen05 kind::f16 operands, fp32 accumulation and statistics; d_k must be 64).
+ACT_DTYPES = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -39,6 +44,42 @@ def _need(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     if t.dtype != dtype:
         raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     return t
+
+
+def _need_act(t: torch.Tensor, name: str, like: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """An activation tensor: fp32, fp16 or bf16 on the device (the same type as `like` when given)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor — the B200 hot path has no CPU fallback")
+    if t.dtype not in ACT_DTYPES:
+        raise RuntimeError(f"{name}: expected dtype float32, float16 or bfloat16, got {t.dtype}")
+    if like is not None and t.dtype != like.dtype:
+        raise RuntimeError(f"{name}: expected dtype {like.dtype} like the other activations, got {t.dtype}")
+    return t
+
+
+class LengthMask:
+    """A key-padding (+ optional causal) mask given by its lengths instead of a (B, Lq, Lk) tensor: key j of batch b is
+    masked iff j >= k_len[b] (Utils.padding_info_mask, Utils.py:41-57) or, when `causal`, j > i (Utils.feature_info_mask,
+    Utils.py:60-70, ORed as in Models.py:89-94).  Pass it wherever the modules take `mask`: the kernels derive every
+    predicate from the lengths, no mask tensor is built or scanned.  dense() materialises the equivalent bool tensor."""
+    __slots__ = ("k_len", "len_q", "len_k", "causal")
+
+    def __init__(self, k_len: torch.Tensor, len_q: int, len_k: int, causal: bool = False):
+        if k_len.dtype != torch.int64 or k_len.dim() != 1:
+            raise RuntimeError("LengthMask: k_len must be a 1-D int64 tensor")
+        self.k_len, self.len_q, self.len_k, self.causal = k_len, int(len_q), int(len_k), bool(causal)
+
+    def size(self):
+        return torch.Size((self.k_len.shape[0], self.len_q, self.len_k))
+
+    def dense(self) -> torch.Tensor:
+        ar = torch.arange(self.len_k, device=self.k_len.device)
+        m = (ar.unsqueeze(0) >= self.k_len.unsqueeze(1)).unsqueeze(1).expand(-1, self.len_q, -1)
+        if self.causal:
+            m = m | torch.ones(self.len_q, self.len_k, dtype=torch.bool, device=m.device).triu(1).unsqueeze(0)
+        return m
 
 
 def _contig(t: torch.Tensor) -> torch.Tensor:
@@ -84,11 +125,14 @@ class GradSink:
     use of the same parameter within one step falls back to the ordinary accumulate path.  `zeroed` is set by the owner of
     the buffer (FlatParams.zero_grad) after it cleared the whole buffer in one pass: the backward operators then skip their
     own per-tensor clears (grads_zeroed in the st_*_bwd_args; ~200 memset nodes per training step otherwise)."""
-    __slots__ = ("view", "written", "zeroed", "uses", "done", "owner")
+    __slots__ = ("view", "written", "zeroed", "uses", "done", "owner", "no_accumulate")
 
     def __init__(self, view: torch.Tensor):
         self.view, self.written, self.zeroed = view, False, False
         self.owner = None      # callable(sinks) of the buffer's owner, told when backward operators have written slices
+        # set by an owner that all-reduces slices DURING backward: a second forward before zero_grad would then add local
+        # gradients on top of already-reduced sums (ranks diverge silently), so it is refused
+        self.no_accumulate = False
         # uses: forward operators that took this parameter since the last zero_grad; done: backward operators that have
         # since written its gradient directly (kernels enqueued).  done == uses >= 1 means the slice is final for this step
         # (stream order) — what parallel.DataParallelTrainer needs to start a bucket's all-reduce under the backward pass.
@@ -99,19 +143,30 @@ _SINK_ATTR = "_st_grad_sink"
 _TWIN_ATTR = "_st_tf32_twin"
 
 
+_stale_twin_warned = [False]
+
+
 def attach_tf32_twin(param: torch.Tensor, view: torch.Tensor) -> None:
-    """Register a caller-maintained TF32-rounded copy of `param` (parallel.FlatParams keeps it current from inside the
-    Adam kernel).  The copy is used only while the parameter's version counter is unchanged, so any PyTorch-side
-    in-place modification (load_state_dict, init, ...) silently falls back to rounding the weight per call."""
+    """Register a caller-maintained operand-precision copy of `param` — TF32-rounded fp32, or fp16 / bf16 for the 16-bit
+    path (parallel.FlatParams keeps it current from inside the Adam kernel).  The copy is used only while the
+    parameter's version counter is unchanged, so any PyTorch-side in-place modification (load_state_dict, init, ...)
+    falls back to rounding the weight per call (logged once: it is a performance cliff, not an error)."""
     setattr(param, _TWIN_ATTR, (view, param._version))
 
 
-def _twins_of(params):
-    """The params' TF32 twins if ALL of them have a current one, else None."""
+def _twins_of(params, dtype=torch.float32):
+    """The params' operand-precision twins of element type `dtype` if ALL of them have a current one, else None."""
     out = []
     for p in params:
         tw = getattr(p, _TWIN_ATTR, None)
-        if tw is None or tw[1] != p._version or tw[0].shape != p.shape:
+        if tw is None or tw[0].dtype != dtype or tw[0].shape != p.shape:
+            return None
+        if tw[1] != p._version:
+            if not _stale_twin_warned[0]:
+                _stale_twin_warned[0] = True
+                import warnings
+                warnings.warn("speech-tranformer-pytorch_b200: a parameter with a registered operand-precision twin was modified "
+                              "in place; its weights are rounded per call until FlatParams.refresh_rounded() is called")
             return None
         out.append(tw[0])
     return out
@@ -123,11 +178,20 @@ def attach_grad_sink(param: torch.Tensor, view: torch.Tensor) -> GradSink:
     return sink
 
 
-def _sinks_of(params):
-    """The params' sinks if ALL of them have an unwritten sink of the right shape, else None."""
+def _sinks_of(params, ctx=None):
+    """The params' sinks if ALL of them have an unwritten sink of the right shape, else None.  Called from an operator's
+    forward with its autograd context; a forward that will never see a backward (torch.no_grad(), eval / decode passes:
+    ctx.needs_input_grad is all False) takes no sinks and counts no use, so the use / done bookkeeping that
+    parallel.GradBuckets relies on stays balanced across ranks."""
+    if ctx is not None and not any(ctx.needs_input_grad):
+        return None
     found = [None if p is None else getattr(p, _SINK_ATTR, None) for p in params]
     for s in found:
         if s is not None:
+            if s.written and s.no_accumulate:
+                raise RuntimeError("gradient accumulation (a second forward/backward before zero_grad) is not supported while "
+                                   "the trainer all-reduces gradient buckets under the backward pass: construct "
+                                   "DataParallelTrainer(overlap=False) to accumulate")
             s.uses += 1
     out = []
     for p, s in zip(params, found):
@@ -183,6 +247,16 @@ def _same(a: torch.Tensor, b: torch.Tensor) -> bool:
     return a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride())
 
 
+def _split_mask(mask, B: int, Lq: int, Lk: int, device):
+    """(tensor mask or None, k_len or None, causal) from what a module received as `mask`."""
+    if isinstance(mask, LengthMask):
+        if tuple(mask.size()) != (B, Lq, Lk):
+            raise RuntimeError(f"mask: expected shape {(B, Lq, Lk)}, got {tuple(mask.size())}")
+        k_len = mask.k_len if mask.k_len.device == device else mask.k_len.to(device)
+        return None, _contig(k_len), int(mask.causal)
+    return mask, None, 0
+
+
 def _mask_args(mask: Optional[torch.Tensor], B: int, Lq: int, Lk: int, device) -> Tuple[Optional[torch.Tensor], int, int, int]:
     """Accept bool or uint8, any strides (stride-0 broadcast views are NOT materialised)."""
     if mask is None:
@@ -210,6 +284,19 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
     rows = x.numel() // max(cols, 1)
     check(lib.st_round_tf32(_p(x), cols, _p(out), cols, rows, cols, _stream()))
     return mark_tf32_clean(out)
+
+
+def cast(x: torch.Tensor, dtype, scale: float = 1.0) -> torch.Tensor:
+    """x converted to `dtype` (fp32 <-> fp16 / bf16) by the library's conversion kernel, optionally scaled (no autograd)."""
+    x = _contig(_need_act(x, "x"))
+    if dtype not in ACT_DTYPES:
+        raise RuntimeError(f"cast: dtype must be float32, float16 or bfloat16, got {dtype}")
+    lib = _lib_for(x)
+    out = torch.empty_like(x, dtype=dtype)
+    cols = x.shape[-1] if x.dim() else 1
+    rows = x.numel() // max(cols, 1)
+    check(lib.st_cast(_p(x), ACT_DTYPES[x.dtype], cols, _p(out), ACT_DTYPES[dtype], cols, rows, cols, float(scale), _stream()))
+    return out
 
 
 def linear_tf32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False
@@ -285,24 +372,30 @@ class _AttentionCore(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, mask, n_head, dropout_p, seed, need_attn):
         ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
-        q, k, v = (_contig(_need(t, n)) for t, n in ((q, "q"), (k, "k"), (v, "v")))
+        q = _contig(_need_act(q, "q"))
+        k, v = _contig(_need_act(k, "k", q)), _contig(_need_act(v, "v", q))
         lib = _lib_for(q)
+        dt = ACT_DTYPES[q.dtype]
         B, Lq, d = q.shape
         Lk = k.shape[1]
         dk = d // n_head
+        mask, k_len, causal = _split_mask(mask, B, Lq, Lk, q.device)
         mask_t, sb, sq, sk = _mask_args(mask, B, Lq, Lk, q.device)
-        qr = q if is_tf32_clean(q) else round_tf32(q)
-        kr = qr if _same(k, q) else (k if is_tf32_clean(k) else round_tf32(k))
-        vr = kr if _same(v, k) else (v if is_tf32_clean(v) else round_tf32(v))
-        out = torch.empty(B, Lq, d, device=q.device, dtype=torch.float32)
+        if dt == _lib.DTYPE_F32:
+            qr = q if is_tf32_clean(q) else round_tf32(q)
+            kr = qr if _same(k, q) else (k if is_tf32_clean(k) else round_tf32(k))
+            vr = kr if _same(v, k) else (v if is_tf32_clean(v) else round_tf32(v))
+        else:
+            qr, kr, vr = q, k, v
+        out = torch.empty(B, Lq, d, device=q.device, dtype=q.dtype)
         lse = torch.empty(B, n_head, Lq, device=q.device, dtype=torch.float32)
         attn = torch.empty(B, n_head, Lq, Lk, device=q.device, dtype=torch.float32) if need_attn else None
         a = _lib.AttnArgs(B=B, H=n_head, Lq=Lq, Lk=Lk, dk=dk, q=_p(qr), ldq=d, k=_p(kr), ldk=d, v=_p(vr), ldv=d,
                           mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, dropout_p=float(dropout_p), seed=int(seed),
-                          ctx=_p(out), ldctx=d, lse=_p(lse), attn=_p(attn))
+                          ctx=_p(out), ldctx=d, lse=_p(lse), attn=_p(attn), dtype=dt, k_len=_p(k_len), causal=causal)
         check(lib.st_attn_fwd(C.byref(a), _stream()))
-        ctx.save_for_backward(qr, kr, vr, out, lse, mask_t)
-        ctx.cfg = (B, n_head, Lq, Lk, dk, float(dropout_p), int(seed))
+        ctx.save_for_backward(qr, kr, vr, out, lse, mask_t, k_len)
+        ctx.cfg = (B, n_head, Lq, Lk, dk, float(dropout_p), int(seed), dt, causal)
         ctx.mark_non_differentiable(*([attn] if attn is not None else []))
         return out, attn
 
@@ -310,11 +403,11 @@ class _AttentionCore(torch.autograd.Function):
     def backward(ctx, dout, _dattn):
         if dout is None:      # only the auxiliary output was used downstream: no gradient flows
             return (None,) * 8
-        qr, kr, vr, out, lse, mask_t = ctx.saved_tensors
-        B, H, Lq, Lk, dk, p, seed = ctx.cfg
+        qr, kr, vr, out, lse, mask_t, k_len = ctx.saved_tensors
+        B, H, Lq, Lk, dk, p, seed, dt, causal = ctx.cfg
         d = H * dk
         lib = _lib_for(qr)
-        dor = round_tf32(_contig(dout))
+        dor = round_tf32(_contig(dout)) if dt == _lib.DTYPE_F32 else _contig(_need_act(dout, "grad_output", qr))
         _, sb, sq, sk = _mask_args(mask_t, B, Lq, Lk, qr.device)
         dq = torch.empty_like(qr)
         dkk = torch.empty_like(kr)
@@ -322,7 +415,7 @@ class _AttentionCore(torch.autograd.Function):
         delta = torch.empty(B, H, Lq, device=qr.device, dtype=torch.float32)
         f = _lib.AttnArgs(B=B, H=H, Lq=Lq, Lk=Lk, dk=dk, q=_p(qr), ldq=d, k=_p(kr), ldk=d, v=_p(vr), ldv=d,
                           mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, dropout_p=p, seed=seed,
-                          ctx=_p(out), ldctx=d, lse=_p(lse), attn=None)
+                          ctx=_p(out), ldctx=d, lse=_p(lse), attn=None, dtype=dt, k_len=_p(k_len), causal=causal)
         a = _lib.AttnBwdArgs(f=f, dctx=_p(dor), lddctx=d, delta=_p(delta), dq=_p(dq), lddq=d, dk=_p(dkk), lddk=d,
                              dv=_p(dv), lddv=d)
         check(lib.st_attn_bwd(C.byref(a), _stream()))
@@ -343,12 +436,14 @@ class _MultiHeadAttention(torch.autograd.Function):
     def forward(ctx, q, k, v, mask, wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b, n_head, residual, eps, dropout_p,
                 seed, need_attn, round_out):
         ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
-        q, k, v = (_need(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v")))
+        q = _need_act(q, "q")
+        k, v = _need_act(k, "k", q), _need_act(v, "v", q)
         same_qk, same_kv = _same(q, k), _same(k, v)
         qc = _contig(q)
         kc = qc if same_qk else _contig(k)
         vc = kc if same_kv else _contig(v)
         lib = _lib_for(qc)
+        dt = ACT_DTYPES[qc.dtype]
         if qc.dim() != 3 or kc.dim() != 3 or vc.dim() != 3:
             raise RuntimeError("multi_head_attention: q, k, v must be (batch, length, d_model)")
         B, Lq, d = qc.shape
@@ -361,31 +456,33 @@ class _MultiHeadAttention(torch.autograd.Function):
             # the reference's `output + v` (Attention.py:94) fails the same way when len_q != len_k
             raise RuntimeError(f"The size of tensor a ({Lq}) must match the size of tensor b ({res.shape[1]}) at "
                                "non-singleton dimension 1 (residual='v' with len_q != len_k; use residual='q')")
+        mask, k_len, causal = _split_mask(mask, B, Lq, Lk, qc.device)
         mask_t, sb, sq, sk = _mask_args(mask, B, Lq, Lk, qc.device)
         params = [_contig(_need(t, "parameter")) for t in (wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b)]
-        inputs_tf32 = int(is_tf32_clean(q) and is_tf32_clean(k) and is_tf32_clean(v))
+        inputs_tf32 = int(dt != _lib.DTYPE_F32 or (is_tf32_clean(q) and is_tf32_clean(k) and is_tf32_clean(v)))
         same_qkv = int(same_qk and same_kv and Lq == Lk)
-        n_saved = lib.st_mha_saved_floats(B, Lq, Lk, n_head, d, same_qkv, int(same_kv), inputs_tf32)
+        n_saved = lib.st_mha_saved_floats_dt(dt, B, Lq, Lk, n_head, d, same_qkv, int(same_kv), inputs_tf32)
         saved = torch.empty(n_saved, device=qc.device, dtype=torch.float32)
-        out = torch.empty(B, Lq, d, device=qc.device, dtype=torch.float32)
+        out = torch.empty(B, Lq, d, device=qc.device, dtype=qc.dtype)
         attn = torch.empty(B, n_head, Lq, Lk, device=qc.device, dtype=torch.float32) if need_attn else None
-        twins = _twins_of((wq, wk, wv, wo)) or [None] * 4
+        twins = _twins_of((wq, wk, wv, wo), qc.dtype) or [None] * 4
         a = _lib.MhaArgs(B=B, Lq=Lq, Lk=Lk, H=n_head, d_model=d, dk=dk, q_in=_p(qc), k_in=_p(kc), v_in=_p(vc),
                          residual=_p(res), wq=_p(params[0]), bq=_p(params[1]), wk=_p(params[2]), bk=_p(params[3]),
                          wv=_p(params[4]), bv=_p(params[5]), wo=_p(params[6]), bo=_p(params[7]), ln_g=_p(params[8]),
                          ln_b=_p(params[9]), mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, eps=float(eps),
                          dropout_p=float(dropout_p), seed=int(seed), inputs_tf32=inputs_tf32, round_out=int(round_out),
                          out=_p(out), attn=_p(attn), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0,
-                         wq_tf32=_p(twins[0]), wk_tf32=_p(twins[1]), wv_tf32=_p(twins[2]), wo_tf32=_p(twins[3]))
+                         wq_tf32=_p(twins[0]), wk_tf32=_p(twins[1]), wv_tf32=_p(twins[2]), wo_tf32=_p(twins[3]),
+                         dtype=dt, k_len=_p(k_len), causal=causal)
         check(lib.st_mha_fwd(C.byref(a), _stream()))
         ctx.twins = twins          # backward must present the same weight copies the forward used
-        ctx.save_for_backward(qc, kc, vc, mask_t, saved, *params)
-        ctx.sinks = _sinks_of((wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b))
+        ctx.save_for_backward(qc, kc, vc, mask_t, k_len, saved, *params)
+        ctx.sinks = _sinks_of((wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b), ctx)
         ctx.cfg = (B, Lq, Lk, n_head, d, dk, residual, float(eps), float(dropout_p), int(seed), inputs_tf32,
-                   same_qk, same_kv)
+                   same_qk, same_kv, dt, causal)
         if attn is not None:
             ctx.mark_non_differentiable(attn)
-        if round_out:
+        if round_out and dt == _lib.DTYPE_F32:
             mark_tf32_clean(out)
         return out, attn
 
@@ -393,14 +490,14 @@ class _MultiHeadAttention(torch.autograd.Function):
     def backward(ctx, dout, _dattn):
         if dout is None:      # only the auxiliary output was used downstream: no gradient flows
             return (None,) * 21
-        qc, kc, vc, mask_t, saved, *params = ctx.saved_tensors
-        B, Lq, Lk, H, d, dk, residual, eps, p, seed, inputs_tf32, same_qk, same_kv = ctx.cfg
+        qc, kc, vc, mask_t, k_len, saved, *params = ctx.saved_tensors
+        B, Lq, Lk, H, d, dk, residual, eps, p, seed, inputs_tf32, same_qk, same_kv, dt, causal = ctx.cfg
         lib = _lib_for(qc)
-        dout = _contig(dout)
+        dout = _contig(_need_act(dout, "grad_output", qc))
         dev = qc.device
         _, sb, sq, sk = _mask_args(mask_t, B, Lq, Lk, dev)
         res = vc if residual == "v" else qc
-        n_ws = lib.st_mha_ws_floats(B, Lq, Lk, H, d)
+        n_ws = lib.st_mha_ws_floats_dt(dt, B, Lq, Lk, H, d)
         ws = torch.empty(n_ws, device=dev, dtype=torch.float32)
         same_qkv = same_qk and same_kv
         dq_in = torch.empty_like(qc)
@@ -421,7 +518,8 @@ class _MultiHeadAttention(torch.autograd.Function):
                          ln_b=_p(params[9]), mask=_p(mask_t), ms_b=sb, ms_q=sq, ms_k=sk, eps=eps, dropout_p=p,
                          seed=seed, inputs_tf32=inputs_tf32, round_out=0, out=None, attn=None, saved=_p(saved),
                          saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws, wq_tf32=_p(ctx.twins[0]),
-                         wk_tf32=_p(ctx.twins[1]), wv_tf32=_p(ctx.twins[2]), wo_tf32=_p(ctx.twins[3]))
+                         wk_tf32=_p(ctx.twins[1]), wv_tf32=_p(ctx.twins[2]), wo_tf32=_p(ctx.twins[3]),
+                         dtype=dt, k_len=_p(k_len), causal=causal)
         a = _lib.MhaBwdArgs(f=f, dout=_p(dout), dq_in=_p(dq_in), dk_in=_p(dk_in), dv_in=_p(dv_in), dresidual=None,
                             dwq=_p(grads[0]), dbq=_p(grads[1]), dwk=_p(grads[2]), dbk=_p(grads[3]), dwv=_p(grads[4]),
                             dbv=_p(grads[5]), dwo=_p(grads[6]), dbo=_p(grads[7]), dln_g=_p(grads[8]),
@@ -454,31 +552,35 @@ class _PositionwiseFFN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, ln_g, ln_b, eps, dropout_p, seed, round_out):
         ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
-        x_clean = int(is_tf32_clean(x))
-        xc = _contig(_need(x, "inputs"))
+        xc = _contig(_need_act(x, "inputs"))
+        dt = ACT_DTYPES[xc.dtype]
+        x_clean = int(dt != _lib.DTYPE_F32 or is_tf32_clean(x))
         lib = _lib_for(xc)
         d = xc.shape[-1]
         rows = xc.numel() // d
         params = [_contig(_need(t, "parameter")) for t in (w1, b1, w2, b2, ln_g, ln_b)]
         d_ff = params[0].shape[0]
-        n_saved = lib.st_ffn_saved_floats(rows, d, d_ff, x_clean)
+        n_saved = lib.st_ffn_saved_floats_dt(dt, rows, d, d_ff, x_clean)
         saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
         out = torch.empty_like(xc)
-        twins = _twins_of((w1, w2)) or [None] * 2
+        twins = _twins_of((w1, w2), xc.dtype) or [None] * 2
         a = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(xc), w1=_p(params[0]), b1=_p(params[1]),
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=float(eps),
                          dropout_p=float(dropout_p), seed=int(seed), x_is_tf32=x_clean, round_out=int(round_out),
                          out=_p(out), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0,
-                         w1_tf32=_p(twins[0]), w2_tf32=_p(twins[1]))
+                         w1_tf32=_p(twins[0]), w2_tf32=_p(twins[1]), dtype=dt)
         check(lib.st_ffn_fwd(C.byref(a), _stream()))
         ctx.twins = twins
         ctx.save_for_backward(xc, saved, *params)
-        ctx.sinks = _sinks_of((w1, b1, w2, b2, ln_g, ln_b))
-        ctx.cfg = (rows, d, d_ff, float(eps), float(dropout_p), int(seed), x_clean)
-        if round_out:
+        ctx.sinks = _sinks_of((w1, b1, w2, b2, ln_g, ln_b), ctx)
+        ctx.cfg = (rows, d, d_ff, float(eps), float(dropout_p), int(seed), x_clean, dt)
+        if round_out and dt == _lib.DTYPE_F32:
             mark_tf32_clean(out)
-        off = lib.st_ffn_hidden_offset(rows, d, d_ff, x_clean)
-        hidden = saved[off:off + rows * d_ff].view(*xc.shape[:-1], d_ff)
+        off = lib.st_ffn_hidden_offset(rows, d, d_ff, x_clean)   # the hidden activation is the first saved tensor
+        if dt == _lib.DTYPE_F32:
+            hidden = saved[off:off + rows * d_ff].view(*xc.shape[:-1], d_ff)
+        else:
+            hidden = saved.view(xc.dtype)[2 * off:2 * off + rows * d_ff].view(*xc.shape[:-1], d_ff)
         ctx.mark_non_differentiable(hidden)
         return out, hidden
 
@@ -487,10 +589,10 @@ class _PositionwiseFFN(torch.autograd.Function):
         if dout is None:      # only the auxiliary output was used downstream: no gradient flows
             return (None,) * 11
         xc, saved, *params = ctx.saved_tensors
-        rows, d, d_ff, eps, p, seed, x_clean = ctx.cfg
+        rows, d, d_ff, eps, p, seed, x_clean, dt = ctx.cfg
         lib = _lib_for(xc)
-        dout = _contig(dout)
-        n_ws = lib.st_ffn_ws_floats(rows, d, d_ff)
+        dout = _contig(_need_act(dout, "grad_output", xc))
+        n_ws = lib.st_ffn_ws_floats_dt(dt, rows, d, d_ff)
         ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
         dx = torch.empty_like(xc)
         direct, zeroed = _claim(ctx.sinks)
@@ -499,7 +601,7 @@ class _PositionwiseFFN(torch.autograd.Function):
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=eps,
                          dropout_p=p, seed=seed, x_is_tf32=x_clean, round_out=0, out=None, saved=_p(saved),
                          saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws, w1_tf32=_p(ctx.twins[0]),
-                         w2_tf32=_p(ctx.twins[1]))
+                         w2_tf32=_p(ctx.twins[1]), dtype=dt)
         a = _lib.FfnBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw1=_p(grads[0]), db1=_p(grads[1]), dw2=_p(grads[2]),
                             db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]), grads_zeroed=zeroed)
         check(lib.st_ffn_bwd(C.byref(a), _stream()))
@@ -591,11 +693,14 @@ def soft_target_ce(logits, q, weight, size_average: bool = True):
 # ------------------------------------------------------------------------------------------------
 class _Frontend(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, ln_g, ln_b, pe, eps, dropout_p, seed, round_out):
+    def forward(ctx, x, w, b, ln_g, ln_b, pe, eps, dropout_p, seed, round_out, out_dtype):
         ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
         xc = _contig(_need(x, "inputs"))
         if xc.dim() != 3:
             raise RuntimeError("frontend: inputs must be (batch, frames, feature_dim)")
+        if out_dtype not in ACT_DTYPES:
+            raise RuntimeError(f"frontend: out_dtype must be float32, float16 or bfloat16, got {out_dtype}")
+        dt = ACT_DTYPES[out_dtype]
         lib = _lib_for(xc)
         B, T, k = xc.shape
         params = [_contig(_need(t, "parameter")) for t in (w, b, ln_g, ln_b)]
@@ -609,16 +714,16 @@ class _Frontend(torch.autograd.Function):
         rows = B * T
         n_saved = lib.st_frontend_saved_floats(rows, k, d)
         saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
-        out = torch.empty(B, T, d, device=xc.device, dtype=torch.float32)
+        out = torch.empty(B, T, d, device=xc.device, dtype=out_dtype)
         a = _lib.FrontendArgs(rows=rows, T=T, in_dim=k, d_model=d, x=_p(xc), w=_p(params[0]), b=_p(params[1]),
                               ln_g=_p(params[2]), ln_b=_p(params[3]), pe=_p(pe), eps=float(eps),
                               dropout_p=float(dropout_p), seed=int(seed), round_out=int(round_out), out=_p(out),
-                              saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
+                              saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0, dtype=dt)
         check(lib.st_frontend_fwd(C.byref(a), _stream()))
         ctx.save_for_backward(xc, saved, pe, *params)
-        ctx.sinks = _sinks_of((w, b, ln_g, ln_b))
-        ctx.cfg = (rows, T, k, d, float(eps), float(dropout_p), int(seed))
-        if round_out:
+        ctx.sinks = _sinks_of((w, b, ln_g, ln_b), ctx)
+        ctx.cfg = (rows, T, k, d, float(eps), float(dropout_p), int(seed), dt)
+        if round_out and dt == _lib.DTYPE_F32:
             mark_tf32_clean(out)
         off = lib.st_frontend_hidden_offset(rows, k, d)
         hidden = saved[off:off + rows * d].view(B, T, d)
@@ -628,11 +733,13 @@ class _Frontend(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dhidden):
         if dout is None:      # only the auxiliary output was used downstream: no gradient flows
-            return (None,) * 10
+            return (None,) * 11
         xc, saved, pe, *params = ctx.saved_tensors
-        rows, T, k, d, eps, p, seed = ctx.cfg
+        rows, T, k, d, eps, p, seed, dt = ctx.cfg
         lib = _lib_for(xc)
         dout = _contig(dout)
+        if ACT_DTYPES.get(dout.dtype) != dt:
+            raise RuntimeError(f"frontend backward: gradient dtype {dout.dtype} does not match the forward output")
         n_ws = lib.st_frontend_ws_floats(rows, k, d)
         ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
         dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
@@ -641,29 +748,32 @@ class _Frontend(torch.autograd.Function):
         f = _lib.FrontendArgs(rows=rows, T=T, in_dim=k, d_model=d, x=_p(xc), w=_p(params[0]), b=_p(params[1]),
                               ln_g=_p(params[2]), ln_b=_p(params[3]), pe=_p(pe), eps=eps, dropout_p=p, seed=seed,
                               round_out=0, out=None, saved=_p(saved), saved_floats=saved.numel(), ws=_p(ws),
-                              ws_floats=n_ws)
+                              ws_floats=n_ws, dtype=dt)
         a = _lib.FrontendBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw=_p(grads[0]), db=_p(grads[1]), dln_g=_p(grads[2]),
                                  dln_b=_p(grads[3]), grads_zeroed=zeroed)
         check(lib.st_frontend_bwd(C.byref(a), _stream()))
         _notify(ctx.sinks, direct)
         if direct is not None:
             grads = [None] * 4
-        return (dx, *grads, None, None, None, None, None)
+        return (dx, *grads, None, None, None, None, None, None)
 
 
 def frontend(x, w, b, ln_g, ln_b, pe=None, eps: float = 1e-6, dropout_p: float = 0.0, seed: int = 0,
-             round_out: bool = None, return_hidden: bool = False):
+             round_out: bool = None, return_hidden: bool = False, out_dtype=torch.float32):
     """Encoder input front-end, Models.py:28-33,42-44: LayerNorm(Dropout(ReLU(Linear(x)))) + pe[:T] as one operator.
-    return_hidden additionally returns Dropout(ReLU(Linear(x))) (non-differentiable test hook, cf. positionwise_ffn)."""
-    out, hidden = _Frontend.apply(x, w, b, ln_g, ln_b, pe, eps, dropout_p, seed, ROUND_OUT if round_out is None else round_out)
+    return_hidden additionally returns Dropout(ReLU(Linear(x))) (non-differentiable test hook, cf. positionwise_ffn).
+    out_dtype: element type of the result (the activation type of the layers that follow); x stays fp32."""
+    out, hidden = _Frontend.apply(x, w, b, ln_g, ln_b, pe, eps, dropout_p, seed, ROUND_OUT if round_out is None else round_out,
+                                  out_dtype)
     return (out, hidden) if return_hidden else out
 
 
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
-        x_clean = int(is_tf32_clean(x))
-        xc = _contig(_need(x, "input"))
+        xc = _contig(_need_act(x, "input"))
+        dt = ACT_DTYPES[xc.dtype]
+        x_clean = int(dt != _lib.DTYPE_F32 or is_tf32_clean(x))
         lib = _lib_for(xc)
         k = xc.shape[-1]
         rows = xc.numel() // k
@@ -673,27 +783,27 @@ class _Linear(torch.autograd.Function):
         if wc.shape != (n, k):
             raise RuntimeError(f"linear: weight {tuple(wc.shape)} does not match input features {k}")
         ldy = (n + 3) // 4 * 4
-        n_saved = lib.st_linear_saved_floats(rows, k, n, x_clean)
+        n_saved = lib.st_linear_saved_floats_dt(dt, rows, k, n, x_clean)
         saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
         y = torch.empty(rows, ldy, device=xc.device, dtype=torch.float32)
         a = _lib.LinearArgs(rows=rows, in_dim=k, out_dim=n, x=_p(xc), x_is_tf32=x_clean, w=_p(wc), b=_p(bc), y=_p(y),
-                            ldy=ldy, saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0)
+                            ldy=ldy, saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0, dtype=dt)
         check(lib.st_linear_fwd(C.byref(a), _stream()))
         ctx.save_for_backward(xc, saved, wc, bc)
-        ctx.sinks = _sinks_of((w, b)) if b is not None else _sinks_of((w,))
-        ctx.cfg = (rows, k, n, x_clean)
+        ctx.sinks = _sinks_of((w, b), ctx) if b is not None else _sinks_of((w,), ctx)
+        ctx.cfg = (rows, k, n, x_clean, dt)
         return y[:, :n].view(*xc.shape[:-1], n)        # a row-padded view when n % 4 != 0 (V = 4337)
 
     @staticmethod
     def backward(ctx, dy):
         xc, saved, wc, bc = ctx.saved_tensors
-        rows, k, n, x_clean = ctx.cfg
+        rows, k, n, x_clean, dt = ctx.cfg
         lib = _lib_for(xc)
-        dy2 = dy.reshape(rows, n)
+        dy2 = _need(dy, "grad_output").reshape(rows, n)
         if dy2.stride(1) != 1 or (rows > 1 and dy2.stride(0) < n):
             dy2 = dy2.contiguous()
         lddy = dy2.stride(0) if rows > 1 else n
-        n_ws = lib.st_linear_ws_floats(rows, k, n)
+        n_ws = lib.st_linear_ws_floats_dt(dt, rows, k, n)
         ws = torch.empty(n_ws, device=xc.device, dtype=torch.float32)
         dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
         direct, zeroed = _claim(ctx.sinks)
@@ -703,7 +813,7 @@ class _Linear(torch.autograd.Function):
             dw = torch.empty_like(wc) if ctx.needs_input_grad[1] else None
             db = torch.empty_like(bc) if (bc is not None and ctx.needs_input_grad[2]) else None
         f = _lib.LinearArgs(rows=rows, in_dim=k, out_dim=n, x=_p(xc), x_is_tf32=x_clean, w=_p(wc), b=_p(bc), y=None, ldy=n,
-                            saved=_p(saved), saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws)
+                            saved=_p(saved), saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws, dtype=dt)
         a = _lib.LinearBwdArgs(f=f, dy=_p(dy2), lddy=lddy, dx=_p(dx), dw=_p(dw), db=_p(db), grads_zeroed=zeroed)
         check(lib.st_linear_bwd(C.byref(a), _stream()))
         _notify(ctx.sinks, direct)
@@ -713,13 +823,17 @@ class _Linear(torch.autograd.Function):
 
 
 def linear(x, weight, bias=None):
-    """y = x @ weight.T + bias (nn.Linear, e.g. tgt_word_proj Models.py:145,151) on the tcgen05 TF32 GEMM, with autograd."""
+    """y = x @ weight.T + bias (nn.Linear, e.g. tgt_word_proj Models.py:145,151) on the tcgen05 GEMM, with autograd.
+    x may be fp32 (TF32 operands) or fp16 / bf16; y (the logits) is always fp32."""
     return _Linear.apply(x, weight, bias)
 
 
 class _Embedding(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, idx, table, pe, padding_idx, round_out):
+    def forward(ctx, idx, table, pe, padding_idx, round_out, out_dtype):
+        if out_dtype not in ACT_DTYPES:
+            raise RuntimeError(f"embedding: out_dtype must be float32, float16 or bfloat16, got {out_dtype}")
+        dt = ACT_DTYPES[out_dtype]
         idx = _contig(_need(idx, "indices", torch.int64))
         table = _contig(_need(table, "embedding weight"))
         lib = _lib_for(table)
@@ -731,32 +845,35 @@ class _Embedding(torch.autograd.Function):
             pe = _contig(_need(pe, "pe"))
             if pe.shape[-1] != d or pe.numel() // d < L:
                 raise RuntimeError(f"embedding: positional table {tuple(pe.shape)} too small for L={L}, d={d}")
-        out = torch.empty(B, L, d, device=table.device, dtype=torch.float32)
-        check(lib.st_embed_fwd(_p(idx), _p(table), _p(pe), L, _p(out), B * L, d, vocab, int(round_out), _stream()))
+        out = torch.empty(B, L, d, device=table.device, dtype=out_dtype)
+        check(lib.st_embed_fwd(_p(idx), _p(table), _p(pe), L, _p(out), B * L, d, vocab, int(round_out), dt, _stream()))
         ctx.save_for_backward(idx)
-        ctx.sinks = _sinks_of((table,))
-        ctx.cfg = (vocab, d, int(padding_idx))
-        if round_out:
+        ctx.sinks = _sinks_of((table,), ctx)
+        ctx.cfg = (vocab, d, int(padding_idx), dt)
+        if round_out and dt == _lib.DTYPE_F32:
             mark_tf32_clean(out)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (idx,) = ctx.saved_tensors
-        vocab, d, padding_idx = ctx.cfg
+        vocab, d, padding_idx, dt = ctx.cfg
         dout = _contig(dout)
+        if ACT_DTYPES.get(dout.dtype) != dt:
+            raise RuntimeError(f"embedding backward: gradient dtype {dout.dtype} does not match the forward output")
         lib = _lib_for(dout)
         direct, zeroed = _claim(ctx.sinks)
         dtable = direct[0] if direct is not None else torch.empty(vocab, d, device=dout.device, dtype=torch.float32)
-        check(lib.st_embed_bwd(_p(idx), _p(dout), _p(dtable), idx.numel(), d, vocab, padding_idx, 0 if zeroed else 1,
+        check(lib.st_embed_bwd(_p(idx), _p(dout), _p(dtable), idx.numel(), d, vocab, padding_idx, 0 if zeroed else 1, dt,
                                _stream()))
         _notify(ctx.sinks, direct)
-        return None, (None if direct is not None else dtable), None, None, None
+        return None, (None if direct is not None else dtable), None, None, None, None
 
 
-def embedding(idx, table, pe=None, padding_idx: int = -1, round_out: bool = None):
-    """table[idx] + pe[:L] (Models.py:84-87); the padding row receives no gradient (nn.Embedding padding_idx)."""
-    return _Embedding.apply(idx, table, pe, padding_idx, ROUND_OUT if round_out is None else round_out)
+def embedding(idx, table, pe=None, padding_idx: int = -1, round_out: bool = None, out_dtype=torch.float32):
+    """table[idx] + pe[:L] (Models.py:84-87); the padding row receives no gradient (nn.Embedding padding_idx).
+    out_dtype: element type of the result (the activation type of the layers that follow); the table stays fp32."""
+    return _Embedding.apply(idx, table, pe, padding_idx, ROUND_OUT if round_out is None else round_out, out_dtype)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -24,6 +24,9 @@ from .transformer.SubLayers import PositionwiseFeedForward
 
 PAD = 0  # transformer/Constants.py:1
 
+COMPUTE_DTYPES = {"tf32": torch.float32, "fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16,
+                  torch.float32: torch.float32, torch.float16: torch.float16, torch.bfloat16: torch.bfloat16}
+
 
 # ------------------------------------------------------------------------------------------------ masks (device side)
 def key_padding_mask(k_lengths: torch.Tensor, len_q: int, len_k: int) -> torch.Tensor:
@@ -85,8 +88,9 @@ class PositionalEncoding(nn.Module):
 # ------------------------------------------------------------------------------------------------ Models.py
 class Encoder(nn.Module):
     def __init__(self, input_size, n_max_seq, n_layers=6, n_head=8, d_k=64, d_v=64, d_model=512, d_inner_hid=1024,
-                 dropout=0.1, emb_scale=1):
+                 dropout=0.1, emb_scale=1, compute_dtype=torch.float32, length_masks=True):
         super(Encoder, self).__init__()
+        self.compute_dtype, self.length_masks = compute_dtype, length_masks
         self.n_max_seq = n_max_seq
         self.d_model = d_model
         self.emb_scale = emb_scale
@@ -102,9 +106,10 @@ class Encoder(nn.Module):
         p = drop.p if self.training else 0.0
         enc_output, hidden = F.frontend(inputs, lin.weight, lin.bias, ln.weight, ln.bias, self.position_enc(T)[0],
                                         eps=ln.eps, dropout_p=p, seed=F.next_seed() if p > 0 else 0,
-                                        return_hidden=True)                           # Models.py:28-33,42-44
+                                        return_hidden=True, out_dtype=self.compute_dtype)   # Models.py:28-33,42-44
         self.last_hidden = hidden if getattr(self, "keep_hidden", False) else None    # test hook (ReLU gate pattern)
-        mask = key_padding_mask(inputs_length, T, T)                                # Models.py:46
+        # Models.py:46 — as lengths (the kernels derive the predicate; no mask tensor) or as the reference's mask tensor
+        mask = F.LengthMask(inputs_length, T, T) if self.length_masks else key_padding_mask(inputs_length, T, T)
         attns = []
         for layer in self.layer_stack:
             layer.slf_attn.return_attention = bool(return_attns)
@@ -116,8 +121,9 @@ class Encoder(nn.Module):
 
 class Decoder(nn.Module):
     def __init__(self, vocab_size, n_max_seq, n_layers=6, n_head=8, d_k=64, d_v=64, d_model=512, d_inner_hid=1024,
-                 dropout=0.1, emb_scale=1):
+                 dropout=0.1, emb_scale=1, compute_dtype=torch.float32, length_masks=True):
         super(Decoder, self).__init__()
+        self.compute_dtype, self.length_masks = compute_dtype, length_masks
         self.n_max_seq = n_max_seq
         self.output_dim = vocab_size
         self.d_model = d_model
@@ -130,10 +136,14 @@ class Decoder(nn.Module):
     def forward(self, outputs_data, outputs_pos, input_pos, enc_output, return_attns=False):
         B, L = outputs_data.shape
         T = enc_output.size(1)
-        dec_output = F.embedding(outputs_data, self.tgt_word_emb.weight, self.position_enc(L)[0],
-                                 padding_idx=PAD)                                     # Models.py:84-87 (as intended)
-        slf_mask = key_padding_mask(outputs_pos, L, L) | subsequent_mask(B, L, outputs_data.device)   # :89-94
-        enc_mask = key_padding_mask(input_pos, L, T)                                 # :96-97
+        dec_output = F.embedding(outputs_data, self.tgt_word_emb.weight, self.position_enc(L)[0], padding_idx=PAD,
+                                 out_dtype=self.compute_dtype)                        # Models.py:84-87 (as intended)
+        if self.length_masks:   # Models.py:89-97 from the length vectors alone
+            slf_mask = F.LengthMask(outputs_pos, L, L, causal=True)
+            enc_mask = F.LengthMask(input_pos, L, T)
+        else:
+            slf_mask = key_padding_mask(outputs_pos, L, L) | subsequent_mask(B, L, outputs_data.device)   # :89-94
+            enc_mask = key_padding_mask(input_pos, L, T)                                 # :96-97
         slf_attns, enc_attns = [], []
         for layer in self.layer_stack:
             layer.slf_attn.return_attention = layer.enc_attn.return_attention = bool(return_attns)
@@ -150,8 +160,13 @@ class Transformer(nn.Module):
     def __init__(self, config):
         super(Transformer, self).__init__()
         self.return_attns = bool(getattr(config, "return_attns", False))
+        # compute_dtype: "tf32" (fp32 storage, TF32 tensor-core operands — BASELINE.json configs[1]), "fp16" or "bf16"
+        # (16-bit activations and tensor-core operands, fp32 parameters / statistics / accumulation — configs[2])
+        self.compute_dtype = COMPUTE_DTYPES[getattr(config, "compute_dtype", None) or "tf32"]
         common = dict(n_head=config.n_heads, d_k=config.d_k, d_v=config.d_v, d_model=config.d_model,
-                      d_inner_hid=config.d_inner_hid, dropout=config.dropout, emb_scale=getattr(config, "emb_scale", 1))
+                      d_inner_hid=config.d_inner_hid, dropout=config.dropout, emb_scale=getattr(config, "emb_scale", 1),
+                      compute_dtype=self.compute_dtype,
+                      length_masks=bool(getattr(config, "length_masks", True)))
         self.encoder = Encoder(input_size=config.feature_dim, n_max_seq=config.max_inputs_length,
                                n_layers=config.num_enc_layer, **common)
         self.decoder = Decoder(vocab_size=config.vocab_size, n_max_seq=config.max_target_length,

@@ -56,7 +56,8 @@ class FlatParams:
     GradSink (functional.attach_grad_sink) pointing at its slice of the gradient buffer: the composite backward
     operators write parameter gradients there directly instead of going through autograd's accumulation."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], twin_dtype=torch.float32):
+        self.twin_dtype = twin_dtype      # element type of the operand-precision twin: float32 (TF32-rounded), float16, bfloat16
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -77,20 +78,28 @@ class FlatParams:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
         from .functional import attach_grad_sink
         self.sinks = [attach_grad_sink(p, p.grad) for p in self.params]
-        # TF32-rounded twin of the whole parameter buffer: the fused Adam kernel rewrites it every step, so the
-        # attention / FFN operators never round (or re-pack) a weight matrix themselves
-        self.flat_tf32 = torch.empty_like(self.flat) if self.flat.is_cuda else None
+        # operand-precision twin of the whole parameter buffer (TF32-rounded fp32, or fp16 / bf16 for the 16-bit path): the
+        # fused Adam kernel rewrites it every step, so the attention / FFN operators never round, convert or re-pack a
+        # weight matrix themselves
+        self.flat_tf32 = torch.empty_like(self.flat, dtype=twin_dtype) if self.flat.is_cuda else None
         self.refresh_rounded()
 
     def refresh_rounded(self) -> None:
-        """Recompute the TF32 twins from the fp32 parameters (after a broadcast, load_state_dict, manual edits)."""
+        """Recompute the twins from the fp32 parameters (after a broadcast, load_state_dict, manual edits).  Parameters
+        owned by a FlatParams may only be modified through the trainer's optimizer step, or by in-place PyTorch edits
+        FOLLOWED by this call: writes through `.data` / raw pointers do not bump the version counter the twins are checked
+        against."""
         if self.flat_tf32 is None:
             return
         from . import _lib
-        from .functional import _stream, attach_tf32_twin
+        from .functional import ACT_DTYPES, _stream, attach_tf32_twin
         lib = _lib.load()
-        _lib.check(lib.st_round_tf32(self.flat.data_ptr(), self.numel, self.flat_tf32.data_ptr(), self.numel, 1, self.numel,
-                                     _stream()))
+        if self.twin_dtype == torch.float32:
+            _lib.check(lib.st_round_tf32(self.flat.data_ptr(), self.numel, self.flat_tf32.data_ptr(), self.numel, 1, self.numel,
+                                         _stream()))
+        else:
+            _lib.check(lib.st_cast(self.flat.data_ptr(), _lib.DTYPE_F32, self.numel, self.flat_tf32.data_ptr(),
+                                   ACT_DTYPES[self.twin_dtype], self.numel, 1, self.numel, 1.0, _stream()))
         for p, o in zip(self.params, self.offsets):
             if p.dim() >= 2:
                 attach_tf32_twin(p, self.flat_tf32[o:o + p.numel()].view_as(p))
@@ -166,9 +175,16 @@ class DataParallelTrainer:
     """zero_grad -> (caller: forward + backward) -> allreduce -> clip + Adam, on flat buffers."""
 
     def __init__(self, module: torch.nn.Module, d_model: int, n_warmup_steps: int = 12000, max_grad_norm: float = 5.0,
-                 betas=(0.9, 0.98), eps: float = 1e-9, process_group=None, overlap: bool = True, bucket_mb: float = 13.0):
+                 betas=(0.9, 0.98), eps: float = 1e-9, process_group=None, overlap: bool = True, bucket_mb: float = 13.0,
+                 compute_dtype=torch.float32, loss_scale: Optional[float] = None):
+        """compute_dtype: activation type the module runs in (float32 = TF32 operands; float16 / bfloat16 = 16-bit operands;
+        the parameter twins follow it).  loss_scale: factor applied to the loss before backward and divided out inside the
+        Adam kernel (a power of two; default 2**14 for float16 — whose activation gradients would otherwise underflow —
+        and 1 otherwise).  A step whose gradient norm is not finite is skipped by the kernel (st_adam_step)."""
         self.module = module
-        self.fp = FlatParams(ordered_parameters(module))
+        self.compute_dtype = compute_dtype
+        self.loss_scale = float(loss_scale) if loss_scale is not None else (16384.0 if compute_dtype == torch.float16 else 1.0)
+        self.fp = FlatParams(ordered_parameters(module), twin_dtype=compute_dtype)
         self.exp_avg = torch.zeros_like(self.fp.flat)
         self.exp_avg_sq = torch.zeros_like(self.fp.flat)
         self.norm_ws = torch.zeros(1, device=self.fp.flat.device, dtype=torch.float32)
@@ -185,6 +201,7 @@ class DataParallelTrainer:
         if self.overlap:
             for s in self.fp.sinks:
                 s.owner = self._on_grads_ready        # per-sink notification: several trainers can coexist
+                s.no_accumulate = True                # early bucket reductions and gradient accumulation do not mix
 
     def _reduce(self, lo: int, hi: int, async_op: bool):
         return dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
@@ -198,9 +215,49 @@ class DataParallelTrainer:
 
     # --- train_multi.py:176-177
     def broadcast_parameters(self, src: int = 0) -> None:
+        """Parameters AND optimizer state from rank `src` (hvd.broadcast_parameters + broadcast_optimizer_state,
+        train_multi.py:176-177): the Adam moments and the step counter that drives the Noam rate and the bias correction."""
         if self.world > 1:
             dist.broadcast(self.fp.flat, src=src, group=self.group)
+            dist.broadcast(self.exp_avg, src=src, group=self.group)
+            dist.broadcast(self.exp_avg_sq, src=src, group=self.group)
+            step = torch.tensor([self.global_step], dtype=torch.int64, device=self.fp.flat.device)
+            dist.broadcast(step, src=src, group=self.group)
+            self.global_step = int(step.item())
             self.fp.refresh_rounded()
+
+    # --- Utils.save_model (Utils.py:116-124) writes {'model', 'optimizer'}; train.py:110-114 loads them back
+    def state_dict(self) -> dict:
+        """Optimizer state in torch.optim.Adam's per-parameter format ('state': {index: {'step', 'exp_avg', 'exp_avg_sq'}},
+        'param_groups') — what the reference's ScheduledOptim.optimizer.state_dict() holds — plus the global step that the
+        reference forgets to restore.  Parameter indices follow module.parameters() order, as torch.optim does."""
+        index = {id(p): i for i, p in enumerate(self.module.parameters())}
+        state = {}
+        for p, o in zip(self.fp.params, self.fp.offsets):
+            n = p.numel()
+            state[index[id(p)]] = {"step": torch.tensor(float(self.global_step)),
+                                   "exp_avg": self.exp_avg[o:o + n].view_as(p).detach().clone(),
+                                   "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).detach().clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "params": sorted(state)}
+        return {"state": state, "param_groups": [group], "global_step": self.global_step, "loss_scale": self.loss_scale}
+
+    def load_state_dict(self, sd: dict) -> None:
+        index = {id(p): i for i, p in enumerate(self.module.parameters())}
+        steps = []
+        with torch.no_grad():
+            for p, o in zip(self.fp.params, self.fp.offsets):
+                st = sd["state"].get(index[id(p)])
+                if st is None:
+                    continue
+                n = p.numel()
+                self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.append(int(float(st.get("step", 0))))
+        self.global_step = int(sd.get("global_step", max(steps) if steps else 0))
+        if "loss_scale" in sd:
+            self.loss_scale = float(sd["loss_scale"])
+        self.fp.refresh_rounded()       # the module's parameters were (presumably) just loaded too
 
     def zero_grad(self) -> None:
         self.fp.zero_grad()
@@ -234,8 +291,10 @@ class DataParallelTrainer:
         a = _lib.AdamArgs(param=self.fp.flat.data_ptr(), grad=g.data_ptr(), exp_avg=self.exp_avg.data_ptr(),
                           exp_avg_sq=self.exp_avg_sq.data_ptr(), n=g.numel(), lr=self.lr, beta1=self.betas[0],
                           beta2=self.betas[1], eps=self.eps, step=self.global_step, max_grad_norm=self.max_grad_norm,
-                          grad_scale=1.0 / self.world, norm_ws=self.norm_ws.data_ptr(),
-                          param_tf32=None if self.fp.flat_tf32 is None else self.fp.flat_tf32.data_ptr())
+                          grad_scale=1.0 / (self.world * self.loss_scale), norm_ws=self.norm_ws.data_ptr(),
+                          param_tf32=None if self.fp.flat_tf32 is None else self.fp.flat_tf32.data_ptr(),
+                          twin_dtype=_lib.DTYPE_F32 if self.fp.flat_tf32 is None else
+                          {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}[self.fp.flat_tf32.dtype])
         _lib.check(lib.st_adam_step(C.byref(a), s))
 
     def train_step(self, loss_fn) -> torch.Tensor:
@@ -247,7 +306,7 @@ class DataParallelTrainer:
             self.zero_grad()
         self._grads_clean = False
         loss = loss_fn()
-        loss.backward()
+        (loss if self.loss_scale == 1.0 else loss * self.loss_scale).backward()
         self.allreduce_gradients()
         self.step()
         self.zero_grad()
