@@ -41,7 +41,11 @@ def parse():
     ap.add_argument("--targets", type=int, default=50, help="L_max")
     ap.add_argument("--layers", type=int, default=6)
     ap.add_argument("--dropout", type=float, default=0.1)
-    ap.add_argument("--cpu-sample-batch", type=int, default=2, help="utterances per CPU-baseline step")
+    ap.add_argument("--cpu-sample-batch", type=int, default=8, help="utterances per CPU-baseline step (BASELINE.md §5: B=8)")
+    ap.add_argument("--dtype", default=os.environ.get("ST_BENCH_DTYPE", "tf32"), choices=["tf32", "fp16", "bf16"],
+                    help="activation / tensor-core operand type: tf32 = fp32 storage (BASELINE.json configs[1]), "
+                         "fp16 / bf16 = 16-bit activations and operands, fp32 accumulate (configs[2])")
+    ap.add_argument("--ragged", action="store_true", help="utterance lengths U[200, frames] padded to --frames (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -153,9 +157,17 @@ def run_cpu(args, steps, warmup, batch):
             "ms_per_step": 1e3 * total / steps}
 
 
+DTYPE_DESC = {"tf32": "tf32 (fp32 storage, TF32 tensor-core operands, fp32 accumulate)",
+              "fp16": "fp16 (fp16 activations and tensor-core operands = TF32's 10-bit mantissa, fp32 accumulate / statistics / "
+                      "parameters / optimizer, loss scale 2^14)",
+              "bf16": "bf16 (bf16 activations and tensor-core operands, fp32 accumulate / statistics / parameters / optimizer)"}
+
+
 def workload_config(args, n):
-    return {"workload": f"BASELINE.json configs[1]: {args.layers}+{args.layers}-layer enc/dec d_model=512 h=8 d_ff=2048, fp32 storage / "
-                        f"TF32 tensor cores, synthetic 80-dim fbank B={args.batch}/GPU T={args.frames} L<={args.targets} V=4337",
+    which = "configs[2]" if (args.ragged or args.dtype == "bf16") else "configs[1]"
+    lens = f"T in U[200,{args.frames}] padded to {args.frames}" if args.ragged else f"T={args.frames}"
+    return {"workload": f"BASELINE.json {which}: {args.layers}+{args.layers}-layer enc/dec d_model=512 h=8 d_ff=2048, "
+                        f"{args.dtype} operands, synthetic 80-dim fbank B={args.batch}/GPU {lens} L<={args.targets} V=4337",
             "step": "fwd + label-smoothed CE + bwd + grad all-reduce + clip + Noam-Adam (train.py:37-46)",
             "dropout": args.dropout, "per_gpu_batch": args.batch, "global_batch": args.batch * n, "parallelism": f"dp{n}",
             "l2": "per-step working set (several GB of activations) >> 126 MB L2, no explicit flush needed"}
@@ -203,16 +215,19 @@ def main_b200(args):
     stb._lib.check(lib.st_device_check(local))
 
     V, d = 4337, 512
-    cfg = smodel.headline_config(num_enc_layer=args.layers, num_dec_layer=args.layers, dropout=args.dropout)
+    cfg = smodel.headline_config(num_enc_layer=args.layers, num_dec_layer=args.layers, dropout=args.dropout,
+                                 compute_dtype=args.dtype)
+    act_dtype = smodel.COMPUTE_DTYPES[args.dtype]
     torch.manual_seed(2018)
     net = smodel.Transformer(cfg)
     smodel.init_parameters(net)
     net = net.to(dev).train()
     crit = stb.LabelSmoothingLoss(0.1, V, weight=torch.ones(V, device=dev), size_average=True, ignore_index=0).to(dev)
-    trainer = spar.DataParallelTrainer(net, d_model=d, n_warmup_steps=12000, max_grad_norm=5.0)
+    trainer = spar.DataParallelTrainer(net, d_model=d, n_warmup_steps=12000, max_grad_norm=5.0, compute_dtype=act_dtype)
     trainer.broadcast_parameters(0)
 
-    host = sdata.synthetic_batch(args.batch, args.frames, args.targets, 80, V, seed=2018 + rank, pin=True)
+    host = sdata.synthetic_batch(args.batch, args.frames, args.targets, 80, V, seed=2018 + rank, pin=True,
+                                 fixed_len=not args.ragged, t_min=min(200, args.frames))
     resident = [t.to(dev) for t in host]
 
     def step_on(inputs, targets, in_len, tgt_len, truth):
@@ -268,6 +283,7 @@ def main_b200(args):
     clocks = sampler.stop() if sampler else None
     frames = args.batch * args.frames * n * args.steps
     value = frames / (ms * 1e-3)
+    valid_frames = int(host[2].sum().item())      # this rank's un-padded frames per step (== batch * frames unless --ragged)
 
     prefetch.submit(host)
     for _ in range(2):
@@ -351,7 +367,7 @@ def main_b200(args):
         except Exception:
             pass
         if g:
-            roofline = {"kernel": "gemm_tf32_kernel (tcgen05 kind::tf32, all projection / FFN / gradient GEMMs)",
+            roofline = {"kernel": f"gemm_kernel / gemm_2sm_kernel (tcgen05 kind::{'tf32' if args.dtype == 'tf32' else 'f16'}, all projection / FFN / gradient GEMMs)",
                         "bound": "tensor", "achieved": g["rate"], "peak": peak, "unit": "TFLOP/s",
                         "frac": g["rate"] / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                         "peak_tf32_measured": tf32_peak, "frac_of_tf32_peak": g["rate"] / tf32_peak,
@@ -359,15 +375,16 @@ def main_b200(args):
                         "avg_launch_ms": g["ms_per_step"] / g["launches_per_step"],
                         "share_of_step": g["share_of_step"],
                         "note": "achieved = algorithmic 2MNK FLOPs / CUDA-event time over every GEMM launch of the profiled "
-                                "steps; TF32 runs at half the bf16 MMA rate, so frac against the bf16 peak is capped at 0.5"}
+                                "steps; TF32 operands run at half the bf16 MMA rate (frac against the bf16 peak is capped at 0.5 "
+                                "for --dtype tf32)"}
 
     # ---- the fused EncoderLayer alone (north_star: tensor-pipe utilisation of EncoderLayer fwd+bwd at B=32,T=1000,d=512,h=8)
     enc_layer = None
     if rank == 0 and not args.no_roofline:
         layer = net.encoder.layer_stack[0]
-        lx = torch.randn(args.batch, args.frames, d, device=dev)
-        lg = torch.randn(args.batch, args.frames, d, device=dev)
-        lmask = smodel.key_padding_mask(resident[2], args.frames, args.frames)
+        lx = torch.randn(args.batch, args.frames, d, device=dev).to(act_dtype)
+        lg = torch.randn(args.batch, args.frames, d, device=dev).to(act_dtype)
+        lmask = stb.functional.LengthMask(resident[2], args.frames, args.frames)
         lparams = [q for q in layer.parameters()]
 
         def layer_step():
@@ -395,9 +412,11 @@ def main_b200(args):
                      "frames_per_s": N_tok / (lms * 1e-3),
                      "frac_of_tf32_peak_measured": tf / tf32_peak if tf32_peak else None,
                      "frac_of_bf16_peak": tf / peak,
+                     "frac_of_bf16_peak_burst": tf / float(peaks.get("bf16_tflops", 1660.0)) if peaks else None,
+                     "dtype": args.dtype,
                      "note": "one EncoderLayer (MHA + FFN, train mode, dropout 0.1) forward + backward, B x T x 512 resident in HBM; "
-                             "FLOPs = 3 x (8Nd^2 + 4BhT^2dk + 4Nd*dff), no recompute counted; the path computes in TF32, "
-                             "whose tensor-pipe rate is half the bf16 rate"}
+                             "FLOPs = 3 x (8Nd^2 + 4BhT^2dk + 4Nd*dff), no recompute counted, padded frames counted as the "
+                             "reference computes them; tf32 operands issue at half the bf16 / fp16 tensor-pipe rate"}
         for q in lparams:
             q.grad = None
         trainer.zero_grad()
@@ -413,7 +432,8 @@ def main_b200(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic", "config": workload_config(args, n),
+                "dtype": DTYPE_DESC[args.dtype], "data": "synthetic", "config": workload_config(args, n),
+                "valid_frames_per_s": valid_frames * n * args.steps / (ms * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "kernel_breakdown": breakdown, "encoder_layer": enc_layer, "cpu_baseline": cpu, "data_parallel": dp}
         print(json.dumps(line), flush=True)

@@ -11,7 +11,7 @@ import torch
 
 from . import model_port
 
-PAD, BOS, EOS = 0, 1, 2   # transformer/Constants.py
+PAD, UNK, BOS, EOS = 0, 1, 2, 3   # transformer/Constants.py:1-4
 
 
 def step_logits(P: dict, cfg: dict, inputs, in_len, prefix):
@@ -21,11 +21,11 @@ def step_logits(P: dict, cfg: dict, inputs, in_len, prefix):
     return model_port.forward(P, cfg, inputs, in_len, prefix, tgt_len)[:, -1, :]
 
 
-def beam_search(P: dict, cfg: dict, inputs, in_len, beam: int, max_len: int, n_best: int = 1, eos: int = EOS):
+def beam_search(P: dict, cfg: dict, inputs, in_len, beam: int, max_len: int, n_best: int = 1, eos: int = EOS, bos: int = BOS):
     B, V = inputs.size(0), cfg["vocab_size"]
     rep_in = inputs.repeat_interleave(beam, 0)           # Decode.py:62-68
     rep_len = in_len.repeat_interleave(beam, 0)
-    prefix = torch.full((B * beam, 1), BOS, dtype=torch.int64)
+    prefix = torch.full((B * beam, 1), int(bos), dtype=torch.int64)
     scores = torch.zeros(B, beam, dtype=P["tgt_word_proj.weight"].dtype)
     done = torch.zeros(B, dtype=torch.bool)
     for t in range(max_len):

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libst_b200.so")
+LIB_PATH = os.environ.get("ST_B200_LIB") or os.path.join(HERE, "libst_b200.so")   # the override serves A/B runs of two builds
 
 c_float_p = C.c_void_p  # raw device pointers travel as integers
 
@@ -194,6 +194,8 @@ def load() -> C.CDLL:
             "(there is no CPU or PyTorch fallback for this path)")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if name.startswith("st_debug_") and os.environ.get("ST_B200_LIB") and not hasattr(lib, name):
+            continue             # an older build loaded for an A/B run may lack a debug hook
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args

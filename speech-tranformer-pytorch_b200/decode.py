@@ -33,9 +33,9 @@ import torch
 from . import _lib
 from . import functional as F
 from ._lib import check
-from .model import PAD, key_padding_mask
+from .model import key_padding_mask
 
-BOS, EOS = 1, 2   # transformer/Constants.py:2-3
+from .data import BOS, EOS, PAD  # transformer/Constants.py:1-4 (PAD 0, UNK 1, BOS 2, EOS 3): ONE definition for training data and decoding
 
 
 def _p(t):
@@ -240,18 +240,21 @@ class IncrementalDecoder:
 
 @torch.no_grad()
 def beam_search(net, inputs: torch.Tensor, input_lengths: torch.Tensor, beam: int = 10, max_len: int = 50,
-                n_best: int = 1, eos: int = EOS, decoder: Optional[IncrementalDecoder] = None
+                n_best: int = 1, eos: int = EOS, decoder: Optional[IncrementalDecoder] = None, bos: int = BOS
                 ) -> Tuple[List[List[List[int]]], torch.Tensor]:
     """Beam decode a batch (Decode.decode_batch, Decode.py:48-179, with Beam.advance semantics, Beam.py:43-74):
     every step adds log-probabilities to the running beam scores, keeps the `beam` best of beam x vocab, records
     the integer back-pointer and symbol; an utterance is finished when its best hypothesis ends in EOS.
     Returns (hypotheses[b][k] = token list without BOS, scores (B, n_best)).  Pass a persistent `decoder`
-    (IncrementalDecoder(net, max_len, use_graphs=True)) to replay CUDA graphs across batches of one shape."""
+    (IncrementalDecoder(net, max_len, use_graphs=True)) to replay CUDA graphs across batches of one shape.
+    `bos` seeds every hypothesis (Constants.BOS = 2, what training feeds as the first target, Dataset.py:36); `eos` stops
+    an utterance (Constants.EOS = 3).  NOTE the reference's Dataset builds its ground truth as labels + [BOS]
+    (Dataset.py:37, sic), so a model trained on that data ends its hypotheses with BOS: pass eos=BOS for such a checkpoint."""
     dec = decoder if decoder is not None else IncrementalDecoder(net, max_len=max_len)
     dec.start(inputs, input_lengths, beam)
     B, V, dev = inputs.size(0), dec.vocab, inputs.device
     scores = torch.zeros(B, beam, device=dev)
-    tokens = torch.full((B * beam,), BOS, dtype=torch.int64, device=dev)
+    tokens = torch.full((B * beam,), int(bos), dtype=torch.int64, device=dev)
     done = torch.zeros(B, dtype=torch.bool, device=dev)
     # one library kernel per position does the bookkeeping (st_beam_step): log-softmax, score update, top-`beam` of
     # beam x V with integer back-pointers (Beam.py:66), freezing of finished utterances, re-parenting / next-token vectors

@@ -209,3 +209,22 @@ def test_python_sources_reference_only_defined_names():
         bad += [f"{os.path.relpath(path, root)}:{n.lineno} {n.id}" for n in ast.walk(tree)
                 if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in known]
     assert not bad, bad
+
+
+def test_token_constants_match_reference():
+    """decode.BOS/EOS, data.*, the oracle's decode port and the reference's Constants.py (PAD 0, UNK 1, BOS 2, EOS 3) agree:
+    a checkpoint trained with BOS = 2 as the start symbol must be decoded from the same symbol."""
+    import importlib
+    import speech_tranformer_pytorch_b200 as stb
+    data = importlib.import_module(stb.__name__ + ".data")
+    decode = importlib.import_module(stb.__name__ + ".decode")
+    from oracle import decode_port
+    want = dict(PAD=0, UNK=1, BOS=2, EOS=3)
+    assert (data.PAD, data.UNK, data.BOS, data.EOS) == (0, 1, 2, 3)
+    assert (decode.PAD, decode.BOS, decode.EOS) == (want["PAD"], want["BOS"], want["EOS"])
+    assert (decode_port.PAD, decode_port.UNK, decode_port.BOS, decode_port.EOS) == (0, 1, 2, 3)
+    ref = os.path.join(ROOT, "oracle", "_ref", "transformer", "Constants.py")
+    if os.path.exists(ref):
+        ns = {}
+        exec(open(ref).read(), ns)
+        assert {k: ns[k] for k in want} == want
