@@ -366,6 +366,23 @@ typedef struct {
 } st_adam_args;
 int st_adam_step(const st_adam_args* a /* host */, cudaStream_t stream);
 
+/* ---- data-parallel gradient exchange (train_multi.py:20,128,161-163,176-177: Horovod all-reduce of every gradient,
+ * broadcast of the initial state) -------------------------------------------------------------------------------
+ * One process per GPU; all gradients live in ONE flat fp32 buffer (what st_*_bwd write into and st_adam_step reads), so
+ * the exchange is one in-place ncclAllReduce(sum) over NVLink / NVSwitch; the average is st_adam_args.grad_scale = 1/world.
+ * NCCL is resolved with dlopen at the first call (no link-time dependency).
+ *   st_allreduce_unique_id : rank 0 fills `id_out` (st_allreduce_id_bytes() = 128 host bytes) and hands it to every rank out
+ *                            of band (MPI, a file, torch.distributed ...)
+ *   st_allreduce_init      : every rank, with its CUDA device current; collective
+ *   st_allreduce_run       : buf[0..n) <- sum over ranks, enqueued on `stream`; st_allreduce_broadcast: buf <- root's buf
+ *   st_allreduce_destroy   : releases the communicator                                                              */
+int st_allreduce_id_bytes(void);
+int st_allreduce_unique_id(void* id_out /* host */);
+int st_allreduce_init(const void* unique_id /* host */, int world, int rank, void** comm_out /* host */);
+int st_allreduce_run(void* comm, float* buf, int64_t n, cudaStream_t stream);
+int st_allreduce_broadcast(void* comm, float* buf, int64_t n, int root, cudaStream_t stream);
+int st_allreduce_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

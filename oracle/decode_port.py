@@ -21,6 +21,30 @@ def step_logits(P: dict, cfg: dict, inputs, in_len, prefix):
     return model_port.forward(P, cfg, inputs, in_len, prefix, tgt_len)[:, -1, :]
 
 
+def beam_advance(scores, word_lk, first: bool):
+    """One Beam.advance (Beam.py:43-74) for a batch of utterances.  scores (B, beam) running scores, word_lk (B, beam, V)
+    log-probabilities of the next symbol.  Returns (new scores, prev_k, next_y), each (B, beam), best first: at the first
+    position only hypothesis 0 is expanded (Beam.py:49-52, all hypotheses are identical); afterwards the `beam` best of the
+    flattened beam x word array (Beam.py:56-59), prev_k = id // num_words (Beam.py:66, integer division as intended),
+    next_y = id - prev_k * num_words (Beam.py:68).  PINNED: tests/golden/beam_advance.npz holds what the reference's own
+    Beam class produces for seeded inputs (oracle/make_golden_beam.py)."""
+    B, beam, V = word_lk.shape
+    cand = word_lk[:, :1] if first else word_lk + scores.unsqueeze(2)           # Beam.py:49-52
+    best, idx = cand.reshape(B, -1).topk(beam, dim=1)                           # Beam.py:56-59
+    prev_k = idx // V                                                           # Beam.py:66
+    return best, prev_k, idx - prev_k * V                                       # Beam.py:68
+
+
+def hypothesis(prev_ks, next_ys, k: int):
+    """Beam.get_hypothesis (Beam.py:99-116) for one utterance: walk the back-pointers from beam position k.
+    prev_ks / next_ys: per-step (beam,) tensors (next_ys WITHOUT the initial BOS row)."""
+    hyp = []
+    for j in range(len(prev_ks) - 1, -1, -1):
+        hyp.append(int(next_ys[j][k]))
+        k = int(prev_ks[j][k])
+    return hyp[::-1]
+
+
 def beam_search(P: dict, cfg: dict, inputs, in_len, beam: int, max_len: int, n_best: int = 1, eos: int = EOS, bos: int = BOS):
     B, V = inputs.size(0), cfg["vocab_size"]
     rep_in = inputs.repeat_interleave(beam, 0)           # Decode.py:62-68
@@ -30,10 +54,7 @@ def beam_search(P: dict, cfg: dict, inputs, in_len, beam: int, max_len: int, n_b
     done = torch.zeros(B, dtype=torch.bool)
     for t in range(max_len):
         logp = torch.log_softmax(step_logits(P, cfg, rep_in, rep_len, prefix), -1).view(B, beam, V)
-        cand = logp + scores.unsqueeze(2) if t > 0 else logp[:, :1]          # Beam.py:49-52
-        best, idx = cand.reshape(B, -1).topk(beam, dim=1)                    # Beam.py:56-59
-        prev_k = idx // V                                                     # Beam.py:66 (integer intent)
-        y = idx - prev_k * V                                                  # Beam.py:68
+        best, prev_k, y = beam_advance(scores, logp, first=(t == 0))         # Beam.py:43-74
         keep = done.unsqueeze(1)
         prev_k = torch.where(keep, torch.arange(beam).expand(B, -1), prev_k)
         y = torch.where(keep, torch.full_like(y, PAD), y)

@@ -13,6 +13,7 @@ must match exactly once; nothing else is touched.
   Models.py:90,92,97  masks built from lengths (outputs_pos), not token ids (outputs_data)
   Models.py:102     the layer returns (out, (slf, enc)) — unpack what Layers.py:44 actually returns
   Utils.py:52,66    uint8 masks -> bool (masked_fill_ rejects uint8 on torch >= 2)
+  Beam.py:66        `best_scores_id / num_words` -> `//` (true division makes the back-pointers floats on torch >= 1.5)
 """
 import os
 import shutil
@@ -34,6 +35,9 @@ PATCHES = {
         ("dec_enc_attn_pad_mask = padding_info_mask(\n            outputs_data, input_pos)",
          "dec_enc_attn_pad_mask = padding_info_mask(\n            outputs_pos, input_pos)"),
         ("dec_output, dec_slf_attn, dec_enc_attn = dec_layer(", "dec_output, (dec_slf_attn, dec_enc_attn) = dec_layer("),
+    ],
+    "Beam.py": [
+        ("prev_k = best_scores_id / num_words", "prev_k = best_scores_id // num_words"),
     ],
     "Utils.py": [
         ("pad_attn_mask = torch.from_numpy(mask_mat).unsqueeze(1)", "pad_attn_mask = torch.from_numpy(mask_mat).bool().unsqueeze(1)"),

@@ -172,6 +172,12 @@ SIGNATURES = {
     "st_ctc_ws_floats": (i64, [C.c_int, C.c_int, C.c_int]),
     "st_ctc_fwd_bwd": (C.c_int, [_P, i64, _P, i64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, i64, _P, i64, _S]),
     "st_ctc_grad": (C.c_int, [_P, i64, _P, i64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, i64, _P, i64, _S]),
+    "st_allreduce_id_bytes": (C.c_int, []),
+    "st_allreduce_unique_id": (C.c_int, [_P]),
+    "st_allreduce_init": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "st_allreduce_run": (C.c_int, [_P, _P, i64, _S]),
+    "st_allreduce_broadcast": (C.c_int, [_P, _P, i64, C.c_int, _S]),
+    "st_allreduce_destroy": (C.c_int, [_P]),
     "st_sumsq": (C.c_int, [_P, i64, _P, _S]),
     "st_adam_step": (C.c_int, [C.POINTER(AdamArgs), _S]),
 }

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libst_b200.so")
 
-SOURCES = ["st_host.cu", "st_gemm.cu", "st_gemm_h.cu", "st_gemm_bf.cu", "st_ln.cu", "st_lsce.cu", "st_attn.cu", "st_attn_bwd.cu", "st_attn16.cu", "st_optim.cu", "st_embed.cu", "st_beam.cu", "st_ctc.cu", "st_selftest.cu", "st_api.cu"]
+SOURCES = ["st_host.cu", "st_gemm.cu", "st_gemm_h.cu", "st_gemm_bf.cu", "st_ln.cu", "st_lsce.cu", "st_attn.cu", "st_attn_bwd.cu", "st_attn16.cu", "st_optim.cu", "st_embed.cu", "st_beam.cu", "st_ctc.cu", "st_selftest.cu", "st_nccl.cu", "st_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs = list(ex.map(lambda s: _compile(s, hdr, force), sources))
     if (force or not os.path.exists(LIB_PATH)
             or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs)):
-        cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -171,16 +171,71 @@ class GradBuckets:
         return [(lo, hi) for lo, hi in out]
 
 
+class LibraryCollective:
+    """The gradient exchange through the C ABI (st_allreduce_*: ncclAllReduce on a communicator the library owns) instead of
+    torch.distributed — what a host that is not PyTorch would call (include/st_b200.h).  torch.distributed is used ONCE, to
+    hand rank 0's NCCL unique id to the other ranks (any out-of-band channel does).  Collectives run on a side stream that
+    waits for the kernels enqueued so far on the compute stream, like torch's NCCL process group does."""
+
+    def __init__(self, device, group=None):
+        from . import _lib
+        self.lib = _lib.load()
+        self._check = _lib.check
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = self.lib.st_allreduce_id_bytes()
+        uid = (C.c_char * n)()
+        if rank == 0:
+            self._check(self.lib.st_allreduce_unique_id(uid))
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        comm = C.c_void_p()
+        with torch.cuda.device(device):
+            self._check(self.lib.st_allreduce_init(box[0], world, rank, C.byref(comm)))
+        self.comm, self.device = comm, device
+        self.stream = torch.cuda.Stream(device)
+
+    class _Work:
+        def __init__(self, event):
+            self.event = event
+
+        def wait(self):
+            torch.cuda.current_stream().wait_event(self.event)
+
+    def all_reduce(self, view: torch.Tensor, async_op: bool):
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        self.stream.wait_event(ready)
+        self._check(self.lib.st_allreduce_run(self.comm, view.data_ptr(), view.numel(), C.c_void_p(self.stream.cuda_stream)))
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        work = LibraryCollective._Work(done)
+        if async_op:
+            return work
+        work.wait()
+        return None
+
+    def broadcast(self, view: torch.Tensor, src: int):
+        self._check(self.lib.st_allreduce_broadcast(self.comm, view.data_ptr(), view.numel(), src,
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def close(self):
+        if self.comm:
+            self._check(self.lib.st_allreduce_destroy(self.comm))
+            self.comm = C.c_void_p()
+
+
 class DataParallelTrainer:
     """zero_grad -> (caller: forward + backward) -> allreduce -> clip + Adam, on flat buffers."""
 
     def __init__(self, module: torch.nn.Module, d_model: int, n_warmup_steps: int = 12000, max_grad_norm: float = 5.0,
                  betas=(0.9, 0.98), eps: float = 1e-9, process_group=None, overlap: bool = True, bucket_mb: float = 13.0,
-                 compute_dtype=torch.float32, loss_scale: Optional[float] = None):
+                 compute_dtype=torch.float32, loss_scale: Optional[float] = None, collective: str = "torch"):
         """compute_dtype: activation type the module runs in (float32 = TF32 operands; float16 / bfloat16 = 16-bit operands;
         the parameter twins follow it).  loss_scale: factor applied to the loss before backward and divided out inside the
         Adam kernel (a power of two; default 2**14 for float16 — whose activation gradients would otherwise underflow —
         and 1 otherwise).  A step whose gradient norm is not finite is skipped by the kernel (st_adam_step)."""
+        if collective not in ("torch", "library"):
+            raise ValueError("collective must be 'torch' (torch.distributed) or 'library' (st_allreduce_* of the C ABI)")
         self.module = module
         self.compute_dtype = compute_dtype
         self.loss_scale = float(loss_scale) if loss_scale is not None else (16384.0 if compute_dtype == torch.float16 else 1.0)
@@ -197,6 +252,7 @@ class DataParallelTrainer:
         self._grads_clean = False
         self.buckets = GradBuckets(self.fp, int(bucket_mb * (1 << 20) / 4))
         self.overlap = bool(overlap) and self.world > 1
+        self.lib_collective = LibraryCollective(self.fp.flat.device, process_group) if (collective == "library" and self.world > 1) else None
         self.early_launches = 0                          # buckets whose all-reduce started under backward (diagnostic)
         if self.overlap:
             for s in self.fp.sinks:
@@ -204,6 +260,8 @@ class DataParallelTrainer:
                 s.no_accumulate = True                # early bucket reductions and gradient accumulation do not mix
 
     def _reduce(self, lo: int, hi: int, async_op: bool):
+        if self.lib_collective is not None:
+            return self.lib_collective.all_reduce(self.fp.grad[lo:hi], async_op)
         return dist.all_reduce(self.fp.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
 
     def _on_grads_ready(self, sinks) -> None:

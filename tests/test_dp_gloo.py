@@ -189,3 +189,74 @@ def test_grad_buckets_tile_the_buffer_for_any_bucket_size():
     assert gb.pending_ranges() == [(0, fp.offsets[-1])]
     gb.reset()
     assert gb.pending_ranges() == [(0, fp.numel)]
+
+
+def test_eval_forward_does_not_unbalance_the_sink_counters():
+    """a forward that never sees a backward (torch.no_grad(): validation, IncrementalDecoder.start) must not count
+    as a use — otherwise that rank's uses/done never match and it launches different collectives than its peers."""
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from speech_tranformer_pytorch_b200 import parallel as P, functional as F
+    net = torch.nn.Linear(8, 4)
+    tr = P.DataParallelTrainer(net, d_model=512)
+    tr.zero_grad()
+    params = (net.weight, net.bias)
+    eval_ctx = types.SimpleNamespace(needs_input_grad=(False, False, False))
+    assert F._sinks_of(params, eval_ctx) is None and all(s.uses == 0 for s in tr.fp.sinks)
+    train_ctx = types.SimpleNamespace(needs_input_grad=(False, True, True))
+    sinks = F._sinks_of(params, train_ctx)
+    assert sinks is not None and all(s.uses == 1 for s in tr.fp.sinks)
+    direct, zeroed = F._claim(sinks)
+    assert direct is not None and zeroed == 1
+    F._notify(sinks, direct)
+    assert all(s.done == s.uses == 1 for s in tr.fp.sinks)
+
+
+def test_overlap_refuses_gradient_accumulation():
+    """with early bucket reductions a second forward before zero_grad would add local gradients on top of reduced
+    sums; the sinks of an overlapping trainer refuse it (overlap=False accumulates through autograd as before)."""
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from speech_tranformer_pytorch_b200 import parallel as P, functional as F
+    net = torch.nn.Linear(8, 4)
+    tr = P.DataParallelTrainer(net, d_model=512)
+    for s in tr.fp.sinks:                       # what DataParallelTrainer(overlap=True) does when world > 1
+        s.no_accumulate = True
+    ctx = types.SimpleNamespace(needs_input_grad=(True, True, True))
+    tr.zero_grad()
+    sinks = F._sinks_of((net.weight, net.bias), ctx)
+    F._claim(sinks)
+    with pytest.raises(RuntimeError, match="accumulation"):
+        F._sinks_of((net.weight, net.bias), ctx)
+    tr.zero_grad()                              # a new step is fine again
+    assert F._sinks_of((net.weight, net.bias), ctx) is not None
+
+
+def test_trainer_state_dict_round_trip():
+    """Utils.save_model / train.py:110-114 checkpoint {'model', 'optimizer'}: the optimizer half in torch.optim.Adam's
+    per-parameter format, plus the global step (Noam rate, bias correction) the reference forgets."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from speech_tranformer_pytorch_b200 import parallel as P
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    tr = P.DataParallelTrainer(net, d_model=512)
+    tr.exp_avg.copy_(torch.randn(tr.fp.numel))
+    tr.exp_avg_sq.copy_(torch.rand(tr.fp.numel))
+    tr.global_step = 1234
+    sd = tr.state_dict()
+    ref = torch.optim.Adam(net.parameters(), betas=(0.9, 0.98), eps=1e-9).state_dict()
+    assert sd["param_groups"][0]["params"] == ref["param_groups"][0]["params"]
+    assert set(sd["state"]) == set(range(4)) and all(set(v) == {"step", "exp_avg", "exp_avg_sq"} for v in sd["state"].values())
+    assert sd["state"][0]["exp_avg"].shape == net[0].weight.shape
+    opt = torch.optim.Adam(net.parameters(), betas=(0.9, 0.98), eps=1e-9)
+    opt.load_state_dict({"state": sd["state"], "param_groups": [dict(ref["param_groups"][0])]})    # loads into stock Adam
+    net2 = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    tr2 = P.DataParallelTrainer(net2, d_model=512)
+    tr2.load_state_dict(sd)
+    assert tr2.global_step == 1234
+    for p_, o in zip(tr.fp.params, tr.fp.offsets):            # (the alignment padding between parameters is not state)
+        n = p_.numel()
+        assert torch.equal(tr2.exp_avg[o:o + n], tr.exp_avg[o:o + n]) and torch.equal(tr2.exp_avg_sq[o:o + n], tr.exp_avg_sq[o:o + n])

@@ -1,0 +1,263 @@
+"""GPU tests closing the round-1 review's holes (VERDICT.md "Next round" 6-8): the fused clip + Noam-Adam kernel against
+clip_grad_norm_ + torch.optim.Adam, the zero-edit path (install() + the reference's OWN Layers.py), whole-model parity at
+the headline width in every compute type, beam width 10 on the 6x512x8 model, aliased-input gradients, and the
+data-parallel collective of the C ABI.  Tolerances as in test_gpu_parity.py / test_gpu_half.py."""
+import ctypes as C
+import json
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+from helpers import TOL, relerr, relu_gate_from_cuda
+from oracle import decode_port, model_port
+from oracle import st_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MEASURED = {}
+
+
+@pytest.fixture(scope="module")
+def stb():
+    import speech_tranformer_pytorch_b200 as m
+    m.build()
+    m._lib.check(m._lib.load().st_device_check(0))
+    return m
+
+
+# ------------------------------------------------------------------------------------------------ optimizer (f-4)
+@pytest.mark.parametrize("twin", [torch.float32, torch.float16, torch.bfloat16])
+def test_fused_clip_adam_matches_torch(stb, twin):
+    """st_sumsq + st_adam_step over 5 steps == clip_grad_norm_(5.0) + torch.optim.Adam(betas=(0.9, 0.98), eps=1e-9) with the
+    Noam rate (train.py:45-46, Optim.py:9-14,36-45), including the operand-precision twin the kernel emits."""
+    from speech_tranformer_pytorch_b200 import parallel as spar
+    torch.manual_seed(4)
+    net = torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.Linear(64, 33)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.Linear(64, 33)).to(DEV)
+    ref.load_state_dict(net.state_dict())
+    tr = spar.DataParallelTrainer(net, d_model=64, n_warmup_steps=3, max_grad_norm=5.0, compute_dtype=twin, loss_scale=1.0)
+    opt = torch.optim.Adam(ref.parameters(), betas=(0.9, 0.98), eps=1e-9)
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    for step in range(1, 6):
+        scale = 30.0 if step % 2 else 0.01          # alternately above / below the clipping threshold
+        tr.zero_grad()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            g = scale * torch.randn(p.shape, device=DEV, generator=gen)
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        tr.step()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 5.0)
+        for group in opt.param_groups:
+            group["lr"] = spar.noam_lr(64, 3, step)
+        opt.step()
+        for (k, p), q in zip(net.named_parameters(), ref.parameters()):
+            assert relerr(p, q) < 2e-6, (step, k, relerr(p, q))
+    # the twin holds the operand-precision copy of the updated parameters
+    for p, o in zip(tr.fp.params, tr.fp.offsets):
+        got = tr.fp.flat_tf32[o:o + p.numel()].view_as(p)
+        if twin == torch.float32:
+            want = stb.functional.round_tf32(p.detach().contiguous())
+            assert torch.equal(got, want)
+        else:
+            assert got.dtype == twin and torch.equal(got, p.detach().to(twin))
+    # a non-finite gradient norm skips the update altogether
+    before = tr.fp.flat.clone()
+    tr.zero_grad()
+    tr.fp.grad[3] = float("inf")
+    tr.step()
+    assert torch.equal(tr.fp.flat, before)
+
+
+# ------------------------------------------------------------------------------------------------ zero-edit path (b)
+def test_install_runs_the_reference_layers_file_unchanged(stb):
+    """stb.install() and then the REFERENCE's own transformer/Layers.py (Layers.py:8-22, imported from oracle/_ref — the scratch
+    copy of the reference package that travels to the GPU box): its EncoderLayer composes the B200 modules without an edit."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isfile(os.path.join(ref_dir, "transformer", "Layers.py")):
+        pytest.skip("oracle/_ref not present (built by oracle/make_ref.py where /root/reference exists)")
+    saved = {k: v for k, v in sys.modules.items() if k == "transformer" or k.startswith("transformer.")}
+    for k in saved:
+        del sys.modules[k]
+    for name in ("editdistance", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, ref_dir)
+    try:
+        import transformer                      # noqa: F401  the reference package (its __init__ is empty)
+        stb.install()
+        from transformer.Layers import EncoderLayer
+        import transformer.Attention as A
+        assert A.MultiHeadAttention is stb.MultiHeadAttention
+        assert "oracle/_ref" in sys.modules["transformer.Layers"].__file__.replace(os.sep, "/")
+        B, L, d, H, dff = 2, 130, 128, 2, 256
+        gen = torch.Generator().manual_seed(77)
+        layer = EncoderLayer(d, dff, H, d // H, d // H, dropout=0.1).eval()
+        P = {k: v.detach().clone().double().requires_grad_() for k, v in layer.state_dict().items()}
+        x = torch.randn(B, L, d, generator=gen)
+        g = torch.randn(B, L, d, generator=gen)
+        lens = torch.tensor([L, 71])
+        mask = O.padding_info_mask(lens, lens).bool()
+        layer = layer.to(DEV)
+        layer.pos_ffn.keep_hidden = True
+        cx = x.to(DEV).requires_grad_()
+        cy, _ = layer(cx, slf_attn_mask=mask.to(DEV))          # Layers.py:18-22
+        cy.backward(g.to(DEV))
+        rx = x.double().requires_grad_()
+        a, _ = O.multi_head_attention(rx, rx, rx, mask, {k[9:]: v for k, v in P.items() if k.startswith("slf_attn.")}, H)
+        gate = relu_gate_from_cuda(layer.pos_ffn.last_hidden, O.ffn_preactivation(a, {k[8:]: v for k, v in P.items() if k.startswith("pos_ffn.")}))
+        ry = O.encoder_layer(rx, mask, P, H, ffn_gate=gate)
+        ry.backward(g.double())
+        assert relerr(cy, ry) < TOL and relerr(cx.grad, rx.grad) < TOL
+        for k, p in layer.named_parameters():
+            if k.endswith("linear_k.bias"):
+                continue                                      # analytically zero
+            assert relerr(p.grad, P[k].grad) < TOL, k
+    finally:
+        stb.uninstall()
+        sys.path.remove(ref_dir)
+        for k in [k for k in sys.modules if k == "transformer" or k.startswith("transformer.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+# ------------------------------------------------------------------------------------------------ whole model at 6+6 x 512
+CFG512 = dict(feature_dim=80, vocab_size=97, max_inputs_length=256, max_target_length=32, d_model=512, n_heads=8, d_k=64,
+              d_v=64, d_inner_hid=2048, num_enc_layer=6, num_dec_layer=6, dropout=0.1, emb_scale=1, return_attns=False)
+TOL_MODEL = {"tf32": 3e-3, "fp16": 3e-3, "bf16": 3e-2}      # composition of 25 modules: 3x the module bound (test_gpu_model.py)
+
+
+@pytest.mark.parametrize("dtype", ["tf32", "fp16", "bf16"])
+def test_whole_model_headline_width(stb, dtype):
+    """6+6 layers, d_model 512, 8 heads, d_ff 2048 (BASELINE.json configs[1] / [2]) on a ragged B=2, T=200 batch against the
+    float64 model port: logits, loss, and every parameter gradient (for the ReLU gate patterns the CUDA forward used)."""
+    from speech_tranformer_pytorch_b200 import model as smodel
+    V = CFG512["vocab_size"]
+    P = model_port.init_params(CFG512, seed=11)
+    gen = torch.Generator().manual_seed(12)
+    with torch.no_grad():
+        for k, v in P.items():                      # non-trivial biases / LayerNorm affines
+            if v.dim() == 1:
+                v.copy_((1.0 if k.endswith("layernorm.weight") or k.endswith("3.weight") else 0.0) + 0.05 * torch.randn(v.shape, generator=gen))
+    inputs, targets, in_len, tgt_len, truth = O.synthetic_batch(2, 200, 20, 80, V, seed=5, fixed_len=False)
+    net = smodel.Transformer(smodel.ModelConfig(CFG512, compute_dtype=dtype))
+    missing = net.load_state_dict({k: v.detach() for k, v in P.items()}, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith(".pe") for k in missing.missing_keys)
+    net = net.to(DEV).eval()
+    net.encoder.keep_hidden = True
+    for layer in list(net.encoder.layer_stack) + list(net.decoder.layer_stack):
+        layer.pos_ffn.keep_hidden = True
+    crit = stb.LabelSmoothingLoss(0.1, V, weight=torch.ones(V, device=DEV), size_average=True, ignore_index=0).to(DEV)
+    logits, _ = net(inputs.to(DEV), in_len.to(DEV), targets.to(DEV), tgt_len.to(DEV))
+    loss = crit(logits.reshape(-1, V), truth.to(DEV).view(-1))
+    scale = 1024.0 if dtype == "fp16" else 1.0
+    (loss * scale).backward()
+    hidden = {"frontend": net.encoder.last_hidden.float()}
+    for i, layer in enumerate(net.encoder.layer_stack):
+        hidden[f"encoder.layer_stack.{i}"] = layer.pos_ffn.last_hidden.float()
+    for i, layer in enumerate(net.decoder.layer_stack):
+        hidden[f"decoder.layer_stack.{i}"] = layer.pos_ffn.last_hidden.float()
+    PD = {k: v.detach().double().requires_grad_() for k, v in P.items()}
+    cfg = dict(d_model=512, n_heads=8, num_enc_layer=6, num_dec_layer=6, vocab_size=V)
+    flips = {}
+
+    def gate_fn(name, pre):
+        g = hidden[name].cpu() > 0
+        flips[name] = float((g != (pre.detach() > 0)).double().mean())
+        return g.to(torch.float64)
+
+    rl = model_port.forward(PD, cfg, inputs.double(), in_len, targets, tgt_len, gate_fn=gate_fn)
+    rloss = O.label_smoothing_loss(rl.reshape(-1, V), truth.reshape(-1), O.smoothing_one_hot(0.1, V, 0, dtype=torch.float64),
+                                   torch.ones(V, dtype=torch.float64), 0.1, 0, True)
+    rloss.backward()
+    tol = TOL_MODEL[dtype]
+    e_logits = relerr(logits, rl)
+    e_loss = abs(float(loss) - float(rloss)) / abs(float(rloss))
+    gscale = max(p.grad.abs().max().item() for p in PD.values())
+    e_grad = max((p.grad.detach().cpu().double() / scale - PD[k].grad).abs().max().item() / gscale for k, p in net.named_parameters())
+    MEASURED[f"whole_model_6+6x512[{dtype}]"] = dict(logits=e_logits, loss=e_loss, grads=e_grad, max_gate_flip_fraction=max(flips.values()))
+    assert max(flips.values()) < 2e-2, flips       # reduced-precision ReLU gates differ from the oracle's only near the kink
+    assert e_logits < tol and e_loss < tol and e_grad < tol, MEASURED
+
+
+# ------------------------------------------------------------------------------------------------ beam width 10 (f-3)
+def test_beam_width_10_on_the_headline_decoder(stb):
+    """BASELINE.json configs[4]: width 10, 6 x 512 x 8 — the incremental K/V-cache decoder + st_beam_step against the pinned
+    full-prefix oracle (oracle/decode_port.py, itself held to the reference's Beam class by tests/test_oracle_golden.py)."""
+    from speech_tranformer_pytorch_b200 import model as smodel
+    from speech_tranformer_pytorch_b200.decode import beam_search
+    cfgd = dict(CFG512, num_enc_layer=2, vocab_size=41)
+    V = cfgd["vocab_size"]
+    P = model_port.init_params(cfgd, seed=21)
+    gen = torch.Generator().manual_seed(22)
+    with torch.no_grad():
+        P["tgt_word_proj.weight"].mul_(6.0)          # sharper distributions: fewer near-ties between TF32 and float64 scores
+        for k, v in P.items():
+            if v.dim() == 1:
+                v.add_(0.05 * torch.randn(v.shape, generator=gen))
+    inputs, _, in_len, _, _ = O.synthetic_batch(2, 60, 8, 80, V, seed=6, fixed_len=False, l_min=4)
+    net = smodel.Transformer(smodel.ModelConfig(cfgd))
+    net.load_state_dict({k: v.detach() for k, v in P.items()}, strict=False)
+    net = net.to(DEV).eval()
+    hyps, scores = beam_search(net, inputs.to(DEV), in_len.to(DEV), beam=10, max_len=6, n_best=3)
+    PD = {k: v.detach().double() for k, v in P.items()}
+    cfg = dict(d_model=512, n_heads=8, num_enc_layer=2, num_dec_layer=6, vocab_size=V)
+    rhyps, rscores = decode_port.beam_search(PD, cfg, inputs.double(), in_len, beam=10, max_len=6, n_best=3)
+    assert relerr(scores, rscores) < 5e-3
+    assert hyps[0][0] == rhyps[0][0] and hyps[1][0] == rhyps[1][0], (hyps, rhyps)     # the best hypothesis of each utterance
+    same = sum(h == r for hb, rb in zip(hyps, rhyps) for h, r in zip(hb, rb))
+    assert same >= 4, (hyps, rhyps)                  # lower ranks may swap where two scores differ by less than the TF32 error
+
+
+# ------------------------------------------------------------------------------------------------ aliased inputs (ADVICE low)
+@pytest.mark.parametrize("alias", ["q_is_k", "q_is_v"])
+def test_mha_aliased_inputs_receive_the_residual_gradient_once(stb, alias):
+    B, L, d, H = 2, 40, 128, 2
+    gen = torch.Generator().manual_seed(31)
+    m = stb.MultiHeadAttention(H, d, d // H, d // H, residual="q" if alias == "q_is_k" else "v").eval()
+    P = {k: v.detach().clone().double().requires_grad_() for k, v in m.state_dict().items()}
+    a, b, g = (torch.randn(B, L, d, generator=gen) for _ in range(3))
+    m = m.to(DEV)
+    ca, cb = a.to(DEV).requires_grad_(), b.to(DEV).requires_grad_()
+    ra, rb = a.double().requires_grad_(), b.double().requires_grad_()
+    if alias == "q_is_k":
+        co, _ = m(ca, ca, cb)
+        ro, _ = O.multi_head_attention(ra, ra, rb, None, P, H, residual="q")
+    else:
+        co, _ = m(ca, cb, ca)
+        ro, _ = O.multi_head_attention(ra, rb, ra, None, P, H, residual="v")
+    co.backward(g.to(DEV))
+    ro.backward(g.double())
+    assert relerr(co, ro) < TOL
+    assert relerr(ca.grad, ra.grad) < TOL and relerr(cb.grad, rb.grad) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ C-ABI collective (b / e)
+def test_allreduce_c_abi_single_rank(stb):
+    """st_allreduce_* (train_multi.py:161-163 through the C ABI): a one-rank communicator reduces a buffer onto itself; the
+    two-rank equality with torch.distributed is checked by tools/check_allreduce_abi.py under torchrun (bench logs)."""
+    lib = stb._lib.load()
+    n = lib.st_allreduce_id_bytes()
+    assert n == 128
+    uid = (C.c_char * n)()
+    stb._lib.check(lib.st_allreduce_unique_id(uid))
+    comm = C.c_void_p()
+    torch.cuda.set_device(0)
+    stb._lib.check(lib.st_allreduce_init(uid, 1, 0, C.byref(comm)))
+    x = torch.randn(1000, device=DEV)
+    want = x.clone()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stb._lib.check(lib.st_allreduce_run(comm, x.data_ptr(), x.numel(), s))
+    stb._lib.check(lib.st_allreduce_broadcast(comm, x.data_ptr(), x.numel(), 0, s))
+    torch.cuda.synchronize()
+    assert torch.equal(x, want)
+    stb._lib.check(lib.st_allreduce_destroy(comm))
+    assert lib.st_allreduce_run(None, x.data_ptr(), 4, s) != 0        # error path: null communicator
+
+
+def test_write_measured_errors():
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "round2_parity_errors.json"), "w") as f:
+        json.dump(MEASURED, f, indent=1, sort_keys=True)

@@ -191,3 +191,26 @@ def test_decode_port_beam1_is_greedy_and_scores_are_sorted():
     wide_h, wide_s = decode_port.beam_search(P, cfg, inputs, in_len, beam=4, max_len=6, n_best=4)
     assert bool((wide_s[:, :-1] >= wide_s[:, 1:]).all())
     assert bool((wide_s[:, 0] >= scores[:, 0] - 1e-9).all())
+
+
+# ------------------------------------------------------------------------------------------------ beam search bookkeeping
+def test_beam_port_matches_reference_beam_class():
+    """oracle/decode_port.beam_advance / hypothesis against what the reference's own Beam class (Beam.py:43-74,99-116) kept for
+    seeded log-probability tables (oracle/make_golden_beam.py): scores to 1e-6, back-pointers / symbols / hypotheses exactly.
+    This pins the oracle that the GPU beam search (decode.py, st_beam_step) is compared with."""
+    from oracle import decode_port
+    g = golden("beam_advance")
+    assert tuple(g["constants"]) == (decode_port.PAD, decode_port.UNK, decode_port.BOS, decode_port.EOS)
+    for ci, (beam, V, steps, seed) in enumerate(g["cases"].tolist()):
+        lk, want_s, want_p, want_y = (g[f"c{ci}.{k}"] for k in ("word_lk", "scores", "prev_k", "next_y"))
+        scores = torch.zeros(1, beam)
+        prev_ks, next_ys = [], []
+        for t in range(lk.shape[0]):
+            scores, prev_k, y = decode_port.beam_advance(scores, torch.from_numpy(lk[t]).unsqueeze(0), first=(t == 0))
+            assert np.array_equal(prev_k[0].numpy(), want_p[t]) and np.array_equal(y[0].numpy(), want_y[t]), (ci, t)
+            assert np.abs(scores[0].numpy() - want_s[t]).max() < 1e-6
+            prev_ks.append(prev_k[0])
+            next_ys.append(y[0])
+            assert bool(y[0, 0] == decode_port.EOS) == bool(g[f"c{ci}.done"][t])          # Beam.py:70-72
+        for k in range(beam):
+            assert decode_port.hypothesis(prev_ks, next_ys, k) == g[f"c{ci}.hyps"][k].tolist()
