@@ -46,6 +46,9 @@ def parse():
                     help="activation / tensor-core operand type: tf32 = fp32 storage (BASELINE.json configs[1]), "
                          "fp16 / bf16 = 16-bit activations and operands, fp32 accumulate (configs[2])")
     ap.add_argument("--ragged", action="store_true", help="utterance lengths U[200, frames] padded to --frames (configs[2])")
+    ap.add_argument("--no-variants", action="store_true",
+                    help="skip the extra measurements of the default run: the same step with fp16 / bf16 operands, BASELINE.json "
+                         "configs[2] (bf16, ragged T <= 2000), and the reference's modules in eager PyTorch on this GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -188,6 +191,140 @@ def main_reference(args):
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
+
+
+
+# ------------------------------------------------------------------------------------------------ variants
+def measure_variant(stb, smodel, spar, sdata, dev, args, dtype, ragged, frames, steps=5, warmup=3):
+    """ms/step and frames/s of the same training step with other operand types / batch shapes (rank-0, single GPU), plus the
+    EncoderLayer forward + backward alone.  Used for the `variants` block of the default run's JSON line."""
+    import torch
+    V, d = 4337, 512
+    cfg = smodel.headline_config(num_enc_layer=args.layers, num_dec_layer=args.layers, dropout=args.dropout, compute_dtype=dtype,
+                                 max_inputs_length=max(2048, frames))
+    act = smodel.COMPUTE_DTYPES[dtype]
+    torch.manual_seed(2018)
+    net = smodel.Transformer(cfg)
+    smodel.init_parameters(net)
+    net = net.to(dev).train()
+    crit = stb.LabelSmoothingLoss(0.1, V, weight=torch.ones(V, device=dev), size_average=True, ignore_index=0).to(dev)
+    trainer = spar.DataParallelTrainer(net, d_model=d, n_warmup_steps=12000, max_grad_norm=5.0, compute_dtype=act, overlap=False)
+    host = sdata.synthetic_batch(args.batch, frames, args.targets, 80, V, seed=2018, fixed_len=not ragged, t_min=min(200, frames))
+    batch = [t.to(dev) for t in host]
+
+    def step():
+        inputs, targets, in_len, tgt_len, truth = batch
+        return trainer.train_step(lambda: crit(net(inputs, in_len, targets, tgt_len)[0].view(-1, V), truth.view(-1)))
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(warmup):
+        loss = step()
+    ms = timed(step, steps)
+    layer = net.encoder.layer_stack[0]
+    lx = torch.randn(args.batch, frames, d, device=dev).to(act)
+    lg = torch.randn(args.batch, frames, d, device=dev).to(act)
+    lmask = stb.functional.LengthMask(batch[2], frames, frames)
+    lparams = list(layer.parameters())
+
+    def layer_step():
+        for q in lparams:
+            q.grad = None
+        xin = lx.detach().requires_grad_()
+        y, _ = layer(xin, slf_attn_mask=lmask)
+        y.backward(lg)
+
+    for _ in range(3):
+        layer_step()
+    lms = timed(layer_step, 10)
+    n_tok = args.batch * frames
+    flops = 3.0 * (8.0 * n_tok * d * d + 4.0 * args.batch * 8 * frames * frames * 64 + 4.0 * n_tok * d * 2048)
+    out = {"dtype": dtype, "ragged": bool(ragged), "frames": frames, "ms_per_step": ms, "frames_per_s": n_tok / (ms * 1e-3),
+           "valid_frames_per_s": int(host[2].sum()) / (ms * 1e-3), "loss_finite": bool(torch.isfinite(loss.detach()).item()),
+           "encoder_layer_ms_fwd_bwd": lms, "encoder_layer_tflops": flops / (lms * 1e-3) / 1e12}
+    del net, trainer, batch, lx, lg
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_eager_reference_on_gpu(dev, args, steps=3, warmup=2):
+    """SURVEY.md §8(d) 'recommended extra': the reference's OWN modules (oracle/_ref, unmodified hot-path files) in eager PyTorch
+    on this GPU (cuBLAS / cuDNN library kernels, fp32 with TF32 matmuls allowed) — shows the gain over the library path."""
+    import torch
+    import types
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "transformer")):
+        return {"unavailable": "oracle/_ref not present"}
+    for name in ("editdistance", "matplotlib", "matplotlib.pyplot", "tensorboardX"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    saved = {k: v for k, v in sys.modules.items() if k == "transformer" or k.startswith("transformer.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, ref_dir)
+    try:
+        from transformer.Models import Transformer
+        from transformer.Utils import AttrDict, init_parameters
+        import transformer.Utils as U
+        from oracle import st_oracle as O
+        V, d = 4337, 512
+        cfgd = dict(feature_dim=80, vocab_size=V, max_inputs_length=2048, max_target_length=64, d_model=d, n_heads=8, d_k=64,
+                    d_v=64, d_inner_hid=2048, num_enc_layer=args.layers, num_dec_layer=args.layers, dropout=args.dropout,
+                    emb_scale=1, return_attns=False)
+        torch.manual_seed(2018)
+        model = Transformer(AttrDict(cfgd))
+        init_parameters(model)
+        model = model.to(dev).train()
+        # Utils.py:41-70 builds its masks with numpy on the host and returns CPU tensors: move them where the model lives
+        pm, fm = U.padding_info_mask, U.feature_info_mask
+        import transformer.Models as M
+        M.padding_info_mask = lambda a, b: pm(a.cpu(), b.cpu()).to(dev)
+        M.feature_info_mask = lambda a: fm(a.cpu()).to(dev)
+        crit = torch.nn.CrossEntropyLoss(ignore_index=0)                 # train.py:120 (Loss.py's class is CPU-only as written)
+        opt = torch.optim.Adam(model.parameters(), betas=(0.9, 0.98), eps=1e-9)
+        inputs, targets, in_len, tgt_len, truth = [t.to(dev) for t in O.synthetic_batch(args.batch, args.frames, args.targets, 80, V, seed=2018)]
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+        def step():
+            opt.zero_grad()
+            logits, _ = model(inputs, in_len, targets, tgt_len)
+            loss = crit(logits.reshape(-1, V), truth.reshape(-1))
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+            opt.step()
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        torch.backends.cuda.matmul.allow_tf32 = old
+        ms = e0.elapsed_time(e1) / steps
+        peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        del model, opt
+        torch.cuda.empty_cache()
+        return {"ms_per_step": ms, "frames_per_s": args.batch * args.frames / (ms * 1e-3), "peak_gib": peak,
+                "what": "the reference's Transformer (oracle/_ref: Attention.py / SubLayers.py / Layers.py / Models.py as patched by "
+                        "oracle/make_ref.py) in eager PyTorch on this GPU, allow_tf32, nn.CrossEntropyLoss + clip + Adam"}
+    except Exception as e:       # a baseline row must never take the bench down
+        return {"unavailable": repr(e)[:300]}
+    finally:
+        sys.path.remove(ref_dir)
+        for k in [k for k in sys.modules if k == "transformer" or k.startswith("transformer.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -429,13 +566,28 @@ def main_b200(args):
         except Exception as e:  # the GPU numbers stand on their own
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)[:200]}
 
+    variants, eager = None, None
+    if rank == 0 and n == 1 and not args.no_variants and not args.no_roofline:
+        del resident
+        torch.cuda.empty_cache()
+        variants = []
+        for dt_, ragged_, frames_ in (("fp16", False, args.frames), ("bf16", False, args.frames), ("bf16", True, 2 * args.frames)):
+            if (dt_, ragged_, frames_) == (args.dtype, args.ragged, args.frames):
+                continue
+            try:
+                variants.append(measure_variant(stb, smodel, spar, sdata, dev, args, dt_, ragged_, frames_))
+            except Exception as e:
+                variants.append({"dtype": dt_, "ragged": ragged_, "frames": frames_, "error": repr(e)[:200]})
+        eager = measure_eager_reference_on_gpu(dev, args)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": DTYPE_DESC[args.dtype], "data": "synthetic", "config": workload_config(args, n),
                 "valid_frames_per_s": valid_frames * n * args.steps / (ms * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "kernel_breakdown": breakdown, "encoder_layer": enc_layer, "cpu_baseline": cpu, "data_parallel": dp}
+                "kernel_breakdown": breakdown, "encoder_layer": enc_layer, "cpu_baseline": cpu, "data_parallel": dp,
+                "variants": variants, "eager_pytorch_on_gpu": eager}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
