@@ -497,16 +497,19 @@ def main_b200(args):
         lib.st_profile_reset()
         g = breakdown.get("gemm_tf32")
         traffic, traffic_note = None, None
-        try:   # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/)
-            with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+        alg_bytes = None
+        try:   # DRAM bytes per launch of the same kernels from the committed ncu launch list of one step (profiles/), averaged
+               # over EVERY GEMM launch of the step, next to the algorithmic bytes (operands + output + aux operand, once each)
+            with open(os.path.join(ROOT, "profiles", f"r2_gemm_traffic_{'tf32' if args.dtype == 'tf32' else 'bf16'}.json")) as f:
                 tj = json.load(f)
-            traffic, traffic_note = tj["dram_bytes_per_launch"], tj["source"]
+            traffic, traffic_note, alg_bytes = tj["dram_bytes_per_launch"], tj["source"], tj.get("algorithmic_bytes_per_launch")
         except Exception:
             pass
         if g:
             roofline = {"kernel": f"gemm_kernel / gemm_2sm_kernel (tcgen05 kind::{'tf32' if args.dtype == 'tf32' else 'f16'}, all projection / FFN / gradient GEMMs)",
                         "bound": "tensor", "achieved": g["rate"], "peak": peak, "unit": "TFLOP/s",
-                        "frac": g["rate"] / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                        "frac": g["rate"] / peak, "traffic": traffic, "traffic_algorithmic": alg_bytes,
+                        "traffic_source": traffic_note, "peak_source": peak_src,
                         "peak_tf32_measured": tf32_peak, "frac_of_tf32_peak": g["rate"] / tf32_peak,
                         "flops_per_launch": g["work_per_step"] / g["launches_per_step"],
                         "avg_launch_ms": g["ms_per_step"] / g["launches_per_step"],

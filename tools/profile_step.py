@@ -40,3 +40,17 @@ def tagstr(t):
     return f" M{M} N{N} K{K} {'NT NN TN'.split()[mode]} fl{fl} var{var} bn{bn * 64}"
 for (cls, work, tag), (n, ms) in sorted(groups.items(), key=lambda kv: -kv[1][1])[:60]:
     print(f"{names[cls]:15s}{tagstr(tag):44s} work {work:14.4g} x{n:3d}  total {ms:7.3f} ms  avg {ms / n * 1e3:8.1f} us  rate {work * n / ms / 1e9:8.1f} G/s*1e3")
+
+# ---- algorithmic HBM bytes of the GEMM class (operands read once, output written once, aux operand read once)
+gb = 0.0
+for (cls, work, tag), (n, ms) in groups.items():
+    if names[cls] != "gemm_tf32" or not tag: continue
+    fl, mode = (tag >> 8) & 15, (tag >> 12) & 3
+    K, N, M = ((tag >> 16) & 0x3FFFF) * 8, (tag >> 34) & 0x3FFF, (tag >> 48) * 8
+    s_in = 4 if a.dtype == "tf32" else 2
+    if a.dtype == "tf32" or fl == 5 or (fl == 2 and mode == 0) or N >= 4336: s_out = 4
+    else: s_out = 2
+    if K <= 80 or (fl == 5 and N == 80): s_in, s_out = 4, 4          # the 80-wide front-end GEMMs stay TF32
+    aux = M * N * s_in if fl in (2, 4) else 0
+    gb += n * ((M * K + N * K) * s_in + M * N * s_out + aux)
+print(f"GEMM class: algorithmic bytes per step {gb / 1e9:.3f} GB over {sum(n for (c, w, t), (n, ms) in groups.items() if names[c] == 'gemm_tf32')} launches")
