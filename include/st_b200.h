@@ -35,6 +35,13 @@ typedef struct CUstream_st* cudaStream_t;
 #define ST_DTYPE_F32 0
 #define ST_DTYPE_F16 1
 #define ST_DTYPE_BF16 2
+/* Composite operators only (st_mha_*, st_ffn_*): fp32 activations at the boundary exactly as with ST_DTYPE_F32 — inputs,
+ * outputs and their gradients are fp32 tensors, outputs rounded to a 10-bit mantissa when round_out is set — but every
+ * INTERNAL tensor-core operand (the inputs' operand copies, Q/K/V, context, FFN hidden, all internal gradients, the weight
+ * copies) is fp16, which carries the same 10-bit mantissa as TF32 at twice the MMA rate and half the bytes.  Internal
+ * gradients are scaled by a power of two derived on the device from max|dout| of each backward call.  d_k must be 64;
+ * the optional *_tf32 weight copies are then fp16.                                                                      */
+#define ST_DTYPE_F32_H16 3
 
 /* ---- library ------------------------------------------------------------------------------- */
 int st_version(void);                       /* 10000*major + 100*minor + patch */
@@ -226,6 +233,7 @@ typedef struct {
 int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32);
 int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff);
 int64_t st_ffn_saved_floats_dt(int dtype, int64_t rows, int d_model, int d_ff, int x_is_tf32);
+int64_t st_ffn_hidden_offset_dt(int dtype, int64_t rows, int d_model, int d_ff, int x_is_tf32);
 int64_t st_ffn_ws_floats_dt(int dtype, int64_t rows, int d_model, int d_ff);
 /* float offset inside `saved` of the hidden activation h = dropout1(relu(fc1(x))), shape (rows, d_ff) — test hook */
 int64_t st_ffn_hidden_offset(int64_t rows, int d_model, int d_ff, int x_is_tf32);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("ST_B200_LIB") or os.path.join(HERE, "libst_b200.so") 
 c_float_p = C.c_void_p  # raw device pointers travel as integers
 
 # ST_DTYPE_* (include/st_b200.h): element type of activation tensors
-DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
+DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F32_H16 = 0, 1, 2, 3
 i64 = C.c_int64
 u64 = C.c_uint64
 
@@ -151,6 +151,7 @@ SIGNATURES = {
     "st_ffn_ws_floats": (i64, [i64, C.c_int, C.c_int]),
     "st_ffn_saved_floats_dt": (i64, [C.c_int, i64, C.c_int, C.c_int, C.c_int]),
     "st_ffn_ws_floats_dt": (i64, [C.c_int, i64, C.c_int, C.c_int]),
+    "st_ffn_hidden_offset_dt": (i64, [C.c_int, i64, C.c_int, C.c_int, C.c_int]),
     "st_ffn_hidden_offset": (i64, [i64, C.c_int, C.c_int, C.c_int]),
     "st_ffn_fwd": (C.c_int, [C.POINTER(FfnArgs), _S]),
     "st_ffn_bwd": (C.c_int, [C.POINTER(FfnBwdArgs), _S]),

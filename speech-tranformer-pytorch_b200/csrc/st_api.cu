@@ -42,6 +42,9 @@ namespace {
 
 inline size_t esz(int dt) { return dt == ST_DTYPE_F32 ? 4 : 2; }
 inline bool is16(int dt) { return dt == ST_DTYPE_F16 || dt == ST_DTYPE_BF16; }
+inline bool is_mixed(int dt) { return dt == ST_DTYPE_F32_H16; }
+// element type of the INTERNAL tensors of a composite operator (its boundary tensors are fp32 in mixed mode)
+inline int internal_dt(int dt) { return is_mixed(dt) ? ST_DTYPE_F16 : dt; }
 // floats occupied by n activation elements of type dt
 inline int64_t act_floats(int dt, int64_t n) { return dt == ST_DTYPE_F32 ? n : (n + 1) / 2; }
 // pointer to element `off` of an activation buffer
@@ -63,10 +66,11 @@ int wgrad_splits(int m_out, int n_out, int64_t k_len, int dt) {
 // dW[out,in] (fp32) = dY[rows,out]^T * X[rows,in]   (overwrites dW); dY and X of type dt
 // zeroed: dW already holds zeros (st_*_bwd_args.grads_zeroed) — no clear needed before the split-K reductions
 int wgrad(cudaStream_t s, int dt, const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int rows, int n_out,
-          int n_in, bool zeroed = false) {
+          int n_in, bool zeroed = false, const float* unscale_amax = nullptr) {
   if (!zeroed) ST_CHECK_CUDA(cudaMemsetAsync(dw, 0, static_cast<size_t>(n_out) * n_in * sizeof(float), s));
   GemmEpilogue ep;
   ep.atomic = 1;
+  ep.unscale_amax = unscale_amax;
   return gemm_any(s, dt, GEMM_TN, dy, lddy, x, ldx, dw, n_in, 0, n_out, n_in, rows, ep, wgrad_splits(n_out, n_in, rows, dt));
 }
 
@@ -117,15 +121,19 @@ struct MhaPlan {
 
 bool mha_pre_rounded(const st_mha_args& a) {
   const int64_t dd = static_cast<int64_t>(a.d_model) * a.d_model;
-  const int dt = a.dtype;
+  const int dt = internal_dt(a.dtype);
   return a.wq_tf32 && a.wk_tf32 && a.wv_tf32 && a.wo_tf32 && a.wk_tf32 == at(a.wq_tf32, dt, dd) && a.wv_tf32 == at(a.wk_tf32, dt, dd) &&
          a.bk == a.bq + a.d_model && a.bv == a.bk + a.d_model;
 }
 
-int64_t mha_saved_floats(int dt, int B, int Lq, int Lk, int H, int d, bool same_qkv, bool same_kv, bool inputs_tf32) {
+int64_t mha_saved_floats(int dt_, int B, int Lq, int Lk, int H, int d, bool same_qkv, bool same_kv, bool inputs_tf32) {
   const int64_t M = static_cast<int64_t>(B) * Lq, Mk = static_cast<int64_t>(B) * Lk;
+  const int dt = internal_dt(dt_);
   int64_t n = 0;
-  if (dt == ST_DTYPE_F32 && !inputs_tf32) {
+  if (is_mixed(dt_)) {            // fp16 operand copies of the fp32 inputs
+    n += pad64a(dt, M * d);
+    if (!same_qkv) { n += pad64a(dt, Mk * d); if (!same_kv) n += pad64a(dt, Mk * d); }
+  } else if (dt == ST_DTYPE_F32 && !inputs_tf32) {
     n += pad64(M * d);
     if (!same_qkv) { n += pad64(Mk * d); if (!same_kv) n += pad64(Mk * d); }
   }
@@ -143,10 +151,17 @@ int plan_mha(const st_mha_args& a, MhaPlan& p) {
   p.M = static_cast<int64_t>(a.B) * a.Lq;
   p.Mk = static_cast<int64_t>(a.B) * a.Lk;
   p.d = a.d_model;
-  p.dt = a.dtype;
-  const int d = a.d_model, dt = a.dtype;
+  p.dt = internal_dt(a.dtype);
+  const int d = a.d_model, dt = p.dt;
   Carver c(a.saved, a.saved_floats);
-  if (dt != ST_DTYPE_F32 || a.inputs_tf32) {
+  if (is_mixed(a.dtype)) {
+    p.xq_r = c.take_act(dt, p.M * d);
+    if (p.same_qkv) { p.xk_r = p.xv_r = p.xq_r; }
+    else {
+      p.xk_r = c.take_act(dt, p.Mk * d);
+      p.xv_r = p.same_kv ? p.xk_r : c.take_act(dt, p.Mk * d);
+    }
+  } else if (dt != ST_DTYPE_F32 || a.inputs_tf32) {
     p.xq_r = a.q_in; p.xk_r = a.k_in; p.xv_r = a.v_in;
   } else {
     p.xq_r = c.take(p.M * d);
@@ -190,28 +205,33 @@ int plan_mha(const st_mha_args& a, MhaPlan& p) {
   return ST_OK;
 }
 
-int check_dtype(int dt, const char* who) {
-  ST_REQUIRE(dt == ST_DTYPE_F32 || dt == ST_DTYPE_F16 || dt == ST_DTYPE_BF16, "%s: bad dtype %d", who, dt);
+int check_dtype(int dt, const char* who, bool composite = false) {
+  ST_REQUIRE(dt == ST_DTYPE_F32 || dt == ST_DTYPE_F16 || dt == ST_DTYPE_BF16 || (composite && dt == ST_DTYPE_F32_H16),
+             "%s: bad dtype %d", who, dt);
   return ST_OK;
 }
 
 int check_mha(const st_mha_args& a) {
-  ST_TRY(check_dtype(a.dtype, "st_mha"));
+  ST_TRY(check_dtype(a.dtype, "st_mha", true));
   ST_REQUIRE(a.B > 0 && a.Lq > 0 && a.Lk > 0 && a.H > 0, "st_mha: empty problem");
   ST_REQUIRE(a.d_model == a.H * a.dk, "st_mha: d_model (%d) != n_head (%d) * d_k (%d)", a.d_model, a.H, a.dk);
-  if (is16(a.dtype)) ST_REQUIRE(a.dk == 64, "st_mha: 16-bit activations need d_k = 64 (got %d)", a.dk);
+  if (is_mixed(a.dtype))
+    ST_REQUIRE(a.residual == a.q_in || a.residual == a.k_in || a.residual == a.v_in,
+               "st_mha: with ST_DTYPE_F32_H16 the residual must be one of the inputs");
+  if (is16(a.dtype) || is_mixed(a.dtype)) ST_REQUIRE(a.dk == 64, "st_mha: 16-bit operands need d_k = 64 (got %d)", a.dk);
   else ST_REQUIRE(a.dk == 32 || a.dk == 64 || a.dk == 128, "st_mha: d_k must be 32, 64 or 128 (got %d)", a.dk);
   return ST_OK;
 }
 
-int64_t mha_ws_floats(int dt, int B, int Lq, int Lk, int H, int d) {
+int64_t mha_ws_floats(int dt_, int B, int Lq, int Lk, int H, int d) {
   const int64_t M = static_cast<int64_t>(B) * Lq, Mk = static_cast<int64_t>(B) * Lk;
-  // backward: dz, dctx, dprojq, dprojk, dprojv, delta
-  return 2 * pad64a(dt, M * d) + pad64a(dt, M * 3 * d) + 2 * pad64a(dt, Mk * 2 * d) + pad64(static_cast<int64_t>(B) * H * Lq) + 64;
+  const int dt = internal_dt(dt_);
+  // backward: dz, dctx, dprojq, dprojk, dprojv, delta, amax
+  return 2 * pad64a(dt, M * d) + pad64a(dt, M * 3 * d) + 2 * pad64a(dt, Mk * 2 * d) + pad64(static_cast<int64_t>(B) * H * Lq) + 128;
 }
 
 void fill_attn(AttnArgs& at_, const st_mha_args& a, const MhaPlan& p) {
-  at_.B = a.B; at_.H = a.H; at_.Lq = a.Lq; at_.Lk = a.Lk; at_.dk = a.dk; at_.dtype = a.dtype;
+  at_.B = a.B; at_.H = a.H; at_.Lq = a.Lq; at_.Lk = a.Lk; at_.dk = a.dk; at_.dtype = p.dt;
   at_.q = p.projq; at_.ldq = p.ldpq; at_.k = p.projk; at_.ldk = p.ldpk; at_.v = p.projv; at_.ldv = p.ldpv;
   at_.mask = a.mask; at_.ms_b = a.ms_b; at_.ms_q = a.ms_q; at_.ms_k = a.ms_k;
   at_.k_len = a.k_len; at_.causal = a.causal;
@@ -400,7 +420,8 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
   ST_TRY(check_mha(a));
   MhaPlan p;
   ST_TRY(plan_mha(a, p));
-  const int d = a.d_model, dt = a.dtype;
+  const int d = a.d_model, dt = p.dt;
+  const bool mixed = is_mixed(a.dtype);
   const int M = static_cast<int>(p.M), Mk = static_cast<int>(p.Mk);
   const int64_t dd = static_cast<int64_t>(d) * d;
 
@@ -414,8 +435,15 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
     ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + d, a.bk, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ST_CHECK_CUDA(cudaMemcpyAsync(p.b_pack + 2 * d, a.bv, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
-  // 2. TF32 copies of the inputs (fp32 path only: 16-bit activations are GEMM operands as they are)
-  if (dt == ST_DTYPE_F32 && !a.inputs_tf32) {
+  // 2. operand copies of the inputs: TF32 rounding (fp32 path), fp16 conversion (mixed: exact for TF32-representable
+  //    inputs); 16-bit activations are GEMM operands as they are
+  if (mixed) {
+    ST_TRY(cast_2d(s, a.q_in, ST_DTYPE_F32, d, const_cast<void*>(p.xq_r), dt, d, M, d));
+    if (!p.same_qkv) {
+      ST_TRY(cast_2d(s, a.k_in, ST_DTYPE_F32, d, const_cast<void*>(p.xk_r), dt, d, Mk, d));
+      if (!p.same_kv) ST_TRY(cast_2d(s, a.v_in, ST_DTYPE_F32, d, const_cast<void*>(p.xv_r), dt, d, Mk, d));
+    }
+  } else if (dt == ST_DTYPE_F32 && !a.inputs_tf32) {
     ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.q_in), d, const_cast<float*>(static_cast<const float*>(p.xq_r)), d, M, d));
     if (!p.same_qkv) {
       ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.k_in), d, const_cast<float*>(static_cast<const float*>(p.xk_r)), d, Mk, d));
@@ -450,10 +478,11 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
   // 5. output projection + bias + residual (Attention.py:92,94): the pre-LayerNorm sum stays fp32
   GemmEpilogue eo;
   eo.bias = a.bo; eo.aux = a.residual; eo.ldaux = d; eo.aux_mode = 1;
+  if (mixed) eo.aux = (a.residual == a.q_in) ? p.xq_r : (a.residual == a.k_in ? p.xk_r : p.xv_r);   // the fp16 copy of the residual
   ST_TRY(gemm_any(s, dt, GEMM_NT, p.ctx, d, p.wo_r, d, p.z, d, 0, M, d, d, eo));
   // 6. LayerNorm (Attention.py:94)
-  return add_ln_fwd_any(s, ST_DTYPE_F32, dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out,
-                        DropoutCfg{});
+  return add_ln_fwd_any(s, ST_DTYPE_F32, mixed ? ST_DTYPE_F32 : dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d,
+                        a.eps, a.round_out, DropoutCfg{});
 }
 
 int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
@@ -464,10 +493,11 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   ST_TRY(check_mha(a));
   MhaPlan p;
   ST_TRY(plan_mha(a, p));
-  const int d = a.d_model, dt = a.dtype;
+  const int d = a.d_model, dt = p.dt;
+  const bool mixed = is_mixed(a.dtype);
   const int M = static_cast<int>(p.M), Mk = static_cast<int>(p.Mk);
   const int64_t dd = static_cast<int64_t>(d) * d;
-  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= mha_ws_floats(dt, a.B, a.Lq, a.Lk, a.H, d), "st_mha_bwd: workspace too small");
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= mha_ws_floats(a.dtype, a.B, a.Lq, a.Lk, a.H, d), "st_mha_bwd: workspace too small");
   Carver w(a.ws, a.ws_floats);
   void* dz = w.take_act(dt, p.M * d);
   void* dctx = w.take_act(dt, p.M * d);
@@ -479,18 +509,26 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
     else { dpk = w.take_act(dt, p.Mk * d); dpv = w.take_act(dt, p.Mk * d); }
   }
   float* delta = w.take(static_cast<int64_t>(a.B) * a.H * a.Lq);
+  // mixed mode: the gradient scale of this call, a power of two derived on the device from max|dout| (st_common.cuh)
+  float* amax = mixed ? w.take(64) : nullptr;
   const bool fused_bias = dt == ST_DTYPE_F32 && attn_bwd_fuses_bias(a.dk);
 
   // LayerNorm backward; dbo = column sums of dz
   ST_CLEAR(b.dln_g, d);
   ST_CLEAR(b.dln_b, d);
   ST_CLEAR(b.dbo, d);
-  ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d, 1, DropoutCfg{}));
+  if (mixed) {
+    ST_TRY(amax_abs(s, static_cast<const float*>(b.dout), p.M * d, amax));
+    ST_TRY(add_ln_bwd_mixed(s, static_cast<const float*>(b.dout), p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d,
+                            DropoutCfg{}, amax));
+  } else {
+    ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d, 1, DropoutCfg{}));
+  }
   // output projection backward
   {
     GemmEpilogue e; e.round_tf32 = 1;
     ST_TRY(gemm_any(s, dt, GEMM_NN, dz, d, p.wo_r, d, dctx, d, 1, M, d, d, e));
-    ST_TRY(wgrad(s, dt, dz, d, p.ctx, d, b.dwo, M, d, d, zeroed));
+    ST_TRY(wgrad(s, dt, dz, d, p.ctx, d, b.dwo, M, d, d, zeroed, amax));
   }
   // attention core backward
   {
@@ -513,46 +551,53 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   if (pack_qkv) {
     if (!fused_bias) {
       ST_CLEAR(b.dbq, 3 * d);
-      ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, 3 * d, b.dbq));
+      ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, 3 * d, b.dbq, amax));
     }
-    ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d, zeroed));
+    ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d, zeroed, amax));
   } else {
     if (!fused_bias) {
       ST_CLEAR(b.dbq, d);
-      ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, d, b.dbq));
+      ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, d, b.dbq, amax));
     }
-    ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d, zeroed));
+    ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d, zeroed, amax));
     if (pack_kv) {
       if (!fused_bias) {
         ST_CLEAR(b.dbk, 2 * d);
-        ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, 2 * d, b.dbk));
+        ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, 2 * d, b.dbk, amax));
       }
-      ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d, zeroed));
+      ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d, zeroed, amax));
     } else {
       if (!fused_bias) {
         ST_CLEAR(b.dbk, d);
         ST_CLEAR(b.dbv, d);
-        ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, d, b.dbk));
-        ST_TRY(colsum_add_any(s, dt, dpv, p.ldpv, Mk, d, b.dbv));
+        ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, d, b.dbk, amax));
+        ST_TRY(colsum_add_any(s, dt, dpv, p.ldpv, Mk, d, b.dbv, amax));
       }
-      ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d, zeroed));
-      ST_TRY(wgrad(s, dt, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d, zeroed));
+      ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d, zeroed, amax));
+      ST_TRY(wgrad(s, dt, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d, zeroed, amax));
     }
   }
   // input gradients; the residual branch contributes dz to EXACTLY ONE input buffer: the first of q, k, v that aliases the
   // residual tensor (aliased inputs receive the sum of their buffers from the caller)
   const bool res_q = (a.residual == a.q_in), res_k = !res_q && (a.residual == a.k_in),
              res_v = !res_q && !res_k && (a.residual == a.v_in);
-  auto with_res = [&](bool on) { GemmEpilogue e; if (on) { e.aux = dz; e.ldaux = d; e.aux_mode = 1; } return e; };
+  // mixed mode: the input gradients leave the operator as fp32 and shed the gradient scale in the epilogue
+  const int out_lp = mixed ? 0 : 1;
+  auto with_res = [&](bool on) {
+    GemmEpilogue e;
+    if (on) { e.aux = dz; e.ldaux = d; e.aux_mode = 1; }
+    e.unscale_amax = amax;
+    return e;
+  };
   if (p.same_qkv) {
-    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, 1, M, d, 3 * d, with_res(res_q)));
+    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, out_lp, M, d, 3 * d, with_res(res_q)));
   } else {
-    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, 1, M, d, d, with_res(res_q)));
+    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, out_lp, M, d, d, with_res(res_q)));
     if (p.same_kv) {
-      ST_TRY(gemm_any(s, dt, GEMM_NN, dpk, p.ldpk, at(p.w_r, dt, dd), d, b.dk_in, d, 1, Mk, d, 2 * d, with_res(res_k || res_v)));
+      ST_TRY(gemm_any(s, dt, GEMM_NN, dpk, p.ldpk, at(p.w_r, dt, dd), d, b.dk_in, d, out_lp, Mk, d, 2 * d, with_res(res_k || res_v)));
     } else {
-      ST_TRY(gemm_any(s, dt, GEMM_NN, dpk, p.ldpk, at(p.w_r, dt, dd), d, b.dk_in, d, 1, Mk, d, d, with_res(res_k)));
-      ST_TRY(gemm_any(s, dt, GEMM_NN, dpv, p.ldpv, at(p.w_r, dt, 2 * dd), d, b.dv_in, d, 1, Mk, d, d, with_res(res_v)));
+      ST_TRY(gemm_any(s, dt, GEMM_NN, dpk, p.ldpk, at(p.w_r, dt, dd), d, b.dk_in, d, out_lp, Mk, d, d, with_res(res_k)));
+      ST_TRY(gemm_any(s, dt, GEMM_NN, dpv, p.ldpv, at(p.w_r, dt, 2 * dd), d, b.dv_in, d, out_lp, Mk, d, d, with_res(res_v)));
     }
   }
   if (!(res_q || res_k || res_v)) {
@@ -566,9 +611,11 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
 namespace {
 struct FfnPlan { const void* x_r; void* h; float *z, *mean, *rstd; void *w1_r, *w2_r; };
 int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
-  const int dt = a.dtype;
+  const int dt = internal_dt(a.dtype);
   Carver c(a.saved, a.saved_floats);
-  p.x_r = (dt != ST_DTYPE_F32 || a.x_is_tf32) ? a.x : c.take(a.rows * a.d_model);
+  // NOTE: the hidden activation must stay the FIRST 16-bit / fp32 tensor after the optional input copy (st_ffn_hidden_offset)
+  if (is_mixed(a.dtype)) p.x_r = c.take_act(dt, a.rows * a.d_model);
+  else p.x_r = (dt != ST_DTYPE_F32 || a.x_is_tf32) ? a.x : c.take(a.rows * a.d_model);
   p.h = c.take_act(dt, a.rows * a.d_ff);
   p.z = c.take(a.rows * a.d_model);
   p.mean = c.take(a.rows);
@@ -583,11 +630,19 @@ int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
   return ST_OK;
 }
 constexpr uint64_t kSeedMix1 = 0x5DEECE66Dull, kSeedMix2 = 0xB5297A4D3F84D5B5ull;
-int64_t ffn_saved_floats(int dt, int64_t rows, int d_model, int d_ff, int x_is_tf32) {
-  return ((dt != ST_DTYPE_F32 || x_is_tf32) ? 0 : pad64(rows * d_model)) + pad64a(dt, rows * d_ff) + pad64(rows * d_model) +
+int64_t ffn_input_copy_floats(int dt_, int64_t rows, int d_model, int x_is_tf32) {
+  if (is_mixed(dt_)) return pad64a(ST_DTYPE_F16, rows * d_model);
+  return (dt_ != ST_DTYPE_F32 || x_is_tf32) ? 0 : pad64(rows * d_model);
+}
+int64_t ffn_saved_floats(int dt_, int64_t rows, int d_model, int d_ff, int x_is_tf32) {
+  const int dt = internal_dt(dt_);
+  return ffn_input_copy_floats(dt_, rows, d_model, x_is_tf32) + pad64a(dt, rows * d_ff) + pad64(rows * d_model) +
          2 * pad64(rows) + 2 * pad64a(dt, static_cast<int64_t>(d_ff) * d_model);
 }
-int64_t ffn_ws_floats(int dt, int64_t rows, int d_model, int d_ff) { return pad64a(dt, rows * d_model) + pad64a(dt, rows * d_ff) + 64; }
+int64_t ffn_ws_floats(int dt_, int64_t rows, int d_model, int d_ff) {
+  const int dt = internal_dt(dt_);
+  return pad64a(dt, rows * d_model) + pad64a(dt, rows * d_ff) + 128;
+}
 }  // namespace
 
 int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32) {
@@ -600,22 +655,29 @@ int64_t st_ffn_hidden_offset(int64_t rows, int d_model, int d_ff, int x_is_tf32)
   (void)d_ff;
   return x_is_tf32 ? 0 : pad64(rows * d_model);
 }
+int64_t st_ffn_hidden_offset_dt(int dtype, int64_t rows, int d_model, int d_ff, int x_is_tf32) {
+  (void)d_ff;
+  return ffn_input_copy_floats(dtype, rows, d_model, x_is_tf32);
+}
 int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff) { return ffn_ws_floats(ST_DTYPE_F32, rows, d_model, d_ff); }
 int64_t st_ffn_ws_floats_dt(int dtype, int64_t rows, int d_model, int d_ff) { return ffn_ws_floats(dtype, rows, d_model, d_ff); }
 
 int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
   ST_REQUIRE(ap != nullptr, "st_ffn_fwd: null args");
   const st_ffn_args& a = *ap;
-  ST_TRY(check_dtype(a.dtype, "st_ffn"));
+  ST_TRY(check_dtype(a.dtype, "st_ffn", true));
   ST_REQUIRE(a.rows > 0 && a.rows < (1ll << 31) && a.d_model > 0 && a.d_ff > 0, "st_ffn: bad shape");
   FfnPlan p;
   ST_TRY(plan_ffn(a, p));
-  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff, dt = a.dtype;
+  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff, dt = internal_dt(a.dtype);
+  const bool mixed = is_mixed(a.dtype);
   if (!(a.w1_tf32 && a.w2_tf32)) {
     ST_TRY(weight_copy(s, dt, a.w1, p.w1_r, f, d));
     ST_TRY(weight_copy(s, dt, a.w2, p.w2_r, d, f));
   }
-  if (dt == ST_DTYPE_F32 && !a.x_is_tf32)
+  if (mixed)
+    ST_TRY(cast_2d(s, a.x, ST_DTYPE_F32, d, const_cast<void*>(p.x_r), dt, d, M, d));
+  else if (dt == ST_DTYPE_F32 && !a.x_is_tf32)
     ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.x), d, const_cast<float*>(static_cast<const float*>(p.x_r)), d, M, d));
   // h = dropout1(relu(fc1(x)))                                           SubLayers.py:25
   GemmEpilogue e1;
@@ -625,11 +687,11 @@ int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
   ST_TRY(gemm_any(s, dt, GEMM_NT, p.x_r, d, p.w1_r, d, p.h, f, 1, M, f, d, e1));
   // z = x + fc2(h)  (fp32)                                               SubLayers.py:26-27
   GemmEpilogue e2;
-  e2.bias = a.b2; e2.aux = a.x; e2.ldaux = d; e2.aux_mode = 1;
+  e2.bias = a.b2; e2.aux = mixed ? p.x_r : a.x; e2.ldaux = d; e2.aux_mode = 1;
   ST_TRY(gemm_any(s, dt, GEMM_NT, p.h, f, p.w2_r, f, p.z, d, 0, M, d, f, e2));
   // out = dropout2(LN(z))                                                SubLayers.py:27
-  return add_ln_fwd_any(s, ST_DTYPE_F32, dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d, a.eps, a.round_out,
-                        make_dropout(a.dropout_p, a.seed ^ kSeedMix2));
+  return add_ln_fwd_any(s, ST_DTYPE_F32, mixed ? ST_DTYPE_F32 : dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d,
+                        a.eps, a.round_out, make_dropout(a.dropout_p, a.seed ^ kSeedMix2));
 }
 
 int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
@@ -637,31 +699,41 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   const st_ffn_bwd_args& b = *bp;
   const bool zeroed = b.grads_zeroed != 0;
   const st_ffn_args& a = b.f;
-  ST_TRY(check_dtype(a.dtype, "st_ffn"));
+  ST_TRY(check_dtype(a.dtype, "st_ffn", true));
   FfnPlan p;
   ST_TRY(plan_ffn(a, p));
-  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff, dt = a.dtype;
-  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= ffn_ws_floats(dt, a.rows, d, f), "st_ffn_bwd: workspace too small");
+  const int M = static_cast<int>(a.rows), d = a.d_model, f = a.d_ff, dt = internal_dt(a.dtype);
+  const bool mixed = is_mixed(a.dtype);
+  ST_REQUIRE(a.ws != nullptr && a.ws_floats >= ffn_ws_floats(a.dtype, a.rows, d, f), "st_ffn_bwd: workspace too small");
   Carver w(a.ws, a.ws_floats);
   void* dz = w.take_act(dt, a.rows * d);
   void* dh = w.take_act(dt, a.rows * f);
+  float* amax = mixed ? w.take(64) : nullptr;     // gradient scale of this call (see st_mha_bwd)
   ST_CLEAR(b.dln_g, d);
   ST_CLEAR(b.dln_b, d);
   ST_CLEAR(b.db2, d);
   ST_CLEAR(b.db1, f);
-  ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d, 1,
-                        make_dropout(a.dropout_p, a.seed ^ kSeedMix2)));
+  if (mixed) {
+    ST_TRY(amax_abs(s, static_cast<const float*>(b.dout), a.rows * d, amax));
+    ST_TRY(add_ln_bwd_mixed(s, static_cast<const float*>(b.dout), p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d,
+                            make_dropout(a.dropout_p, a.seed ^ kSeedMix2), amax));
+  } else {
+    ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d, 1,
+                          make_dropout(a.dropout_p, a.seed ^ kSeedMix2)));
+  }
   // dh = (dz W2) * [h > 0] * dropout1 scale
   GemmEpilogue e;
   e.aux = p.h; e.ldaux = f; e.aux_mode = 2; e.round_tf32 = 1;
   e.aux_scale = make_dropout(a.dropout_p, 0).scale;
   e.colsum = b.db1;   // db1 = column sums of dh, accumulated by the epilogue that produces dh
+  e.unscale_amax = amax;
   ST_TRY(gemm_any(s, dt, GEMM_NN, dz, d, p.w2_r, f, dh, f, 1, M, f, d, e));
-  ST_TRY(wgrad(s, dt, dz, d, p.h, f, b.dw2, M, d, f, zeroed));
-  ST_TRY(wgrad(s, dt, dh, f, p.x_r, d, b.dw1, M, f, d, zeroed));
+  ST_TRY(wgrad(s, dt, dz, d, p.h, f, b.dw2, M, d, f, zeroed, amax));
+  ST_TRY(wgrad(s, dt, dh, f, p.x_r, d, b.dw1, M, f, d, zeroed, amax));
   GemmEpilogue ex;
   ex.aux = dz; ex.ldaux = d; ex.aux_mode = 1;
-  return gemm_any(s, dt, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, 1, M, d, f, ex);
+  ex.unscale_amax = amax;
+  return gemm_any(s, dt, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, mixed ? 0 : 1, M, d, f, ex);
 }
 
 

@@ -401,6 +401,20 @@ template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
 template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t w) {
   return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
 }
+// Power-of-two gradient scale of the fp32-boundary / fp16-operand mode ("mixed", ST_DTYPE_F32_H16): a backward operator
+// measures amax = max|dout| of the gradient it receives and every kernel of that operator derives the SAME scale from it:
+// 2^(4 - ceil(log2(amax))) puts the largest incoming gradient in [8, 16], more than three decades below fp16's maximum
+// (head-room for the sums the backward GEMMs form and for attention's boosted dS) and five above its smallest normal.
+// amax == 0 (or not finite) -> 1.
+__device__ __forceinline__ float grad_scale_from_amax(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);                 // amax = m * 2^e, m in [0.5, 1)  ->  ceil(log2(amax)) <= e
+  e = 4 - e;
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return ldexpf(1.f, e);
+}
+
 // scalar conversions through the same roundings
 template <typename T> __device__ __forceinline__ T from_f32(float x);
 template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }

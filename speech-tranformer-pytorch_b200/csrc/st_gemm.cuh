@@ -30,6 +30,10 @@ struct GemmEpilogue {
   // optional [N]: column sums of the stored values are ACCUMULATED here (caller zeroes) — the bias gradient of the
   // layer whose input gradient this GEMM produces, for free instead of a separate pass over the output
   float* colsum = nullptr;
+  // optional device scalar (mixed mode, st_common.cuh grad_scale_from_amax): the operands carry a power-of-two gradient
+  // scale S derived from *unscale_amax; fp32 results that leave the operator (split-K weight gradients, the fp32 input
+  // gradient of the AUX_ADD epilogue, the column sums) are multiplied by 1/S.  16-bit outputs stay scaled.
+  const float* unscale_amax = nullptr;
 };
 
 // k_splits > 1 requires ep.atomic and a zero-initialised C.

@@ -156,6 +156,10 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
   }
   const int n_chunks = min(BN / 32, (p.N - n_blk * BN + 31) >> 5);
   const bool do_colsum = ep.colsum != nullptr;
+  // mixed mode: fp32 results that leave the operator shed the gradient scale its 16-bit operands carry
+  constexpr bool OSC = Elem<T>::k16 && (ATOMIC || (sizeof(OutT) == 4 && (AUX == 1 || F == EPI_PLAIN)) || AUX == 2);
+  const bool has_osc = OSC && ep.unscale_amax != nullptr;
+  const float osc = has_osc ? 1.f / grad_scale_from_amax(__ldg(ep.unscale_amax)) : 1.f;
 #pragma unroll 1
   for (int c = half; c < n_chunks; c += EPI_WARPS / 4) {
     const int col = col0 + c * 32;
@@ -205,6 +209,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
           v[2] = aux4[i].z > 0.f ? v[2] * ep.aux_scale : 0.f;
           v[3] = aux4[i].w > 0.f ? v[3] * ep.aux_scale : 0.f;
         }
+        if (OSC && AUX != 2 && has_osc) { v[0] *= osc; v[1] *= osc; v[2] *= osc; v[3] *= osc; }
         cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
         if (ROUND) {
 #pragma unroll
@@ -224,7 +229,8 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
         cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], 8);
         cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], 16);
       }
-      if (lane < 8 && col_ok) red_add_v4(ep.colsum + col, cs[0], cs[1], cs[2], cs[3]);
+      if (lane < 8 && col_ok) red_add_v4(ep.colsum + col, cs[0] * (AUX == 2 ? osc : 1.f), cs[1] * (AUX == 2 ? osc : 1.f),
+                                         cs[2] * (AUX == 2 ? osc : 1.f), cs[3] * (AUX == 2 ? osc : 1.f));
     }
     __syncwarp();
   }
@@ -236,6 +242,7 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
                                               int quarter, int half, int lane) {
   const GemmEpilogue& ep = p.ep;
   const bool c_lp = Elem<T>::k16 && p.c_lp;
+  const float osc = (Elem<T>::k16 && !c_lp && ep.unscale_amax != nullptr) ? 1.f / grad_scale_from_amax(__ldg(ep.unscale_amax)) : 1.f;
   const bool vec_ok = !Elem<T>::k16 && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0);
   const int lcol = (lane & 7) * 4;
   const int lrow = lane >> 3;
@@ -290,7 +297,7 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
         if (ep.aux_mode == 1) x += to_f32(ap[t]);
         if (ep.aux_mode == 2) x = to_f32(ap[t]) > 0.f ? x * ep.aux_scale : 0.f;
         if (!Elem<T>::k16 && ep.round_tf32) x = tf32_rna(x);
-        v[t] = x;
+        v[t] = x * osc;
       }
       if (c_lp) {
         T* cp = static_cast<T*>(p.C) + coff;

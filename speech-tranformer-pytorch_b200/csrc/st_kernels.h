@@ -32,7 +32,13 @@ int add_ln_fwd_any(cudaStream_t stream, int in_dt, int out_dt, const void* a, co
 int add_ln_bwd_any(cudaStream_t stream, int dt, const void* dy, const float* z, const float* mean, const float* rstd,
                    const float* gamma, void* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, int round_out,
                    const DropoutCfg& drop, const float* gate = nullptr, float gate_scale = 1.f);
-int colsum_add_any(cudaStream_t stream, int dt, const void* x, int64_t ld, int64_t rows, int cols, float* out);
+// amax (optional device scalar): the sums are divided by grad_scale_from_amax(*amax) (mixed mode, st_common.cuh)
+int colsum_add_any(cudaStream_t stream, int dt, const void* x, int64_t ld, int64_t rows, int cols, float* out,
+                   const float* amax = nullptr);
+int amax_abs(cudaStream_t stream, const float* x, int64_t n, float* out);
+int add_ln_bwd_mixed(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                     void* dz16, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, const DropoutCfg& drop,
+                     const float* amax);
 int cast_2d(cudaStream_t stream, const void* src, int src_dt, int64_t lds, void* dst, int dst_dt, int64_t ldd, int64_t rows, int cols,
             float scale = 1.f);
 int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols);

@@ -165,20 +165,23 @@ add_ln_fwd_kernel(const InT* __restrict__ a, const InT* __restrict__ b, const fl
 // ---------------------------------------------------------------- backward
 // dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat;  dbeta += dy;
 // dzsum += dz (the bias gradient of the linear layer that produced z).
-// ActT: element type of dy and dz (fp32, or the 16-bit activation type); z, statistics, gamma, gate are fp32.
-template <int VPL, typename ActT, bool WIDE>
+// DyT / DzT: element types of dy and dz (fp32, or a 16-bit activation type); z, statistics, gamma, gate are fp32.
+// amax: optional device scalar max|dy| — the stored dz is multiplied by grad_scale_from_amax(*amax) (mixed mode: fp32 dy,
+// fp16 dz); dgamma / dbeta / dzsum are accumulated from the UNSCALED values.
+template <int VPL, typename DyT, typename DzT, bool WIDE>
 __global__ void __launch_bounds__(LN_THREADS)
-add_ln_bwd_kernel(const ActT* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
-                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, ActT* __restrict__ dz,
+add_ln_bwd_kernel(const DyT* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
+                  const float* __restrict__ rstd_in, const float* __restrict__ gamma, DzT* __restrict__ dz,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dzsum, int64_t rows,
                   int d, int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
-                  const float* __restrict__ gate, float gate_scale) {
+                  const float* __restrict__ gate, float gate_scale, const float* __restrict__ amax) {
   pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
   pdl_trigger();
   __shared__ float red[LN_WARPS][32 * 4 + 4];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const float inv_d = 1.f / static_cast<float>(d);
+  const float out_scale = amax ? grad_scale_from_amax(*amax) : 1.f;
 
   float4 g[VPL];
   float4 acc_g[VPL], acc_b[VPL], acc_z[VPL];
@@ -258,7 +261,11 @@ add_ln_bwd_kernel(const ActT* __restrict__ dy, const float* __restrict__ z, cons
           o[2] = gv.z > 0.f ? o[2] * gate_scale : 0.f; o[3] = gv.w > 0.f ? o[3] * gate_scale : 0.f;
         }
         acc_z[i].x += o[0]; acc_z[i].y += o[1]; acc_z[i].z += o[2]; acc_z[i].w += o[3];
-        if (sizeof(ActT) == 4 && round_out) {
+        if (amax) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o[t] *= out_scale;
+        }
+        if (sizeof(DzT) == 4 && round_out) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) o[t] = tf32_rna(o[t]);
         }
@@ -328,9 +335,24 @@ round_tf32_scalar_kernel(const float* __restrict__ src, int64_t lds, float* __re
 }
 
 // ---------------------------------------------------------------- column sums: out[c] += sum_r X[r,c]
+// out <- max(out, max|x|) as an atomicMax on the bit pattern (non-negative floats order like unsigned integers)
+__global__ void __launch_bounds__(256)
+amax_kernel(const float* __restrict__ x, int64_t n4, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  float m = 0.f;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = x4[i];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
+colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out, const float* __restrict__ amax) {
   pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
   pdl_trigger();
   __shared__ float red[8][132];
@@ -351,6 +373,7 @@ colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
     const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (amax) s *= 1.f / grad_scale_from_amax(*amax);      // mixed mode: x carries the operator's gradient scale
     if (cc < cols) atomicAdd(out + cc, s);
   }
 }
@@ -428,21 +451,22 @@ int add_ln_fwd_any(cudaStream_t stream, int in_dt, int out_dt, const void* a, co
 
 namespace {
 
-template <typename ActT>
-int add_ln_bwd_t(cudaStream_t stream, const ActT* dy, const float* z, const float* mean, const float* rstd,
-                 const float* gamma, ActT* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
-                 int round_out, const DropoutCfg& drop, const float* gate, float gate_scale) {
+template <typename DyT, typename DzT>
+int add_ln_bwd_t(cudaStream_t stream, const DyT* dy, const float* z, const float* mean, const float* rstd,
+                 const float* gamma, DzT* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
+                 int round_out, const DropoutCfg& drop, const float* gate, float gate_scale, const float* amax = nullptr) {
   if (rows == 0) return ST_OK;
   ST_REQUIRE(!gate || aligned16(gate), "add_ln_bwd: gate must be 16-byte aligned");
   ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_bwd: d=%d must be a multiple of 4 and <= 1024", d);
-  ST_REQUIRE(aligned8(dy) && aligned16(z) && aligned16(gamma) && aligned8(dz) && (sizeof(ActT) == 2 || (aligned16(dy) && aligned16(dz))),
+  ST_REQUIRE(aligned8(dy) && aligned16(z) && aligned16(gamma) && aligned8(dz) && (sizeof(DyT) == 2 || aligned16(dy)) &&
+                 (sizeof(DzT) == 2 || aligned16(dz)),
              "add_ln_bwd: pointers must be 16-byte aligned");
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 4);
-  ProfScope prof(stream, PROF_LN_BWD, 1.0 * rows * d * 4 + 2.0 * rows * d * sizeof(ActT));
+  ProfScope prof(stream, PROF_LN_BWD, 1.0 * rows * d * 4 + 1.0 * rows * d * (sizeof(DyT) + sizeof(DzT)));
 #define ST_LAUNCH(VPL, W)                                                                                      \
-  ST_CHECK_CUDA(launch_pdl(add_ln_bwd_kernel<VPL, ActT, W>, dim3(grid), dim3(LN_THREADS), 0, stream, dy, z, mean, rstd, gamma, dz, \
-                           dgamma, dbeta, dzsum, rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, gate_scale))
-  constexpr bool k16 = sizeof(ActT) == 2;
+  ST_CHECK_CUDA(launch_pdl(add_ln_bwd_kernel<VPL, DyT, DzT, W>, dim3(grid), dim3(LN_THREADS), 0, stream, dy, z, mean, rstd, gamma, dz, \
+                           dgamma, dbeta, dzsum, rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, gate_scale, amax))
+  constexpr bool k16 = sizeof(DyT) == 2 || sizeof(DzT) == 2;
   const bool wide = k16 && (d % 256) == 0 && aligned16(dy) && aligned16(dz) && !gate;
   if (wide) {
     if constexpr (k16) {
@@ -464,7 +488,15 @@ int add_ln_bwd_t(cudaStream_t stream, const ActT* dy, const float* z, const floa
 int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd,
                const float* gamma, float* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
                int round_out, const DropoutCfg& drop, const float* gate, float gate_scale) {
-  return add_ln_bwd_t<float>(stream, dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum, rows, d, round_out, drop, gate, gate_scale);
+  return add_ln_bwd_t<float, float>(stream, dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum, rows, d, round_out, drop, gate, gate_scale);
+}
+
+// mixed mode: fp32 dy -> fp16 dz scaled by grad_scale_from_amax(*amax)
+int add_ln_bwd_mixed(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                     void* dz16, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, const DropoutCfg& drop,
+                     const float* amax) {
+  return add_ln_bwd_t<float, __half>(stream, dy, z, mean, rstd, gamma, static_cast<__half*>(dz16), dgamma, dbeta, dzsum, rows, d, 0, drop,
+                                     nullptr, 1.f, amax);
 }
 
 // dt: element type of dy and dz
@@ -473,14 +505,15 @@ int add_ln_bwd_any(cudaStream_t stream, int dt, const void* dy, const float* z, 
                    const DropoutCfg& drop, const float* gate, float gate_scale) {
   switch (dt) {
     case ST_DTYPE_F32:
-      return add_ln_bwd_t<float>(stream, static_cast<const float*>(dy), z, mean, rstd, gamma, static_cast<float*>(dz), dgamma, dbeta,
-                                 dzsum, rows, d, round_out, drop, gate, gate_scale);
+      return add_ln_bwd_t<float, float>(stream, static_cast<const float*>(dy), z, mean, rstd, gamma, static_cast<float*>(dz), dgamma,
+                                        dbeta, dzsum, rows, d, round_out, drop, gate, gate_scale);
     case ST_DTYPE_F16:
-      return add_ln_bwd_t<__half>(stream, static_cast<const __half*>(dy), z, mean, rstd, gamma, static_cast<__half*>(dz), dgamma, dbeta,
-                                  dzsum, rows, d, round_out, drop, gate, gate_scale);
+      return add_ln_bwd_t<__half, __half>(stream, static_cast<const __half*>(dy), z, mean, rstd, gamma, static_cast<__half*>(dz), dgamma,
+                                          dbeta, dzsum, rows, d, round_out, drop, gate, gate_scale);
     case ST_DTYPE_BF16:
-      return add_ln_bwd_t<__nv_bfloat16>(stream, static_cast<const __nv_bfloat16*>(dy), z, mean, rstd, gamma,
-                                         static_cast<__nv_bfloat16*>(dz), dgamma, dbeta, dzsum, rows, d, round_out, drop, gate, gate_scale);
+      return add_ln_bwd_t<__nv_bfloat16, __nv_bfloat16>(stream, static_cast<const __nv_bfloat16*>(dy), z, mean, rstd, gamma,
+                                                        static_cast<__nv_bfloat16*>(dz), dgamma, dbeta, dzsum, rows, d, round_out, drop,
+                                                        gate, gate_scale);
   }
   set_error("add_ln_bwd: bad dtype %d", dt);
   return ST_ERR_INVALID;
@@ -508,7 +541,7 @@ int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst
 
 namespace {
 template <typename T>
-int colsum_add_t(cudaStream_t stream, const T* x, int64_t ld, int64_t rows, int cols, float* out) {
+int colsum_add_t(cudaStream_t stream, const T* x, int64_t ld, int64_t rows, int cols, float* out, const float* amax = nullptr) {
   if (rows == 0 || cols == 0) return ST_OK;
   // 4-element vector loads: a ragged width is fine as long as the (padded) row is long enough to read the last group
   ST_REQUIRE((ld & 3) == 0 && ld >= ((cols + 3) & ~3) && (sizeof(T) == 2 ? aligned8(x) : aligned16(x)),
@@ -518,7 +551,7 @@ int colsum_add_t(cudaStream_t stream, const T* x, int64_t ld, int64_t rows, int 
   const int64_t cap = (static_cast<int64_t>(num_sms()) * 8 + grid.x - 1) / grid.x;
   grid.y = static_cast<unsigned>(ychunks < cap ? ychunks : cap);
   ProfScope prof(stream, PROF_COLSUM, 1.0 * rows * cols * sizeof(T));
-  ST_CHECK_CUDA(launch_pdl(colsum_kernel<T>, grid, dim3(256), 0, stream, x, ld, rows, cols, out));
+  ST_CHECK_CUDA(launch_pdl(colsum_kernel<T>, grid, dim3(256), 0, stream, x, ld, rows, cols, out, amax));
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -574,14 +607,25 @@ int cast_t(cudaStream_t stream, const S* src, int64_t lds, D* dst, int64_t ldd, 
 int colsum_add(cudaStream_t stream, const float* x, int64_t ld, int64_t rows, int cols, float* out) {
   return colsum_add_t<float>(stream, x, ld, rows, cols, out);
 }
-int colsum_add_any(cudaStream_t stream, int dt, const void* x, int64_t ld, int64_t rows, int cols, float* out) {
+int colsum_add_any(cudaStream_t stream, int dt, const void* x, int64_t ld, int64_t rows, int cols, float* out, const float* amax) {
   switch (dt) {
-    case ST_DTYPE_F32: return colsum_add_t<float>(stream, static_cast<const float*>(x), ld, rows, cols, out);
-    case ST_DTYPE_F16: return colsum_add_t<__half>(stream, static_cast<const __half*>(x), ld, rows, cols, out);
-    case ST_DTYPE_BF16: return colsum_add_t<__nv_bfloat16>(stream, static_cast<const __nv_bfloat16*>(x), ld, rows, cols, out);
+    case ST_DTYPE_F32: return colsum_add_t<float>(stream, static_cast<const float*>(x), ld, rows, cols, out, amax);
+    case ST_DTYPE_F16: return colsum_add_t<__half>(stream, static_cast<const __half*>(x), ld, rows, cols, out, amax);
+    case ST_DTYPE_BF16: return colsum_add_t<__nv_bfloat16>(stream, static_cast<const __nv_bfloat16*>(x), ld, rows, cols, out, amax);
   }
   set_error("colsum: bad dtype %d", dt);
   return ST_ERR_INVALID;
+}
+
+// *out = max|x| over n fp32 values (n a multiple of 4, x 16-byte aligned); `out` is cleared first
+int amax_abs(cudaStream_t stream, const float* x, int64_t n, float* out) {
+  ST_REQUIRE((n & 3) == 0 && aligned16(x), "amax: n=%lld must be a multiple of 4 and x 16-byte aligned", (long long)n);
+  ST_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  if (n == 0) return ST_OK;
+  ProfScope prof(stream, PROF_ROUND, 4.0 * n);
+  ST_CHECK_CUDA(launch_pdl(amax_kernel, dim3(persistent_grid((n / 4 + 255) / 256, 8)), dim3(256), 0, stream, x, n / 4, out));
+  ST_CHECK_LAUNCH();
+  return ST_OK;
 }
 
 // dst = (dst type)(src * scale); one of the two types is fp32

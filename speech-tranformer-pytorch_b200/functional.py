@@ -18,11 +18,35 @@ from ._lib import StError, check
 __all__ = ["add_layer_norm", "multi_head_attention", "positionwise_ffn", "label_smoothing_ce", "soft_target_ce",
            "attention_core", "linear_tf32", "round_tf32", "is_tf32_clean", "mark_tf32_clean", "next_seed",
            "frontend", "linear", "embedding", "ctc_loss", "GradSink", "attach_grad_sink", "attach_tf32_twin",
-           "LengthMask", "cast", "ACT_DTYPES"]
+           "LengthMask", "cast", "ACT_DTYPES", "set_fp32_engine", "fp32_engine"]
 
 # activation element types and their ST_DTYPE_* codes (include/st_b200.h).  fp32 tensors take the fp32 / TF32 path; fp16 and
 # bf16 tensors take the 16-bit path (tcgen05 kind::f16 operands, fp32 accumulation and statistics; d_k must be 64).
 ACT_DTYPES = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+
+# How the composite operators (multi_head_attention, positionwise_ffn) compute on fp32 tensors:
+#   "fp16"  ST_DTYPE_F32_H16 — fp32 tensors at the operator boundary (inputs, outputs, every gradient), fp16 operands with
+#           fp32 accumulation inside; fp16 carries the same 11 significant bits as TF32, and the backward pass scales its
+#           16-bit tensors by a power of two derived on the device from max|grad_output| so they stay in fp16's range.
+#           Needs d_k = 64 for attention (other head sizes use "tf32").
+#   "tf32"  ST_DTYPE_F32 — TF32 operands everywhere (round 1's path).
+# Set with set_fp32_engine() or the environment variable ST_FP32_ENGINE before import.
+_FP32_ENGINES = ("fp16", "tf32")
+_fp32_engine = [os.environ.get("ST_FP32_ENGINE", "fp16")]
+if _fp32_engine[0] not in _FP32_ENGINES:
+    raise RuntimeError(f"ST_FP32_ENGINE must be one of {_FP32_ENGINES}, got {_fp32_engine[0]!r}")
+
+
+def set_fp32_engine(name: str) -> str:
+    """Choose how the composite operators compute on fp32 tensors ("fp16" or "tf32"); returns the previous setting."""
+    if name not in _FP32_ENGINES:
+        raise ValueError(f"fp32 engine must be one of {_FP32_ENGINES}, got {name!r}")
+    prev, _fp32_engine[0] = _fp32_engine[0], name
+    return prev
+
+
+def fp32_engine() -> str:
+    return _fp32_engine[0]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -170,6 +194,15 @@ def _twins_of(params, dtype=torch.float32):
             return None
         out.append(tw[0])
     return out
+
+
+def _composite_dtype(act_dtype, dk=None):
+    """(ST_DTYPE_* code, element type of the weight twins) a composite operator runs in for activations of `act_dtype`."""
+    if act_dtype != torch.float32:
+        return ACT_DTYPES[act_dtype], act_dtype
+    if _fp32_engine[0] == "fp16" and (dk is None or dk == 64):
+        return _lib.DTYPE_F32_H16, torch.float16
+    return _lib.DTYPE_F32, torch.float32
 
 
 def attach_grad_sink(param: torch.Tensor, view: torch.Tensor) -> GradSink:
@@ -443,7 +476,6 @@ class _MultiHeadAttention(torch.autograd.Function):
         kc = qc if same_qk else _contig(k)
         vc = kc if same_kv else _contig(v)
         lib = _lib_for(qc)
-        dt = ACT_DTYPES[qc.dtype]
         if qc.dim() != 3 or kc.dim() != 3 or vc.dim() != 3:
             raise RuntimeError("multi_head_attention: q, k, v must be (batch, length, d_model)")
         B, Lq, d = qc.shape
@@ -451,6 +483,7 @@ class _MultiHeadAttention(torch.autograd.Function):
         if vc.shape != kc.shape or kc.shape[0] != B or kc.shape[2] != d:
             raise RuntimeError(f"multi_head_attention: incompatible shapes q{tuple(qc.shape)} k{tuple(kc.shape)} v{tuple(vc.shape)}")
         dk = d // n_head
+        dt, twin_dtype = _composite_dtype(qc.dtype, dk)
         res = vc if residual == "v" else qc
         if res.shape != qc.shape:
             # the reference's `output + v` (Attention.py:94) fails the same way when len_q != len_k
@@ -465,7 +498,7 @@ class _MultiHeadAttention(torch.autograd.Function):
         saved = torch.empty(n_saved, device=qc.device, dtype=torch.float32)
         out = torch.empty(B, Lq, d, device=qc.device, dtype=qc.dtype)
         attn = torch.empty(B, n_head, Lq, Lk, device=qc.device, dtype=torch.float32) if need_attn else None
-        twins = _twins_of((wq, wk, wv, wo), qc.dtype) or [None] * 4
+        twins = _twins_of((wq, wk, wv, wo), twin_dtype) or [None] * 4
         a = _lib.MhaArgs(B=B, Lq=Lq, Lk=Lk, H=n_head, d_model=d, dk=dk, q_in=_p(qc), k_in=_p(kc), v_in=_p(vc),
                          residual=_p(res), wq=_p(params[0]), bq=_p(params[1]), wk=_p(params[2]), bk=_p(params[3]),
                          wv=_p(params[4]), bv=_p(params[5]), wo=_p(params[6]), bo=_p(params[7]), ln_g=_p(params[8]),
@@ -553,7 +586,7 @@ class _PositionwiseFFN(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, ln_g, ln_b, eps, dropout_p, seed, round_out):
         ctx.set_materialize_grads(False)   # the auxiliary outputs never carry a gradient: no zero tensors for them
         xc = _contig(_need_act(x, "inputs"))
-        dt = ACT_DTYPES[xc.dtype]
+        dt, twin_dtype = _composite_dtype(xc.dtype)
         x_clean = int(dt != _lib.DTYPE_F32 or is_tf32_clean(x))
         lib = _lib_for(xc)
         d = xc.shape[-1]
@@ -563,7 +596,7 @@ class _PositionwiseFFN(torch.autograd.Function):
         n_saved = lib.st_ffn_saved_floats_dt(dt, rows, d, d_ff, x_clean)
         saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
         out = torch.empty_like(xc)
-        twins = _twins_of((w1, w2), xc.dtype) or [None] * 2
+        twins = _twins_of((w1, w2), twin_dtype) or [None] * 2
         a = _lib.FfnArgs(rows=rows, d_model=d, d_ff=d_ff, x=_p(xc), w1=_p(params[0]), b1=_p(params[1]),
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=float(eps),
                          dropout_p=float(dropout_p), seed=int(seed), x_is_tf32=x_clean, round_out=int(round_out),
@@ -576,11 +609,11 @@ class _PositionwiseFFN(torch.autograd.Function):
         ctx.cfg = (rows, d, d_ff, float(eps), float(dropout_p), int(seed), x_clean, dt)
         if round_out and dt == _lib.DTYPE_F32:
             mark_tf32_clean(out)
-        off = lib.st_ffn_hidden_offset(rows, d, d_ff, x_clean)   # the hidden activation is the first saved tensor
+        off = lib.st_ffn_hidden_offset_dt(dt, rows, d, d_ff, x_clean)   # the hidden activation follows the optional input copy
         if dt == _lib.DTYPE_F32:
             hidden = saved[off:off + rows * d_ff].view(*xc.shape[:-1], d_ff)
         else:
-            hidden = saved.view(xc.dtype)[2 * off:2 * off + rows * d_ff].view(*xc.shape[:-1], d_ff)
+            hidden = saved.view(twin_dtype)[2 * off:2 * off + rows * d_ff].view(*xc.shape[:-1], d_ff)
         ctx.mark_non_differentiable(hidden)
         return out, hidden
 

@@ -224,6 +224,16 @@ class LibraryCollective:
             self.comm = C.c_void_p()
 
 
+def _twin_dtype_for(module: torch.nn.Module, compute_dtype):
+    """Element type of the parameter twins: the compute type, except that fp32 modules whose composite operators run the
+    fp16-operand engine (functional.set_fp32_engine; every attention head 64 wide) keep fp16 twins."""
+    from .functional import fp32_engine
+    if compute_dtype != torch.float32 or fp32_engine() != "fp16":
+        return compute_dtype
+    head_sizes = {m.d_k for m in module.modules() if hasattr(m, "d_k") and hasattr(m, "n_head")}
+    return torch.float16 if head_sizes <= {64} else torch.float32
+
+
 class DataParallelTrainer:
     """zero_grad -> (caller: forward + backward) -> allreduce -> clip + Adam, on flat buffers."""
 
@@ -239,7 +249,7 @@ class DataParallelTrainer:
         self.module = module
         self.compute_dtype = compute_dtype
         self.loss_scale = float(loss_scale) if loss_scale is not None else (16384.0 if compute_dtype == torch.float16 else 1.0)
-        self.fp = FlatParams(ordered_parameters(module), twin_dtype=compute_dtype)
+        self.fp = FlatParams(ordered_parameters(module), twin_dtype=_twin_dtype_for(module, compute_dtype))
         self.exp_avg = torch.zeros_like(self.fp.flat)
         self.exp_avg_sq = torch.zeros_like(self.fp.flat)
         self.norm_ws = torch.zeros(1, device=self.fp.flat.device, dtype=torch.float32)

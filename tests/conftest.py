@@ -18,3 +18,13 @@ def lib_path():
     """Path of the in-tree shared library, built on demand (nvcc cross-compiles without a GPU)."""
     import speech_tranformer_pytorch_b200 as stb
     return stb.build()
+
+
+@pytest.fixture(params=["fp16", "tf32"])
+def engine(request):
+    """Runs the test once per fp32 engine of the composite operators (functional.set_fp32_engine): "fp16" = fp32 boundary
+    tensors with fp16 operands inside (ST_DTYPE_F32_H16, the default), "tf32" = TF32 operands throughout (ST_DTYPE_F32)."""
+    from speech_tranformer_pytorch_b200 import functional as F
+    prev = F.set_fp32_engine(request.param)
+    yield request.param
+    F.set_fp32_engine(prev)

@@ -287,7 +287,7 @@ def test_mask_dtypes_and_views(stb):
 
 # ------------------------------------------------------------------------------------------------ modules vs golden
 @pytest.mark.parametrize("name", ["mha_self_padmask", "mha_self_causal", "mha_self_nomask_h4", "mha_cross_eqlen"])
-def test_mha_module_golden(stb, name):
+def test_mha_module_golden(stb, name, engine):
     g = golden(name)
     H = int(g["n_head"])
     d = g["q"].shape[-1]
@@ -310,7 +310,7 @@ def test_mha_module_golden(stb, name):
         assert err < TOL, (k, err)
 
 
-def test_ffn_module_golden(stb):
+def test_ffn_module_golden(stb, engine):
     g = golden("ffn")
     m = stb.PositionwiseFeedForward(64, 128).to(DEV).eval()
     m.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith("p.")})
@@ -348,7 +348,7 @@ class _EncoderLayer(torch.nn.Module):
         return self.pos_ffn(a), w
 
 
-def test_encoder_layer_golden(stb):
+def test_encoder_layer_golden(stb, engine):
     g = golden("encoder_layer")
     m = _EncoderLayer(stb, 64, 128, 2).to(DEV).eval()
     m.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith("p.")})
@@ -371,7 +371,7 @@ def test_encoder_layer_golden(stb):
 
 # ------------------------------------------------------------------------------------------------ modules vs oracle, larger
 @pytest.mark.parametrize("B,L,d,H,dff", [(2, 300, 512, 8, 2048), (3, 77, 64, 2, 128), (2, 150, 512, 4, 1024)])
-def test_encoder_layer_vs_oracle(stb, B, L, d, H, dff):
+def test_encoder_layer_vs_oracle(stb, B, L, d, H, dff, engine):
     gen = torch.Generator().manual_seed(L)
     m = _EncoderLayer(stb, d, dff, H).eval()
     with torch.no_grad():
@@ -404,7 +404,7 @@ def test_encoder_layer_vs_oracle(stb, B, L, d, H, dff):
     _grad_check(dict(m.named_parameters()), P)
 
 
-def test_cross_attention_residual_q(stb):
+def test_cross_attention_residual_q(stb, engine):
     """Lq != Lk: the reference's `+ v` cannot run; residual='q' is the documented switch."""
     B, Lq, Lk, d, H = 2, 50, 333, 512, 8
     gen = torch.Generator().manual_seed(11)

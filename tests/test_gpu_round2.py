@@ -34,7 +34,16 @@ def stb():
 def test_fused_clip_adam_matches_torch(stb, twin):
     """st_sumsq + st_adam_step over 5 steps == clip_grad_norm_(5.0) + torch.optim.Adam(betas=(0.9, 0.98), eps=1e-9) with the
     Noam rate (train.py:45-46, Optim.py:9-14,36-45), including the operand-precision twin the kernel emits."""
+    from speech_tranformer_pytorch_b200 import functional as sF
     from speech_tranformer_pytorch_b200 import parallel as spar
+    prev = sF.set_fp32_engine("tf32")       # float32 twins = TF32-rounded copies (the fp16 engine's twins are the float16 case)
+    try:
+        _fused_clip_adam_matches_torch(stb, spar, twin)
+    finally:
+        sF.set_fp32_engine(prev)
+
+
+def _fused_clip_adam_matches_torch(stb, spar, twin):
     torch.manual_seed(4)
     net = torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.Linear(64, 33)).to(DEV)
     ref = torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.Linear(64, 33)).to(DEV)
@@ -126,14 +135,25 @@ def test_install_runs_the_reference_layers_file_unchanged(stb):
 # ------------------------------------------------------------------------------------------------ whole model at 6+6 x 512
 CFG512 = dict(feature_dim=80, vocab_size=97, max_inputs_length=256, max_target_length=32, d_model=512, n_heads=8, d_k=64,
               d_v=64, d_inner_hid=2048, num_enc_layer=6, num_dec_layer=6, dropout=0.1, emb_scale=1, return_attns=False)
-TOL_MODEL = {"tf32": 3e-3, "fp16": 3e-3, "bf16": 3e-2}      # composition of 25 modules: 3x the module bound (test_gpu_model.py)
+TOL_MODEL = {"fp32": 3e-3, "tf32": 3e-3, "fp16": 3e-3, "bf16": 3e-2}      # composition of 25 modules: 3x the module bound (test_gpu_model.py)
 
 
-@pytest.mark.parametrize("dtype", ["tf32", "fp16", "bf16"])
+@pytest.mark.parametrize("dtype", ["fp32", "tf32", "fp16", "bf16"])
 def test_whole_model_headline_width(stb, dtype):
     """6+6 layers, d_model 512, 8 heads, d_ff 2048 (BASELINE.json configs[1] / [2]) on a ragged B=2, T=200 batch against the
-    float64 model port: logits, loss, and every parameter gradient (for the ReLU gate patterns the CUDA forward used)."""
+    float64 model port: logits, loss, and every parameter gradient (for the ReLU gate patterns the CUDA forward used).
+    "fp32" = fp32 model with the default fp16-operand engine inside the composite operators, "tf32" = fp32 model with TF32
+    operands throughout, "fp16" / "bf16" = 16-bit activations end to end."""
+    from speech_tranformer_pytorch_b200 import functional as sF
     from speech_tranformer_pytorch_b200 import model as smodel
+    prev = sF.set_fp32_engine("tf32" if dtype == "tf32" else "fp16")
+    try:
+        _whole_model_headline_width(stb, smodel, dtype)
+    finally:
+        sF.set_fp32_engine(prev)
+
+
+def _whole_model_headline_width(stb, smodel, dtype):
     V = CFG512["vocab_size"]
     P = model_port.init_params(CFG512, seed=11)
     gen = torch.Generator().manual_seed(12)
@@ -142,7 +162,7 @@ def test_whole_model_headline_width(stb, dtype):
             if v.dim() == 1:
                 v.copy_((1.0 if k.endswith("layernorm.weight") or k.endswith("3.weight") else 0.0) + 0.05 * torch.randn(v.shape, generator=gen))
     inputs, targets, in_len, tgt_len, truth = O.synthetic_batch(2, 200, 20, 80, V, seed=5, fixed_len=False)
-    net = smodel.Transformer(smodel.ModelConfig(CFG512, compute_dtype=dtype))
+    net = smodel.Transformer(smodel.ModelConfig(CFG512, compute_dtype="tf32" if dtype == "fp32" else dtype))
     missing = net.load_state_dict({k: v.detach() for k, v in P.items()}, strict=False)
     assert not missing.unexpected_keys and all(k.endswith(".pe") for k in missing.missing_keys)
     net = net.to(DEV).eval()
