@@ -42,9 +42,11 @@ def parse():
     ap.add_argument("--layers", type=int, default=6)
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--cpu-sample-batch", type=int, default=8, help="utterances per CPU-baseline step (BASELINE.md §5: B=8)")
-    ap.add_argument("--dtype", default=os.environ.get("ST_BENCH_DTYPE", "tf32"), choices=["tf32", "fp16", "bf16"],
-                    help="activation / tensor-core operand type: tf32 = fp32 storage (BASELINE.json configs[1]), "
-                         "fp16 / bf16 = 16-bit activations and operands, fp32 accumulate (configs[2])")
+    ap.add_argument("--dtype", default=os.environ.get("ST_BENCH_DTYPE", "fp32"), choices=["fp32", "tf32", "fp16", "bf16"],
+                    help="fp32 = fp32 model (BASELINE.json configs[1]): fp32 tensors at every module boundary, fp16 tensor-core "
+                         "operands inside MultiHeadAttention / PositionwiseFeedForward (functional.set_fp32_engine('fp16'), the "
+                         "library default); tf32 = the same fp32 model with TF32 operands throughout; fp16 / bf16 = 16-bit "
+                         "activations end to end, fp32 accumulate (configs[2])")
     ap.add_argument("--ragged", action="store_true", help="utterance lengths U[200, frames] padded to --frames (configs[2])")
     ap.add_argument("--no-variants", action="store_true",
                     help="skip the extra measurements of the default run: the same step with fp16 / bf16 operands, BASELINE.json "
@@ -160,7 +162,11 @@ def run_cpu(args, steps, warmup, batch):
             "ms_per_step": 1e3 * total / steps}
 
 
-DTYPE_DESC = {"tf32": "tf32 (fp32 storage, TF32 tensor-core operands, fp32 accumulate)",
+DTYPE_DESC = {"fp32": "f32 (fp32 parameters, activations and gradients at every module boundary; inside MultiHeadAttention / "
+                      "PositionwiseFeedForward the tensor-core operands are fp16 = TF32's 10-bit mantissa, fp32 accumulate / "
+                      "statistics, per-operator power-of-two gradient scale derived on the device; frontend, vocabulary "
+                      "projection: TF32 operands; loss, optimizer: fp32)",
+              "tf32": "tf32 (fp32 storage, TF32 tensor-core operands, fp32 accumulate)",
               "fp16": "fp16 (fp16 activations and tensor-core operands = TF32's 10-bit mantissa, fp32 accumulate / statistics / "
                       "parameters / optimizer, loss scale 2^14)",
               "bf16": "bf16 (bf16 activations and tensor-core operands, fp32 accumulate / statistics / parameters / optimizer)"}
@@ -170,7 +176,7 @@ def workload_config(args, n):
     which = "configs[2]" if (args.ragged or args.dtype == "bf16") else "configs[1]"
     lens = f"T in U[200,{args.frames}] padded to {args.frames}" if args.ragged else f"T={args.frames}"
     return {"workload": f"BASELINE.json {which}: {args.layers}+{args.layers}-layer enc/dec d_model=512 h=8 d_ff=2048, "
-                        f"{args.dtype} operands, synthetic 80-dim fbank B={args.batch}/GPU {lens} L<={args.targets} V=4337",
+                        f"{'fp32 tensors / fp16 operands in the fused layers' if args.dtype == 'fp32' else args.dtype + ' operands'}, synthetic 80-dim fbank B={args.batch}/GPU {lens} L<={args.targets} V=4337",
             "step": "fwd + label-smoothed CE + bwd + grad all-reduce + clip + Noam-Adam (train.py:37-46)",
             "dropout": args.dropout, "per_gpu_batch": args.batch, "global_batch": args.batch * n, "parallelism": f"dp{n}",
             "l2": "per-step working set (several GB of activations) >> 126 MB L2, no explicit flush needed"}
@@ -200,6 +206,7 @@ def measure_variant(stb, smodel, spar, sdata, dev, args, dtype, ragged, frames, 
     EncoderLayer forward + backward alone.  Used for the `variants` block of the default run's JSON line."""
     import torch
     V, d = 4337, 512
+    stb.functional.set_fp32_engine("tf32" if dtype == "tf32" else "fp16")     # main() restores its own setting afterwards
     cfg = smodel.headline_config(num_enc_layer=args.layers, num_dec_layer=args.layers, dropout=args.dropout, compute_dtype=dtype,
                                  max_inputs_length=max(2048, frames))
     act = smodel.COMPUTE_DTYPES[dtype]
@@ -350,6 +357,7 @@ def main_b200(args):
         dist.barrier()
     lib = stb._lib.load()
     stb._lib.check(lib.st_device_check(local))
+    stb.functional.set_fp32_engine("tf32" if args.dtype == "tf32" else "fp16")
 
     V, d = 4337, 512
     cfg = smodel.headline_config(num_enc_layer=args.layers, num_dec_layer=args.layers, dropout=args.dropout,
@@ -500,7 +508,7 @@ def main_b200(args):
         alg_bytes = None
         try:   # DRAM bytes per launch of the same kernels from the committed ncu launch list of one step (profiles/), averaged
                # over EVERY GEMM launch of the step, next to the algorithmic bytes (operands + output + aux operand, once each)
-            with open(os.path.join(ROOT, "profiles", f"r2_gemm_traffic_{'tf32' if args.dtype == 'tf32' else 'bf16'}.json")) as f:
+            with open(os.path.join(ROOT, "profiles", f"r2_gemm_traffic_{args.dtype if args.dtype in ('tf32', 'fp32') else 'bf16'}.json")) as f:
                 tj = json.load(f)
             traffic, traffic_note, alg_bytes = tj["dram_bytes_per_launch"], tj["source"], tj.get("algorithmic_bytes_per_launch")
         except Exception:
@@ -556,7 +564,8 @@ def main_b200(args):
                      "dtype": args.dtype,
                      "note": "one EncoderLayer (MHA + FFN, train mode, dropout 0.1) forward + backward, B x T x 512 resident in HBM; "
                              "FLOPs = 3 x (8Nd^2 + 4BhT^2dk + 4Nd*dff), no recompute counted, padded frames counted as the "
-                             "reference computes them; tf32 operands issue at half the bf16 / fp16 tensor-pipe rate"}
+                             "reference computes them; --dtype fp32: fp32 in / out, fp16 operands inside; tf32 operands issue at half the "
+                             "bf16 / fp16 tensor-pipe rate"}
         for q in lparams:
             q.grad = None
         trainer.zero_grad()
@@ -574,13 +583,15 @@ def main_b200(args):
         del resident
         torch.cuda.empty_cache()
         variants = []
-        for dt_, ragged_, frames_ in (("fp16", False, args.frames), ("bf16", False, args.frames), ("bf16", True, 2 * args.frames)):
+        for dt_, ragged_, frames_ in (("fp32", False, args.frames), ("tf32", False, args.frames), ("fp16", False, args.frames),
+                                      ("bf16", False, args.frames), ("bf16", True, 2 * args.frames)):
             if (dt_, ragged_, frames_) == (args.dtype, args.ragged, args.frames):
                 continue
             try:
                 variants.append(measure_variant(stb, smodel, spar, sdata, dev, args, dt_, ragged_, frames_))
             except Exception as e:
                 variants.append({"dtype": dt_, "ragged": ragged_, "frames": frames_, "error": repr(e)[:200]})
+        stb.functional.set_fp32_engine("tf32" if args.dtype == "tf32" else "fp16")
         eager = measure_eager_reference_on_gpu(dev, args)
 
     if rank == 0:

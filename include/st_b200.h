@@ -36,11 +36,12 @@ typedef struct CUstream_st* cudaStream_t;
 #define ST_DTYPE_F16 1
 #define ST_DTYPE_BF16 2
 /* Composite operators only (st_mha_*, st_ffn_*): fp32 activations at the boundary exactly as with ST_DTYPE_F32 — inputs,
- * outputs and their gradients are fp32 tensors, outputs rounded to a 10-bit mantissa when round_out is set — but every
- * INTERNAL tensor-core operand (the inputs' operand copies, Q/K/V, context, FFN hidden, all internal gradients, the weight
- * copies) is fp16, which carries the same 10-bit mantissa as TF32 at twice the MMA rate and half the bytes.  Internal
- * gradients are scaled by a power of two derived on the device from max|dout| of each backward call.  d_k must be 64;
- * the optional *_tf32 weight copies are then fp16.                                                                      */
+ * outputs and all gradients are fp32 tensors (inputs_tf32 / x_is_tf32 / round_out are ignored) — but every INTERNAL
+ * tensor-core operand (the inputs' operand copies, Q/K/V, context, FFN hidden, all internal gradients, the weight copies)
+ * is fp16, which carries the same 10-bit mantissa as TF32 at twice the MMA rate and half the bytes.  Internal gradients are
+ * scaled by a power of two derived on the device from max|dout| of each backward call, so gradients of any magnitude are
+ * safe; forward activations must lie in fp16's range.  d_k must be 64, the residual must alias q_in, k_in or v_in, and the
+ * optional *_tf32 weight copies are then fp16.  Sizes: st_*_saved_floats_dt / st_*_ws_floats_dt with this code.          */
 #define ST_DTYPE_F32_H16 3
 
 /* ---- library ------------------------------------------------------------------------------- */

@@ -481,8 +481,9 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
   if (mixed) eo.aux = (a.residual == a.q_in) ? p.xq_r : (a.residual == a.k_in ? p.xk_r : p.xv_r);   // the fp16 copy of the residual
   ST_TRY(gemm_any(s, dt, GEMM_NT, p.ctx, d, p.wo_r, d, p.z, d, 0, M, d, d, eo));
   // 6. LayerNorm (Attention.py:94)
+  // (mixed: the fp32 output is not rounded — its consumers convert it themselves, a TF32 rounding here would only be a second one)
   return add_ln_fwd_any(s, ST_DTYPE_F32, mixed ? ST_DTYPE_F32 : dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d,
-                        a.eps, a.round_out, DropoutCfg{});
+                        a.eps, mixed ? 0 : a.round_out, DropoutCfg{});
 }
 
 int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
@@ -691,7 +692,7 @@ int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
   ST_TRY(gemm_any(s, dt, GEMM_NT, p.h, f, p.w2_r, f, p.z, d, 0, M, d, f, e2));
   // out = dropout2(LN(z))                                                SubLayers.py:27
   return add_ln_fwd_any(s, ST_DTYPE_F32, mixed ? ST_DTYPE_F32 : dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d,
-                        a.eps, a.round_out, make_dropout(a.dropout_p, a.seed ^ kSeedMix2));
+                        a.eps, mixed ? 0 : a.round_out, make_dropout(a.dropout_p, a.seed ^ kSeedMix2));
 }
 
 int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {

@@ -8,10 +8,11 @@ from speech_tranformer_pytorch_b200 import data as sdata, model as smodel, paral
 ap = argparse.ArgumentParser()
 ap.add_argument("--layers", type=int, default=6); ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--frames", type=int, default=1000); ap.add_argument("--dropout", type=float, default=0.1)
-ap.add_argument("--dtype", default="tf32")
+ap.add_argument("--dtype", default="fp32", choices=["fp32", "tf32", "fp16", "bf16"])  # as bench.py --dtype
 a = ap.parse_args()
 dev = torch.device("cuda", 0); V = 4337
 torch.manual_seed(2018)
+stb.functional.set_fp32_engine("tf32" if a.dtype == "tf32" else "fp16")
 net = smodel.Transformer(smodel.headline_config(num_enc_layer=a.layers, num_dec_layer=a.layers, dropout=a.dropout, compute_dtype=a.dtype))
 smodel.init_parameters(net); net = net.to(dev).train()
 crit = stb.LabelSmoothingLoss(0.1, V, weight=torch.ones(V, device=dev), ignore_index=0).to(dev)

@@ -7,10 +7,11 @@ from speech_tranformer_pytorch_b200 import data as sdata, model as smodel, paral
 ap = argparse.ArgumentParser()
 ap.add_argument("--layers", type=int, default=6); ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--frames", type=int, default=1000); ap.add_argument("--dropout", type=float, default=0.1)
-ap.add_argument("--csv", default="gpurun_out/profile_step.csv"); ap.add_argument("--dtype", default="tf32")
+ap.add_argument("--csv", default="gpurun_out/profile_step.csv"); ap.add_argument("--dtype", default="fp32", choices=["fp32", "tf32", "fp16", "bf16"])  # as bench.py --dtype
 a = ap.parse_args()
 lib = stb._lib.load(); dev = torch.device("cuda", 0); V = 4337
 torch.manual_seed(2018)
+stb.functional.set_fp32_engine("tf32" if a.dtype == "tf32" else "fp16")
 net = smodel.Transformer(smodel.headline_config(num_enc_layer=a.layers, num_dec_layer=a.layers, dropout=a.dropout, compute_dtype=a.dtype))
 smodel.init_parameters(net); net = net.to(dev).train()
 crit = stb.LabelSmoothingLoss(0.1, V, weight=torch.ones(V, device=dev), ignore_index=0).to(dev)
@@ -51,6 +52,9 @@ for (cls, work, tag), (n, ms) in groups.items():
     if a.dtype == "tf32" or fl == 5 or (fl == 2 and mode == 0) or N >= 4336: s_out = 4
     else: s_out = 2
     if K <= 80 or (fl == 5 and N == 80): s_in, s_out = 4, 4          # the 80-wide front-end GEMMs stay TF32
+    if a.dtype == "fp32":                                            # fp32 model, fp16 operands inside the fused layers only
+        if max(M, N, K) >= 4336 and min(M, N, K) < 4336 and (N >= 4336 or K >= 4336 or fl == 5): s_in, s_out = 4, 4   # vocabulary projection: TF32
+        if fl == 2: s_out = 4                                        # residual-sum outputs (forward z, backward dx) are fp32
     aux = M * N * s_in if fl in (2, 4) else 0
     gb += n * ((M * K + N * K) * s_in + M * N * s_out + aux)
 print(f"GEMM class: algorithmic bytes per step {gb / 1e9:.3f} GB over {sum(n for (c, w, t), (n, ms) in groups.items() if names[c] == 'gemm_tf32')} launches")
