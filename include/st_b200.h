@@ -194,6 +194,12 @@ typedef struct {
                            dresidual in the backward); parameters and their gradients are always fp32 */
   const int64_t* k_len; /* see st_attn_args: key lengths (B,) or NULL */
   int causal;
+  /* ST_DTYPE_F32_H16 only — chaining operators without conversion passes.  When inputs_tf32 != 0 the caller supplies the
+   * fp16 copies of the inputs (the producer's out_h16, or st_cast): q_h16, plus k_h16 / v_h16 where k_in / v_in are other
+   * tensors; they must stay valid until the backward call, and `saved` does not hold copies of its own.  out_h16: NULL or
+   * (B*Lq, d) fp16, receives a copy of `out` for the next operator.                                                     */
+  const void* q_h16; const void* k_h16; const void* v_h16;
+  void* out_h16;
 } st_mha_args;
 int64_t st_mha_saved_floats(int B, int Lq, int Lk, int H, int d_model, int same_qkv, int same_kv, int inputs_tf32);
 int64_t st_mha_ws_floats(int B, int Lq, int Lk, int H, int d_model);
@@ -212,6 +218,11 @@ typedef struct {
   float* dln_g; float* dln_b;                 /* all parameter gradients are OVERWRITTEN */
   int grads_zeroed;     /* the parameter-gradient buffers already hold zeros (slices of a gradient buffer the caller cleared in
                            one pass, parallel.FlatParams.zero_grad): skip the per-tensor clears (~200 memsets per step) */
+  /* ST_DTYPE_F32_H16 only: dout_amax = NULL or a device scalar holding max|dout| (the dq_amax / dx_amax a later operator's
+   * backward produced for exactly this tensor) — saves the pass that measures it; dq_amax = NULL or a device scalar that
+   * receives max|dq_in|.                                                                                                */
+  const float* dout_amax;
+  float* dq_amax;
 } st_mha_bwd_args;
 int st_mha_bwd(const st_mha_bwd_args* a /* host */, cudaStream_t stream);
 
@@ -230,6 +241,8 @@ typedef struct {
   float* ws; int64_t ws_floats;
   const void* w1_tf32; const void* w2_tf32;   /* optional operand-precision weights (see st_mha_args); NULL = round internally */
   int dtype;            /* ST_DTYPE_*: element type of x, out (and dout, dx) */
+  const void* x_h16;    /* ST_DTYPE_F32_H16 with x_is_tf32 != 0: the caller's fp16 copy of x (see st_mha_args.q_h16) */
+  void* out_h16;        /* ST_DTYPE_F32_H16: NULL or (rows, d_model) fp16 copy of `out` for the next operator */
 } st_ffn_args;
 int64_t st_ffn_saved_floats(int64_t rows, int d_model, int d_ff, int x_is_tf32);
 int64_t st_ffn_ws_floats(int64_t rows, int d_model, int d_ff);
@@ -246,6 +259,8 @@ typedef struct {
   void* dx;
   float* dw1; float* db1; float* dw2; float* db2; float* dln_g; float* dln_b;   /* OVERWRITTEN */
   int grads_zeroed;     /* see st_mha_bwd_args */
+  const float* dout_amax;   /* see st_mha_bwd_args */
+  float* dx_amax;
 } st_ffn_bwd_args;
 int st_ffn_bwd(const st_ffn_bwd_args* a /* host */, cudaStream_t stream);
 

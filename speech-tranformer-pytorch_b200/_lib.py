@@ -51,7 +51,8 @@ class MhaArgs(C.Structure):
                 ("out", C.c_void_p), ("attn", C.c_void_p),
                 ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64),
                 ("wq_tf32", C.c_void_p), ("wk_tf32", C.c_void_p), ("wv_tf32", C.c_void_p), ("wo_tf32", C.c_void_p),
-                ("dtype", C.c_int), ("k_len", C.c_void_p), ("causal", C.c_int)]
+                ("dtype", C.c_int), ("k_len", C.c_void_p), ("causal", C.c_int),
+                ("q_h16", C.c_void_p), ("k_h16", C.c_void_p), ("v_h16", C.c_void_p), ("out_h16", C.c_void_p)]
 
 
 class MhaBwdArgs(C.Structure):
@@ -59,7 +60,8 @@ class MhaBwdArgs(C.Structure):
                 ("dq_in", C.c_void_p), ("dk_in", C.c_void_p), ("dv_in", C.c_void_p), ("dresidual", C.c_void_p),
                 ("dwq", C.c_void_p), ("dbq", C.c_void_p), ("dwk", C.c_void_p), ("dbk", C.c_void_p),
                 ("dwv", C.c_void_p), ("dbv", C.c_void_p), ("dwo", C.c_void_p), ("dbo", C.c_void_p),
-                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p), ("grads_zeroed", C.c_int)]
+                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p), ("grads_zeroed", C.c_int),
+                ("dout_amax", C.c_void_p), ("dq_amax", C.c_void_p)]
 
 
 class FfnArgs(C.Structure):
@@ -69,13 +71,15 @@ class FfnArgs(C.Structure):
                 ("eps", C.c_float), ("dropout_p", C.c_float), ("seed", u64),
                 ("x_is_tf32", C.c_int), ("round_out", C.c_int),
                 ("out", C.c_void_p), ("saved", C.c_void_p), ("saved_floats", i64), ("ws", C.c_void_p), ("ws_floats", i64),
-                ("w1_tf32", C.c_void_p), ("w2_tf32", C.c_void_p), ("dtype", C.c_int)]
+                ("w1_tf32", C.c_void_p), ("w2_tf32", C.c_void_p), ("dtype", C.c_int),
+                ("x_h16", C.c_void_p), ("out_h16", C.c_void_p)]
 
 
 class FfnBwdArgs(C.Structure):
     _fields_ = [("f", FfnArgs), ("dout", C.c_void_p), ("dx", C.c_void_p),
                 ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
-                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p), ("grads_zeroed", C.c_int)]
+                ("dln_g", C.c_void_p), ("dln_b", C.c_void_p), ("grads_zeroed", C.c_int),
+                ("dout_amax", C.c_void_p), ("dx_amax", C.c_void_p)]
 
 
 class FrontendArgs(C.Structure):

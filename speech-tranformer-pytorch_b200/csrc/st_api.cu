@@ -130,9 +130,11 @@ int64_t mha_saved_floats(int dt_, int B, int Lq, int Lk, int H, int d, bool same
   const int64_t M = static_cast<int64_t>(B) * Lq, Mk = static_cast<int64_t>(B) * Lk;
   const int dt = internal_dt(dt_);
   int64_t n = 0;
-  if (is_mixed(dt_)) {            // fp16 operand copies of the fp32 inputs
-    n += pad64a(dt, M * d);
-    if (!same_qkv) { n += pad64a(dt, Mk * d); if (!same_kv) n += pad64a(dt, Mk * d); }
+  if (is_mixed(dt_)) {            // fp16 operand copies of the fp32 inputs, unless the caller supplies them (q_h16 ...)
+    if (!inputs_tf32) {
+      n += pad64a(dt, M * d);
+      if (!same_qkv) { n += pad64a(dt, Mk * d); if (!same_kv) n += pad64a(dt, Mk * d); }
+    }
   } else if (dt == ST_DTYPE_F32 && !inputs_tf32) {
     n += pad64(M * d);
     if (!same_qkv) { n += pad64(Mk * d); if (!same_kv) n += pad64(Mk * d); }
@@ -154,7 +156,16 @@ int plan_mha(const st_mha_args& a, MhaPlan& p) {
   p.dt = internal_dt(a.dtype);
   const int d = a.d_model, dt = p.dt;
   Carver c(a.saved, a.saved_floats);
-  if (is_mixed(a.dtype)) {
+  if (is_mixed(a.dtype) && a.inputs_tf32) {      // the caller's fp16 copies
+    ST_REQUIRE(a.q_h16 != nullptr, "st_mha: inputs_tf32 with ST_DTYPE_F32_H16 needs q_h16");
+    p.xq_r = a.q_h16;
+    if (p.same_qkv) { p.xk_r = p.xv_r = p.xq_r; }
+    else {
+      p.xk_r = (a.k_in == a.q_in && a.Lq == a.Lk) ? a.q_h16 : a.k_h16;
+      p.xv_r = p.same_kv ? p.xk_r : ((a.v_in == a.q_in && a.Lq == a.Lk) ? a.q_h16 : a.v_h16);
+      ST_REQUIRE(p.xk_r && p.xv_r, "st_mha: inputs_tf32 with ST_DTYPE_F32_H16 needs k_h16 / v_h16 for inputs other than q_in");
+    }
+  } else if (is_mixed(a.dtype)) {
     p.xq_r = c.take_act(dt, p.M * d);
     if (p.same_qkv) { p.xk_r = p.xv_r = p.xq_r; }
     else {
@@ -437,7 +448,9 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
   }
   // 2. operand copies of the inputs: TF32 rounding (fp32 path), fp16 conversion (mixed: exact for TF32-representable
   //    inputs); 16-bit activations are GEMM operands as they are
-  if (mixed) {
+  if (mixed && a.inputs_tf32) {
+    // the caller's fp16 copies are the operands
+  } else if (mixed) {
     ST_TRY(cast_2d(s, a.q_in, ST_DTYPE_F32, d, const_cast<void*>(p.xq_r), dt, d, M, d));
     if (!p.same_qkv) {
       ST_TRY(cast_2d(s, a.k_in, ST_DTYPE_F32, d, const_cast<void*>(p.xk_r), dt, d, Mk, d));
@@ -483,7 +496,7 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
   // 6. LayerNorm (Attention.py:94)
   // (mixed: the fp32 output is not rounded — its consumers convert it themselves, a TF32 rounding here would only be a second one)
   return add_ln_fwd_any(s, ST_DTYPE_F32, mixed ? ST_DTYPE_F32 : dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d,
-                        a.eps, mixed ? 0 : a.round_out, DropoutCfg{});
+                        a.eps, mixed ? 0 : a.round_out, DropoutCfg{}, nullptr, 0, mixed ? a.out_h16 : nullptr);
 }
 
 int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
@@ -511,7 +524,8 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   }
   float* delta = w.take(static_cast<int64_t>(a.B) * a.H * a.Lq);
   // mixed mode: the gradient scale of this call, a power of two derived on the device from max|dout| (st_common.cuh)
-  float* amax = mixed ? w.take(64) : nullptr;
+  float* ws_amax = mixed ? w.take(64) : nullptr;
+  const float* amax = ws_amax;
   const bool fused_bias = dt == ST_DTYPE_F32 && attn_bwd_fuses_bias(a.dk);
 
   // LayerNorm backward; dbo = column sums of dz
@@ -519,9 +533,10 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   ST_CLEAR(b.dln_b, d);
   ST_CLEAR(b.dbo, d);
   if (mixed) {
-    ST_TRY(amax_abs(s, static_cast<const float*>(b.dout), p.M * d, amax));
+    if (b.dout_amax) amax = b.dout_amax;     // measured by the operator that produced dout
+    else ST_TRY(amax_abs(s, static_cast<const float*>(b.dout), p.M * d, ws_amax));
     ST_TRY(add_ln_bwd_mixed(s, static_cast<const float*>(b.dout), p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d,
-                            DropoutCfg{}, amax));
+                            DropoutCfg{}, amax, b.dq_amax));
   } else {
     ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d, 1, DropoutCfg{}));
   }
@@ -584,16 +599,17 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
              res_v = !res_q && !res_k && (a.residual == a.v_in);
   // mixed mode: the input gradients leave the operator as fp32 and shed the gradient scale in the epilogue
   const int out_lp = mixed ? 0 : 1;
-  auto with_res = [&](bool on) {
+  auto with_res = [&](bool on, float* amax_out = nullptr) {
     GemmEpilogue e;
     if (on) { e.aux = dz; e.ldaux = d; e.aux_mode = 1; }
     e.unscale_amax = amax;
+    e.amax_out = mixed ? amax_out : nullptr;
     return e;
   };
   if (p.same_qkv) {
-    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, out_lp, M, d, 3 * d, with_res(res_q)));
+    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, out_lp, M, d, 3 * d, with_res(res_q, b.dq_amax)));
   } else {
-    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, out_lp, M, d, d, with_res(res_q)));
+    ST_TRY(gemm_any(s, dt, GEMM_NN, dpq, p.ldpq, p.w_r, d, b.dq_in, d, out_lp, M, d, d, with_res(res_q, b.dq_amax)));
     if (p.same_kv) {
       ST_TRY(gemm_any(s, dt, GEMM_NN, dpk, p.ldpk, at(p.w_r, dt, dd), d, b.dk_in, d, out_lp, Mk, d, 2 * d, with_res(res_k || res_v)));
     } else {
@@ -615,7 +631,10 @@ int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
   const int dt = internal_dt(a.dtype);
   Carver c(a.saved, a.saved_floats);
   // NOTE: the hidden activation must stay the FIRST 16-bit / fp32 tensor after the optional input copy (st_ffn_hidden_offset)
-  if (is_mixed(a.dtype)) p.x_r = c.take_act(dt, a.rows * a.d_model);
+  if (is_mixed(a.dtype) && a.x_is_tf32) {
+    ST_REQUIRE(a.x_h16 != nullptr, "st_ffn: x_is_tf32 with ST_DTYPE_F32_H16 needs x_h16");
+    p.x_r = a.x_h16;
+  } else if (is_mixed(a.dtype)) p.x_r = c.take_act(dt, a.rows * a.d_model);
   else p.x_r = (dt != ST_DTYPE_F32 || a.x_is_tf32) ? a.x : c.take(a.rows * a.d_model);
   p.h = c.take_act(dt, a.rows * a.d_ff);
   p.z = c.take(a.rows * a.d_model);
@@ -632,7 +651,7 @@ int plan_ffn(const st_ffn_args& a, FfnPlan& p) {
 }
 constexpr uint64_t kSeedMix1 = 0x5DEECE66Dull, kSeedMix2 = 0xB5297A4D3F84D5B5ull;
 int64_t ffn_input_copy_floats(int dt_, int64_t rows, int d_model, int x_is_tf32) {
-  if (is_mixed(dt_)) return pad64a(ST_DTYPE_F16, rows * d_model);
+  if (is_mixed(dt_)) return x_is_tf32 ? 0 : pad64a(ST_DTYPE_F16, rows * d_model);   // x_is_tf32: the caller supplies x_h16
   return (dt_ != ST_DTYPE_F32 || x_is_tf32) ? 0 : pad64(rows * d_model);
 }
 int64_t ffn_saved_floats(int dt_, int64_t rows, int d_model, int d_ff, int x_is_tf32) {
@@ -676,7 +695,9 @@ int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
     ST_TRY(weight_copy(s, dt, a.w1, p.w1_r, f, d));
     ST_TRY(weight_copy(s, dt, a.w2, p.w2_r, d, f));
   }
-  if (mixed)
+  if (mixed && a.x_is_tf32) {
+    // the caller's fp16 copy is the operand
+  } else if (mixed)
     ST_TRY(cast_2d(s, a.x, ST_DTYPE_F32, d, const_cast<void*>(p.x_r), dt, d, M, d));
   else if (dt == ST_DTYPE_F32 && !a.x_is_tf32)
     ST_TRY(round_tf32_2d(s, static_cast<const float*>(a.x), d, const_cast<float*>(static_cast<const float*>(p.x_r)), d, M, d));
@@ -692,7 +713,8 @@ int st_ffn_fwd(const st_ffn_args* ap, cudaStream_t s) {
   ST_TRY(gemm_any(s, dt, GEMM_NT, p.h, f, p.w2_r, f, p.z, d, 0, M, d, f, e2));
   // out = dropout2(LN(z))                                                SubLayers.py:27
   return add_ln_fwd_any(s, ST_DTYPE_F32, mixed ? ST_DTYPE_F32 : dt, p.z, nullptr, a.ln_g, a.ln_b, a.out, nullptr, p.mean, p.rstd, M, d,
-                        a.eps, mixed ? 0 : a.round_out, make_dropout(a.dropout_p, a.seed ^ kSeedMix2));
+                        a.eps, mixed ? 0 : a.round_out, make_dropout(a.dropout_p, a.seed ^ kSeedMix2), nullptr, 0,
+                        mixed ? a.out_h16 : nullptr);
 }
 
 int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
@@ -709,15 +731,17 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   Carver w(a.ws, a.ws_floats);
   void* dz = w.take_act(dt, a.rows * d);
   void* dh = w.take_act(dt, a.rows * f);
-  float* amax = mixed ? w.take(64) : nullptr;     // gradient scale of this call (see st_mha_bwd)
+  float* ws_amax = mixed ? w.take(64) : nullptr;     // gradient scale of this call (see st_mha_bwd)
+  const float* amax = ws_amax;
   ST_CLEAR(b.dln_g, d);
   ST_CLEAR(b.dln_b, d);
   ST_CLEAR(b.db2, d);
   ST_CLEAR(b.db1, f);
   if (mixed) {
-    ST_TRY(amax_abs(s, static_cast<const float*>(b.dout), a.rows * d, amax));
+    if (b.dout_amax) amax = b.dout_amax;
+    else ST_TRY(amax_abs(s, static_cast<const float*>(b.dout), a.rows * d, ws_amax));
     ST_TRY(add_ln_bwd_mixed(s, static_cast<const float*>(b.dout), p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d,
-                            make_dropout(a.dropout_p, a.seed ^ kSeedMix2), amax));
+                            make_dropout(a.dropout_p, a.seed ^ kSeedMix2), amax, b.dx_amax));
   } else {
     ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.db2, M, d, 1,
                           make_dropout(a.dropout_p, a.seed ^ kSeedMix2)));
@@ -734,6 +758,7 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   GemmEpilogue ex;
   ex.aux = dz; ex.ldaux = d; ex.aux_mode = 1;
   ex.unscale_amax = amax;
+  ex.amax_out = mixed ? b.dx_amax : nullptr;
   return gemm_any(s, dt, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, mixed ? 0 : 1, M, d, f, ex);
 }
 

@@ -34,6 +34,9 @@ struct GemmEpilogue {
   // scale S derived from *unscale_amax; fp32 results that leave the operator (split-K weight gradients, the fp32 input
   // gradient of the AUX_ADD epilogue, the column sums) are multiplied by 1/S.  16-bit outputs stay scaled.
   const float* unscale_amax = nullptr;
+  // optional device scalar (16-bit operands, fp32 output, plain / residual-add epilogue): max|stored value| is accumulated
+  // here with atomicMax on the bit pattern (caller clears it) — the next backward operator's unscale_amax, measured for free
+  float* amax_out = nullptr;
 };
 
 // k_splits > 1 requires ep.atomic and a zero-initialised C.

@@ -160,6 +160,9 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
   constexpr bool OSC = Elem<T>::k16 && (ATOMIC || (sizeof(OutT) == 4 && (AUX == 1 || F == EPI_PLAIN)) || AUX == 2);
   const bool has_osc = OSC && ep.unscale_amax != nullptr;
   const float osc = has_osc ? 1.f / grad_scale_from_amax(__ldg(ep.unscale_amax)) : 1.f;
+  constexpr bool AMX = Elem<T>::k16 && !ATOMIC && sizeof(OutT) == 4 && (AUX == 1 || F == EPI_PLAIN);
+  const bool do_amx = AMX && ep.amax_out != nullptr;
+  float am = 0.f;
 #pragma unroll 1
   for (int c = half; c < n_chunks; c += EPI_WARPS / 4) {
     const int col = col0 + c * 32;
@@ -210,6 +213,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
           v[3] = aux4[i].w > 0.f ? v[3] * ep.aux_scale : 0.f;
         }
         if (OSC && AUX != 2 && has_osc) { v[0] *= osc; v[1] *= osc; v[2] *= osc; v[3] *= osc; }
+        if (AMX && do_amx) am = fmaxf(fmaxf(am, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
         cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
         if (ROUND) {
 #pragma unroll
@@ -234,6 +238,10 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, uint32_t stg_
     }
     __syncwarp();
   }
+  if (AMX && do_amx) {
+    am = warp_max(am);
+    if (lane == 0 && am > 0.f) atomicMax(reinterpret_cast<unsigned int*>(ep.amax_out), __float_as_uint(am));
+  }
 }
 
 // Any flag combination, any alignment (scalar loads / stores where needed).
@@ -247,6 +255,8 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
   const int lcol = (lane & 7) * 4;
   const int lrow = lane >> 3;
   const int row_base = m_blk * BM + quarter * 32;
+  const bool do_amx = Elem<T>::k16 && !c_lp && !ep.atomic && ep.amax_out != nullptr;
+  float am = 0.f;
 #pragma unroll 1
   for (int c = half; c < BN / 32; c += EPI_WARPS / 4) {
     const int col = n_blk * BN + c * 32 + lcol;
@@ -298,6 +308,7 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
         if (ep.aux_mode == 2) x = to_f32(ap[t]) > 0.f ? x * ep.aux_scale : 0.f;
         if (!Elem<T>::k16 && ep.round_tf32) x = tf32_rna(x);
         v[t] = x * osc;
+        if (do_amx) am = fmaxf(am, fabsf(v[t]));
       }
       if (c_lp) {
         T* cp = static_cast<T*>(p.C) + coff;
@@ -320,6 +331,10 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
       }
     }
     __syncwarp();
+  }
+  if (do_amx) {
+    am = warp_max(am);
+    if (lane == 0 && am > 0.f) atomicMax(reinterpret_cast<unsigned int*>(ep.amax_out), __float_as_uint(am));
   }
 }
 

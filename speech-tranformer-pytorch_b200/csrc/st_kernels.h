@@ -28,7 +28,7 @@ int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float
 // the same with 16-bit activations (ST_DTYPE_*): see st_ln.cu
 int add_ln_fwd_any(cudaStream_t stream, int in_dt, int out_dt, const void* a, const void* b, const float* gamma, const float* beta,
                    void* out, float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
-                   const DropoutCfg& drop, const float* post = nullptr, int64_t post_rows = 0);
+                   const DropoutCfg& drop, const float* post = nullptr, int64_t post_rows = 0, void* out_h16 = nullptr);
 int add_ln_bwd_any(cudaStream_t stream, int dt, const void* dy, const float* z, const float* mean, const float* rstd,
                    const float* gamma, void* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, int round_out,
                    const DropoutCfg& drop, const float* gate = nullptr, float gate_scale = 1.f);
@@ -38,7 +38,7 @@ int colsum_add_any(cudaStream_t stream, int dt, const void* x, int64_t ld, int64
 int amax_abs(cudaStream_t stream, const float* x, int64_t n, float* out);
 int add_ln_bwd_mixed(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                      void* dz16, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, const DropoutCfg& drop,
-                     const float* amax);
+                     const float* amax, float* clear_scalar = nullptr);
 int cast_2d(cudaStream_t stream, const void* src, int src_dt, int64_t lds, void* dst, int dst_dt, int64_t ldd, int64_t rows, int cols,
             float scale = 1.f);
 int round_tf32_2d(cudaStream_t stream, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols);

@@ -59,7 +59,7 @@ add_ln_fwd_kernel(const InT* __restrict__ a, const InT* __restrict__ b, const fl
                   const float* __restrict__ beta, OutT* __restrict__ out, float* __restrict__ z_out,
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int d, float eps,
                   int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
-                  const float* __restrict__ post, int64_t post_rows) {
+                  const float* __restrict__ post, int64_t post_rows, __half* __restrict__ out_h16) {
   pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
   pdl_trigger();
   const int lane = threadIdx.x & 31;
@@ -156,6 +156,8 @@ add_ln_fwd_kernel(const InT* __restrict__ a, const InT* __restrict__ b, const fl
           if (i & 1) st_pair<WIDE>(out + row * d, c - 4, x[i - 1], x[i]);
         } else {
           st4(out + row * d + c, make_float4(o[0], o[1], o[2], o[3]));
+          if (sizeof(OutT) == 4 && out_h16)     // the fp16 copy the next operator consumes (ST_DTYPE_F32_H16)
+            *reinterpret_cast<uint2*>(out_h16 + row * d + c) = make_uint2(pack2<__half>(o[0], o[1]), pack2<__half>(o[2], o[3]));
         }
       }
     }
@@ -174,9 +176,12 @@ add_ln_bwd_kernel(const DyT* __restrict__ dy, const float* __restrict__ z, const
                   const float* __restrict__ rstd_in, const float* __restrict__ gamma, DzT* __restrict__ dz,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dzsum, int64_t rows,
                   int d, int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
-                  const float* __restrict__ gate, float gate_scale, const float* __restrict__ amax) {
+                  const float* __restrict__ gate, float gate_scale, const float* __restrict__ amax, float* __restrict__ clear_scalar) {
   pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
   pdl_trigger();
+  // a scalar a LATER kernel of the same operator accumulates into with atomicMax (st_*_bwd_args.dq_amax / dx_amax): cleared
+  // here, in stream order before that kernel's first global access, instead of by a memset node between the launches
+  if (clear_scalar && blockIdx.x == 0 && threadIdx.x == 0) *clear_scalar = 0.f;
   __shared__ float red[LN_WARPS][32 * 4 + 4];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -393,19 +398,22 @@ namespace {
 template <typename InT, typename OutT>
 int add_ln_fwd_t(cudaStream_t stream, const InT* a, const InT* b, const float* gamma, const float* beta, OutT* out,
                  float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
-                 const DropoutCfg& drop, const float* post, int64_t post_rows) {
+                 const DropoutCfg& drop, const float* post, int64_t post_rows, void* out_h16 = nullptr) {
   if (rows == 0) return ST_OK;
   ST_REQUIRE(!post || (post_rows > 0 && aligned16(post)), "add_ln_fwd: post operand needs post_rows > 0 and 16-byte alignment");
+  ST_REQUIRE(!out_h16 || (sizeof(OutT) == 4 && sizeof(InT) == 4 && aligned8(out_h16)), "add_ln_fwd: the fp16 copy needs fp32 in / out");
   ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_fwd: d=%d must be a multiple of 4 and <= 1024", d);
   ST_REQUIRE(aligned8(a) && (!b || aligned8(b)) && aligned16(gamma) && aligned16(beta) && aligned8(out) &&
                  (!z_out || aligned16(z_out)) && (sizeof(InT) == 2 || (aligned16(a) && (!b || aligned16(b)))) &&
                  (sizeof(OutT) == 2 || aligned16(out)),
              "add_ln_fwd: pointers must be 16-byte aligned");
   const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 8);
-  ProfScope prof(stream, PROF_LN_FWD, (b ? 2.0 : 1.0) * rows * d * sizeof(InT) + 1.0 * rows * d * sizeof(OutT) + (z_out ? 1.0 * rows * d * 4 : 0.0));
+  ProfScope prof(stream, PROF_LN_FWD, (b ? 2.0 : 1.0) * rows * d * sizeof(InT) + 1.0 * rows * d * sizeof(OutT) + (z_out ? 1.0 * rows * d * 4 : 0.0) +
+                                          (out_h16 ? 2.0 * rows * d : 0.0));
 #define ST_LAUNCH(VPL, W)                                                                                         \
   ST_CHECK_CUDA(launch_pdl(add_ln_fwd_kernel<VPL, InT, OutT, W>, dim3(grid), dim3(LN_THREADS), 0, stream, a, b, gamma, beta, out, z_out, \
-                           mean_out, rstd_out, rows, d, eps, round_out, drop.thresh, drop.scale, drop.seed, post, post_rows))
+                           mean_out, rstd_out, rows, d, eps, round_out, drop.thresh, drop.scale, drop.seed, post, post_rows,         \
+                           static_cast<__half*>(out_h16)))
   constexpr bool kAny16 = sizeof(InT) == 2 || sizeof(OutT) == 2;
   const bool wide = kAny16 && (d % 256) == 0 && aligned16(a) && (!b || aligned16(b)) && aligned16(out);
   if (wide) {
@@ -435,10 +443,10 @@ int add_ln_fwd(cudaStream_t stream, const float* a, const float* b, const float*
 // in_dt: element type of a / b (ST_DTYPE_F32 or out_dt); out_dt: element type of out
 int add_ln_fwd_any(cudaStream_t stream, int in_dt, int out_dt, const void* a, const void* b, const float* gamma, const float* beta,
                    void* out, float* z_out, float* mean_out, float* rstd_out, int64_t rows, int d, float eps, int round_out,
-                   const DropoutCfg& drop, const float* post, int64_t post_rows) {
+                   const DropoutCfg& drop, const float* post, int64_t post_rows, void* out_h16) {
 #define ST_CALL(InT, OutT)                                                                                                   \
   return add_ln_fwd_t<InT, OutT>(stream, static_cast<const InT*>(a), static_cast<const InT*>(b), gamma, beta, static_cast<OutT*>(out), \
-                                 z_out, mean_out, rstd_out, rows, d, eps, round_out, drop, post, post_rows)
+                                 z_out, mean_out, rstd_out, rows, d, eps, round_out, drop, post, post_rows, out_h16)
   if (in_dt == ST_DTYPE_F32 && out_dt == ST_DTYPE_F32) ST_CALL(float, float);
   if (in_dt == ST_DTYPE_F32 && out_dt == ST_DTYPE_F16) ST_CALL(float, __half);
   if (in_dt == ST_DTYPE_F32 && out_dt == ST_DTYPE_BF16) ST_CALL(float, __nv_bfloat16);
@@ -454,7 +462,8 @@ namespace {
 template <typename DyT, typename DzT>
 int add_ln_bwd_t(cudaStream_t stream, const DyT* dy, const float* z, const float* mean, const float* rstd,
                  const float* gamma, DzT* dz, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d,
-                 int round_out, const DropoutCfg& drop, const float* gate, float gate_scale, const float* amax = nullptr) {
+                 int round_out, const DropoutCfg& drop, const float* gate, float gate_scale, const float* amax = nullptr,
+                 float* clear_scalar = nullptr) {
   if (rows == 0) return ST_OK;
   ST_REQUIRE(!gate || aligned16(gate), "add_ln_bwd: gate must be 16-byte aligned");
   ST_REQUIRE(d > 0 && (d & 3) == 0 && d <= 1024, "add_ln_bwd: d=%d must be a multiple of 4 and <= 1024", d);
@@ -465,7 +474,7 @@ int add_ln_bwd_t(cudaStream_t stream, const DyT* dy, const float* z, const float
   ProfScope prof(stream, PROF_LN_BWD, 1.0 * rows * d * 4 + 1.0 * rows * d * (sizeof(DyT) + sizeof(DzT)));
 #define ST_LAUNCH(VPL, W)                                                                                      \
   ST_CHECK_CUDA(launch_pdl(add_ln_bwd_kernel<VPL, DyT, DzT, W>, dim3(grid), dim3(LN_THREADS), 0, stream, dy, z, mean, rstd, gamma, dz, \
-                           dgamma, dbeta, dzsum, rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, gate_scale, amax))
+                           dgamma, dbeta, dzsum, rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, gate_scale, amax, clear_scalar))
   constexpr bool k16 = sizeof(DyT) == 2 || sizeof(DzT) == 2;
   const bool wide = k16 && (d % 256) == 0 && aligned16(dy) && aligned16(dz) && !gate;
   if (wide) {
@@ -494,9 +503,9 @@ int add_ln_bwd(cudaStream_t stream, const float* dy, const float* z, const float
 // mixed mode: fp32 dy -> fp16 dz scaled by grad_scale_from_amax(*amax)
 int add_ln_bwd_mixed(cudaStream_t stream, const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                      void* dz16, float* dgamma, float* dbeta, float* dzsum, int64_t rows, int d, const DropoutCfg& drop,
-                     const float* amax) {
+                     const float* amax, float* clear_scalar) {
   return add_ln_bwd_t<float, __half>(stream, dy, z, mean, rstd, gamma, static_cast<__half*>(dz16), dgamma, dbeta, dzsum, rows, d, 0, drop,
-                                     nullptr, 1.f, amax);
+                                     nullptr, 1.f, amax, clear_scalar);
 }
 
 // dt: element type of dy and dz

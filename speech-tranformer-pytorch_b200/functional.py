@@ -205,6 +205,37 @@ def _composite_dtype(act_dtype, dk=None):
     return _lib.DTYPE_F32, torch.float32
 
 
+# Chaining of the fp16-operand engine (ST_DTYPE_F32_H16).  An fp32 activation produced by one composite operator carries the
+# fp16 copy its LayerNorm kernel wrote next to it, and an fp32 gradient produced by one backward operator carries the device
+# scalar max|gradient| its last GEMM epilogue measured; the next operator finds them here and skips its conversion pass /
+# its amax pass.  A tag is honoured only for the very tensor object it was attached to and only while that tensor's version
+# counter is unchanged (an in-place edit, or autograd accumulating another gradient into it, invalidates it).
+_H16_ATTR = "_st_h16"
+_AMAX_ATTR = "_st_amax"
+_CHAIN = os.environ.get("ST_CHAIN", "1") != "0"      # ST_CHAIN=0: attach no tags (A/B measurements)
+
+
+def _tag(t: torch.Tensor, attr: str, value: torch.Tensor) -> None:
+    if _CHAIN:
+        setattr(t, attr, (value, t._version))
+
+
+def _tagged(t: torch.Tensor, attr: str) -> Optional[torch.Tensor]:
+    tag = getattr(t, attr, None)
+    if tag is None or tag[1] != t._version:
+        return None
+    return tag[0]
+
+
+def _h16_of(t: torch.Tensor) -> torch.Tensor:
+    """The fp16 copy of the contiguous fp32 activation `t`: the one its producer left, else made (and remembered) here."""
+    tw = _tagged(t, _H16_ATTR)
+    if tw is None or tw.shape != t.shape:
+        tw = cast(t, torch.float16)
+        _tag(t, _H16_ATTR, tw)
+    return tw
+
+
 def attach_grad_sink(param: torch.Tensor, view: torch.Tensor) -> GradSink:
     sink = GradSink(view)
     setattr(param, _SINK_ATTR, sink)
@@ -493,6 +524,12 @@ class _MultiHeadAttention(torch.autograd.Function):
         mask_t, sb, sq, sk = _mask_args(mask, B, Lq, Lk, qc.device)
         params = [_contig(_need(t, "parameter")) for t in (wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b)]
         inputs_tf32 = int(dt != _lib.DTYPE_F32 or (is_tf32_clean(q) and is_tf32_clean(k) and is_tf32_clean(v)))
+        q16 = k16 = v16 = out16 = None
+        if dt == _lib.DTYPE_F32_H16:      # fp16 operand copies: the producers' (or made once per tensor), see _h16_of
+            q16 = _h16_of(qc)
+            k16 = q16 if same_qk else _h16_of(kc)
+            v16 = k16 if same_kv else _h16_of(vc)
+            out16 = torch.empty(B, Lq, d, device=qc.device, dtype=torch.float16)
         same_qkv = int(same_qk and same_kv and Lq == Lk)
         n_saved = lib.st_mha_saved_floats_dt(dt, B, Lq, Lk, n_head, d, same_qkv, int(same_kv), inputs_tf32)
         saved = torch.empty(n_saved, device=qc.device, dtype=torch.float32)
@@ -506,9 +543,13 @@ class _MultiHeadAttention(torch.autograd.Function):
                          dropout_p=float(dropout_p), seed=int(seed), inputs_tf32=inputs_tf32, round_out=int(round_out),
                          out=_p(out), attn=_p(attn), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0,
                          wq_tf32=_p(twins[0]), wk_tf32=_p(twins[1]), wv_tf32=_p(twins[2]), wo_tf32=_p(twins[3]),
-                         dtype=dt, k_len=_p(k_len), causal=causal)
+                         dtype=dt, k_len=_p(k_len), causal=causal, q_h16=_p(q16), k_h16=_p(k16), v_h16=_p(v16),
+                         out_h16=_p(out16))
         check(lib.st_mha_fwd(C.byref(a), _stream()))
         ctx.twins = twins          # backward must present the same weight copies the forward used
+        ctx.h16 = (q16, k16, v16)  # ... and the same operand copies of the inputs
+        if out16 is not None:
+            _tag(out, _H16_ATTR, out16)
         ctx.save_for_backward(qc, kc, vc, mask_t, k_len, saved, *params)
         ctx.sinks = _sinks_of((wq, bq, wk, bk, wv, bv, wo, bo, ln_g, ln_b), ctx)
         ctx.cfg = (B, Lq, Lk, n_head, d, dk, residual, float(eps), float(dropout_p), int(seed), inputs_tf32,
@@ -552,12 +593,18 @@ class _MultiHeadAttention(torch.autograd.Function):
                          seed=seed, inputs_tf32=inputs_tf32, round_out=0, out=None, attn=None, saved=_p(saved),
                          saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws, wq_tf32=_p(ctx.twins[0]),
                          wk_tf32=_p(ctx.twins[1]), wv_tf32=_p(ctx.twins[2]), wo_tf32=_p(ctx.twins[3]),
-                         dtype=dt, k_len=_p(k_len), causal=causal)
+                         dtype=dt, k_len=_p(k_len), causal=causal, q_h16=_p(ctx.h16[0]), k_h16=_p(ctx.h16[1]),
+                         v_h16=_p(ctx.h16[2]), out_h16=None)
+        mixed = dt == _lib.DTYPE_F32_H16
+        dq_amax = torch.empty(1, device=dev, dtype=torch.float32) if mixed else None    # cleared by the operator
         a = _lib.MhaBwdArgs(f=f, dout=_p(dout), dq_in=_p(dq_in), dk_in=_p(dk_in), dv_in=_p(dv_in), dresidual=None,
                             dwq=_p(grads[0]), dbq=_p(grads[1]), dwk=_p(grads[2]), dbk=_p(grads[3]), dwv=_p(grads[4]),
                             dbv=_p(grads[5]), dwo=_p(grads[6]), dbo=_p(grads[7]), dln_g=_p(grads[8]),
-                            dln_b=_p(grads[9]), grads_zeroed=zeroed)
+                            dln_b=_p(grads[9]), grads_zeroed=zeroed,
+                            dout_amax=_p(_tagged(dout, _AMAX_ATTR)) if mixed else None, dq_amax=_p(dq_amax))
         check(lib.st_mha_bwd(C.byref(a), _stream()))
+        if mixed:
+            _tag(dq_in, _AMAX_ATTR, dq_amax)
         _notify(ctx.sinks, direct)
         # aliased inputs received ONE combined gradient; hand it to the first alias only
         gq, gk, gv = dq_in, (None if same_qkv else dk_in), (None if same_kv else dv_in)
@@ -593,6 +640,10 @@ class _PositionwiseFFN(torch.autograd.Function):
         rows = xc.numel() // d
         params = [_contig(_need(t, "parameter")) for t in (w1, b1, w2, b2, ln_g, ln_b)]
         d_ff = params[0].shape[0]
+        x16 = out16 = None
+        if dt == _lib.DTYPE_F32_H16:
+            x16 = _h16_of(xc)
+            out16 = torch.empty_like(xc, dtype=torch.float16)
         n_saved = lib.st_ffn_saved_floats_dt(dt, rows, d, d_ff, x_clean)
         saved = torch.empty(n_saved, device=xc.device, dtype=torch.float32)
         out = torch.empty_like(xc)
@@ -601,9 +652,12 @@ class _PositionwiseFFN(torch.autograd.Function):
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=float(eps),
                          dropout_p=float(dropout_p), seed=int(seed), x_is_tf32=x_clean, round_out=int(round_out),
                          out=_p(out), saved=_p(saved), saved_floats=n_saved, ws=None, ws_floats=0,
-                         w1_tf32=_p(twins[0]), w2_tf32=_p(twins[1]), dtype=dt)
+                         w1_tf32=_p(twins[0]), w2_tf32=_p(twins[1]), dtype=dt, x_h16=_p(x16), out_h16=_p(out16))
         check(lib.st_ffn_fwd(C.byref(a), _stream()))
         ctx.twins = twins
+        ctx.x16 = x16
+        if out16 is not None:
+            _tag(out, _H16_ATTR, out16)
         ctx.save_for_backward(xc, saved, *params)
         ctx.sinks = _sinks_of((w1, b1, w2, b2, ln_g, ln_b), ctx)
         ctx.cfg = (rows, d, d_ff, float(eps), float(dropout_p), int(seed), x_clean, dt)
@@ -634,10 +688,15 @@ class _PositionwiseFFN(torch.autograd.Function):
                          w2=_p(params[2]), b2=_p(params[3]), ln_g=_p(params[4]), ln_b=_p(params[5]), eps=eps,
                          dropout_p=p, seed=seed, x_is_tf32=x_clean, round_out=0, out=None, saved=_p(saved),
                          saved_floats=saved.numel(), ws=_p(ws), ws_floats=n_ws, w1_tf32=_p(ctx.twins[0]),
-                         w2_tf32=_p(ctx.twins[1]), dtype=dt)
+                         w2_tf32=_p(ctx.twins[1]), dtype=dt, x_h16=_p(ctx.x16), out_h16=None)
+        mixed = dt == _lib.DTYPE_F32_H16
+        dx_amax = torch.empty(1, device=xc.device, dtype=torch.float32) if mixed else None    # cleared by the operator
         a = _lib.FfnBwdArgs(f=f, dout=_p(dout), dx=_p(dx), dw1=_p(grads[0]), db1=_p(grads[1]), dw2=_p(grads[2]),
-                            db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]), grads_zeroed=zeroed)
+                            db2=_p(grads[3]), dln_g=_p(grads[4]), dln_b=_p(grads[5]), grads_zeroed=zeroed,
+                            dout_amax=_p(_tagged(dout, _AMAX_ATTR)) if mixed else None, dx_amax=_p(dx_amax))
         check(lib.st_ffn_bwd(C.byref(a), _stream()))
+        if mixed:
+            _tag(dx, _AMAX_ATTR, dx_amax)
         _notify(ctx.sinks, direct)
         if direct is not None:
             grads = [None] * len(params)

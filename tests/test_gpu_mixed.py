@@ -174,3 +174,59 @@ def test_c_abi_rejects_the_mixed_code_where_it_has_no_meaning(stb):
     assert rc != 0
     rc = lib.st_gemm_dt(stb._lib.DTYPE_F32_H16, 0, a.data_ptr(), 64, a.data_ptr(), 64, a.data_ptr(), 64, 0, 64, 64, 64, None, None)
     assert rc != 0
+
+
+def test_chained_operators_skip_conversion_and_amax_passes(stb):
+    """An operator's fp32 output carries the fp16 copy its LayerNorm kernel wrote and its fp32 input gradient carries the
+    max|.| its last GEMM epilogue measured (functional._H16_ATTR / _AMAX_ATTR): the next operator skips its conversion /
+    amax pass.  Same bits as the unchained sequence (a `* 1.0` between the operators drops both tags), fewer launches."""
+    att, ffn = _layer(stb, seed=21)
+    att2, _ = _layer(stb, seed=22)
+    lib = stb._lib.load()
+    gen = torch.Generator().manual_seed(23)
+    x = torch.randn(2, 130, 512, generator=gen).to(DEV)
+    g = torch.randn(2, 130, 512, generator=gen).to(DEV)
+    params = list(att.parameters()) + list(ffn.parameters()) + list(att2.parameters())
+
+    def run(chained):
+        for p in params:
+            p.grad = None
+        cx = x.clone().requires_grad_()
+        n0 = lib.st_launch_count()
+        a = att(cx, cx, cx)[0]
+        f = ffn(a if chained else a * 1.0)
+        f = f if chained else f * 1.0
+        y = att2(f, f, f)[0]
+        y.backward(g)
+        return y.detach(), cx.grad, [p.grad.clone() for p in params], lib.st_launch_count() - n0
+
+    y1, dx1, gr1, n1 = run(True)
+    y0, dx0, gr0, n0 = run(False)
+    assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    for a, b in zip(gr1, gr0):
+        assert relerr(a, b) < 2e-4          # split-K / column-sum atomics: fp32 summation order
+    # per hand-over: one conversion launch forward, one amax launch backward (two hand-overs here)
+    assert n0 - n1 == 4, (n0, n1)
+
+
+def test_stale_tags_are_not_used(stb):
+    """A tag is tied to the tensor's version counter: after an in-place edit of an operator's output the next operator
+    converts the edited values itself."""
+    from speech_tranformer_pytorch_b200 import functional as F
+    att, ffn = _layer(stb, seed=31)
+    x = torch.randn(1, 64, 512, generator=torch.Generator().manual_seed(32)).to(DEV)
+    with torch.no_grad():
+        a = att(x, x, x)[0]
+        assert F._tagged(a, F._H16_ATTR) is not None
+        want = ffn(a.clone() * 3.0)
+        a.mul_(3.0)
+        assert F._tagged(a, F._H16_ATTR) is None
+        assert torch.equal(ffn(a), want)
+        # an input tensor is converted once and the copy reused while it is unchanged
+        assert F._tagged(x, F._H16_ATTR) is not None
+        n0 = stb._lib.load().st_launch_count()
+        att(x, x, x)
+        n1 = stb._lib.load().st_launch_count()
+        x.add_(1.0)
+        att(x, x, x)
+        assert stb._lib.load().st_launch_count() - n1 == (n1 - n0) + 1
