@@ -471,17 +471,20 @@ int st_mha_fwd(const st_mha_args* ap, cudaStream_t s) {
     ep.bias = p.b_pack;
     ST_TRY(gemm_any(s, dt, GEMM_NT, p.xq_r, d, p.w_r, d, p.projq, p.ldpq, 1, M, 3 * d, d, ep));
   } else {
+    Fork fk(s);                           // the query projection and the key / value projections read different inputs
+    cudaStream_t skv = fk.branch(0);
     ep.bias = p.b_pack;
     ST_TRY(gemm_any(s, dt, GEMM_NT, p.xq_r, d, p.w_r, d, p.projq, p.ldpq, 1, M, d, d, ep));
     if (p.same_kv) {
       ep.bias = p.b_pack + d;
-      ST_TRY(gemm_any(s, dt, GEMM_NT, p.xk_r, d, at(p.w_r, dt, dd), d, p.projk, p.ldpk, 1, Mk, 2 * d, d, ep));
+      ST_TRY(gemm_any(skv, dt, GEMM_NT, p.xk_r, d, at(p.w_r, dt, dd), d, p.projk, p.ldpk, 1, Mk, 2 * d, d, ep));
     } else {
       ep.bias = p.b_pack + d;
-      ST_TRY(gemm_any(s, dt, GEMM_NT, p.xk_r, d, at(p.w_r, dt, dd), d, p.projk, p.ldpk, 1, Mk, d, d, ep));
+      ST_TRY(gemm_any(skv, dt, GEMM_NT, p.xk_r, d, at(p.w_r, dt, dd), d, p.projk, p.ldpk, 1, Mk, d, d, ep));
       ep.bias = p.b_pack + 2 * d;
-      ST_TRY(gemm_any(s, dt, GEMM_NT, p.xv_r, d, at(p.w_r, dt, 2 * dd), d, p.projv, p.ldpv, 1, Mk, d, d, ep));
+      ST_TRY(gemm_any(skv, dt, GEMM_NT, p.xv_r, d, at(p.w_r, dt, 2 * dd), d, p.projv, p.ldpv, 1, Mk, d, d, ep));
     }
+    ST_TRY(fk.join());
   }
   // 4. attention core (Attention.py:78-90)
   AttnArgs at_{};
@@ -540,11 +543,14 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   } else {
     ST_TRY(add_ln_bwd_any(s, dt, b.dout, p.z, p.mean, p.rstd, a.ln_g, dz, b.dln_g, b.dln_b, b.dbo, M, d, 1, DropoutCfg{}));
   }
-  // output projection backward
+  // output projection backward.  Weight gradients and bias column sums never feed another kernel of this call: they run on
+  // a side stream (st_host.h Fork) next to the chain dz -> dctx -> attention backward -> input gradients.
+  Fork fk(s);
   {
+    cudaStream_t sw = fk.branch(0);
     GemmEpilogue e; e.round_tf32 = 1;
     ST_TRY(gemm_any(s, dt, GEMM_NN, dz, d, p.wo_r, d, dctx, d, 1, M, d, d, e));
-    ST_TRY(wgrad(s, dt, dz, d, p.ctx, d, b.dwo, M, d, d, zeroed, amax));
+    ST_TRY(wgrad(sw, dt, dz, d, p.ctx, d, b.dwo, M, d, d, zeroed, amax));
   }
   // attention core backward
   {
@@ -564,33 +570,38 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
   // buffer (functional.py does) and the projections share their input, one GEMM / column sum covers all of them.
   const bool pack_kv = p.same_kv && b.dwv == b.dwk + dd && b.dbv == b.dbk + d;
   const bool pack_qkv = p.same_qkv && pack_kv && b.dwk == b.dwq + dd && b.dbk == b.dbq + d;
-  if (pack_qkv) {
-    if (!fused_bias) {
-      ST_CLEAR(b.dbq, 3 * d);
-      ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, 3 * d, b.dbq, amax));
-    }
-    ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d, zeroed, amax));
-  } else {
-    if (!fused_bias) {
-      ST_CLEAR(b.dbq, d);
-      ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, d, b.dbq, amax));
-    }
-    ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d, zeroed, amax));
-    if (pack_kv) {
+  {
+    cudaStream_t s_main = s;
+    cudaStream_t s = fk.branch(0);     // (shadows the caller's stream inside this block: ST_CLEAR and the kernels below)
+    (void)s_main;
+    if (pack_qkv) {
       if (!fused_bias) {
-        ST_CLEAR(b.dbk, 2 * d);
-        ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, 2 * d, b.dbk, amax));
+        ST_CLEAR(b.dbq, 3 * d);
+        ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, 3 * d, b.dbq, amax));
       }
-      ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d, zeroed, amax));
+      ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, 3 * d, d, zeroed, amax));
     } else {
       if (!fused_bias) {
-        ST_CLEAR(b.dbk, d);
-        ST_CLEAR(b.dbv, d);
-        ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, d, b.dbk, amax));
-        ST_TRY(colsum_add_any(s, dt, dpv, p.ldpv, Mk, d, b.dbv, amax));
+        ST_CLEAR(b.dbq, d);
+        ST_TRY(colsum_add_any(s, dt, dpq, p.ldpq, M, d, b.dbq, amax));
       }
-      ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d, zeroed, amax));
-      ST_TRY(wgrad(s, dt, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d, zeroed, amax));
+      ST_TRY(wgrad(s, dt, dpq, p.ldpq, p.xq_r, d, b.dwq, M, d, d, zeroed, amax));
+      if (pack_kv) {
+        if (!fused_bias) {
+          ST_CLEAR(b.dbk, 2 * d);
+          ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, 2 * d, b.dbk, amax));
+        }
+        ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, 2 * d, d, zeroed, amax));
+      } else {
+        if (!fused_bias) {
+          ST_CLEAR(b.dbk, d);
+          ST_CLEAR(b.dbv, d);
+          ST_TRY(colsum_add_any(s, dt, dpk, p.ldpk, Mk, d, b.dbk, amax));
+          ST_TRY(colsum_add_any(s, dt, dpv, p.ldpv, Mk, d, b.dbv, amax));
+        }
+        ST_TRY(wgrad(s, dt, dpk, p.ldpk, p.xk_r, d, b.dwk, Mk, d, d, zeroed, amax));
+        ST_TRY(wgrad(s, dt, dpv, p.ldpv, p.xv_r, d, b.dwv, Mk, d, d, zeroed, amax));
+      }
     }
   }
   // input gradients; the residual branch contributes dz to EXACTLY ONE input buffer: the first of q, k, v that aliases the
@@ -621,7 +632,7 @@ int st_mha_bwd(const st_mha_bwd_args* bp, cudaStream_t s) {
     ST_REQUIRE(b.dresidual != nullptr, "st_mha_bwd: dresidual is required when residual is a separate tensor");
     ST_CHECK_CUDA(cudaMemcpyAsync(b.dresidual, dz, p.M * d * esz(dt), cudaMemcpyDeviceToDevice, s));
   }
-  return ST_OK;
+  return fk.join();
 }
 
 // ------------------------------------------------------------------ PositionwiseFeedForward
@@ -752,14 +763,18 @@ int st_ffn_bwd(const st_ffn_bwd_args* bp, cudaStream_t s) {
   e.aux_scale = make_dropout(a.dropout_p, 0).scale;
   e.colsum = b.db1;   // db1 = column sums of dh, accumulated by the epilogue that produces dh
   e.unscale_amax = amax;
+  Fork fk(s);                                   // the two weight gradients run next to the chain dz -> dh -> dx (st_host.h)
+  cudaStream_t sw2 = fk.branch(0);
   ST_TRY(gemm_any(s, dt, GEMM_NN, dz, d, p.w2_r, f, dh, f, 1, M, f, d, e));
-  ST_TRY(wgrad(s, dt, dz, d, p.h, f, b.dw2, M, d, f, zeroed, amax));
-  ST_TRY(wgrad(s, dt, dh, f, p.x_r, d, b.dw1, M, f, d, zeroed, amax));
+  cudaStream_t sw1 = fk.branch(1);
+  ST_TRY(wgrad(sw2, dt, dz, d, p.h, f, b.dw2, M, d, f, zeroed, amax));
+  ST_TRY(wgrad(sw1, dt, dh, f, p.x_r, d, b.dw1, M, f, d, zeroed, amax));
   GemmEpilogue ex;
   ex.aux = dz; ex.ldaux = d; ex.aux_mode = 1;
   ex.unscale_amax = amax;
   ex.amax_out = mixed ? b.dx_amax : nullptr;
-  return gemm_any(s, dt, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, mixed ? 0 : 1, M, d, f, ex);
+  ST_TRY(gemm_any(s, dt, GEMM_NN, dh, f, p.w1_r, d, b.dx, d, mixed ? 0 : 1, M, d, f, ex));
+  return fk.join();
 }
 
 

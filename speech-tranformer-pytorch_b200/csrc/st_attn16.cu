@@ -937,6 +937,8 @@ int launch_bwd16(cudaStream_t s, const AttnBwdArgs& a) {
     ST_CHECK_LAUNCH();
   }
   constexpr int SMEM = 4 * 2 * BT * DK * 2 + 1024;
+  Fork fk(s);                           // dK/dV and dQ only share their inputs: two streams (st_host.h)
+  cudaStream_t s_dq = fk.branch(1);
   {
     CUtensorMap tq, tdo;
     ST_TRY(make_act_tmap16(&tq, DT, f.q, f.ldq, cols, f.Lq, f.B, BT, DK));
@@ -958,12 +960,12 @@ int launch_bwd16(cudaStream_t s, const AttnBwdArgs& a) {
     static bool attr = false;
     if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
     dim3 grid((f.Lq + 127) / 128, f.H, f.B);
-    ProfScope prof(s, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
-    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s, static_cast<const T*>(f.q), f.ldq, static_cast<const T*>(a.dctx),
+    ProfScope prof(s_dq, PROF_ATTN_DQ, 6.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
+    ST_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), SMEM, s_dq, static_cast<const T*>(f.q), f.ldq, static_cast<const T*>(a.dctx),
                              a.lddctx, tk, tv, p));
     ST_CHECK_LAUNCH();
   }
-  return ST_OK;
+  return fk.join();
 }
 
 }  // namespace

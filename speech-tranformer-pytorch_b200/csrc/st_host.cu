@@ -45,6 +45,10 @@ Option g_options[] = {
     {"attn_dkv_no_small", 0},  // 1 = never use the single-query-tile dK/dV kernel (A/B testing)
     {"attn_fuse_bias", 0},     // 1 = dq/dk/dv bias column sums from the attention-backward epilogues (measured slower)
     {"attn_dq_res_smem", 0},   // 1 = dQ kernel keeps its resident Q/dO tiles in shared memory (.ss MMAs) instead of TMEM
+    {"ln_bwd_registers", 0},   // 1 = LayerNorm backward with register prefetch (one row per warp in flight) instead of the cp.async ring
+    {"ln_fwd_registers", 0},   // same for the forward
+    {"side_streams", -1},      // independent kernels of a backward operator on library-owned side streams (st_host.h Fork):
+                               // 1 = on, 0 = off, -1 = unset (on unless ST_SIDE_STREAMS=0 in the environment)
     {"pdl", -1},
     {"pdl_graphs", 1},         // keep programmatic dependent launch while the stream is being captured into a CUDA graph (decode:
                                // 73.8 -> 71.0 ms per beam search); 0 / ST_PDL_GRAPHS=0 = plain launches under capture               // programmatic dependent launch: 1 = on, 0 = off, -1 = unset (on unless ST_PDL=0 in the environment)
@@ -154,6 +158,78 @@ void profile_reset() {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();
+}
+
+// ---- side streams
+namespace {
+struct SideDev {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+SideDev g_side[64];
+std::mutex g_side_mu;
+
+SideDev* side_dev() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideDev& d = g_side[dev];
+  if (!d.ok) {
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    if (!d.ok) {
+      bool good = cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < 2 && good; ++i)
+        good = cudaStreamCreateWithFlags(&d.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&d.join[i], cudaEventDisableTiming) == cudaSuccess;
+      if (!good) { cudaGetLastError(); return nullptr; }
+      d.ok = true;
+    }
+  }
+  return &d;
+}
+
+bool side_streams_on(cudaStream_t s) {
+  static Option* opt = [] {
+    Option* o = nullptr;
+    for (auto& x : g_options)
+      if (strcmp(x.name, "side_streams") == 0) o = &x;
+    if (o->value < 0) {
+      const char* e = getenv("ST_SIDE_STREAMS");
+      o->value = (e && e[0] == '0') ? 0 : 1;
+    }
+    return o;
+  }();
+  if (opt->value <= 0) return false;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return st == cudaStreamCaptureStatusNone;
+}
+}  // namespace
+
+Fork::Fork(cudaStream_t main) : main_(main), dev_(side_streams_on(main) ? side_dev() : nullptr) {}
+
+cudaStream_t Fork::branch(int i) {
+  SideDev* d = static_cast<SideDev*>(dev_);
+  if (!d || i < 0 || i > 1) return main_;
+  // an event wait refers to the most recent record at the time of the call: one fork event per device is enough
+  if (cudaEventRecord(d->fork, main_) != cudaSuccess || cudaStreamWaitEvent(d->s[i], d->fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return main_;
+  }
+  used_[i] = true;
+  return d->s[i];
+}
+
+int Fork::join() {
+  SideDev* d = static_cast<SideDev*>(dev_);
+  if (!d) return ST_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (!used_[i]) continue;
+    used_[i] = false;
+    ST_CHECK_CUDA(cudaEventRecord(d->join[i], d->s[i]));
+    ST_CHECK_CUDA(cudaStreamWaitEvent(main_, d->join[i], 0));
+  }
+  return ST_OK;
 }
 
 int num_sms() {

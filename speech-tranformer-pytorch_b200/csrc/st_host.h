@@ -100,6 +100,29 @@ int profile_read(int cls, double* ms, double* work, long long* launches);  // sy
 void profile_reset();
 int profile_dump(const char* path);  // CSV: one line per recorded launch
 
+// ---- side streams.  The backward operators launch kernels that do not depend on each other (the weight-gradient GEMMs
+// and bias column sums against the input-gradient chain; attention's dQ against dK/dV).  Each is a full-device kernel at
+// the encoder's shapes, but at the decoder's (1600 rows) and in every kernel's last wave most SMs idle: branches run on
+// library-owned non-blocking streams (two per device) and rejoin the caller's stream before the operator returns, so the
+// caller sees ordinary stream semantics.  Off under stream capture and with option "side_streams" = 0.
+class Fork {
+ public:
+  explicit Fork(cudaStream_t main);
+  // the stream of branch i (0 or 1), ordered after everything enqueued on the main stream so far; the main stream itself
+  // when side streams are off
+  cudaStream_t branch(int i);
+  // the main stream waits for the branches used so far (also run by the destructor; call it to see the error code)
+  int join();
+  ~Fork() { join(); }
+  Fork(const Fork&) = delete;
+  Fork& operator=(const Fork&) = delete;
+
+ private:
+  cudaStream_t main_;
+  void* dev_;          // per-device state, null = disabled
+  bool used_[2] = {false, false};
+};
+
 // debug / tuning options (st_set_option over the C ABI); unknown names are rejected.
 int set_option(const char* name, int value);
 int get_option(const char* name);

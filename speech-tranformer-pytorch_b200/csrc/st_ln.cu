@@ -307,6 +307,156 @@ add_ln_bwd_kernel(const DyT* __restrict__ dy, const float* __restrict__ z, const
   reduce_store(acc_z, dzsum);
 }
 
+// ---------------------------------------------------------------- backward, fp32 dy: rows staged through shared memory
+// The register-prefetch kernel above keeps ONE row per warp in flight and needs ~195 registers at d = 512 (8 warps per SM):
+// 32 KB in flight per SM, 2.4 TB/s.  Here every warp owns a ring of LNB_STAGES row slots in shared memory filled with
+// cp.async (16 bytes per lane and request, no registers held while the data is in flight), so LNB_STAGES rows of dy and z
+// per warp are outstanding while one is reduced.  Every lane reads back exactly the bytes its own requests wrote — no
+// cross-lane hazard, no barrier; the statistics (8 bytes per row) stay on the one-row register prefetch.
+constexpr int LNB_STAGES = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int VPL, typename DzT>
+__global__ void __launch_bounds__(LN_THREADS)
+add_ln_bwd_staged_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean_in,
+                         const float* __restrict__ rstd_in, const float* __restrict__ gamma, DzT* __restrict__ dz,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dzsum, int64_t rows,
+                         int d, int round_out, uint32_t drop_thresh, float drop_scale, uint64_t drop_seed,
+                         const float* __restrict__ amax, float* __restrict__ clear_scalar) {
+  constexpr int ROWF = VPL * 128;    // floats per row slot (d <= ROWF)
+  extern __shared__ __align__(16) float ln_ring[];
+  __shared__ float red[LN_WARPS][32 * 4 + 4];
+  pdl_wait();      // programmatic dependent launch (st_host.h): before the first global access
+  pdl_trigger();
+  if (clear_scalar && blockIdx.x == 0 && threadIdx.x == 0) *clear_scalar = 0.f;   // see add_ln_bwd_kernel
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const float inv_d = 1.f / static_cast<float>(d);
+  const float out_scale = amax ? grad_scale_from_amax(*amax) : 1.f;
+  float* ring = ln_ring + warp * (LNB_STAGES * 2 * ROWF);
+
+  float4 g[VPL];
+  float4 acc_g[VPL], acc_b[VPL], acc_z[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    g[i] = (c < d) ? ld4(gamma + c) : make_float4(0, 0, 0, 0);
+    acc_g[i] = acc_b[i] = acc_z[i] = make_float4(0, 0, 0, 0);
+  }
+
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * LN_WARPS;
+  const int64_t row_first = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp;
+  auto issue = [&](int64_t r, int slot) {     // one commit group per call, empty past the last row: the group count stays uniform
+    if (r < rows) {
+      float* sdy = ring + (slot * 2) * ROWF;
+      float* sz = sdy + ROWF;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) { cp_async16(sdy + c, dy + r * d + c); cp_async16(sz + c, z + r * d + c); }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < LNB_STAGES; ++s) issue(row_first + s * stride, s);
+  float mean_n = 0.f, rstd_n = 0.f;
+  if (row_first < rows) { mean_n = mean_in[row_first]; rstd_n = rstd_in[row_first]; }
+  int slot = 0;
+  for (int64_t row = row_first; row < rows; row += stride) {
+    cp_async_wait<LNB_STAGES - 1>();          // the oldest group — this row — has landed
+    const float mean = mean_n, rstd = rstd_n;
+    float4 dyc[VPL], zc[VPL];
+    {
+      const float* sdy = ring + (slot * 2) * ROWF;
+      const float* sz = sdy + ROWF;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < d) { dyc[i] = *reinterpret_cast<const float4*>(sdy + c); zc[i] = *reinterpret_cast<const float4*>(sz + c); }
+      }
+    }
+    issue(row + LNB_STAGES * stride, slot);   // refill the slot just read (same lane, same bytes: program order suffices)
+    if (row + stride < rows) { mean_n = mean_in[row + stride]; rstd_n = rstd_in[row + stride]; }
+    slot = (slot + 1 == LNB_STAGES) ? 0 : slot + 1;
+
+    float4 xh[VPL], gy[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float4 dyv = dyc[i];
+        if (drop_thresh) {
+          float* e = reinterpret_cast<float*>(&dyv);
+          const uint32_t key = dropout_row_key(drop_seed, static_cast<uint64_t>(row));
+#pragma unroll
+          for (int t = 0; t < 4; t += 2) {
+            const uint32_t bits = dropout_pair(key, c + t);
+            e[t] = dropout_keep(bits, 0, drop_thresh) ? e[t] * drop_scale : 0.f;
+            e[t + 1] = dropout_keep(bits, 1, drop_thresh) ? e[t + 1] * drop_scale : 0.f;
+          }
+        }
+        const float4 zv = zc[i];
+        xh[i] = make_float4((zv.x - mean) * rstd, (zv.y - mean) * rstd, (zv.z - mean) * rstd, (zv.w - mean) * rstd);
+        gy[i] = make_float4(dyv.x * g[i].x, dyv.y * g[i].y, dyv.z * g[i].z, dyv.w * g[i].w);
+        s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+        s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+        acc_g[i].x += dyv.x * xh[i].x; acc_g[i].y += dyv.y * xh[i].y;
+        acc_g[i].z += dyv.z * xh[i].z; acc_g[i].w += dyv.w * xh[i].w;
+        acc_b[i].x += dyv.x; acc_b[i].y += dyv.y; acc_b[i].z += dyv.z; acc_b[i].w += dyv.w;
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d;
+    const float c2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < d) {
+        float o[4] = {rstd * (gy[i].x - c1 - xh[i].x * c2), rstd * (gy[i].y - c1 - xh[i].y * c2),
+                      rstd * (gy[i].z - c1 - xh[i].z * c2), rstd * (gy[i].w - c1 - xh[i].w * c2)};
+        acc_z[i].x += o[0]; acc_z[i].y += o[1]; acc_z[i].z += o[2]; acc_z[i].w += o[3];
+        if (amax) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o[t] *= out_scale;
+        }
+        if (sizeof(DzT) == 4 && round_out) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) o[t] = tf32_rna(o[t]);
+        }
+        st4(dz + row * d + c, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  auto reduce_store = [&](float4 (&acc)[VPL], float* dst) {
+    if (!dst) return;  // uniform across the block
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      __syncthreads();
+      red[warp][lane * 4 + 0] = acc[i].x; red[warp][lane * 4 + 1] = acc[i].y;
+      red[warp][lane * 4 + 2] = acc[i].z; red[warp][lane * 4 + 3] = acc[i].w;
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) s += red[w][threadIdx.x];
+        const int c = (i * 32 + (threadIdx.x >> 2)) * 4 + (threadIdx.x & 3);
+        if (c < d) atomicAdd(dst + c, s);
+      }
+    }
+  };
+  reduce_store(acc_g, dgamma);
+  reduce_store(acc_b, dbeta);
+  reduce_store(acc_z, dzsum);
+}
+
 // ---------------------------------------------------------------- TF32 rounding copy (2-D, strided)
 __global__ void __launch_bounds__(256)
 round_tf32_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
@@ -470,8 +620,31 @@ int add_ln_bwd_t(cudaStream_t stream, const DyT* dy, const float* z, const float
   ST_REQUIRE(aligned8(dy) && aligned16(z) && aligned16(gamma) && aligned8(dz) && (sizeof(DyT) == 2 || aligned16(dy)) &&
                  (sizeof(DzT) == 2 || aligned16(dz)),
              "add_ln_bwd: pointers must be 16-byte aligned");
-  const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 4);
   ProfScope prof(stream, PROF_LN_BWD, 1.0 * rows * d * 4 + 1.0 * rows * d * (sizeof(DyT) + sizeof(DzT)));
+  if constexpr (sizeof(DyT) == 4) {
+    // fp32 dy (TF32 path, fp16-operand engine): rows staged through shared memory with cp.async
+    if (!gate && d <= 512 && aligned16(dy) && aligned16(z) && (sizeof(DzT) == 4 ? aligned16(dz) : aligned8(dz)) && !get_option("ln_bwd_registers")) {
+      const int vpl = d <= 128 ? 1 : (d <= 256 ? 2 : 4);
+      const size_t smem = static_cast<size_t>(LN_WARPS) * LNB_STAGES * 2 * vpl * 128 * sizeof(float);
+      const int per_sm = vpl == 4 ? 1 : (vpl == 2 ? 2 : 4);
+      const int sgrid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, per_sm);
+#define ST_LAUNCH_S(VPL)                                                                                                \
+  do {                                                                                                                  \
+    auto kern = add_ln_bwd_staged_kernel<VPL, DzT>;                                                                     \
+    static bool attr = false;                                                                                           \
+    if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; } \
+    ST_CHECK_CUDA(launch_pdl(kern, dim3(sgrid), dim3(LN_THREADS), smem, stream, dy, z, mean, rstd, gamma, dz, dgamma, dbeta, dzsum,  \
+                             rows, d, round_out, drop.thresh, drop.scale, drop.seed, amax, clear_scalar));               \
+  } while (0)
+      if (vpl == 1) ST_LAUNCH_S(1);
+      else if (vpl == 2) ST_LAUNCH_S(2);
+      else ST_LAUNCH_S(4);
+#undef ST_LAUNCH_S
+      ST_CHECK_LAUNCH();
+      return ST_OK;
+    }
+  }
+  const int grid = persistent_grid((rows + LN_WARPS - 1) / LN_WARPS, 4);
 #define ST_LAUNCH(VPL, W)                                                                                      \
   ST_CHECK_CUDA(launch_pdl(add_ln_bwd_kernel<VPL, DyT, DzT, W>, dim3(grid), dim3(LN_THREADS), 0, stream, dy, z, mean, rstd, gamma, dz, \
                            dgamma, dbeta, dzsum, rows, d, round_out, drop.thresh, drop.scale, drop.seed, gate, gate_scale, amax, clear_scalar))
