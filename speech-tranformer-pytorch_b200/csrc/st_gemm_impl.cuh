@@ -64,6 +64,7 @@ struct GemmParams {
   int kblocks_total, kblocks_per_split;
   GemmEpilogue ep;
   int flavour;   // EpiFlavour
+  int rows16;    // 0 = transposing epilogue; 1 / 2 = row-layout epilogue, direct / packed-staged stores (epilogue_rows16)
 };
 
 // ---- epilogue ------------------------------------------------------------------------------------------------
@@ -338,6 +339,81 @@ __device__ __noinline__ void epilogue_generic(const GemmParams& p, float* stg, u
   }
 }
 
+// Row-layout epilogue for 16-bit outputs without aux operand or column sums (QKV / KV projections, dctx, fc1): every
+// thread keeps the 32 columns of ITS row that tcgen05.ld delivers, applies bias / ReLU / dropout there and packs them to
+// 64 bytes.  The fp32 transpose of epilogue_fast moves 2 x 128 KB per 128 x 256 tile through shared memory — as much as
+// the MMAs of a K = 512 main loop read from it — so the two legs of the (main loop || epilogue) pipeline contend for
+// shared-memory bandwidth.  Here either nothing goes through shared memory (STAGED = false: each thread stores its own
+// 64-byte row segment) or only the packed result does (STAGED = true: 2 x 64 KB per tile, stores coalesced to 64 bytes
+// per row and 8 rows per instruction).  Requires N % 8 == 0, ldc % 8 == 0 and a 16-byte aligned C (host-checked).
+template <typename T, int BN, bool RELU_DROP, bool STAGED>
+__device__ __forceinline__ void epilogue_rows16(const GemmParams& p, uint32_t stg_s, uint32_t tmem_acc, int m_blk, int n_blk,
+                                                int quarter, int half, int lane) {
+  const GemmEpilogue& ep = p.ep;
+  const int row = m_blk * BM + quarter * 32 + lane;
+  const bool row_ok = row < p.M;
+  const int n_chunks = min(BN / 32, (p.N - n_blk * BN + 31) >> 5);
+  const bool has_bias = ep.bias != nullptr;
+  const uint32_t key = RELU_DROP ? dropout_row_key(ep.drop_seed, static_cast<uint64_t>(row)) : 0u;
+  T* crow = static_cast<T*>(p.C) + static_cast<int64_t>(row) * p.ldc;
+#pragma unroll 1
+  for (int c = half; c < n_chunks; c += EPI_WARPS / 4) {
+    const int col = n_blk * BN + c * 32;
+    const int ncols = min(32, p.N - col);          // multiple of 8
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + c * 32, r);
+    float4 b4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)                    // the same address in every lane: one broadcast transaction each
+      b4[j] = (has_bias && j * 4 < ncols) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tmem_ld_wait();
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v[4] = {__uint_as_float(r[4 * j]) + b4[j].x, __uint_as_float(r[4 * j + 1]) + b4[j].y,
+                    __uint_as_float(r[4 * j + 2]) + b4[j].z, __uint_as_float(r[4 * j + 3]) + b4[j].w};
+      if (RELU_DROP) {
+#pragma unroll
+        for (int t = 0; t < 4; t += 2) {
+          const uint32_t bits = dropout_pair(key, col + 4 * j + t);
+          v[t] = ((bits & 0xFFFFu) >= ep.drop_thresh) ? fmaxf(v[t], 0.f) * ep.drop_scale : 0.f;
+          v[t + 1] = ((bits >> 16) >= ep.drop_thresh) ? fmaxf(v[t + 1], 0.f) * ep.drop_scale : 0.f;
+        }
+      }
+      w[2 * j] = pack2<T>(v[0], v[1]);
+      w[2 * j + 1] = pack2<T>(v[2], v[3]);
+    }
+    if constexpr (!STAGED) {
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q * 8 < ncols) *reinterpret_cast<uint4*>(crow + col + q * 8) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      }
+    } else {
+      // 32 rows x 64 bytes; 16-byte slot q of row r lives at r * 64 + ((q ^ (r >> 1)) & 3) * 16: conflict-free for the
+      // row-per-lane writes and for the (8 rows x 4 slots)-per-instruction reads
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t a = stg_s + lane * 64 + (((q ^ (lane >> 1)) & 3) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
+      }
+      __syncwarp();
+      const int q = lane & 3;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2);
+        uint4 v;
+        const uint32_t a = stg_s + rr * 64 + (((q ^ (rr >> 1)) & 3) << 4);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+        const int grow = m_blk * BM + quarter * 32 + rr;
+        if (grow < p.M && q * 8 < ncols)
+          *reinterpret_cast<uint4*>(static_cast<T*>(p.C) + static_cast<int64_t>(grow) * p.ldc + col + q * 8) = v;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 template <typename T, int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* stg, uint32_t tmem_acc, int m_blk, int n_blk,
                                               int quarter, int half, int lane) {
@@ -355,6 +431,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* stg, u
       default:                  epilogue_generic<T, BN>(p, stg, tmem_acc, m_blk, n_blk, quarter, half, lane); break;
     }
   } else {   // 16-bit operands: the host maps the *_ROUND flavours onto these and sends the other mixes to the generic routine
+    if (p.rows16) {            // warp-uniform; host: 16-bit C, 16-byte rows, no aux / column sums / amax
+      if (p.rows16 == 1) {
+        if (p.flavour == EPI_PLAIN) epilogue_rows16<T, BN, false, false>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane);
+        else epilogue_rows16<T, BN, true, false>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane);
+      } else {
+        if (p.flavour == EPI_PLAIN) epilogue_rows16<T, BN, false, true>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane);
+        else epilogue_rows16<T, BN, true, true>(p, stg_s, tmem_acc, m_blk, n_blk, quarter, half, lane);
+      }
+      return;
+    }
     switch (p.flavour) {
       case EPI_PLAIN:          if (p.c_lp) ST_EPI(EPI_PLAIN, T); else ST_EPI(EPI_PLAIN, float); break;
       case EPI_AUX_ADD:        if (p.c_lp) ST_EPI(EPI_AUX_ADD, T); else ST_EPI(EPI_AUX_ADD, float); break;
@@ -847,6 +933,10 @@ int gemm_run(cudaStream_t stream, GemmMode mode, const void* A, int64_t lda, con
   p.n_tiles = (N + BN - 1) / BN;
   p.ep = ep;
   p.flavour = pick_flavour<T>(ep, C, ldc, p.c_lp, N);
+  p.rows16 = 0;
+  if (E::k16 && p.c_lp && (p.flavour == EPI_PLAIN || p.flavour == EPI_RELU_DROP) && !ep.colsum && !ep.amax_out && (N & 7) == 0 &&
+      (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0))
+    p.rows16 = get_option("gemm_rows16");
   float* deferred_colsum = nullptr;
   if (ep.colsum && (p.flavour == EPI_GENERIC || p.flavour == EPI_ATOMIC || (reinterpret_cast<uintptr_t>(ep.colsum) & 15))) {
     deferred_colsum = ep.colsum;   // the generic epilogue has no fused column sums: separate pass below

@@ -281,3 +281,34 @@ def test_write_measured_errors():
     os.makedirs("gpurun_out", exist_ok=True)
     with open(os.path.join("gpurun_out", "round2_parity_errors.json"), "w") as f:
         json.dump(MEASURED, f, indent=1, sort_keys=True)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM epilogue layouts
+@pytest.mark.parametrize("tdt", [torch.float16, torch.bfloat16])
+def test_gemm_row_layout_epilogue_is_bit_identical(stb, tdt):
+    """16-bit-output GEMMs without aux operand drain their accumulators in row layout (st_gemm_impl.cuh epilogue_rows16, the
+    default) instead of transposing fp32 tiles through shared memory: same bits for every shape class — full tiles, ragged
+    M, N % 32 != 0, bias / no bias, ReLU + dropout — and for both store variants."""
+    L, lib = stb._lib, stb._lib.load()
+    DT = L.DTYPE_F16 if tdt == torch.float16 else L.DTYPE_BF16
+    try:
+        for mode, M, N, K, bias, drop in [(0, 1000, 1536, 512, True, 0.0), (0, 777, 2048, 256, True, 0.1), (1, 640, 512, 512, False, 0.0),
+                                          (0, 333, 520, 192, True, 0.1), (1, 77, 72, 64, False, 0.0), (0, 4100, 264, 128, True, 0.0)]:
+            gen = torch.Generator(device=DEV).manual_seed(M + N)
+            A = torch.randn(M, K, device=DEV, generator=gen).to(tdt)
+            B = torch.randn((N, K) if mode == 0 else (K, N), device=DEV, generator=gen).to(tdt)
+            bvec = torch.randn(N, device=DEV, generator=gen) if bias else None
+            ep = L.GemmEpilogue(bias=None if bvec is None else bvec.data_ptr(), aux=None, ldaux=0, aux_mode=0, relu=1 if drop else 0,
+                                round_tf32=0, k_splits=1, dropout_p=drop, seed=7)
+            outs = []
+            for opt in (0, 1, 2):
+                L.check(lib.st_set_option(b"gemm_rows16", opt))
+                out = torch.full((M, N), 7.0, device=DEV, dtype=tdt)
+                L.check(lib.st_gemm_dt(DT, mode, A.data_ptr(), K, B.data_ptr(), B.shape[1], out.data_ptr(), N, 1, M, N, K, C.byref(ep), None))
+                outs.append(out)
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (mode, M, N, K)
+            if not drop:    # and the value itself, against torch
+                ref = (A.float() @ (B.float().t() if mode == 0 else B.float())) + (bvec if bias else 0.0)
+                assert relerr(outs[2].float(), ref) < (2e-3 if tdt == torch.float16 else 1e-2)
+    finally:
+        L.check(lib.st_set_option(b"gemm_rows16", 2))
