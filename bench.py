@@ -488,11 +488,16 @@ def main_b200(args):
         torch.backends.cuda.matmul.allow_tf32 = old
         tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
         del a, b
+        # per-class times are CUDA-event intervals around every launch: measured with the library's side streams off, so no
+        # interval contains another kernel's work (the timed region above runs with them on)
+        side_on = os.environ.get("ST_SIDE_STREAMS", "1") != "0"
+        lib.st_set_option(b"side_streams", 0)
         lib.st_profile_reset()
         lib.st_profile_enable(1)
         psteps = min(args.steps, 3)
         ms_prof = timed(step_resident, psteps)
         lib.st_profile_enable(0)
+        lib.st_set_option(b"side_streams", 1 if side_on else 0)
         breakdown = {}
         for c in range(lib.st_profile_classes()):
             t, w, k = C.c_double(), C.c_double(), C.c_int64()
@@ -529,15 +534,18 @@ def main_b200(args):
     # ---- the fused EncoderLayer alone (north_star: tensor-pipe utilisation of EncoderLayer fwd+bwd at B=32,T=1000,d=512,h=8)
     enc_layer = None
     if rank == 0 and not args.no_roofline:
-        layer = net.encoder.layer_stack[0]
+        # a private copy of the first encoder layer with its own flat buffers (as in training: operand-precision weight twins,
+        # parameter gradients written straight into the flat gradient buffer) — at N > 1 only rank 0 runs this leg, so it
+        # must not touch the data-parallel trainer's buckets
+        import copy
+        layer = copy.deepcopy(net.encoder.layer_stack[0])
+        ltrainer = spar.DataParallelTrainer(layer, d_model=d, compute_dtype=act_dtype, overlap=False)
         lx = torch.randn(args.batch, args.frames, d, device=dev).to(act_dtype)
         lg = torch.randn(args.batch, args.frames, d, device=dev).to(act_dtype)
         lmask = stb.functional.LengthMask(resident[2], args.frames, args.frames)
-        lparams = [q for q in layer.parameters()]
 
         def layer_step():
-            for q in lparams:
-                q.grad = None
+            ltrainer.zero_grad()
             xin = lx.detach().requires_grad_()
             y, _ = layer(xin, slf_attn_mask=lmask)
             y.backward(lg)
@@ -566,8 +574,7 @@ def main_b200(args):
                              "FLOPs = 3 x (8Nd^2 + 4BhT^2dk + 4Nd*dff), no recompute counted, padded frames counted as the "
                              "reference computes them; --dtype fp32: fp32 in / out, fp16 operands inside; tf32 operands issue at half the "
                              "bf16 / fp16 tensor-pipe rate"}
-        for q in lparams:
-            q.grad = None
+        del ltrainer, layer
         trainer.zero_grad()
 
     cpu = None
