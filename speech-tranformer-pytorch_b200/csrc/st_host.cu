@@ -169,6 +169,8 @@ struct SideDev {
   cudaStream_t s[2] = {nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
   bool ok = false;
+  std::recursive_mutex mu;   // held from a Fork's first branch() to its join(): the streams and events are shared by every host
+                             // thread that drives this device (nested Forks of one operator run on the same thread)
 };
 SideDev g_side[64];
 std::mutex g_side_mu;
@@ -214,9 +216,12 @@ Fork::Fork(cudaStream_t main) : main_(main), dev_(side_streams_on(main) ? side_d
 cudaStream_t Fork::branch(int i) {
   SideDev* d = static_cast<SideDev*>(dev_);
   if (!d || i < 0 || i > 1) return main_;
+  const bool first = !used_[0] && !used_[1];
+  if (first) d->mu.lock();
   // an event wait refers to the most recent record at the time of the call: one fork event per device is enough
   if (cudaEventRecord(d->fork, main_) != cudaSuccess || cudaStreamWaitEvent(d->s[i], d->fork, 0) != cudaSuccess) {
     cudaGetLastError();
+    if (first) d->mu.unlock();
     return main_;
   }
   used_[i] = true;
@@ -225,14 +230,18 @@ cudaStream_t Fork::branch(int i) {
 
 int Fork::join() {
   SideDev* d = static_cast<SideDev*>(dev_);
-  if (!d) return ST_OK;
+  if (!d || (!used_[0] && !used_[1])) return ST_OK;
+  int status = ST_OK;
   for (int i = 0; i < 2; ++i) {
     if (!used_[i]) continue;
     used_[i] = false;
-    ST_CHECK_CUDA(cudaEventRecord(d->join[i], d->s[i]));
-    ST_CHECK_CUDA(cudaStreamWaitEvent(main_, d->join[i], 0));
+    if (cudaEventRecord(d->join[i], d->s[i]) != cudaSuccess || cudaStreamWaitEvent(main_, d->join[i], 0) != cudaSuccess) {
+      set_error("side streams: join failed (%s)", cudaGetErrorString(cudaGetLastError()));
+      status = ST_ERR_CUDA;
+    }
   }
-  return ST_OK;
+  d->mu.unlock();
+  return status;
 }
 
 int num_sms() {
