@@ -887,6 +887,236 @@ attn16_bwd_dkv(const T* __restrict__ k, int64_t ldk, const T* __restrict__ v, in
   if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
 }
 
+// ================================================================================ dK, dV for ONE query tile (Lq <= 64)
+// Decoder cross-attention (50 target positions against 1000 encoder frames) and decoder self-attention.  With a single
+// query tile the kernel above is one short tile per CTA — barrier / TMEM set-up, the resident K/V load and the output write
+// are all exposed (2048 CTAs x ~7 us at B=32, h=8, Lk=1000: 95 us).  Here a CTA keeps the query-side tiles (Q, dO — one
+// copy each serves as K-major and as MN-major operand — log-sum-exp, delta, dropout keys) resident and walks over SEVERAL
+// key tiles: K/V tiles double-buffered in shared memory (TMA), S^T / dP^T and the dV / dK accumulators double-buffered in
+// TMEM, so the loads of tile i+1, the MMAs of tile i and the output write of tile i-1 overlap.  Same mathematics and thread
+// mapping as attn16_bwd_dkv (16-bit twin of st_attn_bwd.cu attn_bwd_dkv_small).
+template <typename T, int DK>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn16_bwd_dkv_small(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                     const __grid_constant__ CUtensorMap tmap_k_res, const __grid_constant__ CUtensorMap tmap_v_res,
+                     const AttnDev p) {
+  constexpr int BKV = 128;
+  constexpr int G = DK / 64;
+  constexpr int T_BYTES = BT * DK * 2;
+  constexpr int RES_BYTES = BKV * DK * 2;
+  constexpr uint32_t TCOLS = 512;
+  // TMEM: S^T x2 | dP^T x2 | dV x2 | dK x2
+  constexpr uint32_t T_ST = 0, T_DPT = 2 * BT, T_DV = 4 * BT, T_DK = 4 * BT + 2 * DK;
+  static_assert(4 * BT + 4 * DK <= 512, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sBase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sRes = sBase;                                  // [2 buffers][K | V]
+  uint8_t* sQ = sBase + 4 * RES_BYTES;                    // Q | dO
+  __shared__ uint64_t q_full, res_full[2], res_empty[2], s_full[2], ds_full[2], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_lse[BT];
+  __shared__ __align__(16) float s_delta[BT];
+  __shared__ __align__(16) uint32_t s_rkey[BT];
+  __shared__ int s_extent;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_kt_all = (p.Lk + BKV - 1) / BKV;
+
+  if (tid == 0) {
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], NCOMP);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NCOMP);
+    }
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) { tmem_alloc(&tmem_slot, TCOLS); tmem_relinquish(); }
+  pdl_wait();      // nothing above reads or writes global memory (programmatic dependent launch, st_host.h)
+  pdl_trigger();
+
+  const int extent = block_key_extent(p, b, &s_extent);
+  // key tiles up to the utterance's last valid key are computed; tiles entirely inside its padding get zeros (below)
+  const int n_kt = (extent > 0 && extent < p.Lk) ? (extent + BKV - 1) / BKV : n_kt_all;
+  const int first = blockIdx.x, step = gridDim.x;
+  const int n_it = first < n_kt ? (n_kt - first + step - 1) / step : 0;   // key tiles of this CTA: first, first + step, ...
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == W_PROD) {
+    // ===================== producer =====================
+    if (n_it > 0) {
+#pragma unroll
+      for (int e = lane; e < BT; e += 32) {   // per-query statistics of the single query tile
+        const int64_t o = (static_cast<int64_t>(b) * p.H + h) * p.Lq + (e < p.Lq ? e : 0);
+        s_lse[e] = e < p.Lq ? p.lse2[o] : INFINITY;   // +inf => probability 0 for padded query rows
+        s_delta[e] = e < p.Lq ? p.delta[o] * p.ds_boost : 0.f;
+        s_rkey[e] = p.drop_thresh ? dropout_row_key(p.drop_seed, static_cast<uint64_t>(o)) : 0u;
+      }
+      __syncwarp();
+      if (elect_one()) {
+        tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k_res); tma_prefetch_desc(&tmap_v_res);
+        mbar_arrive_expect_tx(&q_full, 2 * T_BYTES);   // release: the statistics above become visible with it
+        tma_load_4d(sQ, &tmap_q, &q_full, 0, 0, h * G, b);
+        tma_load_4d(sQ + T_BYTES, &tmap_do, &q_full, 0, 0, h * G, b);
+      }
+      __syncwarp();
+      for (int it = 0; it < n_it; ++it) {
+        const int rb = it & 1, kv0 = (first + it * step) * BKV;
+        if (it >= 2) mbar_wait(&res_empty[rb], ((it >> 1) - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&res_full[rb], 2 * RES_BYTES);
+          tma_load_4d(sRes + rb * 2 * RES_BYTES, &tmap_k_res, &res_full[rb], 0, kv0, h * G, b);               // rows >= Lk: zeros
+          tma_load_4d(sRes + rb * 2 * RES_BYTES + RES_BYTES, &tmap_v_res, &res_full[rb], 0, kv0, h * G, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer (converged warp + elect.sync) =====================
+    if (n_it > 0) {
+      const uint32_t sq0 = smem_u32(sQ), sr0 = smem_u32(sRes);
+      auto koff = [](int ks, int rows) { return static_cast<uint64_t>(((ks / 4) * (rows * 128) + (ks % 4) * 32) >> 4); };
+      const uint64_t dqk = umma_desc_kmajor(sq0), dqm = umma_desc_mn<T>(sq0, BT * 128);
+      const uint64_t ddok = umma_desc_kmajor(sq0 + T_BYTES), ddom = umma_desc_mn<T>(sq0 + T_BYTES, BT * 128);
+      auto issue_a = [&](int it) {   // S^T = K Q^T, dP^T = V dO^T   (A = K / V tile in shared memory, B = Q / dO K-major)
+        const int rb = it & 1;
+        mbar_wait(&res_full[rb], (it >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc<T>(128, BT, false, false);
+          const uint64_t ak0 = umma_desc_kmajor(sr0 + rb * 2 * RES_BYTES), av0 = umma_desc_kmajor(sr0 + rb * 2 * RES_BYTES + RES_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < DK / 16; ++ks)
+            umma_f16_ss(tmem + T_ST + rb * BT, ak0 + koff(ks, BKV), dqk + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < DK / 16; ++ks)
+            umma_f16_ss(tmem + T_DPT + rb * BT, av0 + koff(ks, BKV), ddok + koff(ks, BT), idesc, ks > 0 ? 1u : 0u);
+          umma_commit(&s_full[rb]);
+          umma_commit(&res_empty[rb]);   // only these two products read the K / V tile: its buffer is free as soon as they retire,
+        }                                // so the producer runs two key tiles ahead and the TMA latency stays hidden
+        __syncwarp();
+      };
+      auto issue_b = [&](int it) {   // dV = P^T dO, dK = dS^T Q   (A packed in TMEM, B MN-major)
+        const int rb = it & 1;
+        mbar_wait(&ds_full[rb], (it >> 1) & 1);
+        if (it >= 2) mbar_wait(&acc_empty[rb], ((it >> 1) - 1) & 1);   // the epilogue of tile it-2 has drained this accumulator pair
+        tc_fence_after();
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc<T>(128, DK, false, true);
+#pragma unroll
+          for (int ks = 0; ks < BT / 16; ++ks)   // queries [16 ks, +16): the 8 packed columns slice ks wrote at 16 ks
+            umma_f16_ts(tmem + T_DV + rb * DK, tmem + T_ST + rb * BT + ks * 16, ddom + static_cast<uint64_t>((ks * 2048) >> 4), idesc,
+                        ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < BT / 16; ++ks)
+            umma_f16_ts(tmem + T_DK + rb * DK, tmem + T_DPT + rb * BT + ks * 16, dqm + static_cast<uint64_t>((ks * 2048) >> 4), idesc,
+                        ks > 0 ? 1u : 0u);
+          umma_commit(&acc_full[rb]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(&q_full, 0);
+      tc_fence_after();
+      issue_a(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_a(it + 1);
+        issue_b(it);
+      }
+    }
+  } else {
+    // ===================== compute warps =====================
+    const int quarter = warp & 3, slice = warp >> 2;
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int col0 = slice * 16;
+    const bool mask_per_key = (p.mask != nullptr) && (p.ms_q == 0);
+    const bool mask_dense = ((p.mask != nullptr) && !mask_per_key) || p.causal;
+    const float dscale = p.drop_thresh ? p.drop_scale : 1.f;
+    const float dsc = dscale * p.ds_boost;
+    const float kscale = p.scale / p.ds_boost;
+    auto epilogue = [&](int it) {   // dV = dropout-scale * acc, dK = softmax-scale / boost * acc for the key tile of iteration `it`
+      const int rb = it & 1;
+      const int key = (first + it * step) * BKV + quarter * 32 + lane;
+      const bool key_ok = key < p.Lk;
+      mbar_wait(&acc_full[rb], (it >> 1) & 1);
+      tc_fence_after();
+      if (col0 < DK) {
+        uint32_t rv[16], rk[16];
+        tmem_ld16(t_lane + T_DV + rb * DK + col0, rv);
+        tmem_ld16(t_lane + T_DK + rb * DK + col0, rk);
+        tmem_ld_wait();
+        if (key_ok) {
+          uint32_t wv[8], wk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            wv[i] = pack2<T>(__uint_as_float(rv[2 * i]) * dscale, __uint_as_float(rv[2 * i + 1]) * dscale);
+            wk[i] = pack2<T>(__uint_as_float(rk[2 * i]) * kscale, __uint_as_float(rk[2 * i + 1]) * kscale);
+          }
+          store_words<8>(static_cast<T*>(p.dv) + (static_cast<int64_t>(b) * p.Lk + key) * p.lddv + h * DK + col0, wv);
+          store_words<8>(static_cast<T*>(p.dk) + (static_cast<int64_t>(b) * p.Lk + key) * p.lddk + h * DK + col0, wk);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[rb]);
+    };
+    if (n_it > 0) mbar_wait(&q_full, 0);   // the statistics in shared memory are valid from here on
+    for (int it = 0; it < n_it; ++it) {
+      const int rb = it & 1;
+      const int key = (first + it * step) * BKV + quarter * 32 + lane;
+      const bool key_ok = key < p.Lk;
+      bool key_masked = !key_ok || key >= key_limit(p, b);
+      if (mask_per_key && !key_masked) key_masked = p.mask[b * p.ms_b + static_cast<int64_t>(key) * p.ms_k] != 0;
+      const int causal_key = p.causal ? key : -1;
+      const uint8_t* mrow = (p.mask != nullptr && !mask_per_key) ? p.mask + b * p.ms_b + static_cast<int64_t>(key_ok ? key : 0) * p.ms_k : nullptr;
+      const uint32_t my_ckey = p.drop_thresh ? dropout_col_key(p.drop_seed, static_cast<uint32_t>(key_ok ? key : 0)) : 0u;
+      mbar_wait(&s_full[rb], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t rs[16], rd[16], op[8], ods[8];
+      tmem_ld16(t_lane + T_ST + rb * BT + col0, rs);
+      tmem_ld16(t_lane + T_DPT + rb * BT + col0, rd);
+      tmem_ld_wait();
+      if (!mask_dense && key_masked) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { op[i] = 0u; ods[i] = 0u; }
+      } else {
+        const float* ls = s_lse + col0;
+        const float* de = s_delta + col0;
+        const uint32_t* rk = s_rkey + col0;
+        if (mask_dense) {
+          if (p.drop_thresh) dkv16_t<T, true, true>(rs, rd, op, ods, ls, de, rk, p.scale_log2, dsc, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, !key_masked, causal_key);
+          else dkv16_t<T, true, false>(rs, rd, op, ods, ls, de, rk, p.scale_log2, dsc, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, !key_masked, causal_key);
+        } else {
+          if (p.drop_thresh) dkv16_t<T, false, true>(rs, rd, op, ods, ls, de, rk, p.scale_log2, dsc, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, !key_masked, causal_key);
+          else dkv16_t<T, false, false>(rs, rd, op, ods, ls, de, rk, p.scale_log2, dsc, p.drop_thresh, my_ckey, mrow, p.ms_q, col0, p.Lq, !key_masked, causal_key);
+        }
+      }
+      tmem_st8(t_lane + T_ST + rb * BT + col0, op);     // into the first half of the columns this thread has just read
+      tmem_st8(t_lane + T_DPT + rb * BT + col0, ods);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&ds_full[rb]);
+      if (it > 0) epilogue(it - 1);       // overlaps the gradient MMAs of this tile
+    }
+    if (n_it > 0) epilogue(n_it - 1);
+    // key tiles entirely inside the utterance's padding: zero gradients
+    for (int kt = n_kt + first; kt < n_kt_all; kt += step) {
+      const int rows = min(BKV, p.Lk - kt * BKV);
+      for (int i = tid; i < rows * (DK / 8); i += NCOMP) {
+        const int r = i / (DK / 8), c = (i - r * (DK / 8)) * 8;
+        const int64_t grow = static_cast<int64_t>(b) * p.Lk + kt * BKV + r;
+        *reinterpret_cast<uint4*>(static_cast<T*>(p.dk) + grow * p.lddk + h * DK + c) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(static_cast<T*>(p.dv) + grow * p.lddv + h * DK + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) { tc_fence_after(); tmem_dealloc(tmem, TCOLS); }
+}
+
 // ================================================================================ host side
 int check_attn16(const AttnArgs& a, const char* who) {
   ST_REQUIRE(a.B > 0 && a.H > 0 && a.Lq > 0 && a.Lk > 0, "%s: empty problem", who);
@@ -939,7 +1169,24 @@ int launch_bwd16(cudaStream_t s, const AttnBwdArgs& a) {
   constexpr int SMEM = 4 * 2 * BT * DK * 2 + 1024;
   Fork fk(s);                           // dK/dV and dQ only share their inputs: two streams (st_host.h)
   cudaStream_t s_dq = fk.branch(1);
-  {
+  if (f.Lq <= BT && !get_option("attn_dkv_no_small")) {   // single query tile: the persistent multi-key-tile kernel
+    CUtensorMap tq, tdo, tkr, tvr;
+    ST_TRY(make_act_tmap16(&tq, DT, f.q, f.ldq, cols, f.Lq, f.B, BT, DK));
+    ST_TRY(make_act_tmap16(&tdo, DT, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, DK));
+    ST_TRY(make_act_tmap16(&tkr, DT, f.k, f.ldk, cols, f.Lk, f.B, 128, DK));
+    ST_TRY(make_act_tmap16(&tvr, DT, f.v, f.ldv, cols, f.Lk, f.B, 128, DK));
+    constexpr int SMEM_SMALL = 4 * 128 * DK * 2 + 2 * BT * DK * 2 + 1024;
+    auto ks = attn16_bwd_dkv_small<T, DK>;
+    static bool attr_small = false;
+    if (!attr_small) { ST_CHECK_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SMALL)); attr_small = true; }
+    const int n_kt = (f.Lk + 127) / 128;
+    int split = get_option("attn_dkv_small_split");
+    if (split <= 0) split = 1;
+    dim3 grid(n_kt < split ? n_kt : split, f.H, f.B);
+    ProfScope prof(s, PROF_ATTN_DKV, 4.0 * f.B * f.H * static_cast<double>(f.Lq) * f.Lk * DK);
+    ST_CHECK_CUDA(launch_pdl(ks, grid, dim3(NTHREADS), SMEM_SMALL, s, tq, tdo, tkr, tvr, p));
+    ST_CHECK_LAUNCH();
+  } else {
     CUtensorMap tq, tdo;
     ST_TRY(make_act_tmap16(&tq, DT, f.q, f.ldq, cols, f.Lq, f.B, BT, DK));
     ST_TRY(make_act_tmap16(&tdo, DT, a.dctx, a.lddctx, cols, f.Lq, f.B, BT, DK));
