@@ -423,6 +423,7 @@ def main_b200(args):
     launches0 = lib.st_launch_count()
     early0 = trainer.early_launches
     ms = timed(step_resident, args.steps)
+    peak_mem_gib = torch.cuda.max_memory_allocated(dev) / 2 ** 30      # model + optimizer state + one step's activations
     launches = lib.st_launch_count() - launches0
     early = (trainer.early_launches - early0) / args.steps
     clocks = sampler.stop() if sampler else None
@@ -606,6 +607,7 @@ def main_b200(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": DTYPE_DESC[args.dtype], "data": "synthetic", "config": workload_config(args, n),
                 "valid_frames_per_s": valid_frames * n * args.steps / (ms * 1e-3),
+                "peak_mem_gib": peak_mem_gib,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "kernel_breakdown": breakdown, "encoder_layer": enc_layer, "cpu_baseline": cpu, "data_parallel": dp,
                 "variants": variants, "eager_pytorch_on_gpu": eager}
