@@ -25,6 +25,7 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); step(); e1.record(); torch.cuda.synchronize()
 print(f"unprofiled step: {e0.elapsed_time(e1):.2f} ms")
+lib.st_set_option(b"side_streams", 0)     # per-launch event intervals must not contain another stream's kernels
 lib.st_profile_reset(); lib.st_profile_enable(1); step(); torch.cuda.synchronize(); lib.st_profile_enable(0)
 os.makedirs(os.path.dirname(a.csv) or ".", exist_ok=True)
 lib.st_profile_dump(a.csv.encode())
