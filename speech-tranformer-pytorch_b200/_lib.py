@@ -210,6 +210,11 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    # ST_OPTIONS="name=value,name=value": library options (st_set_option, see csrc/st_host.cu) applied at load time
+    for kv in filter(None, os.environ.get("ST_OPTIONS", "").split(",")):
+        name, _, value = kv.partition("=")
+        if lib.st_set_option(name.strip().encode(), int(value)) != 0:
+            raise StError(f"ST_OPTIONS: {lib.st_last_error().decode()}")
     _lib = lib
     return lib
 
