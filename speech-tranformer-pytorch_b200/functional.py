@@ -209,7 +209,9 @@ def _composite_dtype(act_dtype, dk=None):
 # fp16 copy its LayerNorm kernel wrote next to it, and an fp32 gradient produced by one backward operator carries the device
 # scalar max|gradient| its last GEMM epilogue measured; the next operator finds them here and skips its conversion pass /
 # its amax pass.  A tag is honoured only for the very tensor object it was attached to and only while that tensor's version
-# counter is unchanged (an in-place edit, or autograd accumulating another gradient into it, invalidates it).
+# counter is unchanged (an in-place edit, or autograd accumulating another gradient into it, invalidates it).  Writes
+# through `tensor.data` bypass the version counter — as everywhere in PyTorch, they are invisible to such caches; use
+# ST_CHAIN=0 if a training loop edits activations that way.
 _H16_ATTR = "_st_h16"
 _AMAX_ATTR = "_st_amax"
 _CHAIN = os.environ.get("ST_CHAIN", "1") != "0"      # ST_CHAIN=0: attach no tags (A/B measurements)

@@ -228,3 +228,16 @@ def test_token_constants_match_reference():
         ns = {}
         exec(open(ref).read(), ns)
         assert {k: ns[k] for k in want} == want
+
+
+def test_st_options_environment_is_applied_at_load(lib_path):
+    """ST_OPTIONS="name=value,..." sets library options when the library is loaded; unknown names fail loudly."""
+    import subprocess
+    code = ("import speech_tranformer_pytorch_b200 as m; lib = m._lib.load(); "
+            "import ctypes; print('loaded')")
+    env = dict(os.environ, ST_OPTIONS="gemm_rows16=0,side_streams=0")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "loaded" in r.stdout, r.stderr[-500:]
+    env = dict(os.environ, ST_OPTIONS="no_such_option=1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "unknown option" in r.stderr
