@@ -65,6 +65,8 @@ struct GemmParams {
   GemmEpilogue ep;
   int flavour;   // EpiFlavour
   int rows16;    // 0 = transposing epilogue; 1 / 2 = row-layout epilogue, direct / packed-staged stores (epilogue_rows16)
+  int clc;       // CTA-pair kernel: 1 = one cluster per tile in the grid, resident clusters take over pending ones' tiles
+                 // (cluster launch control) instead of walking a static stride
 };
 
 // ---- epilogue ------------------------------------------------------------------------------------------------
@@ -635,7 +637,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // Per k-block each SM ingests 32 KB instead of 48 KB for the same MACs.
 constexpr int S2_STAGES = 6;
 constexpr int S2_STAGE_BYTES = 2 * A_STAGE_BYTES;   // A 16 KB + half of B 16 KB
-constexpr int S2_SMEM_BYTES = S2_STAGES * S2_STAGE_BYTES + EPI_BYTES + 1024 + 256;
+constexpr int S2_SMEM_BYTES = S2_STAGES * S2_STAGE_BYTES + EPI_BYTES + 1024 + 512;
+
+// ---- cluster launch control (sm_100): dynamic tile scheduling for the CTA-pair kernel.  The grid holds one cluster per
+// tile; a resident cluster, instead of exiting after its tile, CANCELS a cluster that has not been launched yet and
+// computes that cluster's tile.  Tiles are therefore dealt out as SMs become free: a pair that starts late — behind a
+// concurrent kernel of another stream (side streams, NCCL's all-reduce CTAs) — takes fewer tiles instead of holding up the
+// launch with a fixed share.  The 16-byte responses go through a 4-deep ring in shared memory, written into BOTH CTAs of
+// the pair by one multicast request of the leader's producer warp and consumed by every role that walks the tile sequence
+// (producer warps and epilogue warps of both CTAs, the leader's MMA warp: 19 arrivals per slot on the leader's barrier).
+struct ClcRing {
+  uint4 resp[4];
+  uint64_t full[4];    // response k has landed in this CTA (transaction barrier, armed by this CTA's producer warp)
+  uint64_t empty[4];   // leader's copy: every consumer of both CTAs has read the slot's previous response
+};
+constexpr int CLC_CONSUMERS = (2 + EPI_WARPS) + (1 + EPI_WARPS);
+
+__device__ __forceinline__ void clc_try_cancel_pair(void* resp, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+               ::"r"(smem_u32(resp)), "r"(smem_u32(bar)) : "memory");
+}
+// the tile fetched as number k (k = 1, 2, ...; tile 0 is the cluster's own), or -1 when no cluster was left to cancel
+__device__ __forceinline__ int clc_next(ClcRing* ring, int k, int lane) {
+  const int slot = k & 3;
+  mbar_wait(&ring->full[slot], static_cast<uint32_t>((k - 1) >> 2) & 1u);
+  uint32_t valid, x, y, z;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p1;\n\t"
+      ".reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%4];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %3, 1, 0, p1;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n\t"
+      "}"
+      : "=r"(x), "=r"(y), "=r"(z), "=r"(valid)
+      : "r"(smem_u32(&ring->resp[slot]))
+      : "memory");
+  fence_proxy_async_smem();   // this (generic-proxy) read precedes the async-proxy write of the slot's next response
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(&ring->empty[slot], 0);
+  return valid ? static_cast<int>(x >> 1) : -1;
+}
 
 template <typename T, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -655,11 +699,13 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       leader's MMA -> each CTA's epilogue
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]       both CTAs' epilogues -> leader's MMA (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  ClcRing* ring = reinterpret_cast<ClcRing*>(bars + 32);   // 256 bytes behind the barriers, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int crank = static_cast<int>(cluster_ctarank());
   const bool leader = crank == 0;
+  const bool clc = p.clc != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -671,6 +717,10 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * EPI_WARPS * 32);   // the epilogue threads of both CTAs
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&ring->full[s], 1);
+      mbar_init(&ring->empty[s], CLC_CONSUMERS);
     }
     fence_mbar_init();
   }
@@ -695,7 +745,16 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      int k = 0;
+      for (int tile = unit0; tile >= 0 && tile < num_tiles; tile = clc ? clc_next(ring, k, lane) : tile + unit_stride) {
+        ++k;   // the tile AFTER this one is number k: request it now, one tile ahead of its use
+        if (clc && elect_one()) {
+          const int slot = k & 3;
+          if (leader && k >= 5) mbar_wait(&ring->empty[slot], static_cast<uint32_t>(((k - 1) >> 2) - 1) & 1u);
+          mbar_arrive_expect_tx(&ring->full[slot], 16);
+          if (leader) clc_try_cancel_pair(&ring->resp[slot], &ring->full[slot]);
+        }
+        __syncwarp();
         const int n_blk = tile % p.n_tiles;
         const int m_blk = ((tile / p.n_tiles) % m_units) * 2 + crank;
         const int split = tile / tiles_mn;
@@ -724,7 +783,9 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      int k = 0;
+      for (int tile = unit0; tile >= 0 && tile < num_tiles; tile = clc ? clc_next(ring, k, lane) : tile + unit_stride) {
+        ++k;
         const int split = tile / tiles_mn;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
@@ -760,7 +821,9 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     float* stg = epi_smem + (warp - 2) * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+    int k = 0;
+    for (int tile = unit0; tile >= 0 && tile < num_tiles; tile = clc ? clc_next(ring, k, lane) : tile + unit_stride) {
+      ++k;
       const int n_blk = tile % p.n_tiles;
       const int m_blk = ((tile / p.n_tiles) % m_units) * 2 + crank;
       if (p.flavour == EPI_AUX_ADD || p.flavour == EPI_AUX_MASK_ROUND) prefetch_aux_tile<T, BN>(p, m_blk, n_blk, quarter, half, lane);
@@ -847,9 +910,11 @@ int launch_gemm_2sm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMa
   int cap = get_option("gemm_max_ctas");
   if (cap <= 0) cap = num_sms();
   cap = cap / 2 > 0 ? cap / 2 : 1;
-  const int grid = (units < cap ? units : cap) * 2;
+  GemmParams q = p;
+  q.clc = (get_option("gemm_clc") && units > cap) ? 1 : 0;     // more tiles than resident pairs: deal them out dynamically
+  const int grid = (q.clc ? units : (units < cap ? units : cap)) * 2;
   ProfScope prof(stream, PROF_GEMM, 2.0 * p.M * static_cast<double>(p.N) * p.K, gemm_tag<T>(p, A_MN, B_MN, 256, 3));
-  ST_TRY(launch_clustered(kern, grid, S2_SMEM_BYTES, 2, stream, ta, tb, p));
+  ST_TRY(launch_clustered(kern, grid, S2_SMEM_BYTES, 2, stream, ta, tb, q));
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -934,6 +999,7 @@ int gemm_run(cudaStream_t stream, GemmMode mode, const void* A, int64_t lda, con
   p.ep = ep;
   p.flavour = pick_flavour<T>(ep, C, ldc, p.c_lp, N);
   p.rows16 = 0;
+  p.clc = 0;
   if (E::k16 && p.c_lp && (p.flavour == EPI_PLAIN || p.flavour == EPI_RELU_DROP) && !ep.colsum && !ep.amax_out && (N & 7) == 0 &&
       (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0))
     p.rows16 = get_option("gemm_rows16");

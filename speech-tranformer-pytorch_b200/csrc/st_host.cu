@@ -42,6 +42,8 @@ Option g_options[] = {
     {"gemm_rows16", 2},   // 16-bit-output epilogues without aux: 0 = fp32 transpose through smem, 1 = row layout with direct stores,
                           // 2 = row layout, packed result staged through smem (st_gemm_impl.cuh epilogue_rows16; default:
                           // K = 512 GEMMs 8-10 % faster, bit-identical results — tools/check_rows16.py)
+    {"gemm_clc", 0},      // CTA-pair GEMM: 1 = cluster-launch-control tile scheduling (one cluster per tile, resident pairs cancel
+                          // pending ones and take their tiles) instead of a persistent grid with a static stride
     {"gemm_bn", 0},       // 0 = heuristic; 64/128/256 forces the GEMM tile width (tuning / tests)
     {"attn_trace", 0},         // 1 = dK/dV kernel CTA (0,0,0) records its pipeline timeline (st_debug_read_trace)
     {"attn_dkv_small_split", 0},   // CTAs per (batch, head) of the single-query-tile dK/dV kernel (0 = default 1)

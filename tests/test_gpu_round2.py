@@ -312,3 +312,33 @@ def test_gemm_row_layout_epilogue_is_bit_identical(stb, tdt):
                 assert relerr(outs[2].float(), ref) < (2e-3 if tdt == torch.float16 else 1e-2)
     finally:
         L.check(lib.st_set_option(b"gemm_rows16", 2))
+
+
+def test_gemm_cluster_launch_control_schedule_is_bit_identical(stb):
+    """Option gemm_clc: the CTA-pair GEMM launched with one cluster per tile, resident pairs cancelling pending clusters and
+    taking over their tiles (clusterlaunchcontrol.try_cancel, multicast into both CTAs) — same bits as the static persistent
+    schedule, for 16-bit and TF32 operands, fp32 / 16-bit outputs, residual and dropout epilogues, ragged M."""
+    L, lib = stb._lib, stb._lib.load()
+    try:
+        for tdt, DT in ((torch.float16, L.DTYPE_F16), (torch.float32, L.DTYPE_F32)):
+            for mode, M, N, K, bias, drop, c_lp, aux_mode in [(0, 41000, 512, 256, True, 0.0, 1, 0), (0, 39990, 768, 128, True, 0.1, 1, 0),
+                                                              (1, 40000, 512, 192, False, 0.0, 0, 1)]:
+                if tdt == torch.float32:
+                    c_lp = 0
+                gen = torch.Generator(device=DEV).manual_seed(M + N)
+                A = torch.randn(M, K, device=DEV, generator=gen).to(tdt)
+                B = torch.randn((N, K) if mode == 0 else (K, N), device=DEV, generator=gen).to(tdt)
+                bvec = torch.randn(N, device=DEV, generator=gen) if bias else None
+                aux = torch.randn(M, N, device=DEV, generator=gen).to(tdt) if aux_mode else None
+                ep = L.GemmEpilogue(bias=None if bvec is None else bvec.data_ptr(), aux=None if aux is None else aux.data_ptr(), ldaux=N,
+                                    aux_mode=aux_mode, relu=1 if drop else 0, round_tf32=0, k_splits=1, dropout_p=drop, seed=3)
+                outs = []
+                for opt in (0, 1):
+                    L.check(lib.st_set_option(b"gemm_clc", opt))
+                    out = torch.full((M, N), 7.0, device=DEV, dtype=tdt if c_lp else torch.float32)
+                    L.check(lib.st_gemm_dt(DT, mode, A.data_ptr(), K, B.data_ptr(), B.shape[1], out.data_ptr(), N, c_lp, M, N, K,
+                                           C.byref(ep), None))
+                    outs.append(out)
+                assert torch.equal(outs[0], outs[1]), (str(tdt), mode, M, N, K)
+    finally:
+        L.check(lib.st_set_option(b"gemm_clc", 0))
