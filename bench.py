@@ -172,6 +172,19 @@ DTYPE_DESC = {"fp32": "f32 (fp32 parameters, activations and gradients at every 
               "bf16": "bf16 (bf16 activations and tensor-core operands, fp32 accumulate / statistics / parameters / optimizer)"}
 
 
+# what the parity tests establish for each --dtype (tolerances are written in the tests; measured values: DESIGN.md section 2,
+# gpurun_out/round2_parity_errors.json / half_parity_errors.json written by the GPU tests)
+PRECISION_NOTE = {
+    "fp32": "fp32 tensors in / out of every module; fp16 operands carry TF32's 11 significant bits (tcgen05 has no fp32 MMA). "
+            "Every fp32-tolerance parity test (1e-3 per module, 3e-3 for the composed 6+6 x 512 model) runs under this engine AND "
+            "under the TF32 engine (tests/conftest.py `engine`); measured on the 6+6 x 512 model vs the float64 oracle: logits "
+            "1.07e-3, loss 8e-6, parameter gradients 2.1e-3 (TF32 engine: 1.24e-3, 5e-5, 2.2e-3)",
+    "tf32": "fp32 tensors, TF32 operands (round 1's arithmetic): 1e-3 per module, 3e-3 composed; measured 1.24e-3 / 5e-5 / 2.2e-3",
+    "fp16": "fp16 activations end to end, loss scale 2^14: 1.5e-3 per module, 3e-3 composed; measured 1.0e-3 / 7.7e-5 / 2.5e-3",
+    "bf16": "bf16 activations end to end: 2e-2 per module, 3e-2 composed (8-bit mantissa); measured 6.6e-3 / 4e-4 / 7.0e-3",
+}
+
+
 def workload_config(args, n):
     which = "configs[2]" if (args.ragged or args.dtype == "bf16") else "configs[1]"
     lens = f"T in U[200,{args.frames}] padded to {args.frames}" if args.ragged else f"T={args.frames}"
@@ -608,6 +621,7 @@ def main_b200(args):
                 "dtype": DTYPE_DESC[args.dtype], "data": "synthetic", "config": workload_config(args, n),
                 "valid_frames_per_s": valid_frames * n * args.steps / (ms * 1e-3),
                 "peak_mem_gib": peak_mem_gib,
+                "precision": PRECISION_NOTE.get(args.dtype),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "kernel_breakdown": breakdown, "encoder_layer": enc_layer, "cpu_baseline": cpu, "data_parallel": dp,
                 "variants": variants, "eager_pytorch_on_gpu": eager}
